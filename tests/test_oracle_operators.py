@@ -1,0 +1,173 @@
+"""Oracle pinned against the reference's own operator tests
+(/root/reference/test/operators.jl).  CPU only."""
+import numpy as np
+import pytest
+
+import oracle as O
+from oracle import operators as ops
+from oracle import bc, pressure, initializers
+
+
+def _setup(D, T=np.float64):
+    # test/operators.jl:1-45: n = 16, non-uniform grids, all-Dirichlet
+    n = 16
+    if D == 2:
+        x = (O.tanh_grid(0, 1, n, dtype=T), O.tanh_grid(0, 1, n, 1.3, dtype=T))
+    else:
+        x = (
+            O.tanh_grid(0, 1, n, 1.2, dtype=T),
+            O.tanh_grid(0, 1, n, 1.1, dtype=T),
+            O.cosine_grid(0, 1, n, dtype=T),
+        )
+    b = (O.DirichletBC(), O.DirichletBC())
+    setup = O.Setup(x, dict(u=(b,) * D, temp=(b,) * D))
+    return setup
+
+
+def _uref(dim, x, y, *a):
+    return -(dim == 0) * np.sin(x) * np.cos(y) + (dim == 1) * np.cos(x) * np.sin(y) + 0 * sum(a)
+
+
+def _psolver_cg(setup):
+    """Test-only stand-in for the reference's psolver_direct (out of scope for
+    the product): matrix-free CG on -L, L = laplacian! (operators.jl:320-359)."""
+    from scipy.sparse.linalg import LinearOperator, cg
+
+    Ip = setup.Ip
+    shape = tuple(s.stop - s.start for s in Ip)
+    n = int(np.prod(shape))
+
+    def mv(x):
+        p = O.scalarfield(setup)
+        p[Ip] = x.reshape(shape, order="F")
+        bc.apply_bc_p(p, 0.0, setup)
+        return -ops.laplacian_(O.scalarfield(setup), p, setup)[Ip].reshape(-1, order="F")
+
+    A = LinearOperator((n, n), matvec=mv, dtype=np.float64)
+
+    def psolve(p):
+        f = -p[Ip].reshape(-1, order="F")
+        f = f - f.mean()
+        x, info = cg(A, f, rtol=1e-15, atol=0, maxiter=20000)
+        p[Ip] = (x - x.mean()).reshape(shape, order="F")
+        return p
+
+    return psolve
+
+
+_CACHE = {}
+
+
+def _field(setup, rng):
+    # test/operators.jl:23,43: u = velocityfield(setup, uref, 0) (projected)
+    key = setup.D
+    if key not in _CACHE:
+        _CACHE[key] = initializers.velocityfield(setup, _uref, psolver=_psolver_cg(setup))
+    return _CACHE[key]
+
+
+def _w(setup, comp):
+    """Volume weights of the velocity DOFs of component comp (test/operators.jl:73-81)."""
+    D = setup.D
+    w = 1
+    for b in range(D):
+        arr = setup.DeltaU[b] if b == comp else setup.Delta[b]
+        shape = [1] * D
+        shape[b] = -1
+        w = w * arr.reshape(shape)
+    return w
+
+
+@pytest.mark.parametrize("D", [2, 3])
+def test_divergence_is_minus_gradient_transpose(D):
+    # test/operators.jl:54-84
+    setup = _setup(D)
+    rng = np.random.default_rng(0)
+    v = np.asfortranarray(rng.standard_normal(setup.N + (D,)))
+    p = np.asfortranarray(rng.standard_normal(setup.N))
+    bc.apply_bc_u(v, 0.0, setup)
+    bc.apply_bc_p(p, 0.0, setup)
+    Dv = ops.divergence_(O.scalarfield(setup), v, setup)
+    Gp = ops.pressuregradient_(O.vectorfield(setup), p, setup)
+    ODv = ops.scalewithvolume_(Dv.copy(order="F"), setup)
+    pDv = np.sum((p * ODv)[setup.Ip])
+    vGp = 0.0
+    for a in range(D):
+        vGp += np.sum((v[..., a] * _w(setup, a) * Gp[..., a])[setup.Iu[a]])
+    assert np.isclose(pDv, -vGp, rtol=1e-10)
+
+
+@pytest.mark.parametrize("D", [2, 3])
+def test_convection_skew_symmetric(D):
+    # test/operators.jl:103-124
+    setup = _setup(D)
+    u = _field(setup, None)
+    c = ops.convection_(np.zeros_like(u), u, setup)
+    uCu = 0.0
+    for a in range(D):
+        uCu += np.sum((u[..., a] * _w(setup, a) * c[..., a])[setup.Iu[a]])
+    assert abs(uCu) < 1e-12
+
+
+@pytest.mark.parametrize("D", [2, 3])
+def test_diffusion_dissipative(D):
+    # test/operators.jl:126-150
+    setup = _setup(D)
+    u = _field(setup, None)
+    d = ops.diffusion_(np.zeros_like(u), u, setup, 1e-3)
+    uDu = 0.0
+    for a in range(D):
+        uDu += np.sum((u[..., a] * _w(setup, a) * d[..., a])[setup.Iu[a]])
+    assert uDu <= 0
+
+
+@pytest.mark.parametrize("D", [2, 3])
+def test_convectiondiffusion_equals_sum(D):
+    # test/operators.jl:152-167
+    setup = _setup(D)
+    u = _field(setup, None)
+    cd = ops.convectiondiffusion_(np.zeros_like(u), u, setup, 1e-3)
+    c = ops.convection_(np.zeros_like(u), u, setup)
+    d = ops.diffusion_(np.zeros_like(u), u, setup, 1e-3)
+    assert np.allclose(cd, c + d, rtol=1e-12, atol=1e-13)
+
+
+@pytest.mark.parametrize("D", [2, 3])
+def test_laplacian_negative_and_symmetric(D):
+    # test/operators.jl:86-101 (negativity) + L = Ω D G identity used by the psolvers
+    setup = _setup(D)
+    rng = np.random.default_rng(1)
+    p = np.asfortranarray(rng.standard_normal(setup.N))
+    bc.apply_bc_p(p, 0.0, setup)
+    Lp = ops.laplacian_(O.scalarfield(setup), p, setup)
+    assert np.sum((p * Lp)[setup.Ip]) <= 0
+    # laplacian! already carries the volume factor: Lp == Ω div(grad p) on Ip
+    # when the wall-normal gradient at the walls is dropped (homogeneous Neumann).
+    G = ops.pressuregradient_(O.vectorfield(setup), p, setup)
+    bc.apply_bc_u(G, 0.0, setup)  # no-slip zeroes the wall-normal faces
+    DG = ops.scalewithvolume_(ops.divergence_(O.scalarfield(setup), G, setup), setup)
+    assert np.allclose(Lp[setup.Ip], DG[setup.Ip], rtol=1e-9, atol=1e-10)
+
+
+@pytest.mark.parametrize("D", [2, 3])
+def test_gravity_only_in_gdir_and_rhs_finite(D):
+    # test/operators.jl:169-205
+    setup = _setup(D)
+    rng = np.random.default_rng(2)
+    u = _field(setup, None)
+    temp = np.asfortranarray(rng.standard_normal(setup.N))
+    g = ops.applygravity_(np.zeros_like(u), temp, setup, 1, 1.0)
+    for a in range(D):
+        if a != 1:
+            assert np.all(g[..., a] == 0)
+    assert np.any(g[..., 1] != 0)
+    f = dict(u=np.zeros_like(u), temp=np.zeros_like(temp))
+    ops.boussinesq_(f, dict(u=u, temp=temp), 0.0, setup, 1e-3, 1e-3, 1, 1.0, True)
+    assert np.all(np.isfinite(f["u"])) and np.all(np.isfinite(f["temp"]))
+
+
+def test_grids():
+    # test/grid.jl: endpoints and monotonicity
+    for g in (O.cosine_grid(0.0, 2.0, 10), O.tanh_grid(0.0, 2.0, 10, 1.4), O.stretched_grid(0.0, 2.0, 10, 1.1)):
+        assert np.isclose(g[0], 0) and np.isclose(g[-1], 2)
+        assert np.all(np.diff(g) > 0)
