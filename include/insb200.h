@@ -1,0 +1,177 @@
+/* insb200.h -- C ABI of libinsb200.so, the B200 (sm_100a) backend for the
+ * per-time-step hot path of IncompressibleNavierStokes.jl v5.0.1.
+ *
+ * Every entry point names the reference interface it replaces (paths relative
+ * to the reference checkout).  A Julia package extension binds these with
+ * `ccall`; the Python/ctypes harness in
+ * incompressiblenavierstokes.jl_b200/insb200/ binds the very same symbols.
+ *
+ * Conventions
+ *  - All field pointers are DEVICE pointers owned by the caller, laid out exactly
+ *    like the reference's arrays: column-major, one ghost volume per side,
+ *    scalar `N[0] x N[1] (x N[2])`, vector `N... x D` with the component as the
+ *    slowest index (src/initializers.jl:2,5; src/grid.jl:101-112).
+ *  - `stream` is a `cudaStream_t` passed as `void*`.  Calls enqueue work and
+ *    return without synchronising, except where stated.
+ *  - Return value: 0 on success, non-zero on failure; `insb200_last_error()`
+ *    then returns a message.  No C++ exception crosses this boundary.
+ *  - A plan is not re-entrant; distinct plans may be used from distinct threads.
+ *  - There is NO CPU fallback: every function fails if no CUDA device is present.
+ */
+#ifndef INSB200_H
+#define INSB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define INSB200_VERSION 100 /* 0.1.0 */
+
+enum { INSB200_F32 = 0, INSB200_F64 = 1 };
+
+/* src/boundary_conditions.jl:5-39 */
+enum {
+    INSB200_BC_PERIODIC = 0,
+    INSB200_BC_DIRICHLET = 1,
+    INSB200_BC_SYMMETRIC = 2,
+    INSB200_BC_PRESSURE = 3
+};
+
+/* src/pressure.jl: psolver_spectral :321, psolver_transform :215, psolver_tridiagonal :401 */
+enum {
+    INSB200_PSOLVER_NONE = -1,
+    INSB200_PSOLVER_SPECTRAL = 0,
+    INSB200_PSOLVER_TRANSFORM = 1,
+    INSB200_PSOLVER_TRIDIAGONAL = 2,
+    INSB200_PSOLVER_DEFAULT = 3 /* default_psolver, src/pressure.jl:58-78 */
+};
+
+/* The subset of the `Setup` NamedTuple (src/grid.jl:91-208) the hot path consumes.
+ * The 1-D metric tables are DATA computed by the caller exactly as the reference
+ * does; the library never re-derives grid spacings. */
+typedef struct insb200_setup {
+    int D;              /* 2 or 3 */
+    int N[3];           /* volumes per dim INCLUDING ghosts (setup.N) */
+    int dtype;          /* INSB200_F32 / INSB200_F64 = eltype(x[1]) */
+    int bc_u[3][2];     /* boundary_conditions.u[dim][left/right] */
+    int has_temp;       /* boundary_conditions has a `temp` entry */
+    int bc_temp[3][2];  /* boundary_conditions.temp[dim][left/right] */
+    /* HOST pointers to 1-D tables of length N[dim], element type `dtype`:
+     * setup.Δ, setup.Δu, setup.A_stag[dim][1], setup.A_stag[dim][2] */
+    const void *Delta[3];
+    const void *DeltaU[3];
+    const void *A1[3];
+    const void *A2[3];
+    double xlims[3][2];             /* setup.xlims (psolver_transform uses it, pressure.jl:221-223) */
+    double bc_u_value[3][2][3];     /* DirichletBC constants [dim][side][component]; 0 = no-slip */
+    double bc_temp_value[3][2];     /* DirichletBC temperature constants [dim][side] */
+    int psolver;                    /* INSB200_PSOLVER_* */
+    int tridiagonal_dir;            /* wall-normal dir for psolver_tridiagonal, -1 = infer (pressure.jl:410-416) */
+    /* Optional HOST eigenvalue tables (`ahat`, pressure.jl:234-246,336-342; `lam`, :453-460),
+     * element type `dtype`; NULL = computed by the library the way the reference does. */
+    const void *eig[3];
+    int device;                     /* CUDA device ordinal, -1 = current device */
+    /* z-slab decomposition (one process per GPU). world == 1 for a single GPU. */
+    int rank, world;
+} insb200_setup_t;
+
+/* `params` NamedTuple forwarded to force! (src/solver.jl:2-35,176) */
+typedef struct insb200_params {
+    double viscosity;
+    double conductivity;
+    double gravity;
+    int gdir;           /* 0-based */
+    int dodissipation;
+    int boussinesq;     /* 0: navierstokes! (solver.jl:2-6); 1: boussinesq! (solver.jl:16-35) */
+    double bodyforce[3];/* constant body force added to k.u (examples/ChannelFlow.jl:172-176); 0 = none */
+} insb200_params_t;
+
+typedef struct insb200_plan insb200_plan_t;
+
+const char *insb200_last_error(void);
+int insb200_version(void);
+
+/* Plan = device copies of the Setup tables + psolver workspace (replaces the closures
+ * built by psolver_spectral/transform/tridiagonal, pressure.jl:344-347,248-253,469-476)
+ * + time-stepper caches (get_cache, time_steppers/time_stepper_caches.jl:11-24). */
+int insb200_plan_create(const insb200_setup_t *setup, insb200_plan_t **out);
+int insb200_plan_destroy(insb200_plan_t *plan);
+/* Which psolver the plan holds (default_psolver resolved), and bytes of device workspace. */
+int insb200_plan_psolver(const insb200_plan_t *plan);
+long long insb200_plan_workspace_bytes(const insb200_plan_t *plan);
+
+/* apply_bc_u! / apply_bc_p! / apply_bc_temp! (src/boundary_conditions.jl:163-171,200-208,237-245).
+ * dudt != 0 selects the `dudt = true` variant (:341-357). */
+int insb200_apply_bc_u(insb200_plan_t *plan, void *u, double t, int dudt, void *stream);
+int insb200_apply_bc_p(insb200_plan_t *plan, void *p, void *stream);
+int insb200_apply_bc_temp(insb200_plan_t *plan, void *temp, double t, void *stream);
+
+/* Time-dependent (function-valued) DirichletBC, src/boundary_conditions.jl:344-357: the host
+ * evaluates the function on the plane coordinates and hands the plane (device pointer, full
+ * extent of the other dims, column-major) for (dim, side, component); NULL restores the constant. */
+int insb200_set_bc_u_plane(insb200_plan_t *plan, int dim, int side, int comp, const void *plane);
+
+/* navierstokes! / boussinesq! (src/solver.jl:2-35): k.u (and k.temp) are OVERWRITTEN on
+ * 2:N-1 and zeroed elsewhere, like fill!(k,0) followed by convectiondiffusion!
+ * (src/operators.jl:616-628) [+ applygravity! :802, convection_diffusion_temp! :669, dissipation! :772]. */
+int insb200_rhs(insb200_plan_t *plan, const void *u, const void *temp, void *ku, void *ktemp,
+                const insb200_params_t *params, void *stream);
+/* convection! / diffusion! (src/operators.jl:407-416,545-554): ADD to f like the reference. */
+int insb200_convection(insb200_plan_t *plan, void *f, const void *u, void *stream);
+int insb200_diffusion(insb200_plan_t *plan, void *f, const void *u, double viscosity, void *stream);
+
+/* divergence! (src/operators.jl:242-247); scalewithvolume! (:218-231);
+ * pressuregradient! (:277-280); applypressure! (:306-311). */
+int insb200_divergence(insb200_plan_t *plan, void *div, const void *u, void *stream);
+int insb200_scalewithvolume(insb200_plan_t *plan, void *p, void *stream);
+int insb200_pressuregradient(insb200_plan_t *plan, void *G, const void *p, void *stream);
+int insb200_applypressure(insb200_plan_t *plan, void *u, const void *p, void *stream);
+
+/* poisson!(psolver, p) = psolver(p) (src/pressure.jl:22): in place on the ghosted array,
+ * touches only view(p, Ip) (pressure.jl:349-381, 255-317, 507-544). */
+int insb200_psolve(insb200_plan_t *plan, void *p, void *stream);
+/* project!(u, setup; psolver, p) (src/pressure.jl:42-55). p is caller scratch (ghosted scalar). */
+int insb200_project(insb200_plan_t *plan, void *u, void *p, void *stream);
+
+/* timestep!(::ExplicitRungeKuttaMethod, ...) (src/time_steppers/step_explicit_runge_kutta.jl:4-57).
+ * A: s*s row-major SHIFTED tableau (methods.jl:80-85), c: s stage times, both as double;
+ * coef_dtype = eltype of the method (INSB200_F32/F64): the stage combine is evaluated in
+ * promote(field dtype, coef_dtype) like the reference broadcast (:28-32).
+ * u (and temp) are advanced in place from t to t + dt. */
+int insb200_step_rk(insb200_plan_t *plan, const double *A, const double *c, int s, int coef_dtype,
+                    void *u, void *temp, double t, double dt, const insb200_params_t *params,
+                    void *stream);
+/* timestep!(::LMWray3, ...) (src/time_steppers/step_lmwray3.jl:3-94). */
+int insb200_step_lmwray3(insb200_plan_t *plan, void *u, void *temp, double t, double dt,
+                         const insb200_params_t *params, void *stream);
+/* Same as insb200_step_rk but with HOST buffers: H2D copy of u (and temp), nsteps steps,
+ * D2H copy back, stream-synchronised on return (reference callers holding `Array`s). */
+int insb200_step_rk_host(insb200_plan_t *plan, const double *A, const double *c, int s,
+                         int coef_dtype, void *u_host, void *temp_host, double t, double dt,
+                         int nsteps, const insb200_params_t *params, void *stream);
+
+/* right_hand_side!(dudt, u, params_ref, t) (src/sciml.jl:35-48). */
+int insb200_right_hand_side(insb200_plan_t *plan, void *dudt, const void *u, double t,
+                            const insb200_params_t *params, void *stream);
+
+/* propose_timestep(force!, state, setup, params) (src/solver.jl:157-214). Synchronises the
+ * stream and returns the proposed dt (WITHOUT the cfl factor) in *dt_out. */
+int insb200_cfl(insb200_plan_t *plan, const void *u, const insb200_params_t *params,
+                double *dt_out, void *stream);
+/* maximum(abs, u) over the whole vector field (timelogger, src/processors.jl:75); syncs. */
+int insb200_maxabs(insb200_plan_t *plan, const void *u, double *out, void *stream);
+
+/* Number of kernel launches issued by this plan since creation (bench.py `gpu_launches`). */
+long long insb200_launch_count(const insb200_plan_t *plan);
+
+/* Device-timed kernel groups for roofline accounting: when enabled, CUDA events bracket the
+ * stencil (A), Poisson (P) and projection (C) groups of every stage on `stream`. */
+int insb200_profile_enable(insb200_plan_t *plan, int on);
+/* ms accumulated per group [0]=rhs+combine, [1]=divergence, [2]=poisson, [3]=project, [4]=bc;
+ * counts = number of brackets; resets the accumulators. Synchronises. */
+int insb200_profile_read(insb200_plan_t *plan, double ms[5], long long counts[5]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INSB200_H */

@@ -1,0 +1,868 @@
+// api.cu -- plan management, time-step orchestration and the extern "C" surface of
+// libinsb200.so (declared in include/insb200.h).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+#include "internal.h"
+
+namespace insb {
+
+static thread_local std::string g_err;
+void set_error(const std::string &msg) { g_err = msg; }
+
+}  // namespace insb
+
+using namespace insb;
+
+struct insb200_plan {
+    insb200_setup_t s;
+    bool f64 = false;
+    size_t esz = 4;
+    int D = 3;
+    int dev = 0;
+    long long ncell = 0;
+    int Ip[3][2];
+    int Iu[3][3][2];  // [comp][dim][lo/hi)
+    std::vector<std::vector<unsigned char>> host_tables;  // keeps copies of the caller's tables
+    void *dev_tables = nullptr;
+    Grid<float> gf;
+    Grid<double> gd;
+    BcDesc bc;
+    Poisson *ps = nullptr;
+    int psolver = INSB200_PSOLVER_NONE;
+    // work buffers (device): two stage buffers and the accumulator for u (and temp), p scratch,
+    // lazily allocated k storage for general tableaus
+    void *V[2] = {nullptr, nullptr}, *ACC = nullptr, *P = nullptr;
+    void *TV[2] = {nullptr, nullptr}, *TACC = nullptr;
+    std::vector<void *> K, TK;
+    void *HU = nullptr, *HT = nullptr;  // device state of the host-buffer entry point
+    double *scratch = nullptr;  // reductions
+    long long bytes = 0;
+    long long launches = 0;
+    // diffusive / thermal step limits (host, from the tables)
+    double dmin_u[3], dmin_p[3];
+    // profiling
+    bool prof = false;
+    cudaEvent_t ev[6];
+    double prof_ms[5] = {0, 0, 0, 0, 0};
+    long long prof_cnt[5] = {0, 0, 0, 0, 0};
+    struct Bracket {
+        cudaEvent_t a, b;
+        int group;
+    };
+    std::vector<Bracket> brackets;
+    std::vector<cudaEvent_t> evpool;
+};
+
+namespace {
+
+int offset_u(int bc, bool isright, bool isnormal) {
+    switch (bc) {
+        case INSB200_BC_PERIODIC: return 1;
+        case INSB200_BC_DIRICHLET:
+        case INSB200_BC_SYMMETRIC: return 1 + (isright && isnormal ? 1 : 0);
+        default: return 1 + (!isright && !isnormal ? 1 : 0);
+    }
+}
+int offset_p(int bc, bool isright) { return bc == INSB200_BC_PRESSURE ? 1 + (!isright ? 1 : 0) : 1; }
+
+template <typename T>
+int build_grid(insb200_plan *pl, Grid<T> &g) {
+    const insb200_setup_t &s = pl->s;
+    const int D = s.D;
+    g.D = D;
+    size_t total = 0;
+    for (int a = 0; a < 3; a++) {
+        g.N[a] = a < D ? s.N[a] : 1;
+        total += a < D ? (size_t)s.N[a] : 0;
+    }
+    g.s[0] = 1;
+    g.s[1] = g.N[0];
+    g.s[2] = (long long)g.N[0] * g.N[1];
+    g.cs = (long long)g.N[0] * g.N[1] * g.N[2];
+    const int NT = 10;
+    std::vector<T> h(total * NT);
+    const T eps = std::is_same<T, float>::value ? (T)1.1920929e-07f : (T)2.220446049250313e-16;
+    const T tol = 2 * eps;
+    size_t off = 0;
+    std::vector<size_t> offs(D);
+    for (int a = 0; a < D; a++) {
+        int n = s.N[a];
+        offs[a] = off;
+        const T *dl = (const T *)s.Delta[a], *du = (const T *)s.DeltaU[a];
+        const T *a1 = (const T *)s.A1[a], *a2 = (const T *)s.A2[a];
+        for (int i = 0; i < n; i++) {
+            T *row = h.data() + off * NT;
+            row[0 * n + i] = dl[i];
+            row[1 * n + i] = du[i];
+            row[2 * n + i] = T(1) / dl[i];
+            row[3 * n + i] = T(1) / du[i];
+            row[4 * n + i] = dl[i] > tol ? T(1) / dl[i] : T(0);
+            row[5 * n + i] = du[i] > tol ? T(1) / du[i] : T(0);
+            row[6 * n + i] = a1[i];
+            row[7 * n + i] = a2[i];
+            if (i + 1 < n) {
+                row[8 * n + i] = dl[i + 1] / (dl[i] + dl[i + 1]);
+                row[9 * n + i] = dl[i] / (dl[i] + dl[i + 1]);
+            } else {
+                row[8 * n + i] = T(0.5);
+                row[9 * n + i] = T(0.5);
+            }
+        }
+        off += n;
+    }
+    INSB_CUDA(cudaMalloc(&pl->dev_tables, h.size() * sizeof(T)));
+    INSB_CUDA(cudaMemcpy(pl->dev_tables, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    pl->bytes += (long long)(h.size() * sizeof(T));
+    const T *base = (const T *)pl->dev_tables;
+    for (int a = 0; a < 3; a++) {
+        int aa = a < D ? a : 0;
+        int n = s.N[aa];
+        const T *row = base + offs[aa] * NT;
+        g.dl[a] = row + 0 * n;
+        g.du[a] = row + 1 * n;
+        g.rdl[a] = row + 2 * n;
+        g.rdu[a] = row + 3 * n;
+        g.rdlg[a] = row + 4 * n;
+        g.rdug[a] = row + 5 * n;
+        g.a1[a] = row + 6 * n;
+        g.a2[a] = row + 7 * n;
+        g.wa[a] = row + 8 * n;
+        g.wb[a] = row + 9 * n;
+    }
+    // step limits (solver.jl:157-166, :188-197)
+    for (int a = 0; a < D; a++) {
+        const T *dl = (const T *)s.Delta[a], *du = (const T *)s.DeltaU[a];
+        T mu = du[pl->Iu[a][a][0]], mp = dl[pl->Ip[a][0]];
+        for (int i = pl->Iu[a][a][0]; i < pl->Iu[a][a][1]; i++) mu = std::min(mu, du[i]);
+        for (int i = pl->Ip[a][0]; i < pl->Ip[a][1]; i++) mp = std::min(mp, dl[i]);
+        pl->dmin_u[a] = (double)mu;
+        pl->dmin_p[a] = (double)mp;
+    }
+    return 0;
+}
+
+int dev_alloc(insb200_plan *pl, void **p, size_t bytes) {
+    INSB_CUDA(cudaMalloc(p, bytes));
+    INSB_CUDA(cudaMemset(*p, 0, bytes));
+    pl->bytes += (long long)bytes;
+    return 0;
+}
+
+int resolve_default_psolver(const insb200_plan *pl) {
+    // default_psolver (src/pressure.jl:58-78)
+    const insb200_setup_t &s = pl->s;
+    const int D = s.D;
+    bool isper[3], iswall[3], isuni[3];
+    for (int a = 0; a < D; a++) {
+        isper[a] = s.bc_u[a][0] == INSB200_BC_PERIODIC && s.bc_u[a][1] == INSB200_BC_PERIODIC;
+        iswall[a] = s.bc_u[a][0] == INSB200_BC_DIRICHLET && s.bc_u[a][1] == INSB200_BC_DIRICHLET;
+        double tol = std::sqrt(pl->f64 ? 2.220446049250313e-16 : 1.1920929e-07);
+        auto get = [&](int i) {
+            return pl->f64 ? ((const double *)s.Delta[a])[i] : (double)((const float *)s.Delta[a])[i];
+        };
+        double ref = get(pl->Ip[a][0]);
+        isuni[a] = true;
+        for (int i = pl->Ip[a][0]; i < pl->Ip[a][1]; i++)
+            if (std::fabs(get(i) - ref) > tol * std::fmax(std::fabs(get(i)), std::fabs(ref))) isuni[a] = false;
+    }
+    bool allper = true;
+    for (int a = 0; a < D; a++) allper = allper && isper[a] && isuni[a];
+    if (allper) return INSB200_PSOLVER_SPECTRAL;
+    for (int a = 0; a < D; a++) {
+        bool ch = iswall[a];
+        for (int b = 0; b < D; b++) ch = ch && (b == a || (isper[b] && isuni[b]));
+        if (ch) return INSB200_PSOLVER_TRIDIAGONAL;
+    }
+    return INSB200_PSOLVER_NONE;  // psolver_direct is outside the hot path
+}
+
+Launch L_of(insb200_plan *pl, void *stream) { return Launch{(cudaStream_t)stream, &pl->launches}; }
+
+// ---- profiling brackets -------------------------------------------------------------
+struct Scope {
+    insb200_plan *pl;
+    cudaStream_t st;
+    int group;
+    cudaEvent_t a = nullptr, b = nullptr;
+    Scope(insb200_plan *p, cudaStream_t s, int g) : pl(p), st(s), group(g) {
+        if (!pl->prof) return;
+        auto get = [&]() {
+            cudaEvent_t e;
+            if (!pl->evpool.empty()) {
+                e = pl->evpool.back();
+                pl->evpool.pop_back();
+            } else
+                cudaEventCreate(&e);
+            return e;
+        };
+        a = get();
+        b = get();
+        cudaEventRecord(a, st);
+    }
+    ~Scope() {
+        if (!pl->prof) return;
+        cudaEventRecord(b, st);
+        pl->brackets.push_back({a, b, group});
+    }
+};
+
+template <typename T>
+const Grid<T> &grid_of(const insb200_plan *pl);
+template <>
+const Grid<float> &grid_of<float>(const insb200_plan *pl) { return pl->gf; }
+template <>
+const Grid<double> &grid_of<double>(const insb200_plan *pl) { return pl->gd; }
+
+template <typename T>
+int project_t(insb200_plan *pl, T *u, T *p, void *stream) {
+    // project! (src/pressure.jl:42-55)
+    const Grid<T> &g = grid_of<T>(pl);
+    Launch L = L_of(pl, stream);
+    if (!pl->ps) {
+        set_error("this plan has no Poisson solver (psolver = NONE / unsupported BC combination)");
+        return 1;
+    }
+    {
+        Scope sc(pl, L.stream, 1);
+        INSB_TRY(launch_divergence<T>(g, u, p, true, L));
+    }
+    {
+        Scope sc(pl, L.stream, 2);
+        INSB_TRY(poisson_solve(pl->ps, p, L));
+    }
+    {
+        Scope sc(pl, L.stream, 4);
+        INSB_TRY(launch_bc_p<T>(g, pl->bc, p, L));
+    }
+    {
+        Scope sc(pl, L.stream, 3);
+        INSB_TRY(launch_pressuregradient<T>(g, p, (T *)nullptr, u, L));
+    }
+    return 0;
+}
+
+template <typename T>
+void fill_params(StageArgs<T> &a, const insb200_params_t *pr, const insb200_plan *pl) {
+    a.nu = pr->viscosity;
+    a.kappa = pr->conductivity;
+    a.grav = pr->gravity;
+    a.gdir = pr->gdir;
+    a.dodiss = pr->dodissipation;
+    a.bouss = pr->boussinesq;
+    for (int c = 0; c < 3; c++) a.bodyforce[c] = pr->bodyforce[c];
+    a.conv = 1;
+    a.diff = 1;
+    a.add_to_k = 0;
+    a.zero_outside = 0;
+}
+
+int ensure_work(insb200_plan *pl, bool temp) {
+    size_t vb = (size_t)pl->ncell * pl->D * pl->esz, sb = (size_t)pl->ncell * pl->esz;
+    if (!pl->V[0]) {
+        INSB_TRY(dev_alloc(pl, &pl->V[0], vb));
+        INSB_TRY(dev_alloc(pl, &pl->V[1], vb));
+        INSB_TRY(dev_alloc(pl, &pl->ACC, vb));
+        INSB_TRY(dev_alloc(pl, &pl->P, sb));
+    }
+    if (temp && !pl->TV[0]) {
+        INSB_TRY(dev_alloc(pl, &pl->TV[0], sb));
+        INSB_TRY(dev_alloc(pl, &pl->TV[1], sb));
+        INSB_TRY(dev_alloc(pl, &pl->TACC, sb));
+    }
+    return 0;
+}
+
+int ensure_k(insb200_plan *pl, int count, bool temp) {
+    size_t vb = (size_t)pl->ncell * pl->D * pl->esz, sb = (size_t)pl->ncell * pl->esz;
+    while ((int)pl->K.size() < count) {
+        void *p;
+        INSB_TRY(dev_alloc(pl, &p, vb));
+        pl->K.push_back(p);
+    }
+    while (temp && (int)pl->TK.size() < count) {
+        void *p;
+        INSB_TRY(dev_alloc(pl, &p, sb));
+        pl->TK.push_back(p);
+    }
+    return 0;
+}
+
+// One projected stage: v (already combined, interior only) -> BC, project, BC (+ temp BC).
+template <typename T>
+int finish_stage(insb200_plan *pl, T *v, T *tv, double t, void *stream) {
+    const Grid<T> &g = grid_of<T>(pl);
+    Launch L = L_of(pl, stream);
+    {
+        Scope sc(pl, L.stream, 4);
+        INSB_TRY(launch_bc_u<T>(g, pl->bc, v, 0, L));
+    }
+    INSB_TRY(project_t<T>(pl, v, (T *)pl->P, stream));
+    {
+        Scope sc(pl, L.stream, 4);
+        INSB_TRY(launch_bc_u<T>(g, pl->bc, v, 0, L));
+        if (tv) INSB_TRY(launch_bc_temp<T>(g, pl->bc, tv, L));
+    }
+    (void)t;
+    return 0;
+}
+
+// timestep!(::ExplicitRungeKuttaMethod) -- step_explicit_runge_kutta.jl:4-57
+template <typename T>
+int step_rk_t(insb200_plan *pl, const double *A, const double *c, int s, int coef_dtype, T *U, T *TU,
+              double t, double dt, const insb200_params_t *pr, void *stream) {
+    if (s < 1 || s > MAXSTAGE) {
+        set_error("number of stages must be in 1..8");
+        return 1;
+    }
+    const bool bouss = pr->boussinesq != 0;
+    if (bouss && !TU) {
+        set_error("boussinesq forcing needs a temperature field");
+        return 1;
+    }
+    INSB_TRY(ensure_work(pl, bouss));
+    const Grid<T> &g = grid_of<T>(pl);
+    Launch L = L_of(pl, stream);
+    const bool ct_double = pl->f64 || coef_dtype == INSB200_F64;
+    // Δt * A[i,j] evaluated in the coefficient type (see include/insb200.h)
+    auto coef = [&](int i, int j) -> double {
+        if (coef_dtype == INSB200_F32) return (double)((float)dt * (float)A[i * s + j]);
+        return dt * A[i * s + j];
+    };
+    // "fast" tableau: rows 0..s-2 only use their own stage; the last row is accumulated on the fly
+    bool fast = true;
+    for (int i = 0; i < s - 1; i++)
+        for (int j = 0; j < i; j++) fast = fast && A[i * s + j] == 0.0;
+    if (!fast) INSB_TRY(ensure_k(pl, s - 1, bouss));
+    size_t vb = (size_t)pl->ncell * pl->D * pl->esz, sb = (size_t)pl->ncell * pl->esz;
+
+    const T *src = U;
+    const T *tsrc = TU;
+    for (int i = 0; i < s; i++) {
+        const bool last = i == s - 1;
+        T *dst = (last && s > 1) ? U : (T *)pl->V[i & 1];
+        T *tdst = bouss ? ((last && s > 1) ? TU : (T *)pl->TV[i & 1]) : nullptr;
+        StageArgs<T> a{};
+        fill_params(a, pr, pl);
+        a.u = src;
+        a.temp = bouss ? tsrc : nullptr;
+        a.v = dst;
+        a.tv = tdst;
+        a.cv = coef(i, i);
+        if (fast) {
+            if (last && s > 1) {
+                a.vbase = (const T *)pl->ACC;
+                a.tvbase = (const T *)pl->TACC;
+            } else {
+                a.vbase = U;
+                a.tvbase = TU;
+                if (s > 1) {
+                    a.acc_in = i == 0 ? U : (const T *)pl->ACC;
+                    a.acc_out = (T *)pl->ACC;
+                    a.tacc_in = i == 0 ? TU : (const T *)pl->TACC;
+                    a.tacc_out = bouss ? (T *)pl->TACC : nullptr;
+                    a.ca = coef(s - 1, i);
+                }
+            }
+        } else {
+            a.vbase = U;
+            a.tvbase = TU;
+            a.nprev = i;
+            for (int j = 0; j < i; j++) {
+                a.kprev[j] = (const T *)pl->K[j];
+                a.tkprev[j] = bouss ? (const T *)pl->TK[j] : nullptr;
+                a.cprev[j] = coef(i, j);
+            }
+            if (!last) {
+                a.k_out = (T *)pl->K[i];
+                a.tk_out = bouss ? (T *)pl->TK[i] : nullptr;
+            }
+        }
+        {
+            Scope sc(pl, L.stream, 0);
+            INSB_TRY(launch_stage<T>(g, a, ct_double, L));
+        }
+        double ti = t + c[i] * dt;
+        INSB_TRY(finish_stage<T>(pl, dst, tdst, ti, stream));
+        src = dst;
+        tsrc = tdst;
+    }
+    if (s == 1) {  // single-stage methods wrote into V[0]
+        INSB_CUDA(cudaMemcpyAsync(U, pl->V[0], vb, cudaMemcpyDeviceToDevice, L.stream));
+        if (bouss) INSB_CUDA(cudaMemcpyAsync(TU, pl->TV[0], sb, cudaMemcpyDeviceToDevice, L.stream));
+    }
+    return 0;
+}
+
+// timestep!(::LMWray3) -- step_lmwray3.jl:3-94
+template <typename T>
+int step_wray_t(insb200_plan *pl, T *U, T *TU, double t, double dt, const insb200_params_t *pr,
+                void *stream) {
+    const bool bouss = pr->boussinesq != 0;
+    if (bouss && !TU) {
+        set_error("boussinesq forcing needs a temperature field");
+        return 1;
+    }
+    INSB_TRY(ensure_work(pl, bouss));
+    const Grid<T> &g = grid_of<T>(pl);
+    Launch L = L_of(pl, stream);
+    // coefficients in the field type (step_lmwray3.jl:60-62); axpy! converts the scalar to T
+    const T a3[3] = {(T)(8.0 / 15.0), (T)(5.0 / 12.0), (T)(3.0 / 4.0)};
+    const T b3[2] = {(T)(1.0 / 4.0), (T)0};
+    const T c3[3] = {(T)(8.0 / 15.0), (T)(2.0 / 3.0), (T)1};
+    const T *src = U;
+    const T *tsrc = TU;
+    for (int i = 0; i < 3; i++) {
+        const bool last = i == 2;
+        T *dst = last ? U : (T *)pl->V[i & 1];
+        T *tdst = bouss ? (last ? TU : (T *)pl->TV[i & 1]) : nullptr;
+        StageArgs<T> a{};
+        fill_params(a, pr, pl);
+        a.u = src;
+        a.temp = bouss ? tsrc : nullptr;
+        a.v = dst;
+        a.tv = tdst;
+        a.cv = (double)(T)((double)a3[i] * dt);
+        a.vbase = i == 0 ? U : (const T *)pl->ACC;
+        a.tvbase = i == 0 ? TU : (const T *)pl->TACC;
+        if (i == 0) {  // statestart += b[0] Δt k ; (b[1] = 0 leaves it unchanged)
+            a.acc_in = U;
+            a.acc_out = (T *)pl->ACC;
+            a.tacc_in = TU;
+            a.tacc_out = bouss ? (T *)pl->TACC : nullptr;
+            a.ca = (double)(T)((double)b3[0] * dt);
+        }
+        {
+            Scope sc(pl, L.stream, 0);
+            INSB_TRY(launch_stage<T>(g, a, pl->f64, L));
+        }
+        double ti = t + (double)c3[i] * dt;
+        INSB_TRY(finish_stage<T>(pl, dst, tdst, ti, stream));
+        src = dst;
+        tsrc = tdst;
+    }
+    // the trailing apply_bc_u!/apply_bc_temp! at t + Δt (:90-91) repeats the fills above for
+    // constant-in-time BCs; function-valued BCs are refreshed by the host through
+    // insb200_set_bc_u_plane + insb200_apply_bc_u.
+    return 0;
+}
+
+template <typename T>
+static int rhs_t(insb200_plan *pl, const T *u, const T *temp, T *ku, T *ktemp, const insb200_params_t *pr,
+                 int conv, int diff, int add, void *stream) {
+    StageArgs<T> a{};
+    fill_params(a, pr, pl);
+    a.u = u;
+    a.temp = pr->boussinesq ? temp : nullptr;
+    a.k_out = ku;
+    a.tk_out = pr->boussinesq ? ktemp : nullptr;
+    a.zero_outside = add ? 0 : 1;
+    a.add_to_k = add;
+    a.conv = conv;
+    a.diff = diff;
+    Scope sc(pl, (cudaStream_t)stream, 0);
+    return launch_stage<T>(grid_of<T>(pl), a, pl->f64, L_of(pl, stream));
+}
+
+template <typename T>
+static int rhs_sciml_t(insb200_plan *pl, T *dudt, const T *u, double t, const insb200_params_t *pr,
+                       void *stream) {
+    // right_hand_side! (src/sciml.jl:35-48)
+    INSB_TRY(ensure_work(pl, false));
+    const Grid<T> &g = grid_of<T>(pl);
+    Launch L = L_of(pl, stream);
+    size_t vb = (size_t)pl->ncell * pl->D * pl->esz;
+    T *tmp = (T *)pl->V[0];
+    INSB_CUDA(cudaMemcpyAsync(tmp, u, vb, cudaMemcpyDeviceToDevice, L.stream));
+    INSB_TRY(launch_bc_u<T>(g, pl->bc, tmp, 0, L));
+    insb200_params_t p2 = *pr;
+    p2.boussinesq = 0;
+    INSB_TRY(rhs_t<T>(pl, tmp, nullptr, dudt, nullptr, &p2, 1, 1, 0, stream));
+    INSB_TRY(launch_bc_u<T>(g, pl->bc, dudt, 1, L));
+    INSB_TRY(project_t<T>(pl, dudt, (T *)pl->P, stream));
+    (void)t;
+    return 0;
+}
+
+}  // namespace
+
+// =========================================================================================
+// extern "C"
+// =========================================================================================
+#define API_BEGIN try {
+#define API_END                                        \
+    }                                                  \
+    catch (const std::exception &e) {                  \
+        insb::set_error(std::string("exception: ") + e.what()); \
+        return 1;                                      \
+    }                                                  \
+    catch (...) {                                      \
+        insb::set_error("unknown exception");          \
+        return 1;                                      \
+    }
+
+extern "C" {
+
+const char *insb200_last_error(void) { return insb::g_err.c_str(); }
+int insb200_version(void) { return INSB200_VERSION; }
+
+int insb200_plan_create(const insb200_setup_t *setup, insb200_plan_t **out) {
+    API_BEGIN
+    if (!setup || !out) {
+        set_error("null argument");
+        return 1;
+    }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_error("no CUDA device: libinsb200 has no CPU fallback");
+        return 1;
+    }
+    const insb200_setup_t &s = *setup;
+    if (s.D != 2 && s.D != 3) {
+        set_error("D must be 2 or 3");
+        return 1;
+    }
+    if (s.dtype != INSB200_F32 && s.dtype != INSB200_F64) {
+        set_error("dtype must be INSB200_F32 or INSB200_F64");
+        return 1;
+    }
+    for (int a = 0; a < s.D; a++) {
+        if (s.N[a] < 4) {
+            set_error("N[a] must be >= 4");
+            return 1;
+        }
+        if (!s.Delta[a] || !s.DeltaU[a] || !s.A1[a] || !s.A2[a]) {
+            set_error("metric tables must be given");
+            return 1;
+        }
+        bool perl = s.bc_u[a][0] == INSB200_BC_PERIODIC, perr = s.bc_u[a][1] == INSB200_BC_PERIODIC;
+        if (perl != perr) {
+            set_error("Periodic boundary conditions must be periodic on both sides");
+            return 1;
+        }
+    }
+    if (s.world > 1) {
+        set_error("multi-GPU slab decomposition is not available in this build");
+        return 1;
+    }
+    insb200_plan *pl = new insb200_plan();
+    pl->s = s;
+    pl->f64 = s.dtype == INSB200_F64;
+    pl->esz = pl->f64 ? 8 : 4;
+    pl->D = s.D;
+    if (s.device >= 0) INSB_CUDA(cudaSetDevice(s.device));
+    INSB_CUDA(cudaGetDevice(&pl->dev));
+    // keep private copies of the caller's tables
+    pl->host_tables.resize(4 * 3);
+    for (int a = 0; a < s.D; a++) {
+        const void *src[4] = {s.Delta[a], s.DeltaU[a], s.A1[a], s.A2[a]};
+        const void **dst[4] = {&pl->s.Delta[a], &pl->s.DeltaU[a], &pl->s.A1[a], &pl->s.A2[a]};
+        for (int q = 0; q < 4; q++) {
+            auto &v = pl->host_tables[a * 4 + q];
+            v.assign((const unsigned char *)src[q], (const unsigned char *)src[q] + s.N[a] * pl->esz);
+            *dst[q] = v.data();
+        }
+    }
+    pl->ncell = 1;
+    for (int a = 0; a < 3; a++) {
+        for (int c = 0; c < 3; c++) pl->Iu[c][a][0] = 0, pl->Iu[c][a][1] = 1;
+        pl->Ip[a][0] = 0;
+        pl->Ip[a][1] = 1;
+    }
+    for (int a = 0; a < s.D; a++) {
+        pl->ncell *= s.N[a];
+        pl->Ip[a][0] = offset_p(s.bc_u[a][0], false);
+        pl->Ip[a][1] = s.N[a] - offset_p(s.bc_u[a][1], true);
+        for (int c = 0; c < s.D; c++) {
+            pl->Iu[c][a][0] = offset_u(s.bc_u[a][0], false, c == a);
+            pl->Iu[c][a][1] = s.N[a] - offset_u(s.bc_u[a][1], true, c == a);
+        }
+    }
+    int r = pl->f64 ? build_grid<double>(pl, pl->gd) : build_grid<float>(pl, pl->gf);
+    if (r) {
+        insb200_plan_destroy(pl);
+        return r;
+    }
+    std::memset(&pl->bc, 0, sizeof(pl->bc));
+    std::memcpy(pl->bc.bc_u, s.bc_u, sizeof(s.bc_u));
+    std::memcpy(pl->bc.bc_temp, s.has_temp ? s.bc_temp : s.bc_u, sizeof(s.bc_u));
+    std::memcpy(pl->bc.u_val, s.bc_u_value, sizeof(s.bc_u_value));
+    std::memcpy(pl->bc.temp_val, s.bc_temp_value, sizeof(s.bc_temp_value));
+    int kind = s.psolver;
+    if (kind == INSB200_PSOLVER_DEFAULT) kind = resolve_default_psolver(pl);
+    pl->psolver = kind;
+    if (kind != INSB200_PSOLVER_NONE) {
+        r = poisson_create(pl->s, pl->Ip, kind, &pl->ps);
+        if (r) {
+            insb200_plan_destroy(pl);
+            return r;
+        }
+        pl->bytes += poisson_bytes(pl->ps);
+    }
+    if (cudaMalloc((void **)&pl->scratch, 4 * sizeof(double)) != cudaSuccess) {
+        set_error("cudaMalloc failed");
+        insb200_plan_destroy(pl);
+        return 1;
+    }
+    *out = pl;
+    return 0;
+    API_END
+}
+
+int insb200_plan_destroy(insb200_plan_t *pl) {
+    if (!pl) return 0;
+    cudaDeviceSynchronize();
+    if (pl->ps) poisson_destroy(pl->ps);
+    for (void *p : {pl->V[0], pl->V[1], pl->ACC, pl->P, pl->TV[0], pl->TV[1], pl->TACC, pl->dev_tables,
+                    (void *)pl->scratch, pl->HU, pl->HT})
+        if (p) cudaFree(p);
+    for (void *p : pl->K) cudaFree(p);
+    for (void *p : pl->TK) cudaFree(p);
+    for (auto &b : pl->brackets) {
+        cudaEventDestroy(b.a);
+        cudaEventDestroy(b.b);
+    }
+    for (auto e : pl->evpool) cudaEventDestroy(e);
+    delete pl;
+    return 0;
+}
+
+int insb200_plan_psolver(const insb200_plan_t *pl) { return pl ? pl->psolver : INSB200_PSOLVER_NONE; }
+long long insb200_plan_workspace_bytes(const insb200_plan_t *pl) { return pl ? pl->bytes : 0; }
+long long insb200_launch_count(const insb200_plan_t *pl) { return pl ? pl->launches : 0; }
+
+#define DISPATCH(expr_f, expr_d) (pl->f64 ? (expr_d) : (expr_f))
+
+int insb200_apply_bc_u(insb200_plan_t *pl, void *u, double t, int dudt, void *stream) {
+    API_BEGIN(void) t;
+    return DISPATCH(launch_bc_u<float>(pl->gf, pl->bc, (float *)u, dudt, L_of(pl, stream)),
+                    launch_bc_u<double>(pl->gd, pl->bc, (double *)u, dudt, L_of(pl, stream)));
+    API_END
+}
+int insb200_apply_bc_p(insb200_plan_t *pl, void *p, void *stream) {
+    API_BEGIN
+    return DISPATCH(launch_bc_p<float>(pl->gf, pl->bc, (float *)p, L_of(pl, stream)),
+                    launch_bc_p<double>(pl->gd, pl->bc, (double *)p, L_of(pl, stream)));
+    API_END
+}
+int insb200_apply_bc_temp(insb200_plan_t *pl, void *temp, double t, void *stream) {
+    API_BEGIN(void) t;
+    return DISPATCH(launch_bc_temp<float>(pl->gf, pl->bc, (float *)temp, L_of(pl, stream)),
+                    launch_bc_temp<double>(pl->gd, pl->bc, (double *)temp, L_of(pl, stream)));
+    API_END
+}
+int insb200_set_bc_u_plane(insb200_plan_t *pl, int dim, int side, int comp, const void *plane) {
+    if (!pl || dim < 0 || dim >= pl->D || side < 0 || side > 1 || comp < 0 || comp >= pl->D) {
+        set_error("bad (dim, side, comp)");
+        return 1;
+    }
+    pl->bc.u_plane[dim][side][comp] = plane;
+    return 0;
+}
+
+int insb200_rhs(insb200_plan_t *pl, const void *u, const void *temp, void *ku, void *ktemp,
+                const insb200_params_t *pr, void *stream) {
+    API_BEGIN
+    if (pr->boussinesq && (!temp || !ktemp)) {
+        set_error("boussinesq forcing needs temp and ktemp");
+        return 1;
+    }
+    return DISPATCH(rhs_t<float>(pl, (const float *)u, (const float *)temp, (float *)ku, (float *)ktemp, pr, 1,
+                                 1, 0, stream),
+                    rhs_t<double>(pl, (const double *)u, (const double *)temp, (double *)ku, (double *)ktemp,
+                                  pr, 1, 1, 0, stream));
+    API_END
+}
+int insb200_convection(insb200_plan_t *pl, void *f, const void *u, void *stream) {
+    API_BEGIN
+    insb200_params_t pr{};
+    return DISPATCH(rhs_t<float>(pl, (const float *)u, nullptr, (float *)f, nullptr, &pr, 1, 0, 1, stream),
+                    rhs_t<double>(pl, (const double *)u, nullptr, (double *)f, nullptr, &pr, 1, 0, 1, stream));
+    API_END
+}
+int insb200_diffusion(insb200_plan_t *pl, void *f, const void *u, double viscosity, void *stream) {
+    API_BEGIN
+    insb200_params_t pr{};
+    pr.viscosity = viscosity;
+    return DISPATCH(rhs_t<float>(pl, (const float *)u, nullptr, (float *)f, nullptr, &pr, 0, 1, 1, stream),
+                    rhs_t<double>(pl, (const double *)u, nullptr, (double *)f, nullptr, &pr, 0, 1, 1, stream));
+    API_END
+}
+
+int insb200_divergence(insb200_plan_t *pl, void *div, const void *u, void *stream) {
+    API_BEGIN
+    return DISPATCH(launch_divergence<float>(pl->gf, (const float *)u, (float *)div, false, L_of(pl, stream)),
+                    launch_divergence<double>(pl->gd, (const double *)u, (double *)div, false, L_of(pl, stream)));
+    API_END
+}
+int insb200_scalewithvolume(insb200_plan_t *pl, void *p, void *stream) {
+    API_BEGIN
+    return DISPATCH(launch_scalewithvolume<float>(pl->gf, (float *)p, L_of(pl, stream)),
+                    launch_scalewithvolume<double>(pl->gd, (double *)p, L_of(pl, stream)));
+    API_END
+}
+int insb200_pressuregradient(insb200_plan_t *pl, void *G, const void *p, void *stream) {
+    API_BEGIN
+    return DISPATCH(
+        launch_pressuregradient<float>(pl->gf, (const float *)p, (float *)G, (float *)nullptr, L_of(pl, stream)),
+        launch_pressuregradient<double>(pl->gd, (const double *)p, (double *)G, (double *)nullptr,
+                                        L_of(pl, stream)));
+    API_END
+}
+int insb200_applypressure(insb200_plan_t *pl, void *u, const void *p, void *stream) {
+    API_BEGIN
+    return DISPATCH(
+        launch_pressuregradient<float>(pl->gf, (const float *)p, (float *)nullptr, (float *)u, L_of(pl, stream)),
+        launch_pressuregradient<double>(pl->gd, (const double *)p, (double *)nullptr, (double *)u,
+                                        L_of(pl, stream)));
+    API_END
+}
+
+int insb200_psolve(insb200_plan_t *pl, void *p, void *stream) {
+    API_BEGIN
+    if (!pl->ps) {
+        set_error("this plan has no Poisson solver");
+        return 1;
+    }
+    Scope sc(pl, (cudaStream_t)stream, 2);
+    return poisson_solve(pl->ps, p, L_of(pl, stream));
+    API_END
+}
+int insb200_project(insb200_plan_t *pl, void *u, void *p, void *stream) {
+    API_BEGIN
+    return DISPATCH(project_t<float>(pl, (float *)u, (float *)p, stream),
+                    project_t<double>(pl, (double *)u, (double *)p, stream));
+    API_END
+}
+
+int insb200_step_rk(insb200_plan_t *pl, const double *A, const double *c, int s, int coef_dtype, void *u,
+                    void *temp, double t, double dt, const insb200_params_t *pr, void *stream) {
+    API_BEGIN
+    return DISPATCH(step_rk_t<float>(pl, A, c, s, coef_dtype, (float *)u, (float *)temp, t, dt, pr, stream),
+                    step_rk_t<double>(pl, A, c, s, coef_dtype, (double *)u, (double *)temp, t, dt, pr, stream));
+    API_END
+}
+int insb200_step_lmwray3(insb200_plan_t *pl, void *u, void *temp, double t, double dt,
+                         const insb200_params_t *pr, void *stream) {
+    API_BEGIN
+    return DISPATCH(step_wray_t<float>(pl, (float *)u, (float *)temp, t, dt, pr, stream),
+                    step_wray_t<double>(pl, (double *)u, (double *)temp, t, dt, pr, stream));
+    API_END
+}
+
+int insb200_step_rk_host(insb200_plan_t *pl, const double *A, const double *c, int s, int coef_dtype,
+                         void *u_host, void *temp_host, double t, double dt, int nsteps,
+                         const insb200_params_t *pr, void *stream) {
+    API_BEGIN
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t vb = (size_t)pl->ncell * pl->D * pl->esz, sb = (size_t)pl->ncell * pl->esz;
+    // device-resident state lives in the k-storage slots (allocated on first use)
+    bool bouss = pr->boussinesq != 0;
+    if (!pl->HU) INSB_TRY(dev_alloc(pl, &pl->HU, vb));
+    if (bouss && !pl->HT) INSB_TRY(dev_alloc(pl, &pl->HT, sb));
+    void *dU = pl->HU;
+    void *dT = bouss ? pl->HT : nullptr;
+    INSB_CUDA(cudaMemcpyAsync(dU, u_host, vb, cudaMemcpyHostToDevice, st));
+    if (bouss) INSB_CUDA(cudaMemcpyAsync(dT, temp_host, sb, cudaMemcpyHostToDevice, st));
+    for (int n = 0; n < nsteps; n++) {
+        INSB_TRY(insb200_step_rk(pl, A, c, s, coef_dtype, dU, dT, t + n * dt, dt, pr, stream));
+    }
+    INSB_CUDA(cudaMemcpyAsync(u_host, dU, vb, cudaMemcpyDeviceToHost, st));
+    if (bouss) INSB_CUDA(cudaMemcpyAsync(temp_host, dT, sb, cudaMemcpyDeviceToHost, st));
+    INSB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+    API_END
+}
+
+int insb200_right_hand_side(insb200_plan_t *pl, void *dudt, const void *u, double t,
+                            const insb200_params_t *pr, void *stream) {
+    API_BEGIN
+    return DISPATCH(rhs_sciml_t<float>(pl, (float *)dudt, (const float *)u, t, pr, stream),
+                    rhs_sciml_t<double>(pl, (double *)dudt, (const double *)u, t, pr, stream));
+    API_END
+}
+
+int insb200_cfl(insb200_plan_t *pl, const void *u, const insb200_params_t *pr, double *dt_out, void *stream) {
+    API_BEGIN
+    Launch L = L_of(pl, stream);
+    INSB_TRY(DISPATCH(launch_cfl<float>(pl->gf, pl->Iu, (const float *)u, pl->scratch, L),
+                      launch_cfl<double>(pl->gd, pl->Iu, (const double *)u, pl->scratch, L)));
+    unsigned long long h[2];
+    INSB_CUDA(cudaMemcpyAsync(h, pl->scratch, sizeof(h), cudaMemcpyDeviceToHost, L.stream));
+    INSB_CUDA(cudaStreamSynchronize(L.stream));
+    double conv;
+    std::memcpy(&conv, &h[0], 8);
+    if (h[1]) conv = std::nan("");
+    // values were computed in T; the diffusive limits below too (solver.jl:157-166, 188-197)
+    double dt = conv;
+    const int D = pl->D;
+    for (int a = 0; a < D; a++) {
+        double d;
+        if (pl->f64)
+            d = pl->dmin_u[a] * pl->dmin_u[a] / pr->viscosity / (2 * D);
+        else
+            d = (double)((float)pl->dmin_u[a] * (float)pl->dmin_u[a] / (float)pr->viscosity / (float)(2 * D));
+        dt = std::isnan(dt) ? dt : std::fmin(dt, d);
+    }
+    if (pr->boussinesq) {
+        for (int a = 0; a < D; a++) {
+            double d;
+            if (pl->f64)
+                d = pl->dmin_p[a] * pl->dmin_p[a] / pr->conductivity / (2 * D);
+            else
+                d = (double)((float)pl->dmin_p[a] * (float)pl->dmin_p[a] / (float)pr->conductivity /
+                             (float)(2 * D));
+            dt = std::isnan(dt) ? dt : std::fmin(dt, d);
+        }
+    }
+    *dt_out = dt;
+    return 0;
+    API_END
+}
+
+int insb200_maxabs(insb200_plan_t *pl, const void *u, double *out, void *stream) {
+    API_BEGIN
+    Launch L = L_of(pl, stream);
+    long long n = pl->ncell * pl->D;
+    INSB_TRY(DISPATCH(launch_maxabs<float>((const float *)u, n, pl->scratch, L),
+                      launch_maxabs<double>((const double *)u, n, pl->scratch, L)));
+    unsigned long long h[2];
+    INSB_CUDA(cudaMemcpyAsync(h, pl->scratch, sizeof(h), cudaMemcpyDeviceToHost, L.stream));
+    INSB_CUDA(cudaStreamSynchronize(L.stream));
+    double v;
+    std::memcpy(&v, &h[0], 8);
+    *out = h[1] ? std::nan("") : v;
+    return 0;
+    API_END
+}
+
+int insb200_profile_enable(insb200_plan_t *pl, int on) {
+    pl->prof = on != 0;
+    return 0;
+}
+int insb200_profile_read(insb200_plan_t *pl, double ms[5], long long counts[5]) {
+    API_BEGIN
+    INSB_CUDA(cudaDeviceSynchronize());
+    for (auto &b : pl->brackets) {
+        float t = 0;
+        cudaEventElapsedTime(&t, b.a, b.b);
+        pl->prof_ms[b.group] += t;
+        pl->prof_cnt[b.group] += 1;
+        pl->evpool.push_back(b.a);
+        pl->evpool.push_back(b.b);
+    }
+    pl->brackets.clear();
+    for (int i = 0; i < 5; i++) {
+        ms[i] = pl->prof_ms[i];
+        counts[i] = pl->prof_cnt[i];
+        pl->prof_ms[i] = 0;
+        pl->prof_cnt[i] = 0;
+    }
+    return 0;
+    API_END
+}
+
+}  // extern "C"

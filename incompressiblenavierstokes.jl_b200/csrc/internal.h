@@ -1,0 +1,132 @@
+// internal.h -- shared declarations of libinsb200 (host side + kernel launchers).
+//
+// Index conventions: 0-based; a scalar field has N[0]*N[1]*N[2] cells (N[2] = 1 in
+// 2-D) with x fastest; a vector field is D such scalars back to back (the reference's
+// column-major (N..., D) layout, src/initializers.jl:2,5).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/insb200.h"
+
+namespace insb {
+
+constexpr int MAXSTAGE = 8;
+
+void set_error(const std::string &msg);
+
+#define INSB_CUDA(call)                                                                  \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess) {                                                        \
+            insb::set_error(std::string(#call) + ": " + cudaGetErrorString(e__) + " at " \
+                            + __FILE__ + ":" + std::to_string(__LINE__));               \
+            return 1;                                                                    \
+        }                                                                                \
+    } while (0)
+
+#define INSB_TRY(call)          \
+    do {                        \
+        int r__ = (call);       \
+        if (r__) return r__;    \
+    } while (0)
+
+// Device view of the Setup tables (all pointers are device pointers, length N[a]).
+template <typename T>
+struct Grid {
+    int D;
+    int N[3];
+    long long s[3];  // strides of a scalar field: 1, N0, N0*N1
+    long long cs;    // component stride N0*N1*N2
+    const T *dl[3];    // Δ            (src/grid.jl:167-171)
+    const T *du[3];    // Δu           (src/grid.jl:173-177)
+    const T *rdl[3];   // 1/Δ
+    const T *rdu[3];   // 1/Δu
+    const T *rdlg[3];  // 1/Δ  where Δ  > 2 eps, else 0 (guard of δ, src/operators.jl:181-187)
+    const T *rdug[3];  // 1/Δu where Δu > 2 eps, else 0
+    const T *a1[3];    // A_stag[a][1] (src/grid.jl:180-186)
+    const T *a2[3];    // A_stag[a][2]
+    const T *wa[3];    // Δ[i+1]/(Δ[i]+Δ[i+1])  weights of avg (src/operators.jl:197-200)
+    const T *wb[3];    // Δ[i]  /(Δ[i]+Δ[i+1])
+};
+
+// Boundary description used by the ghost-fill kernels.
+struct BcDesc {
+    int bc_u[3][2];
+    int bc_temp[3][2];
+    double u_val[3][2][3];
+    double temp_val[3][2];
+    const void *u_plane[3][2][3];  // optional device planes for function-valued Dirichlet BC
+};
+
+// Arguments of the fused stage kernel (right-hand side + stage combine).
+template <typename T>
+struct StageArgs {
+    const T *u;     // velocity the stencil reads (ghosts filled)
+    const T *temp;  // temperature the stencil reads (Boussinesq) or nullptr
+    // velocity outputs (any may be nullptr)
+    T *v;            // v = vbase + sum_j cprev[j]*kprev[j] + cv*k
+    const T *vbase;
+    double cv;
+    T *acc_out;      // acc_out = acc_in + ca*k
+    const T *acc_in;
+    double ca;
+    T *k_out;        // k itself
+    int zero_outside;  // k_out: also write zeros outside 2:N-1 (insb200_rhs semantics)
+    int nprev;
+    const T *kprev[MAXSTAGE];
+    double cprev[MAXSTAGE];
+    // temperature twins
+    T *tv;
+    const T *tvbase;
+    T *tacc_out;
+    const T *tacc_in;
+    T *tk_out;
+    const T *tkprev[MAXSTAGE];
+    // parameters
+    double nu, kappa, grav;
+    int gdir, dodiss, bouss;
+    double bodyforce[3];
+    int conv, diff;  // which stresses to include (1,1 = convectiondiffusion!)
+    int add_to_k;    // k_out += instead of = (convection!/diffusion! add semantics)
+};
+
+struct Launch {
+    cudaStream_t stream;
+    long long *counter;
+};
+
+// ---- stencil.cu ----
+template <typename T>
+int launch_stage(const Grid<T> &g, const StageArgs<T> &a, bool ct_double, Launch L);
+template <typename T>
+int launch_divergence(const Grid<T> &g, const T *u, T *div, bool scale, Launch L);
+template <typename T>
+int launch_scalewithvolume(const Grid<T> &g, T *p, Launch L);
+template <typename T>
+int launch_pressuregradient(const Grid<T> &g, const T *p, T *G, T *u_sub, Launch L);
+template <typename T>
+int launch_cfl(const Grid<T> &g, const int Iu[3][3][2], const T *u, double *scratch, Launch L);
+template <typename T>
+int launch_maxabs(const T *u, long long n, double *scratch, Launch L);
+
+// ---- bc.cu ----
+template <typename T>
+int launch_bc_u(const Grid<T> &g, const BcDesc &b, T *u, int dudt, Launch L);
+template <typename T>
+int launch_bc_p(const Grid<T> &g, const BcDesc &b, T *p, Launch L);
+template <typename T>
+int launch_bc_temp(const Grid<T> &g, const BcDesc &b, T *temp, Launch L);
+
+// ---- poisson.cu ----
+struct Poisson;  // opaque
+int poisson_create(const insb200_setup_t &s, const int Ip[3][2], int kind, Poisson **out);
+void poisson_destroy(Poisson *p);
+long long poisson_bytes(const Poisson *p);
+int poisson_solve(Poisson *ps, void *p_ghosted, Launch L);
+
+}  // namespace insb

@@ -1,0 +1,791 @@
+// poisson.cu -- FFT-type Poisson solvers on the pressure DOFs, hand-written (no cuFFT).
+//
+// Replaces the closures returned by psolver_spectral (src/pressure.jl:321-382),
+// psolver_transform (:215-318, with manual_dct!/manual_idct! of src/utils.jl:65-155) and
+// psolver_tridiagonal (:401-545).  The solve is a sequence of "line passes": every pass
+// moves a tile of lines (along one dimension) into shared memory, transforms it there
+// (mixed-radix Stockham FFT, DCT-II/III through the FFT, or the Thomas recurrence) and
+// writes it back, so each pass is one read + one write of the spectrum in HBM.  The
+// eigenvalue division (pressure.jl:360-372 / :281-293) is fused into the middle pass
+// together with the inverse transform of that dimension; pack/unpack of view(p, Ip)
+// (pressure.jl:351,378) is fused into the first/last pass.
+#include <cmath>
+#include <cstring>
+
+#include "internal.h"
+
+namespace insb {
+
+template <typename T>
+struct Cx {
+    T x, y;
+};
+template <typename T>
+__host__ __device__ __forceinline__ Cx<T> cmul(Cx<T> a, Cx<T> b) {
+    return Cx<T>{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
+}
+template <typename T>
+__host__ __device__ __forceinline__ Cx<T> cadd(Cx<T> a, Cx<T> b) {
+    return Cx<T>{a.x + b.x, a.y + b.y};
+}
+template <typename T>
+__host__ __device__ __forceinline__ Cx<T> csub(Cx<T> a, Cx<T> b) {
+    return Cx<T>{a.x - b.x, a.y - b.y};
+}
+template <typename T>
+__host__ __device__ __forceinline__ Cx<T> cconj(Cx<T> a) {
+    return Cx<T>{a.x, -a.y};
+}
+
+enum PassOp {
+    P_FFT_FWD = 0,
+    P_FFT_INV = 1,
+    P_DCT_FWD = 2,
+    P_DCT_INV = 3,
+    P_MID_FFT = 4,
+    P_MID_DCT = 5,
+    P_THOMAS = 6
+};
+
+constexpr int MAXRAD = 16;
+
+template <typename T>
+struct PassArgs {
+    int op;
+    int dim;        // dimension the lines run along
+    int n;          // transform length
+    int D;
+    int src_real;   // load from the ghosted real array (imag = 0)
+    int dst_real;   // store real part to the ghosted real array
+    int half_out;   // store only the first n/2+1 entries (R2C)
+    int half_in;    // load n/2+1 entries and Hermitian-extend (C2R)
+    Cx<T> *W;       // complex workspace
+    long long ws[3];
+    int m[3];       // complex extents of W
+    T *R;           // ghosted real array, already offset to the first pressure DOF
+    long long rs[3];
+    int tile;       // lines per block
+    int ld;         // smem leading dimension (complex elements)
+    int nrad;
+    int radix[MAXRAD];
+    const Cx<T> *tw;    // exp(-2 pi i q / n), q = 0..n-1
+    const Cx<T> *dw;    // DCT twiddles w_k    (utils.jl:68-75)
+    const Cx<T> *dwi;   // DCT twiddles winv_k (utils.jl:76-83)
+    const T *eig[3];    // eigenvalue tables (ahat / lam)
+    T sign;             // -1 for spectral (phat = -phat/(...)), +1 for transform
+    T scale;            // 1 / prod(n_periodic)
+    const T *prescale;  // optional factor on load, indexed along pdim (invΩ, pressure.jl:463-465)
+    int pdim;
+    // Thomas
+    const T *ta, *tb, *tc;
+};
+
+// ----------------------------------------------------------------------------------------
+// small DFTs
+// ----------------------------------------------------------------------------------------
+template <typename T, int R>
+__device__ __forceinline__ void dft_small(Cx<T> *v, const Cx<T> *tw, int n, bool inv) {
+    if (R == 2) {
+        Cx<T> a = v[0], b = v[1];
+        v[0] = cadd(a, b);
+        v[1] = csub(a, b);
+    } else if (R == 4) {
+        Cx<T> a = cadd(v[0], v[2]), b = csub(v[0], v[2]);
+        Cx<T> c = cadd(v[1], v[3]), d = csub(v[1], v[3]);
+        // multiply d by -i (forward) or +i (inverse)
+        Cx<T> dj = inv ? Cx<T>{-d.y, d.x} : Cx<T>{d.y, -d.x};
+        v[0] = cadd(a, c);
+        v[2] = csub(a, c);
+        v[1] = cadd(b, dj);
+        v[3] = csub(b, dj);
+    } else {
+        Cx<T> o[R];
+        int step = n / R;
+#pragma unroll
+        for (int q = 0; q < R; q++) {
+            Cx<T> acc = v[0];
+#pragma unroll
+            for (int r = 1; r < R; r++) {
+                Cx<T> w = tw[((q * r) % R) * step];
+                if (inv) w = cconj(w);
+                acc = cadd(acc, cmul(v[r], w));
+            }
+            o[q] = acc;
+        }
+#pragma unroll
+        for (int q = 0; q < R; q++) v[q] = o[q];
+    }
+}
+
+template <typename T, int R>
+__device__ __forceinline__ void stockham_pass(const Cx<T> *A, Cx<T> *B, int nlines, int n, int ld,
+                                              int Ns, const Cx<T> *tw, bool inv) {
+    int nb = n / R;
+    int total = nlines * nb;
+    int tstep = n / (Ns * R);
+    for (int w = threadIdx.x; w < total; w += blockDim.x) {
+        int l = w / nb, j = w - l * nb;
+        int k = j % Ns;
+        Cx<T> v[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            Cx<T> x = A[l * ld + j + r * nb];
+            if (r > 0 && k > 0) {
+                Cx<T> t = tw[r * k * tstep];
+                if (inv) t = cconj(t);
+                x = cmul(x, t);
+            }
+            v[r] = x;
+        }
+        dft_small<T, R>(v, tw, n, inv);
+        int j0 = (j / Ns) * Ns * R + k;
+#pragma unroll
+        for (int r = 0; r < R; r++) B[l * ld + j0 + r * Ns] = v[r];
+    }
+}
+
+// In-smem batched FFT of `nlines` lines of length n; returns the buffer holding the result.
+template <typename T>
+__device__ Cx<T> *fft_lines(Cx<T> *A, Cx<T> *B, int nlines, const PassArgs<T> &a, bool inv) {
+    int Ns = 1;
+    for (int p = 0; p < a.nrad; p++) {
+        int R = a.radix[p];
+        switch (R) {
+            case 2: stockham_pass<T, 2>(A, B, nlines, a.n, a.ld, Ns, a.tw, inv); break;
+            case 3: stockham_pass<T, 3>(A, B, nlines, a.n, a.ld, Ns, a.tw, inv); break;
+            case 4: stockham_pass<T, 4>(A, B, nlines, a.n, a.ld, Ns, a.tw, inv); break;
+            case 5: stockham_pass<T, 5>(A, B, nlines, a.n, a.ld, Ns, a.tw, inv); break;
+            case 7: stockham_pass<T, 7>(A, B, nlines, a.n, a.ld, Ns, a.tw, inv); break;
+            case 11: stockham_pass<T, 11>(A, B, nlines, a.n, a.ld, Ns, a.tw, inv); break;
+            case 13: stockham_pass<T, 13>(A, B, nlines, a.n, a.ld, Ns, a.tw, inv); break;
+            default: break;
+        }
+        __syncthreads();
+        Cx<T> *t = A;
+        A = B;
+        B = t;
+        Ns *= R;
+    }
+    return A;
+}
+
+// DCT-II of the (complex = two real) lines through one complex FFT (Makhoul; the reference
+// does the same per real array, utils.jl:89-122).  Input in A in natural order.
+template <typename T>
+__device__ Cx<T> *dct_fwd_lines(Cx<T> *A, Cx<T> *B, int nlines, const PassArgs<T> &a) {
+    int n = a.n, ld = a.ld, h = n / 2;
+    // permutation (get_perminds, utils.jl:51-63): z[m] = x[2m], z[n-1-m] = x[2m+1]
+    for (int w = threadIdx.x; w < nlines * n; w += blockDim.x) {
+        int l = w / n, q = w - l * n;
+        int src = q < h ? 2 * q : 2 * (n - 1 - q) + 1;
+        B[l * ld + q] = A[l * ld + src];
+    }
+    __syncthreads();
+    Cx<T> *Z = fft_lines<T>(B, A, nlines, a, false);
+    Cx<T> *O = (Z == A) ? B : A;
+    for (int w = threadIdx.x; w < nlines * n; w += blockDim.x) {
+        int l = w / n, k = w - l * n;
+        Cx<T> zk = Z[l * ld + k];
+        Cx<T> zc = cconj(Z[l * ld + (k == 0 ? 0 : n - k)]);
+        // FFT of the real and of the imaginary input sequence
+        Cx<T> fa{(zk.x + zc.x) * T(0.5), (zk.y + zc.y) * T(0.5)};
+        Cx<T> d{(zk.x - zc.x) * T(0.5), (zk.y - zc.y) * T(0.5)};
+        Cx<T> fb{d.y, -d.x};  // d / i
+        Cx<T> wk = a.dw[k];
+        // X = 2 Re(w_k F_k)
+        O[l * ld + k] = Cx<T>{T(2) * (wk.x * fa.x - wk.y * fa.y), T(2) * (wk.x * fb.x - wk.y * fb.y)};
+    }
+    __syncthreads();
+    return O;
+}
+
+// DCT-III (inverse of the above), utils.jl:124-155.
+template <typename T>
+__device__ Cx<T> *dct_inv_lines(Cx<T> *A, Cx<T> *B, int nlines, const PassArgs<T> &a) {
+    int n = a.n, ld = a.ld, h = n / 2;
+    for (int w = threadIdx.x; w < nlines * n; w += blockDim.x) {
+        int l = w / n, k = w - l * n;
+        Cx<T> xk = A[l * ld + k];
+        Cx<T> out;
+        if (k == 0) {
+            T w0 = a.dwi[0].x;
+            out = Cx<T>{w0 * xk.x, w0 * xk.y};
+        } else {
+            Cx<T> xm = A[l * ld + n - k];
+            Cx<T> wk = a.dwi[k], wm = cconj(a.dwi[n - k]);
+            // H[k] = (winv_k x[k] + conj(winv_{n-k}) x[n-k]) / 2 for the two real sequences
+            Cx<T> ha{(wk.x * xk.x + wm.x * xm.x) * T(0.5), (wk.y * xk.x + wm.y * xm.x) * T(0.5)};
+            Cx<T> hb{(wk.x * xk.y + wm.x * xm.y) * T(0.5), (wk.y * xk.y + wm.y * xm.y) * T(0.5)};
+            out = Cx<T>{ha.x - hb.y, ha.y + hb.x};  // ha + i hb
+        }
+        B[l * ld + k] = out;
+    }
+    __syncthreads();
+    Cx<T> *Y = fft_lines<T>(B, A, nlines, a, true);
+    Cx<T> *O = (Y == A) ? B : A;
+    T invn = T(1) / T(n);  // ifft! is normalised (utils.jl:132)
+    for (int w = threadIdx.x; w < nlines * n; w += blockDim.x) {
+        int l = w / n, q = w - l * n;
+        // perminv (utils.jl:59-60): out[2m] = y[m], out[2m+1] = y[n-1-m]
+        int src = (q & 1) ? n - 1 - (q >> 1) : (q >> 1);
+        Cx<T> y = Y[l * ld + src];
+        O[l * ld + q] = Cx<T>{y.x * invn, y.y * invn};
+    }
+    __syncthreads();
+    (void)h;
+    return O;
+}
+
+// ----------------------------------------------------------------------------------------
+// the pass kernel
+// ----------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) line_pass_kernel(PassArgs<T> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Cx<T> *A = reinterpret_cast<Cx<T> *>(smem_raw);
+    Cx<T> *B = A + (size_t)a.tile * a.ld;
+
+    const int dim = a.dim;
+    const int da = dim == 0 ? 1 : 0;                 // fast companion dimension
+    const int db = dim == 2 ? 1 : 2;                 // slow companion dimension
+    const int ma = a.m[da], mb = (a.D == 3) ? a.m[db] : 1;
+    const long long nlines_total = (long long)ma * mb;
+    const long long line0 = (long long)blockIdx.x * a.tile;
+    int nl = (int)min((long long)a.tile, nlines_total - line0);
+    if (nl <= 0) return;
+
+    const int n = a.n, ld = a.ld;
+    const int nin = a.half_in ? n / 2 + 1 : n;
+
+    // ---- load ----
+    const int total_in = nl * nin;
+    for (int w = threadIdx.x; w < total_in; w += blockDim.x) {
+        int l, k;
+        if (dim == 0) {
+            l = w / nin;
+            k = w - l * nin;
+        } else {
+            k = w / nl;
+            l = w - k * nl;
+        }
+        long long line = line0 + l;
+        int ia = (int)(line % ma), ib = (int)(line / ma);
+        Cx<T> v;
+        if (a.src_real) {
+            long long off = k * a.rs[dim] + ia * a.rs[da] + (a.D == 3 ? ib * a.rs[db] : 0);
+            T r = a.R[off];
+            if (a.prescale) {
+                int ip = a.pdim == dim ? k : (a.pdim == da ? ia : ib);
+                r *= a.prescale[ip];
+            }
+            v = Cx<T>{r, T(0)};
+        } else {
+            long long off = k * a.ws[dim] + ia * a.ws[da] + (a.D == 3 ? ib * a.ws[db] : 0);
+            v = a.W[off];
+        }
+        A[l * ld + k] = v;
+    }
+    __syncthreads();
+    if (a.half_in) {  // Hermitian extension X[n-k] = conj(X[k])
+        int hx = n - nin;
+        for (int w = threadIdx.x; w < nl * hx; w += blockDim.x) {
+            int l = w / hx, k = nin + (w - l * hx);
+            A[l * ld + k] = cconj(A[l * ld + n - k]);
+        }
+        __syncthreads();
+    }
+
+    // ---- transform ----
+    Cx<T> *Rbuf = A;
+    Cx<T> *Obuf = B;
+    switch (a.op) {
+        case P_FFT_FWD: Rbuf = fft_lines<T>(A, B, nl, a, false); break;
+        case P_FFT_INV: Rbuf = fft_lines<T>(A, B, nl, a, true); break;
+        case P_DCT_FWD: Rbuf = dct_fwd_lines<T>(A, B, nl, a); break;
+        case P_DCT_INV: Rbuf = dct_inv_lines<T>(A, B, nl, a); break;
+        case P_MID_FFT:
+        case P_MID_DCT: {
+            Rbuf = a.op == P_MID_FFT ? fft_lines<T>(A, B, nl, a, false) : dct_fwd_lines<T>(A, B, nl, a);
+            Obuf = (Rbuf == A) ? B : A;
+            for (int w = threadIdx.x; w < nl * n; w += blockDim.x) {
+                int l = w / n, k = w - l * n;
+                long long line = line0 + l;
+                int ia = (int)(line % ma), ib = (int)(line / ma);
+                int K[3] = {0, 0, 0};
+                K[dim] = k;
+                K[da] = ia;
+                if (a.D == 3) K[db] = ib;
+                T den = a.eig[0][K[0]] + a.eig[1][K[1]];
+                if (a.D == 3) den = den + a.eig[2][K[2]];
+                bool zero = (K[0] | K[1] | K[2]) == 0;
+                T f = zero ? T(0) : a.sign * a.scale / den;
+                Cx<T> v = Rbuf[l * ld + k];
+                Rbuf[l * ld + k] = Cx<T>{v.x * f, v.y * f};
+            }
+            __syncthreads();
+            Rbuf = a.op == P_MID_FFT ? fft_lines<T>(Rbuf, Obuf, nl, a, true)
+                                     : dct_inv_lines<T>(Rbuf, Obuf, nl, a);
+            break;
+        }
+        case P_THOMAS: {
+            // batched Thomas recurrence, one line per thread (pressure.jl:480-504), then the
+            // zero-mode mean removal (:531-532) and the 1/fftscale of :538
+            T *wl = reinterpret_cast<T *>(B);
+            for (int l = threadIdx.x; l < nl; l += blockDim.x) {
+                long long line = line0 + l;
+                int ia = (int)(line % ma), ib = (int)(line / ma);
+                T lam = T(0);
+                bool zero = true;
+                for (int be = 0; be < a.D; be++) {
+                    if (be == dim) continue;
+                    int kb = be == da ? ia : ib;
+                    lam += a.eig[be][kb];
+                    zero = zero && kb == 0;
+                }
+                Cx<T> *f = A + l * ld;
+                T *w = wl + l * 2 * ld;
+                if (lam == T(0)) {
+                    w[0] = T(0);
+                    f[0] = Cx<T>{T(0), T(0)};
+                } else {
+                    T bb = a.tb[0] + lam;
+                    w[0] = a.tc[0] / bb;
+                    f[0] = Cx<T>{f[0].x / bb, f[0].y / bb};
+                }
+                for (int j = 1; j < n; j++) {
+                    T aj = a.ta[j];
+                    T denom = a.tb[j] + lam - aj * w[j - 1];
+                    w[j] = a.tc[j] / denom;
+                    f[j] = Cx<T>{(f[j].x - aj * f[j - 1].x) / denom, (f[j].y - aj * f[j - 1].y) / denom};
+                }
+                for (int j = n - 2; j >= 0; j--) {
+                    f[j] = Cx<T>{f[j].x - w[j] * f[j + 1].x, f[j].y - w[j] * f[j + 1].y};
+                }
+                if (zero) {
+                    Cx<T> s{T(0), T(0)};
+                    for (int j = 0; j < n; j++) s = cadd(s, f[j]);
+                    s = Cx<T>{s.x / T(n), s.y / T(n)};
+                    for (int j = 0; j < n; j++) f[j] = csub(f[j], s);
+                }
+                for (int j = 0; j < n; j++) f[j] = Cx<T>{f[j].x * a.scale, f[j].y * a.scale};
+            }
+            __syncthreads();
+            Rbuf = A;
+            break;
+        }
+    }
+
+    // ---- store ----
+    const int nout = a.half_out ? n / 2 + 1 : n;
+    const int total_out = nl * nout;
+    for (int w = threadIdx.x; w < total_out; w += blockDim.x) {
+        int l, k;
+        if (dim == 0) {
+            l = w / nout;
+            k = w - l * nout;
+        } else {
+            k = w / nl;
+            l = w - k * nl;
+        }
+        long long line = line0 + l;
+        int ia = (int)(line % ma), ib = (int)(line / ma);
+        Cx<T> v = Rbuf[l * ld + k];
+        if (a.dst_real) {
+            long long off = k * a.rs[dim] + ia * a.rs[da] + (a.D == 3 ? ib * a.rs[db] : 0);
+            a.R[off] = v.x;
+        } else {
+            long long off = k * a.ws[dim] + ia * a.ws[da] + (a.D == 3 ? ib * a.ws[db] : 0);
+            a.W[off] = v;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------
+struct Poisson {
+    int D = 0, kind = 0;
+    bool f64 = false;
+    int n[3] = {1, 1, 1};     // Np
+    int ioff[3] = {0, 0, 0};  // first pressure DOF
+    int Ng[3] = {1, 1, 1};
+    int m[3] = {1, 1, 1};     // complex extents
+    long long wstride[3] = {1, 1, 1};
+    int rdim = -1, wdir = -1;
+    bool per[3] = {false, false, false};
+    void *W = nullptr;
+    std::vector<void *> owned;
+    long long bytes = 0;
+    // per-dimension tables (device)
+    void *tw[3] = {nullptr, nullptr, nullptr};
+    void *dw[3] = {nullptr, nullptr, nullptr};
+    void *dwi[3] = {nullptr, nullptr, nullptr};
+    void *eig[3] = {nullptr, nullptr, nullptr};
+    void *ta = nullptr, *tb = nullptr, *tc = nullptr, *invO = nullptr;
+    double sign = 1, scale = 1;
+    std::vector<int> radix[3];
+    struct PassDesc {
+        int op, dim, src_real, dst_real, half_out, half_in;
+    };
+    std::vector<PassDesc> passes;
+    int max_smem = 0;
+};
+
+static bool factorize(int n, std::vector<int> &rad) {
+    rad.clear();
+    while (n % 4 == 0) {
+        rad.push_back(4);
+        n /= 4;
+    }
+    const int primes[6] = {2, 3, 5, 7, 11, 13};
+    for (int p : primes)
+        while (n % p == 0) {
+            rad.push_back(p);
+            n /= p;
+        }
+    return n == 1 && (int)rad.size() <= MAXRAD;
+}
+
+static long double sinpi_ld(long double x) { return sinl(3.14159265358979323846264338327950288L * x); }
+static long double cospi_ld(long double x) { return cosl(3.14159265358979323846264338327950288L * x); }
+
+template <typename T>
+static int upload(Poisson *ps, const std::vector<T> &h, void **dptr) {
+    size_t b = h.size() * sizeof(T);
+    INSB_CUDA(cudaMalloc(dptr, b ? b : sizeof(T)));
+    ps->owned.push_back(*dptr);
+    ps->bytes += (long long)b;
+    INSB_CUDA(cudaMemcpy(*dptr, h.data(), b, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+template <typename T>
+static int build_tables(Poisson *ps, const insb200_setup_t &s, const int Ip[3][2]) {
+    const int D = ps->D;
+    const T *dl[3], *du[3];
+    for (int a = 0; a < D; a++) {
+        dl[a] = (const T *)s.Delta[a];
+        du[a] = (const T *)s.DeltaU[a];
+    }
+    // twiddles
+    for (int a = 0; a < D; a++) {
+        int n = ps->n[a];
+        std::vector<Cx<T>> tw(n), dw(n), dwi(n);
+        for (int q = 0; q < n; q++) {
+            long double x = (long double)(2 * q) / n;
+            tw[q] = Cx<T>{(T)cospi_ld(x), (T)(-sinpi_ld(x))};
+            // w_k = exp(-i pi k / (2n)) / sqrt(2n), w_0 /= sqrt(2)       (utils.jl:68-75)
+            // winv_k = exp(+i pi k / (2n)) * sqrt(2n), winv_0 *= sqrt(2)/2 (utils.jl:76-83)
+            long double y = (long double)q / (2.0L * n);
+            long double nrm = sqrtl(2.0L * n);
+            long double c = cospi_ld(y), sn = sinpi_ld(y);
+            long double f0 = q == 0 ? 1.0L / sqrtl(2.0L) : 1.0L;
+            long double g0 = q == 0 ? sqrtl(2.0L) / 2.0L : 1.0L;
+            dw[q] = Cx<T>{(T)(c / nrm * f0), (T)(-sn / nrm * f0)};
+            dwi[q] = Cx<T>{(T)(c * nrm * g0), (T)(sn * nrm * g0)};
+        }
+        INSB_TRY(upload<Cx<T>>(ps, tw, &ps->tw[a]));
+        if (!ps->per[a] && ps->kind == INSB200_PSOLVER_TRANSFORM) {
+            INSB_TRY(upload<Cx<T>>(ps, dw, &ps->dw[a]));
+            INSB_TRY(upload<Cx<T>>(ps, dwi, &ps->dwi[a]));
+        }
+    }
+    // eigenvalues
+    double nper = 1;
+    for (int a = 0; a < D; a++)
+        if (ps->per[a]) nper *= ps->n[a];
+    ps->scale = 1.0 / nper;
+    if (ps->kind == INSB200_PSOLVER_SPECTRAL) {
+        // pressure.jl:327-342: Δx = first.(Δ) (ghost width), Float64 evaluation rounded into T
+        T dx[3], om = T(1);
+        for (int a = 0; a < D; a++) {
+            dx[a] = dl[a][0];
+            om = a == 0 ? dx[a] : om * dx[a];
+        }
+        for (int a = 0; a < D; a++) {
+            int cnt = ps->n[a];
+            std::vector<T> e(cnt);
+            for (int k = 0; k < cnt; k++) {
+                if (s.eig[a]) {
+                    int kmax = a == 0 ? ps->n[a] / 2 + 1 : ps->n[a];
+                    e[k] = k < kmax ? ((const T *)s.eig[a])[k] : T(0);
+                    continue;
+                }
+                double sp = (double)sinpi_ld((long double)((double)k / (double)ps->n[a]));
+                e[k] = (T)(((double)(T(4) * om) * (sp * sp)) / (double)(dx[a] * dx[a]));
+            }
+            INSB_TRY(upload<T>(ps, e, &ps->eig[a]));
+        }
+        ps->sign = -1;
+    } else if (ps->kind == INSB200_PSOLVER_TRANSFORM) {
+        // pressure.jl:221-246
+        T dx[3], om = T(1);
+        for (int a = 0; a < D; a++) {
+            dx[a] = (T)(((T)s.xlims[a][1] - (T)s.xlims[a][0]) / (T)ps->n[a]);
+            om = a == 0 ? dx[a] : om * dx[a];
+        }
+        for (int a = 0; a < D; a++) {
+            int cnt = ps->n[a];
+            std::vector<T> e(cnt);
+            for (int k = 0; k < cnt; k++) {
+                if (s.eig[a]) {
+                    e[k] = ((const T *)s.eig[a])[k];
+                    continue;
+                }
+                double x = (double)k / (double)ps->n[a];
+                double h2 = (double)(dx[a] * dx[a]);
+                if (ps->per[a]) {
+                    double sp = (double)sinpi_ld((long double)x);
+                    e[k] = (T)(((double)(T(-4) * om) * (sp * sp)) / h2);
+                } else {
+                    double cp = (double)cospi_ld((long double)x);
+                    e[k] = (T)(((double)(T(2) * om) * (cp - 1.0)) / h2);
+                }
+            }
+            INSB_TRY(upload<T>(ps, e, &ps->eig[a]));
+        }
+        ps->sign = 1;
+    } else {  // tridiagonal, pressure.jl:429-466
+        int w = ps->wdir, n = ps->n[w];
+        T h[3];
+        for (int a = 0; a < D; a++) h[a] = dl[a][Ip[a][0]];
+        std::vector<T> ta(n, T(0)), tb(n, T(0)), tc(n, T(0)), io(n);
+        T hper = T(1);
+        for (int a = 0; a < D; a++) hper = hper * (a == w ? T(1) : h[a]);
+        for (int j = 0; j < n; j++) {
+            int i = Ip[w][0] + j;
+            if (j != 0) ta[j] = T(1) / (dl[w][i] * du[w][i - 1]);
+            if (j != n - 1) tc[j] = T(1) / (dl[w][i] * du[w][i]);
+            tb[j] = -(ta[j] + tc[j]);
+            io[j] = T(1) / (hper * dl[w][i]);
+        }
+        INSB_TRY(upload<T>(ps, ta, &ps->ta));
+        INSB_TRY(upload<T>(ps, tb, &ps->tb));
+        INSB_TRY(upload<T>(ps, tc, &ps->tc));
+        INSB_TRY(upload<T>(ps, io, &ps->invO));
+        for (int a = 0; a < D; a++) {
+            int cnt = a == w ? 1 : ps->n[a];
+            std::vector<T> e(cnt, T(0));
+            if (a != w) {
+                for (int k = 0; k < cnt; k++) {
+                    if (s.eig[a]) {
+                        e[k] = ((const T *)s.eig[a])[k];
+                        continue;
+                    }
+                    // evaluated in T (pressure.jl:457-458): argument rounded to T first
+                    T arg = (T)k / (T)ps->n[a];
+                    T sp = (T)sinpi_ld((long double)arg);
+                    e[k] = T(-4) * (sp * sp) / (h[a] * h[a]);
+                }
+            }
+            INSB_TRY(upload<T>(ps, e, &ps->eig[a]));
+        }
+        ps->sign = 1;
+    }
+    return 0;
+}
+
+int poisson_create(const insb200_setup_t &s, const int Ip[3][2], int kind, Poisson **out) {
+    Poisson *ps = new Poisson();
+    ps->D = s.D;
+    ps->kind = kind;
+    ps->f64 = s.dtype == INSB200_F64;
+    const int D = s.D;
+    for (int a = 0; a < D; a++) {
+        ps->Ng[a] = s.N[a];
+        ps->n[a] = Ip[a][1] - Ip[a][0];
+        ps->ioff[a] = Ip[a][0];
+        ps->per[a] = s.bc_u[a][0] == INSB200_BC_PERIODIC && s.bc_u[a][1] == INSB200_BC_PERIODIC;
+    }
+    auto fail = [&](const std::string &m) {
+        set_error(m);
+        poisson_destroy(ps);
+        return 1;
+    };
+    // preconditions (utils.jl:4-15, pressure.jl:225-229, :406-435, utils.jl:53)
+    for (int a = 0; a < D; a++) {
+        bool wall = s.bc_u[a][0] == INSB200_BC_DIRICHLET && s.bc_u[a][1] == INSB200_BC_DIRICHLET;
+        if (kind == INSB200_PSOLVER_SPECTRAL && !ps->per[a])
+            return fail("Spectral psolver requires periodic boundary conditions.");
+        if (kind == INSB200_PSOLVER_SPECTRAL && ps->n[a] % 2)
+            return fail("Spectral psolver requires even number of volumes.");
+        if (kind == INSB200_PSOLVER_TRANSFORM && !(ps->per[a] || wall))
+            return fail("psolver_transform: only PeriodicBC / DirichletBC are supported");
+        if (kind == INSB200_PSOLVER_TRANSFORM && ps->n[a] % 2)
+            return fail("Only even grids supported");
+    }
+    if (kind == INSB200_PSOLVER_TRIDIAGONAL) {
+        int w = s.tridiagonal_dir;
+        if (w < 0) {
+            for (int a = 0; a < D && w < 0; a++)
+                if (s.bc_u[a][0] == INSB200_BC_DIRICHLET && s.bc_u[a][1] == INSB200_BC_DIRICHLET) w = a;
+            if (w < 0)
+                return fail("psolver_tridiagonal: no wall-bounded direction (DirichletBC on both sides) found");
+        }
+        if (w >= D || !(s.bc_u[w][0] == INSB200_BC_DIRICHLET && s.bc_u[w][1] == INSB200_BC_DIRICHLET))
+            return fail("psolver_tridiagonal: direction is not wall-bounded (needs DirichletBC on both sides)");
+        for (int a = 0; a < D; a++)
+            if (a != w && !ps->per[a])
+                return fail("psolver_tridiagonal: all directions except the wall-normal one must be periodic");
+        ps->wdir = w;
+    }
+    // uniform spacing where the solver needs it
+    for (int a = 0; a < D; a++) {
+        if (kind == INSB200_PSOLVER_TRIDIAGONAL && a == ps->wdir) continue;
+        double ref = ps->f64 ? ((const double *)s.Delta[a])[Ip[a][0]] : ((const float *)s.Delta[a])[Ip[a][0]];
+        double tol = std::sqrt(ps->f64 ? 2.220446049250313e-16 : 1.1920929e-07);
+        for (int i = Ip[a][0]; i < Ip[a][1]; i++) {
+            double v = ps->f64 ? ((const double *)s.Delta[a])[i] : ((const float *)s.Delta[a])[i];
+            if (std::fabs(v - ref) > tol * std::fmax(std::fabs(v), std::fabs(ref)))
+                return fail("FFT-type psolver requires uniform grid spacing in the transformed directions.");
+        }
+    }
+    // R2C dimension: first periodic one
+    for (int a = 0; a < D && ps->rdim < 0; a++)
+        if (ps->per[a]) ps->rdim = a;
+    for (int a = 0; a < D; a++) {
+        ps->m[a] = (a == ps->rdim) ? ps->n[a] / 2 + 1 : ps->n[a];
+        if (a == ps->rdim && ps->n[a] % 2)
+            return fail("FFT-type psolver requires an even number of volumes in the first periodic direction.");
+        if (!(kind == INSB200_PSOLVER_TRIDIAGONAL && a == ps->wdir))
+            if (!factorize(ps->n[a], ps->radix[a]))
+                return fail("unsupported transform length (prime factors must be in {2,3,5,7,11,13})");
+    }
+    long long pitch = (ps->m[0] + 7) / 8 * 8;
+    ps->wstride[0] = 1;
+    ps->wstride[1] = pitch;
+    ps->wstride[2] = pitch * ps->m[1];
+    size_t esz = ps->f64 ? 16 : 8;
+    size_t wbytes = (size_t)pitch * ps->m[1] * (D == 3 ? ps->m[2] : 1) * esz;
+    if (cudaMalloc(&ps->W, wbytes) != cudaSuccess) return fail("cudaMalloc of the spectral workspace failed");
+    cudaMemset(ps->W, 0, wbytes);
+    ps->bytes += (long long)wbytes;
+    int r = ps->f64 ? build_tables<double>(ps, s, Ip) : build_tables<float>(ps, s, Ip);
+    if (r) {
+        poisson_destroy(ps);
+        return r;
+    }
+    // pass list: R2C(rdim) -> FFT over the other periodic dims -> wall dims; the last forward
+    // pass is fused with the eigenvalue division and its own inverse; then mirror back.
+    std::vector<int> order;
+    if (ps->rdim >= 0) order.push_back(ps->rdim);
+    for (int a = 0; a < D; a++)
+        if (ps->per[a] && a != ps->rdim) order.push_back(a);
+    for (int a = 0; a < D; a++)
+        if (!ps->per[a]) order.push_back(a);
+    int np = (int)order.size();
+    for (int i = 0; i < np; i++) {
+        int a = order[i];
+        bool first = i == 0, last = i == np - 1;
+        Poisson::PassDesc pd{};
+        pd.dim = a;
+        pd.src_real = first;
+        pd.half_out = first && a == ps->rdim;
+        if (last) {
+            pd.op = kind == INSB200_PSOLVER_TRIDIAGONAL ? P_THOMAS : (ps->per[a] ? P_MID_FFT : P_MID_DCT);
+        } else {
+            pd.op = ps->per[a] ? P_FFT_FWD : P_DCT_FWD;
+        }
+        ps->passes.push_back(pd);
+    }
+    for (int i = np - 2; i >= 0; i--) {
+        int a = order[i];
+        Poisson::PassDesc pd{};
+        pd.dim = a;
+        pd.op = ps->per[a] ? P_FFT_INV : P_DCT_INV;
+        pd.dst_real = i == 0;
+        pd.half_in = i == 0 && a == ps->rdim;
+        ps->passes.push_back(pd);
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&ps->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    *out = ps;
+    return 0;
+}
+
+void poisson_destroy(Poisson *p) {
+    if (!p) return;
+    for (void *q : p->owned) cudaFree(q);
+    if (p->W) cudaFree(p->W);
+    delete p;
+}
+
+long long poisson_bytes(const Poisson *p) { return p ? p->bytes : 0; }
+
+template <typename T>
+static int solve_t(Poisson *ps, T *p, Launch L) {
+    const int D = ps->D;
+    long long rs[3] = {1, ps->Ng[0], (long long)ps->Ng[0] * ps->Ng[1]};
+    T *R = p;
+    for (int a = 0; a < D; a++) R += ps->ioff[a] * rs[a];
+    static bool attr_set[2] = {false, false};
+    for (const auto &pd : ps->passes) {
+        PassArgs<T> a{};
+        a.op = pd.op;
+        a.dim = pd.dim;
+        a.n = ps->n[pd.dim];
+        a.D = D;
+        a.src_real = pd.src_real;
+        a.dst_real = pd.dst_real;
+        a.half_out = pd.half_out;
+        a.half_in = pd.half_in;
+        a.W = (Cx<T> *)ps->W;
+        a.R = R;
+        for (int d = 0; d < 3; d++) {
+            a.ws[d] = ps->wstride[d];
+            a.rs[d] = rs[d];
+            a.m[d] = ps->m[d];
+            a.eig[d] = (const T *)ps->eig[d];
+        }
+        // while data is still real (first pass) / already real (last pass) the companion
+        // extents are the real ones
+        if (pd.src_real || pd.dst_real)
+            for (int d = 0; d < 3; d++) a.m[d] = ps->n[d];
+        if (pd.op == P_THOMAS && !pd.src_real) a.m[pd.dim] = ps->n[pd.dim];
+        a.ld = a.n + 1;
+        size_t per_line = (size_t)a.ld * sizeof(Cx<T>) * 2;
+        int tile = 16;
+        while (tile > 1 && tile * per_line > 200 * 1024) tile >>= 1;
+        if (tile * per_line > (size_t)ps->max_smem) {
+            set_error("transform length too large for the shared-memory line pass");
+            return 1;
+        }
+        a.tile = tile;
+        a.nrad = (int)ps->radix[pd.dim].size();
+        for (int i = 0; i < a.nrad; i++) a.radix[i] = ps->radix[pd.dim][i];
+        a.tw = (const Cx<T> *)ps->tw[pd.dim];
+        a.dw = (const Cx<T> *)ps->dw[pd.dim];
+        a.dwi = (const Cx<T> *)ps->dwi[pd.dim];
+        a.sign = (T)ps->sign;
+        a.scale = (T)ps->scale;
+        a.prescale = nullptr;
+        if (ps->kind == INSB200_PSOLVER_TRIDIAGONAL && pd.src_real) {
+            a.prescale = (const T *)ps->invO;
+            a.pdim = ps->wdir;
+        }
+        a.ta = (const T *)ps->ta;
+        a.tb = (const T *)ps->tb;
+        a.tc = (const T *)ps->tc;
+        int da = pd.dim == 0 ? 1 : 0, db = pd.dim == 2 ? 1 : 2;
+        long long nlines = (long long)a.m[da] * (D == 3 ? a.m[db] : 1);
+        unsigned blocks = (unsigned)((nlines + tile - 1) / tile);
+        size_t smem = tile * per_line;
+        int ti = sizeof(T) == 8;
+        if (!attr_set[ti]) {
+            INSB_CUDA(cudaFuncSetAttribute(line_pass_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           ps->max_smem));
+            attr_set[ti] = true;
+        }
+        line_pass_kernel<T><<<blocks, 256, smem, L.stream>>>(a);
+        if (L.counter) ++*L.counter;
+        INSB_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+int poisson_solve(Poisson *ps, void *p, Launch L) {
+    return ps->f64 ? solve_t<double>(ps, (double *)p, L) : solve_t<float>(ps, (float *)p, L);
+}
+
+}  // namespace insb

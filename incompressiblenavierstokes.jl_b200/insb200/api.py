@@ -1,0 +1,576 @@
+"""Python mirror of the reference's operator / solver API for the hot path, bound to
+libinsb200.so.  Function names follow the Julia ones with ``!`` spelled ``_``:
+
+    Setup, scalarfield, vectorfield, apply_bc_u_, apply_bc_p_, apply_bc_temp_,
+    divergence_, scalewithvolume_, pressuregradient_, applypressure_, convection_,
+    diffusion_, navierstokes_, boussinesq_, psolver_spectral, psolver_transform,
+    psolver_tridiagonal, default_psolver, poisson_, project_, RKMethods, LMWray3,
+    create_stepper, timestep_, propose_timestep, solve_unsteady, right_hand_side_,
+    create_right_hand_side, processor, timelogger, fieldsaver
+
+Fields are torch CUDA tensors whose memory is the reference's column-major ghosted
+layout: a scalar has shape ``(N3, N2, N1)`` (``(N2, N1)`` in 2-D) and a vector
+``(D, N3, N2, N1)`` -- i.e. ``numpy_F_array.T``.  torch only provides device memory and
+streams; all arithmetic happens in the CUDA library.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import time
+from fractions import Fraction
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Insb200Error, ParamsStruct, SetupStruct, check, lib
+from .grid import DirichletBC, PeriodicBC, PressureBC, Setup, SymmetricBC  # noqa: F401
+
+_TORCH_DTYPE = {np.float32: torch.float32, np.float64: torch.float64}
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+# ------------------------------------------------------------------------------------
+# plans
+# ------------------------------------------------------------------------------------
+class Plan:
+    """Owns an ``insb200_plan_t`` (device tables, Poisson workspace, stepper caches)."""
+
+    def __init__(self, setup: Setup, psolver=_lib.PSOLVER_NONE, tridiagonal_dir=-1, eig=None):
+        if not torch.cuda.is_available():
+            raise Insb200Error("no CUDA device: insb200 has no CPU fallback")
+        self.setup = setup
+        s = SetupStruct()
+        s.D = setup.D
+        for d in range(3):
+            s.N[d] = setup.N[d] if d < setup.D else 1
+        s.dtype = _lib.F64 if setup.T is np.float64 else _lib.F32
+        uval, tval = setup.bc_constants()
+        self._keep = []
+        for d in range(setup.D):
+            for side in (0, 1):
+                s.bc_u[d][side] = setup.bc_codes[d][side]
+                if setup.bc_temp is not None:
+                    s.bc_temp[d][side] = setup.bc_temp[d][side].code
+                for c in range(3):
+                    s.bc_u_value[d][side][c] = uval[d, side, c]
+                s.bc_temp_value[d][side] = tval[d, side]
+                s.xlims[d][side] = float(setup.xlims[d][side])
+            for name in ("Delta", "DeltaU", "A1", "A2"):
+                arr = np.ascontiguousarray(getattr(setup, name)[d], dtype=setup.T)
+                self._keep.append(arr)
+                getattr(s, name)[d] = arr.ctypes.data
+            if eig is not None and eig[d] is not None:
+                arr = np.ascontiguousarray(eig[d], dtype=setup.T)
+                self._keep.append(arr)
+                s.eig[d] = arr.ctypes.data
+        s.has_temp = int(setup.bc_temp is not None)
+        s.psolver = psolver
+        s.tridiagonal_dir = tridiagonal_dir
+        s.device = torch.cuda.current_device() if setup.device is None else int(setup.device)
+        s.rank, s.world = 0, 1
+        h = C.c_void_p()
+        check(lib().insb200_plan_create(C.byref(s), C.byref(h)))
+        self.h = h
+        self.psolver = lib().insb200_plan_psolver(h)
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                lib().insb200_plan_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    @property
+    def workspace_bytes(self):
+        return lib().insb200_plan_workspace_bytes(self.h)
+
+    @property
+    def launch_count(self):
+        return lib().insb200_launch_count(self.h)
+
+    def profile_enable(self, on=True):
+        check(lib().insb200_profile_enable(self.h, int(on)))
+
+    def profile_read(self):
+        ms = (C.c_double * 5)()
+        cnt = (C.c_longlong * 5)()
+        check(lib().insb200_profile_read(self.h, ms, cnt))
+        names = ("rhs_combine", "divergence", "poisson", "project", "bc")
+        return {n: (ms[i], cnt[i]) for i, n in enumerate(names)}
+
+
+def _base_plan(setup: Setup) -> Plan:
+    if "base" not in setup._plans:
+        setup._plans["base"] = Plan(setup, _lib.PSOLVER_NONE)
+    return setup._plans["base"]
+
+
+def _params(setup, viscosity=0.0, conductivity=0.0, gravity=0.0, gdir=1, dodissipation=False,
+            boussinesq=False, bodyforce=None):
+    p = ParamsStruct()
+    p.viscosity = float(viscosity)
+    p.conductivity = float(conductivity)
+    p.gravity = float(gravity)
+    p.gdir = int(gdir)
+    p.dodissipation = int(bool(dodissipation))
+    p.boussinesq = int(bool(boussinesq))
+    for c in range(3):
+        p.bodyforce[c] = float(bodyforce[c]) if bodyforce is not None and c < len(bodyforce) else 0.0
+    return p
+
+
+# ------------------------------------------------------------------------------------
+# fields (src/initializers.jl:2,5)
+# ------------------------------------------------------------------------------------
+def _dev(setup):
+    return torch.device("cuda", torch.cuda.current_device() if setup.device is None else int(setup.device))
+
+
+def scalarfield(setup):
+    return torch.zeros(tuple(reversed(setup.N)), dtype=_TORCH_DTYPE[setup.T], device=_dev(setup))
+
+
+def vectorfield(setup):
+    return torch.zeros((setup.D,) + tuple(reversed(setup.N)), dtype=_TORCH_DTYPE[setup.T], device=_dev(setup))
+
+
+def to_device(setup, arr):
+    """NumPy array in the reference layout ((N1,N2[,N3][,D]), any order) -> torch CUDA tensor."""
+    a = np.asfortranarray(arr, dtype=setup.T)
+    return torch.from_numpy(np.ascontiguousarray(a.T)).to(_dev(setup))
+
+
+def to_host(t):
+    """torch tensor -> Fortran-ordered NumPy array in the reference layout."""
+    return t.detach().cpu().numpy().T
+
+
+def _chk(setup, t, vector):
+    want = ((setup.D,) if vector else ()) + tuple(reversed(setup.N))
+    if tuple(t.shape) != want or not t.is_contiguous() or not t.is_cuda:
+        raise ValueError(f"expected a contiguous CUDA tensor of shape {want}, got {tuple(t.shape)}")
+    if t.dtype != _TORCH_DTYPE[setup.T]:
+        raise ValueError("dtype mismatch with the setup")
+    return t
+
+
+# ------------------------------------------------------------------------------------
+# boundary conditions and operators
+# ------------------------------------------------------------------------------------
+def apply_bc_u_(u, t, setup, dudt=False, plan=None):
+    pl = plan or _base_plan(setup)
+    check(lib().insb200_apply_bc_u(pl.h, _ptr(_chk(setup, u, True)), float(t), int(dudt), _stream()))
+    return u
+
+
+def apply_bc_p_(p, t, setup, plan=None):
+    pl = plan or _base_plan(setup)
+    check(lib().insb200_apply_bc_p(pl.h, _ptr(_chk(setup, p, False)), _stream()))
+    return p
+
+
+def apply_bc_temp_(temp, t, setup, plan=None):
+    pl = plan or _base_plan(setup)
+    check(lib().insb200_apply_bc_temp(pl.h, _ptr(_chk(setup, temp, False)), float(t), _stream()))
+    return temp
+
+
+def divergence_(div, u, setup):
+    check(lib().insb200_divergence(_base_plan(setup).h, _ptr(_chk(setup, div, False)), _ptr(_chk(setup, u, True)), _stream()))
+    return div
+
+
+def divergence(u, setup):
+    return divergence_(scalarfield(setup), u, setup)
+
+
+def scalewithvolume_(p, setup):
+    check(lib().insb200_scalewithvolume(_base_plan(setup).h, _ptr(_chk(setup, p, False)), _stream()))
+    return p
+
+
+def pressuregradient_(G, p, setup):
+    check(lib().insb200_pressuregradient(_base_plan(setup).h, _ptr(_chk(setup, G, True)), _ptr(_chk(setup, p, False)), _stream()))
+    return G
+
+
+def pressuregradient(p, setup):
+    return pressuregradient_(vectorfield(setup), p, setup)
+
+
+def applypressure_(u, p, setup):
+    check(lib().insb200_applypressure(_base_plan(setup).h, _ptr(_chk(setup, u, True)), _ptr(_chk(setup, p, False)), _stream()))
+    return u
+
+
+def convection_(f, u, setup):
+    check(lib().insb200_convection(_base_plan(setup).h, _ptr(_chk(setup, f, True)), _ptr(_chk(setup, u, True)), _stream()))
+    return f
+
+
+def diffusion_(f, u, setup, viscosity):
+    check(lib().insb200_diffusion(_base_plan(setup).h, _ptr(_chk(setup, f, True)), _ptr(_chk(setup, u, True)), float(viscosity), _stream()))
+    return f
+
+
+def convection(u, setup):
+    return convection_(torch.zeros_like(u), u, setup)
+
+
+def diffusion(u, setup, viscosity):
+    return diffusion_(torch.zeros_like(u), u, setup, viscosity)
+
+
+def navierstokes_(force, state, t, *, setup, cache=None, viscosity, bodyforce=None):
+    """navierstokes! (src/solver.jl:2-6): force["u"] is overwritten."""
+    pr = _params(setup, viscosity=viscosity, bodyforce=bodyforce)
+    check(lib().insb200_rhs(_base_plan(setup).h, _ptr(_chk(setup, state["u"], True)), None,
+                            _ptr(_chk(setup, force["u"], True)), None, C.byref(pr), _stream()))
+    return force
+
+
+def boussinesq_(force, state, t, *, setup, cache=None, viscosity, conductivity, gdir, gravity, dodissipation):
+    """boussinesq! (src/solver.jl:16-35)."""
+    pr = _params(setup, viscosity, conductivity, gravity, gdir, dodissipation, True)
+    check(lib().insb200_rhs(_base_plan(setup).h, _ptr(_chk(setup, state["u"], True)),
+                            _ptr(_chk(setup, state["temp"], False)), _ptr(_chk(setup, force["u"], True)),
+                            _ptr(_chk(setup, force["temp"], False)), C.byref(pr), _stream()))
+    return force
+
+
+# ------------------------------------------------------------------------------------
+# pressure solvers (src/pressure.jl)
+# ------------------------------------------------------------------------------------
+class PSolver:
+    """Callable like the reference closures: ``psolver(p)`` solves in place on the ghosted
+    array and returns it.  Owns the plan that the fused time steppers use."""
+
+    def __init__(self, setup, kind, **kw):
+        self.setup = setup
+        self.plan = Plan(setup, kind, **kw)
+        self.kind = {0: "spectral", 1: "transform", 2: "tridiagonal", -1: "none"}[self.plan.psolver]
+        if self.plan.psolver == _lib.PSOLVER_NONE:
+            raise Insb200Error(
+                "default_psolver would pick psolver_direct for this setup, which is outside "
+                "the B200 hot path (SURVEY.md §2)"
+            )
+
+    def __call__(self, p):
+        check(lib().insb200_psolve(self.plan.h, _ptr(_chk(self.setup, p, False)), _stream()))
+        return p
+
+
+def psolver_spectral(setup, eig=None):
+    return PSolver(setup, _lib.PSOLVER_SPECTRAL, eig=eig)
+
+
+def psolver_transform(setup, eig=None):
+    return PSolver(setup, _lib.PSOLVER_TRANSFORM, eig=eig)
+
+
+def psolver_tridiagonal(setup, dir=None, eig=None):
+    return PSolver(setup, _lib.PSOLVER_TRIDIAGONAL, tridiagonal_dir=-1 if dir is None else int(dir), eig=eig)
+
+
+def default_psolver(setup):
+    return PSolver(setup, _lib.PSOLVER_DEFAULT)
+
+
+def poisson_(psolver, f):
+    return psolver(f)
+
+
+def project_(u, setup, *, psolver, p):
+    check(lib().insb200_project(psolver.plan.h, _ptr(_chk(setup, u, True)), _ptr(_chk(setup, p, False)), _stream()))
+    return u
+
+
+def project(u, setup, *, psolver):
+    return project_(u.clone(), setup, psolver=psolver, p=scalarfield(setup))
+
+
+# ------------------------------------------------------------------------------------
+# time stepping (src/time_steppers/*.jl)
+# ------------------------------------------------------------------------------------
+class ExplicitRungeKuttaMethod:
+    def __init__(self, A, b, c, r, T=np.float64):
+        self.A, self.b, self.c, self.r, self.T = A, b, c, r, np.dtype(T).type
+
+
+def runge_kutta_method(A, b, c, r, T=np.float64):
+    """methods.jl:71-89: convert to T, then shift the tableau."""
+    T = np.dtype(T).type
+    A = np.array([[float(v) for v in row] for row in A], dtype=np.float64)
+    b = np.array([float(v) for v in b], dtype=np.float64)
+    c = np.array([float(v) for v in c], dtype=np.float64)
+    s = A.shape[0]
+    if not (s == A.shape[1] == len(b) == len(c)):
+        raise ValueError("A, b, and c must have the same sizes")
+    if not np.allclose(np.triu(A), 0):
+        raise ValueError("Only explicit Runge-Kutta methods are supported")
+    A, b, c = A.astype(T), b.astype(T), c.astype(T)
+    return ExplicitRungeKuttaMethod(np.vstack([A[1:, :], b[None, :]]), b, np.append(c[1:], T(1)), T(r), T)
+
+
+class RKMethods:
+    """The tableaus of src/time_steppers/RKMethods.jl used on the hot path (any explicit
+    tableau can be passed through ``runge_kutta_method``)."""
+
+    @staticmethod
+    def FE11(T=np.float64):
+        return runge_kutta_method([[0]], [1], [0], 1, T)
+
+    @staticmethod
+    def RK44(T=np.float64):
+        h = Fraction(1, 2)
+        A = [[0, 0, 0, 0], [h, 0, 0, 0], [0, h, 0, 0], [0, 0, 1, 0]]
+        return runge_kutta_method(A, [Fraction(1, 6), Fraction(1, 3), Fraction(1, 3), Fraction(1, 6)],
+                                  [sum(r) for r in A], 0, T)
+
+    @staticmethod
+    def Wray3(T=np.float64):
+        A = [[Fraction(0)] * 3 for _ in range(3)]
+        A[1][0] = Fraction(8, 15)
+        A[2][0] = Fraction(8, 15) - Fraction(17, 60)
+        A[2][1] = Fraction(5, 12)
+        b = [Fraction(8, 15) - Fraction(17, 60), Fraction(0), Fraction(3, 4)]
+        return runge_kutta_method(A, b, [Fraction(0), A[1][0], A[2][0] + A[2][1]], 0, T)
+
+    @staticmethod
+    def RK33C2(T=np.float64):
+        A = [[0, 0, 0], [Fraction(2, 3), 0, 0], [Fraction(1, 3), Fraction(1, 3), 0]]
+        return runge_kutta_method(A, [Fraction(1, 4), 0, Fraction(3, 4)], [0, Fraction(2, 3), Fraction(2, 3)], 0, T)
+
+
+class LMWray3:
+    def __init__(self, T=np.float64):
+        self.T = np.dtype(T).type
+
+
+def create_stepper(method, *, setup, psolver, state, t, n=0):
+    return dict(setup=setup, psolver=psolver, state=state, t=t, n=n)
+
+
+def get_state(stepper):
+    out = dict(stepper["state"])
+    out["t"], out["n"] = stepper["t"], stepper["n"]
+    return out
+
+
+def _force_params(force, setup, params):
+    params = dict(params or {})
+    if force is navierstokes_:
+        return _params(setup, viscosity=params["viscosity"], bodyforce=params.get("bodyforce"))
+    if force is boussinesq_:
+        return _params(setup, params["viscosity"], params["conductivity"], params["gravity"], params["gdir"],
+                       params["dodissipation"], True, params.get("bodyforce"))
+    raise NotImplementedError("only the built-in navierstokes_/boussinesq_ forces run fused on the B200 path")
+
+
+def _coef_dtype(method_T, dt):
+    dt_T = np.dtype(type(dt)).type if isinstance(dt, np.floating) else np.float64
+    return _lib.F64 if np.result_type(method_T, dt_T) == np.float64 else _lib.F32
+
+
+def timestep_(method, force, stepper, dt, *, params=None, ode_cache=None, force_cache=None):
+    """timestep! -- one fused library call per step."""
+    setup, psolver, state = stepper["setup"], stepper["psolver"], stepper["state"]
+    pr = _force_params(force, setup, params)
+    u = _chk(setup, state["u"], True)
+    temp = _chk(setup, state["temp"], False) if "temp" in state and pr.boussinesq else None
+    t = stepper["t"]
+    if isinstance(method, LMWray3):
+        check(lib().insb200_step_lmwray3(psolver.plan.h, _ptr(u), _ptr(temp), float(t), float(dt), C.byref(pr), _stream()))
+    else:
+        s = len(method.b)
+        A = (C.c_double * (s * s))(*[float(v) for v in np.asarray(method.A).reshape(-1)])
+        c = (C.c_double * s)(*[float(v) for v in method.c])
+        check(lib().insb200_step_rk(psolver.plan.h, A, c, s, _coef_dtype(method.T, dt), _ptr(u), _ptr(temp),
+                                    float(t), float(dt), C.byref(pr), _stream()))
+    return create_stepper(method, setup=setup, psolver=psolver, state=state, t=t + dt, n=stepper["n"] + 1)
+
+
+def propose_timestep(force, state, setup, params, plan=None):
+    pr = _force_params(force, setup, params)
+    out = C.c_double()
+    pl = plan or _base_plan(setup)
+    check(lib().insb200_cfl(pl.h, _ptr(_chk(setup, state["u"], True)), C.byref(pr), C.byref(out), _stream()))
+    return setup.T(out.value)
+
+
+def maxabs(u, setup):
+    out = C.c_double()
+    check(lib().insb200_maxabs(_base_plan(setup).h, _ptr(u), C.byref(out), _stream()))
+    return out.value
+
+
+# ------------------------------------------------------------------------------------
+# processors (src/processors.jl): the call-back boundary of solve_unsteady
+# ------------------------------------------------------------------------------------
+class Observable:
+    def __init__(self, value):
+        self._v, self._l = value, []
+
+    def on(self, f):
+        self._l.append(f)
+        return f
+
+    @property
+    def value(self):
+        return self._v
+
+    @value.setter
+    def value(self, v):
+        self._v = v
+        for f in self._l:
+            f(v)
+
+
+class processor:
+    def __init__(self, initialize, finalize=lambda initialized, state: initialized):
+        self.initialize, self.finalize = initialize, finalize
+
+
+def timelogger(setup, nupdate=1, out=None):
+    """processors.jl:45-80: iteration, t, Δt, umax, wall time per iteration."""
+    log = [] if out is None else out
+
+    def initialize(state):
+        told = [state.value["t"]]
+        wold = [time.time()]
+
+        def cb(st):
+            if st["n"] % nupdate:
+                return
+            now = time.time()
+            log.append(dict(n=st["n"], t=float(st["t"]), dt=float(st["t"] - told[0]) / nupdate,
+                            umax=maxabs(st["u"], setup), itertime=(now - wold[0]) / nupdate))
+            told[0], wold[0] = st["t"], now
+
+        state.on(cb)
+        return log
+
+    return processor(initialize)
+
+
+def fieldsaver(setup, nupdate=1):
+    """processors.jl:234-243: host copies of the state every nupdate steps."""
+
+    def initialize(state):
+        states = []
+
+        def cb(st):
+            if st["n"] % nupdate == 0:
+                states.append({k: (to_host(v).copy() if torch.is_tensor(v) else v) for k, v in st.items()})
+
+        state.on(cb)
+        cb(state.value)
+        return states
+
+    return processor(initialize)
+
+
+def solve_unsteady(*, setup, tlims, start, force=navierstokes_, docopy=True, method=None, psolver=None,
+                   dt=None, dt_min=None, cfl=None, n_adapt_dt=1, processors=None, params):
+    """solve_unsteady (src/solver.jl:77-149)."""
+    T = setup.T
+    method = method if method is not None else LMWray3(T)
+    psolver = psolver if psolver is not None else default_psolver(setup)
+    cfl = T(0.9) if cfl is None else cfl
+    tstart, tend = tlims
+    state = {k: (v.clone() if docopy else v) for k, v in start.items()}
+    stepper = create_stepper(method, setup=setup, psolver=psolver, state=state, t=tstart)
+    obs = Observable(get_state(stepper))
+    processors = processors or {}
+    initialized = {k: p.initialize(obs) for k, p in processors.items()}
+    if dt is None:
+        while stepper["t"] < tend:
+            if stepper["n"] % n_adapt_dt == 0:
+                dt = cfl * propose_timestep(force, stepper["state"], setup, params, plan=psolver.plan)
+                if dt_min is not None:
+                    dt = max(dt, dt_min)
+                if dt < 1e-10 or dt > 100 or np.isnan(dt):
+                    import warnings
+
+                    warnings.warn(f"Proposed time step {dt} is out of bounds. Stopping simulation.")
+                    break
+            dt_step = min(dt, tend - stepper["t"])
+            stepper = timestep_(method, force, stepper, dt_step, params=params)
+            obs.value = get_state(stepper)
+    else:
+        nstep = int(round((tend - tstart) / dt))
+        dt = (tend - tstart) / nstep
+        for _ in range(nstep):
+            stepper = timestep_(method, force, stepper, dt, params=params)
+            obs.value = get_state(stepper)
+    outputs = {k: processors[k].finalize(initialized[k], obs) for k in processors}
+    out = dict(stepper["state"])
+    out["t"] = stepper["t"]
+    return out, outputs
+
+
+# ------------------------------------------------------------------------------------
+# SciML right-hand side (src/sciml.jl)
+# ------------------------------------------------------------------------------------
+def right_hand_side_(dudt, u, params_ref, t):
+    setup, psolver, viscosity = params_ref
+    pr = _params(setup, viscosity=viscosity)
+    check(lib().insb200_right_hand_side(psolver.plan.h, _ptr(_chk(setup, dudt, True)), _ptr(_chk(setup, u, True)),
+                                        float(t), C.byref(pr), _stream()))
+    return None
+
+
+def create_right_hand_side(setup, psolver):
+    def right_hand_side(u, params, t):
+        dudt = torch.empty_like(u)
+        right_hand_side_(dudt, u, (setup, psolver, params["viscosity"]), t)
+        return dudt
+
+    return right_hand_side
+
+
+# ------------------------------------------------------------------------------------
+# initial conditions (src/initializers.jl:45-87): sample on the host, project on the device
+# ------------------------------------------------------------------------------------
+def velocityfield(setup, ufunc, t=0.0, *, psolver=None, doproject=True):
+    D = setup.D
+    u = np.zeros(setup.N + (D,), dtype=setup.T, order="F")
+    for a in range(D):
+        xs = []
+        for b in range(D):
+            lo, hi = setup.Iu[a][b]
+            shape = [1] * D
+            shape[b] = hi - lo
+            xs.append(setup.xu[a][b][lo:hi].reshape(shape))
+        u[setup.slices(setup.Iu[a]) + (a,)] = np.asarray(ufunc(a, *xs), dtype=setup.T)
+    ud = to_device(setup, u)
+    apply_bc_u_(ud, t, setup)
+    if doproject:
+        psolver = psolver if psolver is not None else default_psolver(setup)
+        ud = project(ud, setup, psolver=psolver)
+        apply_bc_u_(ud, t, setup)
+    return ud
+
+
+def temperaturefield(setup, tempfunc, t=0.0):
+    D = setup.D
+    temp = np.zeros(setup.N, dtype=setup.T, order="F")
+    xs = []
+    for b in range(D):
+        lo, hi = setup.Ip[b]
+        shape = [1] * D
+        shape[b] = hi - lo
+        xs.append(setup.xp[b][lo:hi].reshape(shape))
+    temp[setup.slices(setup.Ip)] = np.asarray(tempfunc(*xs), dtype=setup.T)
+    td = to_device(setup, temp)
+    return apply_bc_temp_(td, t, setup)
