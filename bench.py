@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the insb200 hot path.
+
+Metric (BASELINE.json): cell-updates/s per RK44 step on the TaylorGreenVortex3D workload,
+reported with the fraction of the measured HBM roofline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--n 512] [--dtype f32|f64]
+    python bench.py --impl reference ...     # CPU oracle ("port" of the reference schedule)
+
+One "step" = one full RK44 time step (4 right-hand sides, 4 pressure projections) of the
+whole grid.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "incompressiblenavierstokes.jl_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "cell-updates/s per RK44 step (TGV3D N^3)"
+UNIT = "cell-updates/s"
+NU = 1e-3
+
+
+def tgv3d_u(dim, x, y, z):
+    """examples/TaylorGreenVortex3D.jl:38-45"""
+    if dim == 0:
+        return np.sin(2 * np.pi * x) * np.cos(2 * np.pi * y) * np.sin(2 * np.pi * z) / 2
+    if dim == 1:
+        return -np.cos(2 * np.pi * x) * np.sin(2 * np.pi * y) * np.sin(2 * np.pi * z) / 2
+    return 0 * x + 0 * y + 0 * z
+
+
+def fixed_dt(n):
+    # 0.5 x propose_timestep at t = 0 (diffusive limit h^2/(6 nu) vs h/|u|max = 2h)
+    h = 1.0 / n
+    return 0.5 * min(h * h / NU / 6, 2 * h)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [v.strip() for v in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------
+# CPU arm: the oracle executing the reference's unfused schedule
+# ----------------------------------------------------------------------------------------
+def cpu_steps(n, dtype, steps, warmup):
+    import oracle as O
+    from oracle import initializers as oini, pressure as opr, timestep as ots
+
+    cores = len(os.sched_getaffinity(0))
+    opr.WORKERS = cores
+    T = np.float32 if dtype == "f32" else np.float64
+    x = tuple(np.linspace(0.0, 1.0, n + 1).astype(T) for _ in range(3))
+    so = O.Setup(x, {"u": ((O.PeriodicBC(), O.PeriodicBC()),) * 3})
+    ps = opr.psolver_spectral(so)
+    u0 = oini.velocityfield(so, tgv3d_u, psolver=ps)
+    m = ots.RK44(T)
+    st = {"u": u0}
+    cache = ots.get_cache(m, st, so)
+    sp = ots.create_stepper(m, so, ps, st, 0.0)
+    f = ots.make_navierstokes(so, NU)
+    dt = T(fixed_dt(n))
+    for _ in range(warmup):
+        sp = ots.timestep_(m, f, sp, dt, cache)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        sp = ots.timestep_(m, f, sp, dt, cache)
+        times.append(time.perf_counter() - t0)
+    assert np.all(np.isfinite(sp["state"]["u"]))
+    return float(np.sum(times)), cores
+
+
+def run_reference(args):
+    n = args.ref_n
+    tot, cores = cpu_steps(n, args.dtype, args.steps, min(args.warmup, 1))
+    val = n**3 * args.steps / tot
+    sample = f"TGV3D {n}^3 {args.dtype} RK44, {args.steps} steps, NumPy oracle executing the reference's unfused schedule"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": f"TaylorGreenVortex3D {args.n}^3 periodic {args.dtype} RK44 psolver_spectral",
+                   "sample": f"{n}^3 grid (bounded CPU sample of the same workload)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl")
+    import insb200 as I
+
+    T = np.float32 if args.dtype == "f32" else np.float64
+    w = 4 if args.dtype == "f32" else 8
+    n = args.n
+    x = tuple(np.linspace(0.0, 1.0, n + 1).astype(T) for _ in range(3))
+    sg = I.Setup(x, {"u": ((I.PeriodicBC(), I.PeriodicBC()),) * 3})
+    ps = I.psolver_spectral(sg)
+    u = I.velocityfield(sg, tgv3d_u, psolver=ps)
+    method = I.RKMethods.RK44(T)
+    params = dict(viscosity=NU)
+    dt = float(fixed_dt(n))
+    stepper = I.create_stepper(method, setup=sg, psolver=ps, state={"u": u}, t=0.0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        stepper = I.timestep_(method, I.navierstokes_, stepper, dt, params=params)
+    barrier()
+    ps.plan.profile_enable(True)
+    ps.plan.profile_read()
+    l0 = ps.plan.launch_count
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        stepper = I.timestep_(method, I.navierstokes_, stepper, dt, params=params)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ps.plan.launch_count - l0
+    prof = ps.plan.profile_read()
+    ps.plan.profile_enable(False)
+    if world > 1:
+        tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    umax = I.maxabs(stepper["state"]["u"], sg)
+    assert np.isfinite(umax) and 0 < umax < 10, f"solution blew up: max|u| = {umax}"
+
+    cells = n**3 * world  # replicas until the slab decomposition lands
+    value = cells * args.steps / (ms * 1e-3)
+    peak, peak_src = peaks()
+
+    # ---- roofline of the dominant kernel group (DESIGN.md "Algorithmic bytes") ----
+    # per launch and per cell: stage kernel 48w/4, divergence 4w, Poisson pass 2w (5 per solve),
+    # projection 7w; bytes = count * w * n^3
+    alg = {"rhs_combine": 12.0, "divergence": 4.0, "poisson": 10.0, "project": 7.0}
+    dom = max(alg, key=lambda k: prof[k][0])
+    d_ms, d_cnt = prof[dom]
+    per = d_ms / max(d_cnt, 1)
+    achieved = alg[dom] * w * n**3 / (per * 1e-3) / 1e9
+    groups = {k: {"ms_per_step": prof[k][0] / args.steps, "launch_groups": prof[k][1],
+                  "GBps": (alg[k] * w * n**3 / (prof[k][0] / max(prof[k][1], 1) * 1e-3) / 1e9) if k in alg and prof[k][0] > 0 else None}
+              for k in prof}
+    step_bytes = 120.0 * w * n**3
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_cell": alg[dom] * w,
+                "step": {"achieved": step_bytes / (ms / args.steps * 1e-3) / 1e9,
+                         "frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak,
+                         "algorithmic_bytes_per_cell_update": 120.0 * w},
+                "groups": groups}
+
+    # ---- end to end through the C ABI with HOST buffers (pinned), every step H2D + D2H ----
+    e2e = None
+    if rank == 0 and not args.no_e2e:
+        import ctypes as C
+
+        from insb200._lib import lib, check
+        from insb200.api import _params, _coef_dtype
+
+        uh = torch.empty(u.shape, dtype=u.dtype, pin_memory=True)
+        uh.copy_(stepper["state"]["u"])
+        s = len(method.b)
+        A = (C.c_double * (s * s))(*[float(v) for v in np.asarray(method.A).reshape(-1)])
+        cc = (C.c_double * s)(*[float(v) for v in method.c])
+        pr = _params(sg, viscosity=NU)
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        ke = max(2, min(args.steps, 5))
+
+        def host_step(t):
+            check(lib().insb200_step_rk_host(ps.plan.h, A, cc, s, _coef_dtype(method.T, T(dt)),
+                                             C.c_void_p(uh.data_ptr()), None, t, dt, 1, C.byref(pr), st))
+
+        host_step(0.0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(ke):
+            host_step(i * dt)
+        torch.cuda.synchronize()
+        el = time.perf_counter() - t0
+        nbytes = uh.numel() * uh.element_size()
+        e2e = {"value": n**3 * ke / el, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+               "steps": ke, "ms_per_step": 1e3 * el / ke,
+               "note": "insb200_step_rk_host: pinned host u -> device, one fused RK44 step, device -> host, every step"}
+        assert np.isfinite(float(uh.abs().max()))
+
+    # ---- CPU baseline beside it (bounded sample) ----
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        tot, cores = cpu_steps(args.ref_n, args.dtype, 2, 1)
+        cpu = {"value": args.ref_n**3 * 2 / tot, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"TGV3D {args.ref_n}^3 {args.dtype} RK44, 2 steps after 1 warm-up, NumPy oracle executing "
+                         f"the reference's unfused schedule (scipy.fft workers={cores}, NumPy stencils single-threaded)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": f"TaylorGreenVortex3D {n}^3 periodic {args.dtype} RK44 psolver_spectral",
+                       "n": n, "nu": NU, "dt": dt, "method": f"RK44(T={args.dtype})",
+                       "l2": f"working set {14 * w * (n + 2)**3 / 1e9:.1f} GB >> 126 MB L2 (no flush needed)",
+                       "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (slab decomposition pending)"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="insb200", choices=["insb200", "reference"])
+    ap.add_argument("--n", type=int, default=512)
+    ap.add_argument("--ref-n", type=int, default=128, help="grid of the bounded CPU sample")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) == 0:
+            run_reference(args)
+        return
+    run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

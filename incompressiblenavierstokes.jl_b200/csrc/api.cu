@@ -338,6 +338,10 @@ int step_rk_t(insb200_plan *pl, const double *A, const double *c, int s, int coe
     if (!fast) INSB_TRY(ensure_k(pl, s - 1, bouss));
     size_t vb = (size_t)pl->ncell * pl->D * pl->esz, sb = (size_t)pl->ncell * pl->esz;
 
+    if (s == 1) {  // single-stage methods go through V[0]; carry the never-written cells along
+        INSB_CUDA(cudaMemcpyAsync(pl->V[0], U, vb, cudaMemcpyDeviceToDevice, L.stream));
+        if (bouss) INSB_CUDA(cudaMemcpyAsync(pl->TV[0], TU, sb, cudaMemcpyDeviceToDevice, L.stream));
+    }
     const T *src = U;
     const T *tsrc = TU;
     for (int i = 0; i < s; i++) {

@@ -16,8 +16,11 @@ from .grid import (  # noqa: F401
 def __getattr__(name):
     # the API layer needs torch; import it lazily so that `import insb200` (symbol checks,
     # grid set-up) works without touching CUDA
-    from . import api
+    import importlib
 
+    if name == "api":
+        return importlib.import_module(".api", __name__)
+    api = importlib.import_module(".api", __name__)
     try:
         return getattr(api, name)
     except AttributeError:
