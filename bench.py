@@ -183,7 +183,7 @@ def run_gpu(args):
     u = I.velocityfield(sg, tgv3d_u, psolver=ps)
     method = I.RKMethods.RK44(T)
     params = dict(viscosity=NU)
-    dt = float(fixed_dt(n))
+    dt = T(fixed_dt(n))  # eltype(u): the stage combine then stays in the field type
     stepper = I.create_stepper(method, setup=sg, psolver=ps, state={"u": u}, t=0.0)
 
     def barrier():
@@ -261,14 +261,14 @@ def run_gpu(args):
         ke = max(2, min(args.steps, 5))
 
         def host_step(t):
-            check(lib().insb200_step_rk_host(ps.plan.h, A, cc, s, _coef_dtype(method.T, T(dt)),
-                                             C.c_void_p(uh.data_ptr()), None, t, dt, 1, C.byref(pr), st))
+            check(lib().insb200_step_rk_host(ps.plan.h, A, cc, s, _coef_dtype(method.T, dt),
+                                             C.c_void_p(uh.data_ptr()), None, float(t), float(dt), 1, C.byref(pr), st))
 
         host_step(0.0)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for i in range(ke):
-            host_step(i * dt)
+            host_step(i * float(dt))
         torch.cuda.synchronize()
         el = time.perf_counter() - t0
         nbytes = uh.numel() * uh.element_size()
@@ -291,7 +291,7 @@ def run_gpu(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": f"TaylorGreenVortex3D {n}^3 periodic {args.dtype} RK44 psolver_spectral",
-                       "n": n, "nu": NU, "dt": dt, "method": f"RK44(T={args.dtype})",
+                       "n": n, "nu": NU, "dt": float(dt), "method": f"RK44(T={args.dtype})",
                        "l2": f"working set {14 * w * (n + 2)**3 / 1e9:.1f} GB >> 126 MB L2 (no flush needed)",
                        "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (slab decomposition pending)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,

@@ -11,31 +11,13 @@
 // (pressure.jl:351,378) is fused into the first/last pass.
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 
 #include "internal.h"
+#include "cx.cuh"
+#include "fft_fast.h"
 
 namespace insb {
-
-template <typename T>
-struct Cx {
-    T x, y;
-};
-template <typename T>
-__host__ __device__ __forceinline__ Cx<T> cmul(Cx<T> a, Cx<T> b) {
-    return Cx<T>{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
-}
-template <typename T>
-__host__ __device__ __forceinline__ Cx<T> cadd(Cx<T> a, Cx<T> b) {
-    return Cx<T>{a.x + b.x, a.y + b.y};
-}
-template <typename T>
-__host__ __device__ __forceinline__ Cx<T> csub(Cx<T> a, Cx<T> b) {
-    return Cx<T>{a.x - b.x, a.y - b.y};
-}
-template <typename T>
-__host__ __device__ __forceinline__ Cx<T> cconj(Cx<T> a) {
-    return Cx<T>{a.x, -a.y};
-}
 
 enum PassOp {
     P_FFT_FWD = 0,
@@ -429,6 +411,8 @@ struct Poisson {
     };
     std::vector<PassDesc> passes;
     int max_smem = 0;
+    bool fast = false;  // power-of-two all-periodic path (fft_fast.cu)
+    int tile = 8;
 };
 
 static bool factorize(int n, std::vector<int> &rad) {
@@ -697,6 +681,11 @@ int poisson_create(const insb200_setup_t &s, const int Ip[3][2], int kind, Poiss
         pd.half_in = i == 0 && a == ps->rdim;
         ps->passes.push_back(pd);
     }
+    ps->fast = kind == INSB200_PSOLVER_SPECTRAL && getenv("INSB200_GENERIC_FFT") == nullptr;
+    for (int a = 0; a < D; a++) ps->fast = ps->fast && fast_fft_supported(ps->n[a]);
+    ps->tile = ps->f64 ? 4 : 8;
+    if (const char *e = getenv("INSB200_FFT_TILE")) ps->tile = atoi(e) > 0 ? atoi(e) : ps->tile;
+    if (ps->tile > 8) ps->tile = 8;
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&ps->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
@@ -719,6 +708,29 @@ static int solve_t(Poisson *ps, T *p, Launch L) {
     long long rs[3] = {1, ps->Ng[0], (long long)ps->Ng[0] * ps->Ng[1]};
     T *R = p;
     for (int a = 0; a < D; a++) R += ps->ioff[a] * rs[a];
+    if (ps->fast) {
+        FastGeom g;
+        g.D = D;
+        for (int d = 0; d < 3; d++) {
+            g.n[d] = ps->n[d];
+            g.ws[d] = ps->wstride[d];
+            g.rs[d] = rs[d];
+        }
+        g.m0p = (int)ps->wstride[1];
+        const T factor = (T)(ps->sign * ps->scale);
+        const T *e0 = (const T *)ps->eig[0], *e1 = (const T *)ps->eig[1], *e2 = (const T *)ps->eig[2];
+        const int tl = ps->tile;
+        INSB_TRY(fast_pass<T>(3, ps->n[0], R, ps->W, g, 0, ps->tw[0], e0, e1, e2, factor, tl, L));
+        if (D == 3) {
+            INSB_TRY(fast_pass<T>(0, ps->n[1], R, ps->W, g, 1, ps->tw[1], e0, e1, e2, factor, tl, L));
+            INSB_TRY(fast_pass<T>(2, ps->n[2], R, ps->W, g, 2, ps->tw[2], e0, e1, e2, factor, tl, L));
+            INSB_TRY(fast_pass<T>(1, ps->n[1], R, ps->W, g, 1, ps->tw[1], e0, e1, e2, factor, tl, L));
+        } else {
+            INSB_TRY(fast_pass<T>(2, ps->n[1], R, ps->W, g, 1, ps->tw[1], e0, e1, e2, factor, tl, L));
+        }
+        INSB_TRY(fast_pass<T>(4, ps->n[0], R, ps->W, g, 0, ps->tw[0], e0, e1, e2, factor, tl, L));
+        return 0;
+    }
     static bool attr_set[2] = {false, false};
     for (const auto &pd : ps->passes) {
         PassArgs<T> a{};
