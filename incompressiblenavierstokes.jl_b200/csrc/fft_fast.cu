@@ -13,6 +13,8 @@
 //   y: strided forward FFT        z: strided forward FFT + divide + inverse FFT
 //   y: strided inverse FFT        x: two half spectra -> two real rows (C2R), writes view(p, Ip)
 // i.e. 5 passes of one read + one write each (10 w per cell per solve).
+#include <cstdlib>
+
 #include "cx.cuh"
 #include "fft_fast.h"
 
@@ -83,7 +85,22 @@ struct LineSmem {
     T *re[2], *im[2];
 };
 
-template <typename T, int N, bool INV, int S>
+// Shared-memory index of element p for the exchange that follows a stage with (NS, R).
+// LFAST kernels (lanes run over lines): p + p/8.  TFAST kernels (lanes run along the line):
+// pad PADW words per BANKS elements, PADW chosen so that both the strided writes of this
+// exchange and the unit-stride reads are bank-conflict free.
+template <typename T, bool TFAST, int NS, int R>
+__device__ __forceinline__ int sidx(int p) {
+    if constexpr (!TFAST) {
+        return p + (p >> 3);
+    } else {
+        constexpr int BANKS = 128 / (int)sizeof(T);
+        constexpr int PADW = (NS * R >= BANKS) ? (BANKS / R > 0 ? BANKS / R : 1) : NS;
+        return p + PADW * (p / BANKS);
+    }
+}
+
+template <typename T, int N, bool INV, int S, bool TFAST = false>
 __device__ __forceinline__ void fft_stages(Cx<T> (&v)[8], int t, const LineSmem<T> &sm,
                                            const Cx<T> *__restrict__ tw, int &exch) {
     using Sh = FftShape<N>;
@@ -133,7 +150,7 @@ __device__ __forceinline__ void fft_stages(Cx<T> (&v)[8], int t, const LineSmem<
             int j0 = (j / NS) * (NS * R) + (j & (NS - 1));
 #pragma unroll
             for (int r = 0; r < R; r++) {
-                int q = phys(j0 + r * NS);
+                int q = sidx<T, TFAST, NS, R>(j0 + r * NS);
                 re[q] = v[b + B * r].x;
                 im[q] = v[b + B * r].y;
             }
@@ -141,11 +158,11 @@ __device__ __forceinline__ void fft_stages(Cx<T> (&v)[8], int t, const LineSmem<
         __syncthreads();
 #pragma unroll
         for (int m = 0; m < 8; m++) {
-            int q = phys(t + P * m);
+            int q = sidx<T, TFAST, NS, R>(t + P * m);
             v[m] = Cx<T>{re[q], im[q]};
         }
         exch++;
-        fft_stages<T, N, INV, S + 1>(v, t, sm, tw, exch);
+        fft_stages<T, N, INV, S + 1, TFAST>(v, t, sm, tw, exch);
     }
 }
 
@@ -164,8 +181,10 @@ __device__ __forceinline__ LineSmem<T> line_smem(T *base, int l, int L, int LS) 
 // strided pass along dim `tdim` (1 or 2): MODE 0 forward, 1 inverse, 2 forward+divide+inverse
 // grid: x = tiles of L lines along kx, y = index along the remaining dimension
 // ----------------------------------------------------------------------------------------
+// MODE 3 = MODE 2 compiled without the two-blocks-per-SM register cap (selected at run time
+// with INSB200_FFT_MID_UNCAPPED=1 for A/B measurements)
 template <typename T, int N, int MODE>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(512, (sizeof(T) == 4 && MODE != 3) ? 2 : 1)
     fft_strided_kernel(Cx<T> *__restrict__ W, FastGeom g, int tdim, int L, int LS,
                        const Cx<T> *__restrict__ tw, const T *__restrict__ e0, const T *__restrict__ e1,
                        const T *__restrict__ e2, T factor) {
@@ -181,11 +200,11 @@ __global__ void __launch_bounds__(512)
     Cx<T> v[8];
 #pragma unroll
     for (int m = 0; m < 8; m++) v[m] = base[(long long)(t + P * m) * sd];
-    int exch = 0;
-    if (MODE == 0 || MODE == 2) fft_stages<T, N, false, 0>(v, t, sm, tw, exch);
-    if (MODE == 2) {
+    T f[8];
+    if (MODE >= 2) {
         // phat = -phat / ((ax + ay) + az), phat[1] = 0 (pressure.jl:360-372); `factor` carries
-        // the sign and the 1/prod(Np) of the inverse transform
+        // the sign and the 1/prod(Np) of the inverse transform.  Evaluated while the loads
+        // above are in flight.
 #pragma unroll
         for (int m = 0; m < 8; m++) {
             int k = t + P * m;
@@ -199,11 +218,16 @@ __global__ void __launch_bounds__(512)
                 den = e0[kx] + e1[k];
                 zero = (kx | k) == 0;
             }
-            T f = zero ? T(0) : factor / den;
-            v[m] = Cx<T>{v[m].x * f, v[m].y * f};
+            f[m] = zero ? T(0) : factor / den;
         }
     }
-    if (MODE == 1 || MODE == 2) fft_stages<T, N, true, 0>(v, t, sm, tw, exch);
+    int exch = 0;
+    if (MODE == 0 || MODE >= 2) fft_stages<T, N, false, 0>(v, t, sm, tw, exch);
+    if (MODE >= 2) {
+#pragma unroll
+        for (int m = 0; m < 8; m++) v[m] = Cx<T>{v[m].x * f[m], v[m].y * f[m]};
+    }
+    if (MODE >= 1) fft_stages<T, N, true, 0>(v, t, sm, tw, exch);
 #pragma unroll
     for (int m = 0; m < 8; m++) base[(long long)(t + P * m) * sd] = v[m];
 }
@@ -231,10 +255,11 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int m = 0; m < 8; m++) v[m] = Cx<T>{ra[t + P * m], rb[t + P * m]};
     int exch = 0;
-    fft_stages<T, N, false, 0>(v, t, sm, tw, exch);
+    fft_stages<T, N, false, 0, true>(v, t, sm, tw, exch);
     // exchange once more to reach Z[N-k]
     T *re = sm.re[exch & 1], *im = sm.im[exch & 1];
     (void)NST;
+    auto phys = [](int p) { return sidx<T, true, 1, 1>(p); };
 #pragma unroll
     for (int m = 0; m < 8; m++) {
         int p = phys(t + P * m);
@@ -291,7 +316,7 @@ __global__ void __launch_bounds__(256)
         }
     }
     int exch = 0;
-    fft_stages<T, N, true, 0>(v, t, sm, tw, exch);
+    fft_stages<T, N, true, 0, true>(v, t, sm, tw, exch);
     if (valid) {
         T *ra = R + (long long)(2 * jp) * g.rs[1] + (long long)kz * g.rs[2];
         T *rb = ra + g.rs[1];
@@ -325,12 +350,10 @@ static int fast_pass_n(int kind, T *R, Cx<T> *W, const FastGeom &g, int tdim, co
         int LS = line_stride(N, Lt, sizeof(T));
         size_t smem = (size_t)4 * Lt * LS * sizeof(T);
         dim3 grid(g.m0p / Lt, g.D == 3 ? g.n[tdim == 1 ? 2 : 1] : 1);
+        static const bool uncapped = getenv("INSB200_FFT_MID_UNCAPPED") != nullptr;
         auto kern = kind == 0 ? fft_strided_kernel<T, N, 0> : kind == 1 ? fft_strided_kernel<T, N, 1>
-                                                                       : fft_strided_kernel<T, N, 2>;
-        if (!attr_done[kind]) {
-            INSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_done[kind] = true;
-        }
+                    : uncapped ? fft_strided_kernel<T, N, 3> : fft_strided_kernel<T, N, 2>;
+        INSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         if (smem > 200 * 1024) {
             set_error("fast FFT pass: tile does not fit in shared memory");
             return 1;

@@ -103,79 +103,144 @@ struct TileLoad {
     }
 };
 
-template <typename T, typename CT, int TX, int TY>
-__global__ void __launch_bounds__(TX *TY) stage_tile_kernel(Grid<T> g, StageArgs<T> a, int zchunk) {
+// Device-side arguments of the marching kernel: per-component base pointers (so that every
+// access is base + 32-bit cell offset) and coefficients already converted to the types they
+// are used in.
+template <typename T, typename CT>
+struct StageDev {
+    const T *u[3];
+    const T *vbase[3];
+    T *v[3];
+    const T *acc_in[3];
+    T *acc_out[3];
+    T *k_out[3];
+    const T *kprev[MAXSTAGE][3];
+    CT cprev[MAXSTAGE];
+    int nprev;
+    CT cv, ca;
+    T nu;
+    T bf[3];
+};
+
+template <typename T, typename CT>
+__device__ __forceinline__ T axpy_ct(T x, CT c, T k) {
+    return (T)add_rn((CT)x, mul_rn(c, (CT)k));
+}
+
+// ACC: also update the running accumulator; GEN: general tableau (k storage / previous stages)
+template <typename T, typename CT, int TX, int TY, int ZC, bool ACC, bool GEN>
+__global__ void __launch_bounds__(TX *TY) stage_tile_kernel(Grid<T> g, StageDev<T, CT> a) {
     constexpr int PX = TX + 2, PY = TY + 2, PLANE = PX * PY, NT = TX * TY, NE = 3 * PLANE;
     constexpr int NL = (NE + NT - 1) / NT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *s = reinterpret_cast<T *>(smem_raw);  // [4 slots][3 comps][PY][PX]
+    T *zt = s + 4 * NE;                      // [8 tables][ZC + 2]: z metrics of this chunk
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
     const int x0 = 1 + blockIdx.x * TX, y0 = 1 + blockIdx.y * TY;
-    const int zbeg = 1 + blockIdx.z * zchunk;
-    const int zend = min(zbeg + zchunk, g.N[2] - 1);
+    const int zbeg = 1 + blockIdx.z * ZC;
+    const int zend = min(zbeg + ZC, g.N[2] - 1);
     if (zbeg >= zend) return;
-    // this thread's share of a haloed plane: element e = (comp, py, px)
-    int off2d[NL], comp[NL];
+    // z metrics: rdlg[z], rdlg[z+1], rdu[z], a2[z], a1[z+1], rdug[z-1], rdug[z], rdl[z]
+    for (int e = tid; e < 8 * (ZC + 2); e += NT) {
+        int tb = e / (ZC + 2), r = e - tb * (ZC + 2);
+        int z = min(zbeg + r, g.N[2] - 2);
+        const T *src = tb == 0 ? g.rdlg[2] + z : tb == 1 ? g.rdlg[2] + z + 1 : tb == 2 ? g.rdu[2] + z
+                     : tb == 3 ? g.a2[2] + z : tb == 4 ? g.a1[2] + z + 1 : tb == 5 ? g.rdug[2] + z - 1
+                     : tb == 6 ? g.rdug[2] + z : g.rdl[2] + z;
+        zt[e] = *src;
+    }
+    // this thread's share of a haloed plane: element e = (comp, py, px) -> running pointers
+    const T *lp[NL];
+    bool lv[NL];
 #pragma unroll
     for (int i = 0; i < NL; i++) {
         int e = tid + i * NT;
         int c = e / PLANE, r = e - c * PLANE;
         int py = r / PX, px = r - py * PX;
         int gx = min(x0 - 1 + px, g.N[0] - 1), gy = min(y0 - 1 + py, g.N[1] - 1);
-        off2d[i] = gx + gy * (int)g.s[1];
-        comp[i] = e < NE ? c : -1;
+        lv[i] = e < NE;
+        const T *base = c == 0 ? a.u[0] : c == 1 ? a.u[1] : a.u[2];
+        lp[i] = base + gx + (long long)gy * g.s[1] + (long long)(zbeg - 1) * g.s[2];
     }
     T reg[NL];
-    auto load_plane = [&](int z) {
+    const long long zs = g.s[2];
+    auto load_plane = [&]() {  // loads the plane the running pointers stand on, then advances them
 #pragma unroll
-        for (int i = 0; i < NL; i++)
-            if (comp[i] >= 0) reg[i] = __ldg(a.u + comp[i] * g.cs + z * g.s[2] + off2d[i]);
+        for (int i = 0; i < NL; i++) {
+            if (lv[i]) reg[i] = __ldg(lp[i]);
+            lp[i] += zs;
+        }
     };
     auto store_plane = [&](int z) {
-        T *dst = s + (z & 3) * NE;
+        T *dst = s + (z & 3) * NE + tid;
 #pragma unroll
         for (int i = 0; i < NL; i++)
-            if (comp[i] >= 0) dst[tid + i * NT] = reg[i];
+            if (lv[i]) dst[i * NT] = reg[i];
     };
     for (int p = -1; p <= 1; p++) {
-        load_plane(zbeg + p);
+        load_plane();
         store_plane(zbeg + p);
     }
+    const int I0 = x0 + tx, I1 = y0 + ty;
+    const bool active = I0 < g.N[0] - 1 && I1 < g.N[1] - 1;
+    const int Ic0 = min(I0, g.N[0] - 2), Ic1 = min(I1, g.N[1] - 2);
+    RegMetrics<T> M;
+    {
+        const int Ic[2] = {Ic0, Ic1};
+#pragma unroll
+        for (int d = 0; d < 2; d++) {
+            M.v_rdlg[d][0] = g.rdlg[d][Ic[d]];
+            M.v_rdlg[d][1] = g.rdlg[d][Ic[d] + 1];
+            M.v_rdug[d][0] = g.rdug[d][Ic[d] - 1];
+            M.v_rdug[d][1] = g.rdug[d][Ic[d]];
+            M.v_rdu[d] = g.rdu[d][Ic[d]];
+            M.v_rdl[d] = g.rdl[d][Ic[d]];
+            M.v_a2[d] = g.a2[d][Ic[d]];
+            M.v_a1p[d] = g.a1[d][Ic[d] + 1];
+        }
+    }
     __syncthreads();
-    int I[3] = {x0 + tx, y0 + ty, 0};
-    const bool active = I[0] < g.N[0] - 1 && I[1] < g.N[1] - 1;
     const int lidx = (ty + 1) * PX + tx + 1;
-    const long long idx2d = I[0] + I[1] * g.s[1];
-    for (int z = zbeg; z < zend; z++) {
+    unsigned q = (unsigned)(Ic0 + (long long)Ic1 * g.s[1] + (long long)zbeg * g.s[2]);  // cell offset (< 2^32)
+    const unsigned qs = (unsigned)g.s[2];
+    const T nu = a.nu;
+    for (int z = zbeg; z < zend; z++, q += qs) {
         const bool more = z + 1 < zend;
-        if (more) load_plane(z + 2);
+        if (more) load_plane();
         if (active) {
-            I[2] = z;
-            const long long idx = idx2d + z * g.s[2];
             // pointwise operands first, so that their latency overlaps the stencil arithmetic
             T vb[3], ai[3];
 #pragma unroll
             for (int c = 0; c < 3; c++) {
-                vb[c] = a.v ? a.vbase[idx + c * g.cs] : T(0);
-                ai[c] = a.acc_out ? a.acc_in[idx + c * g.cs] : T(0);
+                vb[c] = a.vbase[c][q];
+                ai[c] = ACC ? a.acc_in[c][q] : T(0);
             }
+            const int r = z - zbeg;
+            M.v_rdlg[2][0] = zt[0 * (ZC + 2) + r];
+            M.v_rdlg[2][1] = zt[1 * (ZC + 2) + r];
+            M.v_rdu[2] = zt[2 * (ZC + 2) + r];
+            M.v_a2[2] = zt[3 * (ZC + 2) + r];
+            M.v_a1p[2] = zt[4 * (ZC + 2) + r];
+            M.v_rdug[2][0] = zt[5 * (ZC + 2) + r];
+            M.v_rdug[2][1] = zt[6 * (ZC + 2) + r];
+            M.v_rdl[2] = zt[7 * (ZC + 2) + r];
             TileLoad<T, PX, PLANE> U;
             U.pl[0] = s + ((z - 1) & 3) * NE + lidx;
             U.pl[1] = s + (z & 3) * NE + lidx;
             U.pl[2] = s + ((z + 1) & 3) * NE + lidx;
             T k[3];
-            momentum_rhs<T, 3, true>(U, g, I, (T)a.nu, T(1), k);
+            momentum_rhs_m<T, 3, true>(U, M, nu, T(1), k);
 #pragma unroll
             for (int c = 0; c < 3; c++) {
-                T kc = k[c] + (T)a.bodyforce[c];
-                long long q = idx + c * g.cs;
-                if (a.k_out) a.k_out[q] = kc;
-                if (a.v) {
-                    T x = vb[c];
-                    for (int j = 0; j < a.nprev; j++) x = axpy_rn<T, CT>(x, a.cprev[j], a.kprev[j][q]);
-                    a.v[q] = axpy_rn<T, CT>(x, a.cv, kc);
+                T kc = k[c] + a.bf[c];
+                T x = vb[c];
+                if (GEN) {
+                    if (a.k_out[0]) a.k_out[c][q] = kc;
+#pragma unroll 1
+                    for (int j = 0; j < a.nprev; j++) x = axpy_ct<T, CT>(x, a.cprev[j], a.kprev[j][c][q]);
                 }
-                if (a.acc_out) a.acc_out[q] = axpy_rn<T, CT>(ai[c], a.ca, kc);
+                a.v[c][q] = axpy_ct<T, CT>(x, a.cv, kc);
+                if (ACC) a.acc_out[c][q] = axpy_ct<T, CT>(ai[c], a.ca, kc);
             }
         }
         if (more) store_plane(z + 2);
@@ -185,20 +250,32 @@ __global__ void __launch_bounds__(TX *TY) stage_tile_kernel(Grid<T> g, StageArgs
 
 template <typename T, typename CT>
 static int launch_stage_tile(const Grid<T> &g, const StageArgs<T> &a, Launch L) {
-    constexpr int TX = 32, TY = 16;
-    constexpr size_t smem = (size_t)4 * 3 * (TX + 2) * (TY + 2) * sizeof(T);
-    static bool attr = false;
-    if (!attr) {
-        INSB_CUDA(cudaFuncSetAttribute(stage_tile_kernel<T, CT, TX, TY>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
+    constexpr int TX = 32, TY = 16, ZC = 128;
+    constexpr size_t smem = ((size_t)4 * 3 * (TX + 2) * (TY + 2) + 8 * (ZC + 2)) * sizeof(T);
+    const bool acc = a.acc_out != nullptr, gen = a.k_out != nullptr || a.nprev > 0;
+    auto kern = acc ? (gen ? stage_tile_kernel<T, CT, TX, TY, ZC, true, true> : stage_tile_kernel<T, CT, TX, TY, ZC, true, false>)
+                    : (gen ? stage_tile_kernel<T, CT, TX, TY, ZC, false, true> : stage_tile_kernel<T, CT, TX, TY, ZC, false, false>);
+    INSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    StageDev<T, CT> d{};
+    for (int c = 0; c < 3; c++) {
+        d.u[c] = a.u + c * g.cs;
+        d.vbase[c] = a.vbase ? a.vbase + c * g.cs : nullptr;
+        d.v[c] = a.v ? a.v + c * g.cs : nullptr;
+        d.acc_in[c] = a.acc_in ? a.acc_in + c * g.cs : nullptr;
+        d.acc_out[c] = a.acc_out ? a.acc_out + c * g.cs : nullptr;
+        d.k_out[c] = a.k_out ? a.k_out + c * g.cs : nullptr;
+        for (int j = 0; j < a.nprev; j++) d.kprev[j][c] = a.kprev[j] + c * g.cs;
+        d.bf[c] = (T)a.bodyforce[c];
     }
+    d.nprev = a.nprev;
+    for (int j = 0; j < a.nprev; j++) d.cprev[j] = (CT)a.cprev[j];
+    d.cv = (CT)a.cv;
+    d.ca = (CT)a.ca;
+    d.nu = (T)a.nu;
     int nz = g.N[2] - 2;
-    int zchunk = 128;
-    if (const char *e = getenv("INSB200_ZCHUNK")) zchunk = atoi(e) > 0 ? atoi(e) : zchunk;
     dim3 b(TX, TY, 1);
-    dim3 gr((g.N[0] - 2 + TX - 1) / TX, (g.N[1] - 2 + TY - 1) / TY, (nz + zchunk - 1) / zchunk);
-    stage_tile_kernel<T, CT, TX, TY><<<gr, b, smem, L.stream>>>(g, a, zchunk);
+    dim3 gr((g.N[0] - 2 + TX - 1) / TX, (g.N[1] - 2 + TY - 1) / TY, (nz + ZC - 1) / ZC);
+    kern<<<gr, b, smem, L.stream>>>(g, d);
     if (L.counter) ++*L.counter;
     INSB_CUDA(cudaGetLastError());
     return 0;
@@ -235,7 +312,8 @@ struct WideOf {
 template <typename T>
 int launch_stage(const Grid<T> &g, const StageArgs<T> &a, bool ct_double, Launch L) {
     static const bool force_direct = getenv("INSB200_DIRECT_STAGE") != nullptr;
-    if (g.D == 3 && !a.bouss && a.conv && a.diff && !a.zero_outside && !a.add_to_k && !force_direct) {
+    if (g.D == 3 && !a.bouss && a.conv && a.diff && !a.zero_outside && !a.add_to_k && !force_direct &&
+        a.v != nullptr && g.cs < (1LL << 32)) {
         if (sizeof(T) == 8 || ct_double) return launch_stage_tile<T, double>(g, a, L);
         return launch_stage_tile<T, T>(g, a, L);
     }
@@ -250,22 +328,59 @@ template int launch_stage<double>(const Grid<double> &, const StageArgs<double> 
 // ------------------------------------------------------------------------------------
 // divergence (+ volume scaling)
 // ------------------------------------------------------------------------------------
+// Each thread handles RB consecutive rows (y) of one x column: all loads are issued before the
+// first store so that RB x (D+D) independent requests are in flight per thread.
+constexpr int RB = 4;
+
 template <typename T, int D>
-__global__ void __launch_bounds__(256) divergence_kernel(Grid<T> g, const T *u, T *div, int scale) {
-    int I[3];
-    I[0] = blockIdx.x * blockDim.x + threadIdx.x + 1;
-    I[1] = blockIdx.y * blockDim.y + threadIdx.y + 1;
-    I[2] = (D == 3) ? (int)blockIdx.z + 1 : 0;
-    if (I[0] >= g.N[0] - 1 || I[1] >= g.N[1] - 1) return;
-    long long idx = I[0] + I[1] * g.s[1] + (D == 3 ? I[2] * g.s[2] : 0);
-    GLoad<T, D> U{u + idx, g.s[1], g.s[2], g.cs};
-    div[idx] = divergence_at<T, D>(U, g, I, scale != 0);
+__global__ void __launch_bounds__(128) divergence_kernel(Grid<T> g, const T *__restrict__ u,
+                                                         T *__restrict__ div, int scale) {
+    const int ix = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int iy0 = blockIdx.y * RB + 1;
+    const int iz = (D == 3) ? (int)blockIdx.z + 1 : 0;
+    if (ix >= g.N[0] - 1) return;
+    const long long s1 = g.s[1], s2 = g.s[2], cs = g.cs;
+    const long long base = ix + iy0 * s1 + (D == 3 ? iz * s2 : 0);
+    const int ny = g.N[1] - 1;
+    T ux[RB], uxm[RB], uy[RB + 1], uz[RB], uzm[RB];
+#pragma unroll
+    for (int r = 0; r < RB; r++) {
+        const bool ok = iy0 + r < ny;
+        const long long q = base + r * s1;
+        ux[r] = ok ? __ldg(u + q) : T(0);
+        uxm[r] = ok ? __ldg(u + q - 1) : T(0);
+        uy[r + 1] = ok ? __ldg(u + cs + q) : T(0);
+        if (D == 3) {
+            uz[r] = ok ? __ldg(u + 2 * cs + q) : T(0);
+            uzm[r] = ok ? __ldg(u + 2 * cs + q - s2) : T(0);
+        }
+    }
+    uy[0] = __ldg(u + cs + base - s1);
+    const T rx = __ldg(g.rdlg[0] + ix), dx = __ldg(g.dl[0] + ix);
+    T rz = T(0), dz = T(1);
+    if (D == 3) {
+        rz = __ldg(g.rdlg[2] + iz);
+        dz = __ldg(g.dl[2] + iz);
+    }
+#pragma unroll
+    for (int r = 0; r < RB; r++) {
+        if (iy0 + r >= ny) break;
+        const int iy = iy0 + r;
+        T acc = (ux[r] - uxm[r]) * rx + (uy[r + 1] - uy[r]) * __ldg(g.rdlg[1] + iy);
+        if (D == 3) acc = acc + (uz[r] - uzm[r]) * rz;
+        if (scale) {
+            T om = dx * __ldg(g.dl[1] + iy);
+            if (D == 3) om = om * dz;
+            acc *= om;
+        }
+        div[base + r * s1] = acc;
+    }
 }
 
 template <typename T>
 int launch_divergence(const Grid<T> &g, const T *u, T *div, bool scale, Launch L) {
-    dim3 b(64, 4, 1);
-    dim3 gr((g.N[0] - 2 + b.x - 1) / b.x, (g.N[1] - 2 + b.y - 1) / b.y, g.D == 3 ? g.N[2] - 2 : 1);
+    dim3 b(128, 1, 1);
+    dim3 gr((g.N[0] - 2 + b.x - 1) / b.x, (g.N[1] - 2 + RB - 1) / RB, g.D == 3 ? g.N[2] - 2 : 1);
     if (g.D == 3)
         divergence_kernel<T, 3><<<gr, b, 0, L.stream>>>(g, u, div, scale);
     else
@@ -305,26 +420,57 @@ template int launch_scalewithvolume<double>(const Grid<double> &, double *, Laun
 // pressure gradient: G = δp (pressuregradient!) or u += -δp (applypressure!)
 // ------------------------------------------------------------------------------------
 template <typename T, int D>
-__global__ void __launch_bounds__(256) pgrad_kernel(Grid<T> g, const T *p, T *G, T *usub) {
-    int I[3];
-    I[0] = blockIdx.x * blockDim.x + threadIdx.x + 1;
-    I[1] = blockIdx.y * blockDim.y + threadIdx.y + 1;
-    I[2] = (D == 3) ? (int)blockIdx.z + 1 : 0;
-    if (I[0] >= g.N[0] - 1 || I[1] >= g.N[1] - 1) return;
-    long long idx = I[0] + I[1] * g.s[1] + (D == 3 ? I[2] * g.s[2] : 0);
-    T pc = __ldg(p + idx);
+__global__ void __launch_bounds__(128) pgrad_kernel(Grid<T> g, const T *__restrict__ p, T *G, T *usub) {
+    const int ix = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int iy0 = blockIdx.y * RB + 1;
+    const int iz = (D == 3) ? (int)blockIdx.z + 1 : 0;
+    if (ix >= g.N[0] - 1) return;
+    const long long s1 = g.s[1], s2 = g.s[2], cs = g.cs;
+    const long long base = ix + iy0 * s1 + (D == 3 ? iz * s2 : 0);
+    const int ny = g.N[1] - 1;
+    T pc[RB + 1], px[RB], pz[RB], uo[D][RB];
 #pragma unroll
-    for (int i = 0; i < D; i++) {
-        T d = (__ldg(p + idx + g.s[i]) - pc) * __ldg(g.rdu[i] + I[i]);
-        if (G) G[idx + i * g.cs] = d;
-        if (usub) usub[idx + i * g.cs] += -d;
+    for (int r = 0; r < RB; r++) {
+        const bool ok = iy0 + r < ny;
+        const long long q = base + r * s1;
+        pc[r] = ok ? __ldg(p + q) : T(0);
+        px[r] = ok ? __ldg(p + q + 1) : T(0);
+        if (D == 3) pz[r] = ok ? __ldg(p + q + s2) : T(0);
+        if (usub) {
+#pragma unroll
+            for (int c = 0; c < D; c++) uo[c][r] = ok ? usub[q + c * cs] : T(0);
+        }
+    }
+    {
+        const int last = min(iy0 + RB, ny);  // row above the last one handled here (<= N1-1, in bounds)
+        const T top = __ldg(p + ix + last * s1 + (D == 3 ? iz * s2 : 0));
+        pc[RB] = T(0);
+#pragma unroll
+        for (int r = 1; r <= RB; r++)
+            if (iy0 + r == last) pc[r] = top;
+    }
+    const T rx = __ldg(g.rdu[0] + ix);
+    const T rz = D == 3 ? __ldg(g.rdu[2] + iz) : T(0);
+#pragma unroll
+    for (int r = 0; r < RB; r++) {
+        if (iy0 + r >= ny) break;
+        const long long q = base + r * s1;
+        T d[3];
+        d[0] = (px[r] - pc[r]) * rx;
+        d[1] = (pc[r + 1] - pc[r]) * __ldg(g.rdu[1] + iy0 + r);
+        if (D == 3) d[2] = (pz[r] - pc[r]) * rz;
+#pragma unroll
+        for (int c = 0; c < D; c++) {
+            if (G) G[q + c * cs] = d[c];
+            if (usub) usub[q + c * cs] = uo[c][r] - d[c];
+        }
     }
 }
 
 template <typename T>
 int launch_pressuregradient(const Grid<T> &g, const T *p, T *G, T *u_sub, Launch L) {
-    dim3 b(64, 4, 1);
-    dim3 gr((g.N[0] - 2 + b.x - 1) / b.x, (g.N[1] - 2 + b.y - 1) / b.y, g.D == 3 ? g.N[2] - 2 : 1);
+    dim3 b(128, 1, 1);
+    dim3 gr((g.N[0] - 2 + b.x - 1) / b.x, (g.N[1] - 2 + RB - 1) / RB, g.D == 3 ? g.N[2] - 2 : 1);
     if (g.D == 3)
         pgrad_kernel<T, 3><<<gr, b, 0, L.stream>>>(g, p, G, u_sub);
     else

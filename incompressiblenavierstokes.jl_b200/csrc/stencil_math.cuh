@@ -24,11 +24,36 @@ __device__ __forceinline__ auto at2(const LD &U, int c, int da, int sa, int db, 
     return U(c, dx, dy, dz);
 }
 
-// Momentum right-hand side k_i = (T_i1 + T_i2) + T_i3 at cell I (0-based indices I[]).
+// Metric providers: what momentum_rhs needs from the 1-D tables at cell I.
+//   rdlg(i, s) = guarded 1/Δ_i[I_i + s]   (s = 0, 1)      rdug(j, s) = guarded 1/Δu_j[I_j + s] (s = -1, 0)
+//   rdu(i) = 1/Δu_i[I_i]   rdl(j) = 1/Δ_j[I_j]   a2(i) = A2_i[I_i]   a1p(i) = A1_i[I_i + 1]
+template <typename T>
+struct GridMetrics {  // straight from the device tables (read-only cache)
+    const Grid<T> &g;
+    const int *I;
+    __device__ __forceinline__ T rdlg(int i, int s) const { return __ldg(g.rdlg[i] + I[i] + s); }
+    __device__ __forceinline__ T rdug(int j, int s) const { return __ldg(g.rdug[j] + I[j] + s); }
+    __device__ __forceinline__ T rdu(int i) const { return __ldg(g.rdu[i] + I[i]); }
+    __device__ __forceinline__ T rdl(int j) const { return __ldg(g.rdl[j] + I[j]); }
+    __device__ __forceinline__ T a2(int i) const { return __ldg(g.a2[i] + I[i]); }
+    __device__ __forceinline__ T a1p(int i) const { return __ldg(g.a1[i] + I[i] + 1); }
+};
+
+template <typename T>
+struct RegMetrics {  // preloaded into registers (marching kernel: x/y entries are loop invariant)
+    T v_rdlg[3][2], v_rdug[3][2], v_rdu[3], v_rdl[3], v_a2[3], v_a1p[3];
+    __device__ __forceinline__ T rdlg(int i, int s) const { return v_rdlg[i][s]; }
+    __device__ __forceinline__ T rdug(int j, int s) const { return v_rdug[j][s + 1]; }
+    __device__ __forceinline__ T rdu(int i) const { return v_rdu[i]; }
+    __device__ __forceinline__ T rdl(int j) const { return v_rdl[j]; }
+    __device__ __forceinline__ T a2(int i) const { return v_a2[i]; }
+    __device__ __forceinline__ T a1p(int i) const { return v_a1p[i]; }
+};
+
+// Momentum right-hand side k_i = (T_i1 + T_i2) + T_i3 at cell I.
 // cfac scales the convective stress (1 or 0), nu the diffusive one (0 disables it).
-template <typename T, int D, bool FULL, typename LD>
-__device__ __forceinline__ void momentum_rhs(const LD &U, const Grid<T> &g, const int I[3], T nu,
-                                             T cfac, T k[D]) {
+template <typename T, int D, bool FULL, typename LD, typename MET>
+__device__ __forceinline__ void momentum_rhs_m(const LD &U, const MET &M, T nu, T cfac, T k[D]) {
     const T half = T(0.5);
 #pragma unroll
     for (int i = 0; i < D; i++) {
@@ -47,12 +72,12 @@ __device__ __forceinline__ void momentum_rhs(const LD &U, const Grid<T> &g, cons
                     c0 *= cfac;
                     c1 *= cfac;
                 }
-                T s0 = c0 - nu * ((u0 - um) * __ldg(g.rdlg[i] + I[i]));
-                T s1 = c1 - nu * ((up - u0) * __ldg(g.rdlg[i] + I[i] + 1));
-                t = -(s1 - s0) * __ldg(g.rdu[i] + I[i]);
+                T s0 = c0 - nu * ((u0 - um) * M.rdlg(i, 0));
+                T s1 = c1 - nu * ((up - u0) * M.rdlg(i, 1));
+                t = -(s1 - s0) * M.rdu(i);
             } else {
-                T w2 = __ldg(g.a2[i] + I[i]);
-                T w1 = __ldg(g.a1[i] + I[i] + 1);
+                T w2 = M.a2(i);
+                T w1 = M.a1p(i);
                 T ui_m = at2<D>(U, i, j, -1, j, 0);
                 T ui_0 = U(i, 0, 0, 0);
                 T ui_p = at2<D>(U, i, j, +1, j, 0);
@@ -66,14 +91,21 @@ __device__ __forceinline__ void momentum_rhs(const LD &U, const Grid<T> &g, cons
                     cb *= cfac;
                     ca *= cfac;
                 }
-                T sb = cb - nu * ((ui_p - ui_0) * __ldg(g.rdug[j] + I[j]));
-                T sa = ca - nu * ((ui_0 - ui_m) * __ldg(g.rdug[j] + I[j] - 1));
-                t = -(sb - sa) * __ldg(g.rdl[j] + I[j]);
+                T sb = cb - nu * ((ui_p - ui_0) * M.rdug(j, 0));
+                T sa = ca - nu * ((ui_0 - ui_m) * M.rdug(j, -1));
+                t = -(sb - sa) * M.rdl(j);
             }
             acc = (j == 0) ? t : acc + t;
         }
         k[i] = acc;
     }
+}
+
+template <typename T, int D, bool FULL, typename LD>
+__device__ __forceinline__ void momentum_rhs(const LD &U, const Grid<T> &g, const int I[3], T nu,
+                                             T cfac, T k[D]) {
+    GridMetrics<T> M{g, I};
+    momentum_rhs_m<T, D, FULL>(U, M, nu, cfac, k);
 }
 
 // avg(temp, Δ, I + s*e_i, i)
