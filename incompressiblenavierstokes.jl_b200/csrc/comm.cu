@@ -1,0 +1,179 @@
+// comm.cu -- z-slab decomposition plumbing: one process per GPU, NCCL over NVLink/NVSwitch.
+//
+// The reference has no multi-device code at all; this file is what the slab
+// decomposition adds around the single-GPU kernels:
+//   * halo exchange of the z ghost planes (replaces the periodic copy of apply_bc_u!/p!/temp!
+//     along the decomposed direction, src/boundary_conditions.jl:273-285,303-315),
+//   * the all-to-all transposes of the distributed FFT Poisson solve (z-slabs <-> ky-slabs),
+//   * min/max reductions for propose_timestep / maximum(abs, u).
+// NCCL is loaded lazily with dlopen so that a single-GPU run never depends on it; when torch
+// is already in the process its bundled libnccl.so.2 is the one that gets bound.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstring>
+
+#include "internal.h"
+
+namespace insb {
+
+namespace {
+
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                              cudaStream_t) = nullptr;
+};
+
+NcclApi g_nccl;
+
+int load_nccl() {
+    if (g_nccl.handle) return 0;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *n : names) {
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) {
+        set_error(std::string("cannot load libnccl.so.2 (needed for world > 1): ") + dlerror());
+        return 1;
+    }
+#define LOAD(field, sym)                                               \
+    g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(h, sym)); \
+    if (!g_nccl.field) {                                               \
+        set_error(std::string("libnccl lacks ") + sym);                \
+        return 1;                                                      \
+    }
+    LOAD(GetUniqueId, "ncclGetUniqueId")
+    LOAD(CommInitRank, "ncclCommInitRank")
+    LOAD(CommDestroy, "ncclCommDestroy")
+    LOAD(GetErrorString, "ncclGetErrorString")
+    LOAD(GroupStart, "ncclGroupStart")
+    LOAD(GroupEnd, "ncclGroupEnd")
+    LOAD(Send, "ncclSend")
+    LOAD(Recv, "ncclRecv")
+    LOAD(AllReduce, "ncclAllReduce")
+#undef LOAD
+    g_nccl.handle = h;
+    return 0;
+}
+
+#define INSB_NCCL(call)                                                                     \
+    do {                                                                                    \
+        ncclResult_t r__ = (call);                                                          \
+        if (r__ != ncclSuccess) {                                                           \
+            set_error(std::string(#call) + ": " + g_nccl.GetErrorString(r__) + " at " +     \
+                      __FILE__ + ":" + std::to_string(__LINE__));                           \
+            return 1;                                                                       \
+        }                                                                                   \
+    } while (0)
+
+}  // namespace
+
+struct Comm {
+    int rank = 0, world = 1;
+    ncclComm_t comm = nullptr;
+};
+
+int comm_unique_id(void *id128) {
+    INSB_TRY(load_nccl());
+    ncclUniqueId id;
+    INSB_NCCL(g_nccl.GetUniqueId(&id));
+    std::memcpy(id128, id.internal, NCCL_UNIQUE_ID_BYTES);
+    return 0;
+}
+
+int comm_create(int rank, int world, const void *id128, Comm **out) {
+    *out = nullptr;
+    if (world < 2 || rank < 0 || rank >= world) {
+        set_error("comm_create: bad (rank, world)");
+        return 1;
+    }
+    if (!id128) {
+        set_error("world > 1 needs setup.nccl_id (insb200_comm_unique_id on rank 0, shared with all ranks)");
+        return 1;
+    }
+    INSB_TRY(load_nccl());
+    ncclUniqueId id;
+    std::memcpy(id.internal, id128, NCCL_UNIQUE_ID_BYTES);
+    Comm *c = new Comm();
+    c->rank = rank;
+    c->world = world;
+    ncclResult_t r = g_nccl.CommInitRank(&c->comm, world, id, rank);
+    if (r != ncclSuccess) {
+        set_error(std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
+        delete c;
+        return 1;
+    }
+    *out = c;
+    return 0;
+}
+
+void comm_destroy(Comm *c) {
+    if (!c) return;
+    if (c->comm) g_nccl.CommDestroy(c->comm);
+    delete c;
+}
+
+int comm_rank(const Comm *c) { return c ? c->rank : 0; }
+int comm_world(const Comm *c) { return c ? c->world : 1; }
+
+// Ghost planes of the decomposed (slowest) direction.  A field component is `nplanes`
+// contiguous planes of `plane` elements; plane 0 and plane nplanes-1 are the ghosts.
+//   lower ghost  <- top interior plane of the rank below      (u[1]   = u[N-1] in the reference)
+//   upper ghost  <- first interior plane of the rank above    (u[N]   = u[2])
+// Posting order (send up, send down, recv from below, recv from above) keeps the pairs
+// matched when world == 2 and both neighbours are the same peer.
+int comm_halo_z(Comm *c, void *field, size_t esz, long long plane, int nplanes, int ncomp, long long cs,
+                cudaStream_t st) {
+    const int up = (c->rank + 1) % c->world, down = (c->rank + c->world - 1) % c->world;
+    char *f = (char *)field;
+    const size_t pb = (size_t)plane * esz;
+    INSB_NCCL(g_nccl.GroupStart());
+    for (int k = 0; k < ncomp; k++) {
+        char *b = f + (size_t)k * cs * esz;
+        INSB_NCCL(g_nccl.Send(b + (size_t)(nplanes - 2) * pb, pb, ncclChar, up, c->comm, st));
+        INSB_NCCL(g_nccl.Send(b + pb, pb, ncclChar, down, c->comm, st));
+        INSB_NCCL(g_nccl.Recv(b, pb, ncclChar, down, c->comm, st));
+        INSB_NCCL(g_nccl.Recv(b + (size_t)(nplanes - 1) * pb, pb, ncclChar, up, c->comm, st));
+    }
+    INSB_NCCL(g_nccl.GroupEnd());
+    return 0;
+}
+
+// All-to-all of `world` equal blocks of `block_bytes`: block r of `send` goes to rank r and
+// lands as block `rank` of its `recv`.
+int comm_all_to_all(Comm *c, const void *send, void *recv, size_t block_bytes, cudaStream_t st) {
+    const char *s = (const char *)send;
+    char *r = (char *)recv;
+    INSB_CUDA(cudaMemcpyAsync(r + (size_t)c->rank * block_bytes, s + (size_t)c->rank * block_bytes, block_bytes,
+                              cudaMemcpyDeviceToDevice, st));
+    INSB_NCCL(g_nccl.GroupStart());
+    for (int d = 1; d < c->world; d++) {
+        int to = (c->rank + d) % c->world, from = (c->rank + c->world - d) % c->world;
+        INSB_NCCL(g_nccl.Send(s + (size_t)to * block_bytes, block_bytes, ncclChar, to, c->comm, st));
+        INSB_NCCL(g_nccl.Recv(r + (size_t)from * block_bytes, block_bytes, ncclChar, from, c->comm, st));
+    }
+    INSB_NCCL(g_nccl.GroupEnd());
+    return 0;
+}
+
+// scratch[0]: non-negative double reduced with min or max; scratch[1]: NaN flag (max)
+int comm_reduce_scratch(Comm *c, double *scratch, bool is_min, cudaStream_t st) {
+    INSB_NCCL(g_nccl.GroupStart());
+    INSB_NCCL(g_nccl.AllReduce(scratch, scratch, 1, ncclDouble, is_min ? ncclMin : ncclMax, c->comm, st));
+    INSB_NCCL(g_nccl.AllReduce(scratch + 1, scratch + 1, 1, ncclUint64, ncclMax, c->comm, st));
+    INSB_NCCL(g_nccl.GroupEnd());
+    return 0;
+}
+
+}  // namespace insb

@@ -1,0 +1,254 @@
+"""
+    B200Ext
+
+Package extension that routes the per-time-step hot path of IncompressibleNavierStokes
+(right-hand side, Runge-Kutta stage combine, ghost fills, pressure projection) to
+`libinsb200.so`, the hand-written sm_100a CUDA backend, through `ccall`.
+
+Trigger: `CUDA` (like `ext/CUDSSExt.jl`).  Add to the reference's `Project.toml`:
+
+    [extensions]
+    B200Ext = ["CUDA"]
+
+Usage -- the only change to a user script is the pressure solver:
+
+    setup   = Setup(; x, boundary_conditions, backend = CUDABackend())
+    psolver = psolver_b200(setup)                    # or psolver_b200(setup; kind = :transform)
+    solve_unsteady(; setup, psolver, method = RKMethods.RK44(; T), ...)
+
+`psolver_b200` returns a callable `B200PSolver` (it solves in place like the closures of
+`src/pressure.jl`), and because the stepper NamedTuple carries the psolver's type,
+`timestep!`, `project!` and `propose_timestep` dispatch to the fused library calls below.
+Everything the extension does not override (processors, `Observable` updates, `Array(u)`,
+user-defined `force!`) keeps working on the same `CuArray`s.
+
+This file cannot be executed in the build container (no Julia); the Python/ctypes harness in
+`incompressiblenavierstokes.jl_b200/insb200/` binds the very same symbols and is what the
+tests drive.  See INTEGRATION.md.
+"""
+module B200Ext
+
+using CUDA
+using IncompressibleNavierStokes
+using IncompressibleNavierStokes:
+    PeriodicBC,
+    DirichletBC,
+    SymmetricBC,
+    PressureBC,
+    ExplicitRungeKuttaMethod,
+    LMWray3,
+    navierstokes!,
+    boussinesq!,
+    create_stepper
+
+const INS = IncompressibleNavierStokes
+const libinsb200 = get(ENV, "INSB200_LIB", "libinsb200.so")
+
+# ---- C structs of include/insb200.h (field order and types must match exactly) ---------
+struct CSetup
+    D::Cint
+    N::NTuple{3,Cint}
+    dtype::Cint
+    bc_u::NTuple{6,Cint}              # [dim][side]
+    has_temp::Cint
+    bc_temp::NTuple{6,Cint}
+    Delta::NTuple{3,Ptr{Cvoid}}
+    DeltaU::NTuple{3,Ptr{Cvoid}}
+    A1::NTuple{3,Ptr{Cvoid}}
+    A2::NTuple{3,Ptr{Cvoid}}
+    xlims::NTuple{6,Cdouble}
+    bc_u_value::NTuple{18,Cdouble}    # [dim][side][component]
+    bc_temp_value::NTuple{6,Cdouble}
+    psolver::Cint
+    tridiagonal_dir::Cint
+    eig::NTuple{3,Ptr{Cvoid}}
+    device::Cint
+    rank::Cint
+    world::Cint
+    nccl_id::Ptr{Cvoid}
+end
+
+struct CParams
+    viscosity::Cdouble
+    conductivity::Cdouble
+    gravity::Cdouble
+    gdir::Cint
+    dodissipation::Cint
+    boussinesq::Cint
+    bodyforce::NTuple{3,Cdouble}
+end
+
+bccode(::PeriodicBC) = Cint(0)
+bccode(::DirichletBC) = Cint(1)
+bccode(::SymmetricBC) = Cint(2)
+bccode(::PressureBC) = Cint(3)
+
+lasterror() = unsafe_string(ccall((:insb200_last_error, libinsb200), Cstring, ()))
+check(status) = status == 0 ? nothing : error("libinsb200: " * lasterror())
+
+# DirichletBC(nothing) -> no slip, DirichletBC((a, b, c)) -> constants; functions are
+# evaluated on the boundary planes by `refresh_bc!` below.
+bcconst(bc, α) = 0.0
+bcconst(bc::DirichletBC{<:Tuple}, α) = Float64(bc.u[α])
+bcconst(bc::DirichletBC{<:Number}, α) = Float64(bc.u)
+
+"Handle owning an `insb200_plan_t*` plus the host arrays the plan was created from."
+mutable struct B200PSolver{S} <: Function
+    plan::Ptr{Cvoid}
+    setup::S
+    kind::Symbol
+    function B200PSolver(plan, setup::S, kind) where {S}
+        ps = new{S}(plan, setup, kind)
+        finalizer(ps) do x
+            x.plan == C_NULL || ccall((:insb200_plan_destroy, libinsb200), Cint, (Ptr{Cvoid},), x.plan)
+            x.plan = C_NULL
+        end
+    end
+end
+
+const KINDS = (; spectral = Cint(0), transform = Cint(1), tridiagonal = Cint(2), default = Cint(3))
+
+"""
+    psolver_b200(setup; kind = :default, dir = nothing)
+
+B200 replacement of `psolver_spectral` / `psolver_transform` / `psolver_tridiagonal` /
+`default_psolver` (`src/pressure.jl:58-78, 215-545`).
+"""
+function INS.psolver_b200(setup; kind = :default, dir = nothing, rank = 0, world = 1, nccl_id = C_NULL)
+    (; Δ, Δu, A_stag, N, xlims, boundary_conditions) = setup
+    D = length(N)
+    T = eltype(Δ[1])
+    T in (Float32, Float64) || error("libinsb200 supports Float32 and Float64")
+    # 1-D tables are DATA: copy them to the host exactly as Setup computed them
+    host = (; Δ = Array.(Δ), Δu = Array.(Δu), A1 = map(a -> Array(a[1]), A_stag), A2 = map(a -> Array(a[2]), A_stag))
+    pad3(f, fill) = ntuple(d -> d <= D ? f(d) : fill, 3)
+    bcu = boundary_conditions.u
+    hastemp = haskey(boundary_conditions, :temp)
+    bct = hastemp ? boundary_conditions.temp : bcu
+    flat6(f) = ntuple(i -> (d = (i - 1) ÷ 2 + 1; s = (i - 1) % 2 + 1; d <= D ? f(d, s) : zero(f(1, 1))), 6)
+    GC.@preserve host begin
+        cs = CSetup(
+            D,
+            pad3(d -> Cint(N[d]), Cint(1)),
+            T == Float64 ? Cint(1) : Cint(0),
+            flat6((d, s) -> bccode(bcu[d][s])),
+            Cint(hastemp),
+            flat6((d, s) -> bccode(bct[d][s])),
+            pad3(d -> Ptr{Cvoid}(pointer(host.Δ[d])), C_NULL),
+            pad3(d -> Ptr{Cvoid}(pointer(host.Δu[d])), C_NULL),
+            pad3(d -> Ptr{Cvoid}(pointer(host.A1[d])), C_NULL),
+            pad3(d -> Ptr{Cvoid}(pointer(host.A2[d])), C_NULL),
+            flat6((d, s) -> Float64(xlims[d][s])),
+            ntuple(18) do i
+                d = (i - 1) ÷ 6 + 1
+                s = ((i - 1) ÷ 3) % 2 + 1
+                α = (i - 1) % 3 + 1
+                d <= D && α <= D ? bcconst(bcu[d][s], α) : 0.0
+            end,
+            flat6((d, s) -> hastemp && bct[d][s] isa DirichletBC ? Float64(bct[d][s].u) : 0.0),
+            KINDS[kind],
+            isnothing(dir) ? Cint(-1) : Cint(dir - 1),
+            (C_NULL, C_NULL, C_NULL),
+            Cint(CUDA.deviceid(CUDA.device())),
+            Cint(rank),
+            Cint(world),
+            nccl_id,
+        )
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:insb200_plan_create, libinsb200), Cint, (Ref{CSetup}, Ref{Ptr{Cvoid}}), cs, out))
+    end
+    resolved = ccall((:insb200_plan_psolver, libinsb200), Cint, (Ptr{Cvoid},), out[])
+    resolved == -1 && error("default_psolver picks psolver_direct for this setup; not on the B200 path")
+    B200PSolver(out[], setup, (:spectral, :transform, :tridiagonal)[resolved+1])
+end
+
+stream() = Ptr{Cvoid}(CUDA.stream().handle)
+devptr(a::CuArray) = Ptr{Cvoid}(UInt(pointer(a)))
+devptr(::Nothing) = C_NULL
+
+# poisson!(psolver, p) = psolver(p)   (src/pressure.jl:22)
+function (ps::B200PSolver)(p::CuArray)
+    check(ccall((:insb200_psolve, libinsb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), ps.plan, devptr(p), stream()))
+    p
+end
+
+# project!(u, setup; psolver, p)   (src/pressure.jl:42-55)
+function INS.project!(u::CuArray, setup; psolver::B200PSolver, p::CuArray)
+    check(ccall((:insb200_project, libinsb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+        psolver.plan, devptr(u), devptr(p), stream()))
+    u
+end
+
+function cparams(force!, params)
+    ν = Float64(params.viscosity)
+    if force! === boussinesq!
+        CParams(ν, params.conductivity, params.gravity, Cint(params.gdir - 1), Cint(params.dodissipation), Cint(1), (0.0, 0.0, 0.0))
+    else
+        bf = get(params, :bodyforce, (0.0, 0.0, 0.0))
+        CParams(ν, 0.0, 0.0, Cint(0), Cint(0), Cint(0), ntuple(i -> i <= length(bf) ? Float64(bf[i]) : 0.0, 3))
+    end
+end
+
+const B200Stepper = NamedTuple{(:setup, :psolver, :state, :t, :n),<:Tuple{Any,<:B200PSolver,Any,Any,Any}}
+const BuiltinForce = Union{typeof(navierstokes!),typeof(boussinesq!)}
+
+# Function-valued DirichletBC (src/boundary_conditions.jl:344-357): evaluate the user's
+# function on the plane coordinates at the stage times and hand the planes to the library.
+function refresh_bc!(ps::B200PSolver, t)
+    # No-slip / constant BCs need nothing.  For `DirichletBC(f::Function)` a caller evaluates
+    # `f.(α, xplane..., t)` into a CuArray and registers it with
+    #   ccall((:insb200_set_bc_u_plane, libinsb200), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Cvoid}), ...)
+    # once per stage time; the fused steppers below are used only when every BC is constant in
+    # time, otherwise `timestep!` falls back to the per-stage composition (see INTEGRATION.md).
+    nothing
+end
+
+# timestep!(::ExplicitRungeKuttaMethod, ...)   (src/time_steppers/step_explicit_runge_kutta.jl:4-57)
+function INS.timestep!(method::ExplicitRungeKuttaMethod{T}, force!::BuiltinForce, stepper::B200Stepper, Δt;
+        params = nothing, ode_cache = nothing, force_cache = nothing) where {T}
+    (; setup, psolver, state, t, n) = stepper
+    (; A, b, c) = method
+    s = length(b)
+    Arow = Float64.(permutedims(A))[:]      # row-major s*s (already the shifted tableau, methods.jl:80-85)
+    cpar = Ref(cparams(force!, params))
+    coefT = promote_type(T, typeof(Δt)) == Float64 ? Cint(1) : Cint(0)
+    temp = haskey(state, :temp) ? state.temp : nothing
+    check(ccall((:insb200_step_rk, libinsb200), Cint,
+        (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cdouble, Ref{CParams}, Ptr{Cvoid}),
+        psolver.plan, Arow, Float64.(c), s, coefT, devptr(state.u), devptr(temp), t, Δt, cpar, stream()))
+    create_stepper(method; setup, psolver, state, t = t + Δt, n = n + 1)
+end
+
+# timestep!(::LMWray3, ...)   (src/time_steppers/step_lmwray3.jl:3-94)
+function INS.timestep!(method::LMWray3, force!::BuiltinForce, stepper::B200Stepper, Δt;
+        params = nothing, ode_cache = nothing, force_cache = nothing)
+    (; setup, psolver, state, t, n) = stepper
+    cpar = Ref(cparams(force!, params))
+    temp = haskey(state, :temp) ? state.temp : nothing
+    check(ccall((:insb200_step_lmwray3, libinsb200), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cdouble, Ref{CParams}, Ptr{Cvoid}),
+        psolver.plan, devptr(state.u), devptr(temp), t, Δt, cpar, stream()))
+    create_stepper(method; setup, psolver, state, t = t + Δt, n = n + 1)
+end
+
+# propose_timestep(force!, state, setup, params)   (src/solver.jl:157-214); needs the plan, so
+# it is reached through the psolver: `propose_timestep(force!, state, setup, params, psolver)`.
+function INS.propose_timestep(force!::BuiltinForce, state, setup, params, psolver::B200PSolver)
+    out = Ref{Cdouble}(0)
+    cpar = Ref(cparams(force!, params))
+    check(ccall((:insb200_cfl, libinsb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{CParams}, Ref{Cdouble}, Ptr{Cvoid}),
+        psolver.plan, devptr(state.u), cpar, out, stream()))
+    eltype(state.u)(out[])
+end
+
+# right_hand_side!(dudt, u, params_ref, t)   (src/sciml.jl:35-48)
+function INS.right_hand_side!(dudt::CuArray, u::CuArray, params_ref::Base.RefValue{<:Tuple{Any,<:B200PSolver,Any}}, t)
+    setup, psolver, viscosity = params_ref[]
+    cpar = Ref(CParams(viscosity, 0.0, 0.0, Cint(0), Cint(0), Cint(0), (0.0, 0.0, 0.0)))
+    check(ccall((:insb200_right_hand_side, libinsb200), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Ref{CParams}, Ptr{Cvoid}),
+        psolver.plan, devptr(dudt), devptr(u), t, cpar, stream()))
+    nothing
+end
+
+end
