@@ -48,6 +48,16 @@ def fixed_dt(n):
     return 0.5 * min(h * h / NU / 6, 2 * h)
 
 
+def weak_dims(n, world):
+    d = [n, n, n]
+    k, a = world, 2
+    while k > 1:
+        d[a] *= 2
+        k //= 2
+        a = (a - 1) % 3
+    return tuple(d)
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -177,13 +187,17 @@ def run_gpu(args):
     T = np.float32 if args.dtype == "f32" else np.float64
     w = 4 if args.dtype == "f32" else 8
     n = args.n
-    x = tuple(np.linspace(0.0, 1.0, n + 1).astype(T) for _ in range(3))
-    sg = I.Setup(x, {"u": ((I.PeriodicBC(), I.PeriodicBC()),) * 3})
+    # weak-scaling series: n^3 cells per GPU; the grid doubles along z, then y, then x, so that
+    # N = 1 is BASELINE config[1] (512^3) and N = 8 is config[2]'s 1024^3 box
+    dims = weak_dims(n, world)
+    x = tuple(np.linspace(0.0, 1.0, m + 1).astype(T) for m in dims)
+    nid = I.share_unique_id() if world > 1 else None
+    sg = I.Setup(x, {"u": ((I.PeriodicBC(), I.PeriodicBC()),) * 3}, rank=rank, world=world, nccl_id=nid)
     ps = I.psolver_spectral(sg)
     u = I.velocityfield(sg, tgv3d_u, psolver=ps)
     method = I.RKMethods.RK44(T)
     params = dict(viscosity=NU)
-    dt = T(fixed_dt(n))  # eltype(u): the stage combine then stays in the field type
+    dt = T(fixed_dt(max(dims)))  # eltype(u): the stage combine then stays in the field type
     stepper = I.create_stepper(method, setup=sg, psolver=ps, state={"u": u}, t=0.0)
 
     def barrier():
@@ -216,11 +230,24 @@ def run_gpu(args):
         tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms = float(tms.item())
-    umax = I.maxabs(stepper["state"]["u"], sg)
+    umax = I.maxabs(stepper["state"]["u"], sg, plan=ps.plan)
     assert np.isfinite(umax) and 0 < umax < 10, f"solution blew up: max|u| = {umax}"
 
-    cells = n**3 * world  # replicas until the slab decomposition lands
+    cells = int(np.prod(dims))  # one z-slab of the global grid per GPU
     value = cells * args.steps / (ms * 1e-3)
+    # NVLink traffic per GPU per step: 2 all-to-all transposes per solve, 4 solves;
+    # halo: u (3 comps) twice + p once per stage, 2 planes each
+    nvlink = None
+    if world > 1:
+        m0p = (dims[0] // 2 + 1 + 7) // 8 * 8
+        spec_local = m0p * dims[1] * (dims[2] // world) * 2 * w
+        a2a = 8 * spec_local * (world - 1) / world
+        halo = 4 * 7 * 2 * (dims[0] + 2) * (dims[1] + 2) * w
+        sent = a2a + halo
+        nvlink = {"bytes_sent_per_gpu_per_step": sent, "all_to_all_bytes": a2a, "halo_bytes": halo,
+                  "achieved_GBps": sent / (ms / args.steps * 1e-3) / 1e9, "peak_GBps": 770.0,
+                  "frac": sent / (ms / args.steps * 1e-3) / 1e9 / 770.0,
+                  "peak_source": "measured peer copy per direction (B200_PROFILING.md)"}
     peak, peak_src = peaks()
 
     # ---- roofline of the dominant kernel group (DESIGN.md "Algorithmic bytes") ----
@@ -234,7 +261,7 @@ def run_gpu(args):
     groups = {k: {"ms_per_step": prof[k][0] / args.steps, "launch_groups": prof[k][1],
                   "GBps": (alg[k] * w * n**3 / (prof[k][0] / max(prof[k][1], 1) * 1e-3) / 1e9) if k in alg and prof[k][0] > 0 else None}
               for k in prof}
-    step_bytes = 120.0 * w * n**3
+    step_bytes = 120.0 * w * n**3  # per GPU
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_cell": alg[dom] * w,
@@ -245,7 +272,7 @@ def run_gpu(args):
 
     # ---- end to end through the C ABI with HOST buffers (pinned), every step H2D + D2H ----
     e2e = None
-    if rank == 0 and not args.no_e2e:
+    if not args.no_e2e:  # every rank moves its own slab
         import ctypes as C
 
         from insb200._lib import lib, check
@@ -265,16 +292,21 @@ def run_gpu(args):
                                              C.c_void_p(uh.data_ptr()), None, float(t), float(dt), 1, C.byref(pr), st))
 
         host_step(0.0)
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
         for i in range(ke):
             host_step(i * float(dt))
         torch.cuda.synchronize()
         el = time.perf_counter() - t0
-        nbytes = uh.numel() * uh.element_size()
-        e2e = {"value": n**3 * ke / el, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+        if world > 1:
+            tel = torch.tensor([el], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tel, op=dist.ReduceOp.MAX)
+            el = float(tel.item())
+        nbytes = uh.numel() * uh.element_size() * world
+        e2e = {"value": cells * ke / el, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                "steps": ke, "ms_per_step": 1e3 * el / ke,
-               "note": "insb200_step_rk_host: pinned host u -> device, one fused RK44 step, device -> host, every step"}
+               "note": "insb200_step_rk_host on every rank: pinned host slab of u -> device, one fused RK44 step, "
+                       "device -> host, every step; bytes summed over ranks, time = max over ranks"}
         assert np.isfinite(float(uh.abs().max()))
 
     # ---- CPU baseline beside it (bounded sample) ----
@@ -290,12 +322,15 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": f"TaylorGreenVortex3D {n}^3 periodic {args.dtype} RK44 psolver_spectral",
-                       "n": n, "nu": NU, "dt": float(dt), "method": f"RK44(T={args.dtype})",
-                       "l2": f"working set {14 * w * (n + 2)**3 / 1e9:.1f} GB >> 126 MB L2 (no flush needed)",
-                       "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (slab decomposition pending)"},
+            "config": {"workload": f"TaylorGreenVortex3D {dims[0]}x{dims[1]}x{dims[2]} periodic {args.dtype} RK44 psolver_spectral",
+                       "n": list(dims), "cells_per_gpu": n**3, "nu": NU, "dt": float(dt), "method": f"RK44(T={args.dtype})",
+                       "l2": f"working set {14 * w * (n + 2)**3 / 1e9:.1f} GB per GPU >> 126 MB L2 (no flush needed)",
+                       "parallelism": "1 GPU" if world == 1 else
+                       f"z-slab decomposition over {world} GPUs (halo exchange + all-to-all FFT transposes over NCCL)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         }
+        if nvlink:
+            line["nvlink"] = nvlink
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

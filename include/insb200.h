@@ -71,8 +71,15 @@ typedef struct insb200_setup {
      * element type `dtype`; NULL = computed by the library the way the reference does. */
     const void *eig[3];
     int device;                     /* CUDA device ordinal, -1 = current device */
-    /* z-slab decomposition (one process per GPU). world == 1 for a single GPU. */
+    /* z-slab decomposition (one process per GPU over NCCL; no counterpart in the reference,
+     * SURVEY.md §8e).  world == 1 for a single GPU.  With world > 1 the setup still describes
+     * the GLOBAL grid; every field pointer passed to the library is then this rank's slab:
+     * N[0] x N[1] x ((N[2]-2)/world + 2) per component, i.e. the planes
+     * [rank*nzl, rank*nzl + nzl + 2) of the global ghosted array.  Requires D == 3, periodic z,
+     * (N[2]-2) % world == 0; the Poisson solve then needs psolver_spectral on power-of-two grids. */
     int rank, world;
+    /* 128-byte NCCL unique id from insb200_comm_unique_id(), identical on all ranks (world > 1). */
+    const void *nccl_id;
 } insb200_setup_t;
 
 /* `params` NamedTuple forwarded to force! (src/solver.jl:2-35,176) */
@@ -95,6 +102,12 @@ int insb200_version(void);
  * built by psolver_spectral/transform/tridiagonal, pressure.jl:344-347,248-253,469-476)
  * + time-stepper caches (get_cache, time_steppers/time_stepper_caches.jl:11-24). */
 int insb200_plan_create(const insb200_setup_t *setup, insb200_plan_t **out);
+/* Rank 0 calls this and ships the 128 bytes to the other ranks (MPI.jl / Distributed in Julia,
+ * torch.distributed in the Python harness) before every rank calls insb200_plan_create. */
+int insb200_comm_unique_id(void *id128);
+/* Extents (including ghosts) of the arrays this rank passes in: N of the setup, with the slab
+ * extent in z when world > 1. */
+int insb200_plan_local_n(const insb200_plan_t *plan, int N_local[3]);
 int insb200_plan_destroy(insb200_plan_t *plan);
 /* Which psolver the plan holds (default_psolver resolved), and bytes of device workspace. */
 int insb200_plan_psolver(const insb200_plan_t *plan);

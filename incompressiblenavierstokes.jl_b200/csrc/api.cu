@@ -30,6 +30,9 @@ struct insb200_plan {
     Grid<float> gf;
     Grid<double> gd;
     BcDesc bc;
+    Comm *comm = nullptr;  // z-slab decomposition (world > 1)
+    int nzl = 0;           // interior planes owned by this rank
+    int Iu_loc[3][3][2];   // Iu with the z range of this slab (cfl reduction)
     Poisson *ps = nullptr;
     int psolver = INSB200_PSOLVER_NONE;
     // work buffers (device): two stage buffers and the accumulator for u (and temp), p scratch,
@@ -131,6 +134,13 @@ int build_grid(insb200_plan *pl, Grid<T> &g) {
         g.a2[a] = row + 7 * n;
         g.wa[a] = row + 8 * n;
         g.wb[a] = row + 9 * n;
+    }
+    if (pl->comm) {  // this rank's slab: planes [rank*nzl, rank*nzl + nzl + 2) of the global grid
+        const long long zoff = (long long)comm_rank(pl->comm) * pl->nzl;
+        g.N[2] = pl->nzl + 2;
+        g.cs = (long long)g.N[0] * g.N[1] * g.N[2];
+        g.dl[2] += zoff, g.du[2] += zoff, g.rdl[2] += zoff, g.rdu[2] += zoff, g.rdlg[2] += zoff;
+        g.rdug[2] += zoff, g.a1[2] += zoff, g.a2[2] += zoff, g.wa[2] += zoff, g.wb[2] += zoff;
     }
     // step limits (solver.jl:157-166, :188-197)
     for (int a = 0; a < D; a++) {
@@ -549,8 +559,14 @@ int insb200_plan_create(const insb200_setup_t *setup, insb200_plan_t **out) {
         }
     }
     if (s.world > 1) {
-        set_error("multi-GPU slab decomposition is not available in this build");
-        return 1;
+        if (s.D != 3 || s.bc_u[2][0] != INSB200_BC_PERIODIC) {
+            set_error("world > 1: the slab decomposition needs a 3-D grid that is periodic in z");
+            return 1;
+        }
+        if ((s.N[2] - 2) % s.world) {
+            set_error("world > 1: the number of z volumes must be divisible by the number of ranks");
+            return 1;
+        }
     }
     insb200_plan *pl = new insb200_plan();
     pl->s = s;
@@ -559,6 +575,14 @@ int insb200_plan_create(const insb200_setup_t *setup, insb200_plan_t **out) {
     pl->D = s.D;
     if (s.device >= 0) INSB_CUDA(cudaSetDevice(s.device));
     INSB_CUDA(cudaGetDevice(&pl->dev));
+    if (s.world > 1) {
+        int rc = comm_create(s.rank, s.world, s.nccl_id, &pl->comm);
+        if (rc) {
+            delete pl;
+            return rc;
+        }
+        pl->nzl = (s.N[2] - 2) / s.world;
+    }
     // keep private copies of the caller's tables
     pl->host_tables.resize(4 * 3);
     for (int a = 0; a < s.D; a++) {
@@ -585,12 +609,18 @@ int insb200_plan_create(const insb200_setup_t *setup, insb200_plan_t **out) {
             pl->Iu[c][a][1] = s.N[a] - offset_u(s.bc_u[a][1], true, c == a);
         }
     }
+    std::memcpy(pl->Iu_loc, pl->Iu, sizeof(pl->Iu));
+    if (pl->comm) {
+        pl->ncell = (long long)s.N[0] * s.N[1] * (pl->nzl + 2);
+        for (int c = 0; c < 3; c++) pl->Iu_loc[c][2][0] = 1, pl->Iu_loc[c][2][1] = pl->nzl + 1;
+    }
     int r = pl->f64 ? build_grid<double>(pl, pl->gd) : build_grid<float>(pl, pl->gf);
     if (r) {
         insb200_plan_destroy(pl);
         return r;
     }
     std::memset(&pl->bc, 0, sizeof(pl->bc));
+    pl->bc.comm = pl->comm;
     std::memcpy(pl->bc.bc_u, s.bc_u, sizeof(s.bc_u));
     std::memcpy(pl->bc.bc_temp, s.has_temp ? s.bc_temp : s.bc_u, sizeof(s.bc_u));
     std::memcpy(pl->bc.u_val, s.bc_u_value, sizeof(s.bc_u_value));
@@ -599,7 +629,7 @@ int insb200_plan_create(const insb200_setup_t *setup, insb200_plan_t **out) {
     if (kind == INSB200_PSOLVER_DEFAULT) kind = resolve_default_psolver(pl);
     pl->psolver = kind;
     if (kind != INSB200_PSOLVER_NONE) {
-        r = poisson_create(pl->s, pl->Ip, kind, &pl->ps);
+        r = poisson_create(pl->s, pl->Ip, kind, pl->comm, &pl->ps);
         if (r) {
             insb200_plan_destroy(pl);
             return r;
@@ -630,7 +660,24 @@ int insb200_plan_destroy(insb200_plan_t *pl) {
         cudaEventDestroy(b.b);
     }
     for (auto e : pl->evpool) cudaEventDestroy(e);
+    comm_destroy(pl->comm);
     delete pl;
+    return 0;
+}
+
+int insb200_comm_unique_id(void *id128) {
+    API_BEGIN
+    if (!id128) {
+        set_error("null argument");
+        return 1;
+    }
+    return comm_unique_id(id128);
+    API_END
+}
+int insb200_plan_local_n(const insb200_plan_t *pl, int N_local[3]) {
+    if (!pl || !N_local) return 1;
+    for (int a = 0; a < 3; a++) N_local[a] = a < pl->D ? pl->s.N[a] : 1;
+    if (pl->comm) N_local[2] = pl->nzl + 2;
     return 0;
 }
 
@@ -792,8 +839,9 @@ int insb200_right_hand_side(insb200_plan_t *pl, void *dudt, const void *u, doubl
 int insb200_cfl(insb200_plan_t *pl, const void *u, const insb200_params_t *pr, double *dt_out, void *stream) {
     API_BEGIN
     Launch L = L_of(pl, stream);
-    INSB_TRY(DISPATCH(launch_cfl<float>(pl->gf, pl->Iu, (const float *)u, pl->scratch, L),
-                      launch_cfl<double>(pl->gd, pl->Iu, (const double *)u, pl->scratch, L)));
+    INSB_TRY(DISPATCH(launch_cfl<float>(pl->gf, pl->Iu_loc, (const float *)u, pl->scratch, L),
+                      launch_cfl<double>(pl->gd, pl->Iu_loc, (const double *)u, pl->scratch, L)));
+    if (pl->comm) INSB_TRY(comm_reduce_scratch(pl->comm, pl->scratch, true, L.stream));
     unsigned long long h[2];
     INSB_CUDA(cudaMemcpyAsync(h, pl->scratch, sizeof(h), cudaMemcpyDeviceToHost, L.stream));
     INSB_CUDA(cudaStreamSynchronize(L.stream));
@@ -833,6 +881,7 @@ int insb200_maxabs(insb200_plan_t *pl, const void *u, double *out, void *stream)
     long long n = pl->ncell * pl->D;
     INSB_TRY(DISPATCH(launch_maxabs<float>((const float *)u, n, pl->scratch, L),
                       launch_maxabs<double>((const double *)u, n, pl->scratch, L)));
+    if (pl->comm) INSB_TRY(comm_reduce_scratch(pl->comm, pl->scratch, false, L.stream));
     unsigned long long h[2];
     INSB_CUDA(cudaMemcpyAsync(h, pl->scratch, sizeof(h), cudaMemcpyDeviceToHost, L.stream));
     INSB_CUDA(cudaStreamSynchronize(L.stream));

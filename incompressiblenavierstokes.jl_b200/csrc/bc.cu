@@ -79,8 +79,17 @@ static int offset_p(int bc, bool isright) {
 }
 
 template <typename T>
+static int halo_dim(const Grid<T> &g, const BcDesc &b, T *f, int ncomp, Launch L) {
+    return comm_halo_z(b.comm, f, sizeof(T), g.s[2], g.N[2], ncomp, g.cs, L.stream);
+}
+
+template <typename T>
 int launch_bc_u(const Grid<T> &g, const BcDesc &b, T *u, int dudt, Launch L) {
     for (int beta = 0; beta < g.D; beta++) {
+        if (beta == 2 && b.comm) {
+            INSB_TRY(halo_dim<T>(g, b, u, g.D, L));
+            continue;
+        }
         BcOps ops{};
         ops.ncomp = g.D;
         int n = g.N[beta];
@@ -137,6 +146,10 @@ template <typename T>
 static int scalar_bc(const Grid<T> &g, const BcDesc &b, const int (*types)[2], bool is_temp, T *p,
                      Launch L) {
     for (int beta = 0; beta < g.D; beta++) {
+        if (beta == 2 && b.comm) {  // decomposed direction is periodic for every field
+            INSB_TRY(halo_dim<T>(g, b, p, 1, L));
+            continue;
+        }
         BcOps ops{};
         ops.ncomp = 1;
         int n = g.N[beta];

@@ -12,6 +12,8 @@
 #include <nccl.h>
 
 #include <cstring>
+#include <map>
+#include <mutex>
 
 #include "internal.h"
 
@@ -82,7 +84,14 @@ int load_nccl() {
 struct Comm {
     int rank = 0, world = 1;
     ncclComm_t comm = nullptr;
+    int refs = 1;
+    std::string key;
 };
+
+// One communicator per unique id and process: several plans of the same setup (base plan,
+// psolver plans) share it, since an id can be passed to ncclCommInitRank only once.
+static std::map<std::string, Comm *> g_comms;
+static std::mutex g_comms_mu;
 
 int comm_unique_id(void *id128) {
     INSB_TRY(load_nccl());
@@ -105,7 +114,20 @@ int comm_create(int rank, int world, const void *id128, Comm **out) {
     INSB_TRY(load_nccl());
     ncclUniqueId id;
     std::memcpy(id.internal, id128, NCCL_UNIQUE_ID_BYTES);
+    std::lock_guard<std::mutex> lock(g_comms_mu);
+    std::string key((const char *)id128, NCCL_UNIQUE_ID_BYTES);
+    auto it = g_comms.find(key);
+    if (it != g_comms.end()) {
+        if (it->second->rank != rank || it->second->world != world) {
+            set_error("comm_create: nccl_id already in use with a different (rank, world)");
+            return 1;
+        }
+        it->second->refs++;
+        *out = it->second;
+        return 0;
+    }
     Comm *c = new Comm();
+    c->key = key;
     c->rank = rank;
     c->world = world;
     ncclResult_t r = g_nccl.CommInitRank(&c->comm, world, id, rank);
@@ -114,12 +136,16 @@ int comm_create(int rank, int world, const void *id128, Comm **out) {
         delete c;
         return 1;
     }
+    g_comms[key] = c;
     *out = c;
     return 0;
 }
 
 void comm_destroy(Comm *c) {
     if (!c) return;
+    std::lock_guard<std::mutex> lock(g_comms_mu);
+    if (--c->refs > 0) return;
+    g_comms.erase(c->key);
     if (c->comm) g_nccl.CommDestroy(c->comm);
     delete c;
 }

@@ -194,12 +194,17 @@ __global__ void __launch_bounds__(512, (sizeof(T) == 4 && MODE != 3) ? 2 : 1)
     const int kx = blockIdx.x * L + l;
     const int other = blockIdx.y;
     const int odim = tdim == 1 ? 2 : 1;
-    Cx<T> *base = W + kx + (g.D == 3 ? other * g.ws[odim] : 0);
-    const long long sd = g.ws[tdim];
+    const long long in_sd = g.in_sd >= 0 ? g.in_sd : g.ws[tdim], out_sd = g.out_sd >= 0 ? g.out_sd : g.ws[tdim];
+    const long long in_os = g.in_os >= 0 ? g.in_os : g.ws[odim], out_os = g.out_os >= 0 ? g.out_os : g.ws[odim];
+    const Cx<T> *ibase = (g.in ? (const Cx<T> *)g.in : W) + kx + (g.D == 3 ? other * in_os : 0);
+    Cx<T> *obase = (g.out ? (Cx<T> *)g.out : W) + kx + (g.D == 3 ? other * out_os : 0);
+    const int in_mask = (1 << g.in_sh) - 1, out_mask = (1 << g.out_sh) - 1;
+    auto ioff = [&](int k) { return (long long)(k >> g.in_sh) * g.in_blk + (long long)(k & in_mask) * in_sd; };
+    auto ooff = [&](int k) { return (long long)(k >> g.out_sh) * g.out_blk + (long long)(k & out_mask) * out_sd; };
     LineSmem<T> sm = line_smem<T>(reinterpret_cast<T *>(smem_raw), l, L, LS);
     Cx<T> v[8];
 #pragma unroll
-    for (int m = 0; m < 8; m++) v[m] = base[(long long)(t + P * m) * sd];
+    for (int m = 0; m < 8; m++) v[m] = ibase[ioff(t + P * m)];
     T f[8];
     if (MODE >= 2) {
         // phat = -phat / ((ax + ay) + az), phat[1] = 0 (pressure.jl:360-372); `factor` carries
@@ -211,7 +216,7 @@ __global__ void __launch_bounds__(512, (sizeof(T) == 4 && MODE != 3) ? 2 : 1)
             T den;
             bool zero;
             if (g.D == 3) {
-                int k1 = tdim == 1 ? k : other, k2 = tdim == 1 ? other : k;
+                int k1 = tdim == 1 ? k : other + g.eig_off, k2 = tdim == 1 ? other + g.eig_off : k;
                 den = (e0[kx] + e1[k1]) + e2[k2];
                 zero = (kx | k1 | k2) == 0;
             } else {
@@ -229,7 +234,7 @@ __global__ void __launch_bounds__(512, (sizeof(T) == 4 && MODE != 3) ? 2 : 1)
     }
     if (MODE >= 1) fft_stages<T, N, true, 0>(v, t, sm, tw, exch);
 #pragma unroll
-    for (int m = 0; m < 8; m++) base[(long long)(t + P * m) * sd] = v[m];
+    for (int m = 0; m < 8; m++) obase[ooff(t + P * m)] = v[m];
 }
 
 // ----------------------------------------------------------------------------------------
@@ -349,7 +354,7 @@ static int fast_pass_n(int kind, T *R, Cx<T> *W, const FastGeom &g, int tdim, co
         while (Lt * P > 512 && Lt > 1) Lt >>= 1;
         int LS = line_stride(N, Lt, sizeof(T));
         size_t smem = (size_t)4 * Lt * LS * sizeof(T);
-        dim3 grid(g.m0p / Lt, g.D == 3 ? g.n[tdim == 1 ? 2 : 1] : 1);
+        dim3 grid(g.m0p / Lt, g.D == 3 ? (g.nother >= 0 ? g.nother : g.n[tdim == 1 ? 2 : 1]) : 1);
         static const bool uncapped = getenv("INSB200_FFT_MID_UNCAPPED") != nullptr;
         auto kern = kind == 0 ? fft_strided_kernel<T, N, 0> : kind == 1 ? fft_strided_kernel<T, N, 1>
                     : uncapped ? fft_strided_kernel<T, N, 3> : fft_strided_kernel<T, N, 2>;

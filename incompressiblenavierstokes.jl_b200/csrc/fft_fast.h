@@ -10,6 +10,17 @@ struct FastGeom {
     int m0p;          // padded half-spectrum extent along x (multiple of the tile)
     long long ws[3];  // complex workspace strides
     long long rs[3];  // ghosted real strides
+    // Strided passes only -- generalised addressing used by the slab-decomposed solve
+    // (defaults reproduce the in-place pass on W with strides ws).  Element k of the line is at
+    //   (k >> sh) * blk + (k & ((1 << sh) - 1)) * sd      (sh = 30: plain stride sd)
+    // and the companion index `other` (blockIdx.y) contributes other * os.
+    const void *in = nullptr;
+    void *out = nullptr;
+    long long in_sd = -1, in_os = -1, in_blk = 0;
+    long long out_sd = -1, out_os = -1, out_blk = 0;
+    int in_sh = 30, out_sh = 30;
+    int nother = -1;   // extent of the companion index; -1 = n[other dim]
+    int eig_off = 0;   // added to `other` for the eigenvalue lookup (ky offset of this rank)
 };
 
 bool fast_fft_supported(int n);

@@ -54,8 +54,21 @@ struct Grid {
     const T *wb[3];    // Δ[i]  /(Δ[i]+Δ[i+1])
 };
 
+// ---- comm.cu: z-slab decomposition, one process per GPU over NCCL ----
+struct Comm;
+int comm_unique_id(void *id128);
+int comm_create(int rank, int world, const void *id128, Comm **out);
+void comm_destroy(Comm *c);
+int comm_rank(const Comm *c);   // 0 for nullptr
+int comm_world(const Comm *c);  // 1 for nullptr
+int comm_halo_z(Comm *c, void *field, size_t esz, long long plane, int nplanes, int ncomp, long long cs,
+                cudaStream_t st);
+int comm_all_to_all(Comm *c, const void *send, void *recv, size_t block_bytes, cudaStream_t st);
+int comm_reduce_scratch(Comm *c, double *scratch, bool is_min, cudaStream_t st);
+
 // Boundary description used by the ghost-fill kernels.
 struct BcDesc {
+    Comm *comm;  // non-null: dimension 2 is decomposed into slabs, its ghost planes come from the neighbours
     int bc_u[3][2];
     int bc_temp[3][2];
     double u_val[3][2][3];
@@ -124,7 +137,7 @@ int launch_bc_temp(const Grid<T> &g, const BcDesc &b, T *temp, Launch L);
 
 // ---- poisson.cu ----
 struct Poisson;  // opaque
-int poisson_create(const insb200_setup_t &s, const int Ip[3][2], int kind, Poisson **out);
+int poisson_create(const insb200_setup_t &s, const int Ip[3][2], int kind, Comm *comm, Poisson **out);
 void poisson_destroy(Poisson *p);
 long long poisson_bytes(const Poisson *p);
 int poisson_solve(Poisson *ps, void *p_ghosted, Launch L);

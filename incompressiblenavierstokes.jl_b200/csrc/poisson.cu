@@ -413,6 +413,13 @@ struct Poisson {
     int max_smem = 0;
     bool fast = false;  // power-of-two all-periodic path (fft_fast.cu)
     int tile = 8;
+    // z-slab decomposition (world > 1): W holds this rank's nzl planes in natural layout;
+    // S / Rv are the send / receive sides of the all-to-all transposes (comm.cu), laid out as
+    // [world blocks][nzl planes][n1/world ky rows][m0p] and, equivalently on the receiving
+    // side, [n3 planes][n1/world ky rows][m0p].
+    Comm *comm = nullptr;
+    int nzl = 0, kyl = 0;
+    void *S = nullptr, *Rv = nullptr;
 };
 
 static bool factorize(int n, std::vector<int> &rad) {
@@ -569,8 +576,9 @@ static int build_tables(Poisson *ps, const insb200_setup_t &s, const int Ip[3][2
     return 0;
 }
 
-int poisson_create(const insb200_setup_t &s, const int Ip[3][2], int kind, Poisson **out) {
+int poisson_create(const insb200_setup_t &s, const int Ip[3][2], int kind, Comm *comm, Poisson **out) {
     Poisson *ps = new Poisson();
+    ps->comm = comm;
     ps->D = s.D;
     ps->kind = kind;
     ps->f64 = s.dtype == INSB200_F64;
@@ -636,14 +644,34 @@ int poisson_create(const insb200_setup_t &s, const int Ip[3][2], int kind, Poiss
                 return fail("unsupported transform length (prime factors must be in {2,3,5,7,11,13})");
     }
     long long pitch = (ps->m[0] + 7) / 8 * 8;
+    const int world = comm_world(comm);
+    ps->nzl = D == 3 ? ps->n[2] / world : 1;
+    ps->kyl = ps->n[1] / world;
+    if (world > 1) {
+        bool ok = kind == INSB200_PSOLVER_SPECTRAL && D == 3;
+        for (int a = 0; a < D; a++) ok = ok && fast_fft_supported(ps->n[a]);
+        if (!ok)
+            return fail("world > 1: only psolver_spectral on 3-D power-of-two grids (32..2048 per dim) is decomposed");
+        if (ps->n[2] % world || ps->n[1] % world || (ps->kyl & (ps->kyl - 1)))
+            return fail("world > 1: n2 and n3 must be divisible by the number of ranks (power of two)");
+    }
     ps->wstride[0] = 1;
     ps->wstride[1] = pitch;
     ps->wstride[2] = pitch * ps->m[1];
     size_t esz = ps->f64 ? 16 : 8;
-    size_t wbytes = (size_t)pitch * ps->m[1] * (D == 3 ? ps->m[2] : 1) * esz;
+    size_t wbytes = (size_t)pitch * ps->m[1] * (D == 3 ? (world > 1 ? ps->nzl : ps->m[2]) : 1) * esz;
     if (cudaMalloc(&ps->W, wbytes) != cudaSuccess) return fail("cudaMalloc of the spectral workspace failed");
     cudaMemset(ps->W, 0, wbytes);
     ps->bytes += (long long)wbytes;
+    if (world > 1) {
+        if (cudaMalloc(&ps->S, wbytes) != cudaSuccess || cudaMalloc(&ps->Rv, wbytes) != cudaSuccess)
+            return fail("cudaMalloc of the transpose buffers failed");
+        ps->owned.push_back(ps->S);
+        ps->owned.push_back(ps->Rv);
+        cudaMemset(ps->S, 0, wbytes);
+        cudaMemset(ps->Rv, 0, wbytes);
+        ps->bytes += 2 * (long long)wbytes;
+    }
     int r = ps->f64 ? build_tables<double>(ps, s, Ip) : build_tables<float>(ps, s, Ip);
     if (r) {
         poisson_destroy(ps);
@@ -720,6 +748,49 @@ static int solve_t(Poisson *ps, T *p, Launch L) {
         const T factor = (T)(ps->sign * ps->scale);
         const T *e0 = (const T *)ps->eig[0], *e1 = (const T *)ps->eig[1], *e2 = (const T *)ps->eig[2];
         const int tl = ps->tile;
+        if (ps->comm) {
+            // x, y on the z-slab; transpose to ky-slabs; z (forward, divide, inverse); back.
+            const int world = comm_world(ps->comm), rank = comm_rank(ps->comm);
+            const int kyl = ps->kyl, nzl = ps->nzl;
+            const long long m0p = g.m0p;
+            const long long blk = m0p * kyl * nzl;  // complex elements per peer block
+            int sh = 0;
+            while ((1 << sh) < kyl) sh++;
+            FastGeom gx = g;  // x passes see only the local planes
+            gx.n[2] = nzl;
+            INSB_TRY(fast_pass<T>(3, ps->n[0], R, ps->W, gx, 0, ps->tw[0], e0, e1, e2, factor, tl, L));
+            FastGeom gy = g;  // y forward: W (natural) -> S (blocked by destination rank)
+            gy.nother = nzl;
+            gy.in = ps->W;
+            gy.out = ps->S;
+            gy.out_sd = m0p;
+            gy.out_os = m0p * kyl;
+            gy.out_sh = sh;
+            gy.out_blk = blk;
+            INSB_TRY(fast_pass<T>(0, ps->n[1], R, ps->W, gy, 1, ps->tw[1], e0, e1, e2, factor, tl, L));
+            INSB_TRY(comm_all_to_all(ps->comm, ps->S, ps->Rv, (size_t)blk * sizeof(Cx<T>), L.stream));
+            FastGeom gz = g;  // z: in place on Rv = [n3][kyl][m0p]
+            gz.nother = kyl;
+            gz.in = ps->Rv;
+            gz.out = ps->Rv;
+            gz.in_sd = gz.out_sd = m0p * kyl;
+            gz.in_os = gz.out_os = m0p;
+            gz.eig_off = rank * kyl;
+            INSB_TRY(fast_pass<T>(2, ps->n[2], R, ps->W, gz, 2, ps->tw[2], e0, e1, e2, factor, tl, L));
+            INSB_TRY(comm_all_to_all(ps->comm, ps->Rv, ps->S, (size_t)blk * sizeof(Cx<T>), L.stream));
+            FastGeom gi = g;  // y inverse: S (blocked by source rank) -> W (natural)
+            gi.nother = nzl;
+            gi.in = ps->S;
+            gi.out = ps->W;
+            gi.in_sd = m0p;
+            gi.in_os = m0p * kyl;
+            gi.in_sh = sh;
+            gi.in_blk = blk;
+            INSB_TRY(fast_pass<T>(1, ps->n[1], R, ps->W, gi, 1, ps->tw[1], e0, e1, e2, factor, tl, L));
+            INSB_TRY(fast_pass<T>(4, ps->n[0], R, ps->W, gx, 0, ps->tw[0], e0, e1, e2, factor, tl, L));
+            (void)world;
+            return 0;
+        }
         INSB_TRY(fast_pass<T>(3, ps->n[0], R, ps->W, g, 0, ps->tw[0], e0, e1, e2, factor, tl, L));
         if (D == 3) {
             INSB_TRY(fast_pass<T>(0, ps->n[1], R, ps->W, g, 1, ps->tw[1], e0, e1, e2, factor, tl, L));

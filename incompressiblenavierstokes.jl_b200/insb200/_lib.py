@@ -36,6 +36,7 @@ class SetupStruct(C.Structure):
         ("device", C.c_int),
         ("rank", C.c_int),
         ("world", C.c_int),
+        ("nccl_id", C.c_void_p),
     ]
 
 
@@ -58,6 +59,8 @@ _PROTOTYPES = {
     "insb200_version": (C.c_int, []),
     "insb200_plan_create": (C.c_int, [C.POINTER(SetupStruct), C.POINTER(_P)]),
     "insb200_plan_destroy": (C.c_int, [_P]),
+    "insb200_comm_unique_id": (C.c_int, [_P]),
+    "insb200_plan_local_n": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "insb200_plan_psolver": (C.c_int, [_P]),
     "insb200_plan_workspace_bytes": (C.c_longlong, [_P]),
     "insb200_apply_bc_u": (C.c_int, [_P, _P, C.c_double, C.c_int, _P]),

@@ -76,7 +76,11 @@ class Plan:
         s.psolver = psolver
         s.tridiagonal_dir = tridiagonal_dir
         s.device = torch.cuda.current_device() if setup.device is None else int(setup.device)
-        s.rank, s.world = 0, 1
+        s.rank, s.world = setup.rank, setup.world
+        if setup.world > 1:
+            idbuf = C.create_string_buffer(bytes(setup.nccl_id), 128)
+            self._keep.append(idbuf)
+            s.nccl_id = C.cast(idbuf, C.c_void_p)
         h = C.c_void_p()
         check(lib().insb200_plan_create(C.byref(s), C.byref(h)))
         self.h = h
@@ -137,17 +141,58 @@ def _dev(setup):
 
 
 def scalarfield(setup):
-    return torch.zeros(tuple(reversed(setup.N)), dtype=_TORCH_DTYPE[setup.T], device=_dev(setup))
+    return torch.zeros(tuple(reversed(setup.N_local)), dtype=_TORCH_DTYPE[setup.T], device=_dev(setup))
 
 
 def vectorfield(setup):
-    return torch.zeros((setup.D,) + tuple(reversed(setup.N)), dtype=_TORCH_DTYPE[setup.T], device=_dev(setup))
+    return torch.zeros((setup.D,) + tuple(reversed(setup.N_local)), dtype=_TORCH_DTYPE[setup.T], device=_dev(setup))
+
+
+def local_slab(setup, arr):
+    """This rank's planes (ghosts included) of a GLOBAL array in the reference layout
+    ((N1,N2,N3[,D])); the identity for world == 1."""
+    if setup.world == 1:
+        return arr
+    return arr[:, :, setup.zoff: setup.zoff + setup.nzl + 2]
 
 
 def to_device(setup, arr):
-    """NumPy array in the reference layout ((N1,N2[,N3][,D]), any order) -> torch CUDA tensor."""
+    """NumPy array in the reference layout ((N1,N2[,N3][,D]), any order) -> torch CUDA tensor.
+    A GLOBAL array is cut down to this rank's slab when world > 1."""
+    if setup.world > 1 and arr.shape[2] == setup.N[2]:
+        arr = local_slab(setup, arr)
     a = np.asfortranarray(arr, dtype=setup.T)
     return torch.from_numpy(np.ascontiguousarray(a.T)).to(_dev(setup))
+
+
+def comm_unique_id():
+    """128-byte NCCL unique id (insb200_comm_unique_id); create on rank 0, share with all ranks."""
+    buf = C.create_string_buffer(128)
+    check(lib().insb200_comm_unique_id(C.cast(buf, C.c_void_p)))
+    return buf.raw
+
+
+def share_unique_id():
+    """Rank 0 of the initialised torch.distributed group creates the id, everybody gets it."""
+    import torch.distributed as dist
+
+    obj = [comm_unique_id() if dist.get_rank() == 0 else None]
+    dist.broadcast_object_list(obj, src=0)
+    return obj[0]
+
+
+def gather_global(setup, t):
+    """All ranks: assemble the GLOBAL ghosted array (reference layout, NumPy) from the slabs.
+    Interior planes come from their owners; the two global ghost planes from the end ranks."""
+    if setup.world == 1:
+        return to_host(t)
+    import torch.distributed as dist
+
+    loc = to_host(t)  # (N1, N2, nzl+2[, D])
+    parts = [None] * setup.world
+    dist.all_gather_object(parts, loc)
+    inner = [p[:, :, 1:-1] for p in parts]
+    return np.concatenate([parts[0][:, :, :1]] + inner + [parts[-1][:, :, -1:]], axis=2)
 
 
 def to_host(t):
@@ -156,7 +201,7 @@ def to_host(t):
 
 
 def _chk(setup, t, vector):
-    want = ((setup.D,) if vector else ()) + tuple(reversed(setup.N))
+    want = ((setup.D,) if vector else ()) + tuple(reversed(setup.N_local))
     if tuple(t.shape) != want or not t.is_contiguous() or not t.is_cuda:
         raise ValueError(f"expected a contiguous CUDA tensor of shape {want}, got {tuple(t.shape)}")
     if t.dtype != _TORCH_DTYPE[setup.T]:
@@ -408,9 +453,9 @@ def propose_timestep(force, state, setup, params, plan=None):
     return setup.T(out.value)
 
 
-def maxabs(u, setup):
+def maxabs(u, setup, plan=None):
     out = C.c_double()
-    check(lib().insb200_maxabs(_base_plan(setup).h, _ptr(u), C.byref(out), _stream()))
+    check(lib().insb200_maxabs((plan or _base_plan(setup)).h, _ptr(u), C.byref(out), _stream()))
     return out.value
 
 
@@ -544,15 +589,17 @@ def create_right_hand_side(setup, psolver):
 # ------------------------------------------------------------------------------------
 def velocityfield(setup, ufunc, t=0.0, *, psolver=None, doproject=True):
     D = setup.D
-    u = np.zeros(setup.N + (D,), dtype=setup.T, order="F")
+    u = np.zeros(setup.N_local + (D,), dtype=setup.T, order="F")
     for a in range(D):
-        xs = []
+        xs, sl = [], []
         for b in range(D):
-            lo, hi = setup.Iu[a][b]
+            lo, hi = setup.local_range(setup.Iu[a][b], b)
+            off = setup.zoff if (b == 2 and setup.world > 1) else 0
             shape = [1] * D
             shape[b] = hi - lo
-            xs.append(setup.xu[a][b][lo:hi].reshape(shape))
-        u[setup.slices(setup.Iu[a]) + (a,)] = np.asarray(ufunc(a, *xs), dtype=setup.T)
+            xs.append(setup.xu[a][b][lo + off:hi + off].reshape(shape))
+            sl.append(slice(lo, hi))
+        u[tuple(sl) + (a,)] = np.asarray(ufunc(a, *xs), dtype=setup.T)
     ud = to_device(setup, u)
     apply_bc_u_(ud, t, setup)
     if doproject:
@@ -564,13 +611,15 @@ def velocityfield(setup, ufunc, t=0.0, *, psolver=None, doproject=True):
 
 def temperaturefield(setup, tempfunc, t=0.0):
     D = setup.D
-    temp = np.zeros(setup.N, dtype=setup.T, order="F")
-    xs = []
+    temp = np.zeros(setup.N_local, dtype=setup.T, order="F")
+    xs, sl = [], []
     for b in range(D):
-        lo, hi = setup.Ip[b]
+        lo, hi = setup.local_range(setup.Ip[b], b)
+        off = setup.zoff if (b == 2 and setup.world > 1) else 0
         shape = [1] * D
         shape[b] = hi - lo
-        xs.append(setup.xp[b][lo:hi].reshape(shape))
-    temp[setup.slices(setup.Ip)] = np.asarray(tempfunc(*xs), dtype=setup.T)
+        xs.append(setup.xp[b][lo + off:hi + off].reshape(shape))
+        sl.append(slice(lo, hi))
+    temp[tuple(sl)] = np.asarray(tempfunc(*xs), dtype=setup.T)
     td = to_device(setup, temp)
     return apply_bc_temp_(td, t, setup)

@@ -99,7 +99,10 @@ class Setup:
     demand by :mod:`insb200.api` and cached per psolver kind.
     """
 
-    def __init__(self, x, boundary_conditions, device=None):
+    def __init__(self, x, boundary_conditions, device=None, rank=0, world=1, nccl_id=None):
+        """``rank``/``world``/``nccl_id`` describe the z-slab decomposition (one process per
+        GPU): ``x`` and the BCs are always those of the GLOBAL grid; this rank then owns the
+        z planes ``[rank*nzl, rank*nzl + nzl + 2)`` of every ghosted array (``N_local``)."""
         xs = [np.array(v) for v in x]
         T = xs[0].dtype.type if xs[0].dtype.type in (np.float32, np.float64) else np.float64
         xs = [v.astype(T) for v in xs]
@@ -166,6 +169,27 @@ class Setup:
             A2.append(np.ascontiguousarray(np.concatenate((w2, [1])), dtype=T))
         self.A1, self.A2 = tuple(A1), tuple(A2)
         self._plans = {}
+        # z-slab decomposition
+        self.rank, self.world, self.nccl_id = int(rank), int(world), nccl_id
+        if self.world > 1:
+            if D != 3 or not self.is_periodic(2):
+                raise ValueError("world > 1 needs a 3-D grid that is periodic in z")
+            if (N[2] - 2) % self.world:
+                raise ValueError("the number of z volumes must be divisible by world")
+            if nccl_id is None or len(nccl_id) != 128:
+                raise ValueError("world > 1 needs the 128-byte nccl_id shared by all ranks")
+        self.nzl = (N[2] - 2) // self.world if D == 3 else 1
+        self.zoff = self.rank * self.nzl if self.world > 1 else 0
+        self.N_local = N if self.world == 1 else (N[0], N[1], self.nzl + 2)
+
+    def local_range(self, rng, d):
+        """Half-open global index range ``rng`` of dim ``d`` clipped to this rank's slab and
+        shifted to local indices (ghost planes excluded from ownership)."""
+        lo, hi = rng
+        if self.world == 1 or d != 2:
+            return lo, hi
+        glo, ghi = max(lo, self.zoff + 1), min(hi, self.zoff + self.nzl + 1)
+        return glo - self.zoff, max(ghi, glo) - self.zoff
 
     # -- helpers -------------------------------------------------------------------------
     def is_periodic(self, d):

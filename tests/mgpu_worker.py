@@ -1,0 +1,127 @@
+"""Worker of the multi-GPU equality tests ("P-GPU result == 1-GPU result").
+
+Run under torchrun, one process per GPU:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tests/mgpu_worker.py [--grid 64 32 64] [--dtype f64]
+
+Every rank builds the same seeded global field, keeps its z-slab, and runs projection,
+RK44 / LMWray3 steps, the CFL and max-abs reductions through the slab-decomposed plan;
+rank 0 repeats everything with a world == 1 plan on its own GPU and compares.
+Prints one JSON line per case on rank 0; exit code 1 on any mismatch.
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "incompressiblenavierstokes.jl_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+def rel(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--grid", type=int, nargs=3, default=[64, 32, 64])
+    ap.add_argument("--dtype", default="f64")
+    ap.add_argument("--steps", type=int, default=2)
+    args = ap.parse_args()
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl")
+    import insb200 as I
+
+    T = np.float64 if args.dtype == "f64" else np.float32
+    tol = 1e-12 if T is np.float64 else 1e-5
+    n = args.grid
+    x = tuple(np.linspace(0.0, 1.0, m + 1).astype(T) for m in n)
+    bcs = {"u": ((I.PeriodicBC(), I.PeriodicBC()),) * 3}
+    nid = I.share_unique_id()
+    sd = I.Setup(x, bcs, rank=rank, world=world, nccl_id=nid)
+    s1 = I.Setup(x, bcs) if rank == 0 else None
+    psd = I.psolver_spectral(sd)
+    ps1 = I.psolver_spectral(s1) if rank == 0 else None
+
+    rng = np.random.default_rng(7)
+    ug = np.asfortranarray(rng.standard_normal(sd.N + (3,)).astype(T))
+    pg = np.asfortranarray(rng.standard_normal(sd.N).astype(T))
+    ok = True
+    out = []
+
+    def report(name, err, lim):
+        nonlocal ok
+        good = bool(err <= lim)
+        ok = ok and good
+        out.append({"case": name, "err": err, "tol": lim, "ok": good})
+
+    # ---- ghost fills + projection -------------------------------------------------------
+    ud = I.to_device(sd, ug)
+    I.apply_bc_u_(ud, 0.0, sd, plan=psd.plan)
+    pd = I.scalarfield(sd)
+    I.project_(ud, sd, psolver=psd, p=pd)
+    I.apply_bc_u_(ud, 0.0, sd, plan=psd.plan)
+    div_d = I.divergence_(I.scalarfield(sd), ud, sd)
+    got_u = I.gather_global(sd, ud)
+    got_div = I.gather_global(sd, div_d)
+    # ---- Poisson solve alone ------------------------------------------------------------
+    pd2 = I.to_device(sd, pg)
+    psd(pd2)
+    I.apply_bc_p_(pd2, 0.0, sd, plan=psd.plan)
+    got_p = I.gather_global(sd, pd2)
+    # ---- time stepping ------------------------------------------------------------------
+    dt = T(2e-3)
+    params = dict(viscosity=2e-3)
+    res = {}
+    for name, method in (("RK44", I.RKMethods.RK44(T)), ("LMWray3", I.LMWray3(T))):
+        st = I.create_stepper(method, setup=sd, psolver=psd, state={"u": ud.clone()}, t=0.0)
+        for _ in range(args.steps):
+            st = I.timestep_(method, I.navierstokes_, st, dt, params=params)
+        res[name] = I.gather_global(sd, st["state"]["u"])
+        res[name + "_cfl"] = float(I.propose_timestep(I.navierstokes_, st["state"], sd, params, plan=psd.plan))
+        res[name + "_umax"] = I.maxabs(st["state"]["u"], sd, plan=psd.plan)
+
+    if rank == 0:
+        u1 = I.to_device(s1, ug)
+        I.apply_bc_u_(u1, 0.0, s1)
+        p1 = I.scalarfield(s1)
+        I.project_(u1, s1, psolver=ps1, p=p1)
+        I.apply_bc_u_(u1, 0.0, s1)
+        report("project", rel(got_u, I.to_host(u1)), tol)
+        inner = (slice(1, -1),) * 3
+        report("divergence_after_project", float(np.abs(got_div[inner]).max()), 1e-10 if T is np.float64 else 2e-3)
+        p1b = I.to_device(s1, pg)
+        ps1(p1b)
+        I.apply_bc_p_(p1b, 0.0, s1)
+        report("psolve", rel(got_p, I.to_host(p1b)), tol)
+        for name, method in (("RK44", I.RKMethods.RK44(T)), ("LMWray3", I.LMWray3(T))):
+            st = I.create_stepper(method, setup=s1, psolver=ps1, state={"u": u1.clone()}, t=0.0)
+            for _ in range(args.steps):
+                st = I.timestep_(method, I.navierstokes_, st, dt, params=params)
+            report(name, rel(res[name], I.to_host(st["state"]["u"])), tol)
+            c1 = float(I.propose_timestep(I.navierstokes_, st["state"], s1, params, plan=ps1.plan))
+            report(name + "_cfl", abs(res[name + "_cfl"] - c1) / c1, 1e-6)
+            m1 = I.maxabs(st["state"]["u"], s1)
+            report(name + "_umax", abs(res[name + "_umax"] - m1) / m1, 1e-6)
+        for o in out:
+            o.update(world=world, n=n, dtype=args.dtype)
+            print(json.dumps(o), flush=True)
+    flag = torch.tensor([0 if ok else 1], device="cuda")
+    dist.all_reduce(flag)
+    dist.destroy_process_group()
+    sys.exit(1 if int(flag.item()) else 0)
+
+
+if __name__ == "__main__":
+    main()
