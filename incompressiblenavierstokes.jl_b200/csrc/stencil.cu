@@ -53,12 +53,12 @@ __device__ __forceinline__ void stage_cell(const Grid<T> &g, const StageArgs<T> 
 }
 
 template <typename T, typename CT, int D, bool BOUSS, bool FULL>
-__global__ void __launch_bounds__(256) stage_direct_kernel(Grid<T> g, StageArgs<T> a) {
+__global__ void __launch_bounds__(256) stage_direct_kernel(Grid<T> g, StageArgs<T> a, int xb, int xe) {
     int I[3];
-    I[0] = blockIdx.x * blockDim.x + threadIdx.x;
+    I[0] = xb + blockIdx.x * blockDim.x + threadIdx.x;  // cells xb <= I0 < xe
     I[1] = blockIdx.y * blockDim.y + threadIdx.y;
     I[2] = (D == 3) ? (int)blockIdx.z : 0;
-    if (I[0] >= g.N[0] || I[1] >= g.N[1]) return;
+    if (I[0] >= xe || I[1] >= g.N[1]) return;
     long long idx = I[0] + I[1] * g.s[1] + (D == 3 ? I[2] * g.s[2] : 0);
     bool interior = I[0] >= 1 && I[0] < g.N[0] - 1 && I[1] >= 1 && I[1] < g.N[1] - 1 &&
                     (D == 2 || (I[2] >= 1 && I[2] < g.N[2] - 1));
@@ -248,6 +248,353 @@ __global__ void __launch_bounds__(TX *TY) stage_tile_kernel(Grid<T> g, StageDev<
     }
 }
 
+
+// ------------------------------------------------------------------------------------
+// stage kernel v3 ("pair" kernel): like the marching kernel above, but
+//   * every thread owns TWO x-adjacent cells and does its arithmetic on 2-wide values:
+//     packed FP32 (FFMA2/FADD2/FMUL2, sm_100) halves the issue slots of the flop-heavy
+//     stencil, which is what bounded v2 (307 instructions per cell, 63 % issue-active);
+//   * the z-direction face fluxes are carried in registers from one plane to the next
+//     (the bottom face of cell z is the top face of cell z-1), so only planes z and z+1
+//     are read from shared memory (3-slot ring) and 3 of the 18 face fluxes disappear;
+//   * -nu/Δ, -nu/Δu and A/2 are folded into the metric tables once per block.
+// Face flux of component i through a j-face at J (src/operators.jl:378-393,556):
+//   i == j: ((u_i[J-e_i] + u_i[J])/2)^2 - nu (u_i[J] - u_i[J-e_i]) / Δ_i[J_i]
+//   i != j: (u_i[J] + u_i[J+e_j])/2 * (A2_i u_j[J] + A1_i u_j[J+e_i]) - nu (u_i[J+e_j] - u_i[J]) / Δu_j[J_j]
+// ------------------------------------------------------------------------------------
+template <typename T>
+struct PairOf;
+template <>
+struct PairOf<float> {
+    typedef float2 type;
+};
+template <>
+struct PairOf<double> {
+    typedef double2 type;
+};
+__device__ __forceinline__ float2 pfma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 padd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 pmul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 psub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
+__device__ __forceinline__ float2 pbc(float v) { return make_float2(v, v); }
+__device__ __forceinline__ float2 pmk(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ double2 pfma(double2 a, double2 b, double2 c) {
+    return make_double2(fma(a.x, b.x, c.x), fma(a.y, b.y, c.y));
+}
+__device__ __forceinline__ double2 padd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 pmul(double2 a, double2 b) { return make_double2(a.x * b.x, a.y * b.y); }
+__device__ __forceinline__ double2 psub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 pbc(double v) { return make_double2(v, v); }
+__device__ __forceinline__ double2 pmk(double a, double b) { return make_double2(a, b); }
+
+// diagonal face flux: lo, hi = u_i on the two sides of the face, mnrd = -nu/Δ_i at the face
+template <typename P>
+__device__ __forceinline__ P flux_diag(P lo, P hi, P mnrd, P quarter) {
+    P m = padd(lo, hi);
+    P d = psub(hi, lo);
+    return pfma(mnrd, d, pmul(pmul(m, m), quarter));
+}
+// off-diagonal face flux: a0, a1 = u_i at J, J+e_j; b0, b1 = u_j at J, J+e_i;
+// hw2, hw1 = A2_i/2, A1_i/2; mnrd = -nu/Δu_j at the face
+template <typename P>
+__device__ __forceinline__ P flux_off(P a0, P a1, P b0, P b1, P hw2, P hw1, P mnrd) {
+    P s = padd(a0, a1);
+    P w = pfma(hw1, b1, pmul(hw2, b0));
+    P d = psub(a1, a0);
+    return pfma(s, w, pmul(mnrd, d));
+}
+
+// v (+)= c * k on pairs with separately rounded multiply and add, like the reference broadcast
+// `u + Δt*A[i,j]*k` (step_explicit_runge_kutta.jl:28-32); CT is the coefficient/evaluation type
+template <typename T, typename CT>
+struct PairAxpy {
+    typedef typename PairOf<T>::type P;
+    static __device__ __forceinline__ P run(P x, CT c, P k) {
+        return pmk(axpy_ct<T, CT>(x.x, c, k.x), axpy_ct<T, CT>(x.y, c, k.y));
+    }
+};
+template <>
+struct PairAxpy<float, float> {
+    static __device__ __forceinline__ float2 run(float2 x, float c, float2 k) {
+        return __fadd2_rn(x, __fmul2_rn(make_float2(c, c), k));
+    }
+};
+
+// cp.async (LDGSTS) of one element, and group bookkeeping
+template <typename T>
+__device__ __forceinline__ void cp_async_elem(T *smem_dst, const T *gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    if (sizeof(T) == 4)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Shared-memory footprint of the pair kernel (elements of T), shared by kernel and launcher.
+template <int TY, int ZC, int DEPTH, bool ACC>
+struct PairSmem {
+    static constexpr int TXC = 64, PX = TXC + 4, PY = TY + 2, NE = 3 * PX * PY, NT = 32 * TY;
+    static constexpr int NS = DEPTH + 2;                 // velocity planes z .. z+1+DEPTH
+    static constexpr int NPW = DEPTH + 1;                // pointwise planes z .. z+DEPTH
+    static constexpr int PWE = (ACC ? 2 : 1) * 3 * NT * 2;  // elements per pointwise slot
+    static constexpr int ZT = ZC + 2;
+    static constexpr int total = NS * NE + NPW * PWE + 6 * ZT * 2;
+};
+
+// Memory pipeline: all global reads are cp.async copies issued DEPTH planes ahead of their use
+// (velocity planes into a (DEPTH+2)-slot ring shared by the block; the pointwise operands
+// vbase / acc_in of a thread's own two cells into a private (DEPTH+1)-slot ring), so that
+// 2 x DEPTH x ~20 KB are in flight per SM with only 16 resident warps.
+// One pair (two consecutive elements, naturally aligned) per cp.async
+template <typename T>
+__device__ __forceinline__ void cp_async_pair(T *smem_dst, const T *gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    if (sizeof(T) == 4)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+    else
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+
+// AL8: N0 is even and the arrays are pair-aligned, so x tiles start at EVEN cell indices
+// (tile bx covers cells 64 bx .. 64 bx + 63) and every global access of a cell pair is one
+// naturally aligned 8-/16-byte transaction (cp.async of pairs, STG.64/128).  Otherwise tiles
+// start at cell 1 and pairs are moved as two scalars.
+template <typename T, typename CT, int TY, int ZC, int DEPTH, bool ACC, bool GEN, bool AL8>
+__global__ void __launch_bounds__(32 * TY, sizeof(T) == 4 ? 2 : 1) stage_pair_kernel(Grid<T> g, StageDev<T, CT> a) {
+    typedef typename PairOf<T>::type P;
+    typedef PairSmem<TY, ZC, DEPTH, ACC> SM;
+    constexpr int TXC = SM::TXC, LX = TXC + 2, PX = SM::PX, PY = SM::PY, PLANE = PX * PY, NE = SM::NE;
+    constexpr int NT = SM::NT, NLD = 3 * PY * LX, NL = (NLD + NT - 1) / NT, ZT = SM::ZT, NS = SM::NS, NPW = SM::NPW;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *s = reinterpret_cast<T *>(smem_raw);              // [NS slots][3 comps][PY][PX]; cell x0 sits at column 2
+    T *pw = s + NS * NE;                                 // [NPW slots][arrays][3 comps][NT] pairs
+    P *zt = reinterpret_cast<P *>(pw + NPW * SM::PWE);   // [6 tables][ZT] of (v, v) pairs
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
+    const int x0 = (AL8 ? 0 : 1) + blockIdx.x * TXC, y0 = 1 + blockIdx.y * TY;
+    const int zbeg = 1 + blockIdx.z * ZC;
+    const int zend = min(zbeg + ZC, g.N[2] - 1);
+    if (zbeg >= zend) return;
+    const T nu = a.nu;
+    // this thread's share of a haloed plane; loop-invariant 32-bit offsets from a running plane pointer
+    // (the three components are contiguous, 3 * cs < 2^32 is checked by the host).
+    //  !AL8: element e = (comp, py, px), px in [0, LX) <-> gx = x0 - 1 + px
+    //   AL8: NLC pair chunks (comp, py, j) <-> cells x0 + 2j, x0 + 2j + 1, plus one halo single for
+    //        the first 6 PY threads (comp, py, side)
+    constexpr int NCH = 3 * PY * (TXC / 2), NLC = (NCH + NT - 1) / NT, NG = AL8 ? NLC + 1 : NL;
+    unsigned goff[NG];
+    int soff[NG];
+    if (AL8) {
+#pragma unroll
+        for (int i = 0; i < NLC; i++) {
+            int e = min(tid + i * NT, NCH - 1);
+            int c = e / (PY * (TXC / 2)), r = e - c * (PY * (TXC / 2));
+            int py = r / (TXC / 2), j = r - py * (TXC / 2);
+            int gx = min(x0 + 2 * j, g.N[0] - 2), gy = min(y0 - 1 + py, g.N[1] - 1);
+            goff[i] = (unsigned)(c * g.cs + gx + (long long)gy * g.s[1]);
+            soff[i] = c * PLANE + py * PX + 2 + 2 * j;
+        }
+        int e = min(tid, 6 * PY - 1);
+        int c = e / (2 * PY), r = e - c * (2 * PY);
+        int py = r >> 1, side = r & 1;
+        int gx = side ? min(x0 + TXC, g.N[0] - 1) : max(x0 - 1, 0), gy = min(y0 - 1 + py, g.N[1] - 1);
+        goff[NLC] = (unsigned)(c * g.cs + gx + (long long)gy * g.s[1]);
+        soff[NLC] = c * PLANE + py * PX + (side ? TXC + 2 : 1);
+    } else {
+#pragma unroll
+        for (int i = 0; i < NL; i++) {
+            int e = min(tid + i * NT, NLD - 1);
+            int c = e / (PY * LX), r = e - c * (PY * LX);
+            int py = r / LX, px = r - py * LX;
+            int gx = min(x0 - 1 + px, g.N[0] - 1), gy = min(y0 - 1 + py, g.N[1] - 1);
+            goff[i] = (unsigned)(c * g.cs + gx + (long long)gy * g.s[1]);
+            soff[i] = c * PLANE + py * PX + px + 1;
+        }
+    }
+    const long long zs = g.s[2], cs = g.cs;
+    const int I0 = x0 + 2 * tx, I1 = y0 + ty;
+    const bool act0 = I0 >= 1 && I0 < g.N[0] - 1 && I1 < g.N[1] - 1, act1 = I0 + 1 < g.N[0] - 1 && I1 < g.N[1] - 1;
+    const int Xa = max(1, min(I0, g.N[0] - 2)), Xb = max(1, min(I0 + 1, g.N[0] - 2)), Y = min(I1, g.N[1] - 2);
+    const int Xp = AL8 ? min(I0, g.N[0] - 2) : Xa;  // first element of the pair in memory (even when AL8)
+    const int dxb = AL8 ? 1 : Xb - Xa;              // 1, or 0 when the second cell is clamped
+    const long long q0 = Xp + (long long)Y * g.s[1] + (long long)zbeg * zs;
+    // issue state: next velocity plane / pointwise plane to fetch
+    const T *uplane = a.u[0] + (long long)(zbeg - 1) * zs;
+    int zu = zbeg - 1;           // plane index uplane stands on
+    const T *vb_f = a.vbase[0] + q0;
+    const T *ai_f = ACC ? a.acc_in[0] + q0 : nullptr;
+    int zp = zbeg;               // plane index the pointwise fetch pointers stand on
+    auto fetch_plane = [&]() {   // velocity plane zu -> slot zu % NS (skipped beyond the chunk)
+        if (zu <= zend) {
+            T *dst = s + (zu % NS) * NE;
+            if (AL8) {
+#pragma unroll
+                for (int i = 0; i < NLC; i++)
+                    if ((i + 1) * NT <= NCH || tid + i * NT < NCH) cp_async_pair<T>(dst + soff[i], uplane + goff[i]);
+                if (tid < 6 * PY) cp_async_elem<T>(dst + soff[NLC], uplane + goff[NLC]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < NL; i++)
+                    if ((i + 1) * NT <= NLD || tid + i * NT < NLD) cp_async_elem<T>(dst + soff[i], uplane + goff[i]);
+            }
+        }
+        uplane += zs;
+        zu++;
+    };
+    auto fetch_pointwise = [&]() {  // vbase / acc_in of this thread's cells in plane zp -> slot zp % NPW
+        if (zp < zend) {
+            T *dst = pw + (zp % NPW) * SM::PWE + 2 * tid;
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                if (AL8) {
+                    cp_async_pair<T>(dst + c * 2 * NT, vb_f + c * cs);
+                    if (ACC) cp_async_pair<T>(dst + (3 + c) * 2 * NT, ai_f + c * cs);
+                } else {
+                    cp_async_elem<T>(dst + c * 2 * NT, vb_f + c * cs);
+                    cp_async_elem<T>(dst + c * 2 * NT + 1, vb_f + c * cs + dxb);
+                    if (ACC) {
+                        cp_async_elem<T>(dst + (3 + c) * 2 * NT, ai_f + c * cs);
+                        cp_async_elem<T>(dst + (3 + c) * 2 * NT + 1, ai_f + c * cs + dxb);
+                    }
+                }
+            }
+        }
+        vb_f += zs;
+        if (ACC) ai_f += zs;
+        zp++;
+    };
+    // prologue: group 0 = planes zbeg-1, zbeg, zbeg+1 + pointwise zbeg; then DEPTH-1 more groups
+    fetch_plane();
+    fetch_plane();
+    fetch_plane();
+    fetch_pointwise();
+    cp_async_commit();
+#pragma unroll
+    for (int d = 1; d < DEPTH; d++) {
+        fetch_plane();
+        fetch_pointwise();
+        cp_async_commit();
+    }
+    // z tables, row r <-> plane z = zbeg - 1 + r:
+    //  0: -nu*rdlg[z+1]  1: -nu*rdug[z]  2: rdu[z]  3: rdl[z]  4: a2[z]/2  5: a1[z+1]/2
+    for (int e = tid; e < 6 * ZT; e += NT) {
+        int tb = e / ZT, r = e - tb * ZT;
+        int z = min(zbeg - 1 + r, g.N[2] - 2);
+        T v = tb == 0 ? -nu * g.rdlg[2][z + 1] : tb == 1 ? -nu * g.rdug[2][z] : tb == 2 ? g.rdu[2][z]
+            : tb == 3 ? g.rdl[2][z] : tb == 4 ? T(0.5) * g.a2[2][z] : T(0.5) * g.a1[2][z + 1];
+        zt[e] = pbc(v);
+    }
+    // loop-invariant x (pairs over the two cells) and y (broadcast) metrics
+    const P quarter = pbc(T(0.25));
+    const P x_lg0 = pmk(-nu * g.rdlg[0][Xa], -nu * g.rdlg[0][Xb]);
+    const P x_lg1 = pmk(-nu * g.rdlg[0][Xa + 1], -nu * g.rdlg[0][Xb + 1]);
+    const P x_ugm = pmk(-nu * g.rdug[0][Xa - 1], -nu * g.rdug[0][Xb - 1]);
+    const P x_ug0 = pmk(-nu * g.rdug[0][Xa], -nu * g.rdug[0][Xb]);
+    const P x_rdu = pmk(g.rdu[0][Xa], g.rdu[0][Xb]), x_rdl = pmk(g.rdl[0][Xa], g.rdl[0][Xb]);
+    const P x_hw2 = pmk(T(0.5) * g.a2[0][Xa], T(0.5) * g.a2[0][Xb]);
+    const P x_hw1 = pmk(T(0.5) * g.a1[0][Xa + 1], T(0.5) * g.a1[0][Xb + 1]);
+    const P y_lg0 = pbc(-nu * g.rdlg[1][Y]), y_lg1 = pbc(-nu * g.rdlg[1][Y + 1]);
+    const P y_ugm = pbc(-nu * g.rdug[1][Y - 1]), y_ug0 = pbc(-nu * g.rdug[1][Y]);
+    const P y_rdu = pbc(g.rdu[1][Y]), y_rdl = pbc(g.rdl[1][Y]);
+    const P y_hw2 = pbc(T(0.5) * g.a2[1][Y]), y_hw1 = pbc(T(0.5) * g.a1[1][Y + 1]);
+    const int lidx = (ty + 1) * PX + 2 * tx + 2;  // even: pairs are 8-/16-byte aligned
+    auto AL = [&](const T *pl, int c, int dy) { return *reinterpret_cast<const P *>(pl + c * PLANE + dy * PX); };
+    auto XP = [&](const T *pl, int c, int dy) { return pmk(pl[c * PLANE + dy * PX + 1], pl[c * PLANE + dy * PX + 2]); };
+    auto XM = [&](const T *pl, int c, int dy) { return pmk(pl[c * PLANE + dy * PX - 1], pl[c * PLANE + dy * PX]); };
+    // z-face fluxes through the top face of the cells in the plane at `lo` (`hi` = the plane above)
+    auto top_fluxes = [&](const T *lo, const T *hi, const P *ztr, P &F0, P &F1, P &F2) {
+        const P z_lg = ztr[0 * ZT], z_ug = ztr[1 * ZT];
+        const P u2 = AL(lo, 2, 0);
+        F2 = flux_diag<P>(u2, AL(hi, 2, 0), z_lg, quarter);
+        F0 = flux_off<P>(AL(lo, 0, 0), AL(hi, 0, 0), u2, XP(lo, 2, 0), x_hw2, x_hw1, z_ug);
+        F1 = flux_off<P>(AL(lo, 1, 0), AL(hi, 1, 0), u2, AL(lo, 2, 1), y_hw2, y_hw1, z_ug);
+    };
+    cp_async_wait<DEPTH - 1>();
+    __syncthreads();
+    P Fb0, Fb1, Fb2;  // fluxes through the bottom face of the current cells
+    top_fluxes(s + ((zbeg - 1) % NS) * NE + lidx, s + (zbeg % NS) * NE + lidx, zt, Fb0, Fb1, Fb2);
+    T *v_p = a.v[0] + q0;
+    T *ao_p = ACC ? a.acc_out[0] + q0 : nullptr;
+    unsigned q = (unsigned)q0;  // GEN path only
+    const P *ztr = zt + 1;
+    int sl0 = zbeg % NS, sl1 = (zbeg + 1) % NS, pws = zbeg % NPW;
+    for (int z = zbeg; z < zend; z++) {
+        cp_async_wait<DEPTH - 1>();  // plane z+1 and the pointwise operands of plane z have landed
+        __syncthreads();             // ... for every thread; and everybody is done with plane z-1
+        fetch_plane();               // plane z+1+DEPTH into the slot of plane z-1
+        fetch_pointwise();           // pointwise operands of plane z+DEPTH
+        cp_async_commit();
+        const T *p0 = s + sl0 * NE + lidx, *pp = s + sl1 * NE + lidx;
+        const P z_rdu = ztr[2 * ZT], z_rdl = ztr[3 * ZT], z_hw2 = ztr[4 * ZT], z_hw1 = ztr[5 * ZT];
+        P Ft0, Ft1, Ft2;
+        top_fluxes(p0, pp, ztr, Ft0, Ft1, Ft2);
+        const P u0c = AL(p0, 0, 0), u1c = AL(p0, 1, 0), u2c = AL(p0, 2, 0);
+        const P u0xm = XM(p0, 0, 0), u0xp = XP(p0, 0, 0), u1xm = XM(p0, 1, 0), u1xp = XP(p0, 1, 0);
+        const P u2xm = XM(p0, 2, 0), u2xp = XP(p0, 2, 0);
+        const P u0ym = AL(p0, 0, -1), u0yp = AL(p0, 0, 1), u1ym = AL(p0, 1, -1), u1yp = AL(p0, 1, 1);
+        const P u2ym = AL(p0, 2, -1), u2yp = AL(p0, 2, 1);
+        const P u0zp = AL(pp, 0, 0), u1zp = AL(pp, 1, 0);
+        P k[3];
+        // x component
+        k[0] = pmul(psub(flux_diag<P>(u0xm, u0c, x_lg0, quarter), flux_diag<P>(u0c, u0xp, x_lg1, quarter)), x_rdu);
+        k[0] = pfma(psub(flux_off<P>(u0ym, u0c, u1ym, XP(p0, 1, -1), x_hw2, x_hw1, y_ugm),
+                         flux_off<P>(u0c, u0yp, u1c, u1xp, x_hw2, x_hw1, y_ug0)), y_rdl, k[0]);
+        k[0] = pfma(psub(Fb0, Ft0), z_rdl, k[0]);
+        // y component
+        k[1] = pmul(psub(flux_off<P>(u1xm, u1c, u0xm, XM(p0, 0, 1), y_hw2, y_hw1, x_ugm),
+                         flux_off<P>(u1c, u1xp, u0c, u0yp, y_hw2, y_hw1, x_ug0)), x_rdl);
+        k[1] = pfma(psub(flux_diag<P>(u1ym, u1c, y_lg0, quarter), flux_diag<P>(u1c, u1yp, y_lg1, quarter)), y_rdu, k[1]);
+        k[1] = pfma(psub(Fb1, Ft1), z_rdl, k[1]);
+        // z component
+        k[2] = pmul(psub(flux_off<P>(u2xm, u2c, u0xm, XM(pp, 0, 0), z_hw2, z_hw1, x_ugm),
+                         flux_off<P>(u2c, u2xp, u0c, u0zp, z_hw2, z_hw1, x_ug0)), x_rdl);
+        k[2] = pfma(psub(flux_off<P>(u2ym, u2c, u1ym, AL(pp, 1, -1), z_hw2, z_hw1, y_ugm),
+                         flux_off<P>(u2c, u2yp, u1c, u1zp, z_hw2, z_hw1, y_ug0)), y_rdl, k[2]);
+        k[2] = pfma(psub(Fb2, Ft2), z_rdu, k[2]);
+        Fb0 = Ft0, Fb1 = Ft1, Fb2 = Ft2;
+        const P *pwp = reinterpret_cast<const P *>(pw + pws * SM::PWE) + tid;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const P kc = padd(k[c], pbc(a.bf[c]));
+            P x = pwp[c * NT];
+            if (GEN) {
+                if (a.k_out[0]) {
+                    if (act0) a.k_out[c][q] = kc.x;
+                    if (act1) a.k_out[c][q + 1] = kc.y;
+                }
+#pragma unroll 1
+                for (int j = 0; j < a.nprev; j++) {
+                    P kp = pmk(act0 ? a.kprev[j][c][q] : T(0), act1 ? a.kprev[j][c][q + 1] : T(0));
+                    x = PairAxpy<T, CT>::run(x, a.cprev[j], kp);
+                }
+            }
+            const P vo = PairAxpy<T, CT>::run(x, a.cv, kc);
+            if (AL8 && act0 && act1) {
+                *reinterpret_cast<P *>(v_p + c * cs) = vo;
+            } else {
+                if (act0) v_p[c * cs] = vo.x;
+                if (act1) v_p[c * cs + dxb] = vo.y;
+            }
+            if (ACC) {
+                const P ao = PairAxpy<T, CT>::run(pwp[(3 + c) * NT], a.ca, kc);
+                if (AL8 && act0 && act1) {
+                    *reinterpret_cast<P *>(ao_p + c * cs) = ao;
+                } else {
+                    if (act0) ao_p[c * cs] = ao.x;
+                    if (act1) ao_p[c * cs + dxb] = ao.y;
+                }
+            }
+        }
+        sl0 = sl1;
+        sl1 = sl1 + 1 == NS ? 0 : sl1 + 1;
+        pws = pws + 1 == NPW ? 0 : pws + 1;
+        v_p += zs, q += (unsigned)zs, ztr++;
+        if (ACC) ao_p += zs;
+    }
+}
+
 template <typename T, typename CT>
 static int launch_stage_tile(const Grid<T> &g, const StageArgs<T> &a, Launch L) {
     constexpr int TX = 32, TY = 16, ZC = 128;
@@ -282,22 +629,75 @@ static int launch_stage_tile(const Grid<T> &g, const StageArgs<T> &a, Launch L) 
 }
 
 template <typename T, typename CT, int D>
-static int launch_stage_t(const Grid<T> &g, const StageArgs<T> &a, Launch L) {
-    dim3 b(64, 4, 1);
-    dim3 gr((g.N[0] + b.x - 1) / b.x, (g.N[1] + b.y - 1) / b.y, D == 3 ? g.N[2] : 1);
+static int launch_stage_t(const Grid<T> &g, const StageArgs<T> &a, Launch L, int xb = 0, int xe = -1);
+
+template <typename T, typename CT, bool AL8>
+static int launch_stage_pair_a(const Grid<T> &g, const StageArgs<T> &a, Launch L, int nxt) {
+    constexpr int TY = 8, ZC = 128, DEPTH = 2;
+    const bool acc = a.acc_out != nullptr, gen = a.k_out != nullptr || a.nprev > 0;
+    const size_t smem = (size_t)(acc ? PairSmem<TY, ZC, DEPTH, true>::total : PairSmem<TY, ZC, DEPTH, false>::total) * sizeof(T);
+    auto kern = acc ? (gen ? stage_pair_kernel<T, CT, TY, ZC, DEPTH, true, true, AL8> : stage_pair_kernel<T, CT, TY, ZC, DEPTH, true, false, AL8>)
+                    : (gen ? stage_pair_kernel<T, CT, TY, ZC, DEPTH, false, true, AL8> : stage_pair_kernel<T, CT, TY, ZC, DEPTH, false, false, AL8>);
+    INSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    StageDev<T, CT> d{};
+    for (int c = 0; c < 3; c++) {
+        d.u[c] = a.u + c * g.cs;
+        d.vbase[c] = a.vbase ? a.vbase + c * g.cs : nullptr;
+        d.v[c] = a.v ? a.v + c * g.cs : nullptr;
+        d.acc_in[c] = a.acc_in ? a.acc_in + c * g.cs : nullptr;
+        d.acc_out[c] = a.acc_out ? a.acc_out + c * g.cs : nullptr;
+        d.k_out[c] = a.k_out ? a.k_out + c * g.cs : nullptr;
+        for (int j = 0; j < a.nprev; j++) d.kprev[j][c] = a.kprev[j] + c * g.cs;
+        d.bf[c] = (T)a.bodyforce[c];
+    }
+    d.nprev = a.nprev;
+    for (int j = 0; j < a.nprev; j++) d.cprev[j] = (CT)a.cprev[j];
+    d.cv = (CT)a.cv;
+    d.ca = (CT)a.ca;
+    d.nu = (T)a.nu;
+    int nz = g.N[2] - 2;
+    dim3 b(32, TY, 1);
+    dim3 gr(nxt, (g.N[1] - 2 + TY - 1) / TY, (nz + ZC - 1) / ZC);
+    kern<<<gr, b, smem, L.stream>>>(g, d);
+    if (L.counter) ++*L.counter;
+    INSB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename T, typename CT>
+static int launch_stage_pair(const Grid<T> &g, const StageArgs<T> &a, Launch L) {
+    constexpr int TXC = 64;
+    static const bool no_al8 = getenv("INSB200_STAGE_UNALIGNED") != nullptr;
+    const uintptr_t align = (uintptr_t)a.u | (uintptr_t)a.vbase | (uintptr_t)a.v | (uintptr_t)a.acc_in | (uintptr_t)a.acc_out;
+    const bool al8 = !no_al8 && g.N[0] % 2 == 0 && align % (2 * sizeof(T)) == 0;
+    if (!al8) return launch_stage_pair_a<T, CT, false>(g, a, L, (g.N[0] - 2 + TXC - 1) / TXC);
+    // even-aligned tiles cover cells [0, 64 nxt); a narrow remainder goes to the direct kernel
+    int nxt = (g.N[0] - 1) / TXC;
+    int rest = g.N[0] - 1 - nxt * TXC;
+    if (rest > 8 || nxt == 0) nxt++, rest = 0;
+    INSB_TRY((launch_stage_pair_a<T, CT, true>(g, a, L, nxt)));
+    if (rest > 0) INSB_TRY((launch_stage_t<T, CT, 3>(g, a, L, nxt * TXC, g.N[0] - 1)));
+    return 0;
+}
+
+template <typename T, typename CT, int D>
+static int launch_stage_t(const Grid<T> &g, const StageArgs<T> &a, Launch L, int xb, int xe) {
+    if (xe < 0) xe = g.N[0];
+    dim3 b(xe - xb <= 8 ? 8 : 64, xe - xb <= 8 ? 32 : 4, 1);
+    dim3 gr((xe - xb + b.x - 1) / b.x, (g.N[1] + b.y - 1) / b.y, D == 3 ? g.N[2] : 1);
     bool full = a.conv && a.diff;
     StageArgs<T> aa = a;
     if (!a.diff) aa.nu = 0.0;
     if (a.bouss) {
         if (full)
-            stage_direct_kernel<T, CT, D, true, true><<<gr, b, 0, L.stream>>>(g, aa);
+            stage_direct_kernel<T, CT, D, true, true><<<gr, b, 0, L.stream>>>(g, aa, xb, xe);
         else
-            stage_direct_kernel<T, CT, D, true, false><<<gr, b, 0, L.stream>>>(g, aa);
+            stage_direct_kernel<T, CT, D, true, false><<<gr, b, 0, L.stream>>>(g, aa, xb, xe);
     } else {
         if (full)
-            stage_direct_kernel<T, CT, D, false, true><<<gr, b, 0, L.stream>>>(g, aa);
+            stage_direct_kernel<T, CT, D, false, true><<<gr, b, 0, L.stream>>>(g, aa, xb, xe);
         else
-            stage_direct_kernel<T, CT, D, false, false><<<gr, b, 0, L.stream>>>(g, aa);
+            stage_direct_kernel<T, CT, D, false, false><<<gr, b, 0, L.stream>>>(g, aa, xb, xe);
     }
     if (L.counter) ++*L.counter;
     INSB_CUDA(cudaGetLastError());
@@ -312,10 +712,15 @@ struct WideOf {
 template <typename T>
 int launch_stage(const Grid<T> &g, const StageArgs<T> &a, bool ct_double, Launch L) {
     static const bool force_direct = getenv("INSB200_DIRECT_STAGE") != nullptr;
+    static const bool use_v2 = getenv("INSB200_STAGE_V2") != nullptr;
     if (g.D == 3 && !a.bouss && a.conv && a.diff && !a.zero_outside && !a.add_to_k && !force_direct &&
-        a.v != nullptr && g.cs < (1LL << 32)) {
-        if (sizeof(T) == 8 || ct_double) return launch_stage_tile<T, double>(g, a, L);
-        return launch_stage_tile<T, T>(g, a, L);
+        a.v != nullptr && 3 * g.cs < (1LL << 32)) {
+        if (use_v2) {
+            if (sizeof(T) == 8 || ct_double) return launch_stage_tile<T, double>(g, a, L);
+            return launch_stage_tile<T, T>(g, a, L);
+        }
+        if (sizeof(T) == 8 || ct_double) return launch_stage_pair<T, double>(g, a, L);
+        return launch_stage_pair<T, T>(g, a, L);
     }
     if (sizeof(T) == 8 || ct_double) {
         return g.D == 3 ? launch_stage_t<T, double, 3>(g, a, L) : launch_stage_t<T, double, 2>(g, a, L);
