@@ -2,11 +2,13 @@
 //
 // One thread owns 8 complex values of a line of length N (P = N/8 threads per line) and runs
 // a Stockham auto-sort FFT whose radix-8/4/2 butterflies live entirely in registers; values
-// are exchanged between stages through padded, double-buffered shared memory.  In EVERY
-// stage register m of thread t holds element t + P*m, and so does the final result -- which
-// is also the input distribution of the next transform.  The middle pass of the Poisson
-// solve exploits that: forward FFT, eigenvalue division (pressure.jl:360-372) and inverse
-// FFT run back to back without leaving registers in between.
+// are exchanged between stages through padded, double-buffered shared memory holding whole
+// complex numbers (one 64-/128-bit access per value).  In EVERY stage register m of thread t
+// holds element t + P*m, and so does the final result -- which is also the input distribution
+// of the next transform.  The middle pass of the Poisson solve exploits that: forward FFT,
+// eigenvalue division (pressure.jl:360-372) and inverse FFT run back to back without leaving
+// registers in between.  Float32 arithmetic is done on (re, im) pairs with the packed FP32
+// instructions of sm_100 (FADD2/FMUL2/FFMA2), which halves the issue slots of the butterflies.
 //
 // Pass structure of psolver_spectral (pressure.jl:349-381) with these kernels, 3-D:
 //   x: two real rows -> one complex FFT -> two half spectra (R2C), reads view(p, Ip) directly
@@ -35,74 +37,103 @@ struct FftShape {
     }
 };
 
-__host__ __device__ __forceinline__ constexpr int phys(int p) { return p + (p >> 3); }
+// padded shared-memory position of element p of a line
+__host__ __device__ __forceinline__ constexpr int sp(int p) { return p + (p >> 3); }
 
-template <typename T, bool INV>
-__device__ __forceinline__ Cx<T> rot90(Cx<T> a) {  // multiply by -i (forward) or +i (inverse)
-    return INV ? Cx<T>{-a.y, a.x} : Cx<T>{a.y, -a.x};
-}
+// ----------------------------------------------------------------------------------------
+// complex arithmetic: generic (double) and packed (float)
+// ----------------------------------------------------------------------------------------
+template <typename T>
+struct Ops {
+    typedef Cx<T> C;
+    static __device__ __forceinline__ C add(C a, C b) { return C{a.x + b.x, a.y + b.y}; }
+    static __device__ __forceinline__ C sub(C a, C b) { return C{a.x - b.x, a.y - b.y}; }
+    // a + s*i*b, s = -1 (forward transform) or +1 (inverse)
+    template <bool INV>
+    static __device__ __forceinline__ C add_i(C a, C b) {
+        return INV ? C{a.x - b.y, a.y + b.x} : C{a.x + b.y, a.y - b.x};
+    }
+    template <bool INV>
+    static __device__ __forceinline__ C sub_i(C a, C b) {
+        return INV ? C{a.x + b.y, a.y - b.x} : C{a.x - b.y, a.y + b.x};
+    }
+    static __device__ __forceinline__ C mul(C a, C w) { return C{a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x}; }
+    static __device__ __forceinline__ C axpy(C a, T s, C b) { return C{fma(a.x, s, b.x), fma(a.y, s, b.y)}; }  // b + s a
+    static __device__ __forceinline__ C scale(C a, T s) { return C{a.x * s, a.y * s}; }
+};
+
+template <>
+struct Ops<float> {
+    typedef Cx<float> C;
+    static __device__ __forceinline__ float2 f(C a) { return make_float2(a.x, a.y); }
+    static __device__ __forceinline__ C c(float2 a) { return C{a.x, a.y}; }
+    static __device__ __forceinline__ C add(C a, C b) { return c(__fadd2_rn(f(a), f(b))); }
+    static __device__ __forceinline__ C sub(C a, C b) { return c(__ffma2_rn(f(b), make_float2(-1.f, -1.f), f(a))); }
+    template <bool INV>
+    static __device__ __forceinline__ C add_i(C a, C b) {
+        return c(__ffma2_rn(make_float2(b.y, b.x), INV ? make_float2(-1.f, 1.f) : make_float2(1.f, -1.f), f(a)));
+    }
+    template <bool INV>
+    static __device__ __forceinline__ C sub_i(C a, C b) {
+        return c(__ffma2_rn(make_float2(b.y, b.x), INV ? make_float2(1.f, -1.f) : make_float2(-1.f, 1.f), f(a)));
+    }
+    static __device__ __forceinline__ C mul(C a, C w) {
+        float2 t = __fmul2_rn(make_float2(-a.y, a.y), make_float2(w.y, w.x));
+        return c(__ffma2_rn(make_float2(a.x, a.x), f(w), t));
+    }
+    static __device__ __forceinline__ C axpy(C a, float s, C b) { return c(__ffma2_rn(f(a), make_float2(s, s), f(b))); }
+    static __device__ __forceinline__ C scale(C a, float s) { return c(__fmul2_rn(f(a), make_float2(s, s))); }
+};
 
 // radix-R butterfly on v[b + B*r], r = 0..R-1, natural-order output
 template <typename T, int R, int B, bool INV>
 __device__ __forceinline__ void butterfly(Cx<T> (&v)[8], int b) {
+    typedef Ops<T> O;
     if constexpr (R == 2) {
         Cx<T> a = v[b], c = v[b + B];
-        v[b] = cadd(a, c);
-        v[b + B] = csub(a, c);
+        v[b] = O::add(a, c);
+        v[b + B] = O::sub(a, c);
     } else if constexpr (R == 4) {
-        Cx<T> a0 = cadd(v[b], v[b + 2 * B]), a1 = csub(v[b], v[b + 2 * B]);
-        Cx<T> a2 = cadd(v[b + B], v[b + 3 * B]), a3 = rot90<T, INV>(csub(v[b + B], v[b + 3 * B]));
-        v[b] = cadd(a0, a2);
-        v[b + B] = cadd(a1, a3);
-        v[b + 2 * B] = csub(a0, a2);
-        v[b + 3 * B] = csub(a1, a3);
+        Cx<T> a0 = O::add(v[b], v[b + 2 * B]), a1 = O::sub(v[b], v[b + 2 * B]);
+        Cx<T> a2 = O::add(v[b + B], v[b + 3 * B]), a3 = O::sub(v[b + B], v[b + 3 * B]);
+        v[b] = O::add(a0, a2);
+        v[b + 2 * B] = O::sub(a0, a2);
+        v[b + B] = O::template add_i<INV>(a1, a3);
+        v[b + 3 * B] = O::template sub_i<INV>(a1, a3);
     } else {
         const T h = T(0.70710678118654752440);
-        Cx<T> a0 = cadd(v[0], v[4]), a1 = csub(v[0], v[4]);
-        Cx<T> a2 = cadd(v[2], v[6]), a3 = rot90<T, INV>(csub(v[2], v[6]));
-        Cx<T> a4 = cadd(v[1], v[5]), a5 = csub(v[1], v[5]);
-        Cx<T> a6 = cadd(v[3], v[7]), a7 = rot90<T, INV>(csub(v[3], v[7]));
-        Cx<T> b0 = cadd(a0, a2), b2 = csub(a0, a2), b1 = cadd(a1, a3), b3 = csub(a1, a3);
-        Cx<T> b4 = cadd(a4, a6), b6 = csub(a4, a6), b5 = cadd(a5, a7), b7 = csub(a5, a7);
-        // w8^1 = (1 -+ i)/sqrt2, w8^2 = -+ i, w8^3 = (-1 -+ i)/sqrt2
-        Cx<T> t5 = INV ? Cx<T>{(b5.x - b5.y) * h, (b5.x + b5.y) * h} : Cx<T>{(b5.x + b5.y) * h, (b5.y - b5.x) * h};
-        Cx<T> t6 = rot90<T, INV>(b6);
-        Cx<T> t7 = INV ? Cx<T>{(-b7.x - b7.y) * h, (b7.x - b7.y) * h} : Cx<T>{(b7.y - b7.x) * h, (-b7.x - b7.y) * h};
-        v[0] = cadd(b0, b4);
-        v[4] = csub(b0, b4);
-        v[1] = cadd(b1, t5);
-        v[5] = csub(b1, t5);
-        v[2] = cadd(b2, t6);
-        v[6] = csub(b2, t6);
-        v[3] = cadd(b3, t7);
-        v[7] = csub(b3, t7);
+        Cx<T> a0 = O::add(v[0], v[4]), a1 = O::sub(v[0], v[4]);
+        Cx<T> a2 = O::add(v[2], v[6]), a3 = O::sub(v[2], v[6]);
+        Cx<T> a4 = O::add(v[1], v[5]), a5 = O::sub(v[1], v[5]);
+        Cx<T> a6 = O::add(v[3], v[7]), a7 = O::sub(v[3], v[7]);
+        Cx<T> b0 = O::add(a0, a2), b2 = O::sub(a0, a2);
+        Cx<T> b1 = O::template add_i<INV>(a1, a3), b3 = O::template sub_i<INV>(a1, a3);
+        Cx<T> b4 = O::add(a4, a6), b6 = O::sub(a4, a6);
+        Cx<T> b5 = O::template add_i<INV>(a5, a7), b7 = O::template sub_i<INV>(a5, a7);
+        // w8^1 b5 = h (b5 + s i b5),  w8^3 b7 = -h (b7 - s i b7),  w8^2 b6 = s i b6
+        Cx<T> r5 = O::template add_i<INV>(b5, b5), r7 = O::template sub_i<INV>(b7, b7);
+        v[0] = O::add(b0, b4);
+        v[4] = O::sub(b0, b4);
+        v[1] = O::axpy(r5, h, b1);
+        v[5] = O::axpy(r5, -h, b1);
+        v[2] = O::template add_i<INV>(b2, b6);
+        v[6] = O::template sub_i<INV>(b2, b6);
+        v[3] = O::axpy(r7, -h, b3);
+        v[7] = O::axpy(r7, h, b3);
     }
 }
 
-// Shared-memory view of one line: two buffers x (re, im), padded index phys(p).
+// Per-thread view of the exchange buffers: element p of this thread's line sits at
+// buf[k][sp(p) * ES] (ES = lines per block when the lines are interleaved, 1 otherwise).
 template <typename T>
 struct LineSmem {
-    T *re[2], *im[2];
+    Cx<T> *buf[2];
 };
 
-// Shared-memory index of element p for the exchange that follows a stage with (NS, R).
-// LFAST kernels (lanes run over lines): p + p/8.  TFAST kernels (lanes run along the line):
-// pad PADW words per BANKS elements, PADW chosen so that both the strided writes of this
-// exchange and the unit-stride reads are bank-conflict free.
-template <typename T, bool TFAST, int NS, int R>
-__device__ __forceinline__ int sidx(int p) {
-    if constexpr (!TFAST) {
-        return p + (p >> 3);
-    } else {
-        constexpr int BANKS = 128 / (int)sizeof(T);
-        constexpr int PADW = (NS * R >= BANKS) ? (BANKS / R > 0 ? BANKS / R : 1) : NS;
-        return p + PADW * (p / BANKS);
-    }
-}
-
-template <typename T, int N, bool INV, int S, bool TFAST = false>
+template <typename T, int N, bool INV, int S, int ES>
 __device__ __forceinline__ void fft_stages(Cx<T> (&v)[8], int t, const LineSmem<T> &sm,
                                            const Cx<T> *__restrict__ tw, int &exch) {
+    typedef Ops<T> O;
     using Sh = FftShape<N>;
     constexpr int R = Sh::radix(S);
     constexpr int B = 8 / R;
@@ -117,79 +148,85 @@ __device__ __forceinline__ void fft_stages(Cx<T> (&v)[8], int t, const LineSmem<
             if constexpr (R == 2) {
                 Cx<T> w1 = tw[k * TSTEP];
                 if (INV) w1 = cconj(w1);
-                v[b + B] = cmul(v[b + B], w1);
+                v[b + B] = O::mul(v[b + B], w1);
             } else if constexpr (R == 4) {
                 Cx<T> w1 = tw[k * TSTEP], w2 = tw[2 * k * TSTEP];
                 if (INV) w1 = cconj(w1), w2 = cconj(w2);
-                Cx<T> w3 = cmul(w1, w2);
-                v[b + B] = cmul(v[b + B], w1);
-                v[b + 2 * B] = cmul(v[b + 2 * B], w2);
-                v[b + 3 * B] = cmul(v[b + 3 * B], w3);
+                Cx<T> w3 = O::mul(w1, w2);
+                v[b + B] = O::mul(v[b + B], w1);
+                v[b + 2 * B] = O::mul(v[b + 2 * B], w2);
+                v[b + 3 * B] = O::mul(v[b + 3 * B], w3);
             } else {
                 Cx<T> w1 = tw[k * TSTEP], w2 = tw[2 * k * TSTEP], w4 = tw[4 * k * TSTEP];
                 if (INV) w1 = cconj(w1), w2 = cconj(w2), w4 = cconj(w4);
-                Cx<T> w3 = cmul(w1, w2), w5 = cmul(w1, w4), w6 = cmul(w2, w4);
-                Cx<T> w7 = cmul(w3, w4);
-                v[1] = cmul(v[1], w1);
-                v[2] = cmul(v[2], w2);
-                v[3] = cmul(v[3], w3);
-                v[4] = cmul(v[4], w4);
-                v[5] = cmul(v[5], w5);
-                v[6] = cmul(v[6], w6);
-                v[7] = cmul(v[7], w7);
+                Cx<T> w3 = O::mul(w1, w2), w5 = O::mul(w1, w4), w6 = O::mul(w2, w4);
+                Cx<T> w7 = O::mul(w3, w4);
+                v[1] = O::mul(v[1], w1);
+                v[2] = O::mul(v[2], w2);
+                v[3] = O::mul(v[3], w3);
+                v[4] = O::mul(v[4], w4);
+                v[5] = O::mul(v[5], w5);
+                v[6] = O::mul(v[6], w6);
+                v[7] = O::mul(v[7], w7);
             }
         }
     }
 #pragma unroll
     for (int b = 0; b < B; b++) butterfly<T, R, B, INV>(v, b);
     if constexpr (S < Sh::NST - 1) {
-        T *re = sm.re[exch & 1], *im = sm.im[exch & 1];
+        Cx<T> *buf = sm.buf[exch & 1];
 #pragma unroll
         for (int b = 0; b < B; b++) {
             int j = t + P * b;
             int j0 = (j / NS) * (NS * R) + (j & (NS - 1));
+            if constexpr (NS % 8 == 0 || (NS == 1 && R == 8)) {
+                // sp(j0 + r NS) = sp(j0) + r (NS + NS/8)   (r < 8 when NS == 1, j0 a multiple of 8)
+                constexpr int DS = NS == 1 ? 1 : NS + NS / 8;
+                Cx<T> *w = buf + sp(j0) * ES;
 #pragma unroll
-            for (int r = 0; r < R; r++) {
-                int q = sidx<T, TFAST, NS, R>(j0 + r * NS);
-                re[q] = v[b + B * r].x;
-                im[q] = v[b + B * r].y;
+                for (int r = 0; r < R; r++) w[r * DS * ES] = v[b + B * r];
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; r++) buf[sp(j0 + r * NS) * ES] = v[b + B * r];
             }
         }
         __syncthreads();
+        if constexpr (P % 8 == 0) {
+            const Cx<T> *rd = buf + sp(t) * ES;
 #pragma unroll
-        for (int m = 0; m < 8; m++) {
-            int q = sidx<T, TFAST, NS, R>(t + P * m);
-            v[m] = Cx<T>{re[q], im[q]};
+            for (int m = 0; m < 8; m++) v[m] = rd[m * (P + P / 8) * ES];
+        } else {
+#pragma unroll
+            for (int m = 0; m < 8; m++) v[m] = buf[sp(t + P * m) * ES];
         }
         exch++;
-        fft_stages<T, N, INV, S + 1, TFAST>(v, t, sm, tw, exch);
+        fft_stages<T, N, INV, S + 1, ES>(v, t, sm, tw, exch);
     }
 }
 
-template <typename T>
-__device__ __forceinline__ LineSmem<T> line_smem(T *base, int l, int L, int LS) {
-    LineSmem<T> s;
-    s.re[0] = base + (size_t)l * LS;
-    s.im[0] = base + (size_t)(L + l) * LS;
-    s.re[1] = base + (size_t)(2 * L + l) * LS;
-    s.im[1] = base + (size_t)(3 * L + l) * LS;
-    return s;
-}
-
+// lines per block of the strided passes: 64-byte row segments in Float32/Float64 while the
+// block stays at <= 512 threads (1024 for the longest Float32 lines)
+template <typename T, int N>
+struct StridedShape {
+    static constexpr int P = FftShape<N>::P;
+    static constexpr int L = sizeof(T) == 4 ? (N <= 512 ? 8 : 4) : (N <= 1024 ? 4 : 2);
+    static constexpr int NT = L * P;
+    static constexpr int BUF = sp(N - 1) + 1;  // complex elements per line and buffer
+    static constexpr size_t smem = (size_t)2 * L * BUF * sizeof(Cx<T>);
+};
 
 // ----------------------------------------------------------------------------------------
 // strided pass along dim `tdim` (1 or 2): MODE 0 forward, 1 inverse, 2 forward+divide+inverse
 // grid: x = tiles of L lines along kx, y = index along the remaining dimension
+// BLK: generalised (blocked) addressing of the slab-decomposed solve, see fft_fast.h
 // ----------------------------------------------------------------------------------------
-// MODE 3 = MODE 2 compiled without the two-blocks-per-SM register cap (selected at run time
-// with INSB200_FFT_MID_UNCAPPED=1 for A/B measurements)
-template <typename T, int N, int MODE>
-__global__ void __launch_bounds__(512, (sizeof(T) == 4 && MODE != 3) ? 2 : 1)
-    fft_strided_kernel(Cx<T> *__restrict__ W, FastGeom g, int tdim, int L, int LS,
-                       const Cx<T> *__restrict__ tw, const T *__restrict__ e0, const T *__restrict__ e1,
-                       const T *__restrict__ e2, T factor) {
+template <typename T, int N, int MODE, bool BLK>
+__global__ void __launch_bounds__(StridedShape<T, N>::NT, (sizeof(T) == 4 && StridedShape<T, N>::NT <= 512) ? 2 : 1)
+    fft_strided_kernel(Cx<T> *__restrict__ W, FastGeom g, int tdim, const Cx<T> *__restrict__ tw,
+                       const T *__restrict__ e0, const T *__restrict__ e1, const T *__restrict__ e2, T factor) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int P = FftShape<N>::P;
+    typedef StridedShape<T, N> SS;
+    constexpr int P = SS::P, L = SS::L;
     const int l = threadIdx.x % L, t = threadIdx.x / L;
     const int kx = blockIdx.x * L + l;
     const int other = blockIdx.y;
@@ -198,13 +235,23 @@ __global__ void __launch_bounds__(512, (sizeof(T) == 4 && MODE != 3) ? 2 : 1)
     const long long in_os = g.in_os >= 0 ? g.in_os : g.ws[odim], out_os = g.out_os >= 0 ? g.out_os : g.ws[odim];
     const Cx<T> *ibase = (g.in ? (const Cx<T> *)g.in : W) + kx + (g.D == 3 ? other * in_os : 0);
     Cx<T> *obase = (g.out ? (Cx<T> *)g.out : W) + kx + (g.D == 3 ? other * out_os : 0);
-    const int in_mask = (1 << g.in_sh) - 1, out_mask = (1 << g.out_sh) - 1;
-    auto ioff = [&](int k) { return (long long)(k >> g.in_sh) * g.in_blk + (long long)(k & in_mask) * in_sd; };
-    auto ooff = [&](int k) { return (long long)(k >> g.out_sh) * g.out_blk + (long long)(k & out_mask) * out_sd; };
-    LineSmem<T> sm = line_smem<T>(reinterpret_cast<T *>(smem_raw), l, L, LS);
+    LineSmem<T> sm;
+    sm.buf[0] = reinterpret_cast<Cx<T> *>(smem_raw) + l;
+    sm.buf[1] = sm.buf[0] + L * SS::BUF;
     Cx<T> v[8];
+    if (BLK) {
+        const int in_mask = (1 << g.in_sh) - 1;
 #pragma unroll
-    for (int m = 0; m < 8; m++) v[m] = ibase[ioff(t + P * m)];
+        for (int m = 0; m < 8; m++) {
+            int k = t + P * m;
+            v[m] = ibase[(long long)(k >> g.in_sh) * g.in_blk + (long long)(k & in_mask) * in_sd];
+        }
+    } else {
+        const Cx<T> *ip = ibase + t * in_sd;
+        const long long step = P * in_sd;
+#pragma unroll
+        for (int m = 0; m < 8; m++) v[m] = ip[m * step];
+    }
     T f[8];
     if (MODE >= 2) {
         // phat = -phat / ((ax + ay) + az), phat[1] = 0 (pressure.jl:360-372); `factor` carries
@@ -227,26 +274,46 @@ __global__ void __launch_bounds__(512, (sizeof(T) == 4 && MODE != 3) ? 2 : 1)
         }
     }
     int exch = 0;
-    if (MODE == 0 || MODE >= 2) fft_stages<T, N, false, 0>(v, t, sm, tw, exch);
+    if (MODE == 0 || MODE >= 2) fft_stages<T, N, false, 0, L>(v, t, sm, tw, exch);
     if (MODE >= 2) {
 #pragma unroll
-        for (int m = 0; m < 8; m++) v[m] = Cx<T>{v[m].x * f[m], v[m].y * f[m]};
+        for (int m = 0; m < 8; m++) v[m] = Ops<T>::scale(v[m], f[m]);
     }
-    if (MODE >= 1) fft_stages<T, N, true, 0>(v, t, sm, tw, exch);
+    if (MODE >= 1) fft_stages<T, N, true, 0, L>(v, t, sm, tw, exch);
+    if (BLK) {
+        const int out_mask = (1 << g.out_sh) - 1;
 #pragma unroll
-    for (int m = 0; m < 8; m++) obase[ooff(t + P * m)] = v[m];
+        for (int m = 0; m < 8; m++) {
+            int k = t + P * m;
+            obase[(long long)(k >> g.out_sh) * g.out_blk + (long long)(k & out_mask) * out_sd] = v[m];
+        }
+    } else {
+        Cx<T> *op = obase + t * out_sd;
+        const long long step = P * out_sd;
+#pragma unroll
+        for (int m = 0; m < 8; m++) op[m * step] = v[m];
+    }
 }
 
 // ----------------------------------------------------------------------------------------
 // x pass, real -> half spectrum: rows (2q, 2q+1) along y are transformed as one complex line
 // ----------------------------------------------------------------------------------------
 template <typename T, int N>
-__global__ void __launch_bounds__(256)
-    fft_x_r2c_kernel(const T *__restrict__ R, Cx<T> *__restrict__ W, FastGeom g, int LP, int LS,
+struct XShape {
+    static constexpr int P = FftShape<N>::P;
+    static constexpr int LP = P >= 256 ? 1 : 256 / P;  // row pairs per block
+    static constexpr int NT = LP * P;
+    static constexpr int BUF = (sp(N - 1) + 1 + 3) / 4 * 4 + 2;  // line stride: staggers lines over the banks
+    static constexpr size_t smem = (size_t)2 * LP * BUF * sizeof(Cx<T>);
+};
+
+template <typename T, int N>
+__global__ void __launch_bounds__(XShape<T, N>::NT)
+    fft_x_r2c_kernel(const T *__restrict__ R, Cx<T> *__restrict__ W, FastGeom g,
                      const Cx<T> *__restrict__ tw, long long npairs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int P = FftShape<N>::P;
-    constexpr int NST = FftShape<N>::NST;
+    typedef XShape<T, N> XS;
+    constexpr int P = XS::P, LP = XS::LP;
     const int t = threadIdx.x % P, lp = threadIdx.x / P;
     long long q = (long long)blockIdx.x * LP + lp;
     const bool valid = q < npairs;
@@ -255,22 +322,18 @@ __global__ void __launch_bounds__(256)
     const int jp = (int)(q % hp), kz = (int)(q / hp);
     const T *ra = R + (long long)(2 * jp) * g.rs[1] + (long long)kz * g.rs[2];
     const T *rb = ra + g.rs[1];
-    LineSmem<T> sm = line_smem<T>(reinterpret_cast<T *>(smem_raw), lp, LP, LS);
+    LineSmem<T> sm;
+    sm.buf[0] = reinterpret_cast<Cx<T> *>(smem_raw) + lp * XS::BUF;
+    sm.buf[1] = sm.buf[0] + LP * XS::BUF;
     Cx<T> v[8];
 #pragma unroll
     for (int m = 0; m < 8; m++) v[m] = Cx<T>{ra[t + P * m], rb[t + P * m]};
     int exch = 0;
-    fft_stages<T, N, false, 0, true>(v, t, sm, tw, exch);
+    fft_stages<T, N, false, 0, 1>(v, t, sm, tw, exch);
     // exchange once more to reach Z[N-k]
-    T *re = sm.re[exch & 1], *im = sm.im[exch & 1];
-    (void)NST;
-    auto phys = [](int p) { return sidx<T, true, 1, 1>(p); };
+    Cx<T> *buf = sm.buf[exch & 1];
 #pragma unroll
-    for (int m = 0; m < 8; m++) {
-        int p = phys(t + P * m);
-        re[p] = v[m].x;
-        im[p] = v[m].y;
-    }
+    for (int m = 0; m < 8; m++) buf[sp(t + P * m)] = v[m];
     __syncthreads();
     Cx<T> *wa = W + (long long)(2 * jp) * g.ws[1] + (long long)kz * g.ws[2];
     Cx<T> *wb = wa + g.ws[1];
@@ -279,11 +342,10 @@ __global__ void __launch_bounds__(256)
         for (int m = 0; m < 5; m++) {
             int k = t + P * m;
             if (m == 4 && t != 0) break;  // k = N/2 is handled by t = 0
-            Cx<T> zk = m < 4 ? v[m] : Cx<T>{re[phys(k)], im[phys(k)]};
-            int kc = phys((N - k) & (N - 1));
-            Cx<T> zc{re[kc], -im[kc]};  // conj(Z[N-k])
-            Cx<T> A{(zk.x + zc.x) * T(0.5), (zk.y + zc.y) * T(0.5)};
-            Cx<T> d{(zk.x - zc.x) * T(0.5), (zk.y - zc.y) * T(0.5)};
+            Cx<T> zk = m < 4 ? v[m] : buf[sp(k)];
+            Cx<T> zc = cconj(buf[sp((N - k) & (N - 1))]);  // conj(Z[N-k])
+            Cx<T> A = Ops<T>::scale(Ops<T>::add(zk, zc), T(0.5));
+            Cx<T> d = Ops<T>::scale(Ops<T>::sub(zk, zc), T(0.5));
             wa[k] = A;
             wb[k] = Cx<T>{d.y, -d.x};  // d / i
         }
@@ -294,11 +356,12 @@ __global__ void __launch_bounds__(256)
 // x pass, half spectrum -> real: inverse of the above
 // ----------------------------------------------------------------------------------------
 template <typename T, int N>
-__global__ void __launch_bounds__(256)
-    fft_x_c2r_kernel(T *__restrict__ R, const Cx<T> *__restrict__ W, FastGeom g, int LP, int LS,
+__global__ void __launch_bounds__(XShape<T, N>::NT)
+    fft_x_c2r_kernel(T *__restrict__ R, const Cx<T> *__restrict__ W, FastGeom g,
                      const Cx<T> *__restrict__ tw, long long npairs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int P = FftShape<N>::P;
+    typedef XShape<T, N> XS;
+    constexpr int P = XS::P, LP = XS::LP;
     const int t = threadIdx.x % P, lp = threadIdx.x / P;
     long long q = (long long)blockIdx.x * LP + lp;
     const bool valid = q < npairs;
@@ -307,7 +370,9 @@ __global__ void __launch_bounds__(256)
     const int jp = (int)(q % hp), kz = (int)(q / hp);
     const Cx<T> *wa = W + (long long)(2 * jp) * g.ws[1] + (long long)kz * g.ws[2];
     const Cx<T> *wb = wa + g.ws[1];
-    LineSmem<T> sm = line_smem<T>(reinterpret_cast<T *>(smem_raw), lp, LP, LS);
+    LineSmem<T> sm;
+    sm.buf[0] = reinterpret_cast<Cx<T> *>(smem_raw) + lp * XS::BUF;
+    sm.buf[1] = sm.buf[0] + LP * XS::BUF;
     Cx<T> v[8];
 #pragma unroll
     for (int m = 0; m < 8; m++) {
@@ -321,7 +386,7 @@ __global__ void __launch_bounds__(256)
         }
     }
     int exch = 0;
-    fft_stages<T, N, true, 0, true>(v, t, sm, tw, exch);
+    fft_stages<T, N, true, 0, 1>(v, t, sm, tw, exch);
     if (valid) {
         T *ra = R + (long long)(2 * jp) * g.rs[1] + (long long)kz * g.rs[2];
         T *rb = ra + g.rs[1];
@@ -336,55 +401,38 @@ __global__ void __launch_bounds__(256)
 // ----------------------------------------------------------------------------------------
 // host launchers
 // ----------------------------------------------------------------------------------------
-static int line_stride(int N, int lines_per_txn, int elem_bytes) {
-    int banks = 128 / elem_bytes;
-    int want = banks / (lines_per_txn < banks ? (lines_per_txn < 1 ? 1 : lines_per_txn) : banks);
-    int ls = phys(N - 1) + 1;
-    while (ls % banks != want % banks) ls++;
-    return ls;
+template <typename K>
+static int allow_smem(K kern, size_t smem) {
+    if (smem > 48 * 1024) INSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return 0;
 }
 
 template <typename T, int N>
 static int fast_pass_n(int kind, T *R, Cx<T> *W, const FastGeom &g, int tdim, const Cx<T> *tw, const T *e0,
-                       const T *e1, const T *e2, T factor, int tile, Launch L) {
-    constexpr int P = FftShape<N>::P;
-    static bool attr_done[5] = {false, false, false, false, false};
+                       const T *e1, const T *e2, T factor, Launch L) {
     if (kind <= 2) {  // strided
-        int Lt = tile;
-        while (Lt * P > 512 && Lt > 1) Lt >>= 1;
-        int LS = line_stride(N, Lt, sizeof(T));
-        size_t smem = (size_t)4 * Lt * LS * sizeof(T);
-        dim3 grid(g.m0p / Lt, g.D == 3 ? (g.nother >= 0 ? g.nother : g.n[tdim == 1 ? 2 : 1]) : 1);
-        static const bool uncapped = getenv("INSB200_FFT_MID_UNCAPPED") != nullptr;
-        auto kern = kind == 0 ? fft_strided_kernel<T, N, 0> : kind == 1 ? fft_strided_kernel<T, N, 1>
-                    : uncapped ? fft_strided_kernel<T, N, 3> : fft_strided_kernel<T, N, 2>;
-        INSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        if (smem > 200 * 1024) {
-            set_error("fast FFT pass: tile does not fit in shared memory");
+        typedef StridedShape<T, N> SS;
+        if (g.m0p % SS::L) {
+            set_error("fast FFT pass: padded half-spectrum extent must be a multiple of the line tile");
             return 1;
         }
-        kern<<<grid, Lt * P, smem, L.stream>>>(W, g, tdim, Lt, LS, tw, e0, e1, e2, factor);
+        const bool blk = g.in_sh < 30 || g.out_sh < 30;
+        dim3 grid(g.m0p / SS::L, g.D == 3 ? (g.nother >= 0 ? g.nother : g.n[tdim == 1 ? 2 : 1]) : 1);
+        auto kern = kind == 0 ? (blk ? fft_strided_kernel<T, N, 0, true> : fft_strided_kernel<T, N, 0, false>)
+                    : kind == 1 ? (blk ? fft_strided_kernel<T, N, 1, true> : fft_strided_kernel<T, N, 1, false>)
+                                : (blk ? fft_strided_kernel<T, N, 2, true> : fft_strided_kernel<T, N, 2, false>);
+        INSB_TRY(allow_smem(kern, SS::smem));
+        kern<<<grid, SS::NT, SS::smem, L.stream>>>(W, g, tdim, tw, e0, e1, e2, factor);
     } else {
-        int LP = 256 / P;
-        if (LP < 1) LP = 1;
-        int LS = line_stride(N, 32 / (P < 32 ? P : 32), sizeof(T));
-        size_t smem = (size_t)4 * LP * LS * sizeof(T);
+        typedef XShape<T, N> XS;
         long long npairs = (long long)(g.n[1] / 2) * (g.D == 3 ? g.n[2] : 1);
-        unsigned blocks = (unsigned)((npairs + LP - 1) / LP);
+        unsigned blocks = (unsigned)((npairs + XS::LP - 1) / XS::LP);
         if (kind == 3) {
-            if (!attr_done[3]) {
-                INSB_CUDA(cudaFuncSetAttribute(fft_x_r2c_kernel<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               200 * 1024));
-                attr_done[3] = true;
-            }
-            fft_x_r2c_kernel<T, N><<<blocks, LP * P, smem, L.stream>>>(R, W, g, LP, LS, tw, npairs);
+            INSB_TRY(allow_smem(fft_x_r2c_kernel<T, N>, XS::smem));
+            fft_x_r2c_kernel<T, N><<<blocks, XS::NT, XS::smem, L.stream>>>(R, W, g, tw, npairs);
         } else {
-            if (!attr_done[4]) {
-                INSB_CUDA(cudaFuncSetAttribute(fft_x_c2r_kernel<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               200 * 1024));
-                attr_done[4] = true;
-            }
-            fft_x_c2r_kernel<T, N><<<blocks, LP * P, smem, L.stream>>>(R, W, g, LP, LS, tw, npairs);
+            INSB_TRY(allow_smem(fft_x_c2r_kernel<T, N>, XS::smem));
+            fft_x_c2r_kernel<T, N><<<blocks, XS::NT, XS::smem, L.stream>>>(R, W, g, tw, npairs);
         }
     }
     if (L.counter) ++*L.counter;
@@ -398,14 +446,15 @@ int fast_pass(int kind, int N, T *R, void *W, const FastGeom &g, int tdim, const
               const T *e1, const T *e2, T factor, int tile, Launch L) {
     Cx<T> *Wc = (Cx<T> *)W;
     const Cx<T> *twc = (const Cx<T> *)tw;
+    (void)tile;
     switch (N) {
-        case 32: return fast_pass_n<T, 32>(kind, R, Wc, g, tdim, twc, e0, e1, e2, factor, tile, L);
-        case 64: return fast_pass_n<T, 64>(kind, R, Wc, g, tdim, twc, e0, e1, e2, factor, tile, L);
-        case 128: return fast_pass_n<T, 128>(kind, R, Wc, g, tdim, twc, e0, e1, e2, factor, tile, L);
-        case 256: return fast_pass_n<T, 256>(kind, R, Wc, g, tdim, twc, e0, e1, e2, factor, tile, L);
-        case 512: return fast_pass_n<T, 512>(kind, R, Wc, g, tdim, twc, e0, e1, e2, factor, tile, L);
-        case 1024: return fast_pass_n<T, 1024>(kind, R, Wc, g, tdim, twc, e0, e1, e2, factor, tile, L);
-        case 2048: return fast_pass_n<T, 2048>(kind, R, Wc, g, tdim, twc, e0, e1, e2, factor, tile, L);
+        case 32: return fast_pass_n<T, 32>(kind, R, Wc, g, tdim, twc, e0, e1, e2, factor, L);
+        case 64: return fast_pass_n<T, 64>(kind, R, Wc, g, tdim, twc, e0, e1, e2, factor, L);
+        case 128: return fast_pass_n<T, 128>(kind, R, Wc, g, tdim, twc, e0, e1, e2, factor, L);
+        case 256: return fast_pass_n<T, 256>(kind, R, Wc, g, tdim, twc, e0, e1, e2, factor, L);
+        case 512: return fast_pass_n<T, 512>(kind, R, Wc, g, tdim, twc, e0, e1, e2, factor, L);
+        case 1024: return fast_pass_n<T, 1024>(kind, R, Wc, g, tdim, twc, e0, e1, e2, factor, L);
+        case 2048: return fast_pass_n<T, 2048>(kind, R, Wc, g, tdim, twc, e0, e1, e2, factor, L);
     }
     set_error("fast FFT pass: unsupported length");
     return 1;

@@ -113,6 +113,15 @@ PSOLVER_CASES = [
     ("spectral2", (uniform(32, 2 * np.pi), uniform(32, 2 * np.pi)), ("P", "P"), "spectral"),
     ("spectral3", (uniform(16), uniform(12, 2.0), uniform(20, 0.5)), ("P", "P", "P"), "spectral"),
     ("spectral3b", (uniform(64), uniform(32), uniform(16)), ("P", "P", "P"), "spectral"),
+    # every length of the register-FFT fast path (32..2048), in every position
+    ("spectral_fast_128_32_256", (uniform(128), uniform(32), uniform(256)), ("P", "P", "P"), "spectral"),
+    ("spectral_fast_256_128_32", (uniform(256), uniform(128), uniform(32)), ("P", "P", "P"), "spectral"),
+    ("spectral_fast_512_32_64", (uniform(512), uniform(32), uniform(64)), ("P", "P", "P"), "spectral"),
+    ("spectral_fast_32_1024_32", (uniform(32), uniform(1024), uniform(32)), ("P", "P", "P"), "spectral"),
+    ("spectral_fast_64_32_512", (uniform(64), uniform(32), uniform(512)), ("P", "P", "P"), "spectral"),
+    ("spectral_fast_32_32_2048", (uniform(32), uniform(32), uniform(2048)), ("P", "P", "P"), "spectral"),
+    ("spectral_fast_2048_64", (uniform(2048, 2 * np.pi), uniform(64, 2 * np.pi)), ("P", "P"), "spectral"),
+    ("spectral_fast_1024_2048", (uniform(1024, 2 * np.pi), uniform(2048, 2 * np.pi)), ("P", "P"), "spectral"),
     ("transform_pp", (uniform(32, 2 * np.pi), uniform(32, 2 * np.pi)), ("P", "P"), "transform"),
     ("transform_pw", (uniform(16, 2.0), uniform(12)), ("P", "D"), "transform"),
     ("transform_wp", (uniform(10), uniform(16, 2.0)), ("D", "P"), "transform"),
