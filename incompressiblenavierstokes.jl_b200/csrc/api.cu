@@ -2,6 +2,7 @@
 // libinsb200.so (declared in include/insb200.h).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -33,6 +34,7 @@ struct insb200_plan {
     Comm *comm = nullptr;  // z-slab decomposition (world > 1)
     int nzl = 0;           // interior planes owned by this rank
     int Iu_loc[3][3][2];   // Iu with the z range of this slab (cfl reduction)
+    int wrap = 0;          // dims whose periodic ghost handling is fused into the divergence / projection kernels
     Poisson *ps = nullptr;
     int psolver = INSB200_PSOLVER_NONE;
     // work buffers (device): two stage buffers and the accumulator for u (and temp), p scratch,
@@ -226,30 +228,34 @@ const Grid<float> &grid_of<float>(const insb200_plan *pl) { return pl->gf; }
 template <>
 const Grid<double> &grid_of<double>(const insb200_plan *pl) { return pl->gd; }
 
+// fused = the time-stepper variant: the periodic dimensions in pl->wrap need no ghost fills of
+// v and p (the kernels wrap their neighbour indices) and the projected velocity is stored
+// together with its periodic ghost images, i.e. project! followed by apply_bc_u!.
 template <typename T>
-int project_t(insb200_plan *pl, T *u, T *p, void *stream) {
+int project_t(insb200_plan *pl, T *u, T *p, void *stream, bool fused = false) {
     // project! (src/pressure.jl:42-55)
     const Grid<T> &g = grid_of<T>(pl);
     Launch L = L_of(pl, stream);
+    const int wrap = fused ? pl->wrap : 0, rest = 7 & ~wrap;
     if (!pl->ps) {
         set_error("this plan has no Poisson solver (psolver = NONE / unsupported BC combination)");
         return 1;
     }
     {
         Scope sc(pl, L.stream, 1);
-        INSB_TRY(launch_divergence<T>(g, u, p, true, L));
+        INSB_TRY(launch_divergence<T>(g, u, p, true, L, wrap));
     }
     {
         Scope sc(pl, L.stream, 2);
         INSB_TRY(poisson_solve(pl->ps, p, L));
     }
-    {
+    if (rest & ((1 << g.D) - 1)) {
         Scope sc(pl, L.stream, 4);
-        INSB_TRY(launch_bc_p<T>(g, pl->bc, p, L));
+        INSB_TRY(launch_bc_p<T>(g, pl->bc, p, L, rest));
     }
     {
         Scope sc(pl, L.stream, 3);
-        INSB_TRY(launch_pressuregradient<T>(g, p, (T *)nullptr, u, L));
+        INSB_TRY(launch_pressuregradient<T>(g, p, (T *)nullptr, u, L, wrap));
     }
     return 0;
 }
@@ -305,14 +311,15 @@ template <typename T>
 int finish_stage(insb200_plan *pl, T *v, T *tv, double t, void *stream) {
     const Grid<T> &g = grid_of<T>(pl);
     Launch L = L_of(pl, stream);
-    {
+    const int rest = 7 & ~pl->wrap & ((1 << g.D) - 1);  // dimensions that still need explicit ghost fills
+    if (rest) {
         Scope sc(pl, L.stream, 4);
-        INSB_TRY(launch_bc_u<T>(g, pl->bc, v, 0, L));
+        INSB_TRY(launch_bc_u<T>(g, pl->bc, v, 0, L, rest));
     }
-    INSB_TRY(project_t<T>(pl, v, (T *)pl->P, stream));
+    INSB_TRY(project_t<T>(pl, v, (T *)pl->P, stream, true));
     {
         Scope sc(pl, L.stream, 4);
-        INSB_TRY(launch_bc_u<T>(g, pl->bc, v, 0, L));
+        if (rest) INSB_TRY(launch_bc_u<T>(g, pl->bc, v, 0, L, rest));
         if (tv) INSB_TRY(launch_bc_temp<T>(g, pl->bc, tv, L));
     }
     (void)t;
@@ -621,6 +628,9 @@ int insb200_plan_create(const insb200_setup_t *setup, insb200_plan_t **out) {
     }
     std::memset(&pl->bc, 0, sizeof(pl->bc));
     pl->bc.comm = pl->comm;
+    if (getenv("INSB200_NO_BC_FUSION") == nullptr)
+        for (int a = 0; a < s.D; a++)
+            if (s.bc_u[a][0] == INSB200_BC_PERIODIC && !(a == 2 && pl->comm)) pl->wrap |= 1 << a;
     std::memcpy(pl->bc.bc_u, s.bc_u, sizeof(s.bc_u));
     std::memcpy(pl->bc.bc_temp, s.has_temp ? s.bc_temp : s.bc_u, sizeof(s.bc_u));
     std::memcpy(pl->bc.u_val, s.bc_u_value, sizeof(s.bc_u_value));

@@ -84,8 +84,9 @@ static int halo_dim(const Grid<T> &g, const BcDesc &b, T *f, int ncomp, Launch L
 }
 
 template <typename T>
-int launch_bc_u(const Grid<T> &g, const BcDesc &b, T *u, int dudt, Launch L) {
+int launch_bc_u(const Grid<T> &g, const BcDesc &b, T *u, int dudt, Launch L, int dims) {
     for (int beta = 0; beta < g.D; beta++) {
+        if (!(dims >> beta & 1)) continue;
         if (beta == 2 && b.comm) {
             INSB_TRY(halo_dim<T>(g, b, u, g.D, L));
             continue;
@@ -144,8 +145,9 @@ int launch_bc_u(const Grid<T> &g, const BcDesc &b, T *u, int dudt, Launch L) {
 
 template <typename T>
 static int scalar_bc(const Grid<T> &g, const BcDesc &b, const int (*types)[2], bool is_temp, T *p,
-                     Launch L) {
+                     Launch L, int dims = 7) {
     for (int beta = 0; beta < g.D; beta++) {
+        if (!(dims >> beta & 1)) continue;
         if (beta == 2 && b.comm) {  // decomposed direction is periodic for every field
             INSB_TRY(halo_dim<T>(g, b, p, 1, L));
             continue;
@@ -196,18 +198,18 @@ static int scalar_bc(const Grid<T> &g, const BcDesc &b, const int (*types)[2], b
 }
 
 template <typename T>
-int launch_bc_p(const Grid<T> &g, const BcDesc &b, T *p, Launch L) {
-    return scalar_bc<T>(g, b, b.bc_u, false, p, L);
+int launch_bc_p(const Grid<T> &g, const BcDesc &b, T *p, Launch L, int dims) {
+    return scalar_bc<T>(g, b, b.bc_u, false, p, L, dims);
 }
 template <typename T>
 int launch_bc_temp(const Grid<T> &g, const BcDesc &b, T *temp, Launch L) {
     return scalar_bc<T>(g, b, b.bc_temp, true, temp, L);
 }
 
-template int launch_bc_u<float>(const Grid<float> &, const BcDesc &, float *, int, Launch);
-template int launch_bc_u<double>(const Grid<double> &, const BcDesc &, double *, int, Launch);
-template int launch_bc_p<float>(const Grid<float> &, const BcDesc &, float *, Launch);
-template int launch_bc_p<double>(const Grid<double> &, const BcDesc &, double *, Launch);
+template int launch_bc_u<float>(const Grid<float> &, const BcDesc &, float *, int, Launch, int);
+template int launch_bc_u<double>(const Grid<double> &, const BcDesc &, double *, int, Launch, int);
+template int launch_bc_p<float>(const Grid<float> &, const BcDesc &, float *, Launch, int);
+template int launch_bc_p<double>(const Grid<double> &, const BcDesc &, double *, Launch, int);
 template int launch_bc_temp<float>(const Grid<float> &, const BcDesc &, float *, Launch);
 template int launch_bc_temp<double>(const Grid<double> &, const BcDesc &, double *, Launch);
 

@@ -117,21 +117,22 @@ struct Launch {
 template <typename T>
 int launch_stage(const Grid<T> &g, const StageArgs<T> &a, bool ct_double, Launch L);
 template <typename T>
-int launch_divergence(const Grid<T> &g, const T *u, T *div, bool scale, Launch L);
+int launch_divergence(const Grid<T> &g, const T *u, T *div, bool scale, Launch L, int wrap = 0);
 template <typename T>
 int launch_scalewithvolume(const Grid<T> &g, T *p, Launch L);
 template <typename T>
-int launch_pressuregradient(const Grid<T> &g, const T *p, T *G, T *u_sub, Launch L);
+int launch_pressuregradient(const Grid<T> &g, const T *p, T *G, T *u_sub, Launch L, int wrap = 0);
 template <typename T>
 int launch_cfl(const Grid<T> &g, const int Iu[3][3][2], const T *u, double *scratch, Launch L);
 template <typename T>
 int launch_maxabs(const T *u, long long n, double *scratch, Launch L);
 
 // ---- bc.cu ----
+// dims: bit mask of the dimensions to fill (default all)
 template <typename T>
-int launch_bc_u(const Grid<T> &g, const BcDesc &b, T *u, int dudt, Launch L);
+int launch_bc_u(const Grid<T> &g, const BcDesc &b, T *u, int dudt, Launch L, int dims = 7);
 template <typename T>
-int launch_bc_p(const Grid<T> &g, const BcDesc &b, T *p, Launch L);
+int launch_bc_p(const Grid<T> &g, const BcDesc &b, T *p, Launch L, int dims = 7);
 template <typename T>
 int launch_bc_temp(const Grid<T> &g, const BcDesc &b, T *temp, Launch L);
 

@@ -737,9 +737,11 @@ template int launch_stage<double>(const Grid<double> &, const StageArgs<double> 
 // first store so that RB x (D+D) independent requests are in flight per thread.
 constexpr int RB = 4;
 
+// wrap: bit d set = dimension d is periodic and the lower neighbour of the first interior cell is
+// taken from the last interior cell instead of the ghost cell (which then need not be filled).
 template <typename T, int D>
 __global__ void __launch_bounds__(128) divergence_kernel(Grid<T> g, const T *__restrict__ u,
-                                                         T *__restrict__ div, int scale) {
+                                                         T *__restrict__ div, int scale, int wrap) {
     const int ix = blockIdx.x * blockDim.x + threadIdx.x + 1;
     const int iy0 = blockIdx.y * RB + 1;
     const int iz = (D == 3) ? (int)blockIdx.z + 1 : 0;
@@ -747,20 +749,22 @@ __global__ void __launch_bounds__(128) divergence_kernel(Grid<T> g, const T *__r
     const long long s1 = g.s[1], s2 = g.s[2], cs = g.cs;
     const long long base = ix + iy0 * s1 + (D == 3 ? iz * s2 : 0);
     const int ny = g.N[1] - 1;
+    const long long xm = ((wrap & 1) && ix == 1) ? g.N[0] - 3 : -1;                      // offset to ix-1
+    const long long zm = ((wrap & 4) && iz == 1) ? (long long)(g.N[2] - 3) * s2 : -s2;   // offset to iz-1
     T ux[RB], uxm[RB], uy[RB + 1], uz[RB], uzm[RB];
 #pragma unroll
     for (int r = 0; r < RB; r++) {
         const bool ok = iy0 + r < ny;
         const long long q = base + r * s1;
         ux[r] = ok ? __ldg(u + q) : T(0);
-        uxm[r] = ok ? __ldg(u + q - 1) : T(0);
+        uxm[r] = ok ? __ldg(u + q + xm) : T(0);
         uy[r + 1] = ok ? __ldg(u + cs + q) : T(0);
         if (D == 3) {
             uz[r] = ok ? __ldg(u + 2 * cs + q) : T(0);
-            uzm[r] = ok ? __ldg(u + 2 * cs + q - s2) : T(0);
+            uzm[r] = ok ? __ldg(u + 2 * cs + q + zm) : T(0);
         }
     }
-    uy[0] = __ldg(u + cs + base - s1);
+    uy[0] = __ldg(u + cs + base + (((wrap & 2) && iy0 == 1) ? (long long)(g.N[1] - 3) * s1 : -s1));
     const T rx = __ldg(g.rdlg[0] + ix), dx = __ldg(g.dl[0] + ix);
     T rz = T(0), dz = T(1);
     if (D == 3) {
@@ -783,19 +787,19 @@ __global__ void __launch_bounds__(128) divergence_kernel(Grid<T> g, const T *__r
 }
 
 template <typename T>
-int launch_divergence(const Grid<T> &g, const T *u, T *div, bool scale, Launch L) {
+int launch_divergence(const Grid<T> &g, const T *u, T *div, bool scale, Launch L, int wrap) {
     dim3 b(128, 1, 1);
     dim3 gr((g.N[0] - 2 + b.x - 1) / b.x, (g.N[1] - 2 + RB - 1) / RB, g.D == 3 ? g.N[2] - 2 : 1);
     if (g.D == 3)
-        divergence_kernel<T, 3><<<gr, b, 0, L.stream>>>(g, u, div, scale);
+        divergence_kernel<T, 3><<<gr, b, 0, L.stream>>>(g, u, div, scale, wrap);
     else
-        divergence_kernel<T, 2><<<gr, b, 0, L.stream>>>(g, u, div, scale);
+        divergence_kernel<T, 2><<<gr, b, 0, L.stream>>>(g, u, div, scale, wrap);
     if (L.counter) ++*L.counter;
     INSB_CUDA(cudaGetLastError());
     return 0;
 }
-template int launch_divergence<float>(const Grid<float> &, const float *, float *, bool, Launch);
-template int launch_divergence<double>(const Grid<double> &, const double *, double *, bool, Launch);
+template int launch_divergence<float>(const Grid<float> &, const float *, float *, bool, Launch, int);
+template int launch_divergence<double>(const Grid<double> &, const double *, double *, bool, Launch, int);
 
 template <typename T>
 __global__ void __launch_bounds__(256) scalewithvolume_kernel(Grid<T> g, T *p) {
@@ -824,8 +828,12 @@ template int launch_scalewithvolume<double>(const Grid<double> &, double *, Laun
 // ------------------------------------------------------------------------------------
 // pressure gradient: G = δp (pressuregradient!) or u += -δp (applypressure!)
 // ------------------------------------------------------------------------------------
+// wrap: bit d set = dimension d is periodic: the upper neighbour of the last interior pressure is the
+// first interior one (p ghosts need not be filled), and every updated velocity is also stored
+// to its periodic ghost images (what apply_bc_u! would copy afterwards,
+// src/boundary_conditions.jl:273-285, dims in order => edges and corners included).
 template <typename T, int D>
-__global__ void __launch_bounds__(128) pgrad_kernel(Grid<T> g, const T *__restrict__ p, T *G, T *usub) {
+__global__ void __launch_bounds__(128) pgrad_kernel(Grid<T> g, const T *__restrict__ p, T *G, T *usub, int wrap) {
     const int ix = blockIdx.x * blockDim.x + threadIdx.x + 1;
     const int iy0 = blockIdx.y * RB + 1;
     const int iz = (D == 3) ? (int)blockIdx.z + 1 : 0;
@@ -833,60 +841,90 @@ __global__ void __launch_bounds__(128) pgrad_kernel(Grid<T> g, const T *__restri
     const long long s1 = g.s[1], s2 = g.s[2], cs = g.cs;
     const long long base = ix + iy0 * s1 + (D == 3 ? iz * s2 : 0);
     const int ny = g.N[1] - 1;
+    const long long xp = ((wrap & 1) && ix == g.N[0] - 2) ? -(long long)(g.N[0] - 3) : 1;
+    const long long zp = ((wrap & 4) && iz == g.N[2] - 2) ? -(long long)(g.N[2] - 3) * s2 : s2;
     T pc[RB + 1], px[RB], pz[RB], uo[D][RB];
 #pragma unroll
     for (int r = 0; r < RB; r++) {
         const bool ok = iy0 + r < ny;
         const long long q = base + r * s1;
         pc[r] = ok ? __ldg(p + q) : T(0);
-        px[r] = ok ? __ldg(p + q + 1) : T(0);
-        if (D == 3) pz[r] = ok ? __ldg(p + q + s2) : T(0);
+        px[r] = ok ? __ldg(p + q + xp) : T(0);
+        if (D == 3) pz[r] = ok ? __ldg(p + q + zp) : T(0);
         if (usub) {
 #pragma unroll
             for (int c = 0; c < D; c++) uo[c][r] = ok ? usub[q + c * cs] : T(0);
         }
     }
     {
-        const int last = min(iy0 + RB, ny);  // row above the last one handled here (<= N1-1, in bounds)
+        int last = min(iy0 + RB, ny);  // row above the last one handled here (<= N1-1, in bounds)
+        const int lastr = last;
+        if ((wrap & 2) && last == ny) last = 1;
         const T top = __ldg(p + ix + last * s1 + (D == 3 ? iz * s2 : 0));
         pc[RB] = T(0);
 #pragma unroll
         for (int r = 1; r <= RB; r++)
-            if (iy0 + r == last) pc[r] = top;
+            if (iy0 + r == lastr) pc[r] = top;
     }
     const T rx = __ldg(g.rdu[0] + ix);
     const T rz = D == 3 ? __ldg(g.rdu[2] + iz) : T(0);
+    // periodic ghost images of this column: offsets (0 = none)
+    const long long gx = !(wrap & 1) ? 0 : ix == 1 ? g.N[0] - 2 : ix == g.N[0] - 2 ? -(long long)(g.N[0] - 2) : 0;
+    const long long gz = !(D == 3 && (wrap & 4)) ? 0
+                         : iz == 1 ? (long long)(g.N[2] - 2) * s2 : iz == g.N[2] - 2 ? -(long long)(g.N[2] - 2) * s2 : 0;
 #pragma unroll
     for (int r = 0; r < RB; r++) {
         if (iy0 + r >= ny) break;
+        const int iy = iy0 + r;
         const long long q = base + r * s1;
         T d[3];
         d[0] = (px[r] - pc[r]) * rx;
-        d[1] = (pc[r + 1] - pc[r]) * __ldg(g.rdu[1] + iy0 + r);
+        d[1] = (pc[r + 1] - pc[r]) * __ldg(g.rdu[1] + iy);
         if (D == 3) d[2] = (pz[r] - pc[r]) * rz;
+        const long long gy = !(wrap & 2) ? 0 : iy == 1 ? (long long)(g.N[1] - 2) * s1
+                                               : iy == g.N[1] - 2 ? -(long long)(g.N[1] - 2) * s1 : 0;
 #pragma unroll
         for (int c = 0; c < D; c++) {
             if (G) G[q + c * cs] = d[c];
-            if (usub) usub[q + c * cs] = uo[c][r] - d[c];
+            if (usub) {
+                const T v = uo[c][r] - d[c];
+                T *o = usub + q + c * cs;
+                o[0] = v;
+                if (wrap) {
+                    if (gx) o[gx] = v;
+                    if (gy) {
+                        o[gy] = v;
+                        if (gx) o[gy + gx] = v;
+                    }
+                    if (gz) {
+                        o[gz] = v;
+                        if (gx) o[gz + gx] = v;
+                        if (gy) {
+                            o[gz + gy] = v;
+                            if (gx) o[gz + gy + gx] = v;
+                        }
+                    }
+                }
+            }
         }
     }
 }
 
 template <typename T>
-int launch_pressuregradient(const Grid<T> &g, const T *p, T *G, T *u_sub, Launch L) {
+int launch_pressuregradient(const Grid<T> &g, const T *p, T *G, T *u_sub, Launch L, int wrap) {
     dim3 b(128, 1, 1);
     dim3 gr((g.N[0] - 2 + b.x - 1) / b.x, (g.N[1] - 2 + RB - 1) / RB, g.D == 3 ? g.N[2] - 2 : 1);
     if (g.D == 3)
-        pgrad_kernel<T, 3><<<gr, b, 0, L.stream>>>(g, p, G, u_sub);
+        pgrad_kernel<T, 3><<<gr, b, 0, L.stream>>>(g, p, G, u_sub, wrap);
     else
-        pgrad_kernel<T, 2><<<gr, b, 0, L.stream>>>(g, p, G, u_sub);
+        pgrad_kernel<T, 2><<<gr, b, 0, L.stream>>>(g, p, G, u_sub, wrap);
     if (L.counter) ++*L.counter;
     INSB_CUDA(cudaGetLastError());
     return 0;
 }
-template int launch_pressuregradient<float>(const Grid<float> &, const float *, float *, float *, Launch);
+template int launch_pressuregradient<float>(const Grid<float> &, const float *, float *, float *, Launch, int);
 template int launch_pressuregradient<double>(const Grid<double> &, const double *, double *, double *,
-                                             Launch);
+                                             Launch, int);
 
 // ------------------------------------------------------------------------------------
 // reductions: convective CFL limit (src/solver.jl:171-186) and maximum(abs, u)
