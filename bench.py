@@ -255,6 +255,7 @@ def run_gpu(args):
     # projection 7w; bytes = count * w * n^3
     alg = {"rhs_combine": 12.0, "divergence": 4.0, "poisson": 10.0, "project": 7.0}
     dom = max(alg, key=lambda k: prof[k][0])
+    alg.update({k: 2.0 for k in ("fft_x_r2c", "fft_y_fwd", "fft_z_mid", "fft_y_inv", "fft_x_c2r")})
     d_ms, d_cnt = prof[dom]
     per = d_ms / max(d_cnt, 1)
     achieved = alg[dom] * w * n**3 / (per * 1e-3) / 1e9

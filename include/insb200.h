@@ -105,6 +105,13 @@ int insb200_plan_create(const insb200_setup_t *setup, insb200_plan_t **out);
 /* Rank 0 calls this and ships the 128 bytes to the other ranks (MPI.jl / Distributed in Julia,
  * torch.distributed in the Python harness) before every rank calls insb200_plan_create. */
 int insb200_comm_unique_id(void *id128);
+/* Direct peer-store transposes of the distributed FFT (NVLink P2P through CUDA IPC; optional,
+ * the NCCL all-to-all is used otherwise): every rank exports a 192-byte blob, the host gathers
+ * the blobs of all ranks in rank order (world x 192 bytes) and every rank imports them.  The
+ * strided FFT passes then store each tile straight into the destination rank's buffer and
+ * ranks synchronise through flags in peer memory. */
+int insb200_plan_ipc_export(insb200_plan_t *plan, void *blob192);
+int insb200_plan_ipc_import(insb200_plan_t *plan, const void *blobs);
 /* Extents (including ghosts) of the arrays this rank passes in: N of the setup, with the slab
  * extent in z when world > 1. */
 int insb200_plan_local_n(const insb200_plan_t *plan, int N_local[3]);
@@ -183,6 +190,10 @@ int insb200_profile_enable(insb200_plan_t *plan, int on);
 /* ms accumulated per group [0]=rhs+combine, [1]=divergence, [2]=poisson, [3]=project, [4]=bc;
  * counts = number of brackets; resets the accumulators. Synchronises. */
 int insb200_profile_read(insb200_plan_t *plan, double ms[5], long long counts[5]);
+/* Same with the Poisson solve broken down: groups [5]=x_r2c, [6]=y_fwd, [7]=transpose_fwd,
+ * [8]=z_mid (forward + eigenvalue divide + inverse), [9]=transpose_bwd, [10]=y_inv, [11]=x_c2r;
+ * n <= 12 entries are written. */
+int insb200_profile_read_ex(insb200_plan_t *plan, int n, double *ms, long long *counts);
 
 #ifdef __cplusplus
 }

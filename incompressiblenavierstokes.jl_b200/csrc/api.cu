@@ -17,7 +17,7 @@ void set_error(const std::string &msg) { g_err = msg; }
 
 using namespace insb;
 
-struct insb200_plan {
+struct insb200_plan : public insb::Profiler {
     insb200_setup_t s;
     bool f64 = false;
     size_t esz = 4;
@@ -50,15 +50,41 @@ struct insb200_plan {
     double dmin_u[3], dmin_p[3];
     // profiling
     bool prof = false;
-    cudaEvent_t ev[6];
-    double prof_ms[5] = {0, 0, 0, 0, 0};
-    long long prof_cnt[5] = {0, 0, 0, 0, 0};
+    double prof_ms[NPROF] = {};
+    long long prof_cnt[NPROF] = {};
     struct Bracket {
         cudaEvent_t a, b;
         int group;
     };
     std::vector<Bracket> brackets;
     std::vector<cudaEvent_t> evpool;
+    std::vector<std::pair<int, cudaEvent_t>> open_;  // begin events waiting for their end
+    cudaEvent_t get_event() {
+        cudaEvent_t e;
+        if (!evpool.empty()) {
+            e = evpool.back();
+            evpool.pop_back();
+        } else
+            cudaEventCreate(&e);
+        return e;
+    }
+    void begin(int group, cudaStream_t st) override {
+        if (!prof) return;
+        cudaEvent_t e = get_event();
+        cudaEventRecord(e, st);
+        open_.push_back({group, e});
+    }
+    void end(int group, cudaStream_t st) override {
+        if (!prof) return;
+        for (size_t i = open_.size(); i-- > 0;)
+            if (open_[i].first == group) {
+                cudaEvent_t b = get_event();
+                cudaEventRecord(b, st);
+                brackets.push_back({open_[i].second, b, group});
+                open_.erase(open_.begin() + i);
+                return;
+            }
+    }
 };
 
 namespace {
@@ -191,34 +217,15 @@ int resolve_default_psolver(const insb200_plan *pl) {
     return INSB200_PSOLVER_NONE;  // psolver_direct is outside the hot path
 }
 
-Launch L_of(insb200_plan *pl, void *stream) { return Launch{(cudaStream_t)stream, &pl->launches}; }
+Launch L_of(insb200_plan *pl, void *stream) { return Launch{(cudaStream_t)stream, &pl->launches, pl}; }
 
 // ---- profiling brackets -------------------------------------------------------------
 struct Scope {
     insb200_plan *pl;
     cudaStream_t st;
     int group;
-    cudaEvent_t a = nullptr, b = nullptr;
-    Scope(insb200_plan *p, cudaStream_t s, int g) : pl(p), st(s), group(g) {
-        if (!pl->prof) return;
-        auto get = [&]() {
-            cudaEvent_t e;
-            if (!pl->evpool.empty()) {
-                e = pl->evpool.back();
-                pl->evpool.pop_back();
-            } else
-                cudaEventCreate(&e);
-            return e;
-        };
-        a = get();
-        b = get();
-        cudaEventRecord(a, st);
-    }
-    ~Scope() {
-        if (!pl->prof) return;
-        cudaEventRecord(b, st);
-        pl->brackets.push_back({a, b, group});
-    }
+    Scope(insb200_plan *p, cudaStream_t s, int g) : pl(p), st(s), group(g) { pl->begin(group, st); }
+    ~Scope() { pl->end(group, st); }
 };
 
 template <typename T>
@@ -691,6 +698,25 @@ int insb200_plan_local_n(const insb200_plan_t *pl, int N_local[3]) {
     return 0;
 }
 
+int insb200_plan_ipc_export(insb200_plan_t *pl, void *blob192) {
+    API_BEGIN
+    if (!pl || !pl->ps) {
+        set_error("ipc export: the plan has no Poisson solver");
+        return 1;
+    }
+    return poisson_ipc_export(pl->ps, blob192);
+    API_END
+}
+int insb200_plan_ipc_import(insb200_plan_t *pl, const void *blobs) {
+    API_BEGIN
+    if (!pl || !pl->ps) {
+        set_error("ipc import: the plan has no Poisson solver");
+        return 1;
+    }
+    return poisson_ipc_import(pl->ps, blobs);
+    API_END
+}
+
 int insb200_plan_psolver(const insb200_plan_t *pl) { return pl ? pl->psolver : INSB200_PSOLVER_NONE; }
 long long insb200_plan_workspace_bytes(const insb200_plan_t *pl) { return pl ? pl->bytes : 0; }
 long long insb200_launch_count(const insb200_plan_t *pl) { return pl ? pl->launches : 0; }
@@ -906,8 +932,7 @@ int insb200_profile_enable(insb200_plan_t *pl, int on) {
     pl->prof = on != 0;
     return 0;
 }
-int insb200_profile_read(insb200_plan_t *pl, double ms[5], long long counts[5]) {
-    API_BEGIN
+static int profile_collect(insb200_plan_t *pl) {
     INSB_CUDA(cudaDeviceSynchronize());
     for (auto &b : pl->brackets) {
         float t = 0;
@@ -918,14 +943,24 @@ int insb200_profile_read(insb200_plan_t *pl, double ms[5], long long counts[5]) 
         pl->evpool.push_back(b.b);
     }
     pl->brackets.clear();
-    for (int i = 0; i < 5; i++) {
-        ms[i] = pl->prof_ms[i];
-        counts[i] = pl->prof_cnt[i];
+    return 0;
+}
+int insb200_profile_read_ex(insb200_plan_t *pl, int n, double *ms, long long *counts) {
+    API_BEGIN
+    INSB_TRY(profile_collect(pl));
+    for (int i = 0; i < NPROF; i++) {
+        if (i < n) {
+            ms[i] = pl->prof_ms[i];
+            counts[i] = pl->prof_cnt[i];
+        }
         pl->prof_ms[i] = 0;
         pl->prof_cnt[i] = 0;
     }
     return 0;
     API_END
+}
+int insb200_profile_read(insb200_plan_t *pl, double ms[5], long long counts[5]) {
+    return insb200_profile_read_ex(pl, 5, ms, counts);
 }
 
 }  // extern "C"

@@ -202,4 +202,51 @@ int comm_reduce_scratch(Comm *c, double *scratch, bool is_min, cudaStream_t st) 
     return 0;
 }
 
+// ---- peer flags ---------------------------------------------------------------------------
+struct PeerPtrs {
+    unsigned *p[8];
+};
+
+__global__ void signal_peers_kernel(PeerPtrs flags, int row, int rank, int world, unsigned epoch) {
+    __threadfence_system();
+    int s = threadIdx.x;
+    if (s < world) {
+        volatile unsigned *f = flags.p[s] + row * 8 + rank;
+        *f = epoch;
+    }
+    __threadfence_system();
+}
+
+__global__ void wait_flags_kernel(unsigned *flags, int row, int world, unsigned epoch, unsigned *timeout_flag) {
+    int s = threadIdx.x;
+    if (s < world) {
+        volatile unsigned *f = flags + row * 8 + s;
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while ((int)(*f - epoch) < 0) {
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 20000000000ULL) {  // 20 s: a peer died; do not hang the device
+                *timeout_flag = 1;
+                break;
+            }
+        }
+    }
+    __threadfence_system();
+}
+
+int comm_signal_peers(unsigned *const *peer_flags, int row, int rank, int world, unsigned epoch, cudaStream_t st) {
+    PeerPtrs pp{};
+    for (int s = 0; s < world; s++) pp.p[s] = peer_flags[s];
+    signal_peers_kernel<<<1, 32, 0, st>>>(pp, row, rank, world, epoch);
+    INSB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int comm_wait_flags(unsigned *my_flags, int row, int world, unsigned epoch, unsigned *timeout_flag, cudaStream_t st) {
+    wait_flags_kernel<<<1, 32, 0, st>>>(my_flags, row, world, epoch, timeout_flag);
+    INSB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace insb

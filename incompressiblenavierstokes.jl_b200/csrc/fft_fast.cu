@@ -282,10 +282,20 @@ __global__ void __launch_bounds__(StridedShape<T, N>::NT, (sizeof(T) == 4 && Str
     if (MODE >= 1) fft_stages<T, N, true, 0, L>(v, t, sm, tw, exch);
     if (BLK) {
         const int out_mask = (1 << g.out_sh) - 1;
+        if (g.use_outp) {  // tile-by-tile stores straight into the peers' buffers (NVLink P2P)
+            const long long orel = kx + other * out_os;
 #pragma unroll
-        for (int m = 0; m < 8; m++) {
-            int k = t + P * m;
-            obase[(long long)(k >> g.out_sh) * g.out_blk + (long long)(k & out_mask) * out_sd] = v[m];
+            for (int m = 0; m < 8; m++) {
+                int k = t + P * m;
+                Cx<T> *dst = reinterpret_cast<Cx<T> *>(g.outp[k >> g.out_sh]);
+                dst[orel + (long long)(k & out_mask) * out_sd] = v[m];
+            }
+        } else {
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                int k = t + P * m;
+                obase[(long long)(k >> g.out_sh) * g.out_blk + (long long)(k & out_mask) * out_sd] = v[m];
+            }
         }
     } else {
         Cx<T> *op = obase + t * out_sd;
@@ -416,7 +426,7 @@ static int fast_pass_n(int kind, T *R, Cx<T> *W, const FastGeom &g, int tdim, co
             set_error("fast FFT pass: padded half-spectrum extent must be a multiple of the line tile");
             return 1;
         }
-        const bool blk = g.in_sh < 30 || g.out_sh < 30;
+        const bool blk = g.in_sh < 30 || g.out_sh < 30 || g.use_outp;
         dim3 grid(g.m0p / SS::L, g.D == 3 ? (g.nother >= 0 ? g.nother : g.n[tdim == 1 ? 2 : 1]) : 1);
         auto kern = kind == 0 ? (blk ? fft_strided_kernel<T, N, 0, true> : fft_strided_kernel<T, N, 0, false>)
                     : kind == 1 ? (blk ? fft_strided_kernel<T, N, 1, true> : fft_strided_kernel<T, N, 1, false>)

@@ -21,6 +21,11 @@ struct FastGeom {
     int in_sh = 30, out_sh = 30;
     int nother = -1;   // extent of the companion index; -1 = n[other dim]
     int eig_off = 0;   // added to `other` for the eigenvalue lookup (ky offset of this rank)
+    // Direct peer stores (slab-decomposed solve over NVLink P2P): when use_outp is set, block
+    // (k >> out_sh) of the output goes to outp[k >> out_sh] (a peer-mapped buffer, already offset
+    // to this rank's block there) instead of out + (k >> out_sh) * out_blk.
+    int use_outp = 0;
+    void *outp[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 bool fast_fft_supported(int n);

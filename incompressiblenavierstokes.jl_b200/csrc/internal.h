@@ -65,6 +65,11 @@ int comm_halo_z(Comm *c, void *field, size_t esz, long long plane, int nplanes, 
                 cudaStream_t st);
 int comm_all_to_all(Comm *c, const void *send, void *recv, size_t block_bytes, cudaStream_t st);
 int comm_reduce_scratch(Comm *c, double *scratch, bool is_min, cudaStream_t st);
+// cross-process flags in peer-mapped memory: every rank stores `epoch` into slot `rank` of the
+// flag row `row` of all ranks (after everything enqueued before on `st`), resp. waits until all
+// slots of its own row hold a value >= epoch.
+int comm_signal_peers(unsigned *const *peer_flags, int row, int rank, int world, unsigned epoch, cudaStream_t st);
+int comm_wait_flags(unsigned *my_flags, int row, int world, unsigned epoch, unsigned *timeout_flag, cudaStream_t st);
 
 // Boundary description used by the ghost-fill kernels.
 struct BcDesc {
@@ -108,9 +113,30 @@ struct StageArgs {
     int add_to_k;    // k_out += instead of = (convection!/diffusion! add semantics)
 };
 
+// Optional device-timing hook (CUDA events on the launching stream, see insb200_profile_*).
+struct Profiler {
+    virtual void begin(int group, cudaStream_t st) = 0;
+    virtual void end(int group, cudaStream_t st) = 0;
+    virtual ~Profiler() {}
+};
+constexpr int NPROF = 12;  // 0 rhs+combine 1 divergence 2 poisson 3 project 4 bc 5 x_r2c 6 y_fwd 7 transpose_fwd
+                           // 8 z_mid 9 transpose_bwd 10 y_inv 11 x_c2r
+
 struct Launch {
     cudaStream_t stream;
     long long *counter;
+    Profiler *prof = nullptr;
+};
+
+struct ProfScope {
+    const Launch &L;
+    int group;
+    ProfScope(const Launch &l, int g) : L(l), group(g) {
+        if (L.prof) L.prof->begin(group, L.stream);
+    }
+    ~ProfScope() {
+        if (L.prof) L.prof->end(group, L.stream);
+    }
 };
 
 // ---- stencil.cu ----
@@ -142,5 +168,9 @@ int poisson_create(const insb200_setup_t &s, const int Ip[3][2], int kind, Comm 
 void poisson_destroy(Poisson *p);
 long long poisson_bytes(const Poisson *p);
 int poisson_solve(Poisson *ps, void *p_ghosted, Launch L);
+// direct peer-store transposes: export this rank's IPC handles / import everybody's
+constexpr int POISSON_IPC_BYTES = 192;
+int poisson_ipc_export(Poisson *ps, void *blob);
+int poisson_ipc_import(Poisson *ps, const void *blobs);
 
 }  // namespace insb

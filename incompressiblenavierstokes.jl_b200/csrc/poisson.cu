@@ -420,6 +420,15 @@ struct Poisson {
     Comm *comm = nullptr;
     int nzl = 0, kyl = 0;
     void *S = nullptr, *Rv = nullptr;
+    // direct peer-store transposes (NVLink P2P through CUDA IPC): peers' S / Rv / flag buffers
+    // mapped into this process; flags = 3 rows x 8 slots (row 0: forward transpose done,
+    // row 1: backward transpose done, row 2: wait time-out marker)
+    bool p2p = false;
+    unsigned *flags = nullptr;
+    void *peerS[8] = {}, *peerRv[8] = {};
+    unsigned *peerFlags[8] = {};
+    unsigned epoch = 0;
+    size_t wbytes = 0;
 };
 
 static bool factorize(int n, std::vector<int> &rad) {
@@ -671,6 +680,11 @@ int poisson_create(const insb200_setup_t &s, const int Ip[3][2], int kind, Comm 
         cudaMemset(ps->S, 0, wbytes);
         cudaMemset(ps->Rv, 0, wbytes);
         ps->bytes += 2 * (long long)wbytes;
+        ps->wbytes = wbytes;
+        if (cudaMalloc((void **)&ps->flags, 3 * 8 * sizeof(unsigned)) != cudaSuccess)
+            return fail("cudaMalloc of the peer flags failed");
+        ps->owned.push_back(ps->flags);
+        cudaMemset(ps->flags, 0, 3 * 8 * sizeof(unsigned));
     }
     int r = ps->f64 ? build_tables<double>(ps, s, Ip) : build_tables<float>(ps, s, Ip);
     if (r) {
@@ -723,12 +737,66 @@ int poisson_create(const insb200_setup_t &s, const int Ip[3][2], int kind, Comm 
 
 void poisson_destroy(Poisson *p) {
     if (!p) return;
+    if (p->p2p) {
+        const int rank = comm_rank(p->comm), world = comm_world(p->comm);
+        for (int s = 0; s < world; s++) {
+            if (s == rank) continue;
+            if (p->peerS[s]) cudaIpcCloseMemHandle(p->peerS[s]);
+            if (p->peerRv[s]) cudaIpcCloseMemHandle(p->peerRv[s]);
+            if (p->peerFlags[s]) cudaIpcCloseMemHandle(p->peerFlags[s]);
+        }
+    }
     for (void *q : p->owned) cudaFree(q);
     if (p->W) cudaFree(p->W);
     delete p;
 }
 
 long long poisson_bytes(const Poisson *p) { return p ? p->bytes : 0; }
+
+int poisson_ipc_export(Poisson *ps, void *blob) {
+    if (!ps || !ps->comm) {
+        set_error("ipc export: the plan is not slab-decomposed");
+        return 1;
+    }
+    cudaIpcMemHandle_t h[3];
+    INSB_CUDA(cudaIpcGetMemHandle(&h[0], ps->S));
+    INSB_CUDA(cudaIpcGetMemHandle(&h[1], ps->Rv));
+    INSB_CUDA(cudaIpcGetMemHandle(&h[2], ps->flags));
+    static_assert(sizeof(h) == POISSON_IPC_BYTES, "blob size");
+    std::memcpy(blob, h, sizeof(h));
+    return 0;
+}
+
+int poisson_ipc_import(Poisson *ps, const void *blobs) {
+    if (!ps || !ps->comm) {
+        set_error("ipc import: the plan is not slab-decomposed");
+        return 1;
+    }
+    const int rank = comm_rank(ps->comm), world = comm_world(ps->comm);
+    if (world > 8) {
+        set_error("ipc import: at most 8 ranks");
+        return 1;
+    }
+    if ((ps->nzl & (ps->nzl - 1)) != 0) {
+        set_error("ipc import: planes per rank must be a power of two");
+        return 1;
+    }
+    for (int s = 0; s < world; s++) {
+        if (s == rank) {
+            ps->peerS[s] = ps->S;
+            ps->peerRv[s] = ps->Rv;
+            ps->peerFlags[s] = ps->flags;
+            continue;
+        }
+        cudaIpcMemHandle_t h[3];
+        std::memcpy(h, (const char *)blobs + (size_t)s * POISSON_IPC_BYTES, sizeof(h));
+        INSB_CUDA(cudaIpcOpenMemHandle(&ps->peerS[s], h[0], cudaIpcMemLazyEnablePeerAccess));
+        INSB_CUDA(cudaIpcOpenMemHandle(&ps->peerRv[s], h[1], cudaIpcMemLazyEnablePeerAccess));
+        INSB_CUDA(cudaIpcOpenMemHandle((void **)&ps->peerFlags[s], h[2], cudaIpcMemLazyEnablePeerAccess));
+    }
+    ps->p2p = true;
+    return 0;
+}
 
 template <typename T>
 static int solve_t(Poisson *ps, T *p, Launch L) {
@@ -758,7 +826,10 @@ static int solve_t(Poisson *ps, T *p, Launch L) {
             while ((1 << sh) < kyl) sh++;
             FastGeom gx = g;  // x passes see only the local planes
             gx.n[2] = nzl;
-            INSB_TRY(fast_pass<T>(3, ps->n[0], R, ps->W, gx, 0, ps->tw[0], e0, e1, e2, factor, tl, L));
+            {
+                ProfScope sc(L, 5);
+                INSB_TRY(fast_pass<T>(3, ps->n[0], R, ps->W, gx, 0, ps->tw[0], e0, e1, e2, factor, tl, L));
+            }
             FastGeom gy = g;  // y forward: W (natural) -> S (blocked by destination rank)
             gy.nother = nzl;
             gy.in = ps->W;
@@ -767,8 +838,24 @@ static int solve_t(Poisson *ps, T *p, Launch L) {
             gy.out_os = m0p * kyl;
             gy.out_sh = sh;
             gy.out_blk = blk;
-            INSB_TRY(fast_pass<T>(0, ps->n[1], R, ps->W, gy, 1, ps->tw[1], e0, e1, e2, factor, tl, L));
-            INSB_TRY(comm_all_to_all(ps->comm, ps->S, ps->Rv, (size_t)blk * sizeof(Cx<T>), L.stream));
+            if (ps->p2p) {  // store every destination's block straight into its Rv
+                ps->epoch++;
+                gy.use_outp = 1;
+                for (int s2 = 0; s2 < world; s2++) gy.outp[s2] = (Cx<T> *)ps->peerRv[s2] + (long long)rank * blk;
+            }
+            {
+                ProfScope sc(L, 6);
+                INSB_TRY(fast_pass<T>(0, ps->n[1], R, ps->W, gy, 1, ps->tw[1], e0, e1, e2, factor, tl, L));
+            }
+            {
+                ProfScope sc(L, 7);
+                if (ps->p2p) {
+                    INSB_TRY(comm_signal_peers(ps->peerFlags, 0, rank, world, ps->epoch, L.stream));
+                    INSB_TRY(comm_wait_flags(ps->flags, 0, world, ps->epoch, ps->flags + 16, L.stream));
+                } else {
+                    INSB_TRY(comm_all_to_all(ps->comm, ps->S, ps->Rv, (size_t)blk * sizeof(Cx<T>), L.stream));
+                }
+            }
             FastGeom gz = g;  // z: in place on Rv = [n3][kyl][m0p]
             gz.nother = kyl;
             gz.in = ps->Rv;
@@ -776,8 +863,26 @@ static int solve_t(Poisson *ps, T *p, Launch L) {
             gz.in_sd = gz.out_sd = m0p * kyl;
             gz.in_os = gz.out_os = m0p;
             gz.eig_off = rank * kyl;
-            INSB_TRY(fast_pass<T>(2, ps->n[2], R, ps->W, gz, 2, ps->tw[2], e0, e1, e2, factor, tl, L));
-            INSB_TRY(comm_all_to_all(ps->comm, ps->Rv, ps->S, (size_t)blk * sizeof(Cx<T>), L.stream));
+            if (ps->p2p) {  // z index k -> owner k / nzl, whose S holds [source rank][z local][ky local][kx]
+                int shz = 0;
+                while ((1 << shz) < nzl) shz++;
+                gz.use_outp = 1;
+                gz.out_sh = shz;
+                for (int s2 = 0; s2 < world; s2++) gz.outp[s2] = (Cx<T> *)ps->peerS[s2] + (long long)rank * blk;
+            }
+            {
+                ProfScope sc(L, 8);
+                INSB_TRY(fast_pass<T>(2, ps->n[2], R, ps->W, gz, 2, ps->tw[2], e0, e1, e2, factor, tl, L));
+            }
+            {
+                ProfScope sc(L, 9);
+                if (ps->p2p) {
+                    INSB_TRY(comm_signal_peers(ps->peerFlags, 1, rank, world, ps->epoch, L.stream));
+                    INSB_TRY(comm_wait_flags(ps->flags, 1, world, ps->epoch, ps->flags + 16, L.stream));
+                } else {
+                    INSB_TRY(comm_all_to_all(ps->comm, ps->Rv, ps->S, (size_t)blk * sizeof(Cx<T>), L.stream));
+                }
+            }
             FastGeom gi = g;  // y inverse: S (blocked by source rank) -> W (natural)
             gi.nother = nzl;
             gi.in = ps->S;
@@ -786,20 +891,41 @@ static int solve_t(Poisson *ps, T *p, Launch L) {
             gi.in_os = m0p * kyl;
             gi.in_sh = sh;
             gi.in_blk = blk;
-            INSB_TRY(fast_pass<T>(1, ps->n[1], R, ps->W, gi, 1, ps->tw[1], e0, e1, e2, factor, tl, L));
-            INSB_TRY(fast_pass<T>(4, ps->n[0], R, ps->W, gx, 0, ps->tw[0], e0, e1, e2, factor, tl, L));
-            (void)world;
+            {
+                ProfScope sc(L, 10);
+                INSB_TRY(fast_pass<T>(1, ps->n[1], R, ps->W, gi, 1, ps->tw[1], e0, e1, e2, factor, tl, L));
+            }
+            {
+                ProfScope sc(L, 11);
+                INSB_TRY(fast_pass<T>(4, ps->n[0], R, ps->W, gx, 0, ps->tw[0], e0, e1, e2, factor, tl, L));
+            }
             return 0;
         }
-        INSB_TRY(fast_pass<T>(3, ps->n[0], R, ps->W, g, 0, ps->tw[0], e0, e1, e2, factor, tl, L));
+        {
+            ProfScope sc(L, 5);
+            INSB_TRY(fast_pass<T>(3, ps->n[0], R, ps->W, g, 0, ps->tw[0], e0, e1, e2, factor, tl, L));
+        }
         if (D == 3) {
-            INSB_TRY(fast_pass<T>(0, ps->n[1], R, ps->W, g, 1, ps->tw[1], e0, e1, e2, factor, tl, L));
-            INSB_TRY(fast_pass<T>(2, ps->n[2], R, ps->W, g, 2, ps->tw[2], e0, e1, e2, factor, tl, L));
-            INSB_TRY(fast_pass<T>(1, ps->n[1], R, ps->W, g, 1, ps->tw[1], e0, e1, e2, factor, tl, L));
+            {
+                ProfScope sc(L, 6);
+                INSB_TRY(fast_pass<T>(0, ps->n[1], R, ps->W, g, 1, ps->tw[1], e0, e1, e2, factor, tl, L));
+            }
+            {
+                ProfScope sc(L, 8);
+                INSB_TRY(fast_pass<T>(2, ps->n[2], R, ps->W, g, 2, ps->tw[2], e0, e1, e2, factor, tl, L));
+            }
+            {
+                ProfScope sc(L, 10);
+                INSB_TRY(fast_pass<T>(1, ps->n[1], R, ps->W, g, 1, ps->tw[1], e0, e1, e2, factor, tl, L));
+            }
         } else {
+            ProfScope sc(L, 8);
             INSB_TRY(fast_pass<T>(2, ps->n[1], R, ps->W, g, 1, ps->tw[1], e0, e1, e2, factor, tl, L));
         }
-        INSB_TRY(fast_pass<T>(4, ps->n[0], R, ps->W, g, 0, ps->tw[0], e0, e1, e2, factor, tl, L));
+        {
+            ProfScope sc(L, 11);
+            INSB_TRY(fast_pass<T>(4, ps->n[0], R, ps->W, g, 0, ps->tw[0], e0, e1, e2, factor, tl, L));
+        }
         return 0;
     }
     static bool attr_set[2] = {false, false};

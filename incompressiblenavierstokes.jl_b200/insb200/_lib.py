@@ -61,6 +61,8 @@ _PROTOTYPES = {
     "insb200_plan_destroy": (C.c_int, [_P]),
     "insb200_comm_unique_id": (C.c_int, [_P]),
     "insb200_plan_local_n": (C.c_int, [_P, C.POINTER(C.c_int)]),
+    "insb200_plan_ipc_export": (C.c_int, [_P, _P]),
+    "insb200_plan_ipc_import": (C.c_int, [_P, _P]),
     "insb200_plan_psolver": (C.c_int, [_P]),
     "insb200_plan_workspace_bytes": (C.c_longlong, [_P]),
     "insb200_apply_bc_u": (C.c_int, [_P, _P, C.c_double, C.c_int, _P]),
@@ -93,6 +95,7 @@ _PROTOTYPES = {
     "insb200_launch_count": (C.c_longlong, [_P]),
     "insb200_profile_enable": (C.c_int, [_P, C.c_int]),
     "insb200_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    "insb200_profile_read_ex": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)

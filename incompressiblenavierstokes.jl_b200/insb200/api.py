@@ -17,6 +17,7 @@ streams; all arithmetic happens in the CUDA library.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import time
 from fractions import Fraction
 
@@ -85,6 +86,22 @@ class Plan:
         check(lib().insb200_plan_create(C.byref(s), C.byref(h)))
         self.h = h
         self.psolver = lib().insb200_plan_psolver(h)
+        self.p2p = False
+        if setup.world > 1 and self.psolver != _lib.PSOLVER_NONE and not os.environ.get("INSB200_NO_P2P"):
+            self._enable_p2p()
+
+    def _enable_p2p(self):
+        """Direct peer-store FFT transposes: gather everybody's CUDA IPC handles through the
+        torch.distributed group (insb200_plan_ipc_export / _import)."""
+        import torch.distributed as dist
+
+        blob = C.create_string_buffer(192)
+        check(lib().insb200_plan_ipc_export(self.h, C.cast(blob, C.c_void_p)))
+        blobs = [None] * self.setup.world
+        dist.all_gather_object(blobs, blob.raw)
+        allb = C.create_string_buffer(b"".join(blobs), 192 * self.setup.world)
+        check(lib().insb200_plan_ipc_import(self.h, C.cast(allb, C.c_void_p)))
+        self.p2p = True
 
     def __del__(self):
         try:
@@ -106,10 +123,11 @@ class Plan:
         check(lib().insb200_profile_enable(self.h, int(on)))
 
     def profile_read(self):
-        ms = (C.c_double * 5)()
-        cnt = (C.c_longlong * 5)()
-        check(lib().insb200_profile_read(self.h, ms, cnt))
-        names = ("rhs_combine", "divergence", "poisson", "project", "bc")
+        ms = (C.c_double * 12)()
+        cnt = (C.c_longlong * 12)()
+        check(lib().insb200_profile_read_ex(self.h, 12, ms, cnt))
+        names = ("rhs_combine", "divergence", "poisson", "project", "bc", "fft_x_r2c", "fft_y_fwd", "transpose_fwd",
+                 "fft_z_mid", "transpose_bwd", "fft_y_inv", "fft_x_c2r")
         return {n: (ms[i], cnt[i]) for i, n in enumerate(names)}
 
 
