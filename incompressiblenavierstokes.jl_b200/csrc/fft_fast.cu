@@ -209,7 +209,7 @@ __device__ __forceinline__ void fft_stages(Cx<T> (&v)[8], int t, const LineSmem<
 template <typename T, int N>
 struct StridedShape {
     static constexpr int P = FftShape<N>::P;
-    static constexpr int L = sizeof(T) == 4 ? (N <= 512 ? 8 : 4) : (N <= 1024 ? 4 : 2);
+    static constexpr int L = sizeof(T) == 4 ? (N <= 1024 ? 8 : 4) : (N <= 1024 ? 4 : 2);
     static constexpr int NT = L * P;
     static constexpr int BUF = sp(N - 1) + 1;  // complex elements per line and buffer
     static constexpr size_t smem = (size_t)2 * L * BUF * sizeof(Cx<T>);
