@@ -37,8 +37,13 @@ struct FftShape {
     }
 };
 
-// padded shared-memory position of element p of a line
-__host__ __device__ __forceinline__ constexpr int sp(int p) { return p + (p >> 3); }
+// padded shared-memory position of element p of a line: one pad element per 2^SH elements.
+// SH = 3 is conflict-free when lanes run over lines (strided passes) and for 16-byte elements;
+// 8-byte elements with lanes running along the line (x passes, Float32) want SH = 4
+// (simulated bank conflicts per access 1.25 instead of 1.5-1.8).
+template <int SH>
+__host__ __device__ __forceinline__ constexpr int spx(int p) { return p + (p >> SH); }
+__host__ __device__ __forceinline__ constexpr int sp(int p) { return spx<3>(p); }
 
 // ----------------------------------------------------------------------------------------
 // complex arithmetic: generic (double) and packed (float)
@@ -130,7 +135,7 @@ struct LineSmem {
     Cx<T> *buf[2];
 };
 
-template <typename T, int N, bool INV, int S, int ES>
+template <typename T, int N, bool INV, int S, int ES, int SH = 3>
 __device__ __forceinline__ void fft_stages(Cx<T> (&v)[8], int t, const LineSmem<T> &sm,
                                            const Cx<T> *__restrict__ tw, int &exch) {
     typedef Ops<T> O;
@@ -179,28 +184,29 @@ __device__ __forceinline__ void fft_stages(Cx<T> (&v)[8], int t, const LineSmem<
         for (int b = 0; b < B; b++) {
             int j = t + P * b;
             int j0 = (j / NS) * (NS * R) + (j & (NS - 1));
-            if constexpr (NS % 8 == 0 || (NS == 1 && R == 8)) {
-                // sp(j0 + r NS) = sp(j0) + r (NS + NS/8)   (r < 8 when NS == 1, j0 a multiple of 8)
-                constexpr int DS = NS == 1 ? 1 : NS + NS / 8;
-                Cx<T> *w = buf + sp(j0) * ES;
+            constexpr int PADN = 1 << SH;
+            if constexpr (NS % PADN == 0 || (NS == 1 && R == 8)) {
+                // sp(j0 + r NS) = sp(j0) + r (NS + NS/PADN)   (r < 8 when NS == 1, j0 a multiple of 8)
+                constexpr int DS = NS == 1 ? 1 : NS + NS / PADN;
+                Cx<T> *w = buf + spx<SH>(j0) * ES;
 #pragma unroll
                 for (int r = 0; r < R; r++) w[r * DS * ES] = v[b + B * r];
             } else {
 #pragma unroll
-                for (int r = 0; r < R; r++) buf[sp(j0 + r * NS) * ES] = v[b + B * r];
+                for (int r = 0; r < R; r++) buf[spx<SH>(j0 + r * NS) * ES] = v[b + B * r];
             }
         }
         __syncthreads();
-        if constexpr (P % 8 == 0) {
-            const Cx<T> *rd = buf + sp(t) * ES;
+        if constexpr (P % (1 << SH) == 0) {
+            const Cx<T> *rd = buf + spx<SH>(t) * ES;
 #pragma unroll
-            for (int m = 0; m < 8; m++) v[m] = rd[m * (P + P / 8) * ES];
+            for (int m = 0; m < 8; m++) v[m] = rd[m * (P + P / (1 << SH)) * ES];
         } else {
 #pragma unroll
-            for (int m = 0; m < 8; m++) v[m] = buf[sp(t + P * m) * ES];
+            for (int m = 0; m < 8; m++) v[m] = buf[spx<SH>(t + P * m) * ES];
         }
         exch++;
-        fft_stages<T, N, INV, S + 1, ES>(v, t, sm, tw, exch);
+        fft_stages<T, N, INV, S + 1, ES, SH>(v, t, sm, tw, exch);
     }
 }
 
@@ -306,6 +312,114 @@ __global__ void __launch_bounds__(StridedShape<T, N>::NT, (sizeof(T) == 4 && Str
 }
 
 // ----------------------------------------------------------------------------------------
+// strided DCT pass along dim `tdim` for psolver_transform (pressure.jl:255-317): orthonormal
+// DCT-II / DCT-III of the real and imaginary parts of every line through ONE complex FFT of the
+// same length (the even/odd permutation + twiddle construction of manual_dct!/manual_idct!,
+// src/utils.jl:89-155).  MODE 0 forward, 1 inverse, 2 forward + eigenvalue divide + inverse.
+// ----------------------------------------------------------------------------------------
+// v[m] <-> element k = t + P m; returns in vr[m] element (N - k) mod N
+template <typename T, int N, int ES>
+__device__ __forceinline__ void exchange_rev(const Cx<T> (&v)[8], Cx<T> (&vr)[8], int t, const LineSmem<T> &sm,
+                                             int &exch) {
+    constexpr int P = FftShape<N>::P;
+    Cx<T> *buf = sm.buf[exch & 1];
+#pragma unroll
+    for (int m = 0; m < 8; m++) buf[sp(t + P * m) * ES] = v[m];
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < 8; m++) vr[m] = buf[sp((N - (t + P * m)) & (N - 1)) * ES];
+    exch++;
+}
+
+template <typename T, int N, int MODE>
+__global__ void __launch_bounds__(StridedShape<T, N>::NT, (sizeof(T) == 4 && StridedShape<T, N>::NT <= 512) ? 2 : 1)
+    fft_strided_dct_kernel(Cx<T> *__restrict__ W, FastGeom g, int tdim, const Cx<T> *__restrict__ tw,
+                           const T *__restrict__ e0, const T *__restrict__ e1, const T *__restrict__ e2, T factor) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    typedef StridedShape<T, N> SS;
+    constexpr int P = SS::P, L = SS::L;
+    const int l = threadIdx.x % L, t = threadIdx.x / L;
+    const int kx = blockIdx.x * L + l;
+    const int other = blockIdx.y;
+    const int odim = tdim == 1 ? 2 : 1;
+    const long long sd = g.ws[tdim];
+    Cx<T> *base = W + kx + (g.D == 3 ? other * g.ws[odim] : 0);
+    const Cx<T> *dw = (const Cx<T> *)g.dw, *dwi = (const Cx<T> *)g.dwi;
+    LineSmem<T> sm;
+    sm.buf[0] = reinterpret_cast<Cx<T> *>(smem_raw) + l;
+    sm.buf[1] = sm.buf[0] + L * SS::BUF;
+    Cx<T> v[8], vr[8];
+    // position in the line of element p of the FFT sequence: z[p] = x[2p], z[N-1-p] = x[2p+1]
+    auto perm = [](int p) { return p < N / 2 ? 2 * p : 2 * (N - 1 - p) + 1; };
+    if (MODE == 1) {
+#pragma unroll
+        for (int m = 0; m < 8; m++) v[m] = base[(long long)(t + P * m) * sd];
+    } else {
+#pragma unroll
+        for (int m = 0; m < 8; m++) v[m] = base[(long long)perm(t + P * m) * sd];
+    }
+    T f[8];
+    if (MODE == 2) {
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            int k = t + P * m;
+            T den;
+            bool zero;
+            if (g.D == 3) {
+                int k1 = tdim == 1 ? k : other, k2 = tdim == 1 ? other : k;
+                den = (e0[kx] + e1[k1]) + e2[k2];
+                zero = (kx | k1 | k2) == 0;
+            } else {
+                den = e0[kx] + e1[k];
+                zero = (kx | k) == 0;
+            }
+            f[m] = zero ? T(0) : factor / den;
+        }
+    }
+    int exch = 0;
+    if (MODE != 1) {  // DCT-II: FFT, then X_k = 2 Re(w_k F_k) for the real and the imaginary sequence
+        fft_stages<T, N, false, 0, L>(v, t, sm, tw, exch);
+        exchange_rev<T, N, L>(v, vr, t, sm, exch);
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            const Cx<T> zk = v[m], zc = cconj(vr[m]), wk = dw[t + P * m];
+            const Cx<T> fa{(zk.x + zc.x) * T(0.5), (zk.y + zc.y) * T(0.5)};
+            const Cx<T> d{(zk.x - zc.x) * T(0.5), (zk.y - zc.y) * T(0.5)};
+            const Cx<T> fb{d.y, -d.x};
+            v[m] = Cx<T>{T(2) * (wk.x * fa.x - wk.y * fa.y), T(2) * (wk.x * fb.x - wk.y * fb.y)};
+        }
+    }
+    if (MODE == 2) {
+#pragma unroll
+        for (int m = 0; m < 8; m++) v[m] = Ops<T>::scale(v[m], f[m]);
+    }
+    if (MODE >= 1) {  // DCT-III: H_k from X_k and X_{N-k}, inverse FFT, 1/N, undo the permutation
+        exchange_rev<T, N, L>(v, vr, t, sm, exch);
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            const int k = t + P * m;
+            const Cx<T> xk = v[m], xm = vr[m];
+            if (k == 0) {
+                const T w0 = dwi[0].x;
+                v[m] = Cx<T>{w0 * xk.x, w0 * xk.y};
+            } else {
+                const Cx<T> wk = dwi[k], wm = cconj(dwi[N - k]);
+                const Cx<T> ha{(wk.x * xk.x + wm.x * xm.x) * T(0.5), (wk.y * xk.x + wm.y * xm.x) * T(0.5)};
+                const Cx<T> hb{(wk.x * xk.y + wm.x * xm.y) * T(0.5), (wk.y * xk.y + wm.y * xm.y) * T(0.5)};
+                v[m] = Cx<T>{ha.x - hb.y, ha.y + hb.x};
+            }
+        }
+        fft_stages<T, N, true, 0, L>(v, t, sm, tw, exch);
+        const T invn = T(1) / T(N);
+#pragma unroll
+        for (int m = 0; m < 8; m++) base[(long long)perm(t + P * m) * sd] = Ops<T>::scale(v[m], invn);
+    } else {
+#pragma unroll
+        for (int m = 0; m < 8; m++) base[(long long)(t + P * m) * sd] = v[m];
+    }
+}
+
+// ----------------------------------------------------------------------------------------
 // x pass, real -> half spectrum: rows (2q, 2q+1) along y are transformed as one complex line
 // ----------------------------------------------------------------------------------------
 template <typename T, int N>
@@ -313,7 +427,8 @@ struct XShape {
     static constexpr int P = FftShape<N>::P;
     static constexpr int LP = P >= 256 ? 1 : 256 / P;  // row pairs per block
     static constexpr int NT = LP * P;
-    static constexpr int BUF = (sp(N - 1) + 1 + 3) / 4 * 4 + 2;  // line stride: staggers lines over the banks
+    static constexpr int SH = sizeof(T) == 4 ? 4 : 3;
+    static constexpr int BUF = (spx<SH>(N - 1) + 1 + 3) / 4 * 4 + 2;  // line stride: staggers lines over the banks
     static constexpr size_t smem = (size_t)2 * LP * BUF * sizeof(Cx<T>);
 };
 
@@ -336,14 +451,21 @@ __global__ void __launch_bounds__(XShape<T, N>::NT)
     sm.buf[0] = reinterpret_cast<Cx<T> *>(smem_raw) + lp * XS::BUF;
     sm.buf[1] = sm.buf[0] + LP * XS::BUF;
     Cx<T> v[8];
+    T fa = T(1), fb = T(1);
+    if (g.pre) {
+        const T *pre = (const T *)g.pre;
+        fa = g.pre_dim == 1 ? pre[2 * jp] : pre[kz];
+        fb = g.pre_dim == 1 ? pre[2 * jp + 1] : pre[kz];
+    }
 #pragma unroll
-    for (int m = 0; m < 8; m++) v[m] = Cx<T>{ra[t + P * m], rb[t + P * m]};
+    for (int m = 0; m < 8; m++) v[m] = Cx<T>{ra[t + P * m] * fa, rb[t + P * m] * fb};
     int exch = 0;
-    fft_stages<T, N, false, 0, 1>(v, t, sm, tw, exch);
+    constexpr int SH = XS::SH;
+    fft_stages<T, N, false, 0, 1, SH>(v, t, sm, tw, exch);
     // exchange once more to reach Z[N-k]
     Cx<T> *buf = sm.buf[exch & 1];
 #pragma unroll
-    for (int m = 0; m < 8; m++) buf[sp(t + P * m)] = v[m];
+    for (int m = 0; m < 8; m++) buf[spx<SH>(t + P * m)] = v[m];
     __syncthreads();
     Cx<T> *wa = W + (long long)(2 * jp) * g.ws[1] + (long long)kz * g.ws[2];
     Cx<T> *wb = wa + g.ws[1];
@@ -352,8 +474,8 @@ __global__ void __launch_bounds__(XShape<T, N>::NT)
         for (int m = 0; m < 5; m++) {
             int k = t + P * m;
             if (m == 4 && t != 0) break;  // k = N/2 is handled by t = 0
-            Cx<T> zk = m < 4 ? v[m] : buf[sp(k)];
-            Cx<T> zc = cconj(buf[sp((N - k) & (N - 1))]);  // conj(Z[N-k])
+            Cx<T> zk = m < 4 ? v[m] : buf[spx<SH>(k)];
+            Cx<T> zc = cconj(buf[spx<SH>((N - k) & (N - 1))]);  // conj(Z[N-k])
             Cx<T> A = Ops<T>::scale(Ops<T>::add(zk, zc), T(0.5));
             Cx<T> d = Ops<T>::scale(Ops<T>::sub(zk, zc), T(0.5));
             wa[k] = A;
@@ -396,7 +518,7 @@ __global__ void __launch_bounds__(XShape<T, N>::NT)
         }
     }
     int exch = 0;
-    fft_stages<T, N, true, 0, 1>(v, t, sm, tw, exch);
+    fft_stages<T, N, true, 0, 1, XS::SH>(v, t, sm, tw, exch);
     if (valid) {
         T *ra = R + (long long)(2 * jp) * g.rs[1] + (long long)kz * g.rs[2];
         T *rb = ra + g.rs[1];
@@ -433,6 +555,17 @@ static int fast_pass_n(int kind, T *R, Cx<T> *W, const FastGeom &g, int tdim, co
                                 : (blk ? fft_strided_kernel<T, N, 2, true> : fft_strided_kernel<T, N, 2, false>);
         INSB_TRY(allow_smem(kern, SS::smem));
         kern<<<grid, SS::NT, SS::smem, L.stream>>>(W, g, tdim, tw, e0, e1, e2, factor);
+    } else if (kind >= 5) {  // strided DCT
+        typedef StridedShape<T, N> SS;
+        if (g.m0p % SS::L || !g.dw || !g.dwi) {
+            set_error("fast DCT pass: bad geometry");
+            return 1;
+        }
+        dim3 grid(g.m0p / SS::L, g.D == 3 ? g.n[tdim == 1 ? 2 : 1] : 1);
+        auto kern = kind == 5 ? fft_strided_dct_kernel<T, N, 0> : kind == 6 ? fft_strided_dct_kernel<T, N, 1>
+                                                                           : fft_strided_dct_kernel<T, N, 2>;
+        INSB_TRY(allow_smem(kern, SS::smem));
+        kern<<<grid, SS::NT, SS::smem, L.stream>>>(W, g, tdim, tw, e0, e1, e2, factor);
     } else {
         typedef XShape<T, N> XS;
         long long npairs = (long long)(g.n[1] / 2) * (g.D == 3 ? g.n[2] : 1);
@@ -450,7 +583,7 @@ static int fast_pass_n(int kind, T *R, Cx<T> *W, const FastGeom &g, int tdim, co
     return 0;
 }
 
-// kind: 0 strided fwd, 1 strided inv, 2 strided mid, 3 x r2c, 4 x c2r
+// kind: 0 strided fwd, 1 strided inv, 2 strided mid, 3 x r2c, 4 x c2r, 5/6/7 strided DCT fwd/inv/mid
 template <typename T>
 int fast_pass(int kind, int N, T *R, void *W, const FastGeom &g, int tdim, const void *tw, const T *e0,
               const T *e1, const T *e2, T factor, int tile, Launch L) {

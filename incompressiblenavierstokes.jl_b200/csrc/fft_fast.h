@@ -24,6 +24,12 @@ struct FastGeom {
     // Direct peer stores (slab-decomposed solve over NVLink P2P): when use_outp is set, block
     // (k >> out_sh) of the output goes to outp[k >> out_sh] (a peer-mapped buffer, already offset
     // to this rank's block there) instead of out + (k >> out_sh) * out_blk.
+    // x R2C pass only: optional factor per row applied on load (the 1/Ω of psolver_tridiagonal,
+    // pressure.jl:463-465), indexed by the row's index along dimension pre_dim (1 or 2)
+    const void *pre = nullptr;
+    int pre_dim = 1;
+    // DCT passes (kinds 5-7): twiddles w_k and winv_k of manual_dct_stuff (src/utils.jl:65-87)
+    const void *dw = nullptr, *dwi = nullptr;
     int use_outp = 0;
     void *outp[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
@@ -31,7 +37,8 @@ struct FastGeom {
 bool fast_fft_supported(int n);
 
 // kind: 0 strided forward, 1 strided inverse, 2 strided forward + eigenvalue divide + inverse,
-//       3 x real-to-complex (row pairs), 4 x complex-to-real
+//       3 x real-to-complex (row pairs), 4 x complex-to-real,
+//       5 strided DCT-II, 6 strided DCT-III, 7 strided DCT-II + eigenvalue divide + DCT-III
 template <typename T>
 int fast_pass(int kind, int N, T *R, void *W, const FastGeom &g, int tdim, const void *tw, const T *e0,
               const T *e1, const T *e2, T factor, int tile, Launch L);

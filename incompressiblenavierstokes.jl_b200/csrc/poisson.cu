@@ -383,6 +383,102 @@ __global__ void __launch_bounds__(256) line_pass_kernel(PassArgs<T> a) {
 }
 
 // ----------------------------------------------------------------------------------------
+// Thomas pass of psolver_tridiagonal for the register-FFT fast path (pressure.jl:480-504,
+// 531-538): one thread per Fourier mode (kx, ko) marches along the wall-normal index j;
+// consecutive threads own consecutive kx, so every access of the sweep is a coalesced row.
+// w_j goes to a scratch array for the back substitution, like `thomas_w` in the reference.
+// ----------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128)
+    thomas_march_kernel(Cx<T> *__restrict__ W, T *__restrict__ wbuf, int m0, int n, long long sd, long long so,
+                        const T *__restrict__ ta, const T *__restrict__ tb, const T *__restrict__ tc,
+                        const T *__restrict__ eig0, const T *__restrict__ eigo, T scale) {
+    const int kx = blockIdx.x * blockDim.x + threadIdx.x, ko = blockIdx.y;
+    if (kx >= m0) return;
+    const T lam = eig0[kx] + eigo[ko];
+    Cx<T> *f = W + kx + ko * so;
+    T *w = wbuf + kx + ko * so;
+    Cx<T> fp;
+    T wp;
+    {
+        Cx<T> f0 = f[0];
+        if (lam == T(0)) {
+            wp = T(0);
+            fp = Cx<T>{T(0), T(0)};
+        } else {
+            T bb = tb[0] + lam;
+            wp = tc[0] / bb;
+            fp = Cx<T>{f0.x / bb, f0.y / bb};
+        }
+        w[0] = wp;
+        f[0] = fp;
+    }
+    // rows are processed in chunks of CH with the next chunk's loads in flight (the sweeps are
+    // latency chains; bandwidth comes from the other modes and from this prefetch)
+    constexpr int CH = 4;
+    Cx<T> cur[CH], nxt[CH];
+#pragma unroll
+    for (int i = 0; i < CH; i++)
+        if (1 + i < n) nxt[i] = f[(long long)(1 + i) * sd];
+    for (int j0 = 1; j0 < n; j0 += CH) {
+#pragma unroll
+        for (int i = 0; i < CH; i++) cur[i] = nxt[i];
+#pragma unroll
+        for (int i = 0; i < CH; i++)
+            if (j0 + CH + i < n) nxt[i] = f[(long long)(j0 + CH + i) * sd];
+#pragma unroll
+        for (int i = 0; i < CH; i++) {
+            const int j = j0 + i;
+            if (j < n) {
+                T aj = ta[j];
+                T denom = tb[j] + lam - aj * wp;
+                wp = tc[j] / denom;
+                fp = Cx<T>{(cur[i].x - aj * fp.x) / denom, (cur[i].y - aj * fp.y) / denom};
+                w[(long long)j * sd] = wp;
+                f[(long long)j * sd] = fp;
+            }
+        }
+    }
+    const bool zero = kx == 0 && ko == 0;
+    // back substitution; fp holds f[n-1]
+    if (!zero) f[(long long)(n - 1) * sd] = Cx<T>{fp.x * scale, fp.y * scale};
+    T wc[CH], wn[CH];
+#pragma unroll
+    for (int i = 0; i < CH; i++)
+        if (n - 2 - i >= 0) {
+            nxt[i] = f[(long long)(n - 2 - i) * sd];
+            wn[i] = w[(long long)(n - 2 - i) * sd];
+        }
+    for (int j0 = n - 2; j0 >= 0; j0 -= CH) {
+#pragma unroll
+        for (int i = 0; i < CH; i++) cur[i] = nxt[i], wc[i] = wn[i];
+#pragma unroll
+        for (int i = 0; i < CH; i++)
+            if (j0 - CH - i >= 0) {
+                nxt[i] = f[(long long)(j0 - CH - i) * sd];
+                wn[i] = w[(long long)(j0 - CH - i) * sd];
+            }
+#pragma unroll
+        for (int i = 0; i < CH; i++) {
+            const int j = j0 - i;
+            if (j >= 0) {
+                fp = Cx<T>{cur[i].x - wc[i] * fp.x, cur[i].y - wc[i] * fp.y};
+                f[(long long)j * sd] = zero ? fp : Cx<T>{fp.x * scale, fp.y * scale};
+            }
+        }
+    }
+    if (zero) {  // remove the mean of the zero mode (pressure.jl:531-532), then the 1/fftscale
+        Cx<T> s{T(0), T(0)};
+        for (int j = 0; j < n; j++) s = cadd(s, f[(long long)j * sd]);
+        s = Cx<T>{s.x / T(n), s.y / T(n)};
+        for (int j = 0; j < n; j++) {
+            Cx<T> v = csub(f[(long long)j * sd], s);
+            f[(long long)j * sd] = Cx<T>{v.x * scale, v.y * scale};
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------
 struct Poisson {
@@ -412,6 +508,9 @@ struct Poisson {
     std::vector<PassDesc> passes;
     int max_smem = 0;
     bool fast = false;  // power-of-two all-periodic path (fft_fast.cu)
+    bool fast_tri = false;  // tridiagonal: register FFTs in the periodic directions + marching Thomas pass
+    bool fast_dct = false;  // transform: x periodic (R2C) + register FFT / DCT passes in y (and z)
+    void *thomas_w = nullptr;
     int tile = 8;
     // z-slab decomposition (world > 1): W holds this rank's nzl planes in natural layout;
     // S / Rv are the send / receive sides of the all-to-all transposes (comm.cu), laid out as
@@ -725,6 +824,21 @@ int poisson_create(const insb200_setup_t &s, const int Ip[3][2], int kind, Comm 
     }
     ps->fast = kind == INSB200_PSOLVER_SPECTRAL && getenv("INSB200_GENERIC_FFT") == nullptr;
     for (int a = 0; a < D; a++) ps->fast = ps->fast && fast_fft_supported(ps->n[a]);
+    // psolver_tridiagonal fast path: 3-D, walls in y or z, power-of-two periodic extents
+    ps->fast_tri = kind == INSB200_PSOLVER_TRIDIAGONAL && D == 3 && ps->wdir >= 1 && world == 1 &&
+                   getenv("INSB200_GENERIC_FFT") == nullptr && ps->n[1] % 2 == 0;
+    for (int a = 0; a < D; a++)
+        if (a != ps->wdir) ps->fast_tri = ps->fast_tri && fast_fft_supported(ps->n[a]);
+    if (ps->fast_tri) {
+        size_t wb = (size_t)pitch * ps->m[1] * ps->m[2] * (ps->f64 ? 8 : 4);
+        if (cudaMalloc(&ps->thomas_w, wb) != cudaSuccess) return fail("cudaMalloc of thomas_w failed");
+        ps->owned.push_back(ps->thomas_w);
+        ps->bytes += (long long)wb;
+    }
+    // psolver_transform fast path: x periodic, every extent a supported power of two
+    ps->fast_dct = kind == INSB200_PSOLVER_TRANSFORM && ps->per[0] && world == 1 && D >= 2 &&
+                   getenv("INSB200_GENERIC_FFT") == nullptr && ps->n[1] % 2 == 0;
+    for (int a = 0; a < D; a++) ps->fast_dct = ps->fast_dct && fast_fft_supported(ps->n[a]);
     ps->tile = ps->f64 ? 4 : 8;
     if (const char *e = getenv("INSB200_FFT_TILE")) ps->tile = atoi(e) > 0 ? atoi(e) : ps->tile;
     if (ps->tile > 8) ps->tile = 8;
@@ -925,6 +1039,88 @@ static int solve_t(Poisson *ps, T *p, Launch L) {
         {
             ProfScope sc(L, 11);
             INSB_TRY(fast_pass<T>(4, ps->n[0], R, ps->W, g, 0, ps->tw[0], e0, e1, e2, factor, tl, L));
+        }
+        return 0;
+    }
+    if (ps->fast_dct) {
+        // x R2C -> y (FFT or DCT-II) -> z (forward, divide, inverse; 2-D: y is the middle pass)
+        // -> y inverse -> x C2R; transforms along different directions commute, so this equals
+        // the reference order (DCTs first, pressure.jl:262-300)
+        FastGeom g;
+        g.D = D;
+        for (int d = 0; d < 3; d++) {
+            g.n[d] = ps->n[d];
+            g.ws[d] = ps->wstride[d];
+            g.rs[d] = rs[d];
+        }
+        g.m0p = (int)ps->wstride[1];
+        const T factor = (T)(ps->sign * ps->scale);
+        const T *e0 = (const T *)ps->eig[0], *e1 = (const T *)ps->eig[1], *e2 = (const T *)ps->eig[2];
+        auto pass = [&](int grp, int base_kind, int dim) -> int {
+            FastGeom gd = g;
+            gd.dw = ps->dw[dim];
+            gd.dwi = ps->dwi[dim];
+            const int kind = base_kind + (ps->per[dim] ? 0 : 5);
+            ProfScope sc(L, grp);
+            return fast_pass<T>(kind, ps->n[dim], R, ps->W, gd, dim, ps->tw[dim], e0, e1, e2, factor, 0, L);
+        };
+        {
+            ProfScope sc(L, 5);
+            INSB_TRY(fast_pass<T>(3, ps->n[0], R, ps->W, g, 0, ps->tw[0], e0, e1, e2, factor, 0, L));
+        }
+        if (D == 3) {
+            INSB_TRY(pass(6, 0, 1));
+            INSB_TRY(pass(8, 2, 2));
+            INSB_TRY(pass(10, 1, 1));
+        } else {
+            INSB_TRY(pass(8, 2, 1));
+        }
+        {
+            ProfScope sc(L, 11);
+            INSB_TRY(fast_pass<T>(4, ps->n[0], R, ps->W, g, 0, ps->tw[0], e0, e1, e2, factor, 0, L));
+        }
+        return 0;
+    }
+    if (ps->fast_tri) {
+        // x R2C (with the 1/Ω of pressure.jl:463-465 on load) -> FFT along the other periodic
+        // direction -> Thomas along the wall-normal one -> inverse FFT -> x C2R
+        FastGeom g;
+        g.D = D;
+        for (int d = 0; d < 3; d++) {
+            g.n[d] = ps->n[d];
+            g.ws[d] = ps->wstride[d];
+            g.rs[d] = rs[d];
+        }
+        g.m0p = (int)ps->wstride[1];
+        const int w = ps->wdir, o = w == 1 ? 2 : 1;  // wall-normal and the other periodic dimension
+        const T *e0 = (const T *)ps->eig[0], *eo = (const T *)ps->eig[o];
+        FastGeom gx = g;
+        gx.pre = ps->invO;
+        gx.pre_dim = w;
+        {
+            ProfScope sc(L, 5);
+            INSB_TRY(fast_pass<T>(3, ps->n[0], R, ps->W, gx, 0, ps->tw[0], e0, e0, e0, T(1), 0, L));
+        }
+        {
+            ProfScope sc(L, 6);
+            INSB_TRY(fast_pass<T>(0, ps->n[o], R, ps->W, g, o, ps->tw[o], e0, e0, e0, T(1), 0, L));
+        }
+        {
+            ProfScope sc(L, 8);
+            dim3 b(128), gr((ps->m[0] + 127) / 128, ps->n[o]);
+            thomas_march_kernel<T><<<gr, b, 0, L.stream>>>((Cx<T> *)ps->W, (T *)ps->thomas_w, ps->m[0], ps->n[w],
+                                                           ps->wstride[w], ps->wstride[o], (const T *)ps->ta,
+                                                           (const T *)ps->tb, (const T *)ps->tc, e0, eo, (T)ps->scale);
+            if (L.counter) ++*L.counter;
+            INSB_CUDA(cudaGetLastError());
+        }
+        {
+            ProfScope sc(L, 10);
+            INSB_TRY(fast_pass<T>(1, ps->n[o], R, ps->W, g, o, ps->tw[o], e0, e0, e0, T(1), 0, L));
+        }
+        {
+            ProfScope sc(L, 11);
+            INSB_TRY(fast_pass<T>(4, ps->n[0], R, ps->W, g, 0, ps->tw[0], e0, e0, e0, T(1), 0, L));
         }
         return 0;
     }

@@ -130,6 +130,14 @@ PSOLVER_CASES = [
     ("transform_wpw", (uniform(10), uniform(16), uniform(28)), ("D", "P", "D"), "transform"),
     ("transform_www", (uniform(10), uniform(16), uniform(28)), ("D", "D", "D"), "transform"),
     ("transform_ppp", (uniform(8), uniform(16), uniform(4)), ("P", "P", "P"), "transform"),
+    # register-FFT fast paths of psolver_transform (x periodic, power-of-two extents)
+    ("transform_fast_pww", (uniform(64, np.pi), uniform(32), uniform(128)), ("P", "D", "D"), "transform"),
+    ("transform_fast_ppw", (uniform(32), uniform(64), uniform(32)), ("P", "P", "D"), "transform"),
+    ("transform_fast_pwp", (uniform(128), uniform(256), uniform(32)), ("P", "D", "P"), "transform"),
+    ("transform_fast_pw", (uniform(64, 2.0), uniform(512)), ("P", "D"), "transform"),
+    # ... and of psolver_tridiagonal (walls in y or z, marching Thomas pass)
+    ("tridiag_fast_y", (uniform(64, 4.0), O.tanh_grid(0, 2, 40, 1.4), uniform(128, 2.0)), ("P", "D", "P"), "tridiagonal"),
+    ("tridiag_fast_z", (uniform(128, 4.0), uniform(32, 2.0), O.cosine_grid(0, 1, 23)), ("P", "P", "D"), "tridiagonal"),
 ]
 for _D in (2, 3):
     for _dir in range(_D):
