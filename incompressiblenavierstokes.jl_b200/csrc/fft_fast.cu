@@ -221,6 +221,18 @@ struct StridedShape {
     static constexpr size_t smem = (size_t)2 * L * BUF * sizeof(Cx<T>);
 };
 
+// row-grouped transpose layout (fft_fast.h): offset of row j / of column kx inside a plane
+template <typename T>
+__device__ __forceinline__ long long grp_row(int j, int m0p) {
+    constexpr int U = 64 / (int)sizeof(Cx<T>);
+    return (long long)(j >> 2) * (m0p * 4) + (j & 3) * U;
+}
+template <typename T>
+__device__ __forceinline__ int grp_x(int kx) {
+    constexpr int U = 64 / (int)sizeof(Cx<T>);
+    return (kx / U) * (4 * U) + (kx % U);
+}
+
 // ----------------------------------------------------------------------------------------
 // strided pass along dim `tdim` (1 or 2): MODE 0 forward, 1 inverse, 2 forward+divide+inverse
 // grid: x = tiles of L lines along kx, y = index along the remaining dimension
@@ -239,8 +251,12 @@ __global__ void __launch_bounds__(StridedShape<T, N>::NT, (sizeof(T) == 4 && Str
     const int odim = tdim == 1 ? 2 : 1;
     const long long in_sd = g.in_sd >= 0 ? g.in_sd : g.ws[tdim], out_sd = g.out_sd >= 0 ? g.out_sd : g.ws[tdim];
     const long long in_os = g.in_os >= 0 ? g.in_os : g.ws[odim], out_os = g.out_os >= 0 ? g.out_os : g.ws[odim];
-    const Cx<T> *ibase = (g.in ? (const Cx<T> *)g.in : W) + kx + (g.D == 3 ? other * in_os : 0);
-    Cx<T> *obase = (g.out ? (Cx<T> *)g.out : W) + kx + (g.D == 3 ? other * out_os : 0);
+    // row-grouped transpose layouts (fft_fast.h): column kx sits at grp_x(kx) inside its row group
+    const long long xin = (BLK && g.in_grp) ? grp_x<T>(kx) : kx, xout = (BLK && g.out_grp) ? grp_x<T>(kx) : kx;
+    const long long oin = (BLK && g.in_grp == 2) ? grp_row<T>(other, g.m0p) : other * in_os;
+    const long long oout = (BLK && g.out_grp == 2) ? grp_row<T>(other, g.m0p) : other * out_os;
+    const Cx<T> *ibase = (g.in ? (const Cx<T> *)g.in : W) + xin + (g.D == 3 ? oin : 0);
+    Cx<T> *obase = (g.out ? (Cx<T> *)g.out : W) + xout + (g.D == 3 ? oout : 0);
     LineSmem<T> sm;
     sm.buf[0] = reinterpret_cast<Cx<T> *>(smem_raw) + l;
     sm.buf[1] = sm.buf[0] + L * SS::BUF;
@@ -250,7 +266,9 @@ __global__ void __launch_bounds__(StridedShape<T, N>::NT, (sizeof(T) == 4 && Str
 #pragma unroll
         for (int m = 0; m < 8; m++) {
             int k = t + P * m;
-            v[m] = ibase[(long long)(k >> g.in_sh) * g.in_blk + (long long)(k & in_mask) * in_sd];
+            const int kl = k & in_mask;
+            v[m] = ibase[(long long)(k >> g.in_sh) * g.in_blk +
+                         (g.in_grp == 1 ? grp_row<T>(kl, g.m0p) : (long long)kl * in_sd)];
         }
     } else {
         const Cx<T> *ip = ibase + t * in_sd;
@@ -289,18 +307,21 @@ __global__ void __launch_bounds__(StridedShape<T, N>::NT, (sizeof(T) == 4 && Str
     if (BLK) {
         const int out_mask = (1 << g.out_sh) - 1;
         if (g.use_outp) {  // tile-by-tile stores straight into the peers' buffers (NVLink P2P)
-            const long long orel = kx + other * out_os;
+            const long long orel = xout + oout;
 #pragma unroll
             for (int m = 0; m < 8; m++) {
                 int k = t + P * m;
+                const int kl = k & out_mask;
                 Cx<T> *dst = reinterpret_cast<Cx<T> *>(g.outp[k >> g.out_sh]);
-                dst[orel + (long long)(k & out_mask) * out_sd] = v[m];
+                dst[orel + (g.out_grp == 1 ? grp_row<T>(kl, g.m0p) : (long long)kl * out_sd)] = v[m];
             }
         } else {
 #pragma unroll
             for (int m = 0; m < 8; m++) {
                 int k = t + P * m;
-                obase[(long long)(k >> g.out_sh) * g.out_blk + (long long)(k & out_mask) * out_sd] = v[m];
+                const int kl = k & out_mask;
+                obase[(long long)(k >> g.out_sh) * g.out_blk +
+                      (g.out_grp == 1 ? grp_row<T>(kl, g.m0p) : (long long)kl * out_sd)] = v[m];
             }
         }
     } else {
@@ -548,7 +569,7 @@ static int fast_pass_n(int kind, T *R, Cx<T> *W, const FastGeom &g, int tdim, co
             set_error("fast FFT pass: padded half-spectrum extent must be a multiple of the line tile");
             return 1;
         }
-        const bool blk = g.in_sh < 30 || g.out_sh < 30 || g.use_outp;
+        const bool blk = g.in_sh < 30 || g.out_sh < 30 || g.use_outp || g.in_grp || g.out_grp;
         dim3 grid(g.m0p / SS::L, g.D == 3 ? (g.nother >= 0 ? g.nother : g.n[tdim == 1 ? 2 : 1]) : 1);
         auto kern = kind == 0 ? (blk ? fft_strided_kernel<T, N, 0, true> : fft_strided_kernel<T, N, 0, false>)
                     : kind == 1 ? (blk ? fft_strided_kernel<T, N, 1, true> : fft_strided_kernel<T, N, 1, false>)

@@ -31,6 +31,13 @@ struct FastGeom {
     // DCT passes (kinds 5-7): twiddles w_k and winv_k of manual_dct_stuff (src/utils.jl:65-87)
     const void *dw = nullptr, *dwi = nullptr;
     int use_outp = 0;
+    // Row-grouped transpose layout (slab-decomposed solve): a [rows][m0p] plane is stored as
+    // [rows/4][m0p/U][4][U] with U = 64 bytes of complex elements, so that the four consecutive
+    // line elements a warp holds for one tile of U columns form ONE contiguous 256-byte run
+    // (peer stores over NVLink reach 710 GB/s with >= 128-byte runs against 440-580 GB/s with
+    // 64-byte ones, tools/p2p_microbench.cu).  0: plain strides, 1: the rows are the line
+    // elements (within a block), 2: the rows are the companion index `other`.
+    int in_grp = 0, out_grp = 0;
     void *outp[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 

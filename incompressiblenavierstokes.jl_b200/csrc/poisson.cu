@@ -952,6 +952,9 @@ static int solve_t(Poisson *ps, T *p, Launch L) {
             gy.out_os = m0p * kyl;
             gy.out_sh = sh;
             gy.out_blk = blk;
+            // row-grouped block layouts (fft_fast.h): 256-byte runs for the NVLink stores
+            const bool grp = kyl % 4 == 0 && nzl % 4 == 0 && getenv("INSB200_NO_GROUPED_TRANSPOSE") == nullptr;
+            gy.out_grp = grp ? 1 : 0;  // blocks hold [z local][ky local (grouped)][kx]
             if (ps->p2p) {  // store every destination's block straight into its Rv
                 ps->epoch++;
                 gy.use_outp = 1;
@@ -977,11 +980,16 @@ static int solve_t(Poisson *ps, T *p, Launch L) {
             gz.in_sd = gz.out_sd = m0p * kyl;
             gz.in_os = gz.out_os = m0p;
             gz.eig_off = rank * kyl;
+            gz.in_grp = gz.out_grp = grp ? 2 : 0;
             if (ps->p2p) {  // z index k -> owner k / nzl, whose S holds [source rank][z local][ky local][kx]
                 int shz = 0;
                 while ((1 << shz) < nzl) shz++;
                 gz.use_outp = 1;
                 gz.out_sh = shz;
+                if (grp) {  // ... or, grouped, [source rank][ky local][z local (grouped)][kx]
+                    gz.out_grp = 1;
+                    gz.out_os = m0p * nzl;
+                }
                 for (int s2 = 0; s2 < world; s2++) gz.outp[s2] = (Cx<T> *)ps->peerS[s2] + (long long)rank * blk;
             }
             {
@@ -1005,6 +1013,14 @@ static int solve_t(Poisson *ps, T *p, Launch L) {
             gi.in_os = m0p * kyl;
             gi.in_sh = sh;
             gi.in_blk = blk;
+            if (grp) {
+                if (ps->p2p) {  // [source rank][ky local][z local (grouped)][kx]
+                    gi.in_grp = 2;
+                    gi.in_sd = m0p * nzl;
+                } else {  // the all-to-all moved [z local][ky local (grouped)][kx] blocks verbatim
+                    gi.in_grp = 1;
+                }
+            }
             {
                 ProfScope sc(L, 10);
                 INSB_TRY(fast_pass<T>(1, ps->n[1], R, ps->W, gi, 1, ps->tw[1], e0, e1, e2, factor, tl, L));

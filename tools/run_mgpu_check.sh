@@ -1,0 +1,6 @@
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
+$TR --master-port 29511 tests/mgpu_worker.py --grid 64 32 64 --dtype f64 > gpurun_out/mg2_f64.log 2>&1; echo "rc $?" >> gpurun_out/mg2_f64.log
+$TR --master-port 29512 tests/mgpu_worker.py --grid 128 64 128 --dtype f32 > gpurun_out/mg2_f32.log 2>&1; echo "rc $?" >> gpurun_out/mg2_f32.log
+INSB200_NO_P2P=1 $TR --master-port 29513 tests/mgpu_worker.py --grid 64 32 64 --dtype f64 > gpurun_out/mg2_f64_nccl.log 2>&1; echo "rc $?" >> gpurun_out/mg2_f64_nccl.log
+$TR --master-port 29514 bench.py --gpus 2 --steps 10 --warmup 3 --no-e2e --no-cpu > gpurun_out/mg2_bench.json 2> gpurun_out/mg2_bench.err
+INSB200_NO_GROUPED_TRANSPOSE=1 $TR --master-port 29515 bench.py --gpus 2 --steps 10 --warmup 3 --no-e2e --no-cpu > gpurun_out/mg2_bench_nogrp.json 2> gpurun_out/mg2_bench_nogrp.err
