@@ -28,6 +28,10 @@ for p in (ROOT, PKG):
 
 import numpy as np  # noqa: E402
 
+# ncu --set full, bytes per launch (average over the 4 launches of an RK44 step where they differ)
+NCU_TRAFFIC_SOURCE = "profiles/r1b_ncu_full_summary.md (dram__bytes_read.sum + dram__bytes_write.sum per launch)"
+NCU_TRAFFIC = {"rhs_combine": 6.58e9, "divergence": 2.15e9, "project": 3.73e9, "poisson": 5.27e9}
+
 METRIC = "cell-updates/s per RK44 step (TGV3D N^3)"
 UNIT = "cell-updates/s"
 NU = 1e-3
@@ -253,9 +257,14 @@ def run_gpu(args):
     # ---- roofline of the dominant kernel group (DESIGN.md "Algorithmic bytes") ----
     # per launch and per cell: stage kernel 48w/4, divergence 4w, Poisson pass 2w (5 per solve),
     # projection 7w; bytes = count * w * n^3
-    alg = {"rhs_combine": 12.0, "divergence": 4.0, "poisson": 10.0, "project": 7.0}
+    # with divergence! fused into the first FFT pass (no d array) that pass reads v (3w) and writes
+    # the half spectrum (1w): Poisson 12w per solve, no divergence launches
+    fused_div = prof["divergence"][1] == 0
+    alg = {"rhs_combine": 12.0, "divergence": 4.0, "poisson": 12.0 if fused_div else 10.0, "project": 7.0}
     dom = max(alg, key=lambda k: prof[k][0])
     alg.update({k: 2.0 for k in ("fft_x_r2c", "fft_y_fwd", "fft_z_mid", "fft_y_inv", "fft_x_c2r")})
+    if fused_div:
+        alg["fft_x_r2c"] = 4.0
     d_ms, d_cnt = prof[dom]
     per = d_ms / max(d_cnt, 1)
     achieved = alg[dom] * w * n**3 / (per * 1e-3) / 1e9
@@ -263,8 +272,12 @@ def run_gpu(args):
                   "GBps": (alg[k] * w * n**3 / (prof[k][0] / max(prof[k][1], 1) * 1e-3) / 1e9) if k in alg and prof[k][0] > 0 else None}
               for k in prof}
     step_bytes = 120.0 * w * n**3  # per GPU
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
+    # committed `ncu --set full` capture of this workload (profiles/, 512^3 f32 only)
+    traffic = NCU_TRAFFIC.get(dom) if (n == 512 and args.dtype == "f32") else None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": NCU_TRAFFIC_SOURCE if traffic else None,
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_cell": alg[dom] * w,
                 "step": {"achieved": step_bytes / (ms / args.steps * 1e-3) / 1e9,
                          "frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak,
@@ -279,24 +292,28 @@ def run_gpu(args):
         from insb200._lib import lib, check
         from insb200.api import _params, _coef_dtype
 
-        uh = torch.empty(u.shape, dtype=u.dtype, pin_memory=True)
-        uh.copy_(stepper["state"]["u"])
+        ke = max(2, min(args.steps, 4))
+        uhs = [torch.empty(u.shape, dtype=u.dtype, pin_memory=True) for _ in range(ke)]
+        for uh in uhs:
+            uh.copy_(stepper["state"]["u"])
+        uh = uhs[0]
         s = len(method.b)
         A = (C.c_double * (s * s))(*[float(v) for v in np.asarray(method.A).reshape(-1)])
         cc = (C.c_double * s)(*[float(v) for v in method.c])
         pr = _params(sg, viscosity=NU)
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        ke = max(2, min(args.steps, 5))
+        ptrs = (C.c_void_p * ke)(*[uh_.data_ptr() for uh_ in uhs])
 
-        def host_step(t):
-            check(lib().insb200_step_rk_host(ps.plan.h, A, cc, s, _coef_dtype(method.T, dt),
-                                             C.c_void_p(uh.data_ptr()), None, float(t), float(dt), 1, C.byref(pr), st))
+        def host_steps(nm):
+            # one call = nm independent pinned host states, each: H2D, one fused RK44 step, D2H;
+            # the copies of neighbouring members overlap the kernels (insb200.h)
+            check(lib().insb200_step_rk_host_ensemble(ps.plan.h, A, cc, s, _coef_dtype(method.T, dt), ptrs, None, nm,
+                                                      0.0, float(dt), 1, C.byref(pr), st))
 
-        host_step(0.0)
+        host_steps(2)
         barrier()
         t0 = time.perf_counter()
-        for i in range(ke):
-            host_step(i * float(dt))
+        host_steps(ke)
         torch.cuda.synchronize()
         el = time.perf_counter() - t0
         if world > 1:
@@ -306,9 +323,11 @@ def run_gpu(args):
         nbytes = uh.numel() * uh.element_size() * world
         e2e = {"value": cells * ke / el, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                "steps": ke, "ms_per_step": 1e3 * el / ke,
-               "note": "insb200_step_rk_host on every rank: pinned host slab of u -> device, one fused RK44 step, "
-                       "device -> host, every step; bytes summed over ranks, time = max over ranks"}
-        assert np.isfinite(float(uh.abs().max()))
+               "note": "insb200_step_rk_host_ensemble on every rank: each step = one pinned host state (slab of u) "
+                       "-> device, one fused RK44 step, device -> host; the copies of step i+1 / i-1 overlap the "
+                       "kernels of step i (3 streams); bytes summed over ranks, time = max over ranks"}
+        assert all(np.isfinite(float(uh_.abs().max())) for uh_ in uhs)
+        del uhs
 
     # ---- CPU baseline beside it (bounded sample) ----
     cpu = None

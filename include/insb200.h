@@ -170,6 +170,17 @@ int insb200_step_rk_host(insb200_plan_t *plan, const double *A, const double *c,
                          int coef_dtype, void *u_host, void *temp_host, double t, double dt,
                          int nsteps, const insb200_params_t *params, void *stream);
 
+/* Ensemble variant of insb200_step_rk_host: `nmembers` independent states held in HOST buffers
+ * (pinned memory for full copy bandwidth) are each advanced by nsteps steps.  Member m+1 is
+ * copied in and member m-1 copied out (two extra streams, two device slots) while member m is
+ * being stepped, so that the PCIe copies overlap the kernels; returns after the last copy.
+ * Replaces a host-side loop over independent `Array` states, each advanced with timestep!
+ * (src/time_steppers/step_explicit_runge_kutta.jl:4-57). */
+int insb200_step_rk_host_ensemble(insb200_plan_t *plan, const double *A, const double *c, int s,
+                                  int coef_dtype, void *const *u_hosts, void *const *temp_hosts,
+                                  int nmembers, double t, double dt, int nsteps,
+                                  const insb200_params_t *params, void *stream);
+
 /* right_hand_side!(dudt, u, params_ref, t) (src/sciml.jl:35-48). */
 int insb200_right_hand_side(insb200_plan_t *plan, void *dudt, const void *u, double t,
                             const insb200_params_t *params, void *stream);

@@ -43,6 +43,8 @@ struct insb200_plan : public insb::Profiler {
     void *TV[2] = {nullptr, nullptr}, *TACC = nullptr;
     std::vector<void *> K, TK;
     void *HU = nullptr, *HT = nullptr;  // device state of the host-buffer entry point
+    void *HU2 = nullptr, *HT2 = nullptr;  // second slot of the pipelined ensemble entry point
+    cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of the ensemble entry point
     double *scratch = nullptr;  // reductions
     long long bytes = 0;
     long long launches = 0;
@@ -248,11 +250,23 @@ int project_t(insb200_plan *pl, T *u, T *p, void *stream, bool fused = false) {
         set_error("this plan has no Poisson solver (psolver = NONE / unsupported BC combination)");
         return 1;
     }
-    {
-        Scope sc(pl, L.stream, 1);
-        INSB_TRY(launch_divergence<T>(g, u, p, true, L, wrap));
-    }
-    {
+    if (poisson_fuses_divergence(pl->ps)) {
+        // divergence! + scalewithvolume! evaluated inside the first FFT pass (no d array)
+        DivSource ds{};
+        ds.u = u;
+        ds.cs = g.cs;
+        for (int a = 0; a < g.D; a++) {
+            ds.rdlg[a] = g.rdlg[a];
+            ds.dl[a] = g.dl[a];
+        }
+        ds.wrap = wrap;
+        Scope sc(pl, L.stream, 2);
+        INSB_TRY(poisson_solve(pl->ps, p, L, &ds));
+    } else {
+        {
+            Scope sc(pl, L.stream, 1);
+            INSB_TRY(launch_divergence<T>(g, u, p, true, L, wrap));
+        }
         Scope sc(pl, L.stream, 2);
         INSB_TRY(poisson_solve(pl->ps, p, L));
     }
@@ -668,8 +682,10 @@ int insb200_plan_destroy(insb200_plan_t *pl) {
     cudaDeviceSynchronize();
     if (pl->ps) poisson_destroy(pl->ps);
     for (void *p : {pl->V[0], pl->V[1], pl->ACC, pl->P, pl->TV[0], pl->TV[1], pl->TACC, pl->dev_tables,
-                    (void *)pl->scratch, pl->HU, pl->HT})
+                    (void *)pl->scratch, pl->HU, pl->HT, pl->HU2, pl->HT2})
         if (p) cudaFree(p);
+    if (pl->s_in) cudaStreamDestroy(pl->s_in);
+    if (pl->s_out) cudaStreamDestroy(pl->s_out);
     for (void *p : pl->K) cudaFree(p);
     for (void *p : pl->TK) cudaFree(p);
     for (auto &b : pl->brackets) {
@@ -860,6 +876,65 @@ int insb200_step_rk_host(insb200_plan_t *pl, const double *A, const double *c, i
     INSB_CUDA(cudaMemcpyAsync(u_host, dU, vb, cudaMemcpyDeviceToHost, st));
     if (bouss) INSB_CUDA(cudaMemcpyAsync(temp_host, dT, sb, cudaMemcpyDeviceToHost, st));
     INSB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+    API_END
+}
+
+int insb200_step_rk_host_ensemble(insb200_plan_t *pl, const double *A, const double *c, int s, int coef_dtype,
+                                  void *const *u_hosts, void *const *temp_hosts, int nmembers, double t,
+                                  double dt, int nsteps, const insb200_params_t *pr, void *stream) {
+    API_BEGIN
+    if (nmembers < 1 || !u_hosts) {
+        set_error("step_rk_host_ensemble: need at least one member");
+        return 1;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t vb = (size_t)pl->ncell * pl->D * pl->esz, sb = (size_t)pl->ncell * pl->esz;
+    const bool bouss = pr->boussinesq != 0;
+    if (bouss && !temp_hosts) {
+        set_error("boussinesq forcing needs a temperature field");
+        return 1;
+    }
+    if (!pl->HU) INSB_TRY(dev_alloc(pl, &pl->HU, vb));
+    if (!pl->HU2) INSB_TRY(dev_alloc(pl, &pl->HU2, vb));
+    if (bouss && !pl->HT) INSB_TRY(dev_alloc(pl, &pl->HT, sb));
+    if (bouss && !pl->HT2) INSB_TRY(dev_alloc(pl, &pl->HT2, sb));
+    if (!pl->s_in) INSB_CUDA(cudaStreamCreateWithFlags(&pl->s_in, cudaStreamNonBlocking));
+    if (!pl->s_out) INSB_CUDA(cudaStreamCreateWithFlags(&pl->s_out, cudaStreamNonBlocking));
+    // three-deep pipeline over the members: H2D of member m+1 (s_in) and D2H of member m-1 (s_out)
+    // run while member m is being stepped on the caller's stream; two device slots
+    std::vector<cudaEvent_t> ev(3 * (size_t)nmembers);
+    for (auto &e : ev) INSB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    int rc = 0;
+    {
+        cudaEvent_t start;
+        INSB_CUDA(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
+        INSB_CUDA(cudaEventRecord(start, st));  // work already queued on the caller's stream comes first
+        INSB_CUDA(cudaStreamWaitEvent(pl->s_in, start, 0));
+        INSB_CUDA(cudaEventDestroy(start));
+    }
+    for (int m = 0; m < nmembers && rc == 0; m++) {
+        void *dU = (m & 1) ? pl->HU2 : pl->HU;
+        void *dT = bouss ? ((m & 1) ? pl->HT2 : pl->HT) : nullptr;
+        cudaEvent_t in_done = ev[3 * m], comp_done = ev[3 * m + 1], out_done = ev[3 * m + 2];
+        if (m >= 2) INSB_CUDA(cudaStreamWaitEvent(pl->s_in, ev[3 * (m - 2) + 2], 0));  // slot free again
+        INSB_CUDA(cudaMemcpyAsync(dU, u_hosts[m], vb, cudaMemcpyHostToDevice, pl->s_in));
+        if (bouss) INSB_CUDA(cudaMemcpyAsync(dT, temp_hosts[m], sb, cudaMemcpyHostToDevice, pl->s_in));
+        INSB_CUDA(cudaEventRecord(in_done, pl->s_in));
+        INSB_CUDA(cudaStreamWaitEvent(st, in_done, 0));
+        for (int n = 0; n < nsteps && rc == 0; n++)
+            rc = insb200_step_rk(pl, A, c, s, coef_dtype, dU, dT, t + n * dt, dt, pr, stream);
+        INSB_CUDA(cudaEventRecord(comp_done, st));
+        INSB_CUDA(cudaStreamWaitEvent(pl->s_out, comp_done, 0));
+        INSB_CUDA(cudaMemcpyAsync(u_hosts[m], dU, vb, cudaMemcpyDeviceToHost, pl->s_out));
+        if (bouss) INSB_CUDA(cudaMemcpyAsync(temp_hosts[m], dT, sb, cudaMemcpyDeviceToHost, pl->s_out));
+        INSB_CUDA(cudaEventRecord(out_done, pl->s_out));
+    }
+    cudaError_t e1 = cudaStreamSynchronize(pl->s_out), e2 = cudaStreamSynchronize(st);
+    for (auto &e : ev) cudaEventDestroy(e);
+    if (rc) return rc;
+    INSB_CUDA(e1);
+    INSB_CUDA(e2);
     return 0;
     API_END
 }

@@ -28,6 +28,17 @@ struct FastGeom {
     // pressure.jl:463-465), indexed by the row's index along dimension pre_dim (1 or 2)
     const void *pre = nullptr;
     int pre_dim = 1;
+    // x R2C pass only: fused divergence! + scalewithvolume! (src/operators.jl:218-247).  When div_u
+    // is set the real rows are computed on the fly from the velocity field (same evaluation order
+    // as divergence_kernel, stencil.cu) instead of being read from R, which saves one write and
+    // one read of the pressure array per solve.  div_u and the tables are offset to the first
+    // pressure DOF like R; div_wrap: bit d = the lower neighbour of the first cell along the
+    // periodic dimension d is the last cell (ghosts need not be filled).
+    const void *div_u = nullptr;
+    long long div_cs = 0;  // component stride of the velocity field
+    const void *div_r[3] = {nullptr, nullptr, nullptr};  // guarded 1/Δ
+    const void *div_d[3] = {nullptr, nullptr, nullptr};  // Δ
+    int div_wrap = 0;
     // DCT passes (kinds 5-7): twiddles w_k and winv_k of manual_dct_stuff (src/utils.jl:65-87)
     const void *dw = nullptr, *dwi = nullptr;
     int use_outp = 0;

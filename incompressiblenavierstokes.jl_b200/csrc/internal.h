@@ -167,7 +167,18 @@ struct Poisson;  // opaque
 int poisson_create(const insb200_setup_t &s, const int Ip[3][2], int kind, Comm *comm, Poisson **out);
 void poisson_destroy(Poisson *p);
 long long poisson_bytes(const Poisson *p);
-int poisson_solve(Poisson *ps, void *p_ghosted, Launch L);
+// Optional source of the right-hand side: when given (and poisson_fuses_divergence), the first
+// pass of the solve evaluates divergence! + scalewithvolume! of the velocity `u` itself and
+// p_ghosted is only written (with the solution).  Tables are the ghosted Setup tables.
+struct DivSource {
+    const void *u;
+    long long cs;
+    const void *rdlg[3];
+    const void *dl[3];
+    int wrap;
+};
+bool poisson_fuses_divergence(const Poisson *ps);
+int poisson_solve(Poisson *ps, void *p_ghosted, Launch L, const DivSource *div = nullptr);
 // direct peer-store transposes: export this rank's IPC handles / import everybody's
 constexpr int POISSON_IPC_BYTES = 192;
 int poisson_ipc_export(Poisson *ps, void *blob);

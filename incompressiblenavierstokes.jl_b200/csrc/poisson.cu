@@ -913,11 +913,28 @@ int poisson_ipc_import(Poisson *ps, const void *blobs) {
 }
 
 template <typename T>
-static int solve_t(Poisson *ps, T *p, Launch L) {
+static int solve_t(Poisson *ps, T *p, Launch L, const DivSource *div) {
     const int D = ps->D;
     long long rs[3] = {1, ps->Ng[0], (long long)ps->Ng[0] * ps->Ng[1]};
     T *R = p;
     for (int a = 0; a < D; a++) R += ps->ioff[a] * rs[a];
+    if (div && !poisson_fuses_divergence(ps)) {
+        set_error("poisson_solve: this solver cannot take the divergence from the velocity field");
+        return 1;
+    }
+    // fused divergence! + scalewithvolume!: the x R2C pass computes its rows from the velocity
+    auto with_div = [&](FastGeom &gx) {
+        if (!div) return;
+        const T *u = (const T *)div->u;
+        for (int a = 0; a < D; a++) {
+            u += ps->ioff[a] * rs[a];
+            gx.div_r[a] = (const T *)div->rdlg[a] + ps->ioff[a];
+            gx.div_d[a] = (const T *)div->dl[a] + ps->ioff[a];
+        }
+        gx.div_u = u;
+        gx.div_cs = div->cs;
+        gx.div_wrap = div->wrap;
+    };
     if (ps->fast) {
         FastGeom g;
         g.D = D;
@@ -942,7 +959,9 @@ static int solve_t(Poisson *ps, T *p, Launch L) {
             gx.n[2] = nzl;
             {
                 ProfScope sc(L, 5);
-                INSB_TRY(fast_pass<T>(3, ps->n[0], R, ps->W, gx, 0, ps->tw[0], e0, e1, e2, factor, tl, L));
+                FastGeom gd = gx;
+                with_div(gd);
+                INSB_TRY(fast_pass<T>(3, ps->n[0], R, ps->W, gd, 0, ps->tw[0], e0, e1, e2, factor, tl, L));
             }
             FastGeom gy = g;  // y forward: W (natural) -> S (blocked by destination rank)
             gy.nother = nzl;
@@ -1033,7 +1052,9 @@ static int solve_t(Poisson *ps, T *p, Launch L) {
         }
         {
             ProfScope sc(L, 5);
-            INSB_TRY(fast_pass<T>(3, ps->n[0], R, ps->W, g, 0, ps->tw[0], e0, e1, e2, factor, tl, L));
+            FastGeom gd = g;
+            with_div(gd);
+            INSB_TRY(fast_pass<T>(3, ps->n[0], R, ps->W, gd, 0, ps->tw[0], e0, e1, e2, factor, tl, L));
         }
         if (D == 3) {
             {
@@ -1082,7 +1103,9 @@ static int solve_t(Poisson *ps, T *p, Launch L) {
         };
         {
             ProfScope sc(L, 5);
-            INSB_TRY(fast_pass<T>(3, ps->n[0], R, ps->W, g, 0, ps->tw[0], e0, e1, e2, factor, 0, L));
+            FastGeom gd = g;
+            with_div(gd);
+            INSB_TRY(fast_pass<T>(3, ps->n[0], R, ps->W, gd, 0, ps->tw[0], e0, e1, e2, factor, 0, L));
         }
         if (D == 3) {
             INSB_TRY(pass(6, 0, 1));
@@ -1113,6 +1136,7 @@ static int solve_t(Poisson *ps, T *p, Launch L) {
         FastGeom gx = g;
         gx.pre = ps->invO;
         gx.pre_dim = w;
+        with_div(gx);
         {
             ProfScope sc(L, 5);
             INSB_TRY(fast_pass<T>(3, ps->n[0], R, ps->W, gx, 0, ps->tw[0], e0, e0, e0, T(1), 0, L));
@@ -1205,8 +1229,12 @@ static int solve_t(Poisson *ps, T *p, Launch L) {
     return 0;
 }
 
-int poisson_solve(Poisson *ps, void *p, Launch L) {
-    return ps->f64 ? solve_t<double>(ps, (double *)p, L) : solve_t<float>(ps, (float *)p, L);
+bool poisson_fuses_divergence(const Poisson *ps) {
+    return ps && (ps->fast || ps->fast_dct || ps->fast_tri) && getenv("INSB200_NO_FUSED_DIVERGENCE") == nullptr;
+}
+
+int poisson_solve(Poisson *ps, void *p, Launch L, const DivSource *div) {
+    return ps->f64 ? solve_t<double>(ps, (double *)p, L, div) : solve_t<float>(ps, (float *)p, L, div);
 }
 
 }  // namespace insb

@@ -704,6 +704,58 @@ static int launch_stage_t(const Grid<T> &g, const StageArgs<T> &a, Launch L, int
     return 0;
 }
 
+// ------------------------------------------------------------------------------------
+// Boussinesq terms as a second pass behind the marching momentum kernel (3-D): temperature
+// right-hand side (convection_diffusion_temp! + dissipation!, src/operators.jl:669-681,772-781)
+// with its stage combine, and the buoyancy term g*avg(temp) (applygravity!, :802-829) added to
+// the gravity component of the velocity outputs the momentum kernel has just written.
+// v = (vbase + cv k) + cv g avg(T) instead of vbase + cv (k + g avg(T)): a rounding-level
+// difference, far inside the parity tolerance.
+// ------------------------------------------------------------------------------------
+template <typename T, typename CT>
+__global__ void __launch_bounds__(256) bouss_extra_kernel(Grid<T> g, StageArgs<T> a) {
+    int I[3];
+    I[0] = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    I[1] = blockIdx.y * blockDim.y + threadIdx.y + 1;
+    I[2] = (int)blockIdx.z + 1;
+    if (I[0] >= g.N[0] - 1 || I[1] >= g.N[1] - 1) return;
+    const long long idx = I[0] + I[1] * g.s[1] + I[2] * g.s[2];
+    GLoad<T, 3> U{a.u + idx, g.s[1], g.s[2], g.cs};
+    GLoad<T, 3> Tm{a.temp + idx, g.s[1], g.s[2], 0};
+    const T kt = temperature_rhs<T, 3>(U, Tm, g, I, (T)a.kappa, (T)a.nu, a.dodiss != 0);
+    if (a.tk_out) a.tk_out[idx] = kt;
+    if (a.tv) {
+        T x = a.tvbase[idx];
+        for (int j = 0; j < a.nprev; j++) x = axpy_rn<T, CT>(x, a.cprev[j], a.tkprev[j][idx]);
+        a.tv[idx] = axpy_rn<T, CT>(x, a.cv, kt);
+    }
+    if (a.tacc_out) a.tacc_out[idx] = axpy_rn<T, CT>(a.tacc_in[idx], a.ca, kt);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        if (c != a.gdir) continue;
+        const T gk = (T)a.grav * avg_face<3>(Tm, g, I, c, 0);
+        const long long q = idx + c * g.cs;
+        if (a.k_out) a.k_out[q] += gk;
+        if (a.v) a.v[q] = axpy_rn<T, CT>(a.v[q], a.cv, gk);
+        if (a.acc_out) a.acc_out[q] = axpy_rn<T, CT>(a.acc_out[q], a.ca, gk);
+    }
+}
+
+template <typename T, typename CT>
+static int launch_stage_bouss_split(const Grid<T> &g, const StageArgs<T> &a, Launch L) {
+    StageArgs<T> m = a;  // momentum without the temperature coupling
+    m.bouss = 0;
+    m.temp = nullptr;
+    m.tv = m.tacc_out = m.tk_out = nullptr;
+    INSB_TRY((launch_stage_pair<T, CT>(g, m, L)));
+    dim3 b(64, 4, 1);
+    dim3 gr((g.N[0] - 2 + b.x - 1) / b.x, (g.N[1] - 2 + b.y - 1) / b.y, g.N[2] - 2);
+    bouss_extra_kernel<T, CT><<<gr, b, 0, L.stream>>>(g, a);
+    if (L.counter) ++*L.counter;
+    INSB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 template <typename T>
 struct WideOf {
     typedef double type;
@@ -713,6 +765,12 @@ template <typename T>
 int launch_stage(const Grid<T> &g, const StageArgs<T> &a, bool ct_double, Launch L) {
     static const bool force_direct = getenv("INSB200_DIRECT_STAGE") != nullptr;
     static const bool use_v2 = getenv("INSB200_STAGE_V2") != nullptr;
+    const bool no_split = getenv("INSB200_BOUSS_DIRECT") != nullptr;
+    if (g.D == 3 && a.bouss && a.temp && a.conv && a.diff && !a.zero_outside && !a.add_to_k && !force_direct &&
+        !no_split && a.v != nullptr && 3 * g.cs < (1LL << 32)) {
+        if (sizeof(T) == 8 || ct_double) return launch_stage_bouss_split<T, double>(g, a, L);
+        return launch_stage_bouss_split<T, T>(g, a, L);
+    }
     if (g.D == 3 && !a.bouss && a.conv && a.diff && !a.zero_outside && !a.add_to_k && !force_direct &&
         a.v != nullptr && 3 * g.cs < (1LL << 32)) {
         if (use_v2) {

@@ -1,0 +1,168 @@
+"""GPU: every optimised kernel variant against the plain variant it replaces (same library,
+switched with the INSB200_* environment variables the launchers read at call time), plus the
+host-buffer ensemble entry point against device-resident stepping.  The oracle comparisons of
+the default variants live in test_gpu_parity.py."""
+import contextlib
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+from oracle import bc as obc, pressure as opr
+
+from gpu_helpers import make_setups, random_scal, rel_l2, smooth_vec, uniform
+
+pytestmark = pytest.mark.gpu
+
+
+def ins():
+    import insb200
+
+    return insb200
+
+
+@contextlib.contextmanager
+def env(**kw):
+    old = {k: os.environ.get(k) for k in kw}
+    try:
+        for k, v in kw.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = str(v)
+        yield
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+PIPE_CASES = [
+    ("s3_64_32_128", (uniform(64), uniform(32), uniform(128)), ("P", "P", "P"), "spectral"),
+    ("s3_32_512_64", (uniform(32), uniform(512), uniform(64)), ("P", "P", "P"), "spectral"),
+    ("s3_128_64_1024", (uniform(128), uniform(64), uniform(1024)), ("P", "P", "P"), "spectral"),
+    ("s2_256_2048", (uniform(256), uniform(2048)), ("P", "P"), "spectral"),
+    ("t3_64_32_128", (uniform(64, 4.0), O.tanh_grid(0, 2, 32, 1.4), uniform(128, 2.0)), ("P", "D", "P"), "tridiagonal"),
+]
+
+
+@pytest.mark.parametrize("T", [np.float64, np.float32])
+@pytest.mark.parametrize("name,x,bcs,kind", PIPE_CASES)
+def test_pipelined_fft_passes_bit_identical(name, x, bcs, kind, T):
+    """cp.async-pipelined persistent strided passes == plain strided passes, bit for bit."""
+    I = ins()
+    so, sg = make_setups(x, bcs, T=T)
+    mk = {"spectral": I.psolver_spectral, "tridiagonal": I.psolver_tridiagonal}[kind]
+    ps = mk(sg)
+    f = random_scal(so, 5)
+    with env(INSB200_FFT_PIPELINE=0):
+        a = I.to_host(ps(I.to_device(sg, f)))
+    for mode in (1, 2, 3):
+        with env(INSB200_FFT_PIPELINE=mode):
+            b = I.to_host(ps(I.to_device(sg, f)))
+        assert np.array_equal(a, b), (name, mode, rel_l2(b, a))
+
+
+FUSE_CASES = [
+    ("periodic3", (uniform(32), uniform(64, 2.0), uniform(32, 0.5)), ("P", "P", "P"), "spectral"),
+    ("periodic2", (uniform(64), uniform(32)), ("P", "P"), "spectral"),
+    ("rb3", (uniform(32, np.pi), uniform(64), uniform(32)), ("P", "D", "D"), "transform"),
+    ("channel3", (uniform(64, 4.0), O.tanh_grid(0, 2, 24, 1.4), uniform(32, 2.0)), ("P", "D", "P"), "tridiagonal"),
+    ("channel2", (uniform(32, 4.0), O.cosine_grid(0, 1, 16)), ("P", "D"), "tridiagonal"),
+]
+
+
+@pytest.mark.parametrize("T", [np.float64, np.float32])
+@pytest.mark.parametrize("name,x,bcs,kind", FUSE_CASES)
+def test_fused_divergence_matches_separate_pass(name, x, bcs, kind, T):
+    """divergence! + scalewithvolume! evaluated inside the first FFT pass == separate kernel,
+    and both reproduce the oracle's project!."""
+    I = ins()
+    so, sg = make_setups(x, bcs, T=T)
+    mk_g = {"spectral": I.psolver_spectral, "transform": I.psolver_transform, "tridiagonal": I.psolver_tridiagonal}[kind]
+    mk_o = {"spectral": opr.psolver_spectral, "transform": opr.psolver_transform, "tridiagonal": opr.psolver_tridiagonal}[kind]
+    ps_g, ps_o = mk_g(sg), mk_o(so)
+    u = smooth_vec(so, 31)
+    want = opr.project(u.copy(order="F"), so, ps_o)
+    out = {}
+    for tag, val in (("fused", None), ("separate", 1)):
+        with env(INSB200_NO_FUSED_DIVERGENCE=val):
+            ud = I.to_device(sg, u)
+            I.project_(ud, sg, psolver=ps_g, p=I.scalarfield(sg))
+            out[tag] = I.to_host(ud)
+    tol = 1e-12 if T is np.float64 else 1e-5
+    inner = tuple(slice(1, -1) for _ in range(so.D))
+    for tag in out:
+        assert rel_l2(out[tag][inner], want[inner]) < tol, (name, tag)
+    assert rel_l2(out["fused"], out["separate"]) < (1e-13 if T is np.float64 else 1e-6)
+
+
+@pytest.mark.parametrize("T", [np.float64, np.float32])
+def test_boussinesq_split_matches_single_kernel(T):
+    """marching momentum kernel + temperature/buoyancy pass == the one-kernel direct variant."""
+    I = ins()
+    x = (uniform(32, np.pi), uniform(24), uniform(20))
+    bcs = ("P", "D", "D")
+    tb = ("P", "S", (("D", 1.0), ("D", 0.0)))
+    so, sg = make_setups(x, bcs, temp_bcs=tb, T=T)
+    ps_g = I.psolver_transform(sg)
+    u0 = smooth_vec(so, 41)
+    temp0 = obc.apply_bc_temp(random_scal(so, 42), 0.0, so)
+    params = dict(viscosity=1e-2, conductivity=2e-2, gdir=2, gravity=1.0, dodissipation=True)
+    res = {}
+    for tag, val in (("split", None), ("direct", 1)):
+        with env(INSB200_BOUSS_DIRECT=val):
+            for mname in ("RK44", "Wray3"):
+                m = getattr(I.RKMethods, mname)(T)
+                st = {"u": I.to_device(sg, u0), "temp": I.to_device(sg, temp0)}
+                sp = I.create_stepper(m, setup=sg, psolver=ps_g, state=st, t=0.0)
+                for _ in range(2):
+                    sp = I.timestep_(m, I.boussinesq_, sp, 5e-3, params=params)
+                res[tag, mname] = (I.to_host(sp["state"]["u"]), I.to_host(sp["state"]["temp"]))
+    tol = 1e-13 if T is np.float64 else 1e-6
+    for mname in ("RK44", "Wray3"):
+        for k in (0, 1):
+            assert rel_l2(res["split", mname][k], res["direct", mname][k]) < tol, (mname, k)
+
+
+def test_host_ensemble_matches_device_stepping():
+    """insb200_step_rk_host_ensemble (pipelined H2D / step / D2H over members) == stepping each
+    member on the device."""
+    import torch
+
+    I = ins()
+    from insb200._lib import check, lib
+    from insb200.api import _coef_dtype, _params
+
+    T = np.float32
+    n = 64
+    so, sg = make_setups((uniform(n), uniform(n), uniform(n)), ("P", "P", "P"), T=T)
+    ps = I.psolver_spectral(sg)
+    m = I.RKMethods.RK44(T)
+    dt = T(1e-3)
+    members = [smooth_vec(so, 50 + i) for i in range(5)]
+    want = []
+    for u0 in members:
+        sp = I.create_stepper(m, setup=sg, psolver=ps, state={"u": I.to_device(sg, u0)}, t=0.0)
+        for _ in range(2):
+            sp = I.timestep_(m, I.navierstokes_, sp, dt, params=dict(viscosity=1e-3))
+        want.append(I.to_host(sp["state"]["u"]))
+    hosts = []
+    for u0 in members:
+        h = torch.empty(I.to_device(sg, u0).shape, dtype=torch.float32, pin_memory=True)
+        h.copy_(I.to_device(sg, u0))
+        hosts.append(h)
+    s = len(m.b)
+    A = (C.c_double * (s * s))(*[float(v) for v in np.asarray(m.A).reshape(-1)])
+    cc = (C.c_double * s)(*[float(v) for v in m.c])
+    pr = _params(sg, viscosity=1e-3)
+    ptrs = (C.c_void_p * len(hosts))(*[h.data_ptr() for h in hosts])
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    check(lib().insb200_step_rk_host_ensemble(ps.plan.h, A, cc, s, _coef_dtype(m.T, dt), ptrs, None, len(hosts), 0.0,
+                                              float(dt), 2, C.byref(pr), st))
+    for h, w in zip(hosts, want):
+        assert np.array_equal(I.to_host(h.cuda()), w)

@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--grid", type=int, nargs=3, default=[512, 512, 512])
     ap.add_argument("--dtype", default="f32")
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--pipeline", type=int, nargs="+", default=[0], help="INSB200_FFT_PIPELINE modes to time")
     a = ap.parse_args()
     import insb200 as I
 
@@ -29,19 +30,23 @@ def main():
     ps = I.psolver_spectral(sg)
     p = I.scalarfield(sg)
     p.normal_()
-    for _ in range(3):
-        ps(p)
-    torch.cuda.synchronize()
-    ps.plan.profile_enable(True)
-    ps.plan.profile_read()
-    for _ in range(a.reps):
-        ps(p)
-    prof = ps.plan.profile_read()
     cells = float(np.prod(a.grid))
-    for k in ("poisson", "fft_x_r2c", "fft_y_fwd", "fft_z_mid", "fft_y_inv", "fft_x_c2r"):
-        ms = prof[k][0] / max(prof[k][1], 1)
-        byt = (10 if k == "poisson" else 2) * w * cells
-        print(f"{k:12s} {ms:8.3f} ms  {byt / ms / 1e6:8.0f} GB/s")
+    for mode in a.pipeline:  # INSB200_FFT_PIPELINE is read at every launch
+        os.environ["INSB200_FFT_PIPELINE"] = str(mode)
+        for _ in range(3):
+            ps(p)
+        torch.cuda.synchronize()
+        ps.plan.profile_enable(True)
+        ps.plan.profile_read()
+        for _ in range(a.reps):
+            ps(p)
+        prof = ps.plan.profile_read()
+        ps.plan.profile_enable(False)
+        print(f"# INSB200_FFT_PIPELINE={mode} grid {a.grid} {a.dtype}")
+        for k in ("poisson", "fft_x_r2c", "fft_y_fwd", "fft_z_mid", "fft_y_inv", "fft_x_c2r"):
+            ms = prof[k][0] / max(prof[k][1], 1)
+            byt = (10 if k == "poisson" else 2) * w * cells
+            print(f"{k:12s} {ms:8.3f} ms  {byt / ms / 1e6:8.0f} GB/s", flush=True)
 
 
 if __name__ == "__main__":
