@@ -80,6 +80,7 @@ static int offset_p(int bc, bool isright) {
 
 template <typename T>
 static int halo_dim(const Grid<T> &g, const BcDesc &b, T *f, int ncomp, Launch L) {
+    if (L.counter) *L.counter += comm_halo_launches(b.comm);
     return comm_halo_z(b.comm, f, sizeof(T), g.s[2], g.N[2], ncomp, g.cs, L.stream);
 }
 

@@ -11,6 +11,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -86,7 +87,20 @@ struct Comm {
     ncclComm_t comm = nullptr;
     int refs = 1;
     std::string key;
+    // direct peer-store halo exchange (comm_enable_p2p_halo): every rank owns a window
+    // [flag words | staging slots] in peer-mapped memory
+    bool halo_p2p = false;
+    char *halo_win[8] = {};
+    size_t halo_slot = 0;  // bytes per staging slot
+    unsigned halo_epoch = 0;
 };
+
+// window layout: unsigned words 0..23 belong to the transposes (poisson.cu), word 16 is the
+// time-out marker; halo flags at HALO_FLAG0 + parity*2 + dir, block counter at HALO_COUNTER;
+// staging slots (parity, dir) start at byte HALO_STAGING
+constexpr int HALO_FLAG0 = 32, HALO_COUNTER = 48, HALO_TIMEOUT = 16;
+constexpr size_t HALO_STAGING = 4096;
+size_t comm_halo_window_bytes(size_t slot_bytes) { return HALO_STAGING + 4 * ((slot_bytes + 255) / 256 * 256); }
 
 // One communicator per unique id and process: several plans of the same setup (base plan,
 // psolver plans) share it, since an id can be passed to ncclCommInitRank only once.
@@ -159,8 +173,110 @@ int comm_world(const Comm *c) { return c ? c->world : 1; }
 //   upper ghost  <- first interior plane of the rank above    (u[N]   = u[2])
 // Posting order (send up, send down, recv from below, recv from above) keeps the pairs
 // matched when world == 2 and both neighbours are the same peer.
+// ---- halo exchange by direct peer stores --------------------------------------------------
+// push: the top interior plane of every component goes into the upper neighbour's "from below"
+// slot, the first interior plane into the lower neighbour's "from above" slot; the last block
+// to finish raises the neighbours' flags (stores -> __threadfence_system -> counter -> flags).
+// pull: waits for both flags of this epoch, then copies the slots into the ghost planes.
+// Slots and flags are double-buffered by the parity of the exchange count: a rank can be at
+// most one exchange ahead of its neighbours (it needs their data of exchange e before it can
+// start e + 1), so the slot of exchange e + 2 is free again when it is written.
+template <typename V>
+__global__ void __launch_bounds__(256) halo_push_kernel(const char *field, size_t plane_bytes, int nplanes,
+                                                        size_t cs_bytes, char *up_slot, char *down_slot,
+                                                        unsigned *up_flag, unsigned *down_flag, unsigned epoch,
+                                                        unsigned *counter) {
+    const int comp = blockIdx.y, dir = blockIdx.z;  // dir 0: send up, 1: send down
+    const size_t nv = plane_bytes / sizeof(V);
+    const V *src = reinterpret_cast<const V *>(field + comp * cs_bytes + (dir == 0 ? (size_t)(nplanes - 2) : 1) * plane_bytes);
+    V *dst = reinterpret_cast<V *>((dir == 0 ? up_slot : down_slot) + comp * plane_bytes);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned total = gridDim.x * gridDim.y * gridDim.z;
+        if (atomicAdd(counter, 1u) == total - 1) {
+            *counter = 0;
+            __threadfence_system();
+            *(volatile unsigned *)up_flag = epoch;
+            *(volatile unsigned *)down_flag = epoch;
+            __threadfence_system();
+        }
+    }
+}
+
+template <typename V>
+__global__ void __launch_bounds__(256) halo_pull_kernel(char *field, size_t plane_bytes, int nplanes, size_t cs_bytes,
+                                                        const char *below_slot, const char *above_slot,
+                                                        const unsigned *below_flag, const unsigned *above_flag,
+                                                        unsigned epoch, unsigned *timeout_flag) {
+    const int comp = blockIdx.y, dir = blockIdx.z;  // dir 0: data from below -> lower ghost, 1: from above -> upper ghost
+    if (threadIdx.x == 0) {
+        const volatile unsigned *f = dir == 0 ? below_flag : above_flag;
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while ((int)(*f - epoch) < 0) {
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 20000000000ULL) {  // 20 s: a peer died; do not hang the device
+                *timeout_flag = 1;
+                break;
+            }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    const size_t nv = plane_bytes / sizeof(V);
+    const V *src = reinterpret_cast<const V *>((dir == 0 ? below_slot : above_slot) + comp * plane_bytes);
+    V *dst = reinterpret_cast<V *>(field + comp * cs_bytes + (dir == 0 ? 0 : (size_t)(nplanes - 1)) * plane_bytes);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = __ldcv(src + i);  // written by a peer: do not serve from a stale cache line
+}
+
+template <typename V>
+static int halo_p2p_t(Comm *c, char *f, size_t pb, int nplanes, int ncomp, size_t csb, cudaStream_t st) {
+    const int up = (c->rank + 1) % c->world, down = (c->rank + c->world - 1) % c->world;
+    const unsigned e = ++c->halo_epoch;
+    const int q = e & 1;
+    auto slot = [&](int r, int dir) { return c->halo_win[r] + HALO_STAGING + (size_t)(q * 2 + dir) * c->halo_slot; };
+    auto flag = [&](int r, int dir) { return reinterpret_cast<unsigned *>(c->halo_win[r]) + HALO_FLAG0 + q * 2 + dir; };
+    unsigned *mine = reinterpret_cast<unsigned *>(c->halo_win[c->rank]);
+    const size_t nv = pb / sizeof(V);
+    unsigned nb = (unsigned)((nv + 255) / 256);
+    if (nb > 64) nb = 64;
+    dim3 gr(nb, ncomp, 2);
+    halo_push_kernel<V><<<gr, 256, 0, st>>>(f, pb, nplanes, csb, slot(up, 0), slot(down, 1), flag(up, 0), flag(down, 1),
+                                            e, mine + HALO_COUNTER);
+    INSB_CUDA(cudaGetLastError());
+    halo_pull_kernel<V><<<gr, 256, 0, st>>>(f, pb, nplanes, csb, slot(c->rank, 0), slot(c->rank, 1), flag(c->rank, 0),
+                                            flag(c->rank, 1), e, mine + HALO_TIMEOUT);
+    INSB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int comm_enable_p2p_halo(Comm *c, void *const *windows, size_t slot_bytes) {
+    if (!c || c->halo_p2p) return 0;  // first registration wins (all ranks register in the same order)
+    for (int r = 0; r < c->world; r++) c->halo_win[r] = (char *)windows[r];
+    c->halo_slot = (slot_bytes + 255) / 256 * 256;
+    c->halo_p2p = getenv("INSB200_NCCL_HALO") == nullptr;
+    return 0;
+}
+
+void comm_disable_p2p_halo(Comm *c, const void *my_window) {
+    if (c && c->halo_p2p && c->halo_win[c->rank] == (const char *)my_window) c->halo_p2p = false;
+}
+
+int comm_halo_launches(const Comm *c) { return c && c->halo_p2p ? 2 : 0; }
+
 int comm_halo_z(Comm *c, void *field, size_t esz, long long plane, int nplanes, int ncomp, long long cs,
                 cudaStream_t st) {
+    if (c->halo_p2p && (size_t)ncomp * plane * esz <= c->halo_slot) {
+        const size_t pb = (size_t)plane * esz, csb = (size_t)cs * esz;
+        if (pb % 16 == 0 && csb % 16 == 0 && (uintptr_t)field % 16 == 0)
+            return halo_p2p_t<uint4>(c, (char *)field, pb, nplanes, ncomp, csb, st);
+        return halo_p2p_t<unsigned>(c, (char *)field, pb, nplanes, ncomp, csb, st);
+    }
     const int up = (c->rank + 1) % c->world, down = (c->rank + c->world - 1) % c->world;
     char *f = (char *)field;
     const size_t pb = (size_t)plane * esz;

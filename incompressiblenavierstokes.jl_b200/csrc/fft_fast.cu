@@ -671,9 +671,160 @@ __global__ void __launch_bounds__(XShape<T, N>::NT)
             Cx<T> zc = cconj(buf[spx<SH>((N - k) & (N - 1))]);  // conj(Z[N-k])
             Cx<T> A = Ops<T>::scale(Ops<T>::add(zk, zc), T(0.5));
             Cx<T> d = Ops<T>::scale(Ops<T>::sub(zk, zc), T(0.5));
+            if (g.x_kxl > 0) {  // blocks of modes go to their owners (peer stores)
+                const int r = k / g.x_kxl;
+                Cx<T> *o = reinterpret_cast<Cx<T> *>(g.outp[r]) +
+                           ((long long)(kz + g.x_zoff) * g.n[1] + 2 * jp) * g.x_kxl + (k - r * g.x_kxl);
+                o[0] = A;
+                o[g.x_kxl] = Cx<T>{d.y, -d.x};
+                continue;
+            }
             wa[k] = A;
             wb[k] = Cx<T>{d.y, -d.x};  // d / i
         }
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// x pass with the divergence fused in, shared-memory staged variant.  The per-thread loads of
+// the kernel above (11 scalar loads per element, 64 registers) leave it latency-bound at half
+// the HBM rate; here the block first copies every velocity row it needs -- u_x rows y0..y0+2LP-1,
+// u_y rows y0-1..y0+2LP-1, u_z the same rows of planes z and z-1, each with its left ghost --
+// into shared memory with 8-byte cp.async copies (no registers held, everything in flight at
+// once), evaluates divergence! + scalewithvolume! (src/operators.jl:218-247) from there and
+// then reuses the same shared memory for the FFT exchanges.
+// ----------------------------------------------------------------------------------------
+template <typename T, int N>
+struct XDivShape {
+    static constexpr int P = FftShape<N>::P;
+    static constexpr int NTMAX = sizeof(T) == 4 ? 256 : 128;
+    static constexpr int LP = P >= NTMAX ? 1 : NTMAX / P;  // row pairs per block
+    static constexpr int NT = LP * P;
+    static constexpr int SH = XShape<T, N>::SH;
+    static constexpr int BUF = XShape<T, N>::BUF;
+    static constexpr int RW = N + 2;           // staged row: elements -1 .. N
+    static constexpr int NR = 8 * LP + 1;      // staged rows
+    static constexpr size_t stage_bytes = (size_t)NR * RW * sizeof(T);
+    static constexpr size_t fft_bytes = (size_t)2 * LP * BUF * sizeof(Cx<T>);
+    static constexpr size_t smem = stage_bytes > fft_bytes ? stage_bytes : fft_bytes;
+};
+
+template <typename T, int N>
+__global__ void __launch_bounds__(XDivShape<T, N>::NT)
+    fft_x_r2c_div_kernel(Cx<T> *__restrict__ W, FastGeom g, const Cx<T> *__restrict__ tw) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    typedef XDivShape<T, N> XS;
+    constexpr int P = XS::P, LP = XS::LP, RW = XS::RW, NT = XS::NT;
+    const int t = threadIdx.x % P, lp = threadIdx.x / P;
+    const int hp = g.n[1] / 2;
+    const long long q0 = (long long)blockIdx.x * LP;  // first pair of the block; LP divides hp
+    const int jp0 = (int)(q0 % hp), kz = (int)(q0 / hp);
+    const int y0 = 2 * jp0;
+    const long long s1 = g.rs[1], s2 = g.rs[2];
+    T *stage = reinterpret_cast<T *>(smem_raw);
+    // ---- stage the rows: 8-byte copies starting at the left ghost of every row ----
+    {
+        const T *U0 = (const T *)g.div_u + (long long)kz * s2 - 1;  // element -1 of row y = 0, plane kz
+        const T *U1 = U0 + g.div_cs, *U2 = U1 + g.div_cs;
+        const long long ym = ((g.div_wrap & 2) && jp0 == 0) ? (long long)(g.n[1] - 1) * s1 : -s1;
+        const long long zm = ((g.div_wrap & 4) && kz == 0) ? (long long)(g.n[2] - 1) * s2 : -s2;
+        constexpr int EPC = 8 / (int)sizeof(T);        // elements per copy
+        constexpr int CPR = (N + 1 + EPC - 1) / EPC;   // copies per row: elements -1 .. N-1 at least
+        const int nrows = g.D == 3 ? 8 * LP + 1 : 4 * LP + 1;
+        for (int c = threadIdx.x; c < nrows * CPR; c += NT) {
+            const int r = c / CPR, e = (c - r * CPR) * EPC;
+            const T *src;
+            if (r < 2 * LP)
+                src = U0 + (long long)(y0 + r) * s1;                                   // u_x rows
+            else if (r < 4 * LP + 1)
+                src = r == 2 * LP ? U1 + (long long)y0 * s1 + ym : U1 + (long long)(y0 + r - 2 * LP - 1) * s1;  // u_y rows y0-1 ..
+            else if (r < 6 * LP + 1)
+                src = U2 + (long long)(y0 + r - 4 * LP - 1) * s1;                      // u_z rows, plane z
+            else
+                src = U2 + (long long)(y0 + r - 6 * LP - 1) * s1 + zm;                 // u_z rows, plane z-1
+            unsigned d = (unsigned)__cvta_generic_to_shared(stage + r * RW + e);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src + e) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    // tables while the copies are in flight
+    const int jp = jp0 + lp;
+    const T *r0 = (const T *)g.div_r[0], *d0 = (const T *)g.div_d[0];
+    const T *r1 = (const T *)g.div_r[1], *d1 = (const T *)g.div_d[1];
+    const T rya = r1[2 * jp], ryb = r1[2 * jp + 1], dya = d1[2 * jp], dyb = d1[2 * jp + 1];
+    T rz = T(0), dz = T(1);
+    if (g.D == 3) {
+        rz = ((const T *)g.div_r[2])[kz];
+        dz = ((const T *)g.div_d[2])[kz];
+    }
+    T fa = T(1), fb = T(1);
+    if (g.pre) {
+        const T *pre = (const T *)g.pre;
+        fa = g.pre_dim == 1 ? pre[2 * jp] : pre[kz];
+        fb = g.pre_dim == 1 ? pre[2 * jp + 1] : pre[kz];
+    }
+    T rx[8], dx[8];
+#pragma unroll
+    for (int m = 0; m < 8; m++) {
+        rx[m] = __ldg(r0 + t + P * m);
+        dx[m] = __ldg(d0 + t + P * m);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    Cx<T> v[8];
+    {
+        const int a = 2 * lp;
+        const T *UXa = stage + a * RW, *UXb = UXa + RW;
+        const T *UY0 = stage + (2 * LP + a) * RW, *UY1 = UY0 + RW, *UY2 = UY1 + RW;
+        const T *UZa = stage + (4 * LP + 1 + a) * RW, *UZb = UZa + RW;
+        const T *UMa = stage + (6 * LP + 1 + a) * RW, *UMb = UMa + RW;
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            const int i = t + P * m, ix = i + 1;
+            const int im = ((g.div_wrap & 1) && i == 0) ? N : i;  // staged index of element i-1
+            T da = (UXa[ix] - UXa[im]) * rx[m] + (UY1[ix] - UY0[ix]) * rya;
+            T db = (UXb[ix] - UXb[im]) * rx[m] + (UY2[ix] - UY1[ix]) * ryb;
+            T oa = dx[m] * dya, ob = dx[m] * dyb;
+            if (g.D == 3) {
+                da = da + (UZa[ix] - UMa[ix]) * rz;
+                db = db + (UZb[ix] - UMb[ix]) * rz;
+                oa = oa * dz;
+                ob = ob * dz;
+            }
+            v[m] = Cx<T>{da * oa * fa, db * ob * fb};
+        }
+    }
+    __syncthreads();  // the staging area becomes the exchange buffers
+    LineSmem<T> sm;
+    sm.buf[0] = reinterpret_cast<Cx<T> *>(smem_raw) + lp * XS::BUF;
+    sm.buf[1] = sm.buf[0] + LP * XS::BUF;
+    int exch = 0;
+    constexpr int SH = XS::SH;
+    fft_stages<T, N, false, 0, 1, SH>(v, t, sm, tw, exch);
+    Cx<T> *buf = sm.buf[exch & 1];
+#pragma unroll
+    for (int m = 0; m < 8; m++) buf[spx<SH>(t + P * m)] = v[m];
+    __syncthreads();
+    Cx<T> *wa = W + (long long)(2 * jp) * g.ws[1] + (long long)kz * g.ws[2];
+    Cx<T> *wb = wa + g.ws[1];
+#pragma unroll
+    for (int m = 0; m < 5; m++) {
+        int k = t + P * m;
+        if (m == 4 && t != 0) break;  // k = N/2 is handled by t = 0
+        Cx<T> zk = m < 4 ? v[m] : buf[spx<SH>(k)];
+        Cx<T> zc = cconj(buf[spx<SH>((N - k) & (N - 1))]);  // conj(Z[N-k])
+        Cx<T> A = Ops<T>::scale(Ops<T>::add(zk, zc), T(0.5));
+        Cx<T> d = Ops<T>::scale(Ops<T>::sub(zk, zc), T(0.5));
+        if (g.x_kxl > 0) {  // blocks of modes go to their owners (peer stores)
+            const int r = k / g.x_kxl;
+            Cx<T> *o = reinterpret_cast<Cx<T> *>(g.outp[r]) +
+                       ((long long)(kz + g.x_zoff) * g.n[1] + 2 * jp) * g.x_kxl + (k - r * g.x_kxl);
+            o[0] = A;
+            o[g.x_kxl] = Cx<T>{d.y, -d.x};
+            continue;
+        }
+        wa[k] = A;
+        wb[k] = Cx<T>{d.y, -d.x};  // d / i
     }
 }
 
@@ -751,6 +902,8 @@ static int fast_pass_n(int kind, T *R, Cx<T> *W, const FastGeom &g, int tdim, co
                         : kind == 1 ? (blk ? fft_strided_pipe_kernel<T, N, 1, true> : fft_strided_pipe_kernel<T, N, 1, false>)
                                     : (blk ? fft_strided_pipe_kernel<T, N, 2, true> : fft_strided_pipe_kernel<T, N, 2, false>);
             INSB_TRY(allow_smem(kern, psmem));
+            INSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                           cudaSharedmemCarveoutMaxShared));
             int occ = 0, dev = 0, sms = 0;
             INSB_CUDA(cudaGetDevice(&dev));
             INSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -758,6 +911,7 @@ static int fast_pass_n(int kind, T *R, Cx<T> *W, const FastGeom &g, int tdim, co
             if (occ < 1) occ = 1;
             const int nbx = (int)grid.x, ntiles = (int)(grid.x * grid.y);
             const int blocks = ntiles < occ * sms ? ntiles : occ * sms;
+            if (getenv("INSB200_DEBUG")) fprintf(stderr, "[insb200] pipelined strided pass N=%d kind=%d: %d blocks/SM, %d blocks, %zu B smem\n", N, kind, occ, blocks, psmem);
             kern<<<blocks, SS::NT, psmem, L.stream>>>(W, g, tdim, tw, e0, e1, e2, factor, nbx, ntiles);
         } else {
             auto kern = kind == 0 ? (blk ? fft_strided_kernel<T, N, 0, true> : fft_strided_kernel<T, N, 0, false>)
@@ -781,7 +935,19 @@ static int fast_pass_n(int kind, T *R, Cx<T> *W, const FastGeom &g, int tdim, co
         typedef XShape<T, N> XS;
         long long npairs = (long long)(g.n[1] / 2) * (g.D == 3 ? g.n[2] : 1);
         unsigned blocks = (unsigned)((npairs + XS::LP - 1) / XS::LP);
-        if (kind == 3 && g.div_u) {
+        typedef XDivShape<T, N> XD;
+        const char *sd = getenv("INSB200_DIV_STAGED");
+        // staged variant: whole blocks inside one z plane, even row length (8-byte aligned row
+        // starts), 8-byte aligned base and component stride
+        const bool staged = kind == 3 && g.div_u && (sd == nullptr || atoi(sd) != 0) && XD::smem <= 200 * 1024 &&
+                            (g.n[1] / 2) % XD::LP == 0 && g.rs[1] % 2 == 0 && (g.rs[2] % 2 == 0 || g.D == 2) &&
+                            g.div_cs % 2 == 0 && ((uintptr_t)((const T *)g.div_u - 1)) % 8 == 0;
+        if (staged) {
+            INSB_TRY(allow_smem(fft_x_r2c_div_kernel<T, N>, XD::smem));
+            INSB_CUDA(cudaFuncSetAttribute(fft_x_r2c_div_kernel<T, N>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                           cudaSharedmemCarveoutMaxShared));
+            fft_x_r2c_div_kernel<T, N><<<(unsigned)(npairs / XD::LP), XD::NT, XD::smem, L.stream>>>(W, g, tw);
+        } else if (kind == 3 && g.div_u) {
             INSB_TRY(allow_smem(fft_x_r2c_kernel<T, N, true>, XS::smem));
             fft_x_r2c_kernel<T, N, true><<<blocks, XS::NT, XS::smem, L.stream>>>(R, W, g, tw, npairs);
         } else if (kind == 3) {

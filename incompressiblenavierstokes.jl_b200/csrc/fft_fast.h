@@ -42,6 +42,9 @@ struct FastGeom {
     // DCT passes (kinds 5-7): twiddles w_k and winv_k of manual_dct_stuff (src/utils.jl:65-87)
     const void *dw = nullptr, *dwi = nullptr;
     int use_outp = 0;
+    // x R2C pass, decomposed psolver_tridiagonal: when x_kxl > 0 mode kx of row (y, z) is stored to
+    // outp[kx / x_kxl] (the owner of that block of modes) at [z + x_zoff][y][kx % x_kxl]
+    int x_kxl = 0, x_zoff = 0;
     // Row-grouped transpose layout (slab-decomposed solve): a [rows][m0p] plane is stored as
     // [rows/4][m0p/U][4][U] with U = 64 bytes of complex elements, so that the four consecutive
     // line elements a warp holds for one tile of U columns form ONE contiguous 256-byte run

@@ -63,6 +63,13 @@ int comm_rank(const Comm *c);   // 0 for nullptr
 int comm_world(const Comm *c);  // 1 for nullptr
 int comm_halo_z(Comm *c, void *field, size_t esz, long long plane, int nplanes, int ncomp, long long cs,
                 cudaStream_t st);
+// Halo exchange by direct peer stores: `windows[r]` is rank r's window (peer-mapped, windows[rank]
+// local) of comm_halo_window_bytes(slot_bytes) bytes, zero-initialised; slot_bytes >= bytes of
+// the ghost planes of one exchange (all components).  Until enabled comm_halo_z uses NCCL.
+size_t comm_halo_window_bytes(size_t slot_bytes);
+int comm_enable_p2p_halo(Comm *c, void *const *windows, size_t slot_bytes);
+void comm_disable_p2p_halo(Comm *c, const void *my_window);
+int comm_halo_launches(const Comm *c);  // kernels of this library per halo exchange (0 on the NCCL path)
 int comm_all_to_all(Comm *c, const void *send, void *recv, size_t block_bytes, cudaStream_t st);
 int comm_reduce_scratch(Comm *c, double *scratch, bool is_min, cudaStream_t st);
 // cross-process flags in peer-mapped memory: every rank stores `epoch` into slot `rank` of the

@@ -392,10 +392,11 @@ template <typename T>
 __global__ void __launch_bounds__(128)
     thomas_march_kernel(Cx<T> *__restrict__ W, T *__restrict__ wbuf, int m0, int n, long long sd, long long so,
                         const T *__restrict__ ta, const T *__restrict__ tb, const T *__restrict__ tc,
-                        const T *__restrict__ eig0, const T *__restrict__ eigo, T scale) {
+                        const T *__restrict__ eig0, const T *__restrict__ eigo, T scale, int kx_off, int m0_glob) {
+    // kx: column inside this rank's block of kx modes (kx_off = first global mode of the block)
     const int kx = blockIdx.x * blockDim.x + threadIdx.x, ko = blockIdx.y;
-    if (kx >= m0) return;
-    const T lam = eig0[kx] + eigo[ko];
+    if (kx >= m0 || kx + kx_off >= m0_glob) return;
+    const T lam = eig0[kx + kx_off] + eigo[ko];
     Cx<T> *f = W + kx + ko * so;
     T *w = wbuf + kx + ko * so;
     Cx<T> fp;
@@ -439,7 +440,7 @@ __global__ void __launch_bounds__(128)
             }
         }
     }
-    const bool zero = kx == 0 && ko == 0;
+    const bool zero = kx + kx_off == 0 && ko == 0;
     // back substitution; fp holds f[n-1]
     if (!zero) f[(long long)(n - 1) * sd] = Cx<T>{fp.x * scale, fp.y * scale};
     T wc[CH], wn[CH];
@@ -518,6 +519,7 @@ struct Poisson {
     // side, [n3 planes][n1/world ky rows][m0p].
     Comm *comm = nullptr;
     int nzl = 0, kyl = 0;
+    int kxl = 0;  // decomposed psolver_tridiagonal: kx modes per rank after the transpose
     void *S = nullptr, *Rv = nullptr;
     // direct peer-store transposes (NVLink P2P through CUDA IPC): peers' S / Rv / flag buffers
     // mapped into this process; flags = 3 rows x 8 slots (row 0: forward transpose done,
@@ -528,6 +530,7 @@ struct Poisson {
     unsigned *peerFlags[8] = {};
     unsigned epoch = 0;
     size_t wbytes = 0;
+    size_t halo_slot = 0;
 };
 
 static bool factorize(int n, std::vector<int> &rad) {
@@ -756,12 +759,23 @@ int poisson_create(const insb200_setup_t &s, const int Ip[3][2], int kind, Comm 
     ps->nzl = D == 3 ? ps->n[2] / world : 1;
     ps->kyl = ps->n[1] / world;
     if (world > 1) {
-        bool ok = kind == INSB200_PSOLVER_SPECTRAL && D == 3;
-        for (int a = 0; a < D; a++) ok = ok && fast_fft_supported(ps->n[a]);
-        if (!ok)
-            return fail("world > 1: only psolver_spectral on 3-D power-of-two grids (32..2048 per dim) is decomposed");
-        if (ps->n[2] % world || ps->n[1] % world || (ps->kyl & (ps->kyl - 1)))
-            return fail("world > 1: n2 and n3 must be divisible by the number of ranks (power of two)");
+        bool spec = kind == INSB200_PSOLVER_SPECTRAL && D == 3;
+        for (int a = 0; a < D; a++) spec = spec && fast_fft_supported(ps->n[a]);
+        // psolver_tridiagonal with walls in y: x R2C on the z-slab, transpose to blocks of kx
+        // modes (all y, all z), z FFT + Thomas along y + inverse z FFT there, transpose back
+        const bool tri = kind == INSB200_PSOLVER_TRIDIAGONAL && D == 3 && ps->wdir == 1 &&
+                         fast_fft_supported(ps->n[0]) && fast_fft_supported(ps->n[2]) && ps->n[1] % 2 == 0;
+        if (!spec && !tri)
+            return fail("world > 1: only psolver_spectral on 3-D power-of-two grids (32..2048 per dim) and "
+                        "psolver_tridiagonal with walls in y (power-of-two x and z extents) are decomposed");
+        if (ps->n[2] % world || (ps->nzl & (ps->nzl - 1)))
+            return fail("world > 1: n3 must be divisible by the number of ranks (power-of-two planes per rank)");
+        if (spec && (ps->n[1] % world || (ps->kyl & (ps->kyl - 1))))
+            return fail("world > 1: n2 must be divisible by the number of ranks (power of two)");
+        if (tri) {  // whole line tiles per rank: pad the half spectrum to a multiple of 8 * world
+            pitch = (ps->m[0] + 8 * world - 1) / (8 * world) * (8 * world);
+            ps->kxl = (int)(pitch / world);
+        }
     }
     ps->wstride[0] = 1;
     ps->wstride[1] = pitch;
@@ -780,10 +794,14 @@ int poisson_create(const insb200_setup_t &s, const int Ip[3][2], int kind, Comm 
         cudaMemset(ps->Rv, 0, wbytes);
         ps->bytes += 2 * (long long)wbytes;
         ps->wbytes = wbytes;
-        if (cudaMalloc((void **)&ps->flags, 3 * 8 * sizeof(unsigned)) != cudaSuccess)
-            return fail("cudaMalloc of the peer flags failed");
+        // flag words of the transposes + the window of the peer-store halo exchange (comm.cu)
+        ps->halo_slot = (size_t)3 * ps->Ng[0] * ps->Ng[1] * esz / 2;  // esz = complex size here
+        const size_t fb = comm_halo_window_bytes(ps->halo_slot);
+        if (cudaMalloc((void **)&ps->flags, fb) != cudaSuccess)
+            return fail("cudaMalloc of the peer flags / halo window failed");
         ps->owned.push_back(ps->flags);
-        cudaMemset(ps->flags, 0, 3 * 8 * sizeof(unsigned));
+        cudaMemset(ps->flags, 0, fb);
+        ps->bytes += (long long)fb;
     }
     int r = ps->f64 ? build_tables<double>(ps, s, Ip) : build_tables<float>(ps, s, Ip);
     if (r) {
@@ -825,12 +843,12 @@ int poisson_create(const insb200_setup_t &s, const int Ip[3][2], int kind, Comm 
     ps->fast = kind == INSB200_PSOLVER_SPECTRAL && getenv("INSB200_GENERIC_FFT") == nullptr;
     for (int a = 0; a < D; a++) ps->fast = ps->fast && fast_fft_supported(ps->n[a]);
     // psolver_tridiagonal fast path: 3-D, walls in y or z, power-of-two periodic extents
-    ps->fast_tri = kind == INSB200_PSOLVER_TRIDIAGONAL && D == 3 && ps->wdir >= 1 && world == 1 &&
-                   getenv("INSB200_GENERIC_FFT") == nullptr && ps->n[1] % 2 == 0;
+    ps->fast_tri = kind == INSB200_PSOLVER_TRIDIAGONAL && D == 3 && ps->wdir >= 1 &&
+                   (world == 1 ? getenv("INSB200_GENERIC_FFT") == nullptr : ps->wdir == 1) && ps->n[1] % 2 == 0;
     for (int a = 0; a < D; a++)
         if (a != ps->wdir) ps->fast_tri = ps->fast_tri && fast_fft_supported(ps->n[a]);
     if (ps->fast_tri) {
-        size_t wb = (size_t)pitch * ps->m[1] * ps->m[2] * (ps->f64 ? 8 : 4);
+        size_t wb = (size_t)pitch * ps->m[1] * (world > 1 ? ps->nzl : ps->m[2]) * (ps->f64 ? 8 : 4);
         if (cudaMalloc(&ps->thomas_w, wb) != cudaSuccess) return fail("cudaMalloc of thomas_w failed");
         ps->owned.push_back(ps->thomas_w);
         ps->bytes += (long long)wb;
@@ -851,6 +869,7 @@ int poisson_create(const insb200_setup_t &s, const int Ip[3][2], int kind, Comm 
 
 void poisson_destroy(Poisson *p) {
     if (!p) return;
+    if (p->comm && p->flags) comm_disable_p2p_halo(p->comm, p->flags);
     if (p->p2p) {
         const int rank = comm_rank(p->comm), world = comm_world(p->comm);
         for (int s = 0; s < world; s++) {
@@ -909,6 +928,7 @@ int poisson_ipc_import(Poisson *ps, const void *blobs) {
         INSB_CUDA(cudaIpcOpenMemHandle((void **)&ps->peerFlags[s], h[2], cudaIpcMemLazyEnablePeerAccess));
     }
     ps->p2p = true;
+    INSB_TRY(comm_enable_p2p_halo(ps->comm, (void *const *)ps->peerFlags, ps->halo_slot));
     return 0;
 }
 
@@ -1137,6 +1157,74 @@ static int solve_t(Poisson *ps, T *p, Launch L, const DivSource *div) {
         gx.pre = ps->invO;
         gx.pre_dim = w;
         with_div(gx);
+        if (ps->comm) {
+            if (!ps->p2p) {
+                set_error("decomposed psolver_tridiagonal needs peer access (insb200_plan_ipc_import)");
+                return 1;
+            }
+            const int world = comm_world(ps->comm), rank = comm_rank(ps->comm);
+            const int nzl = ps->nzl, kxl = ps->kxl, n1 = ps->n[1], n3 = ps->n[2];
+            const long long pitch = g.m0p;
+            ps->epoch++;
+            gx.n[2] = nzl;
+            gx.x_kxl = kxl;  // x R2C: blocks of kxl modes go straight into their owners' Rv = [n3][n1][kxl]
+            gx.x_zoff = rank * nzl;
+            for (int s2 = 0; s2 < world; s2++) gx.outp[s2] = ps->peerRv[s2];
+            {
+                ProfScope sc(L, 5);
+                INSB_TRY(fast_pass<T>(3, ps->n[0], R, ps->W, gx, 0, ps->tw[0], e0, e0, e0, T(1), 0, L));
+            }
+            {
+                ProfScope sc(L, 7);
+                INSB_TRY(comm_signal_peers(ps->peerFlags, 0, rank, world, ps->epoch, L.stream));
+                INSB_TRY(comm_wait_flags(ps->flags, 0, world, ps->epoch, ps->flags + 16, L.stream));
+            }
+            FastGeom gz = g;  // z forward, in place on Rv
+            gz.m0p = kxl;
+            gz.nother = n1;
+            gz.in = ps->Rv;
+            gz.out = ps->Rv;
+            gz.in_sd = gz.out_sd = (long long)n1 * kxl;
+            gz.in_os = gz.out_os = kxl;
+            {
+                ProfScope sc(L, 6);
+                INSB_TRY(fast_pass<T>(0, n3, R, ps->W, gz, 2, ps->tw[2], e0, e0, e0, T(1), 0, L));
+            }
+            {
+                ProfScope sc(L, 8);
+                dim3 b(128), gr((kxl + 127) / 128, n3);
+                thomas_march_kernel<T><<<gr, b, 0, L.stream>>>((Cx<T> *)ps->Rv, (T *)ps->thomas_w, kxl, n1, kxl,
+                                                               (long long)n1 * kxl, (const T *)ps->ta, (const T *)ps->tb,
+                                                               (const T *)ps->tc, e0, eo, (T)ps->scale, rank * kxl,
+                                                               ps->m[0]);
+                if (L.counter) ++*L.counter;
+                INSB_CUDA(cudaGetLastError());
+            }
+            FastGeom gi = gz;  // z inverse, plane k -> its owner's S = [nzl][n1][pitch] (natural slab layout)
+            int shz = 0;
+            while ((1 << shz) < nzl) shz++;
+            gi.use_outp = 1;
+            gi.out_sh = shz;
+            gi.out_sd = (long long)n1 * pitch;
+            gi.out_os = pitch;
+            for (int s2 = 0; s2 < world; s2++) gi.outp[s2] = (Cx<T> *)ps->peerS[s2] + (long long)rank * kxl;
+            {
+                ProfScope sc(L, 10);
+                INSB_TRY(fast_pass<T>(1, n3, R, ps->W, gi, 2, ps->tw[2], e0, e0, e0, T(1), 0, L));
+            }
+            {
+                ProfScope sc(L, 9);
+                INSB_TRY(comm_signal_peers(ps->peerFlags, 1, rank, world, ps->epoch, L.stream));
+                INSB_TRY(comm_wait_flags(ps->flags, 1, world, ps->epoch, ps->flags + 16, L.stream));
+            }
+            FastGeom gc = g;
+            gc.n[2] = nzl;
+            {
+                ProfScope sc(L, 11);
+                INSB_TRY(fast_pass<T>(4, ps->n[0], R, ps->S, gc, 0, ps->tw[0], e0, e0, e0, T(1), 0, L));
+            }
+            return 0;
+        }
         {
             ProfScope sc(L, 5);
             INSB_TRY(fast_pass<T>(3, ps->n[0], R, ps->W, gx, 0, ps->tw[0], e0, e0, e0, T(1), 0, L));
@@ -1150,7 +1238,8 @@ static int solve_t(Poisson *ps, T *p, Launch L, const DivSource *div) {
             dim3 b(128), gr((ps->m[0] + 127) / 128, ps->n[o]);
             thomas_march_kernel<T><<<gr, b, 0, L.stream>>>((Cx<T> *)ps->W, (T *)ps->thomas_w, ps->m[0], ps->n[w],
                                                            ps->wstride[w], ps->wstride[o], (const T *)ps->ta,
-                                                           (const T *)ps->tb, (const T *)ps->tc, e0, eo, (T)ps->scale);
+                                                           (const T *)ps->tb, (const T *)ps->tc, e0, eo, (T)ps->scale,
+                                                           0, ps->m[0]);
             if (L.counter) ++*L.counter;
             INSB_CUDA(cudaGetLastError());
         }

@@ -36,6 +36,9 @@ def main():
     ap.add_argument("--grid", type=int, nargs=3, default=[64, 32, 64])
     ap.add_argument("--dtype", default="f64")
     ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--case", default="periodic", choices=["periodic", "channel"],
+                    help="periodic: psolver_spectral; channel: no-slip walls in y on a tanh-stretched grid, "
+                         "psolver_tridiagonal (BASELINE config 5 shape)")
     args = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
@@ -48,11 +51,20 @@ def main():
     n = args.grid
     x = tuple(np.linspace(0.0, 1.0, m + 1).astype(T) for m in n)
     bcs = {"u": ((I.PeriodicBC(), I.PeriodicBC()),) * 3}
+    mk = I.psolver_spectral
+    if args.case == "channel":
+        import oracle as O
+
+        x = (np.linspace(0.0, 4.0, n[0] + 1).astype(T), O.tanh_grid(0, 2, n[1], 1.4).astype(T),
+             np.linspace(0.0, 2.0, n[2] + 1).astype(T))
+        bcs = {"u": ((I.PeriodicBC(), I.PeriodicBC()), (I.DirichletBC(), I.DirichletBC()),
+                     (I.PeriodicBC(), I.PeriodicBC()))}
+        mk = I.psolver_tridiagonal
     nid = I.share_unique_id()
     sd = I.Setup(x, bcs, rank=rank, world=world, nccl_id=nid)
     s1 = I.Setup(x, bcs) if rank == 0 else None
-    psd = I.psolver_spectral(sd)
-    ps1 = I.psolver_spectral(s1) if rank == 0 else None
+    psd = mk(sd)
+    ps1 = mk(s1) if rank == 0 else None
 
     rng = np.random.default_rng(7)
     ug = np.asfortranarray(rng.standard_normal(sd.N + (3,)).astype(T))
@@ -115,7 +127,7 @@ def main():
             m1 = I.maxabs(st["state"]["u"], s1)
             report(name + "_umax", abs(res[name + "_umax"] - m1) / m1, 1e-6)
         for o in out:
-            o.update(world=world, n=n, dtype=args.dtype)
+            o.update(world=world, n=n, dtype=args.dtype, case=args.case)
             print(json.dumps(o), flush=True)
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag)

@@ -73,6 +73,14 @@ FUSE_CASES = [
     ("rb3", (uniform(32, np.pi), uniform(64), uniform(32)), ("P", "D", "D"), "transform"),
     ("channel3", (uniform(64, 4.0), O.tanh_grid(0, 2, 24, 1.4), uniform(32, 2.0)), ("P", "D", "P"), "tridiagonal"),
     ("channel2", (uniform(32, 4.0), O.cosine_grid(0, 1, 16)), ("P", "D"), "tridiagonal"),
+    # extents where whole blocks of row pairs fit into a plane: shared-memory staged variant
+    ("staged_512_16_8", (uniform(512), uniform(16, 2.0), uniform(8, 0.5)), ("P", "P", "P"), "spectral"),
+    ("staged_256_32_8", (uniform(256), uniform(32), uniform(8)), ("P", "P", "P"), "spectral"),
+    ("staged_1024_8_4", (uniform(1024), uniform(8), uniform(4)), ("P", "P", "P"), "spectral"),
+    ("staged_64_64_64", (uniform(64), uniform(64), uniform(64)), ("P", "P", "P"), "spectral"),
+    ("staged2_512_64", (uniform(512), uniform(64)), ("P", "P"), "spectral"),
+    ("staged_rb_128_64_32", (uniform(128, np.pi), uniform(64), uniform(32)), ("P", "D", "D"), "transform"),
+    ("staged_channel_128_64_32", (uniform(128, 4.0), O.tanh_grid(0, 2, 64, 1.4), uniform(32, 2.0)), ("P", "D", "P"), "tridiagonal"),
 ]
 
 
@@ -89,8 +97,8 @@ def test_fused_divergence_matches_separate_pass(name, x, bcs, kind, T):
     u = smooth_vec(so, 31)
     want = opr.project(u.copy(order="F"), so, ps_o)
     out = {}
-    for tag, val in (("fused", None), ("separate", 1)):
-        with env(INSB200_NO_FUSED_DIVERGENCE=val):
+    for tag, nofuse, staged in (("fused", None, None), ("fused_unstaged", None, 0), ("separate", 1, None)):
+        with env(INSB200_NO_FUSED_DIVERGENCE=nofuse, INSB200_DIV_STAGED=staged):
             ud = I.to_device(sg, u)
             I.project_(ud, sg, psolver=ps_g, p=I.scalarfield(sg))
             out[tag] = I.to_host(ud)
@@ -99,6 +107,27 @@ def test_fused_divergence_matches_separate_pass(name, x, bcs, kind, T):
     for tag in out:
         assert rel_l2(out[tag][inner], want[inner]) < tol, (name, tag)
     assert rel_l2(out["fused"], out["separate"]) < (1e-13 if T is np.float64 else 1e-6)
+    assert rel_l2(out["fused_unstaged"], out["separate"]) < (1e-13 if T is np.float64 else 1e-6)
+
+
+@pytest.mark.parametrize("T", [np.float64, np.float32])
+def test_fused_divergence_inside_periodic_step(T):
+    """The time stepper's variant (periodic wrap instead of ghost reads): staged == unstaged == separate."""
+    I = ins()
+    so, sg = make_setups((uniform(128), uniform(32), uniform(16)), ("P", "P", "P"), T=T)
+    ps = I.psolver_spectral(sg)
+    u0 = smooth_vec(so, 61)
+    m = I.RKMethods.RK44(T)
+    res = {}
+    for tag, nofuse, staged in (("fused", None, None), ("fused_unstaged", None, 0), ("separate", 1, None)):
+        with env(INSB200_NO_FUSED_DIVERGENCE=nofuse, INSB200_DIV_STAGED=staged):
+            sp = I.create_stepper(m, setup=sg, psolver=ps, state={"u": I.to_device(sg, u0)}, t=0.0)
+            for _ in range(2):
+                sp = I.timestep_(m, I.navierstokes_, sp, T(2e-3), params=dict(viscosity=1e-3))
+            res[tag] = I.to_host(sp["state"]["u"])
+    tol = 1e-13 if T is np.float64 else 2e-6
+    assert rel_l2(res["fused"], res["separate"]) < tol
+    assert rel_l2(res["fused_unstaged"], res["separate"]) < tol
 
 
 @pytest.mark.parametrize("T", [np.float64, np.float32])

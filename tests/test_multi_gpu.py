@@ -20,15 +20,16 @@ def _ngpu():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("grid,dtype", [((64, 32, 64), "f64"), ((128, 64, 128), "f32")])
-def test_slab_equals_single_gpu(grid, dtype):
+@pytest.mark.parametrize("grid,dtype,case", [((64, 32, 64), "f64", "periodic"), ((128, 64, 128), "f32", "periodic"),
+                                             ((64, 24, 64), "f64", "channel"), ((128, 32, 64), "f32", "channel")])
+def test_slab_equals_single_gpu(grid, dtype, case):
     n = _ngpu()
     if n < 2:
         pytest.skip("needs at least 2 GPUs")
     world = 1 << (n.bit_length() - 1)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "mgpu_worker.py"),
-           "--grid", *map(str, grid), "--dtype", dtype]
+           "--grid", *map(str, grid), "--dtype", dtype, "--case", case]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
     assert r.returncode == 0 and lines and all(l["ok"] for l in lines), r.stdout[-3000:] + r.stderr[-3000:]

@@ -36,9 +36,10 @@ def run(name, sg, ps, state, method, force, params, dt, steps, warm=2):
     ms = e0.elapsed_time(e1) / steps
     prof = ps.plan.profile_read()
     ps.plan.profile_enable(False)
-    umax = I.maxabs(st["state"]["u"], sg)
+    umax = I.maxabs(st["state"]["u"], sg, plan=ps.plan)
     cells = float(np.prod(sg.Np))
-    print(json.dumps({"case": name, "N": list(sg.N), "dtype": sg.dtype.name, "ms_per_step": ms,
+    if sg.rank == 0:
+        print(json.dumps({"case": name, "N": list(sg.N), "dtype": sg.dtype.name, "ms_per_step": ms,
                       "cell_updates_per_s": cells / ms * 1e3, "umax": umax,
                       "groups_ms_per_step": {k: round(v[0] / steps, 3) for k, v in prof.items() if v[1]}}), flush=True)
 
@@ -47,8 +48,19 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", nargs="+", default=["cfg1", "cfg4", "cfg5"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink every extent (tests)")
+    ap.add_argument("--world", type=int, default=1, help="cfg5 only: z-slab decomposition (run under torchrun)")
     a = ap.parse_args()
     import insb200 as I
+
+    rank, nid = 0, None
+    if a.world > 1:
+        import torch.distributed as dist
+
+        rank = int(os.environ["RANK"])
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl")
+        nid = I.share_unique_id()
 
     def sz(n):
         return max(8, int(round(n * a.scale / 2)) * 2)
@@ -81,7 +93,7 @@ def main():
     if "cfg5" in a.cases:  # examples/ChannelFlow.jl:33-167
         n = (sz(1024), sz(512), sz(512))
         x = (np.linspace(0, 4 * np.pi, n[0] + 1), I.tanh_grid(0.0, 2.0, n[1], 1.4), np.linspace(0, 4 * np.pi / 3, n[2] + 1))
-        sg = I.Setup(x, {"u": ((P(), P()), (D(), D()), (P(), P()))})
+        sg = I.Setup(x, {"u": ((P(), P()), (D(), D()), (P(), P()))}, rank=rank, world=a.world, nccl_id=nid)
         ps = I.default_psolver(sg)
         assert ps.kind == "tridiagonal"
 
@@ -91,7 +103,7 @@ def main():
             return 0.05 * np.sin(2 * x) * np.sin(np.pi * y) * np.cos(3 * z) + 0 * (x + y + z)
 
         u = I.velocityfield(sg, U, psolver=ps)
-        run("cfg5 ChannelFlow3D RK44", sg, ps, {"u": u}, I.RKMethods.RK44(), I.navierstokes_,
+        run(f"cfg5 ChannelFlow3D RK44 ({a.world} GPU)", sg, ps, {"u": u}, I.RKMethods.RK44(), I.navierstokes_,
             dict(viscosity=1 / 180, bodyforce=(1.0, 0.0, 0.0)), 1e-4, 3)
 
 
