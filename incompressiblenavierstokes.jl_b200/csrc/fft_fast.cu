@@ -135,16 +135,9 @@ struct LineSmem {
     Cx<T> *buf[2];
 };
 
-struct NoHook {
-    __device__ __forceinline__ void operator()() const {}
-};
-
-// `hook` runs once, right after the barrier of the first exchange (all threads of the block
-// have consumed their input registers by then): the pipelined passes issue the next tile's
-// asynchronous loads there.
-template <typename T, int N, bool INV, int S, int ES, int SH = 3, typename Hook = NoHook>
+template <typename T, int N, bool INV, int S, int ES, int SH = 3>
 __device__ __forceinline__ void fft_stages(Cx<T> (&v)[8], int t, const LineSmem<T> &sm,
-                                           const Cx<T> *__restrict__ tw, int &exch, const Hook &hook = Hook()) {
+                                           const Cx<T> *__restrict__ tw, int &exch) {
     typedef Ops<T> O;
     using Sh = FftShape<N>;
     constexpr int R = Sh::radix(S);
@@ -204,7 +197,6 @@ __device__ __forceinline__ void fft_stages(Cx<T> (&v)[8], int t, const LineSmem<
             }
         }
         __syncthreads();
-        if constexpr (S == 0) hook();
         if constexpr (P % (1 << SH) == 0) {
             const Cx<T> *rd = buf + spx<SH>(t) * ES;
 #pragma unroll
@@ -214,7 +206,7 @@ __device__ __forceinline__ void fft_stages(Cx<T> (&v)[8], int t, const LineSmem<
             for (int m = 0; m < 8; m++) v[m] = buf[spx<SH>(t + P * m) * ES];
         }
         exch++;
-        fft_stages<T, N, INV, S + 1, ES, SH, NoHook>(v, t, sm, tw, exch);
+        fft_stages<T, N, INV, S + 1, ES, SH>(v, t, sm, tw, exch);
     }
 }
 
@@ -337,131 +329,6 @@ __global__ void __launch_bounds__(StridedShape<T, N>::NT, (sizeof(T) == 4 && Str
         const long long step = P * out_sd;
 #pragma unroll
         for (int m = 0; m < 8; m++) op[m * step] = v[m];
-    }
-}
-
-// ----------------------------------------------------------------------------------------
-// Pipelined variant of the strided pass: a persistent block walks over tiles (round robin) and
-// copies the NEXT tile's elements into a private shared-memory staging area with cp.async while
-// the current tile goes through its butterflies and exchanges, so that the memory system stays
-// busy during the compute phases (the plain kernel alternates load -> compute -> store per
-// block and relies on the second resident block for overlap).  Each thread stages and reads
-// back only its own 8 elements: no extra barrier.
-// ----------------------------------------------------------------------------------------
-template <typename T>
-__device__ __forceinline__ void cp_async_cx(Cx<T> *smem_dst, const Cx<T> *gsrc) {
-    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    if constexpr (sizeof(Cx<T>) == 8)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
-    else
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
-
-template <typename T, bool BLK>
-struct StridedAddr {
-    const Cx<T> *ibase;
-    Cx<T> *obase;
-    long long in_sd, out_sd, orel;
-    int kx, other;
-    __device__ __forceinline__ void init(const FastGeom &g, Cx<T> *W, int tdim, int kx_, int other_) {
-        kx = kx_;
-        other = other_;
-        const int odim = tdim == 1 ? 2 : 1;
-        in_sd = g.in_sd >= 0 ? g.in_sd : g.ws[tdim];
-        out_sd = g.out_sd >= 0 ? g.out_sd : g.ws[tdim];
-        const long long in_os = g.in_os >= 0 ? g.in_os : g.ws[odim], out_os = g.out_os >= 0 ? g.out_os : g.ws[odim];
-        const long long xin = (BLK && g.in_grp) ? grp_x<T>(kx) : kx, xout = (BLK && g.out_grp) ? grp_x<T>(kx) : kx;
-        const long long oin = (BLK && g.in_grp == 2) ? grp_row<T>(other, g.m0p) : other * in_os;
-        const long long oout = (BLK && g.out_grp == 2) ? grp_row<T>(other, g.m0p) : other * out_os;
-        ibase = (g.in ? (const Cx<T> *)g.in : W) + xin + (g.D == 3 ? oin : 0);
-        obase = (g.out ? (Cx<T> *)g.out : W) + xout + (g.D == 3 ? oout : 0);
-        orel = xout + oout;
-    }
-    __device__ __forceinline__ const Cx<T> *src(const FastGeom &g, int k) const {
-        if (BLK) {
-            const int kl = k & ((1 << g.in_sh) - 1);
-            return ibase + (long long)(k >> g.in_sh) * g.in_blk +
-                   (g.in_grp == 1 ? grp_row<T>(kl, g.m0p) : (long long)kl * in_sd);
-        }
-        return ibase + k * in_sd;
-    }
-    __device__ __forceinline__ Cx<T> *dst(const FastGeom &g, int k) const {
-        if (BLK) {
-            const int kl = k & ((1 << g.out_sh) - 1);
-            const long long o = g.out_grp == 1 ? grp_row<T>(kl, g.m0p) : (long long)kl * out_sd;
-            if (g.use_outp) return reinterpret_cast<Cx<T> *>(g.outp[k >> g.out_sh]) + orel + o;
-            return obase + (long long)(k >> g.out_sh) * g.out_blk + o;
-        }
-        return obase + k * out_sd;
-    }
-};
-
-template <typename T, int N, int MODE, bool BLK>
-__global__ void __launch_bounds__(StridedShape<T, N>::NT, (sizeof(T) == 4 && StridedShape<T, N>::NT <= 512) ? 2 : 1)
-    fft_strided_pipe_kernel(Cx<T> *__restrict__ W, FastGeom g, int tdim, const Cx<T> *__restrict__ tw,
-                            const T *__restrict__ e0, const T *__restrict__ e1, const T *__restrict__ e2, T factor,
-                            int nbx, int ntiles) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    typedef StridedShape<T, N> SS;
-    constexpr int P = SS::P, L = SS::L, NT = SS::NT;
-    const int l = threadIdx.x % L, t = threadIdx.x / L;
-    LineSmem<T> sm;
-    sm.buf[0] = reinterpret_cast<Cx<T> *>(smem_raw) + l;
-    sm.buf[1] = sm.buf[0] + L * SS::BUF;
-    Cx<T> *stage = reinterpret_cast<Cx<T> *>(smem_raw + SS::smem) + threadIdx.x;
-    int tile = blockIdx.x;
-    StridedAddr<T, BLK> A;
-    if (tile < ntiles) {
-        A.init(g, W, tdim, (tile % nbx) * L + l, tile / nbx);
-#pragma unroll
-        for (int m = 0; m < 8; m++) cp_async_cx<T>(stage + m * NT, A.src(g, t + P * m));
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    int exch = 0;
-    for (; tile < ntiles; tile += gridDim.x) {
-        A.init(g, W, tdim, (tile % nbx) * L + l, tile / nbx);
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        Cx<T> v[8];
-#pragma unroll
-        for (int m = 0; m < 8; m++) v[m] = stage[m * NT];
-        const int next = tile + gridDim.x;
-        auto prefetch = [&]() {
-            if (next < ntiles) {
-                StridedAddr<T, BLK> B;
-                B.init(g, W, tdim, (next % nbx) * L + l, next / nbx);
-#pragma unroll
-                for (int m = 0; m < 8; m++) cp_async_cx<T>(stage + m * NT, B.src(g, t + P * m));
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        T f[8];
-        if (MODE >= 2) {
-            const int kx = A.kx, other = A.other;
-#pragma unroll
-            for (int m = 0; m < 8; m++) {
-                int k = t + P * m;
-                T den;
-                bool zero;
-                if (g.D == 3) {
-                    int k1 = tdim == 1 ? k : other + g.eig_off, k2 = tdim == 1 ? other + g.eig_off : k;
-                    den = (e0[kx] + e1[k1]) + e2[k2];
-                    zero = (kx | k1 | k2) == 0;
-                } else {
-                    den = e0[kx] + e1[k];
-                    zero = (kx | k) == 0;
-                }
-                f[m] = zero ? T(0) : factor / den;
-            }
-        }
-        if (MODE == 0 || MODE >= 2) fft_stages<T, N, false, 0, L, 3>(v, t, sm, tw, exch, prefetch);
-        if (MODE >= 2) {
-#pragma unroll
-            for (int m = 0; m < 8; m++) v[m] = Ops<T>::scale(v[m], f[m]);
-        }
-        if (MODE == 1) fft_stages<T, N, true, 0, L, 3>(v, t, sm, tw, exch, prefetch);
-        if (MODE >= 2) fft_stages<T, N, true, 0, L>(v, t, sm, tw, exch);
-#pragma unroll
-        for (int m = 0; m < 8; m++) *A.dst(g, t + P * m) = v[m];
     }
 }
 
@@ -894,32 +761,11 @@ static int fast_pass_n(int kind, T *R, Cx<T> *W, const FastGeom &g, int tdim, co
         }
         const bool blk = g.in_sh < 30 || g.out_sh < 30 || g.use_outp || g.in_grp || g.out_grp;
         dim3 grid(g.m0p / SS::L, g.D == 3 ? (g.nother >= 0 ? g.nother : g.n[tdim == 1 ? 2 : 1]) : 1);
-        const char *pe = getenv("INSB200_FFT_PIPELINE");  // bit 0: forward/inverse passes, bit 1: middle pass
-        const int pipe = pe ? atoi(pe) : 0;
-        constexpr size_t psmem = SS::smem + (size_t)8 * SS::NT * sizeof(Cx<T>);
-        if (((kind == 2 && (pipe & 2)) || (kind < 2 && (pipe & 1))) && psmem <= 227 * 1024) {
-            auto kern = kind == 0 ? (blk ? fft_strided_pipe_kernel<T, N, 0, true> : fft_strided_pipe_kernel<T, N, 0, false>)
-                        : kind == 1 ? (blk ? fft_strided_pipe_kernel<T, N, 1, true> : fft_strided_pipe_kernel<T, N, 1, false>)
-                                    : (blk ? fft_strided_pipe_kernel<T, N, 2, true> : fft_strided_pipe_kernel<T, N, 2, false>);
-            INSB_TRY(allow_smem(kern, psmem));
-            INSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                           cudaSharedmemCarveoutMaxShared));
-            int occ = 0, dev = 0, sms = 0;
-            INSB_CUDA(cudaGetDevice(&dev));
-            INSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-            INSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SS::NT, psmem));
-            if (occ < 1) occ = 1;
-            const int nbx = (int)grid.x, ntiles = (int)(grid.x * grid.y);
-            const int blocks = ntiles < occ * sms ? ntiles : occ * sms;
-            if (getenv("INSB200_DEBUG")) fprintf(stderr, "[insb200] pipelined strided pass N=%d kind=%d: %d blocks/SM, %d blocks, %zu B smem\n", N, kind, occ, blocks, psmem);
-            kern<<<blocks, SS::NT, psmem, L.stream>>>(W, g, tdim, tw, e0, e1, e2, factor, nbx, ntiles);
-        } else {
-            auto kern = kind == 0 ? (blk ? fft_strided_kernel<T, N, 0, true> : fft_strided_kernel<T, N, 0, false>)
-                        : kind == 1 ? (blk ? fft_strided_kernel<T, N, 1, true> : fft_strided_kernel<T, N, 1, false>)
-                                    : (blk ? fft_strided_kernel<T, N, 2, true> : fft_strided_kernel<T, N, 2, false>);
-            INSB_TRY(allow_smem(kern, SS::smem));
-            kern<<<grid, SS::NT, SS::smem, L.stream>>>(W, g, tdim, tw, e0, e1, e2, factor);
-        }
+        auto kern = kind == 0 ? (blk ? fft_strided_kernel<T, N, 0, true> : fft_strided_kernel<T, N, 0, false>)
+                    : kind == 1 ? (blk ? fft_strided_kernel<T, N, 1, true> : fft_strided_kernel<T, N, 1, false>)
+                                : (blk ? fft_strided_kernel<T, N, 2, true> : fft_strided_kernel<T, N, 2, false>);
+        INSB_TRY(allow_smem(kern, SS::smem));
+        kern<<<grid, SS::NT, SS::smem, L.stream>>>(W, g, tdim, tw, e0, e1, e2, factor);
     } else if (kind >= 5) {  // strided DCT
         typedef StridedShape<T, N> SS;
         if (g.m0p % SS::L || !g.dw || !g.dwi) {
@@ -936,10 +782,10 @@ static int fast_pass_n(int kind, T *R, Cx<T> *W, const FastGeom &g, int tdim, co
         long long npairs = (long long)(g.n[1] / 2) * (g.D == 3 ? g.n[2] : 1);
         unsigned blocks = (unsigned)((npairs + XS::LP - 1) / XS::LP);
         typedef XDivShape<T, N> XD;
-        const char *sd = getenv("INSB200_DIV_STAGED");
-        // staged variant: whole blocks inside one z plane, even row length (8-byte aligned row
-        // starts), 8-byte aligned base and component stride
-        const bool staged = kind == 3 && g.div_u && (sd == nullptr || atoi(sd) != 0) && XD::smem <= 200 * 1024 &&
+        const char *sd = getenv("INSB200_FUSED_DIVERGENCE");
+        // staged variant (INSB200_FUSED_DIVERGENCE=2): whole blocks inside one z plane, even row length
+        // (8-byte aligned row starts), 8-byte aligned base and component stride
+        const bool staged = kind == 3 && g.div_u && sd != nullptr && atoi(sd) == 2 && XD::smem <= 200 * 1024 &&
                             (g.n[1] / 2) % XD::LP == 0 && g.rs[1] % 2 == 0 && (g.rs[2] % 2 == 0 || g.D == 2) &&
                             g.div_cs % 2 == 0 && ((uintptr_t)((const T *)g.div_u - 1)) % 8 == 0;
         if (staged) {

@@ -1318,8 +1318,13 @@ static int solve_t(Poisson *ps, T *p, Launch L, const DivSource *div) {
     return 0;
 }
 
+// Opt-in (INSB200_FUSED_DIVERGENCE=1: per-thread loads, =2: shared-memory staged rows).  Measured
+// on B200 at 512^3 Float32 the fused pass (0.65-0.72 ms, latency-bound behind the FFT's barriers)
+// is no faster than divergence_kernel (0.37 ms, 5.7 TB/s) + the plain R2C pass (0.24 ms), so the
+// separate kernels stay the default; profiles/r1d_ncu_full_summary.md.
 bool poisson_fuses_divergence(const Poisson *ps) {
-    return ps && (ps->fast || ps->fast_dct || ps->fast_tri) && getenv("INSB200_NO_FUSED_DIVERGENCE") == nullptr;
+    const char *e = getenv("INSB200_FUSED_DIVERGENCE");
+    return ps && (ps->fast || ps->fast_dct || ps->fast_tri) && e != nullptr && atoi(e) > 0;
 }
 
 int poisson_solve(Poisson *ps, void *p, Launch L, const DivSource *div) {

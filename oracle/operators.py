@@ -12,6 +12,17 @@ from __future__ import annotations
 
 import numpy as np
 
+# "numpy": the slicing restatement below (default, what the parity tests compare against);
+# "c": the stencil operators run through oracle/c (cell-by-cell C/OpenMP restatement, the
+# multithreaded CPU baseline of bench.py).  Both give the same IEEE results.
+BACKEND = "numpy"
+
+
+def _c():
+    from . import ckernels
+
+    return ckernels
+
 
 # ---------------------------------------------------------------------------
 # helpers
@@ -142,24 +153,32 @@ def _contract_tensor_add(setup, f, term):
 # ---------------------------------------------------------------------------
 def convection_(f, u, setup):
     """convection! (operators.jl:407-416): adds to f."""
+    if BACKEND == "c":
+        return _c().convdiff_add(f, u, setup, 0.0, conv=True, diff=False)
     sig = lambda i, j, off: convstress(setup, u, i, j, off)
     return _contract_tensor_add(setup, f, lambda i, j: tensordivergence(setup, sig, i, j))
 
 
 def diffusion_(f, u, setup, visc):
     """diffusion! (operators.jl:545-554): adds to f."""
+    if BACKEND == "c":
+        return _c().convdiff_add(f, u, setup, visc, conv=False, diff=True)
     sig = lambda i, j, off: diffstress(setup, u, visc, i, j, off)
     return _contract_tensor_add(setup, f, lambda i, j: tensordivergence(setup, sig, i, j))
 
 
 def convectiondiffusion_(f, u, setup, visc):
     """convectiondiffusion! (operators.jl:616-628): adds to f."""
+    if BACKEND == "c":
+        return _c().convdiff_add(f, u, setup, visc)
     sig = lambda i, j, off: convdiffstress(setup, u, visc, i, j, off)
     return _contract_tensor_add(setup, f, lambda i, j: tensordivergence(setup, sig, i, j))
 
 
 def divergence_(div, u, setup):
     """divergence! (operators.jl:242-247, contract_vector! :90-100)."""
+    if BACKEND == "c":
+        return _c().divergence(div, u, setup)
     D = setup.D
     z = _zero(D)
     s = delta_u(setup, u, 0, 0, z) + delta_u(setup, u, 1, 1, z)
@@ -171,6 +190,8 @@ def divergence_(div, u, setup):
 
 def scalewithvolume_(p, setup):
     """scalewithvolume! (operators.jl:218-231): WHOLE array, p *= (Δx*Δy)*Δz."""
+    if BACKEND == "c":
+        return _c().scalewithvolume(p, setup)
     D = setup.D
     dx = setup.Delta[0].reshape((-1,) + (1,) * (D - 1))
     dy = setup.Delta[1].reshape((1, -1) + (1,) * (D - 2))
@@ -191,6 +212,8 @@ def pressuregradient_(G, p, setup):
 
 def applypressure_(u, p, setup):
     """applypressure! (operators.jl:306-311): u[I,i] += -δ(p,i,I)."""
+    if BACKEND == "c":
+        return _c().applypressure(u, p, setup)
     z = _zero(setup.D)
     for i in range(setup.D):
         u[_sl(setup, z, i)] += -delta_p(setup, p, i, z)

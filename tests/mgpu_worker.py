@@ -36,7 +36,7 @@ def main():
     ap.add_argument("--grid", type=int, nargs=3, default=[64, 32, 64])
     ap.add_argument("--dtype", default="f64")
     ap.add_argument("--steps", type=int, default=2)
-    ap.add_argument("--case", default="periodic", choices=["periodic", "channel"],
+    ap.add_argument("--case", default="periodic", choices=["periodic", "channel", "both"],
                     help="periodic: psolver_spectral; channel: no-slip walls in y on a tanh-stretched grid, "
                          "psolver_tridiagonal (BASELINE config 5 shape)")
     args = ap.parse_args()
@@ -44,6 +44,16 @@ def main():
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dist.init_process_group("nccl")
+    ok = True
+    for case in (["periodic", "channel"] if args.case == "both" else [args.case]):
+        ok = run_case(args, case, rank, world) and ok
+    flag = torch.tensor([0 if ok else 1], device="cuda")
+    dist.all_reduce(flag)
+    dist.destroy_process_group()
+    sys.exit(1 if int(flag.item()) else 0)
+
+
+def run_case(args, case, rank, world):
     import insb200 as I
 
     T = np.float64 if args.dtype == "f64" else np.float32
@@ -52,7 +62,7 @@ def main():
     x = tuple(np.linspace(0.0, 1.0, m + 1).astype(T) for m in n)
     bcs = {"u": ((I.PeriodicBC(), I.PeriodicBC()),) * 3}
     mk = I.psolver_spectral
-    if args.case == "channel":
+    if case == "channel":
         import oracle as O
 
         x = (np.linspace(0.0, 4.0, n[0] + 1).astype(T), O.tanh_grid(0, 2, n[1], 1.4).astype(T),
@@ -127,12 +137,9 @@ def main():
             m1 = I.maxabs(st["state"]["u"], s1)
             report(name + "_umax", abs(res[name + "_umax"] - m1) / m1, 1e-6)
         for o in out:
-            o.update(world=world, n=n, dtype=args.dtype, case=args.case)
+            o.update(world=world, n=n, dtype=args.dtype, problem=case)
             print(json.dumps(o), flush=True)
-    flag = torch.tensor([0 if ok else 1], device="cuda")
-    dist.all_reduce(flag)
-    dist.destroy_process_group()
-    sys.exit(1 if int(flag.item()) else 0)
+    return ok
 
 
 if __name__ == "__main__":

@@ -1,4 +1,4 @@
-"""GPU: every optimised kernel variant against the plain variant it replaces (same library,
+"""GPU: every alternative kernel variant against the default variant (same library,
 switched with the INSB200_* environment variables the launchers read at call time), plus the
 host-buffer ensemble entry point against device-resident stepping.  The oracle comparisons of
 the default variants live in test_gpu_parity.py."""
@@ -41,32 +41,6 @@ def env(**kw):
                 os.environ[k] = v
 
 
-PIPE_CASES = [
-    ("s3_64_32_128", (uniform(64), uniform(32), uniform(128)), ("P", "P", "P"), "spectral"),
-    ("s3_32_512_64", (uniform(32), uniform(512), uniform(64)), ("P", "P", "P"), "spectral"),
-    ("s3_128_64_1024", (uniform(128), uniform(64), uniform(1024)), ("P", "P", "P"), "spectral"),
-    ("s2_256_2048", (uniform(256), uniform(2048)), ("P", "P"), "spectral"),
-    ("t3_64_32_128", (uniform(64, 4.0), O.tanh_grid(0, 2, 32, 1.4), uniform(128, 2.0)), ("P", "D", "P"), "tridiagonal"),
-]
-
-
-@pytest.mark.parametrize("T", [np.float64, np.float32])
-@pytest.mark.parametrize("name,x,bcs,kind", PIPE_CASES)
-def test_pipelined_fft_passes_bit_identical(name, x, bcs, kind, T):
-    """cp.async-pipelined persistent strided passes == plain strided passes, bit for bit."""
-    I = ins()
-    so, sg = make_setups(x, bcs, T=T)
-    mk = {"spectral": I.psolver_spectral, "tridiagonal": I.psolver_tridiagonal}[kind]
-    ps = mk(sg)
-    f = random_scal(so, 5)
-    with env(INSB200_FFT_PIPELINE=0):
-        a = I.to_host(ps(I.to_device(sg, f)))
-    for mode in (1, 2, 3):
-        with env(INSB200_FFT_PIPELINE=mode):
-            b = I.to_host(ps(I.to_device(sg, f)))
-        assert np.array_equal(a, b), (name, mode, rel_l2(b, a))
-
-
 FUSE_CASES = [
     ("periodic3", (uniform(32), uniform(64, 2.0), uniform(32, 0.5)), ("P", "P", "P"), "spectral"),
     ("periodic2", (uniform(64), uniform(32)), ("P", "P"), "spectral"),
@@ -97,8 +71,8 @@ def test_fused_divergence_matches_separate_pass(name, x, bcs, kind, T):
     u = smooth_vec(so, 31)
     want = opr.project(u.copy(order="F"), so, ps_o)
     out = {}
-    for tag, nofuse, staged in (("fused", None, None), ("fused_unstaged", None, 0), ("separate", 1, None)):
-        with env(INSB200_NO_FUSED_DIVERGENCE=nofuse, INSB200_DIV_STAGED=staged):
+    for tag, fuse in (("fused", 2), ("fused_unstaged", 1), ("separate", None)):
+        with env(INSB200_FUSED_DIVERGENCE=fuse):
             ud = I.to_device(sg, u)
             I.project_(ud, sg, psolver=ps_g, p=I.scalarfield(sg))
             out[tag] = I.to_host(ud)
@@ -119,8 +93,8 @@ def test_fused_divergence_inside_periodic_step(T):
     u0 = smooth_vec(so, 61)
     m = I.RKMethods.RK44(T)
     res = {}
-    for tag, nofuse, staged in (("fused", None, None), ("fused_unstaged", None, 0), ("separate", 1, None)):
-        with env(INSB200_NO_FUSED_DIVERGENCE=nofuse, INSB200_DIV_STAGED=staged):
+    for tag, fuse in (("fused", 2), ("fused_unstaged", 1), ("separate", None)):
+        with env(INSB200_FUSED_DIVERGENCE=fuse):
             sp = I.create_stepper(m, setup=sg, psolver=ps, state={"u": I.to_device(sg, u0)}, t=0.0)
             for _ in range(2):
                 sp = I.timestep_(m, I.navierstokes_, sp, T(2e-3), params=dict(viscosity=1e-3))

@@ -19,7 +19,6 @@ def main():
     ap.add_argument("--grid", type=int, nargs=3, default=[512, 512, 512])
     ap.add_argument("--dtype", default="f32")
     ap.add_argument("--reps", type=int, default=20)
-    ap.add_argument("--pipeline", type=int, nargs="+", default=[0], help="INSB200_FFT_PIPELINE modes to time")
     a = ap.parse_args()
     import insb200 as I
 
@@ -31,8 +30,7 @@ def main():
     p = I.scalarfield(sg)
     p.normal_()
     cells = float(np.prod(a.grid))
-    for mode in a.pipeline:  # INSB200_FFT_PIPELINE is read at every launch
-        os.environ["INSB200_FFT_PIPELINE"] = str(mode)
+    for mode in [0]:
         for _ in range(3):
             ps(p)
         torch.cuda.synchronize()
@@ -42,7 +40,7 @@ def main():
             ps(p)
         prof = ps.plan.profile_read()
         ps.plan.profile_enable(False)
-        print(f"# INSB200_FFT_PIPELINE={mode} grid {a.grid} {a.dtype}")
+        print(f"# grid {a.grid} {a.dtype}")
         for k in ("poisson", "fft_x_r2c", "fft_y_fwd", "fft_z_mid", "fft_y_inv", "fft_x_c2r"):
             ms = prof[k][0] / max(prof[k][1], 1)
             byt = (10 if k == "poisson" else 2) * w * cells
