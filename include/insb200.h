@@ -181,6 +181,30 @@ int insb200_step_rk_host_ensemble(insb200_plan_t *plan, const double *A, const d
                                   int nmembers, double t, double dt, int nsteps,
                                   const insb200_params_t *params, void *stream);
 
+/* solve_unsteady (src/solver.jl:77-149): the time loop itself, so that a run of many small steps
+ * does not return to the host language per step.
+ *   method 0: explicit Runge-Kutta with the tableau (A, c, s, coef_dtype) of insb200_step_rk;
+ *   method 1: LMWray3 (A, c ignored).
+ *   dt > 0: fixed step, rounded so that (tend - tstart) / dt is an integer (:123-132); with
+ *     use_graph != 0 (single GPU) the step is captured into a CUDA graph once and replayed;
+ *   dt <= 0: adaptive (:98-122): every n_adapt_dt steps dt = cfl * propose_timestep, raised to
+ *     dt_min when dt_min > 0; a proposal < 1e-10, > 100 or NaN stops the loop with the status
+ *     INSB200_STOPPED_BAD_DT (the reference warns and breaks); the last step is clipped to tend.
+ *   time_dtype: INSB200_F32/F64, the type t and dt arithmetic is evaluated in (typeof(tlims)).
+ *   callback: called after every step whose number n is a multiple of callback_every
+ *     (0 = never) -- the reference's processors observe the state after every step and act every
+ *     `nupdate` steps (src/processors.jl:45-80), so pass the gcd of their nupdate.  The state is
+ *     ordered on `stream` when the callback runs; a non-zero return value ends the loop.
+ * Outputs: final time and the number of steps taken. */
+#define INSB200_STOPPED_BAD_DT 2
+typedef int (*insb200_step_callback_t)(void *user, long long n, double t);
+int insb200_solve_unsteady(insb200_plan_t *plan, int method, const double *A, const double *c, int s,
+                           int coef_dtype, void *u, void *temp, double tstart, double tend, double dt,
+                           double dt_min, double cfl, int n_adapt_dt, int time_dtype,
+                           const insb200_params_t *params, int callback_every,
+                           insb200_step_callback_t callback, void *user, int use_graph, double *t_out,
+                           long long *n_out, void *stream);
+
 /* right_hand_side!(dudt, u, params_ref, t) (src/sciml.jl:35-48). */
 int insb200_right_hand_side(insb200_plan_t *plan, void *dudt, const void *u, double t,
                             const insb200_params_t *params, void *stream);

@@ -45,6 +45,7 @@ struct insb200_plan : public insb::Profiler {
     void *HU = nullptr, *HT = nullptr;  // device state of the host-buffer entry point
     void *HU2 = nullptr, *HT2 = nullptr;  // second slot of the pipelined ensemble entry point
     cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of the ensemble entry point
+    cudaStream_t s_graph = nullptr;                // capture / replay stream of insb200_solve_unsteady
     double *scratch = nullptr;  // reductions
     long long bytes = 0;
     long long launches = 0;
@@ -686,6 +687,7 @@ int insb200_plan_destroy(insb200_plan_t *pl) {
         if (p) cudaFree(p);
     if (pl->s_in) cudaStreamDestroy(pl->s_in);
     if (pl->s_out) cudaStreamDestroy(pl->s_out);
+    if (pl->s_graph) cudaStreamDestroy(pl->s_graph);
     for (void *p : pl->K) cudaFree(p);
     for (void *p : pl->TK) cudaFree(p);
     for (auto &b : pl->brackets) {
@@ -936,6 +938,136 @@ int insb200_step_rk_host_ensemble(insb200_plan_t *pl, const double *A, const dou
     INSB_CUDA(e1);
     INSB_CUDA(e2);
     return 0;
+    API_END
+}
+
+// solve_unsteady (src/solver.jl:77-149): the whole time loop inside the library.
+int insb200_solve_unsteady(insb200_plan_t *pl, int method, const double *A, const double *c, int s, int coef_dtype,
+                           void *u, void *temp, double tstart, double tend, double dt, double dt_min, double cfl,
+                           int n_adapt_dt, int time_dtype, const insb200_params_t *pr, int callback_every,
+                           insb200_step_callback_t cb, void *user, int use_graph, double *t_out, long long *n_out,
+                           void *stream) {
+    API_BEGIN
+    if (method != 0 && method != 1) {
+        set_error("solve_unsteady: method must be 0 (explicit Runge-Kutta tableau) or 1 (LMWray3)");
+        return 1;
+    }
+    if (method == 0 && (!A || !c)) {
+        set_error("solve_unsteady: the Runge-Kutta method needs its tableau");
+        return 1;
+    }
+    const bool tf32 = time_dtype == INSB200_F32;
+    // t, Δt arithmetic in the caller's time type (the reference keeps typeof(tstart), typeof(Δt))
+    auto R = [&](double v) { return tf32 ? (double)(float)v : v; };
+    auto step = [&](void *st, double t, double h) -> int {
+        if (method == 1) return insb200_step_lmwray3(pl, u, temp, t, h, pr, st);
+        return insb200_step_rk(pl, A, c, s, coef_dtype, u, temp, t, h, pr, st);
+    };
+    double t = tstart;
+    long long n = 0;
+    int rc = 0;
+    bool stop = false;
+    auto notify = [&]() {
+        if (cb && callback_every > 0 && n % callback_every == 0 && cb(user, n, t) != 0) stop = true;
+    };
+    if (dt <= 0) {  // adaptive: CFL every n_adapt_dt steps, last step clipped to tend (:98-122)
+        if (n_adapt_dt < 1) n_adapt_dt = 1;
+        double h = 0;
+        while (t < tend && !stop) {
+            if (n % n_adapt_dt == 0) {
+                double prop;
+                INSB_TRY(insb200_cfl(pl, u, pr, &prop, stream));
+                h = pl->f64 ? cfl * prop : (double)((float)cfl * (float)prop);  // cfl and the proposal are eltype(u)
+                if (dt_min > 0) h = std::fmax(h, dt_min);
+                if (h < 1e-10 || h > 100 || std::isnan(h)) {
+                    set_error("Proposed time step " + std::to_string(h) + " is out of bounds. Stopping simulation.");
+                    rc = INSB200_STOPPED_BAD_DT;
+                    break;
+                }
+            }
+            const double hs = std::fmin(h, R(tend - t));
+            INSB_TRY(step(stream, t, hs));
+            t = R(t + hs);
+            n++;
+            notify();
+        }
+    } else {  // fixed: Δt rounded so that (tend - tstart) / Δt is an integer (:123-132)
+        const long long nstep = std::llround(R(tend - tstart) / dt);
+        if (nstep < 1) {
+            set_error("solve_unsteady: (tend - tstart) / dt rounds to zero steps");
+            return 1;
+        }
+        const double h = R(R(tend - tstart) / (double)nstep);
+        cudaStream_t user_st = (cudaStream_t)stream;
+        const bool graph = use_graph && !pl->comm && !pl->prof && nstep > 2;
+        if (!graph) {
+            for (long long it = 0; it < nstep && !stop; it++) {
+                INSB_TRY(step(stream, t, h));
+                t = R(t + h);
+                n++;
+                notify();
+            }
+        } else {
+            // one eager step (allocations, function attributes), then the step is captured once and
+            // replayed: the launch-bound small grids (config 1: 256^2) stop paying per-kernel launches.
+            // The legacy default stream cannot be captured: run on a private stream ordered after it.
+            if (!pl->s_graph) INSB_CUDA(cudaStreamCreateWithFlags(&pl->s_graph, cudaStreamNonBlocking));
+            cudaEvent_t ev;
+            INSB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            auto handoff = [&](cudaStream_t from, cudaStream_t to) -> int {
+                INSB_CUDA(cudaEventRecord(ev, from));
+                INSB_CUDA(cudaStreamWaitEvent(to, ev, 0));
+                return 0;
+            };
+            INSB_TRY(step(stream, t, h));
+            t = R(t + h);
+            n++;
+            notify();
+            INSB_TRY(handoff(user_st, pl->s_graph));
+            const long long l0 = pl->launches;
+            cudaGraph_t g = nullptr;
+            cudaGraphExec_t ge = nullptr;
+            INSB_CUDA(cudaStreamBeginCapture(pl->s_graph, cudaStreamCaptureModeThreadLocal));
+            int src = step((void *)pl->s_graph, t, h);
+            cudaError_t ce = cudaStreamEndCapture(pl->s_graph, &g);
+            const long long per_step = pl->launches - l0;
+            pl->launches = l0;
+            if (src || ce != cudaSuccess || !g) {
+                if (g) cudaGraphDestroy(g);
+                cudaEventDestroy(ev);
+                if (!src) set_error(std::string("CUDA graph capture of the time step failed: ") + cudaGetErrorString(ce));
+                return 1;
+            }
+            ce = cudaGraphInstantiate(&ge, g, 0);
+            if (ce != cudaSuccess) {
+                cudaGraphDestroy(g);
+                cudaEventDestroy(ev);
+                set_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
+                return 1;
+            }
+            for (long long it = 1; it < nstep && !stop; it++) {
+                ce = cudaGraphLaunch(ge, pl->s_graph);
+                if (ce != cudaSuccess) break;
+                pl->launches += per_step;
+                t = R(t + h);
+                n++;
+                if (cb && callback_every > 0 && n % callback_every == 0) {
+                    rc = handoff(pl->s_graph, user_st);  // the callback sees the state on the caller's stream
+                    if (rc) break;
+                    notify();
+                }
+            }
+            int hrc = handoff(pl->s_graph, user_st);
+            cudaGraphExecDestroy(ge);
+            cudaGraphDestroy(g);
+            cudaEventDestroy(ev);
+            INSB_CUDA(ce);
+            if (rc || hrc) return 1;
+        }
+    }
+    if (t_out) *t_out = t;
+    if (n_out) *n_out = n;
+    return rc;
     API_END
 }
 

@@ -94,6 +94,12 @@ _PROTOTYPES = {
         [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_int, C.POINTER(C.c_void_p),
          C.POINTER(C.c_void_p), C.c_int, C.c_double, C.c_double, C.c_int, C.POINTER(ParamsStruct), _P],
     ),
+    "insb200_solve_unsteady": (
+        C.c_int,
+        [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_int, _P, _P, C.c_double, C.c_double,
+         C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.POINTER(ParamsStruct), C.c_int, _P, _P, C.c_int,
+         C.POINTER(C.c_double), C.POINTER(C.c_longlong), _P],
+    ),
     "insb200_right_hand_side": (C.c_int, [_P, _P, _P, C.c_double, C.POINTER(ParamsStruct), _P]),
     "insb200_cfl": (C.c_int, [_P, _P, C.POINTER(ParamsStruct), C.POINTER(C.c_double), _P]),
     "insb200_maxabs": (C.c_int, [_P, _P, C.POINTER(C.c_double), _P]),

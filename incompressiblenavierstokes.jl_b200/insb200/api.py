@@ -500,8 +500,9 @@ class Observable:
 
 
 class processor:
-    def __init__(self, initialize, finalize=lambda initialized, state: initialized):
+    def __init__(self, initialize, finalize=lambda initialized, state: initialized, nupdate=1):
         self.initialize, self.finalize = initialize, finalize
+        self.nupdate = int(nupdate)  # the observers only act on steps that are multiples of this
 
 
 def timelogger(setup, nupdate=1, out=None):
@@ -523,7 +524,7 @@ def timelogger(setup, nupdate=1, out=None):
         state.on(cb)
         return log
 
-    return processor(initialize)
+    return processor(initialize, nupdate=nupdate)
 
 
 def fieldsaver(setup, nupdate=1):
@@ -540,12 +541,57 @@ def fieldsaver(setup, nupdate=1):
         cb(state.value)
         return states
 
-    return processor(initialize)
+    return processor(initialize, nupdate=nupdate)
+
+
+_STEP_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_longlong, C.c_double)
+
+
+def _solve_native(setup, method, force, stepper, tend, dt, dt_min, cfl, n_adapt_dt, params, obs, every, graph):
+    """The time loop inside the library (insb200_solve_unsteady): one call for the whole run,
+    a CUDA-graph replay per step for fixed dt on one GPU, call-backs only every `every` steps."""
+    import math
+    import warnings
+
+    psolver, state = stepper["psolver"], stepper["state"]
+    pr = _force_params(force, setup, params)
+    u = _chk(setup, state["u"], True)
+    temp = _chk(setup, state["temp"], False) if "temp" in state and pr.boussinesq else None
+    tstart = stepper["t"]
+    adaptive = dt is None
+    tT = setup.T if adaptive else (np.dtype(type(dt)).type if isinstance(dt, np.floating) else np.float64)
+    is_wray = isinstance(method, LMWray3)
+    s = 0 if is_wray else len(method.b)
+    A = None if is_wray else (C.c_double * (s * s))(*[float(v) for v in np.asarray(method.A).reshape(-1)])
+    cc = None if is_wray else (C.c_double * s)(*[float(v) for v in method.c])
+    coef = _lib.F64 if is_wray else _coef_dtype(method.T, setup.T(0) if adaptive else dt)
+
+    def on_step(_user, n, t):
+        stepper["t"], stepper["n"] = tT(t), int(n)
+        obs.value = get_state(stepper)
+        return 0
+
+    cb = _STEP_CB(on_step)
+    t_out, n_out = C.c_double(), C.c_longlong()
+    rc = lib().insb200_solve_unsteady(
+        psolver.plan.h, int(is_wray), A, cc, s, coef, _ptr(u), _ptr(temp), float(tstart), float(tend),
+        -1.0 if adaptive else float(dt), -1.0 if dt_min is None else float(dt_min), float(cfl), int(n_adapt_dt),
+        _lib.F32 if tT is np.float32 else _lib.F64, C.byref(pr), int(every), C.cast(cb, C.c_void_p), None, int(graph),
+        C.byref(t_out), C.byref(n_out), _stream())
+    if rc == 2:  # INSB200_STOPPED_BAD_DT: the reference warns and leaves the loop (solver.jl:113-116)
+        warnings.warn(lib().insb200_last_error().decode())
+    else:
+        check(rc)
+    stepper["t"], stepper["n"] = tT(t_out.value), int(n_out.value)
+    if every == 0 or stepper["n"] % max(every, 1):
+        obs.value = get_state(stepper)  # final state for finalize()
+    return stepper
 
 
 def solve_unsteady(*, setup, tlims, start, force=navierstokes_, docopy=True, method=None, psolver=None,
-                   dt=None, dt_min=None, cfl=None, n_adapt_dt=1, processors=None, params):
-    """solve_unsteady (src/solver.jl:77-149)."""
+                   dt=None, dt_min=None, cfl=None, n_adapt_dt=1, processors=None, params, native=True, graph=True):
+    """solve_unsteady (src/solver.jl:77-149).  native=True runs the loop inside the library
+    (insb200_solve_unsteady); native=False steps from Python, one library call per step."""
     T = setup.T
     method = method if method is not None else LMWray3(T)
     psolver = psolver if psolver is not None else default_psolver(setup)
@@ -556,7 +602,15 @@ def solve_unsteady(*, setup, tlims, start, force=navierstokes_, docopy=True, met
     obs = Observable(get_state(stepper))
     processors = processors or {}
     initialized = {k: p.initialize(obs) for k, p in processors.items()}
-    if dt is None:
+    if native and force in (navierstokes_, boussinesq_):
+        import math
+
+        every = 0
+        for p in processors.values():
+            every = math.gcd(every, max(int(getattr(p, "nupdate", 1)), 1))
+        stepper = _solve_native(setup, method, force, stepper, tend, dt, dt_min, cfl, n_adapt_dt, params, obs, every,
+                                graph)
+    elif dt is None:
         while stepper["t"] < tend:
             if stepper["n"] % n_adapt_dt == 0:
                 dt = cfl * propose_timestep(force, stepper["state"], setup, params, plan=psolver.plan)

@@ -169,3 +169,46 @@ def test_host_ensemble_matches_device_stepping():
                                               float(dt), 2, C.byref(pr), st))
     for h, w in zip(hosts, want):
         assert np.array_equal(I.to_host(h.cuda()), w)
+
+
+@pytest.mark.parametrize("mname", ["RK44", "LMWray3"])
+@pytest.mark.parametrize("adaptive", [False, True])
+def test_native_time_loop_matches_python_loop(mname, adaptive):
+    """insb200_solve_unsteady (loop inside the library, CUDA-graph replay for fixed dt) ==
+    one library call per step driven from Python; processors see the same states."""
+    I = ins()
+    T = np.float64
+    so, sg = make_setups((uniform(32), uniform(32)), ("P", "P"), T=T)
+    ps = I.psolver_spectral(sg)
+    u0 = I.to_device(sg, smooth_vec(so, 71))
+    I.project_(u0, sg, psolver=ps, p=I.scalarfield(sg))
+    I.apply_bc_u_(u0, 0.0, sg)
+    m = I.LMWray3(T) if mname == "LMWray3" else I.RKMethods.RK44(T)
+    kw = dict(setup=sg, tlims=(0.0, 0.1), start={"u": u0}, method=m, psolver=ps, params=dict(viscosity=1e-2))
+    kw.update(dict(cfl=0.5, n_adapt_dt=3) if adaptive else dict(dt=0.004))
+    res = {}
+    for tag, opts in (("python", dict(native=False)), ("native", dict(native=True, graph=False)),
+                      ("graph", dict(native=True, graph=True))):
+        log = []
+        out, outputs = I.solve_unsteady(processors={"log": I.timelogger(sg, nupdate=5, out=log),
+                                                    "save": I.fieldsaver(sg, nupdate=10)}, **kw, **opts)
+        res[tag] = (I.to_host(out["u"]), float(out["t"]), [(e["n"], e["t"], e["umax"]) for e in log],
+                    [(s["n"], s["u"]) for s in outputs["save"]])
+    for tag in ("native", "graph"):
+        assert np.array_equal(res[tag][0], res["python"][0]), tag
+        assert res[tag][1] == res["python"][1]
+        assert res[tag][2] == res["python"][2], tag
+        assert len(res[tag][3]) == len(res["python"][3])
+        for (na, ua), (nb, ub) in zip(res[tag][3], res["python"][3]):
+            assert na == nb and np.array_equal(ua, ub)
+    assert abs(res["python"][1] - 0.1) < 1e-12
+
+
+def test_native_time_loop_stops_on_bad_dt():
+    I = ins()
+    so, sg = make_setups((uniform(16), uniform(16)), ("P", "P"))
+    ps = I.psolver_spectral(sg)
+    u0 = I.vectorfield(sg)  # u = 0 and nu = 1e6: the diffusive limit h^2 / (4 nu) is below 1e-10
+    with pytest.warns(UserWarning, match="out of bounds"):
+        out, _ = I.solve_unsteady(setup=sg, tlims=(0.0, 1.0), start={"u": u0}, psolver=ps, params=dict(viscosity=1e8))
+    assert float(out["t"]) == 0.0

@@ -74,6 +74,21 @@ def main():
         u = I.velocityfield(sg, lambda d, x, y: (-np.sin(x) * np.cos(y) if d == 0 else np.cos(x) * np.sin(y)) + 0 * x * y,
                             psolver=ps)
         run("cfg1 TGV2D RK44", sg, ps, {"u": u}, I.RKMethods.RK44(), I.navierstokes_, dict(viscosity=5e-4), 0.02, 100)
+        # the whole 100-step run through solve_unsteady: Python loop, native loop, native loop + CUDA graph
+        import time
+
+        for tag, opts in (("python loop", dict(native=False)), ("native loop", dict(native=True, graph=False)),
+                          ("native loop + CUDA graph", dict(native=True, graph=True))):
+            best = 1e9
+            for _ in range(3):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                out, _ = I.solve_unsteady(setup=sg, tlims=(0.0, 2.0), start={"u": u}, method=I.RKMethods.RK44(),
+                                          psolver=ps, dt=0.02, params=dict(viscosity=5e-4), **opts)
+                torch.cuda.synchronize()
+                best = min(best, time.perf_counter() - t0)
+            print(json.dumps({"case": f"cfg1 TGV2D RK44 solve_unsteady 100 steps, {tag}", "wall_ms_per_step": best * 10,
+                              "cell_updates_per_s": n * n * 100 / best}), flush=True)
     if "cfg4" in a.cases:  # examples/RayleighBenard3D.jl:23-79
         for T in (np.float64, np.float32):
             n = (sz(512), sz(512), sz(256))
