@@ -362,7 +362,10 @@ __device__ __forceinline__ void cp_async_pair(T *smem_dst, const T *gsrc) {
 // (tile bx covers cells 64 bx .. 64 bx + 63) and every global access of a cell pair is one
 // naturally aligned 8-/16-byte transaction (cp.async of pairs, STG.64/128).  Otherwise tiles
 // start at cell 1 and pairs are moved as two scalars.
-template <typename T, typename CT, int TY, int ZC, int DEPTH, bool ACC, bool GEN, bool AL8>
+// SAME: vbase (and acc_in) alias the velocity the stencil reads -- the first stage of every step --
+// so the pointwise operands are the centre cells already sitting in the plane ring: no separate
+// fetch of them at all.
+template <typename T, typename CT, int TY, int ZC, int DEPTH, bool ACC, bool GEN, bool AL8, bool SAME = false>
 __global__ void __launch_bounds__(32 * TY, sizeof(T) == 4 ? 2 : 1) stage_pair_kernel(Grid<T> g, StageDev<T, CT> a) {
     typedef typename PairOf<T>::type P;
     typedef PairSmem<TY, ZC, DEPTH, ACC> SM;
@@ -444,6 +447,7 @@ __global__ void __launch_bounds__(32 * TY, sizeof(T) == 4 ? 2 : 1) stage_pair_ke
         zu++;
     };
     auto fetch_pointwise = [&]() {  // vbase / acc_in of this thread's cells in plane zp -> slot zp % NPW
+        if (SAME) return;
         if (zp < zend) {
             T *dst = pw + (zp % NPW) * SM::PWE + 2 * tid;
 #pragma unroll
@@ -558,7 +562,8 @@ __global__ void __launch_bounds__(32 * TY, sizeof(T) == 4 ? 2 : 1) stage_pair_ke
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             const P kc = padd(k[c], pbc(a.bf[c]));
-            P x = pwp[c * NT];
+            const P uc = c == 0 ? u0c : c == 1 ? u1c : u2c;
+            P x = SAME ? uc : pwp[c * NT];
             if (GEN) {
                 if (a.k_out[0]) {
                     if (act0) a.k_out[c][q] = kc.x;
@@ -578,7 +583,7 @@ __global__ void __launch_bounds__(32 * TY, sizeof(T) == 4 ? 2 : 1) stage_pair_ke
                 if (act1) v_p[c * cs + dxb] = vo.y;
             }
             if (ACC) {
-                const P ao = PairAxpy<T, CT>::run(pwp[(3 + c) * NT], a.ca, kc);
+                const P ao = PairAxpy<T, CT>::run(SAME ? uc : pwp[(3 + c) * NT], a.ca, kc);
                 if (AL8 && act0 && act1) {
                     *reinterpret_cast<P *>(ao_p + c * cs) = ao;
                 } else {
@@ -636,8 +641,13 @@ static int launch_stage_pair_a(const Grid<T> &g, const StageArgs<T> &a, Launch L
     constexpr int TY = 8, ZC = 128, DEPTH = 2;
     const bool acc = a.acc_out != nullptr, gen = a.k_out != nullptr || a.nprev > 0;
     const size_t smem = (size_t)(acc ? PairSmem<TY, ZC, DEPTH, true>::total : PairSmem<TY, ZC, DEPTH, false>::total) * sizeof(T);
-    auto kern = acc ? (gen ? stage_pair_kernel<T, CT, TY, ZC, DEPTH, true, true, AL8> : stage_pair_kernel<T, CT, TY, ZC, DEPTH, true, false, AL8>)
-                    : (gen ? stage_pair_kernel<T, CT, TY, ZC, DEPTH, false, true, AL8> : stage_pair_kernel<T, CT, TY, ZC, DEPTH, false, false, AL8>);
+    const bool same = !gen && a.vbase == a.u && (!acc || a.acc_in == a.u) && getenv("INSB200_STAGE_NO_SAME") == nullptr;
+    auto kern = acc ? (gen ? stage_pair_kernel<T, CT, TY, ZC, DEPTH, true, true, AL8>
+                           : (same ? stage_pair_kernel<T, CT, TY, ZC, DEPTH, true, false, AL8, true>
+                                   : stage_pair_kernel<T, CT, TY, ZC, DEPTH, true, false, AL8>))
+                    : (gen ? stage_pair_kernel<T, CT, TY, ZC, DEPTH, false, true, AL8>
+                           : (same ? stage_pair_kernel<T, CT, TY, ZC, DEPTH, false, false, AL8, true>
+                                   : stage_pair_kernel<T, CT, TY, ZC, DEPTH, false, false, AL8>));
     INSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     StageDev<T, CT> d{};
     for (int c = 0; c < 3; c++) {

@@ -212,3 +212,24 @@ def test_native_time_loop_stops_on_bad_dt():
     with pytest.warns(UserWarning, match="out of bounds"):
         out, _ = I.solve_unsteady(setup=sg, tlims=(0.0, 1.0), start={"u": u0}, psolver=ps, params=dict(viscosity=1e8))
     assert float(out["t"]) == 0.0
+
+
+@pytest.mark.parametrize("T", [np.float64, np.float32])
+def test_first_stage_reuses_ring_planes_bit_identical(T):
+    """First stage of a step (vbase = acc_in = u): operands taken from the shared-memory plane
+    ring == fetched separately."""
+    I = ins()
+    so, sg = make_setups((uniform(70), uniform(24), uniform(20)), ("P", "P", "P"), T=T)
+    ps = I.psolver_spectral(sg)
+    u0 = smooth_vec(so, 81)
+    res = {}
+    for tag, val in (("ring", None), ("fetched", 1)):
+        with env(INSB200_STAGE_NO_SAME=val):
+            for mname in ("RK44", "LMWray3", "FE11"):
+                m = I.LMWray3(T) if mname == "LMWray3" else getattr(I.RKMethods, mname)(T)
+                sp = I.create_stepper(m, setup=sg, psolver=ps, state={"u": I.to_device(sg, u0)}, t=0.0)
+                for _ in range(2):
+                    sp = I.timestep_(m, I.navierstokes_, sp, T(1e-3), params=dict(viscosity=1e-2))
+                res[tag, mname] = I.to_host(sp["state"]["u"])
+    for mname in ("RK44", "LMWray3", "FE11"):
+        assert np.array_equal(res["ring", mname], res["fetched", mname]), mname
