@@ -241,6 +241,56 @@ function INS.propose_timestep(force!::BuiltinForce, state, setup, params, psolve
     eltype(state.u)(out[])
 end
 
+# solve_unsteady(; ...)   (src/solver.jl:77-149): with a B200 psolver and a built-in force the
+# whole time loop runs inside the library (insb200_solve_unsteady): CFL adaptation, clipping to
+# tend, the bad-Δt stop, a CUDA-graph replay of the step for fixed Δt; the processors are
+# notified through a C call-back every gcd(nupdate...) steps.
+function b200_on_step(user::Ptr{Cvoid}, n::Clonglong, t::Cdouble)::Cint
+    f = unsafe_pointer_to_objref(user)::Base.RefValue{Any}
+    f[](n, t)
+    Cint(0)
+end
+
+function INS.solve_unsteady_b200(; setup, tlims, start, force!::BuiltinForce = navierstokes!, docopy = true,
+        method = LMWray3(; T = eltype(start.u)), psolver::B200PSolver, Δt = nothing, Δt_min = nothing,
+        cfl = eltype(start.u)(0.9), n_adapt_Δt = 1, processors = (;), nupdate = 1, params, use_graph = true)
+    tstart, tend = tlims
+    T = eltype(start.u)
+    state = docopy ? deepcopy(start) : start
+    stepper = Ref{Any}(create_stepper(method; setup, psolver, state, t = tstart))
+    obs = INS.Observable(INS.get_state(stepper[]))
+    initialized = (; (k => v.initialize(obs) for (k, v) in pairs(processors))...)
+    notify = Ref{Any}((n, t) -> begin
+        stepper[] = create_stepper(method; setup, psolver, state, t = typeof(tstart)(t), n = Int(n))
+        obs[] = INS.get_state(stepper[])
+    end)
+    isrk = method isa ExplicitRungeKuttaMethod
+    s = isrk ? length(method.b) : 0
+    Arow = isrk ? Float64.(permutedims(method.A))[:] : Float64[]
+    crow = isrk ? Float64.(method.c) : Float64[]
+    Tm = isrk ? typeof(method).parameters[1] : T
+    coefT = promote_type(Tm, isnothing(Δt) ? T : typeof(Δt)) == Float64 ? Cint(1) : Cint(0)
+    timeT = (isnothing(Δt) ? T : typeof(Δt)) == Float32 ? Cint(0) : Cint(1)
+    cpar = Ref(cparams(force!, params))
+    tout, nout = Ref{Cdouble}(0), Ref{Clonglong}(0)
+    temp = haskey(state, :temp) ? state.temp : nothing
+    cb = @cfunction(b200_on_step, Cint, (Ptr{Cvoid}, Clonglong, Cdouble))
+    GC.@preserve notify Arow crow begin
+        status = ccall((:insb200_solve_unsteady, libinsb200), Cint,
+            (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cdouble, Cdouble,
+             Cdouble, Cdouble, Cint, Cint, Ref{CParams}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ref{Cdouble}, Ref{Clonglong},
+             Ptr{Cvoid}),
+            psolver.plan, isrk ? Cint(0) : Cint(1), Arow, crow, s, coefT, devptr(state.u), devptr(temp), tstart, tend,
+            isnothing(Δt) ? -1.0 : Float64(Δt), isnothing(Δt_min) ? -1.0 : Float64(Δt_min), Float64(cfl), n_adapt_Δt,
+            timeT, cpar, isempty(processors) ? Cint(0) : Cint(nupdate), cb, pointer_from_objref(notify), Cint(use_graph),
+            tout, nout, stream())
+    end
+    status == 2 ? (@warn lasterror()) : check(status)   # INSB200_STOPPED_BAD_DT: warn and stop (solver.jl:113-116)
+    notify[](nout[], tout[])
+    outputs = (; (k => processors[k].finalize(initialized[k], obs) for k in keys(processors))...)
+    (; state..., t = typeof(tstart)(tout[])), outputs
+end
+
 # right_hand_side!(dudt, u, params_ref, t)   (src/sciml.jl:35-48)
 function INS.right_hand_side!(dudt::CuArray, u::CuArray, params_ref::Base.RefValue{<:Tuple{Any,<:B200PSolver,Any}}, t)
     setup, psolver, viscosity = params_ref[]
