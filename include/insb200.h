@@ -181,6 +181,26 @@ int insb200_step_rk_host_ensemble(insb200_plan_t *plan, const double *A, const d
                                   int nmembers, double t, double dt, int nsteps,
                                   const insb200_params_t *params, void *stream);
 
+/* ---- diagnostics feeding the processors (src/operators.jl:853-1066) -----------------------
+ * One pass over the fields each; outputs have the layout of the reference's arrays (scalar or
+ * vector field, ghosted), entries outside the reference's index range are left untouched.
+ * vorticity! (:853-881): omega is a scalar field in 2-D, a vector field in 3-D. */
+int insb200_vorticity(insb200_plan_t *plan, void *omega, const void *u, void *stream);
+/* interpolate_u_p! (:921-940): velocity at the pressure points. */
+int insb200_interpolate_u_p(insb200_plan_t *plan, void *up, const void *u, void *stream);
+/* interpolate_ω_p! (:950-984): vorticity at the pressure points. */
+int insb200_interpolate_omega_p(insb200_plan_t *plan, void *omegap, const void *omega, void *stream);
+/* qcrit! (:989-1000): Q = -tr(G G)/2 of the collocated velocity gradient. */
+int insb200_qcrit(insb200_plan_t *plan, void *q, const void *u, void *stream);
+/* kinetic_energy! (:1027-1055), interpolate_first = 0/1. */
+int insb200_kinetic_energy(insb200_plan_t *plan, void *ke, const void *u, int interpolate_first,
+                           void *stream);
+/* total_kinetic_energy (:1061-1066): sum over the pressure volumes of ke * cell volume, evaluated
+ * without materialising ke (summed in double, deterministic order; all-reduced over the ranks of a
+ * decomposed plan).  Synchronises the stream and returns the host scalar. */
+int insb200_total_kinetic_energy(insb200_plan_t *plan, const void *u, int interpolate_first,
+                                 double *out, void *stream);
+
 /* solve_unsteady (src/solver.jl:77-149): the time loop itself, so that a run of many small steps
  * does not return to the host language per step.
  *   method 0: explicit Runge-Kutta with the tableau (A, c, s, coef_dtype) of insb200_step_rk;

@@ -47,6 +47,7 @@ struct insb200_plan : public insb::Profiler {
     cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of the ensemble entry point
     cudaStream_t s_graph = nullptr;                // capture / replay stream of insb200_solve_unsteady
     double *scratch = nullptr;  // reductions
+    double *ke_partial = nullptr;  // block partials of total_kinetic_energy
     long long bytes = 0;
     long long launches = 0;
     // diffusive / thermal step limits (host, from the tables)
@@ -683,7 +684,7 @@ int insb200_plan_destroy(insb200_plan_t *pl) {
     cudaDeviceSynchronize();
     if (pl->ps) poisson_destroy(pl->ps);
     for (void *p : {pl->V[0], pl->V[1], pl->ACC, pl->P, pl->TV[0], pl->TV[1], pl->TACC, pl->dev_tables,
-                    (void *)pl->scratch, pl->HU, pl->HT, pl->HU2, pl->HT2})
+                    (void *)pl->scratch, (void *)pl->ke_partial, pl->HU, pl->HT, pl->HU2, pl->HT2})
         if (p) cudaFree(p);
     if (pl->s_in) cudaStreamDestroy(pl->s_in);
     if (pl->s_out) cudaStreamDestroy(pl->s_out);
@@ -1114,6 +1115,67 @@ int insb200_cfl(insb200_plan_t *pl, const void *u, const insb200_params_t *pr, d
         }
     }
     *dt_out = dt;
+    return 0;
+    API_END
+}
+
+// ---- diagnostics (src/operators.jl:853-1066), diag.cu --------------------------------
+static void local_ip(const insb200_plan *pl, int Ip[3][2]) {
+    std::memcpy(Ip, pl->Ip, sizeof(pl->Ip));
+    if (pl->comm) Ip[2][0] = 1, Ip[2][1] = pl->nzl + 1;
+}
+
+static int diag_call(insb200_plan_t *pl, int op, const void *in, void *out, void *stream) {
+    int Ip[3][2];
+    local_ip(pl, Ip);
+    return DISPATCH(launch_diag<float>(pl->gf, Ip, op, (const float *)in, (float *)out, L_of(pl, stream)),
+                    launch_diag<double>(pl->gd, Ip, op, (const double *)in, (double *)out, L_of(pl, stream)));
+}
+
+int insb200_vorticity(insb200_plan_t *pl, void *omega, const void *u, void *stream) {
+    API_BEGIN
+    return diag_call(pl, 0, u, omega, stream);
+    API_END
+}
+
+int insb200_interpolate_u_p(insb200_plan_t *pl, void *up, const void *u, void *stream) {
+    API_BEGIN
+    return diag_call(pl, 1, u, up, stream);
+    API_END
+}
+
+int insb200_interpolate_omega_p(insb200_plan_t *pl, void *omegap, const void *omega, void *stream) {
+    API_BEGIN
+    return diag_call(pl, 2, omega, omegap, stream);
+    API_END
+}
+
+int insb200_qcrit(insb200_plan_t *pl, void *q, const void *u, void *stream) {
+    API_BEGIN
+    return diag_call(pl, 3, u, q, stream);
+    API_END
+}
+
+int insb200_kinetic_energy(insb200_plan_t *pl, void *ke, const void *u, int interpolate_first, void *stream) {
+    API_BEGIN
+    return diag_call(pl, interpolate_first ? 5 : 4, u, ke, stream);
+    API_END
+}
+
+int insb200_total_kinetic_energy(insb200_plan_t *pl, const void *u, int interpolate_first, double *out,
+                                 void *stream) {
+    API_BEGIN
+    constexpr int NPART = 148 * 4;
+    if (!pl->ke_partial) INSB_CUDA(cudaMalloc((void **)&pl->ke_partial, NPART * sizeof(double)));
+    int Ip[3][2];
+    local_ip(pl, Ip);
+    Launch L = L_of(pl, stream);
+    INSB_TRY(DISPATCH(
+        launch_total_ke<float>(pl->gf, Ip, (const float *)u, interpolate_first != 0, pl->ke_partial, NPART, pl->scratch, L),
+        launch_total_ke<double>(pl->gd, Ip, (const double *)u, interpolate_first != 0, pl->ke_partial, NPART, pl->scratch, L)));
+    if (pl->comm) INSB_TRY(comm_sum_double(pl->comm, pl->scratch, L.stream));
+    INSB_CUDA(cudaMemcpyAsync(out, pl->scratch, sizeof(double), cudaMemcpyDeviceToHost, L.stream));
+    INSB_CUDA(cudaStreamSynchronize(L.stream));
     return 0;
     API_END
 }

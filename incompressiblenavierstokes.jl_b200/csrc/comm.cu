@@ -318,6 +318,11 @@ int comm_reduce_scratch(Comm *c, double *scratch, bool is_min, cudaStream_t st) 
     return 0;
 }
 
+int comm_sum_double(Comm *c, double *value, cudaStream_t st) {
+    INSB_NCCL(g_nccl.AllReduce(value, value, 1, ncclDouble, ncclSum, c->comm, st));
+    return 0;
+}
+
 // ---- peer flags ---------------------------------------------------------------------------
 struct PeerPtrs {
     unsigned *p[8];

@@ -72,6 +72,7 @@ void comm_disable_p2p_halo(Comm *c, const void *my_window);
 int comm_halo_launches(const Comm *c);  // kernels of this library per halo exchange (0 on the NCCL path)
 int comm_all_to_all(Comm *c, const void *send, void *recv, size_t block_bytes, cudaStream_t st);
 int comm_reduce_scratch(Comm *c, double *scratch, bool is_min, cudaStream_t st);
+int comm_sum_double(Comm *c, double *value, cudaStream_t st);  // in-place all-reduce(sum) of one device double
 // cross-process flags in peer-mapped memory: every rank stores `epoch` into slot `rank` of the
 // flag row `row` of all ranks (after everything enqueued before on `st`), resp. waits until all
 // slots of its own row hold a value >= epoch.
@@ -159,6 +160,15 @@ template <typename T>
 int launch_cfl(const Grid<T> &g, const int Iu[3][3][2], const T *u, double *scratch, Launch L);
 template <typename T>
 int launch_maxabs(const T *u, long long n, double *scratch, Launch L);
+
+// ---- diag.cu ----
+// op: 0 vorticity, 1 interpolate_u_p, 2 interpolate_ω_p, 3 qcrit, 4 kinetic energy, 5 kinetic energy
+// (interpolate first); Ip = pressure DOF range (0-based, half open)
+template <typename T>
+int launch_diag(const Grid<T> &g, const int Ip[3][2], int op, const T *in, T *out, Launch L);
+template <typename T>
+int launch_total_ke(const Grid<T> &g, const int Ip[3][2], const T *u, bool first, double *partial, int npartial,
+                    double *out, Launch L);
 
 // ---- bc.cu ----
 // dims: bit mask of the dimensions to fill (default all)

@@ -94,6 +94,12 @@ _PROTOTYPES = {
         [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_int, C.POINTER(C.c_void_p),
          C.POINTER(C.c_void_p), C.c_int, C.c_double, C.c_double, C.c_int, C.POINTER(ParamsStruct), _P],
     ),
+    "insb200_vorticity": (C.c_int, [_P, _P, _P, _P]),
+    "insb200_interpolate_u_p": (C.c_int, [_P, _P, _P, _P]),
+    "insb200_interpolate_omega_p": (C.c_int, [_P, _P, _P, _P]),
+    "insb200_qcrit": (C.c_int, [_P, _P, _P, _P]),
+    "insb200_kinetic_energy": (C.c_int, [_P, _P, _P, C.c_int, _P]),
+    "insb200_total_kinetic_energy": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_double), _P]),
     "insb200_solve_unsteady": (
         C.c_int,
         [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_int, _P, _P, C.c_double, C.c_double,

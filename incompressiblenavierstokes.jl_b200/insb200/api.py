@@ -478,6 +478,66 @@ def maxabs(u, setup, plan=None):
 
 
 # ------------------------------------------------------------------------------------
+# diagnostics (src/operators.jl:853-1066)
+# ------------------------------------------------------------------------------------
+def vorticity_(omega, u, setup):
+    check(lib().insb200_vorticity(_base_plan(setup).h, _ptr(_chk(setup, omega, setup.D == 3)), _ptr(_chk(setup, u, True)),
+                                  _stream()))
+    return omega
+
+
+def vorticity(u, setup):
+    return vorticity_(scalarfield(setup) if setup.D == 2 else vectorfield(setup), u, setup)
+
+
+def interpolate_u_p_(up, u, setup):
+    check(lib().insb200_interpolate_u_p(_base_plan(setup).h, _ptr(_chk(setup, up, True)), _ptr(_chk(setup, u, True)),
+                                        _stream()))
+    return up
+
+
+def interpolate_u_p(u, setup):
+    return interpolate_u_p_(vectorfield(setup), u, setup)
+
+
+def interpolate_omega_p_(omegap, omega, setup):
+    v = setup.D == 3
+    check(lib().insb200_interpolate_omega_p(_base_plan(setup).h, _ptr(_chk(setup, omegap, v)), _ptr(_chk(setup, omega, v)),
+                                            _stream()))
+    return omegap
+
+
+def interpolate_omega_p(omega, setup):
+    return interpolate_omega_p_(scalarfield(setup) if setup.D == 2 else vectorfield(setup), omega, setup)
+
+
+def qcrit_(q, u, setup):
+    check(lib().insb200_qcrit(_base_plan(setup).h, _ptr(_chk(setup, q, False)), _ptr(_chk(setup, u, True)), _stream()))
+    return q
+
+
+def qcrit(u, setup):
+    return qcrit_(scalarfield(setup), u, setup)
+
+
+def kinetic_energy_(ke, u, setup, interpolate_first=False):
+    check(lib().insb200_kinetic_energy(_base_plan(setup).h, _ptr(_chk(setup, ke, False)), _ptr(_chk(setup, u, True)),
+                                       int(interpolate_first), _stream()))
+    return ke
+
+
+def kinetic_energy(u, setup, interpolate_first=False):
+    return kinetic_energy_(scalarfield(setup), u, setup, interpolate_first)
+
+
+def total_kinetic_energy(u, setup, interpolate_first=False, plan=None):
+    out = C.c_double()
+    check(lib().insb200_total_kinetic_energy((plan or _base_plan(setup)).h, _ptr(_chk(setup, u, True)),
+                                             int(interpolate_first), C.byref(out), _stream()))
+    return setup.T(out.value)
+
+
+# ------------------------------------------------------------------------------------
 # processors (src/processors.jl): the call-back boundary of solve_unsteady
 # ------------------------------------------------------------------------------------
 class Observable:

@@ -1,0 +1,80 @@
+"""GPU parity of the on-device diagnostics against oracle/postprocess.py."""
+import numpy as np
+import pytest
+
+import oracle as O
+from oracle import postprocess as opp
+
+from gpu_helpers import make_setups, random_vec, rel_l2, smooth_vec, uniform
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    ("periodic3", (uniform(16), uniform(12, 2.0), uniform(20, 0.5)), ("P", "P", "P")),
+    ("walls3", (O.tanh_grid(0, 1, 12, 1.2), O.tanh_grid(0, 1, 10, 1.1), O.cosine_grid(0, 1, 14)), ("D", "D", "D")),
+    ("channel3", (uniform(16, 4.0), O.tanh_grid(0, 2, 12, 1.4), uniform(8, 2.0)), ("P", "D", "P")),
+    ("mixed3", (uniform(10), O.cosine_grid(0, 1, 8), uniform(12)), (("D", "O"), "S", "P")),
+    ("periodic2", (uniform(16), uniform(24, 2.0)), ("P", "P")),
+    ("walls2", (O.tanh_grid(0, 1, 16), O.tanh_grid(0, 1, 12, 1.3)), ("D", "D")),
+]
+
+
+@pytest.mark.parametrize("T", [np.float64, np.float32])
+@pytest.mark.parametrize("name,x,bcs", CASES)
+def test_diagnostics_match_oracle(name, x, bcs, T):
+    import insb200 as I
+
+    so, sg = make_setups(x, bcs, T=T)
+    u = smooth_vec(so, 91)
+    ud = I.to_device(sg, u)
+    tol = 1e-13 if T is np.float64 else 2e-6
+    # outputs start from the same random content: entries outside the reference's range stay untouched
+    junk_v, junk_s = random_vec(so, 92), random_vec(so, 93)[..., 0].copy(order="F")
+    vort_shape_vec = so.D == 3
+    w_o = opp.vorticity_(junk_v.copy(order="F") if vort_shape_vec else junk_s.copy(order="F"), u, so)
+    w_g = I.vorticity_(I.to_device(sg, junk_v if vort_shape_vec else junk_s), ud, sg)
+    assert rel_l2(I.to_host(w_g), w_o) < tol
+    up_o = opp.interpolate_u_p_(junk_v.copy(order="F"), u, so)
+    up_g = I.interpolate_u_p_(I.to_device(sg, junk_v), ud, sg)
+    assert rel_l2(I.to_host(up_g), up_o) < tol
+    wp_o = opp.interpolate_omega_p_(junk_v.copy(order="F") if vort_shape_vec else junk_s.copy(order="F"), w_o, so)
+    wp_g = I.interpolate_omega_p_(I.to_device(sg, junk_v if vort_shape_vec else junk_s), w_g, sg)
+    assert rel_l2(I.to_host(wp_g), wp_o) < tol
+    q_o = opp.qcrit_(junk_s.copy(order="F"), u, so)
+    q_g = I.qcrit_(I.to_device(sg, junk_s), ud, sg)
+    assert rel_l2(I.to_host(q_g), q_o) < (1e-12 if T is np.float64 else 2e-5)
+    for first in (False, True):
+        ke_o = opp.kinetic_energy_(junk_s.copy(order="F"), u, so, first)
+        ke_g = I.kinetic_energy_(I.to_device(sg, junk_s), ud, sg, first)
+        assert rel_l2(I.to_host(ke_g), ke_o) < tol
+        tot_o = float(opp.total_kinetic_energy(u, so, first))
+        tot_g = float(I.total_kinetic_energy(ud, sg, first))
+        assert abs(tot_g - tot_o) <= (1e-13 if T is np.float64 else 2e-6) * abs(tot_o)
+
+
+def test_diagnostics_at_bench_size_properties():
+    """256^3 F32 Taylor-Green field: analytic vorticity / energy, finite Q (size-independent checks)."""
+    import torch
+
+    import insb200 as I
+
+    n = 256
+    T = np.float32
+    x = tuple(np.linspace(0.0, 1.0, n + 1).astype(T) for _ in range(3))
+    sg = I.Setup(x, {"u": ((I.PeriodicBC(), I.PeriodicBC()),) * 3})
+
+    def U(dim, x, y, z):
+        if dim == 0:
+            return np.sin(2 * np.pi * x) * np.cos(2 * np.pi * y) * np.sin(2 * np.pi * z) / 2
+        if dim == 1:
+            return -np.cos(2 * np.pi * x) * np.sin(2 * np.pi * y) * np.sin(2 * np.pi * z) / 2
+        return 0 * x + 0 * y + 0 * z
+
+    u = I.velocityfield(sg, U, doproject=False)
+    e = float(I.total_kinetic_energy(u, sg))
+    assert abs(e - 1.0 / 32) < 2e-4  # int (u^2 + v^2)/2 = 2 * (1/4) * (1/8) / 2
+    w = I.vorticity(u, sg)
+    q = I.qcrit(u, sg)
+    assert bool(torch.isfinite(w).all()) and bool(torch.isfinite(q).all())
+    # omega_z = dv/dx - du/dy = 2 pi sin(2 pi x) sin(2 pi y) sin(2 pi z): max = 2 pi
+    assert abs(float(w[2].abs().max()) - 2 * np.pi) < 2e-2

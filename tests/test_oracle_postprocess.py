@@ -1,0 +1,66 @@
+"""Oracle diagnostics (oracle/postprocess.py) against analytic fields and identities."""
+import numpy as np
+
+import oracle as O
+from oracle import bc as obc, initializers as oini, postprocess as opp
+
+from gpu_helpers import uniform
+
+
+def _periodic(n, D, T=np.float64, L=2 * np.pi):
+    x = tuple(np.linspace(0.0, L, n + 1).astype(T) for _ in range(D))
+    return O.Setup(x, {"u": ((O.PeriodicBC(), O.PeriodicBC()),) * D})
+
+
+def test_tgv2d_vorticity_energy_and_q():
+    n = 128
+    so = _periodic(n, 2)
+    u = oini.velocityfield(so, lambda d, x, y: (-np.sin(x) * np.cos(y) if d == 0 else np.cos(x) * np.sin(y)) + 0 * x * y,
+                           doproject=False)
+    w = opp.vorticity(u, so)  # at the cell corners (right/top faces of cell I): omega = -2 sin x sin y
+    N = so.N[0]
+    xc, yc = so.x[0][1:N], so.x[1][1:N]
+    want = -2 * np.sin(xc)[:, None] * np.sin(yc)[None, :]
+    assert np.max(np.abs(w[: N - 1, : N - 1] - want)) < 2e-3
+    # total kinetic energy of the 2-D Taylor-Green vortex on [0, 2pi]^2: pi^2 (both variants, O(h^2))
+    assert abs(opp.total_kinetic_energy(u, so) - np.pi**2) < 2e-3
+    assert abs(opp.total_kinetic_energy(u, so, interpolate_first=True) - np.pi**2) < 1e-2
+    # G = [[-cx cy, sx sy], [-sx sy, cx cy]] -> tr(G G) = 2 cx^2 cy^2 - 2 sx^2 sy^2 -> Q = sx^2 sy^2 - cx^2 cy^2
+    q = opp.qcrit(u, so)
+    xp, yp = so.xp[0][1:-1], so.xp[1][1:-1]
+    qa = (np.sin(xp) ** 2)[:, None] * (np.sin(yp) ** 2)[None, :] - (np.cos(xp) ** 2)[:, None] * (np.cos(yp) ** 2)[None, :]
+    assert np.max(np.abs(q[1:-1, 1:-1] - qa)) < 5e-3
+    # interpolation to pressure points is second order
+    up = opp.interpolate_u_p(u, so)
+    ua = -np.sin(xp)[:, None] * np.cos(yp)[None, :]
+    assert np.max(np.abs(up[1:-1, 1:-1, 0] - ua)) < 1e-3
+    wp = opp.interpolate_omega_p(w, so)
+    assert np.max(np.abs(wp[1:-1, 1:-1] + 2 * np.sin(xp)[:, None] * np.sin(yp)[None, :])) < 3e-3
+
+
+def test_3d_vorticity_of_rigid_rotation_and_energy_identity():
+    n = 16
+    x = tuple(np.linspace(-1.0, 1.0, n + 1) for _ in range(3))
+    so = O.Setup(x, {"u": ((O.DirichletBC(), O.DirichletBC()),) * 3})
+    u = O.vectorfield(so)
+    # u = Omega x r with Omega = (0, 0, 1): (-y, x, 0) sampled at the velocity points -> curl = (0, 0, 2)
+    X = [so.xu[a] for a in range(3)]
+    u[..., 0] = -X[0][1].reshape(1, -1, 1) + 0 * X[0][0].reshape(-1, 1, 1) + 0 * X[0][2].reshape(1, 1, -1)
+    u[..., 1] = X[1][0].reshape(-1, 1, 1) + 0 * X[1][1].reshape(1, -1, 1) + 0 * X[1][2].reshape(1, 1, -1)
+    w = opp.vorticity(u, so)
+    inner = (slice(1, n), slice(1, n), slice(1, n))
+    assert np.allclose(w[inner + (2,)], 2.0, atol=1e-12)
+    assert np.allclose(w[inner + (0,)], 0.0, atol=1e-12) and np.allclose(w[inner + (1,)], 0.0, atol=1e-12)
+    # ke (not interpolated first) >= ke (interpolated first), equal for a uniform field
+    ke_a = opp.kinetic_energy(u, so)
+    ke_b = opp.kinetic_energy(u, so, interpolate_first=True)
+    assert np.all(ke_a[so.Ip] >= ke_b[so.Ip] - 1e-14)
+    u[...] = 1.0
+    assert np.allclose(opp.kinetic_energy(u, so)[so.Ip], 1.5) and np.allclose(opp.kinetic_energy(u, so, True)[so.Ip], 1.5)
+    # qcrit of rigid rotation: G = [[0,-1,0],[1,0,0],[0,0,0]] -> tr(GG) = -2 -> Q = 1
+    u = O.vectorfield(so)
+    u[..., 0] = -X[0][1].reshape(1, -1, 1) + 0 * X[0][0].reshape(-1, 1, 1) + 0 * X[0][2].reshape(1, 1, -1)
+    u[..., 1] = X[1][0].reshape(-1, 1, 1) + 0 * X[1][1].reshape(1, -1, 1) + 0 * X[1][2].reshape(1, 1, -1)
+    q = opp.qcrit(u, so)
+    mid = (slice(3, n - 2),) * 3
+    assert np.allclose(q[mid], 1.0, atol=1e-12)
