@@ -91,7 +91,16 @@ typedef struct insb200_params {
     int dodissipation;
     int boussinesq;     /* 0: navierstokes! (solver.jl:2-6); 1: boussinesq! (solver.jl:16-35) */
     double bodyforce[3];/* constant body force added to k.u (examples/ChannelFlow.jl:172-176); 0 = none */
+    /* eddy-viscosity closure added to k.u, i.e. the force_eddy! of examples/ChannelFlow.jl:177-182:
+     * navierstokes! + eddy_viscosity_closure!(model, ...) (src/eddyviscosity.jl:356-378), 3-D only */
+    int eddy_model;     /* 0 none, 1 Smagorinsky, 2 WALE, 3 Vreman, 4 QR (INSB200_EDDY_*) */
+    double eddy_C;      /* model constant (Smagorinsky(C), WALE(C), ...) */
 } insb200_params_t;
+#define INSB200_EDDY_NONE 0
+#define INSB200_EDDY_SMAGORINSKY 1
+#define INSB200_EDDY_WALE 2
+#define INSB200_EDDY_VREMAN 3
+#define INSB200_EDDY_QR 4
 
 typedef struct insb200_plan insb200_plan_t;
 
@@ -180,6 +189,11 @@ int insb200_step_rk_host_ensemble(insb200_plan_t *plan, const double *A, const d
                                   int coef_dtype, void *const *u_hosts, void *const *temp_hosts,
                                   int nmembers, double t, double dt, int nsteps,
                                   const insb200_params_t *params, void *stream);
+
+/* eddy_viscosity_closure!(model, f, u, cache, setup) (src/eddyviscosity.jl:356-378): f -= div of the
+ * modelled stress; the cache (visc, G) is plan-owned scratch. */
+int insb200_eddy_viscosity_closure(insb200_plan_t *plan, int model, double C, void *f, const void *u,
+                                   void *stream);
 
 /* ---- diagnostics feeding the processors (src/operators.jl:853-1066) -----------------------
  * One pass over the fields each; outputs have the layout of the reference's arrays (scalar or

@@ -48,6 +48,7 @@ struct insb200_plan : public insb::Profiler {
     cudaStream_t s_graph = nullptr;                // capture / replay stream of insb200_solve_unsteady
     double *scratch = nullptr;  // reductions
     double *ke_partial = nullptr;  // block partials of total_kinetic_energy
+    void *LES_G = nullptr, *LES_visc = nullptr;  // eddy-viscosity scratch: 9 tensor components + viscosity
     long long bytes = 0;
     long long launches = 0;
     // diffusive / thermal step limits (host, from the tables)
@@ -292,6 +293,8 @@ void fill_params(StageArgs<T> &a, const insb200_params_t *pr, const insb200_plan
     a.dodiss = pr->dodissipation;
     a.bouss = pr->boussinesq;
     for (int c = 0; c < 3; c++) a.bodyforce[c] = pr->bodyforce[c];
+    a.eddy_model = pr->eddy_model;
+    a.eddy_C = pr->eddy_C;
     a.conv = 1;
     a.diff = 1;
     a.add_to_k = 0;
@@ -325,6 +328,21 @@ int ensure_k(insb200_plan *pl, int count, bool temp) {
         void *p;
         INSB_TRY(dev_alloc(pl, &p, sb));
         pl->TK.push_back(p);
+    }
+    return 0;
+}
+
+// Stage kernel followed by the eddy-viscosity closure when params ask for one: the closure term is
+// applied to the outputs the stage kernel has just written (k, v, acc), like the Boussinesq pass.
+template <typename T>
+int stage_with_closures(insb200_plan *pl, const Grid<T> &g, const StageArgs<T> &a, bool ct_double, Launch L) {
+    INSB_TRY(launch_stage<T>(g, a, ct_double, L));
+    if (a.eddy_model != 0) {
+        size_t sb = (size_t)pl->ncell * pl->esz;
+        if (!pl->LES_G) INSB_TRY(dev_alloc(pl, &pl->LES_G, 9 * sb));
+        if (!pl->LES_visc) INSB_TRY(dev_alloc(pl, &pl->LES_visc, sb));
+        INSB_TRY(launch_les_closure<T>(g, pl->bc, a.eddy_model, a.eddy_C, a.u, (T *)pl->LES_G, (T *)pl->LES_visc, a.k_out,
+                                       a.v, a.cv, a.acc_out, a.ca, ct_double, L));
     }
     return 0;
 }
@@ -426,7 +444,7 @@ int step_rk_t(insb200_plan *pl, const double *A, const double *c, int s, int coe
         }
         {
             Scope sc(pl, L.stream, 0);
-            INSB_TRY(launch_stage<T>(g, a, ct_double, L));
+            INSB_TRY(stage_with_closures<T>(pl, g, a, ct_double, L));
         }
         double ti = t + c[i] * dt;
         INSB_TRY(finish_stage<T>(pl, dst, tdst, ti, stream));
@@ -480,7 +498,7 @@ int step_wray_t(insb200_plan *pl, T *U, T *TU, double t, double dt, const insb20
         }
         {
             Scope sc(pl, L.stream, 0);
-            INSB_TRY(launch_stage<T>(g, a, pl->f64, L));
+            INSB_TRY(stage_with_closures<T>(pl, g, a, pl->f64, L));
         }
         double ti = t + (double)c3[i] * dt;
         INSB_TRY(finish_stage<T>(pl, dst, tdst, ti, stream));
@@ -507,7 +525,8 @@ static int rhs_t(insb200_plan *pl, const T *u, const T *temp, T *ku, T *ktemp, c
     a.conv = conv;
     a.diff = diff;
     Scope sc(pl, (cudaStream_t)stream, 0);
-    return launch_stage<T>(grid_of<T>(pl), a, pl->f64, L_of(pl, stream));
+    if (!(conv && diff)) a.eddy_model = 0;  // convection! / diffusion! alone never carry the closure
+    return stage_with_closures<T>(pl, grid_of<T>(pl), a, pl->f64, L_of(pl, stream));
 }
 
 template <typename T>
@@ -684,7 +703,7 @@ int insb200_plan_destroy(insb200_plan_t *pl) {
     cudaDeviceSynchronize();
     if (pl->ps) poisson_destroy(pl->ps);
     for (void *p : {pl->V[0], pl->V[1], pl->ACC, pl->P, pl->TV[0], pl->TV[1], pl->TACC, pl->dev_tables,
-                    (void *)pl->scratch, (void *)pl->ke_partial, pl->HU, pl->HT, pl->HU2, pl->HT2})
+                    (void *)pl->scratch, (void *)pl->ke_partial, pl->LES_G, pl->LES_visc, pl->HU, pl->HT, pl->HU2, pl->HT2})
         if (p) cudaFree(p);
     if (pl->s_in) cudaStreamDestroy(pl->s_in);
     if (pl->s_out) cudaStreamDestroy(pl->s_out);
@@ -1116,6 +1135,21 @@ int insb200_cfl(insb200_plan_t *pl, const void *u, const insb200_params_t *pr, d
     }
     *dt_out = dt;
     return 0;
+    API_END
+}
+
+int insb200_eddy_viscosity_closure(insb200_plan_t *pl, int model, double C, void *f, const void *u, void *stream) {
+    API_BEGIN
+    size_t sb = (size_t)pl->ncell * pl->esz;
+    if (!pl->LES_G) INSB_TRY(dev_alloc(pl, &pl->LES_G, 9 * sb));
+    if (!pl->LES_visc) INSB_TRY(dev_alloc(pl, &pl->LES_visc, sb));
+    Launch L = L_of(pl, stream);
+    return DISPATCH(launch_les_closure<float>(pl->gf, pl->bc, model, C, (const float *)u, (float *)pl->LES_G,
+                                              (float *)pl->LES_visc, (float *)f, (float *)nullptr, 0.0, (float *)nullptr,
+                                              0.0, false, L),
+                    launch_les_closure<double>(pl->gd, pl->bc, model, C, (const double *)u, (double *)pl->LES_G,
+                                               (double *)pl->LES_visc, (double *)f, (double *)nullptr, 0.0,
+                                               (double *)nullptr, 0.0, true, L));
     API_END
 }
 

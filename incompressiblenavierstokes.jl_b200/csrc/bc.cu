@@ -18,8 +18,9 @@ struct PlaneOp {
     double val;
     const void *arr;
 };
+constexpr int MAXBCF = 9;  // components / fields handled by one launch (9: a tensor field)
 struct BcOps {
-    PlaneOp op[2][3];
+    PlaneOp op[2][MAXBCF];
     int ncomp;
 };
 
@@ -144,17 +145,19 @@ int launch_bc_u(const Grid<T> &g, const BcDesc &b, T *u, int dudt, Launch L, int
     return 0;
 }
 
+// nf scalar fields of the same kind back to back (stride g.cs) share the launches
 template <typename T>
 static int scalar_bc(const Grid<T> &g, const BcDesc &b, const int (*types)[2], bool is_temp, T *p,
-                     Launch L, int dims = 7) {
+                     Launch L, int dims = 7, int nf = 1) {
     for (int beta = 0; beta < g.D; beta++) {
         if (!(dims >> beta & 1)) continue;
         if (beta == 2 && b.comm) {  // decomposed direction is periodic for every field
-            INSB_TRY(halo_dim<T>(g, b, p, 1, L));
+            for (int f0 = 0; f0 < nf; f0 += 3)  // the peer-store halo window holds three planes per side
+                INSB_TRY(halo_dim<T>(g, b, p + (long long)f0 * g.cs, nf - f0 < 3 ? nf - f0 : 3, L));
             continue;
         }
         BcOps ops{};
-        ops.ncomp = 1;
+        ops.ncomp = nf;
         int n = g.N[beta];
         // planes always come from Ip, which is defined by the VELOCITY BC types
         int plo = offset_p(b.bc_u[beta][0], false), phi = n - offset_p(b.bc_u[beta][1], true);
@@ -193,7 +196,34 @@ static int scalar_bc(const Grid<T> &g, const BcDesc &b, const int (*types)[2], b
                     break;
             }
         }
+        for (int side = 0; side < 2; side++)
+            for (int f = 1; f < nf; f++) ops.op[side][f] = ops.op[side][0];
         INSB_TRY(run_dim<T>(g, beta, ops, p, L));
+    }
+    return 0;
+}
+
+// apply_bc_p! on nf scalar fields stored back to back (the tensor components of les.cu)
+template <typename T>
+int launch_bc_p_fields(const Grid<T> &g, const BcDesc &b, T *fields, int nf, Launch L) {
+    return scalar_bc<T>(g, b, b.bc_u, false, fields, L, 7, nf);
+}
+
+// zero_out_wall! (src/eddyviscosity.jl:344-353): first and last plane of every Dirichlet dimension
+template <typename T>
+int launch_zero_out_wall(const Grid<T> &g, const BcDesc &b, T *fields, int nf, Launch L) {
+    for (int beta = 0; beta < g.D; beta++) {
+        if (beta == 2 && b.comm) continue;  // the decomposed direction is periodic
+        BcOps ops{};
+        ops.ncomp = nf;
+        for (int side = 0; side < 2; side++)
+            if (b.bc_u[beta][side] == INSB200_BC_DIRICHLET)
+                for (int f = 0; f < nf; f++) {
+                    ops.op[side][f].mode = OP_CONST;
+                    ops.op[side][f].val = 0.0;
+                    ops.op[side][f].dst = side ? g.N[beta] - 1 : 0;
+                }
+        INSB_TRY(run_dim<T>(g, beta, ops, fields, L));
     }
     return 0;
 }
@@ -211,6 +241,10 @@ template int launch_bc_u<float>(const Grid<float> &, const BcDesc &, float *, in
 template int launch_bc_u<double>(const Grid<double> &, const BcDesc &, double *, int, Launch, int);
 template int launch_bc_p<float>(const Grid<float> &, const BcDesc &, float *, Launch, int);
 template int launch_bc_p<double>(const Grid<double> &, const BcDesc &, double *, Launch, int);
+template int launch_bc_p_fields<float>(const Grid<float> &, const BcDesc &, float *, int, Launch);
+template int launch_bc_p_fields<double>(const Grid<double> &, const BcDesc &, double *, int, Launch);
+template int launch_zero_out_wall<float>(const Grid<float> &, const BcDesc &, float *, int, Launch);
+template int launch_zero_out_wall<double>(const Grid<double> &, const BcDesc &, double *, int, Launch);
 template int launch_bc_temp<float>(const Grid<float> &, const BcDesc &, float *, Launch);
 template int launch_bc_temp<double>(const Grid<double> &, const BcDesc &, double *, Launch);
 

@@ -117,6 +117,8 @@ struct StageArgs {
     double nu, kappa, grav;
     int gdir, dodiss, bouss;
     double bodyforce[3];
+    int eddy_model;  // eddy-viscosity closure added to k (0 = none), see les.cu
+    double eddy_C;
     int conv, diff;  // which stresses to include (1,1 = convectiondiffusion!)
     int add_to_k;    // k_out += instead of = (convection!/diffusion! add semantics)
 };
@@ -178,6 +180,19 @@ template <typename T>
 int launch_bc_p(const Grid<T> &g, const BcDesc &b, T *p, Launch L, int dims = 7);
 template <typename T>
 int launch_bc_temp(const Grid<T> &g, const BcDesc &b, T *temp, Launch L);
+
+template <typename T>
+int launch_bc_p_fields(const Grid<T> &g, const BcDesc &b, T *fields, int nf, Launch L);
+template <typename T>
+int launch_zero_out_wall(const Grid<T> &g, const BcDesc &b, T *fields, int nf, Launch L);
+
+// ---- les.cu ----
+// eddy_viscosity_closure! (src/eddyviscosity.jl:356-378).  model: 1 Smagorinsky, 2 WALE, 3 Vreman,
+// 4 QR.  G: 9 scalar fields, visc: 1 (scratch).  With fl = -(div sigma): k_out += fl, v += cv fl,
+// acc += ca fl (null pointers are skipped).
+template <typename T>
+int launch_les_closure(const Grid<T> &g, const BcDesc &b, int model, double C, const T *u, T *G, T *visc, T *k_out, T *v,
+                       double cv, T *acc, double ca, bool ct_double, Launch L);
 
 // ---- poisson.cu ----
 struct Poisson;  // opaque

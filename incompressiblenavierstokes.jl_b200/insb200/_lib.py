@@ -49,6 +49,8 @@ class ParamsStruct(C.Structure):
         ("dodissipation", C.c_int),
         ("boussinesq", C.c_int),
         ("bodyforce", C.c_double * 3),
+        ("eddy_model", C.c_int),
+        ("eddy_C", C.c_double),
     ]
 
 
@@ -94,6 +96,7 @@ _PROTOTYPES = {
         [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_int, C.POINTER(C.c_void_p),
          C.POINTER(C.c_void_p), C.c_int, C.c_double, C.c_double, C.c_int, C.POINTER(ParamsStruct), _P],
     ),
+    "insb200_eddy_viscosity_closure": (C.c_int, [_P, C.c_int, C.c_double, _P, _P, _P]),
     "insb200_vorticity": (C.c_int, [_P, _P, _P, _P]),
     "insb200_interpolate_u_p": (C.c_int, [_P, _P, _P, _P]),
     "insb200_interpolate_omega_p": (C.c_int, [_P, _P, _P, _P]),

@@ -137,9 +137,31 @@ def _base_plan(setup: Setup) -> Plan:
     return setup._plans["base"]
 
 
+class Smagorinsky:
+    """Eddy-viscosity model structs of src/eddyviscosity.jl:252-263."""
+    code = 1
+
+    def __init__(self, C):
+        self.C = float(C)
+
+
+class WALE(Smagorinsky):
+    code = 2
+
+
+class Vreman(Smagorinsky):
+    code = 3
+
+
+class QR(Smagorinsky):
+    code = 4
+
+
 def _params(setup, viscosity=0.0, conductivity=0.0, gravity=0.0, gdir=1, dodissipation=False,
-            boussinesq=False, bodyforce=None):
+            boussinesq=False, bodyforce=None, eddyviscosity=None):
     p = ParamsStruct()
+    p.eddy_model = 0 if eddyviscosity is None else int(eddyviscosity.code)
+    p.eddy_C = 0.0 if eddyviscosity is None else float(eddyviscosity.C)
     p.viscosity = float(viscosity)
     p.conductivity = float(conductivity)
     p.gravity = float(gravity)
@@ -433,7 +455,8 @@ def get_state(stepper):
 def _force_params(force, setup, params):
     params = dict(params or {})
     if force is navierstokes_:
-        return _params(setup, viscosity=params["viscosity"], bodyforce=params.get("bodyforce"))
+        return _params(setup, viscosity=params["viscosity"], bodyforce=params.get("bodyforce"),
+                       eddyviscosity=params.get("eddyviscosity"))
     if force is boussinesq_:
         return _params(setup, params["viscosity"], params["conductivity"], params["gravity"], params["gdir"],
                        params["dodissipation"], True, params.get("bodyforce"))
@@ -475,6 +498,14 @@ def maxabs(u, setup, plan=None):
     out = C.c_double()
     check(lib().insb200_maxabs((plan or _base_plan(setup)).h, _ptr(u), C.byref(out), _stream()))
     return out.value
+
+
+def eddy_viscosity_closure_(eddyvisc, f, u, cache, setup):
+    """eddy_viscosity_closure! (src/eddyviscosity.jl:356-378): f -= div(-2 nu_t S); the cache is
+    plan-owned scratch (`cache` is accepted for signature parity and ignored)."""
+    check(lib().insb200_eddy_viscosity_closure(_base_plan(setup).h, int(eddyvisc.code), float(eddyvisc.C),
+                                               _ptr(_chk(setup, f, True)), _ptr(_chk(setup, u, True)), _stream()))
+    return None
 
 
 # ------------------------------------------------------------------------------------

@@ -76,7 +76,15 @@ struct CParams
     dodissipation::Cint
     boussinesq::Cint
     bodyforce::NTuple{3,Cdouble}
+    eddy_model::Cint            # 0 none, 1 Smagorinsky, 2 WALE, 3 Vreman, 4 QR
+    eddy_C::Cdouble
 end
+
+eddycode(::Nothing) = (Cint(0), 0.0)
+eddycode(e::INS.Smagorinsky) = (Cint(1), Float64(e.C))
+eddycode(e::INS.WALE) = (Cint(2), Float64(e.C))
+eddycode(e::INS.Vreman) = (Cint(3), Float64(e.C))
+eddycode(e::INS.QR) = (Cint(4), Float64(e.C))
 
 bccode(::PeriodicBC) = Cint(0)
 bccode(::DirichletBC) = Cint(1)
@@ -182,10 +190,13 @@ end
 function cparams(force!, params)
     ν = Float64(params.viscosity)
     if force! === boussinesq!
-        CParams(ν, params.conductivity, params.gravity, Cint(params.gdir - 1), Cint(params.dodissipation), Cint(1), (0.0, 0.0, 0.0))
+        CParams(ν, params.conductivity, params.gravity, Cint(params.gdir - 1), Cint(params.dodissipation), Cint(1),
+            (0.0, 0.0, 0.0), Cint(0), 0.0)
     else
         bf = get(params, :bodyforce, (0.0, 0.0, 0.0))
-        CParams(ν, 0.0, 0.0, Cint(0), Cint(0), Cint(0), ntuple(i -> i <= length(bf) ? Float64(bf[i]) : 0.0, 3))
+        # `eddyviscosity = WALE(C)` etc.: navierstokes! + eddy_viscosity_closure! (examples/ChannelFlow.jl:177-182)
+        CParams(ν, 0.0, 0.0, Cint(0), Cint(0), Cint(0), ntuple(i -> i <= length(bf) ? Float64(bf[i]) : 0.0, 3),
+            eddycode(get(params, :eddyviscosity, nothing))...)
     end
 end
 
@@ -294,7 +305,7 @@ end
 # right_hand_side!(dudt, u, params_ref, t)   (src/sciml.jl:35-48)
 function INS.right_hand_side!(dudt::CuArray, u::CuArray, params_ref::Base.RefValue{<:Tuple{Any,<:B200PSolver,Any}}, t)
     setup, psolver, viscosity = params_ref[]
-    cpar = Ref(CParams(viscosity, 0.0, 0.0, Cint(0), Cint(0), Cint(0), (0.0, 0.0, 0.0)))
+    cpar = Ref(CParams(viscosity, 0.0, 0.0, Cint(0), Cint(0), Cint(0), (0.0, 0.0, 0.0), Cint(0), 0.0))
     check(ccall((:insb200_right_hand_side, libinsb200), Cint,
         (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Ref{CParams}, Ptr{Cvoid}),
         psolver.plan, devptr(dudt), devptr(u), t, cpar, stream()))

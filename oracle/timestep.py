@@ -216,6 +216,24 @@ def make_navierstokes(setup, viscosity):
     return force_
 
 
+def make_navierstokes_eddy(setup, viscosity, model, C, bodyforce=None):
+    """force_eddy! of examples/ChannelFlow.jl:177-182: navierstokes! + eddy_viscosity_closure!
+    (+ constant body force)."""
+    from . import eddyviscosity as ev
+
+    cache = dict(visc=scalarfield(setup), G=ev.tensorfield(setup))
+
+    def force_(force, state, t):
+        ops.navierstokes_(force, state, t, setup, viscosity)
+        ev.eddy_viscosity_closure_(model, C, force["u"], state["u"], setup, cache)
+        if bodyforce is not None:
+            for c, b in enumerate(bodyforce):
+                force["u"][..., c] += setup.T(b)
+
+    force_.params = dict(viscosity=viscosity)
+    return force_
+
+
 def make_boussinesq(setup, viscosity, conductivity, gdir, gravity, dodissipation):
     def force_(force, state, t):
         ops.boussinesq_(

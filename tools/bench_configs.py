@@ -118,6 +118,9 @@ def main():
             return 0.05 * np.sin(2 * x) * np.sin(np.pi * y) * np.cos(3 * z) + 0 * (x + y + z)
 
         u = I.velocityfield(sg, U, psolver=ps)
+        if a.world == 1:  # the example's LES variant: navierstokes! + eddy_viscosity_closure!(WALE) (ChannelFlow.jl:177-182)
+            run("cfg5 ChannelFlow3D RK44 + WALE closure (1 GPU)", sg, ps, {"u": u.clone()}, I.RKMethods.RK44(), I.navierstokes_,
+                dict(viscosity=1 / 180, bodyforce=(1.0, 0.0, 0.0), eddyviscosity=I.WALE(0.569)), 1e-4, 3)
         run(f"cfg5 ChannelFlow3D RK44 ({a.world} GPU)", sg, ps, {"u": u}, I.RKMethods.RK44(), I.navierstokes_,
             dict(viscosity=1 / 180, bodyforce=(1.0, 0.0, 0.0)), 1e-4, 3)
 
