@@ -199,9 +199,14 @@ int launch_les_closure(const Grid<T> &g, const BcDesc &b, int model, double C, c
     }
     dim3 blk(64, 4, 1);
     dim3 gr((g.N[0] - 2 + blk.x - 1) / blk.x, (g.N[1] - 2 + blk.y - 1) / blk.y, g.N[2] - 2);
-    // fill!(visc, 0); fill!(g, 0) (:358-361)
-    INSB_CUDA(cudaMemsetAsync(G, 0, (size_t)9 * g.cs * sizeof(T), L.stream));
-    INSB_CUDA(cudaMemsetAsync(visc, 0, (size_t)g.cs * sizeof(T), L.stream));
+    // fill!(visc, 0); fill!(g, 0) (:358-361): every interior entry is written below and every ghost
+    // plane by zero_out_wall! / apply_bc_p!, except the second ghost layer of a PressureBC side
+    bool pressure_bc = false;
+    for (int a = 0; a < 3; a++) pressure_bc = pressure_bc || b.bc_u[a][0] == INSB200_BC_PRESSURE || b.bc_u[a][1] == INSB200_BC_PRESSURE;
+    if (pressure_bc) {
+        INSB_CUDA(cudaMemsetAsync(G, 0, (size_t)9 * g.cs * sizeof(T), L.stream));
+        INSB_CUDA(cudaMemsetAsync(visc, 0, (size_t)g.cs * sizeof(T), L.stream));
+    }
     les_gradient_kernel<T><<<gr, blk, 0, L.stream>>>(g, u, G);
     if (L.counter) ++*L.counter;
     INSB_TRY(launch_zero_out_wall<T>(g, b, G, 9, L));

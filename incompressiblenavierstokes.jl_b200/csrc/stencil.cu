@@ -693,7 +693,13 @@ static int launch_stage_pair(const Grid<T> &g, const StageArgs<T> &a, Launch L) 
 template <typename T, typename CT, int D>
 static int launch_stage_t(const Grid<T> &g, const StageArgs<T> &a, Launch L, int xb, int xe) {
     if (xe < 0) xe = g.N[0];
-    dim3 b(xe - xb <= 8 ? 8 : 64, xe - xb <= 8 ? 32 : 4, 1);
+    // narrow strips (the remainder next to the marching kernel's tiles): no idle x lanes
+    int bx = 64;
+    if (xe - xb <= 8) {
+        bx = 1;
+        while (bx < xe - xb) bx <<= 1;
+    }
+    dim3 b(bx, 256 / bx, 1);
     dim3 gr((xe - xb + b.x - 1) / b.x, (g.N[1] + b.y - 1) / b.y, D == 3 ? g.N[2] : 1);
     bool full = a.conv && a.diff;
     StageArgs<T> aa = a;
