@@ -113,6 +113,15 @@ def run_case(args, case, rank, world):
         res[name] = I.gather_global(sd, st["state"]["u"])
         res[name + "_cfl"] = float(I.propose_timestep(I.navierstokes_, st["state"], sd, params, plan=psd.plan))
         res[name + "_umax"] = I.maxabs(st["state"]["u"], sd, plan=psd.plan)
+    # eddy-viscosity closure inside the stepper (9 tensor components through the halo exchange),
+    # total kinetic energy (all-reduced sum), vorticity
+    les = dict(viscosity=2e-3, eddyviscosity=I.WALE(0.569))
+    st = I.create_stepper(I.RKMethods.RK44(T), setup=sd, psolver=psd, state={"u": ud.clone()}, t=0.0)
+    for _ in range(args.steps):
+        st = I.timestep_(I.RKMethods.RK44(T), I.navierstokes_, st, dt, params=les)
+    res["LES"] = I.gather_global(sd, st["state"]["u"])
+    res["tke"] = float(I.total_kinetic_energy(st["state"]["u"], sd, plan=psd.plan))
+    res["vort"] = I.gather_global(sd, I.vorticity(st["state"]["u"], sd))
 
     if rank == 0:
         u1 = I.to_device(s1, ug)
@@ -136,6 +145,15 @@ def run_case(args, case, rank, world):
             report(name + "_cfl", abs(res[name + "_cfl"] - c1) / c1, 1e-6)
             m1 = I.maxabs(st["state"]["u"], s1)
             report(name + "_umax", abs(res[name + "_umax"] - m1) / m1, 1e-6)
+        st = I.create_stepper(I.RKMethods.RK44(T), setup=s1, psolver=ps1, state={"u": u1.clone()}, t=0.0)
+        for _ in range(args.steps):
+            st = I.timestep_(I.RKMethods.RK44(T), I.navierstokes_, st, dt, params=les)
+        report("LES_WALE_RK44", rel(res["LES"], I.to_host(st["state"]["u"])), tol)
+        e1 = float(I.total_kinetic_energy(st["state"]["u"], s1))
+        report("total_kinetic_energy", abs(res["tke"] - e1) / e1, 1e-12 if T is np.float64 else 1e-6)
+        w1 = I.to_host(I.vorticity(st["state"]["u"], s1))
+        inner = (slice(1, -1),) * 3
+        report("vorticity", rel(res["vort"][inner], w1[inner]), tol)
         for o in out:
             o.update(world=world, n=n, dtype=args.dtype, problem=case)
             print(json.dumps(o), flush=True)
