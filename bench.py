@@ -94,7 +94,14 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def ready(self):
+        return self.proc is None or len(self.lines) > 0
+
+    def mark(self):
+        """start of the timed region: only samples taken from here on are reported"""
+        self.t0 = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
@@ -107,7 +114,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        t0 = getattr(self, "t0", 0.0)
+        inside = [ln for ts, ln in self.lines if ts >= t0]
+        if not inside and self.lines:  # region shorter than the sampling period: the sample closest to it
+            inside = [self.lines[-1][1]]
+        for ln in inside:
             f = [v.strip() for v in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -223,8 +234,20 @@ def run_gpu(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    # keep stepping (untimed) until nvidia-smi delivers its first sample, so that the clocks line
+    # really covers the timed region; all ranks take the same number of extra steps
+    for _ in range(200):
+        flag = torch.tensor([1 if (rank != 0 or sampler.ready()) else 0], device="cuda")
+        if world > 1:
+            dist.broadcast(flag, src=0)
+        if int(flag.item()):
+            break
+        stepper = I.timestep_(method, I.navierstokes_, stepper, dt, params=params)
+    ps.plan.profile_read()
+    l0 = ps.plan.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark()
     e0.record()
     for _ in range(args.steps):
         stepper = I.timestep_(method, I.navierstokes_, stepper, dt, params=params)
