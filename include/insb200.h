@@ -43,7 +43,10 @@ enum {
     INSB200_PSOLVER_SPECTRAL = 0,
     INSB200_PSOLVER_TRANSFORM = 1,
     INSB200_PSOLVER_TRIDIAGONAL = 2,
-    INSB200_PSOLVER_DEFAULT = 3 /* default_psolver, src/pressure.jl:58-78 */
+    INSB200_PSOLVER_DEFAULT = 3, /* default_psolver, src/pressure.jl:58-78 */
+    INSB200_PSOLVER_CG = 4       /* psolver_cg, src/pressure.jl:155-203: any boundary conditions / grids.
+                                  * default_psolver resolves to it where the reference would build the
+                                  * sparse direct solver (psolver_direct is not on the GPU path) */
 };
 
 /* The subset of the `Setup` NamedTuple (src/grid.jl:91-208) the hot path consumes.
@@ -80,6 +83,10 @@ typedef struct insb200_setup {
     int rank, world;
     /* 128-byte NCCL unique id from insb200_comm_unique_id(), identical on all ranks (world > 1). */
     const void *nccl_id;
+    /* psolver_cg keyword arguments (pressure.jl:157-161); 0 = the reference defaults
+     * (abstol 0, reltol sqrt(eps(T)), maxiter prod(Np)) */
+    double cg_abstol, cg_reltol;
+    long long cg_maxiter;
 } insb200_setup_t;
 
 /* `params` NamedTuple forwarded to force! (src/solver.jl:2-35,176) */
@@ -159,6 +166,8 @@ int insb200_applypressure(insb200_plan_t *plan, void *u, const void *p, void *st
 /* poisson!(psolver, p) = psolver(p) (src/pressure.jl:22): in place on the ghosted array,
  * touches only view(p, Ip) (pressure.jl:349-381, 255-317, 507-544). */
 int insb200_psolve(insb200_plan_t *plan, void *p, void *stream);
+/* Iterations the last psolver_cg solve of this plan took (0 for the FFT-type solvers). */
+int insb200_psolver_iterations(const insb200_plan_t *plan);
 /* project!(u, setup; psolver, p) (src/pressure.jl:42-55). p is caller scratch (ghosted scalar). */
 int insb200_project(insb200_plan_t *plan, void *u, void *p, void *stream);
 

@@ -219,7 +219,9 @@ int resolve_default_psolver(const insb200_plan *pl) {
         for (int b = 0; b < D; b++) ch = ch && (b == a || (isper[b] && isuni[b]));
         if (ch) return INSB200_PSOLVER_TRIDIAGONAL;
     }
-    return INSB200_PSOLVER_NONE;  // psolver_direct is outside the hot path
+    // the reference builds the sparse direct solver here (pressure.jl:71-77); on the GPU path the
+    // general fallback is psolver_cg (single GPU)
+    return pl->comm ? INSB200_PSOLVER_NONE : INSB200_PSOLVER_CG;
 }
 
 Launch L_of(insb200_plan *pl, void *stream) { return Launch{(cudaStream_t)stream, &pl->launches, pl}; }
@@ -756,6 +758,7 @@ int insb200_plan_ipc_import(insb200_plan_t *pl, const void *blobs) {
 }
 
 int insb200_plan_psolver(const insb200_plan_t *pl) { return pl ? pl->psolver : INSB200_PSOLVER_NONE; }
+int insb200_psolver_iterations(const insb200_plan_t *pl) { return pl ? poisson_iterations(pl->ps) : 0; }
 long long insb200_plan_workspace_bytes(const insb200_plan_t *pl) { return pl ? pl->bytes : 0; }
 long long insb200_launch_count(const insb200_plan_t *pl) { return pl ? pl->launches : 0; }
 
@@ -853,7 +856,11 @@ int insb200_psolve(insb200_plan_t *pl, void *p, void *stream) {
         return 1;
     }
     Scope sc(pl, (cudaStream_t)stream, 2);
-    return poisson_solve(pl->ps, p, L_of(pl, stream));
+    INSB_TRY(poisson_solve(pl->ps, p, L_of(pl, stream)));
+    if (pl->psolver == INSB200_PSOLVER_CG)  // the reference's CG returns p with its ghosts filled (p += alpha q, q padded)
+        return DISPATCH(launch_bc_p<float>(pl->gf, pl->bc, (float *)p, L_of(pl, stream)),
+                        launch_bc_p<double>(pl->gd, pl->bc, (double *)p, L_of(pl, stream)));
+    return 0;
     API_END
 }
 int insb200_project(insb200_plan_t *pl, void *u, void *p, void *stream) {
@@ -1019,7 +1026,8 @@ int insb200_solve_unsteady(insb200_plan_t *pl, int method, const double *A, cons
         }
         const double h = R(R(tend - tstart) / (double)nstep);
         cudaStream_t user_st = (cudaStream_t)stream;
-        const bool graph = use_graph && !pl->comm && !pl->prof && nstep > 2;
+        // (psolver_cg reads its residual back while iterating: not capturable)
+        const bool graph = use_graph && !pl->comm && !pl->prof && nstep > 2 && pl->psolver != INSB200_PSOLVER_CG;
         if (!graph) {
             for (long long it = 0; it < nstep && !stop; it++) {
                 INSB_TRY(step(stream, t, h));

@@ -199,6 +199,15 @@ struct Poisson;  // opaque
 int poisson_create(const insb200_setup_t &s, const int Ip[3][2], int kind, Comm *comm, Poisson **out);
 void poisson_destroy(Poisson *p);
 long long poisson_bytes(const Poisson *p);
+int poisson_iterations(const Poisson *p);  // psolver_cg: iterations of the last solve
+// ---- cg.cu ----
+struct CgSolver;
+int cg_create(const insb200_setup_t &s, const int Ip[3][2], double reltol, double abstol, long long maxiter,
+              CgSolver **out);
+void cg_destroy(CgSolver *c);
+long long cg_bytes(const CgSolver *c);
+int cg_iterations(const CgSolver *c);
+int cg_solve(CgSolver *c, void *p_ghosted, Launch L);
 // Optional source of the right-hand side: when given (and poisson_fuses_divergence), the first
 // pass of the solve evaluates divergence! + scalewithvolume! of the velocity `u` itself and
 // p_ghosted is only written (with the solution).  Tables are the ghosted Setup tables.

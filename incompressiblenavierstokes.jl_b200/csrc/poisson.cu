@@ -529,6 +529,7 @@ struct Poisson {
     void *peerS[8] = {}, *peerRv[8] = {};
     unsigned *peerFlags[8] = {};
     unsigned epoch = 0;
+    CgSolver *cg = nullptr;  // kind == INSB200_PSOLVER_CG: everything else in this struct is unused
     size_t wbytes = 0;
     size_t halo_slot = 0;
 };
@@ -705,6 +706,16 @@ int poisson_create(const insb200_setup_t &s, const int Ip[3][2], int kind, Comm 
         poisson_destroy(ps);
         return 1;
     };
+    if (kind == INSB200_PSOLVER_CG) {
+        if (comm_world(comm) > 1) return fail("psolver_cg is not decomposed: world > 1 needs an FFT-type solver");
+        if (cg_create(s, Ip, s.cg_reltol, s.cg_abstol, s.cg_maxiter, &ps->cg)) {
+            poisson_destroy(ps);
+            return 1;
+        }
+        ps->bytes = cg_bytes(ps->cg);
+        *out = ps;
+        return 0;
+    }
     // preconditions (utils.jl:4-15, pressure.jl:225-229, :406-435, utils.jl:53)
     for (int a = 0; a < D; a++) {
         bool wall = s.bc_u[a][0] == INSB200_BC_DIRICHLET && s.bc_u[a][1] == INSB200_BC_DIRICHLET;
@@ -869,6 +880,7 @@ int poisson_create(const insb200_setup_t &s, const int Ip[3][2], int kind, Comm 
 
 void poisson_destroy(Poisson *p) {
     if (!p) return;
+    if (p->cg) cg_destroy(p->cg);
     if (p->comm && p->flags) comm_disable_p2p_halo(p->comm, p->flags);
     if (p->p2p) {
         const int rank = comm_rank(p->comm), world = comm_world(p->comm);
@@ -885,6 +897,7 @@ void poisson_destroy(Poisson *p) {
 }
 
 long long poisson_bytes(const Poisson *p) { return p ? p->bytes : 0; }
+int poisson_iterations(const Poisson *p) { return p && p->cg ? cg_iterations(p->cg) : 0; }
 
 int poisson_ipc_export(Poisson *ps, void *blob) {
     if (!ps || !ps->comm) {
@@ -1328,6 +1341,7 @@ bool poisson_fuses_divergence(const Poisson *ps) {
 }
 
 int poisson_solve(Poisson *ps, void *p, Launch L, const DivSource *div) {
+    if (ps->cg) return cg_solve(ps->cg, p, L);
     return ps->f64 ? solve_t<double>(ps, (double *)p, L, div) : solve_t<float>(ps, (float *)p, L, div);
 }
 

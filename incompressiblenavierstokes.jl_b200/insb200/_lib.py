@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libinsb200.so")
 
 F32, F64 = 0, 1
 BC_PERIODIC, BC_DIRICHLET, BC_SYMMETRIC, BC_PRESSURE = 0, 1, 2, 3
-PSOLVER_NONE, PSOLVER_SPECTRAL, PSOLVER_TRANSFORM, PSOLVER_TRIDIAGONAL, PSOLVER_DEFAULT = -1, 0, 1, 2, 3
+PSOLVER_NONE, PSOLVER_SPECTRAL, PSOLVER_TRANSFORM, PSOLVER_TRIDIAGONAL, PSOLVER_DEFAULT, PSOLVER_CG = -1, 0, 1, 2, 3, 4
 
 
 class SetupStruct(C.Structure):
@@ -37,6 +37,9 @@ class SetupStruct(C.Structure):
         ("rank", C.c_int),
         ("world", C.c_int),
         ("nccl_id", C.c_void_p),
+        ("cg_abstol", C.c_double),
+        ("cg_reltol", C.c_double),
+        ("cg_maxiter", C.c_longlong),
     ]
 
 
@@ -96,6 +99,7 @@ _PROTOTYPES = {
         [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_int, C.POINTER(C.c_void_p),
          C.POINTER(C.c_void_p), C.c_int, C.c_double, C.c_double, C.c_int, C.POINTER(ParamsStruct), _P],
     ),
+    "insb200_psolver_iterations": (C.c_int, [_P]),
     "insb200_eddy_viscosity_closure": (C.c_int, [_P, C.c_int, C.c_double, _P, _P, _P]),
     "insb200_vorticity": (C.c_int, [_P, _P, _P, _P]),
     "insb200_interpolate_u_p": (C.c_int, [_P, _P, _P, _P]),

@@ -45,7 +45,7 @@ def _ptr(t):
 class Plan:
     """Owns an ``insb200_plan_t`` (device tables, Poisson workspace, stepper caches)."""
 
-    def __init__(self, setup: Setup, psolver=_lib.PSOLVER_NONE, tridiagonal_dir=-1, eig=None):
+    def __init__(self, setup: Setup, psolver=_lib.PSOLVER_NONE, tridiagonal_dir=-1, eig=None, cg=None):
         if not torch.cuda.is_available():
             raise Insb200Error("no CUDA device: insb200 has no CPU fallback")
         self.setup = setup
@@ -76,6 +76,9 @@ class Plan:
         s.has_temp = int(setup.bc_temp is not None)
         s.psolver = psolver
         s.tridiagonal_dir = tridiagonal_dir
+        if cg:
+            s.cg_abstol, s.cg_reltol = float(cg.get("abstol") or 0.0), float(cg.get("reltol") or 0.0)
+            s.cg_maxiter = int(cg.get("maxiter") or 0)
         s.device = torch.cuda.current_device() if setup.device is None else int(setup.device)
         s.rank, s.world = setup.rank, setup.world
         if setup.world > 1:
@@ -343,12 +346,14 @@ class PSolver:
     def __init__(self, setup, kind, **kw):
         self.setup = setup
         self.plan = Plan(setup, kind, **kw)
-        self.kind = {0: "spectral", 1: "transform", 2: "tridiagonal", -1: "none"}[self.plan.psolver]
+        self.kind = {0: "spectral", 1: "transform", 2: "tridiagonal", 4: "cg", -1: "none"}[self.plan.psolver]
         if self.plan.psolver == _lib.PSOLVER_NONE:
-            raise Insb200Error(
-                "default_psolver would pick psolver_direct for this setup, which is outside "
-                "the B200 hot path (SURVEY.md §2)"
-            )
+            raise Insb200Error("no Poisson solver is available for this setup (decomposed plans need an FFT-type solver)")
+
+    @property
+    def iterations(self):
+        """iterations of the last psolver_cg solve (0 for the FFT-type solvers)"""
+        return int(lib().insb200_psolver_iterations(self.plan.h))
 
     def __call__(self, p):
         check(lib().insb200_psolve(self.plan.h, _ptr(_chk(self.setup, p, False)), _stream()))
@@ -367,7 +372,14 @@ def psolver_tridiagonal(setup, dir=None, eig=None):
     return PSolver(setup, _lib.PSOLVER_TRIDIAGONAL, tridiagonal_dir=-1 if dir is None else int(dir), eig=eig)
 
 
+def psolver_cg(setup, abstol=None, reltol=None, maxiter=None):
+    """psolver_cg (src/pressure.jl:155-203): preconditioned conjugate gradients, any BC / grid."""
+    return PSolver(setup, _lib.PSOLVER_CG, cg=dict(abstol=abstol, reltol=reltol, maxiter=maxiter))
+
+
 def default_psolver(setup):
+    """default_psolver (src/pressure.jl:58-78); where the reference falls back to the sparse direct
+    solver this returns psolver_cg."""
     return PSolver(setup, _lib.PSOLVER_DEFAULT)
 
 

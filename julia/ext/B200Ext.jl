@@ -66,6 +66,9 @@ struct CSetup
     rank::Cint
     world::Cint
     nccl_id::Ptr{Cvoid}
+    cg_abstol::Cdouble              # psolver_cg keyword arguments, 0 = reference defaults
+    cg_reltol::Cdouble
+    cg_maxiter::Clonglong
 end
 
 struct CParams
@@ -114,7 +117,7 @@ mutable struct B200PSolver{S} <: Function
     end
 end
 
-const KINDS = (; spectral = Cint(0), transform = Cint(1), tridiagonal = Cint(2), default = Cint(3))
+const KINDS = (; spectral = Cint(0), transform = Cint(1), tridiagonal = Cint(2), default = Cint(3), cg = Cint(4))
 
 """
     psolver_b200(setup; kind = :default, dir = nothing)
@@ -122,7 +125,8 @@ const KINDS = (; spectral = Cint(0), transform = Cint(1), tridiagonal = Cint(2),
 B200 replacement of `psolver_spectral` / `psolver_transform` / `psolver_tridiagonal` /
 `default_psolver` (`src/pressure.jl:58-78, 215-545`).
 """
-function INS.psolver_b200(setup; kind = :default, dir = nothing, rank = 0, world = 1, nccl_id = C_NULL)
+function INS.psolver_b200(setup; kind = :default, dir = nothing, rank = 0, world = 1, nccl_id = C_NULL,
+        abstol = 0.0, reltol = 0.0, maxiter = 0)
     (; Δ, Δu, A_stag, N, xlims, boundary_conditions) = setup
     D = length(N)
     T = eltype(Δ[1])
@@ -161,13 +165,16 @@ function INS.psolver_b200(setup; kind = :default, dir = nothing, rank = 0, world
             Cint(rank),
             Cint(world),
             nccl_id,
+            Float64(abstol),
+            Float64(reltol),
+            Clonglong(maxiter),
         )
         out = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:insb200_plan_create, libinsb200), Cint, (Ref{CSetup}, Ref{Ptr{Cvoid}}), cs, out))
     end
     resolved = ccall((:insb200_plan_psolver, libinsb200), Cint, (Ptr{Cvoid},), out[])
-    resolved == -1 && error("default_psolver picks psolver_direct for this setup; not on the B200 path")
-    B200PSolver(out[], setup, (:spectral, :transform, :tridiagonal)[resolved+1])
+    resolved == -1 && error("no Poisson solver on the B200 path for this setup")
+    B200PSolver(out[], setup, (:spectral, :transform, :tridiagonal, :default, :cg)[resolved+1])
 end
 
 stream() = Ptr{Cvoid}(CUDA.stream().handle)

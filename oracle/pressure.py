@@ -382,3 +382,68 @@ def psolver_tridiagonal(setup, dir=None):
     psolve.fftscale = fftscale
     psolve.tables = tb
     return psolve
+
+
+# ---------------------------------------------------------------------------
+# psolver_cg (pressure.jl:135-203)
+# ---------------------------------------------------------------------------
+def create_laplace_diag(setup):
+    """create_laplace_diag (pressure.jl:136-153): z[I] = -p[I] / d over Ip."""
+    D, T = setup.D, setup.T
+    Ip = setup.Ip
+
+    def met(arr, dim, off=0):
+        v = arr[Ip[dim].start + off : Ip[dim].stop + off]
+        shape = [1] * D
+        shape[dim] = len(v)
+        return v.reshape(shape)
+
+    omega = met(setup.Delta[0], 0)
+    for a in range(1, D):
+        omega = omega * met(setup.Delta[a], a)
+    d = np.zeros(setup.Np, dtype=T)
+    for a in range(D):
+        d = d - omega / met(setup.Delta[a], a) * (T(1) / met(setup.DeltaU[a], a) + T(1) / met(setup.DeltaU[a], a, -1))
+
+    def laplace_diag(z, p):
+        z[Ip] = -p[Ip] / d
+        return z
+
+    return laplace_diag
+
+
+def psolver_cg(setup, abstol=0.0, reltol=None, maxiter=None, preconditioner=None):
+    """psolver_cg (pressure.jl:156-203): diagonally preconditioned conjugate gradients."""
+    T = setup.T
+    Ip = setup.Ip
+    reltol = np.sqrt(np.finfo(T).eps) if reltol is None else reltol
+    maxiter = int(np.prod(setup.Np)) if maxiter is None else maxiter
+    preconditioner = preconditioner or create_laplace_diag(setup)
+    r, L, q = scalarfield(setup), scalarfield(setup), scalarfield(setup)
+
+    def psolve(p):
+        q[...] = 0
+        r[...] = p
+        rho_prev = T(1)
+        residual = np.sqrt(np.sum(r[Ip] ** 2))
+        tolerance = max(T(reltol) * residual, T(abstol))
+        iteration = 0
+        p[...] = 0
+        while iteration < maxiter and residual > tolerance:
+            preconditioner(L, r)
+            rho = np.sum(L[Ip] * r[Ip])
+            beta = rho / rho_prev
+            q[...] = L + beta * q
+            _bc.apply_bc_p(q, T(0), setup)
+            ops.laplacian_(L, q, setup)
+            alpha = rho / np.sum(q[Ip] * L[Ip])
+            p += alpha * q
+            r[...] = r - alpha * L
+            rho_prev = rho
+            residual = np.sqrt(np.sum(r[Ip] ** 2))
+            iteration += 1
+        psolve.iterations = iteration
+        return p
+
+    psolve.kind = "cg"
+    return psolve

@@ -104,3 +104,29 @@ def test_manual_dct_matches_library(shape):
         )
     with pytest.raises(AssertionError):
         pressure.manual_dct_(u + 1j, 0, stuff)
+
+
+def test_psolver_cg_reproduces_manufactured_pressure():
+    """test/psolvers.jl:13-36 for psolver_cg, on grids / BCs the FFT-type solvers do not cover."""
+    import oracle as O
+    from oracle import bc as obc, operators as oops, pressure as opr
+
+    cases = [
+        ((O.tanh_grid(0, 1, 12, 1.2), O.tanh_grid(0, 1, 10, 1.1), O.cosine_grid(0, 1, 14)),
+         ((O.DirichletBC(), O.DirichletBC()),) * 3, False),
+        ((np.linspace(0, 1, 11), O.cosine_grid(0, 1, 8), np.linspace(0, 1, 13)),
+         ((O.DirichletBC(), O.PressureBC()), (O.SymmetricBC(), O.SymmetricBC()), (O.PeriodicBC(), O.PeriodicBC())), True),
+    ]
+    for x, bc, pinned in cases:
+        so = O.Setup(tuple(np.asarray(v) for v in x), {"u": bc})
+        pe = O.scalarfield(so)
+        pe[so.Ip] = np.random.default_rng(3).standard_normal(so.Np)
+        obc.apply_bc_p(pe, 0.0, so)
+        lap = oops.laplacian_(O.scalarfield(so), pe, so)
+        ps = opr.psolver_cg(so)
+        got = ps(lap.copy(order="F"))[so.Ip]
+        want = pe[so.Ip]
+        if not pinned:
+            got, want = got - got.mean(), want - want.mean()
+        assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-5
+        assert 0 < ps.iterations < np.prod(so.Np)
