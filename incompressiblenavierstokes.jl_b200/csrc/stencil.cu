@@ -88,12 +88,9 @@ __global__ void __launch_bounds__(256) stage_direct_kernel(Grid<T> g, StageArgs<
 
 
 // ------------------------------------------------------------------------------------
-// stage kernel, 2.5-D marching variant (3-D, momentum only): a block owns a TX x TY column of
-// cells and marches along z.  The planes z-1, z, z+1 of the three velocity components (with
-// a one-cell xy halo) sit in a 4-slot shared-memory ring; plane z+2 is prefetched into
-// registers while plane z is being computed and dropped into the free slot afterwards, so
-// there is a single barrier per plane.  Every velocity value is read from HBM/L2 once per
-// block column instead of ~45 times through L1 in the direct variant.
+// Shared-memory plane ring shared by the marching kernels: planes z-1, z, z+1 of a few fields
+// (with a one-cell xy halo) sit in shared memory, so every value is read from HBM/L2 once per
+// block column instead of dozens of times through L1 as in the direct variant.
 // ------------------------------------------------------------------------------------
 template <typename T, int PX, int PLANE>
 struct TileLoad {
@@ -126,128 +123,6 @@ template <typename T, typename CT>
 __device__ __forceinline__ T axpy_ct(T x, CT c, T k) {
     return (T)add_rn((CT)x, mul_rn(c, (CT)k));
 }
-
-// ACC: also update the running accumulator; GEN: general tableau (k storage / previous stages)
-template <typename T, typename CT, int TX, int TY, int ZC, bool ACC, bool GEN>
-__global__ void __launch_bounds__(TX *TY) stage_tile_kernel(Grid<T> g, StageDev<T, CT> a) {
-    constexpr int PX = TX + 2, PY = TY + 2, PLANE = PX * PY, NT = TX * TY, NE = 3 * PLANE;
-    constexpr int NL = (NE + NT - 1) / NT;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *s = reinterpret_cast<T *>(smem_raw);  // [4 slots][3 comps][PY][PX]
-    T *zt = s + 4 * NE;                      // [8 tables][ZC + 2]: z metrics of this chunk
-    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
-    const int x0 = 1 + blockIdx.x * TX, y0 = 1 + blockIdx.y * TY;
-    const int zbeg = 1 + blockIdx.z * ZC;
-    const int zend = min(zbeg + ZC, g.N[2] - 1);
-    if (zbeg >= zend) return;
-    // z metrics: rdlg[z], rdlg[z+1], rdu[z], a2[z], a1[z+1], rdug[z-1], rdug[z], rdl[z]
-    for (int e = tid; e < 8 * (ZC + 2); e += NT) {
-        int tb = e / (ZC + 2), r = e - tb * (ZC + 2);
-        int z = min(zbeg + r, g.N[2] - 2);
-        const T *src = tb == 0 ? g.rdlg[2] + z : tb == 1 ? g.rdlg[2] + z + 1 : tb == 2 ? g.rdu[2] + z
-                     : tb == 3 ? g.a2[2] + z : tb == 4 ? g.a1[2] + z + 1 : tb == 5 ? g.rdug[2] + z - 1
-                     : tb == 6 ? g.rdug[2] + z : g.rdl[2] + z;
-        zt[e] = *src;
-    }
-    // this thread's share of a haloed plane: element e = (comp, py, px) -> running pointers
-    const T *lp[NL];
-    bool lv[NL];
-#pragma unroll
-    for (int i = 0; i < NL; i++) {
-        int e = tid + i * NT;
-        int c = e / PLANE, r = e - c * PLANE;
-        int py = r / PX, px = r - py * PX;
-        int gx = min(x0 - 1 + px, g.N[0] - 1), gy = min(y0 - 1 + py, g.N[1] - 1);
-        lv[i] = e < NE;
-        const T *base = c == 0 ? a.u[0] : c == 1 ? a.u[1] : a.u[2];
-        lp[i] = base + gx + (long long)gy * g.s[1] + (long long)(zbeg - 1) * g.s[2];
-    }
-    T reg[NL];
-    const long long zs = g.s[2];
-    auto load_plane = [&]() {  // loads the plane the running pointers stand on, then advances them
-#pragma unroll
-        for (int i = 0; i < NL; i++) {
-            if (lv[i]) reg[i] = __ldg(lp[i]);
-            lp[i] += zs;
-        }
-    };
-    auto store_plane = [&](int z) {
-        T *dst = s + (z & 3) * NE + tid;
-#pragma unroll
-        for (int i = 0; i < NL; i++)
-            if (lv[i]) dst[i * NT] = reg[i];
-    };
-    for (int p = -1; p <= 1; p++) {
-        load_plane();
-        store_plane(zbeg + p);
-    }
-    const int I0 = x0 + tx, I1 = y0 + ty;
-    const bool active = I0 < g.N[0] - 1 && I1 < g.N[1] - 1;
-    const int Ic0 = min(I0, g.N[0] - 2), Ic1 = min(I1, g.N[1] - 2);
-    RegMetrics<T> M;
-    {
-        const int Ic[2] = {Ic0, Ic1};
-#pragma unroll
-        for (int d = 0; d < 2; d++) {
-            M.v_rdlg[d][0] = g.rdlg[d][Ic[d]];
-            M.v_rdlg[d][1] = g.rdlg[d][Ic[d] + 1];
-            M.v_rdug[d][0] = g.rdug[d][Ic[d] - 1];
-            M.v_rdug[d][1] = g.rdug[d][Ic[d]];
-            M.v_rdu[d] = g.rdu[d][Ic[d]];
-            M.v_rdl[d] = g.rdl[d][Ic[d]];
-            M.v_a2[d] = g.a2[d][Ic[d]];
-            M.v_a1p[d] = g.a1[d][Ic[d] + 1];
-        }
-    }
-    __syncthreads();
-    const int lidx = (ty + 1) * PX + tx + 1;
-    unsigned q = (unsigned)(Ic0 + (long long)Ic1 * g.s[1] + (long long)zbeg * g.s[2]);  // cell offset (< 2^32)
-    const unsigned qs = (unsigned)g.s[2];
-    const T nu = a.nu;
-    for (int z = zbeg; z < zend; z++, q += qs) {
-        const bool more = z + 1 < zend;
-        if (more) load_plane();
-        if (active) {
-            // pointwise operands first, so that their latency overlaps the stencil arithmetic
-            T vb[3], ai[3];
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                vb[c] = a.vbase[c][q];
-                ai[c] = ACC ? a.acc_in[c][q] : T(0);
-            }
-            const int r = z - zbeg;
-            M.v_rdlg[2][0] = zt[0 * (ZC + 2) + r];
-            M.v_rdlg[2][1] = zt[1 * (ZC + 2) + r];
-            M.v_rdu[2] = zt[2 * (ZC + 2) + r];
-            M.v_a2[2] = zt[3 * (ZC + 2) + r];
-            M.v_a1p[2] = zt[4 * (ZC + 2) + r];
-            M.v_rdug[2][0] = zt[5 * (ZC + 2) + r];
-            M.v_rdug[2][1] = zt[6 * (ZC + 2) + r];
-            M.v_rdl[2] = zt[7 * (ZC + 2) + r];
-            TileLoad<T, PX, PLANE> U;
-            U.pl[0] = s + ((z - 1) & 3) * NE + lidx;
-            U.pl[1] = s + (z & 3) * NE + lidx;
-            U.pl[2] = s + ((z + 1) & 3) * NE + lidx;
-            T k[3];
-            momentum_rhs_m<T, 3, true>(U, M, nu, T(1), k);
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                T kc = k[c] + a.bf[c];
-                T x = vb[c];
-                if (GEN) {
-                    if (a.k_out[0]) a.k_out[c][q] = kc;
-#pragma unroll 1
-                    for (int j = 0; j < a.nprev; j++) x = axpy_ct<T, CT>(x, a.cprev[j], a.kprev[j][c][q]);
-                }
-                a.v[c][q] = axpy_ct<T, CT>(x, a.cv, kc);
-                if (ACC) a.acc_out[c][q] = axpy_ct<T, CT>(ai[c], a.ca, kc);
-            }
-        }
-        if (more) store_plane(z + 2);
-        __syncthreads();
-    }
-}
-
 
 // ------------------------------------------------------------------------------------
 // stage kernel v3 ("pair" kernel): like the marching kernel above, but
@@ -600,39 +475,6 @@ __global__ void __launch_bounds__(32 * TY, sizeof(T) == 4 ? 2 : 1) stage_pair_ke
     }
 }
 
-template <typename T, typename CT>
-static int launch_stage_tile(const Grid<T> &g, const StageArgs<T> &a, Launch L) {
-    constexpr int TX = 32, TY = 16, ZC = 128;
-    constexpr size_t smem = ((size_t)4 * 3 * (TX + 2) * (TY + 2) + 8 * (ZC + 2)) * sizeof(T);
-    const bool acc = a.acc_out != nullptr, gen = a.k_out != nullptr || a.nprev > 0;
-    auto kern = acc ? (gen ? stage_tile_kernel<T, CT, TX, TY, ZC, true, true> : stage_tile_kernel<T, CT, TX, TY, ZC, true, false>)
-                    : (gen ? stage_tile_kernel<T, CT, TX, TY, ZC, false, true> : stage_tile_kernel<T, CT, TX, TY, ZC, false, false>);
-    INSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    StageDev<T, CT> d{};
-    for (int c = 0; c < 3; c++) {
-        d.u[c] = a.u + c * g.cs;
-        d.vbase[c] = a.vbase ? a.vbase + c * g.cs : nullptr;
-        d.v[c] = a.v ? a.v + c * g.cs : nullptr;
-        d.acc_in[c] = a.acc_in ? a.acc_in + c * g.cs : nullptr;
-        d.acc_out[c] = a.acc_out ? a.acc_out + c * g.cs : nullptr;
-        d.k_out[c] = a.k_out ? a.k_out + c * g.cs : nullptr;
-        for (int j = 0; j < a.nprev; j++) d.kprev[j][c] = a.kprev[j] + c * g.cs;
-        d.bf[c] = (T)a.bodyforce[c];
-    }
-    d.nprev = a.nprev;
-    for (int j = 0; j < a.nprev; j++) d.cprev[j] = (CT)a.cprev[j];
-    d.cv = (CT)a.cv;
-    d.ca = (CT)a.ca;
-    d.nu = (T)a.nu;
-    int nz = g.N[2] - 2;
-    dim3 b(TX, TY, 1);
-    dim3 gr((g.N[0] - 2 + TX - 1) / TX, (g.N[1] - 2 + TY - 1) / TY, (nz + ZC - 1) / ZC);
-    kern<<<gr, b, smem, L.stream>>>(g, d);
-    if (L.counter) ++*L.counter;
-    INSB_CUDA(cudaGetLastError());
-    return 0;
-}
-
 template <typename T, typename CT, int D>
 static int launch_stage_t(const Grid<T> &g, const StageArgs<T> &a, Launch L, int xb = 0, int xe = -1);
 
@@ -757,6 +599,93 @@ __global__ void __launch_bounds__(256) bouss_extra_kernel(Grid<T> g, StageArgs<T
     }
 }
 
+// Shared-memory variant of the pass above: the direct kernel issues ~70 loads per cell through L1
+// (the dissipation term averages every off-diagonal derivative over four corners); here a block
+// marches a TX x TY column along z with the planes z-1, z, z+1 of (u_x, u_y, u_z, temp) and a
+// one-cell halo in a 4-slot ring (next plane prefetched into registers during the arithmetic), so
+// every value comes from HBM/L2 once per block column.
+template <typename T, typename CT, int TX, int TY, int ZC>
+__global__ void __launch_bounds__(TX *TY) bouss_tile_kernel(Grid<T> g, StageArgs<T> a) {
+    constexpr int PX = TX + 2, PY = TY + 2, PLANE = PX * PY, NT = TX * TY, NE = 4 * PLANE;
+    constexpr int NL = (NE + NT - 1) / NT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *s = reinterpret_cast<T *>(smem_raw);  // [4 slots][u_x, u_y, u_z, temp][PY][PX]
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
+    const int x0 = 1 + blockIdx.x * TX, y0 = 1 + blockIdx.y * TY;
+    const int zbeg = 1 + blockIdx.z * ZC;
+    const int zend = min(zbeg + ZC, g.N[2] - 1);
+    if (zbeg >= zend) return;
+    const T *lp[NL];
+    bool lv[NL];
+#pragma unroll
+    for (int i = 0; i < NL; i++) {
+        int e = min(tid + i * NT, NE - 1);
+        int c = e / PLANE, r = e - c * PLANE;
+        int py = r / PX, px = r - py * PX;
+        int gx = min(x0 - 1 + px, g.N[0] - 1), gy = min(y0 - 1 + py, g.N[1] - 1);
+        lv[i] = tid + i * NT < NE;
+        const T *base = c < 3 ? a.u + c * g.cs : a.temp;
+        lp[i] = base + gx + (long long)gy * g.s[1] + (long long)(zbeg - 1) * g.s[2];
+    }
+    T reg[NL];
+    const long long zs = g.s[2];
+    auto load_plane = [&]() {
+#pragma unroll
+        for (int i = 0; i < NL; i++) {
+            if (lv[i]) reg[i] = __ldg(lp[i]);
+            lp[i] += zs;
+        }
+    };
+    auto store_plane = [&](int z) {
+        T *dst = s + (z & 3) * NE + tid;
+#pragma unroll
+        for (int i = 0; i < NL; i++)
+            if (lv[i]) dst[i * NT] = reg[i];
+    };
+    for (int p = -1; p <= 1; p++) {
+        load_plane();
+        store_plane(zbeg + p);
+    }
+    const int I0 = x0 + tx, I1 = y0 + ty;
+    const bool active = I0 < g.N[0] - 1 && I1 < g.N[1] - 1;
+    const int Ic0 = min(I0, g.N[0] - 2), Ic1 = min(I1, g.N[1] - 2);
+    __syncthreads();
+    const int lidx = (ty + 1) * PX + tx + 1;
+    long long idx = Ic0 + (long long)Ic1 * g.s[1] + (long long)zbeg * g.s[2];
+    for (int z = zbeg; z < zend; z++, idx += zs) {
+        const bool more = z + 1 < zend;
+        if (more) load_plane();
+        if (active) {
+            const int I[3] = {Ic0, Ic1, z};
+            TileLoad<T, PX, PLANE> U, Tm;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                U.pl[k] = s + ((z - 1 + k) & 3) * NE + lidx;
+                Tm.pl[k] = U.pl[k] + 3 * PLANE;
+            }
+            const T kt = temperature_rhs<T, 3>(U, Tm, g, I, (T)a.kappa, (T)a.nu, a.dodiss != 0);
+            if (a.tk_out) a.tk_out[idx] = kt;
+            if (a.tv) {
+                T x = a.tvbase[idx];
+                for (int j = 0; j < a.nprev; j++) x = axpy_rn<T, CT>(x, a.cprev[j], a.tkprev[j][idx]);
+                a.tv[idx] = axpy_rn<T, CT>(x, a.cv, kt);
+            }
+            if (a.tacc_out) a.tacc_out[idx] = axpy_rn<T, CT>(a.tacc_in[idx], a.ca, kt);
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                if (c != a.gdir) continue;
+                const T gk = (T)a.grav * avg_face<3>(Tm, g, I, c, 0);
+                const long long q = idx + c * g.cs;
+                if (a.k_out) a.k_out[q] += gk;
+                if (a.v) a.v[q] = axpy_rn<T, CT>(a.v[q], a.cv, gk);
+                if (a.acc_out) a.acc_out[q] = axpy_rn<T, CT>(a.acc_out[q], a.ca, gk);
+            }
+        }
+        if (more) store_plane(z + 2);
+        __syncthreads();
+    }
+}
+
 template <typename T, typename CT>
 static int launch_stage_bouss_split(const Grid<T> &g, const StageArgs<T> &a, Launch L) {
     StageArgs<T> m = a;  // momentum without the temperature coupling
@@ -764,6 +693,19 @@ static int launch_stage_bouss_split(const Grid<T> &g, const StageArgs<T> &a, Lau
     m.temp = nullptr;
     m.tv = m.tacc_out = m.tk_out = nullptr;
     INSB_TRY((launch_stage_pair<T, CT>(g, m, L)));
+    // measured at 512x512x256 (cfg 4): Float32 2.07 -> 1.60 ms per launch with the tile kernel, Float64
+    // 3.05 -> 3.30 ms (table loads, not field loads, dominate there): tiles for Float32 only
+    const char *te = getenv("INSB200_BOUSS_TILE");
+    if (te ? atoi(te) != 0 : sizeof(T) == 4) {
+        constexpr int TX = 32, TY = 8, ZC = 64;
+        constexpr size_t smem = (size_t)4 * 4 * (TX + 2) * (TY + 2) * sizeof(T);
+        dim3 b(TX, TY, 1);
+        dim3 gr((g.N[0] - 2 + TX - 1) / TX, (g.N[1] - 2 + TY - 1) / TY, (g.N[2] - 2 + ZC - 1) / ZC);
+        bouss_tile_kernel<T, CT, TX, TY, ZC><<<gr, b, smem, L.stream>>>(g, a);
+        if (L.counter) ++*L.counter;
+        INSB_CUDA(cudaGetLastError());
+        return 0;
+    }
     dim3 b(64, 4, 1);
     dim3 gr((g.N[0] - 2 + b.x - 1) / b.x, (g.N[1] - 2 + b.y - 1) / b.y, g.N[2] - 2);
     bouss_extra_kernel<T, CT><<<gr, b, 0, L.stream>>>(g, a);
@@ -780,7 +722,6 @@ struct WideOf {
 template <typename T>
 int launch_stage(const Grid<T> &g, const StageArgs<T> &a, bool ct_double, Launch L) {
     static const bool force_direct = getenv("INSB200_DIRECT_STAGE") != nullptr;
-    static const bool use_v2 = getenv("INSB200_STAGE_V2") != nullptr;
     const bool no_split = getenv("INSB200_BOUSS_DIRECT") != nullptr;
     if (g.D == 3 && a.bouss && a.temp && a.conv && a.diff && !a.zero_outside && !a.add_to_k && !force_direct &&
         !no_split && a.v != nullptr && 3 * g.cs < (1LL << 32)) {
@@ -789,10 +730,6 @@ int launch_stage(const Grid<T> &g, const StageArgs<T> &a, bool ct_double, Launch
     }
     if (g.D == 3 && !a.bouss && a.conv && a.diff && !a.zero_outside && !a.add_to_k && !force_direct &&
         a.v != nullptr && 3 * g.cs < (1LL << 32)) {
-        if (use_v2) {
-            if (sizeof(T) == 8 || ct_double) return launch_stage_tile<T, double>(g, a, L);
-            return launch_stage_tile<T, T>(g, a, L);
-        }
         if (sizeof(T) == 8 || ct_double) return launch_stage_pair<T, double>(g, a, L);
         return launch_stage_pair<T, T>(g, a, L);
     }

@@ -117,8 +117,8 @@ def test_boussinesq_split_matches_single_kernel(T):
     temp0 = obc.apply_bc_temp(random_scal(so, 42), 0.0, so)
     params = dict(viscosity=1e-2, conductivity=2e-2, gdir=2, gravity=1.0, dodissipation=True)
     res = {}
-    for tag, val in (("split", None), ("direct", 1)):
-        with env(INSB200_BOUSS_DIRECT=val):
+    for tag, val, tile in (("split", None, 1), ("split_notile", None, 0), ("direct", 1, None)):
+        with env(INSB200_BOUSS_DIRECT=val, INSB200_BOUSS_TILE=tile):
             for mname in ("RK44", "Wray3"):
                 m = getattr(I.RKMethods, mname)(T)
                 st = {"u": I.to_device(sg, u0), "temp": I.to_device(sg, temp0)}
@@ -130,6 +130,7 @@ def test_boussinesq_split_matches_single_kernel(T):
     for mname in ("RK44", "Wray3"):
         for k in (0, 1):
             assert rel_l2(res["split", mname][k], res["direct", mname][k]) < tol, (mname, k)
+            assert np.array_equal(res["split", mname][k], res["split_notile", mname][k]), (mname, k)
 
 
 def test_host_ensemble_matches_device_stepping():
