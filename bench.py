@@ -320,7 +320,7 @@ def run_gpu(args):
         from insb200._lib import lib, check
         from insb200.api import _params, _coef_dtype
 
-        ke = max(2, min(args.steps, 4))
+        ke = max(2, min(args.steps, 3 if world > 1 else 4))  # pinned host states per rank (1.6 GB each at 512^3)
         uhs = [torch.empty(u.shape, dtype=u.dtype, pin_memory=True) for _ in range(ke)]
         for uh in uhs:
             uh.copy_(stepper["state"]["u"])

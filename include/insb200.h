@@ -224,6 +224,12 @@ int insb200_kinetic_energy(insb200_plan_t *plan, void *ke, const void *u, int in
 int insb200_total_kinetic_energy(insb200_plan_t *plan, const void *u, int interpolate_first,
                                  double *out, void *stream);
 
+/* energyspectrum(u, setup) (src/spectral.jl:75-117) on a plan holding psolver_spectral (periodic,
+ * power-of-two extents, single GPU): the solver's FFT passes transform every component, the modes
+ * are binned into the shells kappa = 0..kmax (kmax < 0: minimum(Np) / 2, spectral_stuff :36); ehat
+ * receives kmax + 1 host doubles whose sum is the mean kinetic energy density.  Synchronises. */
+int insb200_energy_spectrum(insb200_plan_t *plan, const void *u, int kmax, double *ehat, void *stream);
+
 /* solve_unsteady (src/solver.jl:77-149): the time loop itself, so that a run of many small steps
  * does not return to the host language per step.
  *   method 0: explicit Runge-Kutta with the tableau (A, c, s, coef_dtype) of insb200_step_rk;

@@ -1222,6 +1222,33 @@ int insb200_total_kinetic_energy(insb200_plan_t *pl, const void *u, int interpol
     API_END
 }
 
+int insb200_energy_spectrum(insb200_plan_t *pl, const void *u, int kmax, double *ehat, void *stream) {
+    API_BEGIN
+    if (!pl->ps) {
+        set_error("energyspectrum needs a plan with psolver_spectral");
+        return 1;
+    }
+    if (kmax < 0) {  // spectral_stuff default: minimum(Np) / 2 (spectral.jl:36)
+        kmax = pl->s.N[0] - 2;
+        for (int a = 0; a < pl->D; a++) kmax = std::min(kmax, (pl->Ip[a][1] - pl->Ip[a][0]) / 2);
+    }
+    double *dev = nullptr;
+    INSB_CUDA(cudaMalloc((void **)&dev, (size_t)(kmax + 1) * sizeof(double)));
+    Launch L = L_of(pl, stream);
+    int rc = poisson_energy_spectrum(pl->ps, u, pl->ncell, kmax, dev, L);
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(ehat, dev, (size_t)(kmax + 1) * sizeof(double), cudaMemcpyDeviceToHost, L.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(L.stream);
+        if (e != cudaSuccess) {
+            set_error(std::string("energyspectrum: ") + cudaGetErrorString(e));
+            rc = 1;
+        }
+    }
+    cudaFree(dev);
+    return rc;
+    API_END
+}
+
 int insb200_maxabs(insb200_plan_t *pl, const void *u, double *out, void *stream) {
     API_BEGIN
     Launch L = L_of(pl, stream);

@@ -199,7 +199,9 @@ struct Poisson;  // opaque
 int poisson_create(const insb200_setup_t &s, const int Ip[3][2], int kind, Comm *comm, Poisson **out);
 void poisson_destroy(Poisson *p);
 long long poisson_bytes(const Poisson *p);
-int poisson_iterations(const Poisson *p);  // psolver_cg: iterations of the last solve
+int poisson_iterations(const Poisson *p);
+// energyspectrum (src/spectral.jl:75-117): ehat = kmax + 1 device doubles
+int poisson_energy_spectrum(Poisson *ps, const void *u, long long cs, int kmax, double *ehat, Launch L);  // psolver_cg: iterations of the last solve
 // ---- cg.cu ----
 struct CgSolver;
 int cg_create(const insb200_setup_t &s, const int Ip[3][2], double reltol, double abstol, long long maxiter,

@@ -899,6 +899,82 @@ void poisson_destroy(Poisson *p) {
 long long poisson_bytes(const Poisson *p) { return p ? p->bytes : 0; }
 int poisson_iterations(const Poisson *p) { return p && p->cg ? cg_iterations(p->cg) : 0; }
 
+// ----------------------------------------------------------------------------------------
+// energyspectrum (src/spectral.jl:75-117) with the solver's own FFT passes: per velocity
+// component x R2C -> y -> z forward transforms into the half-spectrum workspace, then
+// |u_hat|^2 / (2 N^2) is binned into the integer shells kappa <= |k| < kappa + 1, the modes
+// whose conjugate partner is not stored (0 < kx < n0/2) counted twice (spectral.jl:36-66).
+// ----------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) spectrum_bin_kernel(const Cx<T> *__restrict__ W, int m0, int m0p, int n0, int n1, int n2,
+                                                           int kmax, double scale, double *ehat) {
+    extern __shared__ double bins[];
+    for (int i = threadIdx.x; i <= kmax; i += blockDim.x) bins[i] = 0.0;
+    __syncthreads();
+    const long long total = (long long)m0 * n1 * n2;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+        const int kx = (int)(q % m0);
+        const int iy = (int)((q / m0) % n1), iz = (int)(q / ((long long)m0 * n1));
+        const int ky = iy < (n1 + 1) / 2 ? iy : iy - n1;  // fftfreq_int (spectral.jl:7)
+        const int kz = n2 > 1 ? (iz < (n2 + 1) / 2 ? iz : iz - n2) : 0;
+        const long long k2 = (long long)kx * kx + (long long)ky * ky + (long long)kz * kz;
+        int kap = (int)sqrt((double)k2);
+        while ((long long)kap * kap > k2) kap--;
+        while ((long long)(kap + 1) * (kap + 1) <= k2) kap++;
+        if (kap > kmax) continue;
+        const Cx<T> v = W[kx + (long long)iy * m0p + (long long)iz * m0p * n1];
+        const double w = (kx > 0 && kx < n0 / 2) ? 2.0 : 1.0;
+        atomicAdd(&bins[kap], w * scale * ((double)v.x * (double)v.x + (double)v.y * (double)v.y));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i <= kmax; i += blockDim.x)
+        if (bins[i] != 0.0) atomicAdd(ehat + i, bins[i]);
+}
+
+// u: ghosted velocity field (D components, stride cs); ehat: kmax + 1 device doubles (zeroed here)
+template <typename T>
+static int spectrum_t(Poisson *ps, const T *u, long long cs, int kmax, double *ehat, Launch L) {
+    const int D = ps->D;
+    long long rs[3] = {1, ps->Ng[0], (long long)ps->Ng[0] * ps->Ng[1]};
+    FastGeom g;
+    g.D = D;
+    for (int d = 0; d < 3; d++) {
+        g.n[d] = ps->n[d];
+        g.ws[d] = ps->wstride[d];
+        g.rs[d] = rs[d];
+    }
+    g.m0p = (int)ps->wstride[1];
+    const T *e0 = (const T *)ps->eig[0];
+    INSB_CUDA(cudaMemsetAsync(ehat, 0, (size_t)(kmax + 1) * sizeof(double), L.stream));
+    double np = 1.0;
+    for (int a = 0; a < D; a++) np *= (double)ps->n[a];
+    for (int c = 0; c < D; c++) {
+        T *R = const_cast<T *>(u) + c * cs;  // the R2C pass only reads R
+        for (int a = 0; a < D; a++) R += ps->ioff[a] * rs[a];
+        INSB_TRY(fast_pass<T>(3, ps->n[0], R, ps->W, g, 0, ps->tw[0], e0, e0, e0, T(1), 0, L));
+        INSB_TRY(fast_pass<T>(0, ps->n[1], R, ps->W, g, 1, ps->tw[1], e0, e0, e0, T(1), 0, L));
+        if (D == 3) INSB_TRY(fast_pass<T>(0, ps->n[2], R, ps->W, g, 2, ps->tw[2], e0, e0, e0, T(1), 0, L));
+        spectrum_bin_kernel<T><<<148 * 4, 256, (size_t)(kmax + 1) * sizeof(double), L.stream>>>(
+            (const Cx<T> *)ps->W, ps->m[0], g.m0p, ps->n[0], ps->n[1], D == 3 ? ps->n[2] : 1, kmax, 1.0 / (2.0 * np * np), ehat);
+        if (L.counter) ++*L.counter;
+    }
+    INSB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int poisson_energy_spectrum(Poisson *ps, const void *u, long long cs, int kmax, double *ehat, Launch L) {
+    if (!ps || !ps->fast || ps->comm) {
+        set_error("energyspectrum needs a single-GPU psolver_spectral plan on a power-of-two periodic grid");
+        return 1;
+    }
+    if (kmax < 0 || kmax > 4095) {
+        set_error("energyspectrum: kmax out of range");
+        return 1;
+    }
+    return ps->f64 ? spectrum_t<double>(ps, (const double *)u, cs, kmax, ehat, L)
+                   : spectrum_t<float>(ps, (const float *)u, cs, kmax, ehat, L);
+}
+
 int poisson_ipc_export(Poisson *ps, void *blob) {
     if (!ps || !ps->comm) {
         set_error("ipc export: the plan is not slab-decomposed");

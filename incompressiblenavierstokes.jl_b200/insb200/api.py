@@ -580,6 +580,15 @@ def total_kinetic_energy(u, setup, interpolate_first=False, plan=None):
     return setup.T(out.value)
 
 
+def energyspectrum(u, setup, psolver, kmax=None):
+    """energyspectrum (src/spectral.jl:75-117) -> dict(kappa, ehat); `psolver` must be the
+    psolver_spectral of this setup (its FFT passes and workspace are used)."""
+    kmax = min(setup.Np) // 2 if kmax is None else int(kmax)
+    out = (C.c_double * (kmax + 1))()
+    check(lib().insb200_energy_spectrum(psolver.plan.h, _ptr(_chk(setup, u, True)), kmax, out, _stream()))
+    return dict(kappa=np.arange(kmax + 1), ehat=np.array(out[:], dtype=setup.T))
+
+
 # ------------------------------------------------------------------------------------
 # processors (src/processors.jl): the call-back boundary of solve_unsteady
 # ------------------------------------------------------------------------------------

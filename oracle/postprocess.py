@@ -157,3 +157,34 @@ def total_kinetic_energy(u, setup, interpolate_first=False):
     k = kinetic_energy(u, setup, interpolate_first)
     k = scalewithvolume_(k, setup)
     return k[setup.Ip].sum()
+
+
+def energyspectrum(u, setup, kmax=None):
+    """energyspectrum (src/spectral.jl:75-117, shells of spectral_stuff :36-66): ehat[kappa] = sum over
+    kappa <= |k| < kappa + 1 of |u_hat|^2 / 2 with u_hat = rfft(u) / prod(Np), the modes whose
+    conjugate is not stored counted twice.  Returns (kappa, ehat)."""
+    import scipy.fft as sfft
+
+    D, Np = setup.D, setup.Np
+    kmax = min(Np) // 2 if kmax is None else kmax
+    axes = tuple(range(D - 1, -1, -1))  # real transform along dim 0 (Julia dim 1)
+    ntot = float(np.prod(Np))
+    efield = 0
+    for a in range(D):
+        uhat = sfft.rfftn(np.ascontiguousarray(u[setup.Ip + (a,)]).astype(np.float64), axes=axes)
+        efield = efield + np.abs(uhat) ** 2
+    efield = efield / (2 * ntot**2)
+    kx = np.arange(Np[0] // 2 + 1)
+    k2 = (kx**2).reshape((-1,) + (1,) * (D - 1)).astype(np.int64)
+    for a in range(1, D):
+        ka = np.fft.fftfreq(Np[a], 1.0 / Np[a]).astype(np.int64)
+        shape = [1] * D
+        shape[a] = Np[a]
+        k2 = k2 + (ka**2).reshape(shape)
+    shell = np.floor(np.sqrt(k2)).astype(np.int64)
+    shell = np.where((shell + 1) ** 2 <= k2, shell + 1, shell)
+    shell = np.where(shell**2 > k2, shell - 1, shell)
+    weight = np.where((kx > 0) & (kx < Np[0] // 2), 2.0, 1.0).reshape((-1,) + (1,) * (D - 1))
+    w = efield * weight
+    ehat = np.array([w[shell == kap].sum() for kap in range(kmax + 1)])
+    return np.arange(kmax + 1), ehat

@@ -78,3 +78,30 @@ def test_diagnostics_at_bench_size_properties():
     assert bool(torch.isfinite(w).all()) and bool(torch.isfinite(q).all())
     # omega_z = dv/dx - du/dy = 2 pi sin(2 pi x) sin(2 pi y) sin(2 pi z): max = 2 pi
     assert abs(float(w[2].abs().max()) - 2 * np.pi) < 2e-2
+
+
+@pytest.mark.parametrize("T", [np.float64, np.float32])
+@pytest.mark.parametrize("n", [(64, 32, 128), (128, 64)])
+def test_energy_spectrum_matches_oracle(n, T):
+    import insb200 as I
+
+    D = len(n)
+    so, sg = make_setups(tuple(uniform(m, 2 * np.pi) for m in n), ("P",) * D, T=T)
+    ps = I.psolver_spectral(sg)
+    u = smooth_vec(so, 121) + 0.05 * random_vec(so, 122)
+    kmax = int(np.sqrt(D) * max(n) / 2) + 1
+    for km in (None, kmax):
+        kap, want = opp.energyspectrum(u.astype(T), so, kmax=km)
+        got = I.energyspectrum(I.to_device(sg, u), sg, ps, kmax=km)
+        assert np.array_equal(got["kappa"], kap)
+        scale = want.max()
+        assert np.max(np.abs(got["ehat"].astype(np.float64) - want)) < (1e-12 if T is np.float64 else 2e-5) * scale
+    # Parseval with all shells
+    assert abs(float(got["ehat"].astype(np.float64).sum()) - 0.5 * np.mean(np.sum(u[so.Ip].astype(np.float64) ** 2, axis=-1))) < (
+        1e-11 if T is np.float64 else 1e-4)
+    # the Poisson solve still works afterwards (the workspace is shared)
+    f = smooth_vec(so, 123)[..., 0].copy(order="F")
+    a = I.to_host(ps(I.to_device(sg, f)))
+    I.energyspectrum(I.to_device(sg, u), sg, ps)
+    b = I.to_host(ps(I.to_device(sg, f)))
+    assert np.array_equal(a, b)

@@ -64,3 +64,30 @@ def test_3d_vorticity_of_rigid_rotation_and_energy_identity():
     q = opp.qcrit(u, so)
     mid = (slice(3, n - 2),) * 3
     assert np.allclose(q[mid], 1.0, atol=1e-12)
+
+
+def test_energy_spectrum_of_taylor_green_sits_in_one_shell():
+    """test/spectral.jl:9-25: TGV energy 1/4 (2-D) and 1/8 (3-D) in the shell kappa = 1."""
+    n = 32
+    so = _periodic(n, 2)
+    u = oini.velocityfield(so, lambda d, x, y: (-np.sin(x) * np.cos(y) if d == 0 else np.cos(x) * np.sin(y)) + 0 * x * y,
+                           doproject=False)
+    kap, e = opp.energyspectrum(u, so)
+    assert abs(e[1] - 0.25) < 1e-12 and abs(e.sum() - 0.25) < 1e-12
+    so = _periodic(n, 3)
+
+    def U(d, x, y, z):
+        if d == 0:
+            return np.sin(x) * np.cos(y) * np.cos(z)
+        if d == 1:
+            return -np.cos(x) * np.sin(y) * np.cos(z)
+        return 0 * x + 0 * y + 0 * z
+
+    u = oini.velocityfield(so, U, doproject=False)
+    kap, e = opp.energyspectrum(u, so)
+    assert abs(e[1] - 0.125) < 1e-12 and abs(e.sum() - 0.125) < 1e-12
+    # Parseval: the shells up to the corner wavenumber hold the mean kinetic energy density
+    rng = np.random.default_rng(0)
+    u = np.asfortranarray(rng.standard_normal(so.N + (3,)))
+    kap, e = opp.energyspectrum(u, so, kmax=int(np.sqrt(3) * n / 2) + 1)
+    assert abs(e.sum() - 0.5 * np.mean(np.sum(u[so.Ip] ** 2, axis=-1))) < 1e-12
