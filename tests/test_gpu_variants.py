@@ -234,3 +234,20 @@ def test_first_stage_reuses_ring_planes_bit_identical(T):
                 res[tag, mname] = I.to_host(sp["state"]["u"])
     for mname in ("RK44", "LMWray3", "FE11"):
         assert np.array_equal(res["ring", mname], res["fetched", mname]), mname
+
+
+def test_native_loop_graph_replay_with_large_shared_memory_kernels():
+    """CUDA-graph capture of a step whose FFT passes need > 48 KB of dynamic shared memory
+    (the launchers raise the limit with cudaFuncSetAttribute on every call, also while capturing)."""
+    I = ins()
+    T = np.float32
+    so, sg = make_setups((uniform(512), uniform(32), uniform(1024)), ("P", "P", "P"), T=T)
+    ps = I.psolver_spectral(sg)
+    u0 = I.to_device(sg, smooth_vec(so, 131))
+    I.project_(u0, sg, psolver=ps, p=I.scalarfield(sg))
+    I.apply_bc_u_(u0, 0.0, sg)
+    kw = dict(setup=sg, tlims=(0.0, 0.005), start={"u": u0}, method=I.RKMethods.RK44(T), psolver=ps, dt=0.001,
+              params=dict(viscosity=1e-3))
+    a, _ = I.solve_unsteady(native=False, **kw)
+    b, _ = I.solve_unsteady(native=True, graph=True, **kw)
+    assert np.array_equal(I.to_host(a["u"]), I.to_host(b["u"]))
