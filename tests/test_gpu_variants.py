@@ -246,8 +246,9 @@ def test_native_loop_graph_replay_with_large_shared_memory_kernels():
     u0 = I.to_device(sg, smooth_vec(so, 131))
     I.project_(u0, sg, psolver=ps, p=I.scalarfield(sg))
     I.apply_bc_u_(u0, 0.0, sg)
-    kw = dict(setup=sg, tlims=(0.0, 0.005), start={"u": u0}, method=I.RKMethods.RK44(T), psolver=ps, dt=0.001,
+    kw = dict(setup=sg, tlims=(0.0, 1e-4), start={"u": u0}, method=I.RKMethods.RK44(T), psolver=ps, dt=2e-5,
               params=dict(viscosity=1e-3))
     a, _ = I.solve_unsteady(native=False, **kw)
     b, _ = I.solve_unsteady(native=True, graph=True, **kw)
-    assert np.array_equal(I.to_host(a["u"]), I.to_host(b["u"]))
+    ua = I.to_host(a["u"])
+    assert np.all(np.isfinite(ua)) and np.array_equal(ua, I.to_host(b["u"]))
