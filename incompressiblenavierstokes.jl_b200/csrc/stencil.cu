@@ -480,7 +480,7 @@ static int launch_stage_t(const Grid<T> &g, const StageArgs<T> &a, Launch L, int
 
 template <typename T, typename CT, bool AL8>
 static int launch_stage_pair_a(const Grid<T> &g, const StageArgs<T> &a, Launch L, int nxt) {
-    constexpr int TY = 8, ZC = 128, DEPTH = 2;
+    constexpr int TY = 8, ZC = 128, DEPTH = 2;  // (DEPTH = 3 measured: rhs+combine 5.64 -> 6.06 ms/step)
     const bool acc = a.acc_out != nullptr, gen = a.k_out != nullptr || a.nprev > 0;
     const size_t smem = (size_t)(acc ? PairSmem<TY, ZC, DEPTH, true>::total : PairSmem<TY, ZC, DEPTH, false>::total) * sizeof(T);
     const bool same = !gen && a.vbase == a.u && (!acc || a.acc_in == a.u) && getenv("INSB200_STAGE_NO_SAME") == nullptr;
