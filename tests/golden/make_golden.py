@@ -85,11 +85,60 @@ def compute(name, x, bcs, kind, fk, params, dt, T):
         return out
 
 
+EXTRA_CASES = ("box3d_periodic_f64", "channel3d_f64", "box3d_periodic_f32")
+LES_MODELS = (("smagorinsky", 0.17), ("wale", 0.569), ("vreman", 0.28), ("qr", 0.092))
+
+
+def compute_extras(name, x, bcs, kind, fk, params, dt, T):
+    """Rows N2-N4 of SURVEY.md §8f on the same grids: eddy-viscosity closure terms and an LES step,
+    field diagnostics, energy spectrum (periodic boxes), psolver_cg."""
+    from oracle import eddyviscosity as oev, postprocess as opp
+
+    xs = tuple(np.asarray(v).astype(T) for v in x)
+    so = O.Setup(xs, bcs)
+    ps = getattr(opr, "psolver_" + kind)(so)
+    rng = np.random.default_rng(sum(map(ord, name)) + 1)
+    u = (0.5 * rng.standard_normal(so.N + (so.D,))).astype(T, order="F")
+    obc.apply_bc_u(u, 0.0, so)
+    u0 = opr.project(u, so, ps)
+    obc.apply_bc_u(u0, 0.0, so)
+    out = {"u0": u0}
+    for model, C in LES_MODELS:
+        f = np.zeros_like(u0)
+        oev.eddy_viscosity_closure_(model, C, f, u0, so)
+        out["les_" + model] = f
+    force = ots.make_navierstokes_eddy(so, params["viscosity"], "wale", 0.569, (1.0, 0.0, 0.0))
+    m = ots.RK44(T)
+    st = {"u": u0.copy(order="F")}
+    sp = ots.create_stepper(m, so, ps, st, 0.0)
+    cache = ots.get_cache(m, st, so)
+    for _ in range(2):
+        sp = ots.timestep_(m, force, sp, T(dt), cache)
+    out["les_wale_rk44_u"] = sp["state"]["u"]
+    out["vorticity"] = opp.vorticity(u0, so)
+    out["u_p"] = opp.interpolate_u_p(u0, so)
+    out["vorticity_p"] = opp.interpolate_omega_p(out["vorticity"], so)
+    out["qcrit"] = opp.qcrit(u0, so)
+    out["ke"] = opp.kinetic_energy(u0, so)
+    out["ke_first"] = opp.kinetic_energy(u0, so, True)
+    out["total_ke"] = np.array([opp.total_kinetic_energy(u0, so), opp.total_kinetic_energy(u0, so, True)], dtype=np.float64)
+    if kind == "spectral":
+        out["spectrum"] = opp.energyspectrum(u0, so)[1]
+    rhs = oops.scalewithvolume_(oops.divergence_(O.scalarfield(so), u, so), so)
+    out["cg_rhs"] = rhs
+    out["cg_sol"] = opr.psolver_cg(so, reltol=1e-13 if T is np.float64 else 1e-6)(rhs.copy(order="F"))
+    return out
+
+
 def main():
     for case in cases():
         out = compute(*case)
         np.savez_compressed(os.path.join(HERE, case[0] + ".npz"), **out)
         print(case[0], {k: v.shape for k, v in out.items()})
+        if case[0] in EXTRA_CASES:
+            out = compute_extras(*case)
+            np.savez_compressed(os.path.join(HERE, case[0] + "_extras.npz"), **out)
+            print(case[0] + "_extras", sorted(out))
 
 
 if __name__ == "__main__":
