@@ -29,7 +29,7 @@ for p in (ROOT, PKG):
 import numpy as np  # noqa: E402
 
 # ncu --set full, bytes per launch (average over the 4 launches of an RK44 step where they differ)
-NCU_TRAFFIC_SOURCE = "profiles/r1b_ncu_full_summary.md (dram__bytes_read.sum + dram__bytes_write.sum per launch)"
+NCU_TRAFFIC_SOURCE = "profiles/r1e_ncu_full_summary.md (dram__bytes_read.sum + dram__bytes_write.sum per launch)"
 NCU_TRAFFIC = {"rhs_combine": 6.58e9, "divergence": 2.15e9, "project": 3.73e9, "poisson": 5.27e9}
 
 METRIC = "cell-updates/s per RK44 step (TGV3D N^3)"

@@ -219,9 +219,10 @@ __global__ void __launch_bounds__(256) halo_pull_kernel(char *field, size_t plan
         while ((int)(*f - epoch) < 0) {
             unsigned long long t1;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 20000000000ULL) {  // 20 s: a peer died; do not hang the device
-                *timeout_flag = 1;
-                break;
+            if (t1 - t0 > 20000000000ULL) {  // 20 s: a peer died; fail loudly instead of hanging or
+                *timeout_flag = 1;           // continuing with stale ghost planes
+                __threadfence_system();
+                __trap();
             }
         }
         __threadfence_system();
@@ -347,9 +348,10 @@ __global__ void wait_flags_kernel(unsigned *flags, int row, int world, unsigned 
         while ((int)(*f - epoch) < 0) {
             unsigned long long t1;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 20000000000ULL) {  // 20 s: a peer died; do not hang the device
-                *timeout_flag = 1;
-                break;
+            if (t1 - t0 > 20000000000ULL) {  // 20 s: a peer died; fail loudly (sticky launch error)
+                *timeout_flag = 1;           // instead of hanging or transforming stale data
+                __threadfence_system();
+                __trap();
             }
         }
     }
