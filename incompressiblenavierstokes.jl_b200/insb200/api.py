@@ -700,6 +700,157 @@ def _solve_native(setup, method, force, stepper, tend, dt, dt_min, cfl, n_adapt_
     return stepper
 
 
+def _interior(setup, t, vector):
+    """host copy of view(f, Ip[, :]) in the reference layout -- the device -> host staging of a
+    plotted / saved frame moves the interior of ONE derived field, not the state"""
+    a = to_host(t)
+    return np.ascontiguousarray(a[setup.slices(setup.Ip) + ((slice(None),) if vector else ())])
+
+
+def observefield(state, *, setup, fieldname, psolver=None):
+    """observefield (src/processors.jl:85-144): an Observable holding the host copy of a derived
+    field on the pressure points; the derived fields are computed on the device (diag.cu)."""
+    state = state if isinstance(state, Observable) else Observable(state)
+    D = setup.D
+    buf = {}
+
+    def compute(st):
+        u = st["u"]
+        if fieldname in (1, 2, 3):
+            buf["up"] = interpolate_u_p_(buf.get("up") if "up" in buf else vectorfield(setup), u, setup)
+            return _interior(setup, buf["up"][fieldname - 1], False)
+        if fieldname == "velocity":
+            buf["up"] = interpolate_u_p_(buf.get("up") if "up" in buf else vectorfield(setup), u, setup)
+            return _interior(setup, buf["up"], True)
+        if fieldname == "velocitynorm":
+            buf["ke"] = kinetic_energy_(buf.get("ke") if "ke" in buf else scalarfield(setup), u, setup)
+            return np.sqrt(2 * _interior(setup, buf["ke"], False))
+        if fieldname == "vorticity":
+            apply_bc_u_(u, st.get("t", 0.0), setup)
+            w = vorticity_(buf.get("w") if "w" in buf else (scalarfield(setup) if D == 2 else vectorfield(setup)), u, setup)
+            buf["w"] = w
+            wp = interpolate_omega_p_(buf.get("wp") if "wp" in buf else torch.zeros_like(w), w, setup)
+            buf["wp"] = wp
+            return _interior(setup, wp, D == 3)
+        if fieldname == "qcrit":
+            buf["q"] = qcrit_(buf.get("q") if "q" in buf else scalarfield(setup), u, setup)
+            return _interior(setup, buf["q"], False)
+        if fieldname == "temperature":
+            return _interior(setup, st["temp"], False)
+        raise ValueError("Unknown fieldname")
+
+    field = Observable(compute(state.value))
+    state.on(lambda st: setattr(field, "value", compute(st)))
+    return field
+
+
+def observespectrum(state, *, setup, psolver):
+    """observespectrum (src/processors.jl:249-277) -> dict(ehat=Observable, kappa=...); the spectrum is
+    evaluated by the psolver_spectral plan's FFT passes (insb200_energy_spectrum)."""
+    state = state if isinstance(state, Observable) else Observable(state)
+    first = energyspectrum(state.value["u"], setup, psolver)
+    ehat = Observable(first["ehat"])
+    state.on(lambda st: setattr(ehat, "value", energyspectrum(st["u"], setup, psolver)["ehat"]))
+    return dict(ehat=ehat, kappa=first["kappa"])
+
+
+def _write_vtr(filename, coords, fields, t):
+    """Minimal VTK XML rectilinear-grid (.vtr) writer, ASCII point data at the pressure points
+    (what WriteVTK's vtk_grid(filename, xp...) produces for the reference, processors.jl:163-190)."""
+    dims = [len(c) for c in coords] + [1] * (3 - len(coords))
+    ext = " ".join(f"0 {n - 1}" for n in dims)
+
+    def arr(name, data, ncomp=1):
+        flat = " ".join(repr(float(v)) for v in np.asarray(data, dtype=np.float64).ravel())
+        return (f'<DataArray type="Float64" Name="{name}" NumberOfComponents="{ncomp}" format="ascii">{flat}</DataArray>')
+
+    out = ['<?xml version="1.0"?>', '<VTKFile type="RectilinearGrid" version="1.0" byte_order="LittleEndian">',
+           f'<RectilinearGrid WholeExtent="{ext}">', '<FieldData>', arr("TimeValue", [t]), '</FieldData>',
+           f'<Piece Extent="{ext}">', '<PointData>']
+    for name, f in fields.items():
+        if isinstance(f, tuple):  # vector: components interleaved per point, x fastest
+            comps = [np.asarray(c, dtype=np.float64).ravel(order="F") for c in f]
+            out.append(arr(name, np.stack(comps, axis=1), len(comps)))
+        else:
+            out.append(arr(name, np.asarray(f, dtype=np.float64).ravel(order="F")))
+    out += ['</PointData>', '<Coordinates>']
+    for i in range(3):
+        out.append(arr("xyz"[i], coords[i] if i < len(coords) else [0.0]))
+    out += ['</Coordinates>', '</Piece>', '</RectilinearGrid>', '</VTKFile>']
+    if not filename.endswith(".vtr"):
+        filename += ".vtr"
+    with open(filename, "w") as fh:
+        fh.write("\n".join(out))
+    return filename
+
+
+def snapshotsaver(state, *, setup, fieldnames=("velocity",), psolver=None):
+    """snapshotsaver (src/processors.jl:150-190): returns savesnapshot(filename) writing the observed
+    fields at the pressure points to a .vtr file; 2-D vectors get a zero z-component."""
+    state = state if isinstance(state, Observable) else Observable(state)
+    D = setup.D
+    coords = [np.asarray(setup.xp[a][setup.Ip[a][0]:setup.Ip[a][1]], dtype=np.float64) for a in range(D)]
+    fields = {fn: observefield(state, setup=setup, fieldname=fn, psolver=psolver) for fn in fieldnames}
+
+    def savesnapshot(filename, pvd=None):
+        data = {}
+        for fn, f in fields.items():
+            g = f.value
+            if g.ndim == D:
+                data[str(fn)] = g
+            else:
+                comps = [g[..., c] for c in range(g.shape[-1])]
+                if D == 2:
+                    comps.append(np.zeros_like(comps[0]))
+                data[str(fn)] = tuple(comps)
+        path = _write_vtr(filename, coords, data, float(state.value.get("t", 0.0)))
+        if pvd is not None:
+            pvd.append((float(state.value.get("t", 0.0)), path))
+        return path
+
+    return savesnapshot
+
+
+def save_vtk(state, *, setup, filename="output/solution", **kwargs):
+    """save_vtk (src/processors.jl:197-202)."""
+    d = os.path.dirname(filename)
+    if d:
+        os.makedirs(d, exist_ok=True)
+    return snapshotsaver(state, setup=setup, **kwargs)(filename)
+
+
+def vtk_writer(setup, nupdate=1, dir="output", filename="solution", **kwargs):
+    """vtk_writer (src/processors.jl:210-230): a .vtr file every nupdate steps + a ParaView .pvd
+    collection written by finalize."""
+
+    def initialize(outer):
+        os.makedirs(dir, exist_ok=True)
+        pvd = []
+        inner = Observable(outer.value)
+        save = snapshotsaver(inner, setup=setup, **kwargs)
+
+        def cb(st):
+            if st["n"] % nupdate:
+                return
+            inner.value = st
+            save(os.path.join(dir, f"{filename}_t={str(float(st['t'])).replace('.', 'p')}"), pvd)
+
+        outer.on(cb)
+        cb(outer.value)
+        return pvd
+
+    def finalize(pvd, state):
+        lines = ['<?xml version="1.0"?>', '<VTKFile type="Collection" version="1.0">', '<Collection>']
+        lines += [f'<DataSet timestep="{t!r}" part="0" file="{os.path.basename(p)}"/>' for t, p in pvd]
+        lines += ['</Collection>', '</VTKFile>']
+        path = os.path.join(dir, filename + ".pvd")
+        with open(path, "w") as fh:
+            fh.write("\n".join(lines))
+        return path
+
+    return processor(initialize, finalize, nupdate=nupdate)
+
+
 def solve_unsteady(*, setup, tlims, start, force=navierstokes_, docopy=True, method=None, psolver=None,
                    dt=None, dt_min=None, cfl=None, n_adapt_dt=1, processors=None, params, native=True, graph=True):
     """solve_unsteady (src/solver.jl:77-149).  native=True runs the loop inside the library

@@ -105,3 +105,57 @@ def test_energy_spectrum_matches_oracle(n, T):
     I.energyspectrum(I.to_device(sg, u), sg, ps)
     b = I.to_host(ps(I.to_device(sg, f)))
     assert np.array_equal(a, b)
+
+
+def test_field_observers_and_vtk_output(tmp_path):
+    """observefield / observespectrum / vtk_writer (src/processors.jl:85-277) over the device diagnostics."""
+    import xml.etree.ElementTree as ET
+
+    import insb200 as I
+
+    so, sg = make_setups((uniform(32, 2 * np.pi), uniform(32, 2 * np.pi), uniform(32, 2 * np.pi)), ("P", "P", "P"))
+    ps = I.psolver_spectral(sg)
+    u = opr_project(smooth_vec(so, 141), so)
+    ud = I.to_device(sg, u)
+    st = I.Observable({"u": ud, "t": 0.0, "n": 0})
+    Ip = so.Ip
+    want = {
+        "velocity": opp.interpolate_u_p(u, so)[Ip],
+        2: opp.interpolate_u_p(u, so)[Ip + (1,)],
+        "velocitynorm": np.sqrt(2 * opp.kinetic_energy(u, so)[Ip]),
+        "vorticity": opp.interpolate_omega_p(opp.vorticity(u, so), so)[Ip],
+        "qcrit": opp.qcrit(u, so)[Ip],
+    }
+    for fn, w in want.items():
+        f = I.observefield(st, setup=sg, fieldname=fn)
+        assert f.value.shape == w.shape and rel_l2(f.value, w) < 1e-13, fn
+    spec = I.observespectrum(st, setup=sg, psolver=ps)
+    assert np.allclose(spec["ehat"].value, opp.energyspectrum(u, so)[1], rtol=0, atol=1e-12 * spec["ehat"].value.max())
+    # observers follow the state
+    f = I.observefield(st, setup=sg, fieldname="velocitynorm")
+    st.value = {"u": 2 * ud, "t": 0.1, "n": 1}
+    assert rel_l2(f.value, 2 * want["velocitynorm"]) < 1e-13
+    assert np.allclose(spec["ehat"].value, 4 * opp.energyspectrum(u, so)[1], rtol=1e-12)
+    # VTK output through solve_unsteady
+    out, outputs = I.solve_unsteady(setup=sg, tlims=(0.0, 0.02), start={"u": ud}, method=I.RKMethods.RK44(), psolver=ps,
+                                    dt=0.005, params=dict(viscosity=1e-2),
+                                    processors={"vtk": I.vtk_writer(sg, nupdate=2, dir=str(tmp_path), filename="sol",
+                                                                    fieldnames=("velocity", "qcrit"))})
+    pvd = ET.parse(outputs["vtk"]).getroot()
+    files = [d.attrib["file"] for d in pvd.iter("DataSet")]
+    assert len(files) == 3  # n = 0, 2, 4
+    root = ET.parse(str(tmp_path / files[-1])).getroot()
+    arrays = {a.attrib["Name"]: a for a in root.iter("DataArray")}
+    assert {"velocity", "qcrit", "TimeValue", "x", "y", "z"} <= set(arrays)
+    vel = np.array(arrays["velocity"].text.split(), dtype=np.float64).reshape(-1, 3)
+    up = I.to_host(I.interpolate_u_p(out["u"], sg))[Ip]
+    assert np.allclose(vel[:, 0], up[..., 0].ravel(order="F")) and np.allclose(vel[:, 2], up[..., 2].ravel(order="F"))
+    assert abs(float(arrays["TimeValue"].text) - 0.02) < 1e-12
+
+
+def opr_project(u, so):
+    from oracle import bc as obc, pressure as opr
+
+    u = opr.project(u, so, opr.psolver_spectral(so))
+    obc.apply_bc_u(u, 0.0, so)
+    return u
