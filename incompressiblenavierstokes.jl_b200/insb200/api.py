@@ -42,6 +42,77 @@ def _ptr(t):
 # ------------------------------------------------------------------------------------
 # plans
 # ------------------------------------------------------------------------------------
+class BcPlanes:
+    """Function-valued DirichletBC (src/boundary_conditions.jl:341-372): the user function cannot
+    cross the C ABI, so the host evaluates it on the boundary-plane coordinates -- `bcfunc(α, x..., t)`
+    over the plane `boundary(β, N, Iu[α], isright)`, all of the other dimensions -- into small device
+    buffers that every plan of the setup holds pointers to (insb200_set_bc_u_plane).  `refresh(t)`
+    re-evaluates them (time-dependent functions: once per stage time); `dudt=True` gives the centred
+    time derivative with step sqrt(eps)/2 (:348-354) used by right_hand_side!."""
+
+    def __init__(self, setup):
+        self.setup = setup
+        self.funcs = setup.bc_functions()
+        if self.funcs and setup.world > 1:
+            raise NotImplementedError("function-valued DirichletBC on a decomposed grid")
+        self.planes = {}
+        self.state = None
+        if not self.funcs:
+            self.time_dependent = False
+            return
+        a = self._evaluate(0.0, False)
+        b = self._evaluate(0.7853981, False)
+        self.time_dependent = any(not np.array_equal(a[k], b[k]) for k in a)
+        for k, v in a.items():
+            self.planes[k] = torch.from_numpy(v).to(_dev(setup))
+        self.state = (0.0, False)
+
+    def _evaluate(self, t, dudt):
+        sg = self.setup
+        D, T = sg.D, sg.T
+        out = {}
+        for beta, side, fn in self.funcs:
+            for a in range(D):
+                lo, hi = sg.Iu[a][beta]
+                i = hi if side else lo - 1
+                xs = []
+                for g in range(D):
+                    c = sg.xu[a][g][i:i + 1] if g == beta else sg.xu[a][g]
+                    shape = [1] * D
+                    shape[g] = len(c)
+                    xs.append(c.reshape(shape))
+                if dudt:
+                    h = T(np.sqrt(np.finfo(T).eps) / 2)
+                    val = (fn(a, *xs, T(t) + h) - fn(a, *xs, T(t) - h)) / (2 * h)
+                else:
+                    val = fn(a, *xs, T(t))
+                shape = [1 if g == beta else sg.N[g] for g in range(D)]
+                full = np.broadcast_to(np.asarray(val, dtype=T), shape)
+                # plane element (i1, i2) over the remaining dimensions, first one fastest
+                out[beta, side, a] = np.ascontiguousarray(np.squeeze(full, axis=beta).T if D == 3 else np.squeeze(full, axis=beta))
+        return out
+
+    def attach(self, plan):
+        for (beta, side, a), tns in self.planes.items():
+            check(lib().insb200_set_bc_u_plane(plan.h, beta, side, a, _ptr(tns)))
+
+    def refresh(self, t, dudt=False):
+        if not self.funcs:
+            return
+        want = (float(t) if (self.time_dependent or dudt) else 0.0, bool(dudt))
+        if self.state == want:
+            return
+        for k, v in self._evaluate(want[0], dudt).items():
+            self.planes[k].copy_(torch.from_numpy(v))
+        self.state = want
+
+
+def _bc_planes(setup) -> BcPlanes:
+    if "bcplanes" not in setup._plans:
+        setup._plans["bcplanes"] = BcPlanes(setup)
+    return setup._plans["bcplanes"]
+
+
 class Plan:
     """Owns an ``insb200_plan_t`` (device tables, Poisson workspace, stepper caches)."""
 
@@ -89,6 +160,7 @@ class Plan:
         check(lib().insb200_plan_create(C.byref(s), C.byref(h)))
         self.h = h
         self.psolver = lib().insb200_plan_psolver(h)
+        _bc_planes(setup).attach(self)
         self.p2p = False
         if setup.world > 1 and self.psolver != _lib.PSOLVER_NONE and not os.environ.get("INSB200_NO_P2P"):
             self._enable_p2p()
@@ -256,6 +328,7 @@ def _chk(setup, t, vector):
 # boundary conditions and operators
 # ------------------------------------------------------------------------------------
 def apply_bc_u_(u, t, setup, dudt=False, plan=None):
+    _bc_planes(setup).refresh(t, dudt)
     pl = plan or _base_plan(setup)
     check(lib().insb200_apply_bc_u(pl.h, _ptr(_chk(setup, u, True)), float(t), int(dudt), _stream()))
     return u
@@ -319,9 +392,10 @@ def diffusion(u, setup, viscosity):
     return diffusion_(torch.zeros_like(u), u, setup, viscosity)
 
 
-def navierstokes_(force, state, t, *, setup, cache=None, viscosity, bodyforce=None):
-    """navierstokes! (src/solver.jl:2-6): force["u"] is overwritten."""
-    pr = _params(setup, viscosity=viscosity, bodyforce=bodyforce)
+def navierstokes_(force, state, t, *, setup, cache=None, viscosity, bodyforce=None, eddyviscosity=None):
+    """navierstokes! (src/solver.jl:2-6): force["u"] is overwritten (with `eddyviscosity` the
+    eddy_viscosity_closure! term is added, examples/ChannelFlow.jl:177-182)."""
+    pr = _params(setup, viscosity=viscosity, bodyforce=bodyforce, eddyviscosity=eddyviscosity)
     check(lib().insb200_rhs(_base_plan(setup).h, _ptr(_chk(setup, state["u"], True)), None,
                             _ptr(_chk(setup, force["u"], True)), None, C.byref(pr), _stream()))
     return force
@@ -480,9 +554,62 @@ def _coef_dtype(method_T, dt):
     return _lib.F64 if np.result_type(method_T, dt_T) == np.float64 else _lib.F32
 
 
+def _timestep_staged(method, force, stepper, dt, params):
+    """timestep! composed stage by stage on the host (step_explicit_runge_kutta.jl:4-57,
+    step_lmwray3.jl:3-94) for setups whose Dirichlet functions depend on time: the boundary
+    planes are re-evaluated at every stage time tstart + c[i] Δt before apply_bc_u!.  Kernels are
+    the library's (insb200_rhs, ghost fills, project); the stage combine is a handful of axpys."""
+    setup, psolver, state, t0 = stepper["setup"], stepper["psolver"], stepper["state"], stepper["t"]
+    keys = [k for k in ("u", "temp") if k in state]
+    start = {k: state[k].clone() for k in keys}
+    p = scalarfield(setup)
+    T = setup.T
+
+    def rhs(st, t):
+        k = {kk: torch.zeros_like(st[kk]) for kk in keys}
+        force(k, st, t, setup=setup, **params)
+        return k
+
+    def finish(t):
+        apply_bc_u_(state["u"], t, setup, plan=psolver.plan)
+        project_(state["u"], setup, psolver=psolver, p=p)
+        apply_bc_u_(state["u"], t, setup, plan=psolver.plan)
+        if "temp" in state:
+            apply_bc_temp_(state["temp"], t, setup, plan=psolver.plan)
+
+    if isinstance(method, LMWray3):
+        a3, b3, c3 = (T(8 / 15), T(5 / 12), T(3 / 4)), (T(1 / 4), T(0)), (T(8 / 15), T(2 / 3), T(1))
+        for i in range(3):
+            k = rhs(state, t0 + (0 if i == 0 else float(c3[i - 1]) * dt))
+            t = t0 + float(c3[i]) * dt
+            for kk in keys:
+                state[kk].copy_(start[kk]).add_(k[kk], alpha=float(T(a3[i] * T(dt))))
+            finish(t)
+            if i != 2:
+                for kk in keys:
+                    start[kk].add_(k[kk], alpha=float(T(b3[i] * T(dt))))
+    else:
+        A, c = np.asarray(method.A), method.c
+        ks = []
+        t = t0
+        for i in range(len(method.b)):
+            ks.append(rhs(state, t))
+            for kk in keys:
+                state[kk].copy_(start[kk])
+                for j in range(i + 1):
+                    state[kk].add_(ks[j][kk], alpha=float(dt) * float(A[i, j]))
+            t = t0 + float(c[i]) * dt
+            finish(t)
+    return create_stepper(method, setup=setup, psolver=psolver, state=state, t=t0 + dt, n=stepper["n"] + 1)
+
+
 def timestep_(method, force, stepper, dt, *, params=None, ode_cache=None, force_cache=None):
     """timestep! -- one fused library call per step."""
     setup, psolver, state = stepper["setup"], stepper["psolver"], stepper["state"]
+    planes = _bc_planes(setup)
+    if planes.time_dependent:
+        return _timestep_staged(method, force, stepper, dt, dict(params or {}))
+    planes.refresh(stepper["t"])
     pr = _force_params(force, setup, params)
     u = _chk(setup, state["u"], True)
     temp = _chk(setup, state["temp"], False) if "temp" in state and pr.boussinesq else None
@@ -865,7 +992,7 @@ def solve_unsteady(*, setup, tlims, start, force=navierstokes_, docopy=True, met
     obs = Observable(get_state(stepper))
     processors = processors or {}
     initialized = {k: p.initialize(obs) for k, p in processors.items()}
-    if native and force in (navierstokes_, boussinesq_):
+    if native and force in (navierstokes_, boussinesq_) and not _bc_planes(setup).time_dependent:
         import math
 
         every = 0
@@ -904,6 +1031,9 @@ def solve_unsteady(*, setup, tlims, start, force=navierstokes_, docopy=True, met
 # ------------------------------------------------------------------------------------
 def right_hand_side_(dudt, u, params_ref, t):
     setup, psolver, viscosity = params_ref
+    if _bc_planes(setup).funcs:
+        raise NotImplementedError("right_hand_side! with function-valued DirichletBC: compose apply_bc_u_(u, t), "
+                                  "navierstokes_, apply_bc_u_(dudt, t, dudt=True) and project_ on the host")
     pr = _params(setup, viscosity=viscosity)
     check(lib().insb200_right_hand_side(psolver.plan.h, _ptr(_chk(setup, dudt, True)), _ptr(_chk(setup, u, True)),
                                         float(t), C.byref(pr), _stream()))

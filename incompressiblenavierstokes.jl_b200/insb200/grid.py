@@ -202,6 +202,11 @@ class Setup:
         """Half-open index ranges -> tuple of slices for a (N1, N2[, N3]) NumPy view."""
         return tuple(slice(lo, hi) for lo, hi in rng)
 
+    def bc_functions(self):
+        """[(dim, side, fn)] of the function-valued DirichletBC(u), u(dim, x..., t) (boundary_conditions.jl:7-20)"""
+        return [(d, side, self.bc_u[d][side].u) for d in range(self.D) for side in (0, 1)
+                if isinstance(self.bc_u[d][side], DirichletBC) and callable(self.bc_u[d][side].u)]
+
     def bc_constants(self):
         """Dirichlet constants as (u_val[d][side][comp], temp_val[d][side]); function-valued
         BCs are not representable here and raise."""
@@ -213,10 +218,9 @@ class Setup:
                 bc = self.bc_u[d][side]
                 if isinstance(bc, DirichletBC) and bc.u is not None:
                     if callable(bc.u):
-                        raise NotImplementedError(
-                            "function-valued DirichletBC must be supplied as planes "
-                            "(insb200_set_bc_u_plane); see INTEGRATION.md"
-                        )
+                        # function-valued: evaluated on the plane coordinates by the host and handed
+                        # to the library as planes (api.BcPlanes, insb200_set_bc_u_plane)
+                        continue
                     for c in range(D):
                         uval[d, side, c] = float(bc.u[c])
                 if self.bc_temp is not None:
