@@ -89,7 +89,8 @@ class BcPlanes:
                 shape = [1 if g == beta else sg.N[g] for g in range(D)]
                 full = np.broadcast_to(np.asarray(val, dtype=T), shape)
                 # plane element (i1, i2) over the remaining dimensions, first one fastest
-                out[beta, side, a] = np.ascontiguousarray(np.squeeze(full, axis=beta).T if D == 3 else np.squeeze(full, axis=beta))
+                plane = np.squeeze(full, axis=beta)
+                out[beta, side, a] = np.array(plane.T if D == 3 else plane, dtype=T, order="C", copy=True)
         return out
 
     def attach(self, plan):
