@@ -91,3 +91,24 @@ def test_energy_spectrum_of_taylor_green_sits_in_one_shell():
     u = np.asfortranarray(rng.standard_normal(so.N + (3,)))
     kap, e = opp.energyspectrum(u, so, kmax=int(np.sqrt(3) * n / 2) + 1)
     assert abs(e.sum() - 0.5 * np.mean(np.sum(u[so.Ip] ** 2, axis=-1))) < 1e-12
+
+
+def test_random_field_spectrum_matches_target_profile():
+    """test/spectral.jl:29-56: random_field is divergence free on the staggered grid and its spectrum
+    (energyspectrum, an independent restatement) equals the Orlandi target in every shell."""
+    from oracle import operators as oops
+
+    for D in (2, 3):
+        n = 64 if D == 2 else 32
+        x = tuple(np.linspace(0.0, 1.0, n + 1) for _ in range(D))
+        so = O.Setup(x, {"u": ((O.PeriodicBC(), O.PeriodicBC()),) * D})
+        total, kpeak = 0.3, 5
+        u = oini.random_field(so, 0.0, totalenergy=total, kpeak=kpeak, rng=np.random.default_rng(123))
+        div = oops.divergence_(O.scalarfield(so), u, so)
+        assert np.max(np.abs(div[so.Ip])) < 1e-8
+        kdiag = int(np.floor(np.sqrt(sum((m // 2) ** 2 for m in so.Np))))
+        kap, e = opp.energyspectrum(u, so, kmax=kdiag)
+        target = oini.orlandi_profile(kap.astype(np.float64), kpeak=kpeak)
+        target = total * target / target.sum()
+        assert abs(e.sum() - total) < 1e-12
+        assert np.linalg.norm(e - target) <= 1e-8 * np.linalg.norm(target)
