@@ -210,14 +210,44 @@ end
 const B200Stepper = NamedTuple{(:setup, :psolver, :state, :t, :n),<:Tuple{Any,<:B200PSolver,Any,Any,Any}}
 const BuiltinForce = Union{typeof(navierstokes!),typeof(boussinesq!)}
 
-# Function-valued DirichletBC (src/boundary_conditions.jl:344-357): evaluate the user's
-# function on the plane coordinates at the stage times and hand the planes to the library.
-function refresh_bc!(ps::B200PSolver, t)
-    # No-slip / constant BCs need nothing.  For `DirichletBC(f::Function)` a caller evaluates
-    # `f.(α, xplane..., t)` into a CuArray and registers it with
-    #   ccall((:insb200_set_bc_u_plane, libinsb200), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Cvoid}), ...)
-    # once per stage time; the fused steppers below are used only when every BC is constant in
-    # time, otherwise `timestep!` falls back to the per-stage composition (see INTEGRATION.md).
+# Function-valued DirichletBC (src/boundary_conditions.jl:344-357): the closure cannot cross the C
+# ABI, so it is evaluated here on the boundary-plane coordinates -- exactly the broadcast of the
+# reference, `bcfunc.(α, xI..., t)` over the plane `boundary(β, N, Iu[α], isright)` -- into device
+# planes the plan keeps pointers to.  `dudt = true` uses the same centred difference (:348-354).
+# A time-independent function is evaluated once; a time-dependent one must be refreshed at every
+# stage time, so `timestep!` then uses the per-stage composition (INTEGRATION.md §3).
+const BCPLANES = IdDict{Any,Dict{NTuple{3,Int},Any}}()
+
+function refresh_bc!(ps::B200PSolver, t; dudt = false)
+    setup = ps.setup
+    (; boundary_conditions, xu, Iu, N) = setup
+    D = length(N)
+    T = eltype(setup.Δ[1])
+    planes = get!(() -> Dict{NTuple{3,Int},Any}(), BCPLANES, ps)
+    for β = 1:D, (side, isright) in ((1, false), (2, true))
+        bc = boundary_conditions.u[β][side]
+        (bc isa DirichletBC && bc.u isa Function) || continue
+        for α = 1:D
+            i = isright ? last(Iu[α].indices[β]) + 1 : first(Iu[α].indices[β]) - 1
+            xI = ntuple(g -> g == β ? Array(xu[α][g])[i:i] : Array(xu[α][g]), D)
+            xb = ntuple(g -> reshape(xI[g], ntuple(k -> k == g ? length(xI[g]) : 1, D)), D)
+            vals = if dudt
+                h = sqrt(eps(T)) / 2
+                (bc.u.(α, xb..., T(t) + h) .- bc.u.(α, xb..., T(t) - h)) ./ 2h
+            else
+                bc.u.(α, xb..., T(t))
+            end
+            host = T.(dropdims(collect(vals); dims = β))      # (other dims), first one fastest
+            key = (β, side, α)
+            if haskey(planes, key)
+                copyto!(planes[key], host)
+            else
+                planes[key] = CuArray(host)
+                check(ccall((:insb200_set_bc_u_plane, libinsb200), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Cvoid}),
+                    ps.plan, β - 1, side - 1, α - 1, devptr(planes[key])))
+            end
+        end
+    end
     nothing
 end
 
