@@ -68,30 +68,7 @@ class BcPlanes:
         self.state = (0.0, False)
 
     def _evaluate(self, t, dudt):
-        sg = self.setup
-        D, T = sg.D, sg.T
-        out = {}
-        for beta, side, fn in self.funcs:
-            for a in range(D):
-                lo, hi = sg.Iu[a][beta]
-                i = hi if side else lo - 1
-                xs = []
-                for g in range(D):
-                    c = sg.xu[a][g][i:i + 1] if g == beta else sg.xu[a][g]
-                    shape = [1] * D
-                    shape[g] = len(c)
-                    xs.append(c.reshape(shape))
-                if dudt:
-                    h = T(np.sqrt(np.finfo(T).eps) / 2)
-                    val = (fn(a, *xs, T(t) + h) - fn(a, *xs, T(t) - h)) / (2 * h)
-                else:
-                    val = fn(a, *xs, T(t))
-                shape = [1 if g == beta else sg.N[g] for g in range(D)]
-                full = np.broadcast_to(np.asarray(val, dtype=T), shape)
-                # plane element (i1, i2) over the remaining dimensions, first one fastest
-                plane = np.squeeze(full, axis=beta)
-                out[beta, side, a] = np.array(plane.T if D == 3 else plane, dtype=T, order="C", copy=True)
-        return out
+        return self.setup.evaluate_bc_planes(t, dudt)
 
     def attach(self, plan):
         for (beta, side, a), tns in self.planes.items():

@@ -207,6 +207,34 @@ class Setup:
         return [(d, side, self.bc_u[d][side].u) for d in range(self.D) for side in (0, 1)
                 if isinstance(self.bc_u[d][side], DirichletBC) and callable(self.bc_u[d][side].u)]
 
+    def evaluate_bc_planes(self, t, dudt=False):
+        """{(dim, side, comp): plane} of every function-valued DirichletBC at time t: the reference's
+        `u[I, α] .= bcfunc.(α, xI..., t)` over the plane `boundary(β, N, Iu[α], isright)` spanning the full
+        (ghosted) extent of the other dimensions (src/boundary_conditions.jl:341-372), or its centred
+        time derivative with step sqrt(eps)/2 (:348-354).  Plane element (i1, i2) over the remaining
+        dimensions sits at i1 + N[d1] * i2 (what insb200_set_bc_u_plane expects)."""
+        D, T = self.D, self.T
+        out = {}
+        for beta, side, fn in self.bc_functions():
+            for a in range(D):
+                lo, hi = self.Iu[a][beta]
+                i = hi if side else lo - 1
+                xs = []
+                for g in range(D):
+                    c = self.xu[a][g][i:i + 1] if g == beta else self.xu[a][g]
+                    shape = [1] * D
+                    shape[g] = len(c)
+                    xs.append(c.reshape(shape))
+                if dudt:
+                    h = T(np.sqrt(np.finfo(T).eps) / 2)
+                    val = (fn(a, *xs, T(t) + h) - fn(a, *xs, T(t) - h)) / (2 * h)
+                else:
+                    val = fn(a, *xs, T(t))
+                shape = [1 if g == beta else self.N[g] for g in range(D)]
+                plane = np.squeeze(np.broadcast_to(np.asarray(val, dtype=T), shape), axis=beta)
+                out[beta, side, a] = np.array(plane.T if D == 3 else plane, dtype=T, order="C", copy=True)
+        return out
+
     def bc_constants(self):
         """Dirichlet constants as (u_val[d][side][comp], temp_val[d][side]); function-valued
         BCs are not representable here and raise."""
