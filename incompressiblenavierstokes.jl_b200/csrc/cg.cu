@@ -170,15 +170,32 @@ __global__ void __launch_bounds__(256) cg_update_kernel(CgDev<T> g, T *__restric
     block_sum2(a, b, part_a, part_b);
 }
 
-// one thread: add the block partials in index order and derive the scalars
+// one block: add the block partials (fixed assignment + fixed tree order: deterministic) and derive
+// the scalars.  (A single thread walking the 2 x 592 partials took 40 us per call -- more than the
+// field passes of a small problem; profiles/r1e_ncu_secondary_summary.md.)
 //   mode 0 (after init / update): res2 = sum a, rho_prev = rho, rho = sum b, beta = rho / rho_prev
 //   mode 1 (after laplacian):     qL = sum a, alpha = rho / qL
-__global__ void cg_finish_kernel(const double *part_a, const double *part_b, int n, double *S, int mode, int first) {
+__global__ void __launch_bounds__(256) cg_finish_kernel(const double *part_a, const double *part_b, int n, double *S,
+                                                        int mode, int first) {
+    __shared__ double sa[256], sb[256];
     double a = 0.0, b = 0.0;
-    for (int i = 0; i < n; i++) {
+    for (int i = threadIdx.x; i < n; i += 256) {
         a += part_a[i];
         b += part_b[i];
     }
+    sa[threadIdx.x] = a;
+    sb[threadIdx.x] = b;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            sa[threadIdx.x] += sa[threadIdx.x + s];
+            sb[threadIdx.x] += sb[threadIdx.x + s];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x != 0) return;
+    a = sa[0];
+    b = sb[0];
     if (mode == 0) {
         S[S_RES2] = a;
         const double prev = first ? 1.0 : S[S_RHO];  // rho_prev = one(T) before the first iteration
@@ -299,7 +316,7 @@ static int cg_solve_t(CgSolver *c, T *p, Launch L) {
     INSB_CUDA(cudaMemsetAsync(q, 0, (size_t)ncell * sizeof(T), st));
     cg_init_kernel<T><<<NPART, 256, 0, st>>>(g, p, r, pa, pb);
     INSB_CUDA(cudaMemsetAsync(p, 0, (size_t)ncell * sizeof(T), st));
-    cg_finish_kernel<<<1, 1, 0, st>>>(pa, pb, NPART, c->S, 0, 1);
+    cg_finish_kernel<<<1, 256, 0, st>>>(pa, pb, NPART, c->S, 0, 1);
     count(2);
     INSB_CUDA(cudaMemcpyAsync(c->host, c->S + S_RES2, sizeof(double), cudaMemcpyDeviceToHost, st));
     INSB_CUDA(cudaStreamSynchronize(st));
@@ -311,9 +328,9 @@ static int cg_solve_t(CgSolver *c, T *p, Launch L) {
         for (int k = 0; k < CHECK && it < c->maxiter; k++, it++) {
             cg_direction_kernel<T><<<NPART, 256, 0, st>>>(g, r, q, c->S);
             cg_laplacian_kernel<T><<<NPART, 256, 0, st>>>(g, q, Lq, pa, pb);
-            cg_finish_kernel<<<1, 1, 0, st>>>(pa, pb, NPART, c->S, 1, 0);
+            cg_finish_kernel<<<1, 256, 0, st>>>(pa, pb, NPART, c->S, 1, 0);
             cg_update_kernel<T><<<NPART, 256, 0, st>>>(g, p, r, q, Lq, c->S, pa, pb);
-            cg_finish_kernel<<<1, 1, 0, st>>>(pa, pb, NPART, c->S, 0, 0);
+            cg_finish_kernel<<<1, 256, 0, st>>>(pa, pb, NPART, c->S, 0, 0);
             count(5);
         }
         INSB_CUDA(cudaMemcpyAsync(c->host, c->S + S_RES2, sizeof(double), cudaMemcpyDeviceToHost, st));

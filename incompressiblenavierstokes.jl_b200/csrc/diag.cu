@@ -180,10 +180,17 @@ __global__ void __launch_bounds__(256) total_ke_kernel(Grid<T> g, DiagRange ip, 
     if (threadIdx.x == 0) partial[blockIdx.x] = sm[0];
 }
 
-__global__ void sum_partials_kernel(const double *partial, int n, double *out) {
+__global__ void __launch_bounds__(256) sum_partials_kernel(const double *partial, int n, double *out) {
+    __shared__ double sm[256];
     double s = 0.0;
-    for (int i = 0; i < n; i++) s += partial[i];
-    out[0] = s;
+    for (int i = threadIdx.x; i < n; i += 256) s += partial[i];  // fixed assignment, fixed tree: deterministic
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) {
+        if (threadIdx.x < k) sm[threadIdx.x] += sm[threadIdx.x + k];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = sm[0];
 }
 
 template <typename T>
@@ -198,7 +205,7 @@ int launch_total_ke(const Grid<T> &g, const int Ip[3][2], const T *u, bool first
         if (first) total_ke_kernel<T, 2, true><<<npartial, 256, 0, L.stream>>>(g, ip, u, partial);
         else total_ke_kernel<T, 2, false><<<npartial, 256, 0, L.stream>>>(g, ip, u, partial);
     }
-    sum_partials_kernel<<<1, 1, 0, L.stream>>>(partial, npartial, out);
+    sum_partials_kernel<<<1, 256, 0, L.stream>>>(partial, npartial, out);
     if (L.counter) *L.counter += 2;
     INSB_CUDA(cudaGetLastError());
     return 0;
