@@ -20,6 +20,11 @@ import sys
 import threading
 import time
 
+# torch.distributed.run exports OMP_NUM_THREADS=1 to its workers; the CPU arms below are meant to use every
+# host core (the OpenMP runtime reads the variable when it is loaded, i.e. before the first oracle call)
+if "TORCHELASTIC_RUN_ID" in os.environ and os.environ.get("OMP_NUM_THREADS") == "1":
+    del os.environ["OMP_NUM_THREADS"]
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, "incompressiblenavierstokes.jl_b200")
 for p in (ROOT, PKG):
@@ -137,7 +142,7 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------
 # CPU arm: the oracle executing the reference's unfused schedule
 # ----------------------------------------------------------------------------------------
-def cpu_steps(n, dtype, steps, warmup):
+def cpu_setup(n, dtype):
     import oracle as O
     from oracle import ckernels, initializers as oini, operators as oops, pressure as opr, timestep as ots
 
@@ -158,29 +163,45 @@ def cpu_steps(n, dtype, steps, warmup):
     sp = ots.create_stepper(m, so, ps, st, 0.0)
     f = ots.make_navierstokes(so, NU)
     dt = T(fixed_dt(n))
+    return dict(so=so, ps=ps, m=m, cache=cache, sp=sp, f=f, dt=dt, cores=cores, ots=ots, T=T)
+
+
+def cpu_steps(n, dtype, steps, warmup, budget_s=None):
+    """-> (seconds, steps executed, cores); with a time budget the loop stops early (never before one step)"""
+    c = cpu_setup(n, dtype)
+    ots, sp = c["ots"], c["sp"]
     for _ in range(warmup):
-        sp = ots.timestep_(m, f, sp, dt, cache)
+        sp = ots.timestep_(c["m"], c["f"], sp, c["dt"], c["cache"])
     times = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        sp = ots.timestep_(m, f, sp, dt, cache)
+        sp = ots.timestep_(c["m"], c["f"], sp, c["dt"], c["cache"])
         times.append(time.perf_counter() - t0)
+        if budget_s is not None and sum(times) + times[-1] > budget_s:
+            break
     assert np.all(np.isfinite(sp["state"]["u"]))
-    return float(np.sum(times)), cores
+    return float(np.sum(times)), len(times), c["cores"]
+
+
+CPU_SAMPLE = ("oracle executing the reference's unfused schedule (C/OpenMP stencil kernels on {cores} threads, "
+              "scipy.fft workers={cores}, serial NumPy broadcasts)")
 
 
 def run_reference(args):
-    n = args.ref_n
-    tot, cores = cpu_steps(n, args.dtype, args.steps, min(args.warmup, 1))
-    val = n**3 * args.steps / tot
-    sample = (f"TGV3D {n}^3 {args.dtype} RK44, {args.steps} steps, oracle executing the reference's unfused schedule "
-              f"(C/OpenMP stencil kernels on {cores} threads, scipy.fft workers={cores}, serial NumPy broadcasts)")
+    # the SAME configuration as the GPU arm (512^3), bounded in time instead of in size: up to
+    # --steps steps, stopping once --ref-budget seconds of stepping are used up
+    n = args.ref_n if args.ref_n > 0 else args.n
+    warm = 1 if n <= 256 else 0
+    tot, done, cores = cpu_steps(n, args.dtype, args.steps, warm, budget_s=args.ref_budget)
+    val = n**3 * done / tot
+    sample = (f"TGV3D {n}^3 {args.dtype} RK44, {done} of the {args.steps} requested steps (time budget {args.ref_budget:.0f} s), "
+              f"{warm} warm-up, " + CPU_SAMPLE.format(cores=cores))
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True,
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
+        "steps_requested": args.steps, "warmup": warm, "ms_per_step": 1e3 * tot / done, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": f"TaylorGreenVortex3D {args.n}^3 periodic {args.dtype} RK44 psolver_spectral",
-                   "sample": f"{n}^3 grid (bounded CPU sample of the same workload)"},
+                   "sample": f"{n}^3 grid" + ("" if n == args.n else " (bounded CPU sample of the same workload)")},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -219,6 +240,7 @@ def run_gpu(args):
     params = dict(viscosity=NU)
     dt = T(fixed_dt(max(dims)))  # eltype(u): the stage combine then stays in the field type
     stepper = I.create_stepper(method, setup=sg, psolver=ps, state={"u": u}, t=0.0)
+    ke0 = float(I.total_kinetic_energy(u, sg, plan=ps.plan))
 
     def barrier():
         if world > 1:
@@ -264,6 +286,27 @@ def run_gpu(args):
         ms = float(tms.item())
     umax = I.maxabs(stepper["state"]["u"], sg, plan=ps.plan)
     assert np.isfinite(umax) and 0 < umax < 10, f"solution blew up: max|u| = {umax}"
+    # ---- self-check of the state the timed steps produced (a wrong halo / transpose that stays finite
+    # would still break these): post-projection divergence at round-off level, and the kinetic energy
+    # of the Taylor-Green vortex against its viscous decay KE(0) exp(-2 nu |k|^2 t), |k|^2 = 12 pi^2
+    # (the energy-conserving convection moves energy between modes without dissipating it; at these
+    # early times the decay is the linear one to O(1e-4))
+    div = I.divergence_(I.scalarfield(sg), stepper["state"]["u"], sg)
+    max_div = float(div[1:-1, 1:-1, 1:-1].abs().max().item())  # (diagnostic outside the timed region)
+    del div
+    if world > 1:
+        td = torch.tensor([max_div], device="cuda", dtype=torch.float64)
+        dist.all_reduce(td, op=dist.ReduceOp.MAX)
+        max_div = float(td.item())
+    ke = float(I.total_kinetic_energy(stepper["state"]["u"], sg, plan=ps.plan))
+    t_end = float(stepper["t"])
+    ke_expected = ke0 * float(np.exp(-2.0 * NU * 12.0 * np.pi**2 * t_end))
+    eps = float(np.finfo(T).eps)
+    selfcheck = {"t": t_end, "max_abs_u": umax, "max_div_after_projection": max_div,
+                 "max_div_bound": 50 * eps * umax * max(dims), "kinetic_energy": ke, "kinetic_energy_t0": ke0,
+                 "kinetic_energy_expected": ke_expected, "kinetic_energy_rel_dev": abs(ke / ke_expected - 1.0)}
+    assert max_div < selfcheck["max_div_bound"], f"projected field is not divergence free: {selfcheck}"
+    assert selfcheck["kinetic_energy_rel_dev"] < 1e-3, f"kinetic energy off the Taylor-Green decay: {selfcheck}"
 
     cells = int(np.prod(dims))  # one z-slab of the global grid per GPU
     value = cells * args.steps / (ms * 1e-3)
@@ -338,46 +381,108 @@ def run_gpu(args):
             check(lib().insb200_step_rk_host_ensemble(ps.plan.h, A, cc, s, _coef_dtype(method.T, dt), ptrs, None, nm,
                                                       0.0, float(dt), 1, C.byref(pr), st))
 
+        def timed(fn):
+            barrier()
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize()
+            el = time.perf_counter() - t0
+            if world > 1:
+                tel = torch.tensor([el], device="cuda", dtype=torch.float64)
+                dist.all_reduce(tel, op=dist.ReduceOp.MAX)
+                el = float(tel.item())
+            return el
+
         host_steps(2)
-        barrier()
-        t0 = time.perf_counter()
-        host_steps(ke)
-        torch.cuda.synchronize()
-        el = time.perf_counter() - t0
-        if world > 1:
-            tel = torch.tensor([el], device="cuda", dtype=torch.float64)
-            dist.all_reduce(tel, op=dist.ReduceOp.MAX)
-            el = float(tel.item())
+        el = timed(lambda: host_steps(ke))
+
+        # the same state stepped sequentially: every step waits for its own H2D and D2H (no overlap)
+        def seq_steps():
+            for _ in range(ke):
+                check(lib().insb200_step_rk_host(ps.plan.h, A, cc, s, _coef_dtype(method.T, dt), C.c_void_p(uhs[0].data_ptr()), None, 0.0,
+                                                 float(dt), 1, C.byref(pr), st))
+
+        seq_steps()
+        el_seq = timed(seq_steps)
         nbytes = uh.numel() * uh.element_size() * world
         e2e = {"value": cells * ke / el, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                "steps": ke, "ms_per_step": 1e3 * el / ke,
+               "sequential": {"value": cells * ke / el_seq, "unit": UNIT, "ms_per_step": 1e3 * el_seq / ke,
+                              "note": "insb200_step_rk_host on ONE state: H2D, fused RK44 step, D2H, synchronise, repeat"},
                "note": "insb200_step_rk_host_ensemble on every rank: each step = one pinned host state (slab of u) "
                        "-> device, one fused RK44 step, device -> host; the copies of step i+1 / i-1 overlap the "
                        "kernels of step i (3 streams); bytes summed over ranks, time = max over ranks"}
         assert all(np.isfinite(float(uh_.abs().max())) for uh_ in uhs)
         del uhs
 
-    # ---- CPU baseline beside it (bounded sample) ----
+    # ---- parity at full size + CPU baseline beside it (N = 1 only) ----
+    # rank 0 runs the oracle (the reference's unfused schedule on all host cores) on the SAME grid from the
+    # same initial field: step 1 is compared with the CUDA path (north_star: rel L2 <= 1e-5 in Float32,
+    # 1e-12 in Float64), step 2 is the timed CPU sample.
     cpu = None
-    if rank == 0 and not args.no_cpu:
-        tot, cores = cpu_steps(args.ref_n, args.dtype, 2, 1)
-        cpu = {"value": args.ref_n**3 * 2 / tot, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"TGV3D {args.ref_n}^3 {args.dtype} RK44, 2 steps after 1 warm-up, oracle executing the "
-                         f"reference's unfused schedule (C/OpenMP stencil kernels on {cores} threads, scipy.fft "
-                         f"workers={cores}, serial NumPy broadcasts)"}
+    parity = None
+    if world == 1 and not args.no_cpu:
+        nref = args.ref_n if args.ref_n > 0 else n
+        c = cpu_setup(nref, args.dtype)
+        ots = c["ots"]
+        do_check = nref == n and not args.no_check
+        if do_check:
+            ug = I.to_device(sg, c["sp"]["state"]["u"])
+            spg = I.create_stepper(method, setup=sg, psolver=ps, state={"u": ug}, t=0.0)
+        sp = ots.timestep_(c["m"], c["f"], c["sp"], c["dt"], c["cache"])
+        if do_check:
+            spg = I.timestep_(method, I.navierstokes_, spg, dt, params=params)
+            got = spg["state"]["u"].cpu().numpy().T
+            ref = sp["state"]["u"]
+            num = float(np.sqrt(np.sum((got.astype(np.float64) - ref) ** 2)))
+            den = float(np.sqrt(np.sum(ref.astype(np.float64) ** 2)))
+            dv = I.divergence_(I.scalarfield(sg), spg["state"]["u"], sg)
+            parity = {"grid": [nref] * 3, "steps": 1, "rel_l2": num / den, "tol": 1e-5 if args.dtype == "f32" else 1e-12,
+                      "max_div": float(dv[1:-1, 1:-1, 1:-1].abs().max().item()),
+                      "against": "CPU oracle (oracle/, C/OpenMP + NumPy restatement of the reference), same initial field"}
+            del got, ref, dv, ug, spg
+            assert parity["rel_l2"] < parity["tol"], f"full-size parity failed: {parity}"
+        t0 = time.perf_counter()
+        sp = ots.timestep_(c["m"], c["f"], sp, c["dt"], c["cache"])
+        tot = time.perf_counter() - t0
+        cpu = {"value": nref**3 / tot, "unit": UNIT, "cores": c["cores"], "kind": "port",
+               "sample": f"TGV3D {nref}^3 {args.dtype} RK44, 1 step after 1 warm-up step, " + CPU_SAMPLE.format(cores=c["cores"])}
+        del c, sp
+
+    # ---- P GPUs == 1 GPU on a small grid of the same problem class (N > 1) ----
+    equality = None
+    if world > 1 and not args.no_check:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import mgpu_worker
+
+        ea = argparse.Namespace(grid=[128, 64, 128], dtype=args.dtype, steps=2)
+        ok, rows = mgpu_worker.run_case(ea, "periodic", rank, world, quiet=True)
+        if rank == 0:
+            equality = {"grid": ea.grid, "steps": ea.steps, "ok": ok,
+                        "max_rel_err": max(r["err"] for r in rows if r["case"] in ("project", "psolve", "RK44", "LMWray3")),
+                        "cases": {r["case"]: r["err"] for r in rows},
+                        "against": f"the same problem on ONE GPU (rank 0), {world}-GPU slab decomposition gathered"}
+            assert ok, f"{world}-GPU result differs from the 1-GPU result: {rows}"
 
     if rank == 0:
+        wl = f"TaylorGreenVortex3D {dims[0]}x{dims[1]}x{dims[2]} periodic {args.dtype} RK44 psolver_spectral"
+        if world > 1:
+            wl += (f" (weak-scaling series of BASELINE config[1]: {n}^3 cells per GPU; the cost per cell equals "
+                   "config[2] DecayingTurbulence3D, whose random_field initial condition this run does not use)")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": f"TaylorGreenVortex3D {dims[0]}x{dims[1]}x{dims[2]} periodic {args.dtype} RK44 psolver_spectral",
+            "config": {"workload": wl,
                        "n": list(dims), "cells_per_gpu": n**3, "nu": NU, "dt": float(dt), "method": f"RK44(T={args.dtype})",
                        "l2": f"working set {14 * w * (n + 2)**3 / 1e9:.1f} GB per GPU >> 126 MB L2 (no flush needed)",
                        "parallelism": "1 GPU" if world == 1 else
-                       f"z-slab decomposition over {world} GPUs (halo exchange + all-to-all FFT transposes over NCCL)"},
+                       f"z-slab decomposition over {world} GPUs (halo exchange + FFT transposes by peer stores over NVLink)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "selfcheck": selfcheck, "parity": parity,
         }
+        if equality:
+            line["equality_vs_1gpu"] = equality
         if nvlink:
             line["nvlink"] = nvlink
         print(json.dumps(line), flush=True)
@@ -392,7 +497,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="insb200", choices=["insb200", "reference"])
     ap.add_argument("--n", type=int, default=512)
-    ap.add_argument("--ref-n", type=int, default=256, help="grid of the bounded CPU sample")
+    ap.add_argument("--ref-n", type=int, default=0, help="grid of the CPU arms (0 = the workload's own grid)")
+    ap.add_argument("--ref-budget", type=float, default=150.0, help="seconds of CPU stepping of --impl reference")
+    ap.add_argument("--no-check", action="store_true", help="skip the full-size parity leg against the oracle")
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

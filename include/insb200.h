@@ -46,7 +46,12 @@ enum {
     INSB200_PSOLVER_DEFAULT = 3, /* default_psolver, src/pressure.jl:58-78 */
     INSB200_PSOLVER_CG = 4       /* psolver_cg, src/pressure.jl:155-203: any boundary conditions / grids.
                                   * default_psolver resolves to it where the reference would build the
-                                  * sparse direct solver (psolver_direct is not on the GPU path) */
+                                  * sparse direct solver (psolver_direct is not on the GPU path).  In that
+                                  * case -- and unless cg_reltol / cg_abstol are given -- the relative
+                                  * tolerance is 1e-13 (Float64) / 1e-5 (Float32) instead of psolver_cg's
+                                  * sqrt(eps), and the iteration stops when the residual has not fallen for
+                                  * 200 iterations, so that the substitute solves to round-off level like the
+                                  * direct solver; insb200_plan_psolver() tells which solver was chosen */
 };
 
 /* The subset of the `Setup` NamedTuple (src/grid.jl:91-208) the hot path consumes.

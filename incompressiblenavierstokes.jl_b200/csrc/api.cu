@@ -680,7 +680,14 @@ int insb200_plan_create(const insb200_setup_t *setup, insb200_plan_t **out) {
     std::memcpy(pl->bc.u_val, s.bc_u_value, sizeof(s.bc_u_value));
     std::memcpy(pl->bc.temp_val, s.bc_temp_value, sizeof(s.bc_temp_value));
     int kind = s.psolver;
-    if (kind == INSB200_PSOLVER_DEFAULT) kind = resolve_default_psolver(pl);
+    if (kind == INSB200_PSOLVER_DEFAULT) {
+        kind = resolve_default_psolver(pl);
+        // Where the reference's default is the exact sparse direct solver, the stand-in is CG: make it
+        // converge to round-off level (not the sqrt(eps) of psolver_cg's own default) unless the caller
+        // chose tolerances, so that projected fields stay divergence free to about the same level.
+        if (kind == INSB200_PSOLVER_CG && pl->s.cg_reltol == 0 && pl->s.cg_abstol == 0)
+            pl->s.cg_reltol = -(pl->f64 ? 1e-13 : 1e-5);  // negative: "tight default", enables the stagnation stop
+    }
     pl->psolver = kind;
     if (kind != INSB200_PSOLVER_NONE) {
         r = poisson_create(pl->s, pl->Ip, kind, pl->comm, &pl->ps);

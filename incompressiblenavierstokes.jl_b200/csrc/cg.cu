@@ -7,9 +7,9 @@
 //   q = z + beta q            (z = -r/d, the Jacobi preconditioner, recomputed on the fly)
 //   Lq = laplacian(q), <q, Lq>  (ghost values by index logic: no apply_bc_p! pass)
 //   p += alpha q, r -= alpha Lq, <r, r>, <z, r>
-// -- with alpha, beta, rho kept in device memory (two one-thread kernels finish the
-// deterministic two-stage reductions), and the host only reads the residual every few
-// iterations to decide when to stop.
+// -- with alpha, beta, rho kept in device memory (one-block kernels finish the deterministic
+// two-stage reductions with a fixed-order shared-memory tree), and the host only reads the
+// residual every few iterations to decide when to stop.
 #include <cmath>
 
 #include "internal.h"
@@ -220,6 +220,7 @@ struct CgSolver {
     double *S = nullptr, *part = nullptr;
     double *host = nullptr;  // pinned: residual read-back
     double reltol = 0, abstol = 0;
+    bool stagnation_stop = false;  // tight default of default_psolver: stop when the residual no longer falls
     long long maxiter = 0;
     long long bytes = 0;
     int iterations = 0;
@@ -281,6 +282,8 @@ int cg_create(const insb200_setup_t &s, const int Ip[3][2], double reltol, doubl
         return fail("cudaMalloc failed (cg scalars)");
     c->bytes = 3 * (long long)fb;
     // defaults of psolver_cg (pressure.jl:158-161)
+    c->stagnation_stop = reltol < 0;
+    if (reltol < 0) reltol = -reltol;
     c->reltol = reltol > 0 ? reltol : std::sqrt(c->f64 ? 2.220446049250313e-16 : 1.1920929e-07);
     c->abstol = abstol > 0 ? abstol : 0.0;
     c->maxiter = maxiter > 0 ? maxiter : ndof;
@@ -323,7 +326,9 @@ static int cg_solve_t(CgSolver *c, T *p, Launch L) {
     double residual = std::sqrt(c->host[0]);
     const double tolerance = std::fmax(c->reltol * residual, c->abstol);
     long long it = 0;
-    constexpr int CHECK = 4;  // iterations between residual read-backs
+    constexpr int CHECK = 4;  // iterations between residual read-backs (the count reported is a multiple of it)
+    double best = residual;
+    long long best_it = 0;
     while (it < c->maxiter && residual > tolerance) {
         for (int k = 0; k < CHECK && it < c->maxiter; k++, it++) {
             cg_direction_kernel<T><<<NPART, 256, 0, st>>>(g, r, q, c->S);
@@ -340,6 +345,8 @@ static int cg_solve_t(CgSolver *c, T *p, Launch L) {
             set_error("psolver_cg: the residual became NaN");
             return 1;
         }
+        if (residual < 0.9 * best) best = residual, best_it = it;
+        if (c->stagnation_stop && it - best_it >= 200) break;  // round-off floor reached above the tight tolerance
     }
     c->iterations = (int)it;
     c->residual = residual;

@@ -146,7 +146,7 @@ template int launch_diag<double>(const Grid<double> &, const int[3][2], int, con
 
 // total_kinetic_energy: sum over Ip of ke * (Δx Δy Δz) without materialising ke.  Deterministic:
 // fixed assignment of cells to threads, block partials in double, one block adds the partials
-// in index order.
+// with a fixed-order shared-memory tree (same result for the same grid on every run).
 template <typename T, int D, bool FIRST>
 __global__ void __launch_bounds__(256) total_ke_kernel(Grid<T> g, DiagRange ip, const T *__restrict__ u, double *partial) {
     const int nx = ip.hi[0] - ip.lo[0], ny = ip.hi[1] - ip.lo[1], nz = D == 3 ? ip.hi[2] - ip.lo[2] : 1;

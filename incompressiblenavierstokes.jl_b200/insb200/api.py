@@ -61,10 +61,18 @@ class BcPlanes:
             self.time_dependent = False
             return
         a = self._evaluate(0.0, False)
-        b = self._evaluate(0.7853981, False)
-        self.time_dependent = any(not np.array_equal(a[k], b[k]) for k in a)
+        declared = [setup.bc_u[d][side].time_dependent for d, side, _ in self.funcs]
+        if any(v is True for v in declared):
+            self.time_dependent = True
+        elif all(v is False for v in declared):
+            self.time_dependent = False
+        else:  # undeclared: probe two more times now, and keep probing at every step start (refresh)
+            self.time_dependent = any(not np.array_equal(a[k], b[k]) for t in (0.7853981, 1.9098593)
+                                      for b in (self._evaluate(t, False),) for k in a)
+        self.probing = not self.time_dependent and any(v is None for v in declared)
         for k, v in a.items():
             self.planes[k] = torch.from_numpy(v).to(_dev(setup))
+        self.host = a
         self.state = (0.0, False)
 
     def _evaluate(self, t, dudt):
@@ -77,6 +85,13 @@ class BcPlanes:
     def refresh(self, t, dudt=False):
         if not self.funcs:
             return
+        if self.probing and not dudt and float(t) != 0.0:
+            # a function not declared time independent is re-evaluated at the current time: as soon as its
+            # planes differ from the ones in use it is time dependent from here on (a ramp that starts
+            # late, a period the construction-time probes happened to hit)
+            now = self._evaluate(float(t), False)
+            if any(not np.array_equal(now[k], self.host[k]) for k in now):
+                self.time_dependent, self.probing = True, False
         want = (float(t) if (self.time_dependent or dudt) else 0.0, bool(dudt))
         if self.state == want:
             return
@@ -585,9 +600,9 @@ def timestep_(method, force, stepper, dt, *, params=None, ode_cache=None, force_
     """timestep! -- one fused library call per step."""
     setup, psolver, state = stepper["setup"], stepper["psolver"], stepper["state"]
     planes = _bc_planes(setup)
+    planes.refresh(stepper["t"])  # (also probes undeclared functions for time dependence)
     if planes.time_dependent:
         return _timestep_staged(method, force, stepper, dt, dict(params or {}))
-    planes.refresh(stepper["t"])
     pr = _force_params(force, setup, params)
     u = _chk(setup, state["u"], True)
     temp = _chk(setup, state["temp"], False) if "temp" in state and pr.boussinesq else None
@@ -783,10 +798,18 @@ def _solve_native(setup, method, force, stepper, tend, dt, dt_min, cfl, n_adapt_
     cc = None if is_wray else (C.c_double * s)(*[float(v) for v in method.c])
     coef = _lib.F64 if is_wray else _coef_dtype(method.T, setup.T(0) if adaptive else dt)
 
+    _bc_planes(setup).refresh(tstart)  # planes may hold d/dt values of an earlier right_hand_side! call
+    failure = []
+
     def on_step(_user, n, t):
-        stepper["t"], stepper["n"] = tT(t), int(n)
-        obs.value = get_state(stepper)
-        return 0
+        # an exception must not vanish inside ctypes: remember it, stop the loop, re-raise below
+        try:
+            stepper["t"], stepper["n"] = tT(t), int(n)
+            obs.value = get_state(stepper)
+            return 0
+        except BaseException as e:  # noqa: BLE001
+            failure.append(e)
+            return 1
 
     cb = _STEP_CB(on_step)
     t_out, n_out = C.c_double(), C.c_longlong()
@@ -795,6 +818,8 @@ def _solve_native(setup, method, force, stepper, tend, dt, dt_min, cfl, n_adapt_
         -1.0 if adaptive else float(dt), -1.0 if dt_min is None else float(dt_min), float(cfl), int(n_adapt_dt),
         _lib.F32 if tT is np.float32 else _lib.F64, C.byref(pr), int(every), C.cast(cb, C.c_void_p), None, int(graph),
         C.byref(t_out), C.byref(n_out), _stream())
+    if failure:
+        raise failure[0]
     if rc == 2:  # INSB200_STOPPED_BAD_DT: the reference warns and leaves the loop (solver.jl:113-116)
         warnings.warn(lib().insb200_last_error().decode())
     else:
@@ -970,7 +995,9 @@ def solve_unsteady(*, setup, tlims, start, force=navierstokes_, docopy=True, met
     obs = Observable(get_state(stepper))
     processors = processors or {}
     initialized = {k: p.initialize(obs) for k, p in processors.items()}
-    if native and force in (navierstokes_, boussinesq_) and not _bc_planes(setup).time_dependent:
+    planes = _bc_planes(setup)
+    # (a Dirichlet function not declared time independent keeps being probed step by step: Python loop)
+    if native and force in (navierstokes_, boussinesq_) and not planes.time_dependent and not getattr(planes, "probing", False):
         import math
 
         every = 0

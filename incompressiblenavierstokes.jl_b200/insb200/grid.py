@@ -24,12 +24,17 @@ class PeriodicBC:
 
 
 class DirichletBC:
-    """``u``: None (no-slip), a tuple of D constants, a number (temperature BC)."""
+    """``u``: None (no-slip), a tuple of D constants, a number (temperature BC), or a function
+    ``u(dim, x..., t)`` (src/boundary_conditions.jl:7-20).  ``time_dependent`` declares whether a function
+    depends on ``t``: True -> the steppers re-evaluate it at every stage time, False -> evaluated once;
+    None (default) -> treated as time dependent as soon as two evaluations at different times differ
+    (checked when the plan is built and again at the start of every step)."""
 
     code = _lib.BC_DIRICHLET
 
-    def __init__(self, u=None):
+    def __init__(self, u=None, time_dependent=None):
         self.u = u
+        self.time_dependent = time_dependent
 
     def __repr__(self):
         return f"DirichletBC({self.u!r})"

@@ -208,9 +208,14 @@ def timestep_(method, force_, stepper, dt, cache):
 # ---------------------------------------------------------------------------
 # forces
 # ---------------------------------------------------------------------------
-def make_navierstokes(setup, viscosity):
+def make_navierstokes(setup, viscosity, bodyforce=None):
+    """navierstokes! (solver.jl:2-6); bodyforce: the constant body force of examples/ChannelFlow.jl:172-176"""
+
     def force_(force, state, t):
         ops.navierstokes_(force, state, t, setup, viscosity)
+        if bodyforce is not None:
+            for c, b in enumerate(bodyforce):
+                force["u"][..., c] += setup.T(b)
 
     force_.params = dict(viscosity=viscosity)
     return force_

@@ -46,14 +46,14 @@ def main():
     dist.init_process_group("nccl")
     ok = True
     for case in (["periodic", "channel"] if args.case == "both" else [args.case]):
-        ok = run_case(args, case, rank, world) and ok
+        ok = run_case(args, case, rank, world)[0] and ok
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag)
     dist.destroy_process_group()
     sys.exit(1 if int(flag.item()) else 0)
 
 
-def run_case(args, case, rank, world):
+def run_case(args, case, rank, world, quiet=False):
     import insb200 as I
 
     T = np.float64 if args.dtype == "f64" else np.float32
@@ -156,8 +156,9 @@ def run_case(args, case, rank, world):
         report("vorticity", rel(res["vort"][inner], w1[inner]), tol)
         for o in out:
             o.update(world=world, n=n, dtype=args.dtype, problem=case)
-            print(json.dumps(o), flush=True)
-    return ok
+            if not quiet:
+                print(json.dumps(o), flush=True)
+    return ok, out
 
 
 if __name__ == "__main__":
