@@ -330,8 +330,13 @@ def run_gpu(args):
     # projection 7w; bytes = count * w * n^3
     # with divergence! fused into the first FFT pass (no d array) that pass reads v (3w) and writes
     # the half spectrum (1w): Poisson 12w per solve, no divergence launches
-    fused_div = prof["divergence"][1] == 0
-    alg = {"rhs_combine": 12.0, "divergence": 4.0, "poisson": 12.0 if fused_div else 10.0, "project": 7.0}
+    # fused periodic path (csrc/stage_fused.cu): one stencil launch per stage does the lazy projection of the
+    # previous stage, the right-hand side, the stage combine and the divergence -- (10 + 17 + 17 + 11) w / 4
+    # per launch -- and only the last stage of a step is projected explicitly
+    fused_step = prof["divergence"][1] == 0 and 0 < prof["project"][1] < prof["rhs_combine"][1]
+    fused_div = prof["divergence"][1] == 0 and not fused_step
+    alg = {"rhs_combine": 13.75 if fused_step else 12.0, "divergence": 4.0, "poisson": 12.0 if fused_div else 10.0,
+           "project": 7.0}
     dom = max(alg, key=lambda k: prof[k][0])
     alg.update({k: 2.0 for k in ("fft_x_r2c", "fft_y_fwd", "fft_z_mid", "fft_y_inv", "fft_x_c2r")})
     if fused_div:
@@ -352,7 +357,8 @@ def run_gpu(args):
                 "algorithmic_bytes_per_cell": alg[dom] * w,
                 "step": {"achieved": step_bytes / (ms / args.steps * 1e-3) / 1e9,
                          "frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak,
-                         "algorithmic_bytes_per_cell_update": 120.0 * w},
+                         "algorithmic_bytes_per_cell_update": 120.0 * w,
+                         "moved_bytes_per_cell_update": (102.0 if fused_step else 136.0) * w},
                 "groups": groups}
 
     # ---- end to end through the C ABI with HOST buffers (pinned), every step H2D + D2H ----

@@ -270,6 +270,11 @@ int insb200_cfl(insb200_plan_t *plan, const void *u, const insb200_params_t *par
 /* maximum(abs, u) over the whole vector field (timelogger, src/processors.jl:75); syncs. */
 int insb200_maxabs(insb200_plan_t *plan, const void *u, double *out, void *stream);
 
+/* Debugging aid of the fused periodic time-step path (tools/debug_fused.py): copies one of the plan's
+ * padded internal arrays to the host.  which: 0, 1 = unprojected stage velocities, 2 = running accumulator,
+ * 3 = pressure, 4 = scaled divergence; dims receives {NPX, NPY, NPZ, components}; host may be NULL. */
+int insb200_debug_fused_copy(insb200_plan_t *plan, int which, void *host, long long host_bytes, int dims[4]);
+
 /* Number of kernel launches issued by this plan since creation (bench.py `gpu_launches`). */
 long long insb200_launch_count(const insb200_plan_t *plan);
 

@@ -6,6 +6,7 @@
 #include <cstring>
 #include <mutex>
 
+#include "fused.h"
 #include "internal.h"
 
 namespace insb {
@@ -49,12 +50,18 @@ struct insb200_plan : public insb::Profiler {
     double *scratch = nullptr;  // reductions
     double *ke_partial = nullptr;  // block partials of total_kinetic_energy
     void *LES_G = nullptr, *LES_visc = nullptr;  // eddy-viscosity scratch: 9 tensor components + viscosity
+    // fused periodic time-step path (fused.h): padded internal arrays -- two unprojected stage velocities,
+    // the running accumulator, the pressure and the scaled divergence -- and their tensor maps
+    void *FV[2] = {nullptr, nullptr}, *FACC = nullptr, *FP = nullptr, *FD = nullptr;
+    FusedCtx fctx{};
+    bool fused_ready = false;
     long long bytes = 0;
     long long launches = 0;
     // diffusive / thermal step limits (host, from the tables)
     double dmin_u[3], dmin_p[3];
     // profiling
     bool prof = false;
+    bool prof_legacy = false;  // keep the stage-by-stage path (per-kernel profiling groups of round 1)
     double prof_ms[NPROF] = {};
     long long prof_cnt[NPROF] = {};
     struct Bracket {
@@ -334,6 +341,75 @@ int ensure_k(insb200_plan *pl, int count, bool temp) {
     return 0;
 }
 
+
+// ---- fused periodic path (fused.h) -----------------------------------------------------
+// 3-D, all-periodic, psolver_spectral on the register-FFT fast path, plain navierstokes! forcing (+ constant
+// body force), one GPU.  Everything else keeps the stage-by-stage path below.
+bool fused_applicable(const insb200_plan *pl, const insb200_params_t *pr) {
+    const bool off = getenv("INSB200_NO_FUSED_STEP") != nullptr;  // (read per call: the tests toggle it)
+    if (off || pl->D != 3 || pl->comm || pl->prof_legacy) return false;
+    for (int a = 0; a < 3; a++)
+        if (pl->s.bc_u[a][0] != INSB200_BC_PERIODIC || pl->s.bc_u[a][1] != INSB200_BC_PERIODIC) return false;
+    if (pr->boussinesq || pr->eddy_model != 0) return false;
+    if (!pl->ps || pl->psolver != INSB200_PSOLVER_SPECTRAL || !poisson_supports_io(pl->ps)) return false;
+    const int n0 = pl->s.N[0] - 2, n1 = pl->s.N[1] - 2, n2 = pl->s.N[2] - 2;
+    if (n0 % 2 || n0 < 8 || n1 < 8 || n2 < 8) return false;
+    const FusedLayout L = make_fused_layout(n0, n1, n2);
+    return 3 * L.cs < (1LL << 31) && 3 * (long long)pl->ncell < (1LL << 32);
+}
+
+int ensure_fused(insb200_plan *pl) {
+    if (pl->fused_ready) return 0;
+    const int n0 = pl->s.N[0] - 2, n1 = pl->s.N[1] - 2, n2 = pl->s.N[2] - 2;
+    pl->fctx.L = make_fused_layout(n0, n1, n2);
+    pl->fctx.zwrap = 1;
+    pl->fctx.zoff = 0;
+    pl->fctx.n2g = n2;
+    INSB_TRY(fused_maps_create(&pl->fctx.maps));
+    const size_t sb = (size_t)pl->fctx.L.cs * pl->esz;
+    INSB_TRY(dev_alloc(pl, &pl->FV[0], 3 * sb));
+    INSB_TRY(dev_alloc(pl, &pl->FV[1], 3 * sb));
+    INSB_TRY(dev_alloc(pl, &pl->FACC, 3 * sb));
+    INSB_TRY(dev_alloc(pl, &pl->FP, sb));
+    INSB_TRY(dev_alloc(pl, &pl->FD, sb));
+    pl->fused_ready = true;
+    return 0;
+}
+
+// One fused stage followed by its Poisson solve: the stage kernel leaves the unprojected velocity in v_out
+// and the scaled divergence in FD; the solve turns FD into the pressure FP (with its ghost images).
+template <typename T>
+int fused_stage_and_solve(insb200_plan *pl, const FusedStage<T> &st, bool ct_double, void *stream) {
+    const Grid<T> &g = grid_of<T>(pl);
+    Launch L = L_of(pl, stream);
+    {
+        Scope sc(pl, L.stream, 0);
+        INSB_TRY(launch_stage_fused<T>(g, pl->fctx, st, ct_double, L));
+    }
+    const FusedLayout &FL = pl->fctx.L;
+    PoissonIO io{};
+    io.rhs = (const T *)pl->FD + FL.at(1, 1, 1);
+    io.sol = (T *)pl->FP + FL.at(1, 1, 1);
+    io.rs1 = FL.s1;
+    io.rs2 = FL.s2;
+    io.img = 1 | (pl->fctx.zwrap ? 2 : 0);
+    Scope sc(pl, L.stream, 2);
+    return poisson_solve(pl->ps, nullptr, L, nullptr, &io);
+}
+
+template <typename T>
+int fused_finish(insb200_plan *pl, const T *v, T *U, void *stream) {
+    Launch L = L_of(pl, stream);
+    Scope sc(pl, L.stream, 3);
+    return launch_project_out<T>(grid_of<T>(pl), pl->fctx, v, (const T *)pl->FP, U, L);
+}
+
+template <typename T>
+void fused_params(FusedStage<T> &st, const insb200_params_t *pr) {
+    st.nu = pr->viscosity;
+    for (int c = 0; c < 3; c++) st.bodyforce[c] = pr->bodyforce[c];
+}
+
 // Stage kernel followed by the eddy-viscosity closure when params ask for one: the closure term is
 // applied to the outputs the stage kernel has just written (k, v, acc), like the Boussinesq pass.
 template <typename T>
@@ -395,6 +471,39 @@ int step_rk_t(insb200_plan *pl, const double *A, const double *c, int s, int coe
     bool fast = true;
     for (int i = 0; i < s - 1; i++)
         for (int j = 0; j < i; j++) fast = fast && A[i * s + j] == 0.0;
+    if (fast && s >= 2 && fused_applicable(pl, pr)) {
+        // fused periodic path: per stage ONE stencil launch (lazy projection of the previous stage on load,
+        // stage combine, divergence of its own output) + the Poisson solve; explicit projection only at the end
+        INSB_TRY(ensure_fused(pl));
+        for (int i = 0; i < s; i++) {
+            const bool last = i == s - 1;
+            FusedStage<T> st;
+            fused_params(st, pr);
+            st.cv = coef(i, i);
+            st.v_out = (T *)pl->FV[i & 1];
+            st.d_out = (T *)pl->FD;
+            if (i == 0) {
+                st.u_ref = U;
+            } else {
+                st.v_in = (const T *)pl->FV[(i - 1) & 1];
+                st.p_in = (const T *)pl->FP;
+            }
+            if (!last) {
+                st.acc_out = (T *)pl->FACC;
+                st.ca = coef(s - 1, i);
+                if (i > 0) {
+                    st.vbase_ref = U;
+                    st.acc_in = (const T *)pl->FACC;
+                }
+            } else {
+                st.vbase_int = (const T *)pl->FACC;
+            }
+            INSB_TRY(fused_stage_and_solve<T>(pl, st, ct_double, stream));
+            if (const char *e = getenv("INSB200_FUSED_STOP_AFTER"))  // debugging aid (tools/debug_fused.py)
+                if (atoi(e) == i + 1) return 0;
+        }
+        return fused_finish<T>(pl, (const T *)pl->FV[(s - 1) & 1], U, stream);
+    }
     if (!fast) INSB_TRY(ensure_k(pl, s - 1, bouss));
     size_t vb = (size_t)pl->ncell * pl->D * pl->esz, sb = (size_t)pl->ncell * pl->esz;
 
@@ -476,6 +585,27 @@ int step_wray_t(insb200_plan *pl, T *U, T *TU, double t, double dt, const insb20
     const T a3[3] = {(T)(8.0 / 15.0), (T)(5.0 / 12.0), (T)(3.0 / 4.0)};
     const T b3[2] = {(T)(1.0 / 4.0), (T)0};
     const T c3[3] = {(T)(8.0 / 15.0), (T)(2.0 / 3.0), (T)1};
+    if (fused_applicable(pl, pr)) {
+        INSB_TRY(ensure_fused(pl));
+        for (int i = 0; i < 3; i++) {
+            FusedStage<T> st;
+            fused_params(st, pr);
+            st.cv = (double)(T)((double)a3[i] * dt);
+            st.v_out = (T *)pl->FV[i & 1];
+            st.d_out = (T *)pl->FD;
+            if (i == 0) {  // statestart += b[0] dt k; v = u + a[0] dt k
+                st.u_ref = U;
+                st.acc_out = (T *)pl->FACC;
+                st.ca = (double)(T)((double)b3[0] * dt);
+            } else {
+                st.v_in = (const T *)pl->FV[(i - 1) & 1];
+                st.p_in = (const T *)pl->FP;
+                st.vbase_int = (const T *)pl->FACC;
+            }
+            INSB_TRY(fused_stage_and_solve<T>(pl, st, pl->f64, stream));
+        }
+        return fused_finish<T>(pl, (const T *)pl->FV[0], U, stream);
+    }
     const T *src = U;
     const T *tsrc = TU;
     for (int i = 0; i < 3; i++) {
@@ -712,8 +842,10 @@ int insb200_plan_destroy(insb200_plan_t *pl) {
     cudaDeviceSynchronize();
     if (pl->ps) poisson_destroy(pl->ps);
     for (void *p : {pl->V[0], pl->V[1], pl->ACC, pl->P, pl->TV[0], pl->TV[1], pl->TACC, pl->dev_tables,
-                    (void *)pl->scratch, (void *)pl->ke_partial, pl->LES_G, pl->LES_visc, pl->HU, pl->HT, pl->HU2, pl->HT2})
+                    (void *)pl->scratch, (void *)pl->ke_partial, pl->LES_G, pl->LES_visc, pl->HU, pl->HT, pl->HU2, pl->HT2,
+                    pl->FV[0], pl->FV[1], pl->FACC, pl->FP, pl->FD})
         if (p) cudaFree(p);
+    if (pl->fctx.maps) fused_maps_destroy(pl->fctx.maps);
     if (pl->s_in) cudaStreamDestroy(pl->s_in);
     if (pl->s_out) cudaStreamDestroy(pl->s_out);
     if (pl->s_graph) cudaStreamDestroy(pl->s_graph);
@@ -1269,6 +1401,28 @@ int insb200_maxabs(insb200_plan_t *pl, const void *u, double *out, void *stream)
     double v;
     std::memcpy(&v, &h[0], 8);
     *out = h[1] ? std::nan("") : v;
+    return 0;
+    API_END
+}
+
+// Debugging aid (not part of the reference-facing surface): copy one padded internal array of the fused
+// path to the host.  which: 0, 1 = stage velocities, 2 = accumulator, 3 = pressure, 4 = scaled divergence;
+// dims receives {NPX, NPY, NPZ, components}.
+int insb200_debug_fused_copy(insb200_plan_t *pl, int which, void *host, long long host_bytes, int dims[4]) {
+    API_BEGIN
+    if (!pl->fused_ready) {
+        set_error("the fused path has not run on this plan");
+        return 1;
+    }
+    void *src[5] = {pl->FV[0], pl->FV[1], pl->FACC, pl->FP, pl->FD};
+    if (which < 0 || which > 4) return 1;
+    const int nc = which < 3 ? 3 : 1;
+    dims[0] = pl->fctx.L.NPX, dims[1] = pl->fctx.L.NPY, dims[2] = pl->fctx.L.NPZ, dims[3] = nc;
+    const size_t bytes = (size_t)pl->fctx.L.cs * nc * pl->esz;
+    if (host && (long long)bytes <= host_bytes) {
+        INSB_CUDA(cudaDeviceSynchronize());
+        INSB_CUDA(cudaMemcpy(host, src[which], bytes, cudaMemcpyDeviceToHost));
+    }
     return 0;
     API_END
 }

@@ -740,6 +740,24 @@ __global__ void __launch_bounds__(XShape<T, N>::NT)
             ra[t + P * m] = v[m].x;
             rb[t + P * m] = v[m].y;
         }
+        if (g.img) {
+            // two ghost layers of periodic images: rows 0, 1 -> n1, n1 + 1; rows n1 - 2, n1 - 1 -> -2, -1; the
+            // same along x and (bit 1) z
+            const int n1 = g.n[1], n2 = g.n[2];
+            const long long yo = (jp == 0 ? (long long)n1 : (2 * jp + 2 == n1 ? -(long long)n1 : 0)) * g.rs[1];
+            const long long zo = !(g.img & 2) ? 0 : (kz < 2 ? (long long)n2 : (kz >= n2 - 2 ? -(long long)n2 : 0)) * g.rs[2];
+            for (int iz = 0; iz < (zo ? 2 : 1); iz++)
+                for (int iy = 0; iy < (yo ? 2 : 1); iy++) {
+                    T *a2 = ra + (iz ? zo : 0) + (iy ? yo : 0), *b2 = a2 + g.rs[1];
+#pragma unroll
+                    for (int m = 0; m < 8; m++) {
+                        const int i = t + P * m;
+                        const int xo = i < 2 ? N : (i >= N - 2 ? -N : 0);
+                        if (iz | iy) a2[i] = v[m].x, b2[i] = v[m].y;
+                        if (xo) a2[i + xo] = v[m].x, b2[i + xo] = v[m].y;
+                    }
+                }
+        }
     }
 }
 

@@ -53,6 +53,10 @@ struct FastGeom {
     // elements (within a block), 2: the rows are the companion index `other`.
     int in_grp = 0, out_grp = 0;
     void *outp[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // x C2R pass only: also store the periodic images of the result into the two ghost layers around
+    // the interior (the internal layout of the fused time-step path, fused.h): bit 0 = x and y images,
+    // bit 1 = z images (z periodic on this GPU)
+    int img = 0;
 };
 
 bool fast_fft_supported(int n);

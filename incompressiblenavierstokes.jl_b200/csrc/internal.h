@@ -221,7 +221,17 @@ struct DivSource {
     int wrap;
 };
 bool poisson_fuses_divergence(const Poisson *ps);
-int poisson_solve(Poisson *ps, void *p_ghosted, Launch L, const DivSource *div = nullptr);
+// Separate input / output arrays in the internal layout of the fused time-step path (fused.h): the right-hand
+// side is read from `rhs`, the solution written to `sol` together with its periodic ghost images (img, see
+// FastGeom::img); both point at the first interior cell, strides rs1 / rs2.  Spectral fast path only.
+struct PoissonIO {
+    const void *rhs;
+    void *sol;
+    long long rs1, rs2;
+    int img;
+};
+bool poisson_supports_io(const Poisson *ps);
+int poisson_solve(Poisson *ps, void *p_ghosted, Launch L, const DivSource *div = nullptr, const PoissonIO *io = nullptr);
 // direct peer-store transposes: export this rank's IPC handles / import everybody's
 constexpr int POISSON_IPC_BYTES = 192;
 int poisson_ipc_export(Poisson *ps, void *blob);

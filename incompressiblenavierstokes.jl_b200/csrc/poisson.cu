@@ -1022,11 +1022,22 @@ int poisson_ipc_import(Poisson *ps, const void *blobs) {
 }
 
 template <typename T>
-static int solve_t(Poisson *ps, T *p, Launch L, const DivSource *div) {
+static int solve_t(Poisson *ps, T *p, Launch L, const DivSource *div, const PoissonIO *io) {
     const int D = ps->D;
     long long rs[3] = {1, ps->Ng[0], (long long)ps->Ng[0] * ps->Ng[1]};
     T *R = p;
     for (int a = 0; a < D; a++) R += ps->ioff[a] * rs[a];
+    T *Rout = R;
+    if (io) {
+        if (!poisson_supports_io(ps) || div) {
+            set_error("poisson_solve: separate input / output arrays need the spectral fast path");
+            return 1;
+        }
+        R = const_cast<T *>((const T *)io->rhs);  // the R2C pass only reads it
+        Rout = (T *)io->sol;
+        rs[1] = io->rs1;
+        rs[2] = io->rs2;
+    }
     if (div && !poisson_fuses_divergence(ps)) {
         set_error("poisson_solve: this solver cannot take the divergence from the velocity field");
         return 1;
@@ -1155,7 +1166,9 @@ static int solve_t(Poisson *ps, T *p, Launch L, const DivSource *div) {
             }
             {
                 ProfScope sc(L, 11);
-                INSB_TRY(fast_pass<T>(4, ps->n[0], R, ps->W, gx, 0, ps->tw[0], e0, e1, e2, factor, tl, L));
+                FastGeom go = gx;
+                go.img = io ? (io->img & 1) : 0;
+                INSB_TRY(fast_pass<T>(4, ps->n[0], Rout, ps->W, go, 0, ps->tw[0], e0, e1, e2, factor, tl, L));
             }
             return 0;
         }
@@ -1184,7 +1197,9 @@ static int solve_t(Poisson *ps, T *p, Launch L, const DivSource *div) {
         }
         {
             ProfScope sc(L, 11);
-            INSB_TRY(fast_pass<T>(4, ps->n[0], R, ps->W, g, 0, ps->tw[0], e0, e1, e2, factor, tl, L));
+            FastGeom go = g;
+            go.img = io ? io->img : 0;
+            INSB_TRY(fast_pass<T>(4, ps->n[0], Rout, ps->W, go, 0, ps->tw[0], e0, e1, e2, factor, tl, L));
         }
         return 0;
     }
@@ -1416,9 +1431,11 @@ bool poisson_fuses_divergence(const Poisson *ps) {
     return ps && (ps->fast || ps->fast_dct || ps->fast_tri) && e != nullptr && atoi(e) > 0;
 }
 
-int poisson_solve(Poisson *ps, void *p, Launch L, const DivSource *div) {
+bool poisson_supports_io(const Poisson *ps) { return ps && ps->fast && ps->D == 3; }
+
+int poisson_solve(Poisson *ps, void *p, Launch L, const DivSource *div, const PoissonIO *io) {
     if (ps->cg) return cg_solve(ps->cg, p, L);
-    return ps->f64 ? solve_t<double>(ps, (double *)p, L, div) : solve_t<float>(ps, (float *)p, L, div);
+    return ps->f64 ? solve_t<double>(ps, (double *)p, L, div, io) : solve_t<float>(ps, (float *)p, L, div, io);
 }
 
 }  // namespace insb

@@ -118,6 +118,7 @@ _PROTOTYPES = {
     "insb200_cfl": (C.c_int, [_P, _P, C.POINTER(ParamsStruct), C.POINTER(C.c_double), _P]),
     "insb200_maxabs": (C.c_int, [_P, _P, C.POINTER(C.c_double), _P]),
     "insb200_launch_count": (C.c_longlong, [_P]),
+    "insb200_debug_fused_copy": (C.c_int, [_P, C.c_int, _P, C.c_longlong, C.POINTER(C.c_int)]),
     "insb200_profile_enable": (C.c_int, [_P, C.c_int]),
     "insb200_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "insb200_profile_read_ex": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),

@@ -155,3 +155,49 @@ def test_channel_256_step():
     got, ref = I.to_host(sp_g["state"]["u"]), sp_o["state"]["u"]
     for a in range(3):
         assert rel_l2(got[so.Iu[a] + (a,)], ref[so.Iu[a] + (a,)]) < TOL[T]
+
+
+# ---- fused periodic path (csrc/stage_fused.cu): lazy projection + fused divergence + TMA plane staging ----
+FUSED_GRIDS = [(32, 64, 32), (64, 32, 64), (128, 32, 256), (256, 64, 32)]
+
+
+@pytest.mark.parametrize("T", [np.float64, np.float32])
+@pytest.mark.parametrize("mname", ["RK44", "LMWray3"])
+@pytest.mark.parametrize("n", FUSED_GRIDS)
+def test_fused_step_matches_oracle_and_staged_path(n, mname, T):
+    # power-of-two periodic boxes take the fused path: partial x tiles (32), several x / y tiles, two z
+    # chunks (256), constant body force; compared with the oracle and with the stage-by-stage CUDA path
+    I = ins()
+    so, sg = make_setups((uniform(n[0]), uniform(n[1], 0.5), uniform(n[2], 2.0)), ("P", "P", "P"), T=T)
+    ps_o, ps_g = opr.psolver_spectral(so), I.psolver_spectral(sg)
+    u0 = opr.project(smooth_vec(so, 45), so, ps_o)
+    obc.apply_bc_u(u0, 0.0, so)
+    bf = (0.3, -0.2, 0.1)
+    f_o = ots.make_navierstokes(so, 2e-3, bodyforce=bf)
+    pg = dict(viscosity=2e-3, bodyforce=bf)
+    sp_o, sp_g = _step_both(so, sg, ps_o, ps_g, mname, {"u": u0.copy(order="F")}, {"u": I.to_device(sg, u0)}, f_o,
+                            I.navierstokes_, pg, 2e-3, T, nsteps=2)
+    got = I.to_host(sp_g["state"]["u"])
+    assert rel_l2(got, sp_o["state"]["u"]) < 2 * TOL[T]
+    assert _max_div(I, sg, so, sp_g["state"]["u"]) < (1e-12 if T is np.float64 else 2e-4) * np.max(np.abs(u0)) * max(n)
+    os.environ["INSB200_NO_FUSED_STEP"] = "1"
+    try:
+        _, sp_s = _step_both(so, sg, ps_o, ps_g, mname, {"u": u0.copy(order="F")}, {"u": I.to_device(sg, u0)}, f_o,
+                             I.navierstokes_, pg, 2e-3, T, nsteps=2)
+    finally:
+        del os.environ["INSB200_NO_FUSED_STEP"]
+    assert rel_l2(got, I.to_host(sp_s["state"]["u"])) < 2 * TOL[T]
+
+
+def test_fused_path_is_taken():
+    # the fused step launches 1 stencil + 5 FFT kernels per stage and one projection per step
+    I = ins()
+    so, sg = make_setups((uniform(64), uniform(64), uniform(64)), ("P", "P", "P"), T=np.float32)
+    ps_g = I.psolver_spectral(sg)
+    u = I.velocityfield(sg, tgv3d, psolver=ps_g)
+    m = I.RKMethods.RK44(np.float32)
+    sp = I.create_stepper(m, setup=sg, psolver=ps_g, state={"u": u}, t=0.0)
+    sp = I.timestep_(m, I.navierstokes_, sp, np.float32(1e-3), params=dict(viscosity=1e-3))
+    l0 = ps_g.plan.launch_count
+    sp = I.timestep_(m, I.navierstokes_, sp, np.float32(1e-3), params=dict(viscosity=1e-3))
+    assert ps_g.plan.launch_count - l0 == 4 * 6 + 1
