@@ -89,7 +89,7 @@ struct FShape {
     // plane ring: column c <-> cell i0 - 4 + c (TMA boxes must start on a 16-byte boundary of the innermost
     // dimension: a Float32 box starting at cell i0 - 2 faults), row r <-> cell j0 - 2 + r
     static constexpr int PX = 72, PYU = TY + 3, PYP = TY + 4, PLANE = PX * PYU, NE = 3 * PLANE, NEP = PX * PYP;
-    static constexpr int D = IN == 0 ? 2 : 1;  // planes (groups) in flight ahead of their use
+    static constexpr int D = 2;  // planes (groups) in flight ahead of their use
     static constexpr int ZC = 128, ZT = ZC + 4;  // z tables: planes zbeg - 2 .. zend + 1
     static constexpr size_t al(size_t b) { return (b + 127) / 128 * 128; }
     static constexpr int NVRAW = IN ? D + 1 : 1, NPRAW = IN ? D + 2 : 1, NU = IN ? 3 : D + 2, NPW = D + 1;
@@ -142,7 +142,8 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1)
     T *const EXX = reinterpret_cast<T *>(smem + S::OFF_EXX);
     T *const zt = reinterpret_cast<T *>(smem + S::OFF_ZT);
     unsigned long long *const bars = reinterpret_cast<unsigned long long *>(smem + S::OFF_BAR);
-    auto uslot = [&](int q) { return reinterpret_cast<T *>(smem + S::OFF_U + (size_t)(((q % S::NU) + S::NU) % S::NU) * S::U_SLOT); };
+    // ring slots are tracked as small rotating indices (no modulo arithmetic in the march)
+    auto uslot = [&](int slot) { return reinterpret_cast<T *>(smem + S::OFF_U + (size_t)slot * S::U_SLOT); };
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool halo = warp == TY;
@@ -212,11 +213,12 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1)
             soff[q] = c * PLANE + py * PX + px + 2;
         }
     }
-    int zu = zs - 1;  // next reference-layout velocity plane to fetch
+    int zu = zs - 1;  // next reference-layout velocity plane to fetch ...
+    int fu = 0;       // ... into this slot (plane q sits in slot (q - (zs - 1)) mod NU)
     auto fetch_uref = [&]() {
         if (IN == 0) {
             if (zu <= zend) {
-                T *dst = uslot(zu);
+                T *dst = uslot(fu);
                 if (zu < 0 && !a.zwrap) {  // plane -1 of the slab: sent by the rank below, [3][N1][N0]
 #pragma unroll
                     for (int q = 0; q < NL; q++)
@@ -232,16 +234,17 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1)
                 }
             }
             zu++;
+            fu = fu + 1 == S::NU ? 0 : fu + 1;
         }
     };
     // ---- pointwise operands of plane k ----
     // VB == 1: vbase from the reference layout, 4-byte copies: main threads [c][thread][2], warp 8: the halo
     // row (y component) and the halo column (x component)
     const long long pw_off = (long long)min(i0 + 2 * lane, n0 - 1) + (long long)wrap1(min(Yraw, n1), n1) * a.N0;
-    auto fetch_pw_ref = [&](int k) {
+    auto fetch_pw_ref = [&](int k, int slot) {
         if (VB == 1) {
             if (k >= zs && k < zend) {
-                T *dst = reinterpret_cast<T *>(smem + S::OFF_PWV + (size_t)(k % S::NPW) * S::PWV_SLOT);
+                T *dst = reinterpret_cast<T *>(smem + S::OFF_PWV + (size_t)slot * S::PWV_SLOT);
                 const T *src = a.vb_ref + (long long)(a.zwrap ? wrap1(k, nz) : k) * a.rs2;
                 if (!halo) {
 #pragma unroll
@@ -260,9 +263,11 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1)
     };
     // ---- TMA group j = { vraw(j + 2), praw(j + 3) [, praw(j + 2) for the first group], pw(j) } ----
     const int bx0 = i0 + OX - 1, by0 = j0 + OY - 1;  // internal indices of the tile's first cell
-    auto issue_group = [&](int j, bool first) {
+    // group j lives in barrier / vraw / pointwise slot sb = (j - zfirst) mod (D + 1) and praw slot
+    // sp = (j - zfirst) mod (D + 2)
+    auto issue_group = [&](int j, int sb, int sp, bool first) {
         if (IN == 1) {
-            void *bar = bars + (((j % (D + 1)) + (D + 1)) % (D + 1));
+            void *bar = bars + sb;
             unsigned bytes = 0;
             const bool pw = j >= zs && j < zend;
             bytes += (unsigned)(NE * sizeof(T)) + (unsigned)(S::NEP * sizeof(T)) * (first ? 2u : 1u);
@@ -271,17 +276,14 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(bar, bytes);
             const int qv = j + 2, qp = j + 3;
-            tma_load_4d(smem + S::OFF_VRAW + (size_t)(((qv % S::NVRAW) + S::NVRAW) % S::NVRAW) * S::VRAW_SLOT, &tm_v, bar,
-                        bx0 - 4, by0 - 2, qv + OZ - 1, 0);
-            tma_load_3d(smem + S::OFF_PRAW + (size_t)(((qp % S::NPRAW) + S::NPRAW) % S::NPRAW) * S::PRAW_SLOT, &tm_p, bar,
-                        bx0 - 4, by0 - 2, qp + OZ - 1);
-            if (first)
-                tma_load_3d(smem + S::OFF_PRAW + (size_t)((((qp - 1) % S::NPRAW) + S::NPRAW) % S::NPRAW) * S::PRAW_SLOT, &tm_p,
-                            bar, bx0 - 4, by0 - 2, qp - 1 + OZ - 1);
+            tma_load_4d(smem + S::OFF_VRAW + (size_t)sb * S::VRAW_SLOT, &tm_v, bar, bx0 - 4, by0 - 2, qv + OZ - 1, 0);
+            tma_load_3d(smem + S::OFF_PRAW + (size_t)sp * S::PRAW_SLOT, &tm_p, bar, bx0 - 4, by0 - 2, qp + OZ - 1);
+            if (first)  // praw(j + 2) of the very first group: slot "-1"
+                tma_load_3d(smem + S::OFF_PRAW + (size_t)(D + 1) * S::PRAW_SLOT, &tm_p, bar, bx0 - 4, by0 - 2, qp - 1 + OZ - 1);
             if (pw && VB == 2)
-                tma_load_4d(smem + S::OFF_PWV + (size_t)(j % S::NPW) * S::PWV_SLOT, &tm_vb, bar, bx0 - 4, by0 - 1, j + OZ - 1, 0);
+                tma_load_4d(smem + S::OFF_PWV + (size_t)sb * S::PWV_SLOT, &tm_vb, bar, bx0 - 4, by0 - 1, j + OZ - 1, 0);
             if (pw && S::PWA)
-                tma_load_4d(smem + S::OFF_PWA + (size_t)(j % S::NPW) * S::PWA_SLOT, &tm_acc, bar, bx0, by0, j + OZ - 1, 0);
+                tma_load_4d(smem + S::OFF_PWA + (size_t)sb * S::PWA_SLOT, &tm_acc, bar, bx0, by0, j + OZ - 1, 0);
         }
     };
     // ---- lazy projection of plane q: U(q) = vraw(q) - G praw   (applypressure!, src/operators.jl:306-311) ----
@@ -296,14 +298,14 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1)
 #pragma unroll
         for (int rr = 0; rr < PRR; rr++) prj_ry[rr] = g.rdu[1][wrap1(min(j0 - 2 + prow0 + rr, n1 + 2), n1)];
     }
-    auto project_plane = [&](int q) {
+    // vraw(q) sits in slot sv, praw(q) / praw(q + 1) in slots spm / sp, the result goes to ring slot su
+    auto project_plane = [&](int sv, int spm, int sp, int su, const T rz) {
         if (IN == 1) {
             if (tid < PRG * PX) {
-                const T *vr = reinterpret_cast<const T *>(smem + S::OFF_VRAW + (size_t)(((q % S::NVRAW) + S::NVRAW) % S::NVRAW) * S::VRAW_SLOT);
-                const T *pr = reinterpret_cast<const T *>(smem + S::OFF_PRAW + (size_t)(((q % S::NPRAW) + S::NPRAW) % S::NPRAW) * S::PRAW_SLOT);
-                const T *pu = reinterpret_cast<const T *>(smem + S::OFF_PRAW + (size_t)((((q + 1) % S::NPRAW) + S::NPRAW) % S::NPRAW) * S::PRAW_SLOT);
-                T *uo = uslot(q);
-                const T rz = zt[2 * ZT + (q - (zbeg - 2))];
+                const T *vr = reinterpret_cast<const T *>(smem + S::OFF_VRAW + (size_t)sv * S::VRAW_SLOT);
+                const T *pr = reinterpret_cast<const T *>(smem + S::OFF_PRAW + (size_t)spm * S::PRAW_SLOT);
+                const T *pu = reinterpret_cast<const T *>(smem + S::OFF_PRAW + (size_t)sp * S::PRAW_SLOT);
+                T *uo = uslot(su);
 #pragma unroll
                 for (int rr = 0; rr < PRR; rr++) {
                     const int r = prow0 + rr;
@@ -329,9 +331,9 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1)
     P vn0 = pbc(T(0)), vn1 = pbc(T(0)), vn2 = pbc(T(0));  // stage output of the previous plane (divergence is one plane late)
     P vzm = pbc(T(0));                                    // its z component one plane further down
     T hFb = T(0);                                         // warp 8, lanes < 8: bottom flux of the halo column (x component)
-    auto init_bottom = [&](int k) {  // fluxes through the top faces of plane k - 1 = bottom faces of plane k
-        const T *lo = uslot(k - 1) + lidx, *hi = uslot(k) + lidx;
-        const T *ztr = zt + (k - 1 - (zbeg - 2));
+    // fluxes through the top faces of the plane in slot slo (z-table row ztr) = bottom faces of the plane in slot shi
+    auto init_bottom = [&](int slo, int shi, const T *ztr) {
+        const T *lo = uslot(slo) + lidx, *hi = uslot(shi) + lidx;
         const P z_lg = pbc(ztr[0]), z_ug = pbc(ztr[ZT]);
         const P u2 = AL(lo, 2, 0);
         if (!halo) {
@@ -341,7 +343,7 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1)
         Fb1 = flux_off<P>(AL(lo, 1, 0), AL(hi, 1, 0), u2, AL(lo, 2, 1), y_hw2, y_hw1, z_ug);
         if (halo && lane < TY) {
             const int hi_i = wrap1(i0 - 1, n0);
-            const T *l2 = uslot(k - 1) + (lane + 2) * PX + 3, *h2 = uslot(k) + (lane + 2) * PX + 3;
+            const T *l2 = uslot(slo) + (lane + 2) * PX + 3, *h2 = uslot(shi) + (lane + 2) * PX + 3;
             const P w2 = pbc(T(0.5) * g.a2[0][hi_i]), w1 = pbc(T(0.5) * g.a1[0][hi_i + 1]);
             hFb = flux_off<P>(pbc(l2[0]), pbc(h2[0]), pbc(l2[2 * PLANE]), pbc(l2[2 * PLANE + 1]), w2, w1, z_ug).x;
         }
@@ -358,13 +360,12 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1)
     const long long gy = (cj <= 2 ? (long long)n1 : (cj >= n1 - 1 ? -(long long)n1 : 0)) * a.s1;
 
     // divergence of the stage output of plane k - 1 (vn*, vzm), emitted at the start of iteration k
-    auto emit_div = [&](int kprev) {
+    auto emit_div = [&](int kprev, const T *ztr) {
         const int par = kprev & 1;
         T up = __shfl_up_sync(0xffffffffu, vn0.y, 1);
         if (lane == 0) up = EXX[par * 8 + ty];
         const P vxm = pmk(up, vn0.x);
         const P vym = *reinterpret_cast<const P *>(EXY + (par * (TY + 1) + ty) * 64 + 2 * lane);
-        const T *ztr = zt + (kprev - (zbeg - 2));
         P dd = padd(pmul(psub(vn0, vxm), dv_rx), pmul(psub(vn1, vym), pbc(dv_ry)));
         dd = padd(dd, pmul(psub(vn2, vzm), pbc(ztr[6 * ZT])));
         const P om = pmul(pmul(dv_dx, pbc(dv_dy)), pbc(ztr[7 * ZT]));
@@ -373,6 +374,10 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1)
     };
 
     // =========================== prologue ===========================
+    const int zfirst = IN == 1 ? zs - 3 : zs;
+    const T *ztz = zt + (zfirst - (zbeg - 2));  // z-table row of plane z (valid from the first computed plane on)
+    int su0, su1, su2 = 0;                      // ring slots of planes z, z + 1 (read) and z + 2 (lazily projected)
+    int wb = 0, wpar = 0, wp = 0;               // group z: barrier / vraw / pointwise slot, barrier parity, praw slot
     if (IN == 0) {
         // planes zs - 1, zs, zs + 1 (group 0), then D - 1 more groups
         fetch_uref();
@@ -386,26 +391,27 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1)
         }
         cpa_wait<D - 1>();
         __syncthreads();
-        init_bottom(zs);
+        init_bottom(0, 1, ztz - 1);
+        su0 = 1, su1 = 2;
     } else {
         __syncthreads();  // barriers initialised, z tables written
         if (tid == TY * 32) {
 #pragma unroll
-            for (int d = 0; d < D; d++) issue_group(zs - 3 + d, d == 0);
+            for (int d = 0; d < D; d++) issue_group(zfirst + d, d, d, d == 0);
         }
 #pragma unroll
         for (int d = 0; d < D; d++) {
-            fetch_pw_ref(zs - 3 + d);
+            fetch_pw_ref(zfirst + d, d);
             cpa_commit();
         }
+        su0 = 1, su1 = 2;  // (U(z + 2) goes to slot (z - zfirst) mod 3)
     }
 
     // =========================== march ===========================
-    const int zfirst = IN == 1 ? zs - 3 : zs;
     long long zo = (long long)(zfirst + OZ - 1) * a.s2;  // plane z of the internal arrays
     for (int z = zfirst; z < zend; z++) {
         if (IN == 1) {
-            mbar_wait(bars + (((z % (D + 1)) + (D + 1)) % (D + 1)), (unsigned)((((z - zfirst) / (D + 1))) & 1));
+            mbar_wait(bars + wb, (unsigned)wpar);
             if (VB == 1) cpa_wait<D - 1>();
         } else {
             cpa_wait<D - 1>();
@@ -413,22 +419,24 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1)
         __syncthreads();
         // next loads
         if (IN == 1) {
-            if (tid == TY * 32 && z + D < zend) issue_group(z + D, false);
-            fetch_pw_ref(z + D);
+            const int ib = wb == 0 ? D : wb - 1;              // (wb + D) mod (D + 1)
+            const int ip = wp >= 2 ? wp - 2 : wp + D;         // (wp + D) mod (D + 2)
+            if (tid == TY * 32 && z + D < zend) issue_group(z + D, ib, ip, false);
+            fetch_pw_ref(z + D, ib);
             cpa_commit();
         } else {
             fetch_uref();  // plane z + 1 + D
             cpa_commit();
         }
         const bool comp = z >= zs;
-        if (!halo && comp && z > zs) emit_div(z - 1);
+        if (!halo && comp && z > zs) emit_div(z - 1, ztz - 1);
         if (IN == 1) {
-            project_plane(z + 2);
-            if (z == zs - 1) init_bottom(zs);  // U(zs - 1), U(zs) are complete (projected two / one iterations ago)
+            project_plane(wb, wp == 0 ? D + 1 : wp - 1, wp, su2, ztz[2 * ZT + 2]);
+            if (z == zs - 1) init_bottom(su0, su1, ztz);  // U(zs - 1), U(zs): projected two / one iterations ago
         }
         if (comp) {
-            const T *p0 = uslot(z) + lidx, *pp = uslot(z + 1) + lidx;
-            const T *ztr = zt + (z - (zbeg - 2));
+            const T *p0 = uslot(su0) + lidx, *pp = uslot(su1) + lidx;
+            const T *ztr = ztz;
             const P z_lg = pbc(ztr[0]), z_ug = pbc(ztr[ZT]);
             const P z_rdu = pbc(ztr[2 * ZT]), z_rdl = pbc(ztr[3 * ZT]), z_hw2 = pbc(ztr[4 * ZT]), z_hw1 = pbc(ztr[5 * ZT]);
             const P u0c = AL(p0, 0, 0), u1c = AL(p0, 1, 0), u2c = AL(p0, 2, 0);
@@ -443,7 +451,7 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1)
             k1 = pfma(psub(Fb1, Ft1), z_rdl, k1);
             Fb1 = Ft1;
             k1 = padd(k1, pbc(a.bf[1]));
-            const int slot_pw = z % S::NPW;
+            const int slot_pw = wb;
             if (!halo) {
                 const P u0xp = XP(p0, 0, 0), u2xm = XM(p0, 2, 0), u2xp = XP(p0, 2, 0);
                 const P u0ym = AL(p0, 0, -1), u2ym = AL(p0, 2, -1), u2yp = AL(p0, 2, 1);
@@ -531,7 +539,7 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1)
                 // column part: x component at (i0 - 1, j0 + lane), lanes 0..TY-1 (both pair slots hold the same cell)
                 if (lane < TY) {
                     const int ic = wrap1(i0 - 1, n0), jc = min(j0 + lane, n1);
-                    const T *c0 = uslot(z) + (lane + 2) * PX + 3, *cp = uslot(z + 1) + (lane + 2) * PX + 3;
+                    const T *c0 = uslot(su0) + (lane + 2) * PX + 3, *cp = uslot(su1) + (lane + 2) * PX + 3;
                     const P cx_lg0 = pbc(-nu * g.rdlg[0][ic]), cx_lg1 = pbc(-nu * g.rdlg[0][ic + 1]);
                     const P cx_rdu = pbc(g.rdu[0][ic]);
                     const P cx_hw2 = pbc(T(0.5) * g.a2[0][ic]), cx_hw1 = pbc(T(0.5) * g.a1[0][ic + 1]);
@@ -560,10 +568,21 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1)
             }
         }
         zo += a.s2;
+        ztz++;
+        if (IN == 1) {
+            const int t3 = su0;
+            su0 = su1, su1 = su2, su2 = t3;
+            wb = wb == D ? 0 : wb + 1;
+            wpar ^= wb == 0;
+            wp = wp == D + 1 ? 0 : wp + 1;
+        } else {
+            su0 = su1;
+            su1 = su1 + 1 == S::NU ? 0 : su1 + 1;
+        }
     }
     // divergence of the last plane
     __syncthreads();
-    if (!halo) emit_div(zend - 1);
+    if (!halo) emit_div(zend - 1, ztz - 1);
 }
 
 
