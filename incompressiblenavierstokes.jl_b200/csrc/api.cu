@@ -53,6 +53,7 @@ struct insb200_plan : public insb::Profiler {
     // fused periodic time-step path (fused.h): padded internal arrays -- two unprojected stage velocities,
     // the running accumulator, the pressure and the scaled divergence -- and their tensor maps
     void *FV[2] = {nullptr, nullptr}, *FACC = nullptr, *FP = nullptr, *FD = nullptr;
+    void *FUB = nullptr;  // slab mode: plane "-1" of the caller's velocity (from the rank below), [3][N1][N0]
     FusedCtx fctx{};
     bool fused_ready = false;
     long long bytes = 0;
@@ -347,12 +348,13 @@ int ensure_k(insb200_plan *pl, int count, bool temp) {
 // body force), one GPU.  Everything else keeps the stage-by-stage path below.
 bool fused_applicable(const insb200_plan *pl, const insb200_params_t *pr) {
     const bool off = getenv("INSB200_NO_FUSED_STEP") != nullptr;  // (read per call: the tests toggle it)
-    if (off || pl->D != 3 || pl->comm || pl->prof_legacy) return false;
+    if (off || pl->D != 3 || pl->prof_legacy) return false;
+    if (pl->comm && getenv("INSB200_NO_FUSED_SLAB") != nullptr) return false;
     for (int a = 0; a < 3; a++)
         if (pl->s.bc_u[a][0] != INSB200_BC_PERIODIC || pl->s.bc_u[a][1] != INSB200_BC_PERIODIC) return false;
     if (pr->boussinesq || pr->eddy_model != 0) return false;
     if (!pl->ps || pl->psolver != INSB200_PSOLVER_SPECTRAL || !poisson_supports_io(pl->ps)) return false;
-    const int n0 = pl->s.N[0] - 2, n1 = pl->s.N[1] - 2, n2 = pl->s.N[2] - 2;
+    const int n0 = pl->s.N[0] - 2, n1 = pl->s.N[1] - 2, n2 = pl->comm ? pl->nzl : pl->s.N[2] - 2;
     if (n0 % 2 || n0 < 8 || n1 < 8 || n2 < 8) return false;
     const FusedLayout L = make_fused_layout(n0, n1, n2);
     return 3 * L.cs < (1LL << 31) && 3 * (long long)pl->ncell < (1LL << 32);
@@ -360,11 +362,12 @@ bool fused_applicable(const insb200_plan *pl, const insb200_params_t *pr) {
 
 int ensure_fused(insb200_plan *pl) {
     if (pl->fused_ready) return 0;
-    const int n0 = pl->s.N[0] - 2, n1 = pl->s.N[1] - 2, n2 = pl->s.N[2] - 2;
+    const int n0 = pl->s.N[0] - 2, n1 = pl->s.N[1] - 2, n2g = pl->s.N[2] - 2, n2 = pl->comm ? pl->nzl : n2g;
     pl->fctx.L = make_fused_layout(n0, n1, n2);
-    pl->fctx.zwrap = 1;
-    pl->fctx.zoff = 0;
-    pl->fctx.n2g = n2;
+    pl->fctx.zwrap = pl->comm ? 0 : 1;
+    pl->fctx.zoff = pl->comm ? comm_rank(pl->comm) * pl->nzl : 0;
+    pl->fctx.n2g = n2g;
+    if (pl->comm) INSB_TRY(dev_alloc(pl, &pl->FUB, (size_t)3 * pl->s.N[0] * pl->s.N[1] * pl->esz));
     INSB_TRY(fused_maps_create(&pl->fctx.maps));
     const size_t sb = (size_t)pl->fctx.L.cs * pl->esz;
     INSB_TRY(dev_alloc(pl, &pl->FV[0], 3 * sb));
@@ -378,13 +381,38 @@ int ensure_fused(insb200_plan *pl) {
 
 // One fused stage followed by its Poisson solve: the stage kernel leaves the unprojected velocity in v_out
 // and the scaled divergence in FD; the solve turns FD into the pressure FP (with its ghost images).
+// Slab mode: the two z ghost planes on either side of `ncomp` padded internal arrays come from the neighbouring
+// ranks (whole padded planes: their x / y ghost images travel along).
 template <typename T>
-int fused_stage_and_solve(insb200_plan *pl, const FusedStage<T> &st, bool ct_double, void *stream) {
+int fused_halo(insb200_plan *pl, T *f, int ncomp, Launch L) {
+    const FusedLayout &FL = pl->fctx.L;
+    if (L.counter) *L.counter += comm_exchange_launches(pl->comm, (size_t)FusedLayout::OZ * FL.s2 * sizeof(T), ncomp);
+    return comm_halo_planes(pl->comm, f, sizeof(T), FL.s2, FL.NPZ, FusedLayout::OZ, ncomp, FL.cs, L.stream);
+}
+
+template <typename T>
+int fused_stage_and_solve(insb200_plan *pl, const FusedStage<T> &st_in, bool ct_double, void *stream) {
     const Grid<T> &g = grid_of<T>(pl);
     Launch L = L_of(pl, stream);
+    FusedStage<T> st = st_in;
+    if (pl->comm && st.u_ref) {
+        // first stage of a step on a slab: the stage output on ghost plane 0 needs the caller's velocity on
+        // plane -1 = the top interior plane but one of the rank below
+        Scope sc(pl, L.stream, 4);
+        const size_t pb = (size_t)g.s[2] * sizeof(T);
+        if (L.counter) *L.counter += comm_exchange_launches(pl->comm, pb, 3);
+        INSB_TRY(comm_exchange(pl->comm, (const char *)st.u_ref + (size_t)(pl->nzl - 1) * pb, nullptr, pl->FUB, nullptr, pb, 3,
+                               (size_t)g.cs * sizeof(T), pb, L.stream));
+        st.u_below = (const T *)pl->FUB;
+    }
     {
         Scope sc(pl, L.stream, 0);
         INSB_TRY(launch_stage_fused<T>(g, pl->fctx, st, ct_double, L));
+    }
+    if (pl->comm) {
+        Scope sc(pl, L.stream, 4);
+        INSB_TRY(fused_halo<T>(pl, st.v_out, 3, L));
+        if (st.acc_out) INSB_TRY(fused_halo<T>(pl, st.acc_out, 3, L));
     }
     const FusedLayout &FL = pl->fctx.L;
     PoissonIO io{};
@@ -393,15 +421,29 @@ int fused_stage_and_solve(insb200_plan *pl, const FusedStage<T> &st, bool ct_dou
     io.rs1 = FL.s1;
     io.rs2 = FL.s2;
     io.img = 1 | (pl->fctx.zwrap ? 2 : 0);
-    Scope sc(pl, L.stream, 2);
-    return poisson_solve(pl->ps, nullptr, L, nullptr, &io);
+    {
+        Scope sc(pl, L.stream, 2);
+        INSB_TRY(poisson_solve(pl->ps, nullptr, L, nullptr, &io));
+    }
+    if (pl->comm) {
+        Scope sc(pl, L.stream, 4);
+        INSB_TRY(fused_halo<T>(pl, (T *)pl->FP, 1, L));
+    }
+    return 0;
 }
 
 template <typename T>
 int fused_finish(insb200_plan *pl, const T *v, T *U, void *stream) {
     Launch L = L_of(pl, stream);
-    Scope sc(pl, L.stream, 3);
-    return launch_project_out<T>(grid_of<T>(pl), pl->fctx, v, (const T *)pl->FP, U, L);
+    {
+        Scope sc(pl, L.stream, 3);
+        INSB_TRY(launch_project_out<T>(grid_of<T>(pl), pl->fctx, v, (const T *)pl->FP, U, L));
+    }
+    if (pl->comm) {  // z ghost planes of the result (apply_bc_u! along the decomposed direction)
+        Scope sc(pl, L.stream, 4);
+        INSB_TRY(launch_bc_u<T>(grid_of<T>(pl), pl->bc, U, 0, L, 4));
+    }
+    return 0;
 }
 
 template <typename T>

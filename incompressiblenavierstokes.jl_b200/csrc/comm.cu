@@ -182,16 +182,19 @@ int comm_world(const Comm *c) { return c ? c->world : 1; }
 // most one exchange ahead of its neighbours (it needs their data of exchange e before it can
 // start e + 1), so the slot of exchange e + 2 is free again when it is written.
 template <typename V>
-__global__ void __launch_bounds__(256) halo_push_kernel(const char *field, size_t plane_bytes, int nplanes,
+__global__ void __launch_bounds__(256) halo_push_kernel(const char *src_up, const char *src_down, size_t chunk_bytes,
                                                         size_t cs_bytes, char *up_slot, char *down_slot,
                                                         unsigned *up_flag, unsigned *down_flag, unsigned epoch,
                                                         unsigned *counter) {
     const int comp = blockIdx.y, dir = blockIdx.z;  // dir 0: send up, 1: send down
-    const size_t nv = plane_bytes / sizeof(V);
-    const V *src = reinterpret_cast<const V *>(field + comp * cs_bytes + (dir == 0 ? (size_t)(nplanes - 2) : 1) * plane_bytes);
-    V *dst = reinterpret_cast<V *>((dir == 0 ? up_slot : down_slot) + comp * plane_bytes);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (size_t)gridDim.x * blockDim.x)
-        dst[i] = src[i];
+    const size_t nv = chunk_bytes / sizeof(V);
+    const char *s = dir == 0 ? src_up : src_down;
+    if (s) {
+        const V *src = reinterpret_cast<const V *>(s + comp * cs_bytes);
+        V *dst = reinterpret_cast<V *>((dir == 0 ? up_slot : down_slot) + comp * chunk_bytes);
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (size_t)gridDim.x * blockDim.x)
+            dst[i] = src[i];
+    }
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -207,8 +210,8 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const char *field, size_
 }
 
 template <typename V>
-__global__ void __launch_bounds__(256) halo_pull_kernel(char *field, size_t plane_bytes, int nplanes, size_t cs_bytes,
-                                                        const char *below_slot, const char *above_slot,
+__global__ void __launch_bounds__(256) halo_pull_kernel(char *dst_below, char *dst_above, size_t chunk_bytes,
+                                                        size_t cs_bytes, const char *below_slot, const char *above_slot,
                                                         const unsigned *below_flag, const unsigned *above_flag,
                                                         unsigned epoch, unsigned *timeout_flag) {
     const int comp = blockIdx.y, dir = blockIdx.z;  // dir 0: data from below -> lower ghost, 1: from above -> upper ghost
@@ -228,30 +231,36 @@ __global__ void __launch_bounds__(256) halo_pull_kernel(char *field, size_t plan
         __threadfence_system();
     }
     __syncthreads();
-    const size_t nv = plane_bytes / sizeof(V);
-    const V *src = reinterpret_cast<const V *>((dir == 0 ? below_slot : above_slot) + comp * plane_bytes);
-    V *dst = reinterpret_cast<V *>(field + comp * cs_bytes + (dir == 0 ? 0 : (size_t)(nplanes - 1)) * plane_bytes);
+    char *d = dir == 0 ? dst_below : dst_above;
+    if (!d) return;
+    const size_t nv = chunk_bytes / sizeof(V);
+    const V *src = reinterpret_cast<const V *>((dir == 0 ? below_slot : above_slot) + comp * chunk_bytes);
+    V *dst = reinterpret_cast<V *>(d + comp * cs_bytes);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (size_t)gridDim.x * blockDim.x)
         dst[i] = __ldcv(src + i);  // written by a peer: do not serve from a stale cache line
 }
 
+// chunk `send_up` (+ c * src_cs) of every component c goes to the rank above, which receives it in `recv_below`
+// (+ c * dst_cs); `send_down` / `recv_above` likewise for the other direction.  Null pointers skip a direction
+// (all ranks alike); the flags of both directions are raised and awaited regardless.
 template <typename V>
-static int halo_p2p_t(Comm *c, char *f, size_t pb, int nplanes, int ncomp, size_t csb, cudaStream_t st) {
+static int exchange_p2p_t(Comm *c, const char *send_up, const char *send_down, char *recv_below, char *recv_above,
+                          size_t chunk, int ncomp, size_t src_cs, size_t dst_cs, cudaStream_t st) {
     const int up = (c->rank + 1) % c->world, down = (c->rank + c->world - 1) % c->world;
     const unsigned e = ++c->halo_epoch;
     const int q = e & 1;
     auto slot = [&](int r, int dir) { return c->halo_win[r] + HALO_STAGING + (size_t)(q * 2 + dir) * c->halo_slot; };
     auto flag = [&](int r, int dir) { return reinterpret_cast<unsigned *>(c->halo_win[r]) + HALO_FLAG0 + q * 2 + dir; };
     unsigned *mine = reinterpret_cast<unsigned *>(c->halo_win[c->rank]);
-    const size_t nv = pb / sizeof(V);
+    const size_t nv = chunk / sizeof(V);
     unsigned nb = (unsigned)((nv + 255) / 256);
     if (nb > 64) nb = 64;
     dim3 gr(nb, ncomp, 2);
-    halo_push_kernel<V><<<gr, 256, 0, st>>>(f, pb, nplanes, csb, slot(up, 0), slot(down, 1), flag(up, 0), flag(down, 1),
-                                            e, mine + HALO_COUNTER);
+    halo_push_kernel<V><<<gr, 256, 0, st>>>(send_up, send_down, chunk, src_cs, slot(up, 0), slot(down, 1), flag(up, 0),
+                                            flag(down, 1), e, mine + HALO_COUNTER);
     INSB_CUDA(cudaGetLastError());
-    halo_pull_kernel<V><<<gr, 256, 0, st>>>(f, pb, nplanes, csb, slot(c->rank, 0), slot(c->rank, 1), flag(c->rank, 0),
-                                            flag(c->rank, 1), e, mine + HALO_TIMEOUT);
+    halo_pull_kernel<V><<<gr, 256, 0, st>>>(recv_below, recv_above, chunk, dst_cs, slot(c->rank, 0), slot(c->rank, 1),
+                                            flag(c->rank, 0), flag(c->rank, 1), e, mine + HALO_TIMEOUT);
     INSB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -270,27 +279,49 @@ void comm_disable_p2p_halo(Comm *c, const void *my_window) {
 
 int comm_halo_launches(const Comm *c) { return c && c->halo_p2p ? 2 : 0; }
 
-int comm_halo_z(Comm *c, void *field, size_t esz, long long plane, int nplanes, int ncomp, long long cs,
-                cudaStream_t st) {
-    if (c->halo_p2p && (size_t)ncomp * plane * esz <= c->halo_slot) {
-        const size_t pb = (size_t)plane * esz, csb = (size_t)cs * esz;
-        if (pb % 16 == 0 && csb % 16 == 0 && (uintptr_t)field % 16 == 0)
-            return halo_p2p_t<uint4>(c, (char *)field, pb, nplanes, ncomp, csb, st);
-        return halo_p2p_t<unsigned>(c, (char *)field, pb, nplanes, ncomp, csb, st);
+int comm_exchange(Comm *c, const void *send_up, const void *send_down, void *recv_below, void *recv_above,
+                  size_t chunk_bytes, int ncomp, size_t src_cs_bytes, size_t dst_cs_bytes, cudaStream_t st) {
+    if (c->halo_p2p && (size_t)ncomp * chunk_bytes <= c->halo_slot) {
+        const uintptr_t all = (uintptr_t)send_up | (uintptr_t)send_down | (uintptr_t)recv_below | (uintptr_t)recv_above |
+                              chunk_bytes | src_cs_bytes | dst_cs_bytes;
+        if (all % 16 == 0)
+            return exchange_p2p_t<uint4>(c, (const char *)send_up, (const char *)send_down, (char *)recv_below,
+                                         (char *)recv_above, chunk_bytes, ncomp, src_cs_bytes, dst_cs_bytes, st);
+        return exchange_p2p_t<unsigned>(c, (const char *)send_up, (const char *)send_down, (char *)recv_below,
+                                        (char *)recv_above, chunk_bytes, ncomp, src_cs_bytes, dst_cs_bytes, st);
     }
+    // Posting order (send up, send down, recv from below, recv from above) keeps the pairs matched when
+    // world == 2 and both neighbours are the same peer.
     const int up = (c->rank + 1) % c->world, down = (c->rank + c->world - 1) % c->world;
-    char *f = (char *)field;
-    const size_t pb = (size_t)plane * esz;
     INSB_NCCL(g_nccl.GroupStart());
     for (int k = 0; k < ncomp; k++) {
-        char *b = f + (size_t)k * cs * esz;
-        INSB_NCCL(g_nccl.Send(b + (size_t)(nplanes - 2) * pb, pb, ncclChar, up, c->comm, st));
-        INSB_NCCL(g_nccl.Send(b + pb, pb, ncclChar, down, c->comm, st));
-        INSB_NCCL(g_nccl.Recv(b, pb, ncclChar, down, c->comm, st));
-        INSB_NCCL(g_nccl.Recv(b + (size_t)(nplanes - 1) * pb, pb, ncclChar, up, c->comm, st));
+        const size_t so = (size_t)k * src_cs_bytes, dof = (size_t)k * dst_cs_bytes;
+        if (send_up) INSB_NCCL(g_nccl.Send((const char *)send_up + so, chunk_bytes, ncclChar, up, c->comm, st));
+        if (send_down) INSB_NCCL(g_nccl.Send((const char *)send_down + so, chunk_bytes, ncclChar, down, c->comm, st));
+        if (recv_below) INSB_NCCL(g_nccl.Recv((char *)recv_below + dof, chunk_bytes, ncclChar, down, c->comm, st));
+        if (recv_above) INSB_NCCL(g_nccl.Recv((char *)recv_above + dof, chunk_bytes, ncclChar, up, c->comm, st));
     }
     INSB_NCCL(g_nccl.GroupEnd());
     return 0;
+}
+
+int comm_exchange_launches(const Comm *c, size_t chunk_bytes, int ncomp) {
+    return c && c->halo_p2p && (size_t)ncomp * chunk_bytes <= c->halo_slot ? 2 : 0;
+}
+
+// Ghost planes of a field whose component is `nplanes` contiguous planes of `plane` elements with `ng` ghost
+// planes on either side: the top ng interior planes go up, the first ng interior planes go down.
+int comm_halo_planes(Comm *c, void *field, size_t esz, long long plane, int nplanes, int ng, int ncomp, long long cs,
+                     cudaStream_t st) {
+    char *f = (char *)field;
+    const size_t pb = (size_t)plane * esz, csb = (size_t)cs * esz;
+    return comm_exchange(c, f + (size_t)(nplanes - 2 * ng) * pb, f + (size_t)ng * pb, f, f + (size_t)(nplanes - ng) * pb,
+                         (size_t)ng * pb, ncomp, csb, csb, st);
+}
+
+int comm_halo_z(Comm *c, void *field, size_t esz, long long plane, int nplanes, int ncomp, long long cs,
+                cudaStream_t st) {
+    return comm_halo_planes(c, field, esz, plane, nplanes, 1, ncomp, cs, st);
 }
 
 // All-to-all of `world` equal blocks of `block_bytes`: block r of `send` goes to rank r and

@@ -63,6 +63,15 @@ int comm_rank(const Comm *c);   // 0 for nullptr
 int comm_world(const Comm *c);  // 1 for nullptr
 int comm_halo_z(Comm *c, void *field, size_t esz, long long plane, int nplanes, int ncomp, long long cs,
                 cudaStream_t st);
+// Generic neighbour exchange along the decomposed direction: chunk `send_up` (+ c * src_cs_bytes for component
+// c) goes to the rank above, which receives it in `recv_below` (+ c * dst_cs_bytes); `send_down` / `recv_above`
+// likewise downwards.  Null pointers skip a direction (all ranks alike).
+int comm_exchange(Comm *c, const void *send_up, const void *send_down, void *recv_below, void *recv_above,
+                  size_t chunk_bytes, int ncomp, size_t src_cs_bytes, size_t dst_cs_bytes, cudaStream_t st);
+int comm_exchange_launches(const Comm *c, size_t chunk_bytes, int ncomp);
+// `ng` ghost planes on either side of `nplanes` contiguous planes per component
+int comm_halo_planes(Comm *c, void *field, size_t esz, long long plane, int nplanes, int ng, int ncomp, long long cs,
+                     cudaStream_t st);
 // Halo exchange by direct peer stores: `windows[r]` is rank r's window (peer-mapped, windows[rank]
 // local) of comm_halo_window_bytes(slot_bytes) bytes, zero-initialised; slot_bytes >= bytes of
 // the ghost planes of one exchange (all components).  Until enabled comm_halo_z uses NCCL.

@@ -806,7 +806,8 @@ int poisson_create(const insb200_setup_t &s, const int Ip[3][2], int kind, Comm 
         ps->bytes += 2 * (long long)wbytes;
         ps->wbytes = wbytes;
         // flag words of the transposes + the window of the peer-store halo exchange (comm.cu)
-        ps->halo_slot = (size_t)3 * ps->Ng[0] * ps->Ng[1] * esz / 2;  // esz = complex size here
+        // (largest exchange: two padded planes of the three components of the fused path, fused.h)
+        ps->halo_slot = (size_t)6 * ((ps->Ng[0] + 9) / 4 * 4) * (ps->Ng[1] + 2) * esz / 2;  // esz = complex size here
         const size_t fb = comm_halo_window_bytes(ps->halo_slot);
         if (cudaMalloc((void **)&ps->flags, fb) != cudaSuccess)
             return fail("cudaMalloc of the peer flags / halo window failed");
