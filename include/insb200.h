@@ -176,6 +176,23 @@ int insb200_psolver_iterations(const insb200_plan_t *plan);
 /* project!(u, setup; psolver, p) (src/pressure.jl:42-55). p is caller scratch (ghosted scalar). */
 int insb200_project(insb200_plan_t *plan, void *u, void *p, void *stream);
 
+/* The stage of a Runge-Kutta step composed on the host -- user-defined force! functions (src/solver.jl:55-61)
+ * or Dirichlet functions that depend on time, whose planes the host re-evaluates at every stage time:
+ *   copyto!(u, u_start); for j: @. u += coef[j] * k[j]      (step_explicit_runge_kutta.jl:27-32,
+ *                                                            step_lmwray3.jl:41-50: one k, coef = a[i] dt)
+ *   apply_bc_u!(u, t); project!(u, setup; psolver, p); apply_bc_u!(u, t); apply_bc_temp!(temp, t)   (:38-52)
+ * coef[j] = dt * A[i, j] evaluated by the caller in promote(eltype(method), typeof(dt)); coef_dtype says which
+ * type that was (the products and sums are rounded like the reference broadcast, no FMA contraction).
+ * u may alias u_start.  temp / temp_start / ktemp may be NULL (no temperature).  p: ghosted scalar scratch.
+ * insb200_stage_combine is the combine alone on `ncomp` scalar fields (D for a velocity, 1 for a scalar);
+ * insb200_axpy is y += a * x (the statestart update of step_lmwray3.jl:86-90). */
+int insb200_stage_combine(insb200_plan_t *plan, void *dst, const void *base, int nk, const void *const *k,
+                          const double *coef, int coef_dtype, int ncomp, void *stream);
+int insb200_stage_combine_project(insb200_plan_t *plan, void *u, const void *u_start, void *temp,
+                                  const void *temp_start, int nk, const void *const *k, const void *const *ktemp,
+                                  const double *coef, int coef_dtype, void *p, double t_stage, void *stream);
+int insb200_axpy(insb200_plan_t *plan, void *y, double a, const void *x, int coef_dtype, int ncomp, void *stream);
+
 /* timestep!(::ExplicitRungeKuttaMethod, ...) (src/time_steppers/step_explicit_runge_kutta.jl:4-57).
  * A: s*s row-major SHIFTED tableau (methods.jl:80-85), c: s stage times, both as double;
  * coef_dtype = eltype of the method (INSB200_F32/F64): the stage combine is evaluated in

@@ -7,6 +7,7 @@
 #include <mutex>
 
 #include "fused.h"
+#include "stencil_math.cuh"
 #include "internal.h"
 
 namespace insb {
@@ -728,6 +729,71 @@ static int rhs_sciml_t(insb200_plan *pl, T *dudt, const T *u, double t, const in
 // =========================================================================================
 // extern "C"
 // =========================================================================================
+// ---- host-composed stages (insb200.h: insb200_stage_combine / _project / insb200_axpy) ----------------
+namespace {
+template <typename T>
+struct CombineArgs {
+    const T *k[MAXSTAGE];
+    double c[MAXSTAGE];
+    int nk;
+};
+
+template <typename T, typename CT>
+__global__ void __launch_bounds__(256) combine_kernel(T *__restrict__ dst, const T *base, CombineArgs<T> a, long long n) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    T x = base[q];
+    for (int j = 0; j < a.nk; j++) x = axpy_rn<T, CT>(x, a.c[j], a.k[j][q]);
+    dst[q] = x;
+}
+
+template <typename T>
+int combine_t(insb200_plan *pl, T *dst, const T *base, int nk, const void *const *k, const double *coef, int coef_dtype,
+              int ncomp, void *stream) {
+    if (nk < 0 || nk > MAXSTAGE) {
+        set_error("stage combine: 0..8 stage arrays");
+        return 1;
+    }
+    CombineArgs<T> a{};
+    a.nk = nk;
+    for (int j = 0; j < nk; j++) a.k[j] = (const T *)k[j], a.c[j] = coef[j];
+    const long long n = pl->ncell * ncomp;
+    Launch L = L_of(pl, stream);
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    if (pl->f64 || coef_dtype == INSB200_F64)
+        combine_kernel<T, double><<<nb, 256, 0, L.stream>>>(dst, base, a, n);
+    else
+        combine_kernel<T, T><<<nb, 256, 0, L.stream>>>(dst, base, a, n);
+    if (L.counter) ++*L.counter;
+    INSB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+int combine_project_t(insb200_plan *pl, T *u, const T *u0, T *temp, const T *temp0, int nk, const void *const *k,
+                      const void *const *ktemp, const double *coef, int coef_dtype, T *p, double t, void *stream) {
+    if (!pl->ps) {
+        set_error("stage_combine_project: the plan has no pressure solver");
+        return 1;
+    }
+    if (temp && (!temp0 || !ktemp)) {
+        set_error("stage_combine_project: temp needs temp_start and ktemp");
+        return 1;
+    }
+    INSB_TRY(combine_t<T>(pl, u, u0, nk, k, coef, coef_dtype, pl->D, stream));
+    if (temp) INSB_TRY(combine_t<T>(pl, temp, temp0, nk, ktemp, coef, coef_dtype, 1, stream));
+    const Grid<T> &g = grid_of<T>(pl);
+    Launch L = L_of(pl, stream);
+    INSB_TRY(launch_bc_u<T>(g, pl->bc, u, 0, L));
+    INSB_TRY(project_t<T>(pl, u, p, stream));
+    INSB_TRY(launch_bc_u<T>(g, pl->bc, u, 0, L));
+    if (temp) INSB_TRY(launch_bc_temp<T>(g, pl->bc, temp, L));
+    (void)t;  // function-valued planes are refreshed by the host before the call (insb200_set_bc_u_plane)
+    return 0;
+}
+}  // namespace
+
+
 #define API_BEGIN try {
 #define API_END                                        \
     }                                                  \
@@ -1048,6 +1114,32 @@ int insb200_project(insb200_plan_t *pl, void *u, void *p, void *stream) {
     API_BEGIN
     return DISPATCH(project_t<float>(pl, (float *)u, (float *)p, stream),
                     project_t<double>(pl, (double *)u, (double *)p, stream));
+    API_END
+}
+
+int insb200_stage_combine(insb200_plan_t *pl, void *dst, const void *base, int nk, const void *const *k, const double *coef,
+                          int coef_dtype, int ncomp, void *stream) {
+    API_BEGIN
+    return DISPATCH(combine_t<float>(pl, (float *)dst, (const float *)base, nk, k, coef, coef_dtype, ncomp, stream),
+                    combine_t<double>(pl, (double *)dst, (const double *)base, nk, k, coef, coef_dtype, ncomp, stream));
+    API_END
+}
+int insb200_stage_combine_project(insb200_plan_t *pl, void *u, const void *u_start, void *temp, const void *temp_start,
+                                  int nk, const void *const *k, const void *const *ktemp, const double *coef,
+                                  int coef_dtype, void *p, double t_stage, void *stream) {
+    API_BEGIN
+    return DISPATCH(combine_project_t<float>(pl, (float *)u, (const float *)u_start, (float *)temp, (const float *)temp_start,
+                                             nk, k, ktemp, coef, coef_dtype, (float *)p, t_stage, stream),
+                    combine_project_t<double>(pl, (double *)u, (const double *)u_start, (double *)temp,
+                                              (const double *)temp_start, nk, k, ktemp, coef, coef_dtype, (double *)p,
+                                              t_stage, stream));
+    API_END
+}
+int insb200_axpy(insb200_plan_t *pl, void *y, double a, const void *x, int coef_dtype, int ncomp, void *stream) {
+    API_BEGIN
+    const void *k[1] = {x};
+    return DISPATCH(combine_t<float>(pl, (float *)y, (const float *)y, 1, k, &a, coef_dtype, ncomp, stream),
+                    combine_t<double>(pl, (double *)y, (const double *)y, 1, k, &a, coef_dtype, ncomp, stream));
     API_END
 }
 

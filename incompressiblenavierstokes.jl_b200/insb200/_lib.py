@@ -83,6 +83,12 @@ _PROTOTYPES = {
     "insb200_applypressure": (C.c_int, [_P, _P, _P, _P]),
     "insb200_psolve": (C.c_int, [_P, _P, _P]),
     "insb200_project": (C.c_int, [_P, _P, _P, _P]),
+    "insb200_stage_combine": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_double), C.c_int,
+                                        C.c_int, _P]),
+    "insb200_stage_combine_project": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.POINTER(C.c_void_p),
+                                                C.POINTER(C.c_void_p), C.POINTER(C.c_double), C.c_int, _P, C.c_double,
+                                                _P]),
+    "insb200_axpy": (C.c_int, [_P, _P, C.c_double, _P, C.c_int, C.c_int, _P]),
     "insb200_step_rk": (
         C.c_int,
         [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_int, _P, _P, C.c_double,

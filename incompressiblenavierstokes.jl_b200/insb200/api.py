@@ -547,52 +547,74 @@ def _coef_dtype(method_T, dt):
     return _lib.F64 if np.result_type(method_T, dt_T) == np.float64 else _lib.F32
 
 
+def _stage_cache(stepper, nstage):
+    """ode_cache of the host-composed steppers (get_cache, src/time_steppers/*.jl): statestart, the stage
+    arrays k and the pressure scratch p, allocated once per (setup, state keys) and kept on the setup."""
+    setup, state = stepper["setup"], stepper["state"]
+    keys = tuple(k for k in ("u", "temp") if k in state)
+    cache = setup._plans.setdefault("stage_cache", {})
+    c = cache.get(keys)
+    if c is None or len(c["k"]) < nstage:
+        mk = {"u": vectorfield, "temp": scalarfield}
+        c = {"start": {kk: mk[kk](setup) for kk in keys}, "p": scalarfield(setup),
+             "k": [{kk: mk[kk](setup) for kk in keys} for _ in range(nstage)]}
+        cache[keys] = c
+    return keys, c
+
+
 def _timestep_staged(method, force, stepper, dt, params):
     """timestep! composed stage by stage on the host (step_explicit_runge_kutta.jl:4-57,
-    step_lmwray3.jl:3-94) for setups whose Dirichlet functions depend on time: the boundary
-    planes are re-evaluated at every stage time tstart + c[i] Δt before apply_bc_u!.  Kernels are
-    the library's (insb200_rhs, ghost fills, project); the stage combine is a handful of axpys."""
+    step_lmwray3.jl:3-94): user-defined force functions, and setups whose Dirichlet functions depend on
+    time -- their boundary planes are re-evaluated at every stage time tstart + c[i] dt before apply_bc_u!.
+    Every device operation is the library's: the force (insb200_rhs for the built-in ones), the stage
+    combine + ghost fills + projection (insb200_stage_combine_project), the statestart update (insb200_axpy)."""
     setup, psolver, state, t0 = stepper["setup"], stepper["psolver"], stepper["state"], stepper["t"]
-    keys = [k for k in ("u", "temp") if k in state]
-    start = {k: state[k].clone() for k in keys}
-    p = scalarfield(setup)
     T = setup.T
+    wray = isinstance(method, LMWray3)
+    nstage = 1 if wray else len(method.b)
+    keys, cache = _stage_cache(stepper, nstage)
+    start, p, ks = cache["start"], cache["p"], cache["k"]
+    h, st = psolver.plan.h, _stream()
+    planes = _bc_planes(setup)
+    ncomp = {"u": setup.D, "temp": 1}
+    for kk in keys:  # copyto!(statestart, state)
+        check(lib().insb200_stage_combine(h, _ptr(start[kk]), _ptr(_chk(setup, state[kk], kk == "u")), 0, None, None,
+                                          _lib.F64, ncomp[kk], st))
+    temp = state.get("temp")
 
-    def rhs(st, t):
-        k = {kk: torch.zeros_like(st[kk]) for kk in keys}
-        force(k, st, t, setup=setup, **params)
-        return k
+    def combine_project(nk, coefs, t):
+        planes.refresh(t)
+        cf = (C.c_double * max(nk, 1))(*coefs)
+        ku = (C.c_void_p * max(nk, 1))(*[_ptr(ks[j]["u"]) for j in range(nk)])
+        kt = (C.c_void_p * max(nk, 1))(*[_ptr(ks[j]["temp"]) for j in range(nk)]) if temp is not None else None
+        check(lib().insb200_stage_combine_project(
+            h, _ptr(state["u"]), _ptr(start["u"]), _ptr(temp), _ptr(start["temp"]) if temp is not None else None, nk,
+            ku, kt, cf, cdt, _ptr(p), float(t), st))
 
-    def finish(t):
-        apply_bc_u_(state["u"], t, setup, plan=psolver.plan)
-        project_(state["u"], setup, psolver=psolver, p=p)
-        apply_bc_u_(state["u"], t, setup, plan=psolver.plan)
-        if "temp" in state:
-            apply_bc_temp_(state["temp"], t, setup, plan=psolver.plan)
-
-    if isinstance(method, LMWray3):
+    if wray:
+        cdt = _lib.F64 if T is np.float64 else _lib.F32  # axpy! converts the scalar to the field type (:60-62)
         a3, b3, c3 = (T(8 / 15), T(5 / 12), T(3 / 4)), (T(1 / 4), T(0)), (T(8 / 15), T(2 / 3), T(1))
         for i in range(3):
-            k = rhs(state, t0 + (0 if i == 0 else float(c3[i - 1]) * dt))
-            t = t0 + float(c3[i]) * dt
-            for kk in keys:
-                state[kk].copy_(start[kk]).add_(k[kk], alpha=float(T(a3[i] * T(dt))))
-            finish(t)
+            force(ks[0], state, t0 + (0 if i == 0 else float(c3[i - 1]) * dt), setup=setup, **params)
+            combine_project(1, [float(T(a3[i] * T(dt)))], t0 + float(c3[i]) * dt)
             if i != 2:
                 for kk in keys:
-                    start[kk].add_(k[kk], alpha=float(T(b3[i] * T(dt))))
+                    check(lib().insb200_axpy(h, _ptr(start[kk]), float(T(b3[i] * T(dt))), _ptr(ks[0][kk]), cdt,
+                                             ncomp[kk], st))
     else:
+        cdt = _coef_dtype(method.T, dt)
         A, c = np.asarray(method.A), method.c
-        ks = []
+
+        def coef(i, j):  # dt * A[i, j] in the coefficient type (include/insb200.h)
+            if cdt == _lib.F32:
+                return float(np.float32(dt) * np.float32(A[i, j]))
+            return float(dt) * float(A[i, j])
+
         t = t0
-        for i in range(len(method.b)):
-            ks.append(rhs(state, t))
-            for kk in keys:
-                state[kk].copy_(start[kk])
-                for j in range(i + 1):
-                    state[kk].add_(ks[j][kk], alpha=float(dt) * float(A[i, j]))
+        for i in range(nstage):
+            force(ks[i], state, t, setup=setup, **params)
             t = t0 + float(c[i]) * dt
-            finish(t)
+            combine_project(i + 1, [coef(i, j) for j in range(i + 1)], t)
     return create_stepper(method, setup=setup, psolver=psolver, state=state, t=t0 + dt, n=stepper["n"] + 1)
 
 
@@ -601,7 +623,8 @@ def timestep_(method, force, stepper, dt, *, params=None, ode_cache=None, force_
     setup, psolver, state = stepper["setup"], stepper["psolver"], stepper["state"]
     planes = _bc_planes(setup)
     planes.refresh(stepper["t"])  # (also probes undeclared functions for time dependence)
-    if planes.time_dependent:
+    if planes.time_dependent or (force is not navierstokes_ and force is not boussinesq_):
+        # Dirichlet functions of time, or a user-defined force (src/solver.jl:55-61): stage-by-stage composition
         return _timestep_staged(method, force, stepper, dt, dict(params or {}))
     pr = _force_params(force, setup, params)
     u = _chk(setup, state["u"], True)

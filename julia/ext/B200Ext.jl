@@ -102,19 +102,44 @@ check(status) = status == 0 ? nothing : error("libinsb200: " * lasterror())
 bcconst(bc, α) = 0.0
 bcconst(bc::DirichletBC{<:Tuple}, α) = Float64(bc.u[α])
 bcconst(bc::DirichletBC{<:Number}, α) = Float64(bc.u)
+isfuncbc(bc) = bc isa DirichletBC && bc.u isa Function
+hasfuncbc(setup) = any(isfuncbc, Iterators.flatten(setup.boundary_conditions.u))
+
+# Temperature: DirichletBC() (u === nothing) is zero like in the reference (boundary_conditions.jl:237-245);
+# function-valued temperature planes have no entry point yet, so they are refused instead of silently zeroed.
+tempconst(bc) = 0.0
+tempconst(bc::DirichletBC{Nothing}) = 0.0
+tempconst(bc::DirichletBC{<:Number}) = Float64(bc.u)
+tempconst(bc::DirichletBC{<:Function}) =
+    error("libinsb200: function-valued DirichletBC for the temperature is not supported by the B200 backend")
 
 "Handle owning an `insb200_plan_t*` plus the host arrays the plan was created from."
 mutable struct B200PSolver{S} <: Function
     plan::Ptr{Cvoid}
     setup::S
     kind::Symbol
-    function B200PSolver(plan, setup::S, kind) where {S}
-        ps = new{S}(plan, setup, kind)
+    bcplanes::Dict{NTuple{3,Int},Any}       # device planes of function-valued DirichletBC (owned here: the
+    bchost::Dict{NTuple{3,Int},Any}         # finalizer releases them with the plan), their host copies,
+    bcstate::Tuple{Float64,Bool}            # the (t, dudt) they were evaluated at
+    bc_time_dependent::Bool                 # functions depend on t: timestep! composes the step stage by stage
+    cache::Dict{Symbol,Any}                 # statestart / k / p of the stage-by-stage composition
+    function B200PSolver(plan, setup::S, kind; bc_time_dependent) where {S}
+        ps = new{S}(plan, setup, kind, Dict{NTuple{3,Int},Any}(), Dict{NTuple{3,Int},Any}(), (NaN, false),
+            bc_time_dependent, Dict{Symbol,Any}())
         finalizer(ps) do x
             x.plan == C_NULL || ccall((:insb200_plan_destroy, libinsb200), Cint, (Ptr{Cvoid},), x.plan)
             x.plan = C_NULL
         end
     end
+end
+
+# The stock drivers call `propose_timestep(force!, state, setup, params)` without the psolver
+# (src/solver.jl:111): the plan is found through the setup it was made for.  Weak keys: a setup that is
+# garbage collected drops its entry, and the psolver is only referenced weakly through its own finalizer.
+const PLAN_OF_SETUP = WeakKeyDict{Any,WeakRef}()
+function psolver_of(setup)
+    w = get(PLAN_OF_SETUP, setup, nothing)
+    isnothing(w) ? nothing : w.value
 end
 
 const KINDS = (; spectral = Cint(0), transform = Cint(1), tridiagonal = Cint(2), default = Cint(3), cg = Cint(4))
@@ -126,7 +151,7 @@ B200 replacement of `psolver_spectral` / `psolver_transform` / `psolver_tridiago
 `default_psolver` (`src/pressure.jl:58-78, 215-545`).
 """
 function INS.psolver_b200(setup; kind = :default, dir = nothing, rank = 0, world = 1, nccl_id = C_NULL,
-        abstol = 0.0, reltol = 0.0, maxiter = 0)
+        abstol = 0.0, reltol = 0.0, maxiter = 0, bc_time_dependent = nothing)
     (; Δ, Δu, A_stag, N, xlims, boundary_conditions) = setup
     D = length(N)
     T = eltype(Δ[1])
@@ -157,7 +182,7 @@ function INS.psolver_b200(setup; kind = :default, dir = nothing, rank = 0, world
                 α = (i - 1) % 3 + 1
                 d <= D && α <= D ? bcconst(bcu[d][s], α) : 0.0
             end,
-            flat6((d, s) -> hastemp && bct[d][s] isa DirichletBC ? Float64(bct[d][s].u) : 0.0),
+            flat6((d, s) -> hastemp ? tempconst(bct[d][s]) : 0.0),
             KINDS[kind],
             isnothing(dir) ? Cint(-1) : Cint(dir - 1),
             (C_NULL, C_NULL, C_NULL),
@@ -174,7 +199,13 @@ function INS.psolver_b200(setup; kind = :default, dir = nothing, rank = 0, world
     end
     resolved = ccall((:insb200_plan_psolver, libinsb200), Cint, (Ptr{Cvoid},), out[])
     resolved == -1 && error("no Poisson solver on the B200 path for this setup")
-    B200PSolver(out[], setup, (:spectral, :transform, :tridiagonal, :default, :cg)[resolved+1])
+    # function-valued DirichletBC: time dependent unless the caller says otherwise (a closure cannot be
+    # inspected); `bc_time_dependent = false` keeps the fused one-call steppers and the CUDA-graph replay
+    td = isnothing(bc_time_dependent) ? hasfuncbc(setup) : bc_time_dependent
+    ps = B200PSolver(out[], setup, (:spectral, :transform, :tridiagonal, :default, :cg)[resolved+1]; bc_time_dependent = td)
+    PLAN_OF_SETUP[setup] = WeakRef(ps)
+    hasfuncbc(setup) && refresh_bc!(ps, 0)      # the planes must exist before the first ghost fill
+    ps
 end
 
 stream() = Ptr{Cvoid}(CUDA.stream().handle)
@@ -216,14 +247,16 @@ const BuiltinForce = Union{typeof(navierstokes!),typeof(boussinesq!)}
 # planes the plan keeps pointers to.  `dudt = true` uses the same centred difference (:348-354).
 # A time-independent function is evaluated once; a time-dependent one must be refreshed at every
 # stage time, so `timestep!` then uses the per-stage composition (INTEGRATION.md §3).
-const BCPLANES = IdDict{Any,Dict{NTuple{3,Int},Any}}()
-
 function refresh_bc!(ps::B200PSolver, t; dudt = false)
     setup = ps.setup
+    hasfuncbc(setup) || return nothing
+    want = ((ps.bc_time_dependent || dudt) ? Float64(t) : 0.0, dudt)
+    ps.bcstate == want && return nothing
+    t = want[1]
     (; boundary_conditions, xu, Iu, N) = setup
     D = length(N)
     T = eltype(setup.Δ[1])
-    planes = get!(() -> Dict{NTuple{3,Int},Any}(), BCPLANES, ps)
+    planes = ps.bcplanes
     for β = 1:D, (side, isright) in ((1, false), (2, true))
         bc = boundary_conditions.u[β][side]
         (bc isa DirichletBC && bc.u isa Function) || continue
@@ -239,6 +272,7 @@ function refresh_bc!(ps::B200PSolver, t; dudt = false)
             end
             host = T.(dropdims(collect(vals); dims = β))      # (other dims), first one fastest
             key = (β, side, α)
+            ps.bchost[key] = host
             if haskey(planes, key)
                 copyto!(planes[key], host)
             else
@@ -248,13 +282,121 @@ function refresh_bc!(ps::B200PSolver, t; dudt = false)
             end
         end
     end
+    ps.bcstate = want
     nothing
 end
+
+# ghost fills through the library (the planes are refreshed first): apply_bc_u!(u, t, setup; dudt)
+function b200_apply_bc_u!(ps::B200PSolver, u::CuArray, t; dudt = false)
+    refresh_bc!(ps, t; dudt)
+    check(ccall((:insb200_apply_bc_u, libinsb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cint, Ptr{Cvoid}),
+        ps.plan, devptr(u), Float64(t), Cint(dudt), stream()))
+    u
+end
+
+# ---- stage-by-stage composition (user-defined force!, time-dependent Dirichlet functions) ----------
+# Mirrors step_explicit_runge_kutta.jl:18-54 / step_lmwray3.jl:41-90 with one library call per stage for
+# copyto! + the axpys + apply_bc_u! + project! + apply_bc_u! (+ apply_bc_temp!): insb200_stage_combine_project.
+# The force is the caller's: a built-in one goes to insb200_rhs, anything else runs as Julia code on CuArrays.
+function stage_cache(ps::B200PSolver, state, nstage)
+    c = ps.cache
+    if !haskey(c, :k) || length(c[:k]) < nstage || keys(c[:start]) != keys(state)
+        c[:start] = map(similar, state)
+        c[:k] = [map(similar, state) for _ = 1:nstage]
+        c[:p] = similar(state.u, size(state.u)[1:end-1])
+    end
+    c[:start], c[:k], c[:p]
+end
+
+function b200_force!(force!, k, state, t, ps::B200PSolver, params, force_cache)
+    if force! isa BuiltinForce
+        cpar = Ref(cparams(force!, params))
+        temp = haskey(state, :temp) ? state.temp : nothing
+        ktemp = haskey(k, :temp) ? k.temp : nothing
+        check(ccall((:insb200_rhs, libinsb200), Cint,
+            (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{CParams}, Ptr{Cvoid}),
+            ps.plan, devptr(state.u), devptr(temp), devptr(k.u), devptr(ktemp), cpar, stream()))
+    else
+        force!(k, state, t; setup = ps.setup, cache = force_cache, params...)
+    end
+    k
+end
+
+function combine_project!(ps::B200PSolver, state, start, ks, nk, coefs::Vector{Float64}, coefT, p, t)
+    refresh_bc!(ps, t)
+    ku = Ptr{Cvoid}[devptr(ks[j].u) for j = 1:nk]
+    hastemp = haskey(state, :temp)
+    kt = hastemp ? Ptr{Cvoid}[devptr(ks[j].temp) for j = 1:nk] : Ptr{Cvoid}[]
+    GC.@preserve ku kt coefs begin
+        check(ccall((:insb200_stage_combine_project, libinsb200), Cint,
+            (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}},
+             Ptr{Cdouble}, Cint, Ptr{Cvoid}, Cdouble, Ptr{Cvoid}),
+            ps.plan, devptr(state.u), devptr(start.u), hastemp ? devptr(state.temp) : C_NULL,
+            hastemp ? devptr(start.temp) : C_NULL, nk, ku, hastemp ? pointer(kt) : Ptr{Ptr{Cvoid}}(C_NULL), coefs, coefT,
+            devptr(p), Float64(t), stream()))
+    end
+    state
+end
+
+function timestep_staged!(method::ExplicitRungeKuttaMethod{T}, force!, stepper, Δt; params, force_cache) where {T}
+    (; setup, psolver, state, t, n) = stepper
+    (; A, b, c) = method
+    nstage = length(b)
+    start, ks, p = stage_cache(psolver, state, nstage)
+    map(copyto!, start, state)
+    CT = promote_type(T, typeof(Δt))
+    coefT = CT == Float64 ? Cint(1) : Cint(0)
+    tstart = t
+    for i = 1:nstage
+        b200_force!(force!, ks[i], state, t, psolver, params, force_cache)
+        t = tstart + c[i] * Δt
+        combine_project!(psolver, state, start, ks, i, Float64[Float64(CT(Δt) * CT(A[i, j])) for j = 1:i], coefT, p, t)
+    end
+    create_stepper(method; setup, psolver, state, t, n = n + 1)
+end
+
+function timestep_staged!(method::LMWray3, force!, stepper, Δt; params, force_cache)
+    (; setup, psolver, state, t, n) = stepper
+    T = eltype(state.u)
+    start, ks, p = stage_cache(psolver, state, 1)
+    map(copyto!, start, state)
+    a = T(8 / 15), T(5 / 12), T(3 / 4)
+    b = T(1 / 4), T(0)
+    c = T(8 / 15), T(2 / 3), T(1)
+    coefT = T == Float64 ? Cint(1) : Cint(0)
+    tstart = t
+    for i = 1:3
+        b200_force!(force!, ks[1], state, t, psolver, params, force_cache)
+        t = tstart + c[i] * Δt
+        combine_project!(psolver, state, start, ks, 1, Float64[Float64(T(a[i] * T(Δt)))], coefT, p, t)
+        if i != 3
+            for key in keys(state)
+                ncomp = key == :u ? length(setup.N) : 1
+                check(ccall((:insb200_axpy, libinsb200), Cint,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}),
+                    psolver.plan, devptr(start[key]), Float64(T(b[i] * T(Δt))), devptr(ks[1][key]), coefT, Cint(ncomp),
+                    stream()))
+            end
+        end
+    end
+    create_stepper(method; setup, psolver, state, t = tstart + Δt, n = n + 1)
+end
+
+# Any force! that is not one of the built-in ones: stage-by-stage composition (no CPU path, less fusion).
+# (one method per stepper type: a Union in the first argument would be ambiguous with the reference's own methods)
+INS.timestep!(method::ExplicitRungeKuttaMethod, force!, stepper::B200Stepper, Δt;
+        params = nothing, ode_cache = nothing, force_cache = nothing) =
+    timestep_staged!(method, force!, stepper, Δt; params, force_cache)
+INS.timestep!(method::LMWray3, force!, stepper::B200Stepper, Δt;
+        params = nothing, ode_cache = nothing, force_cache = nothing) =
+    timestep_staged!(method, force!, stepper, Δt; params, force_cache)
 
 # timestep!(::ExplicitRungeKuttaMethod, ...)   (src/time_steppers/step_explicit_runge_kutta.jl:4-57)
 function INS.timestep!(method::ExplicitRungeKuttaMethod{T}, force!::BuiltinForce, stepper::B200Stepper, Δt;
         params = nothing, ode_cache = nothing, force_cache = nothing) where {T}
     (; setup, psolver, state, t, n) = stepper
+    psolver.bc_time_dependent && return timestep_staged!(method, force!, stepper, Δt; params, force_cache)
+    refresh_bc!(psolver, t)
     (; A, b, c) = method
     s = length(b)
     Arow = Float64.(permutedims(A))[:]      # row-major s*s (already the shifted tableau, methods.jl:80-85)
@@ -271,6 +413,8 @@ end
 function INS.timestep!(method::LMWray3, force!::BuiltinForce, stepper::B200Stepper, Δt;
         params = nothing, ode_cache = nothing, force_cache = nothing)
     (; setup, psolver, state, t, n) = stepper
+    psolver.bc_time_dependent && return timestep_staged!(method, force!, stepper, Δt; params, force_cache)
+    refresh_bc!(psolver, t)
     cpar = Ref(cparams(force!, params))
     temp = haskey(state, :temp) ? state.temp : nothing
     check(ccall((:insb200_step_lmwray3, libinsb200), Cint,
@@ -289,6 +433,14 @@ function INS.propose_timestep(force!::BuiltinForce, state, setup, params, psolve
     eltype(state.u)(out[])
 end
 
+# The 4-argument form is what the stock solve_unsteady calls (src/solver.jl:111).  It is specialised on CuArray
+# states only; the plan comes from the setup's registered psolver, and without one the generic method runs.
+function INS.propose_timestep(force!::BuiltinForce, state::NamedTuple{K,<:Tuple{CuArray,Vararg}}, setup, params) where {K}
+    ps = psolver_of(setup)
+    isnothing(ps) && return invoke(INS.propose_timestep, Tuple{Any,Any,Any,Any}, force!, state, setup, params)
+    INS.propose_timestep(force!, state, setup, params, ps)
+end
+
 # solve_unsteady(; ...)   (src/solver.jl:77-149): with a B200 psolver and a built-in force the
 # whole time loop runs inside the library (insb200_solve_unsteady): CFL adaptation, clipping to
 # tend, the bad-Δt stop, a CUDA-graph replay of the step for fixed Δt; the processors are
@@ -304,6 +456,13 @@ function INS.solve_unsteady_b200(; setup, tlims, start, force!::BuiltinForce = n
         cfl = eltype(start.u)(0.9), n_adapt_Δt = 1, processors = (;), nupdate = 1, params, use_graph = true)
     tstart, tend = tlims
     T = eltype(start.u)
+    if psolver.bc_time_dependent
+        # planes change at every stage time: the library loop (and its CUDA graph) would freeze them.  The stock
+        # driver runs instead; its timestep! / propose_timestep calls dispatch to this extension.
+        return INS.solve_unsteady(; setup, tlims, start, force!, docopy, method, psolver, Δt, Δt_min, cfl, n_adapt_Δt,
+            processors, params)
+    end
+    refresh_bc!(psolver, tstart)
     state = docopy ? deepcopy(start) : start
     stepper = Ref{Any}(create_stepper(method; setup, psolver, state, t = tstart))
     obs = INS.Observable(INS.get_state(stepper[]))
@@ -342,10 +501,12 @@ end
 # right_hand_side!(dudt, u, params_ref, t)   (src/sciml.jl:35-48)
 function INS.right_hand_side!(dudt::CuArray, u::CuArray, params_ref::Base.RefValue{<:Tuple{Any,<:B200PSolver,Any}}, t)
     setup, psolver, viscosity = params_ref[]
+    refresh_bc!(psolver, t; dudt = true)      # apply_bc_u!(dudt, t, setup; dudt = true), sciml.jl:44
     cpar = Ref(CParams(viscosity, 0.0, 0.0, Cint(0), Cint(0), Cint(0), (0.0, 0.0, 0.0), Cint(0), 0.0))
     check(ccall((:insb200_right_hand_side, libinsb200), Cint,
         (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Ref{CParams}, Ptr{Cvoid}),
         psolver.plan, devptr(dudt), devptr(u), t, cpar, stream()))
+    refresh_bc!(psolver, t)                   # back to the values for the next ghost fill of u
     nothing
 end
 

@@ -252,3 +252,71 @@ def test_native_loop_graph_replay_with_large_shared_memory_kernels():
     b, _ = I.solve_unsteady(native=True, graph=True, **kw)
     ua = I.to_host(a["u"])
     assert np.all(np.isfinite(ua)) and np.array_equal(ua, I.to_host(b["u"]))
+
+
+@pytest.mark.parametrize("T", [np.float64, np.float32])
+@pytest.mark.parametrize("bcs", [("P", "P", "P"), ("P", "D", "P")])
+def test_user_defined_force_composed_stage_by_stage(T, bcs):
+    """A force the library does not know (src/solver.jl:55-61: any `force!` with the built-in signature) makes
+    timestep_ compose the step on the host: force -> insb200_stage_combine_project per stage, the statestart
+    update of LMWray3 through insb200_axpy.  With the built-in right-hand side wrapped in a user function the
+    result must equal the fused one-call steppers (general tableaus, diagonal tableaus, low-storage Wray3) and,
+    through them, the oracle; the stage arrays are allocated once and no torch kernel runs inside a step."""
+    import torch
+
+    I = ins()
+    so, sg = make_setups((uniform(40), uniform(24), uniform(16)), bcs, T=T)
+    ps = I.psolver_spectral(sg) if bcs[1] == "P" else I.psolver_tridiagonal(sg)
+    u0 = smooth_vec(so, 17)
+    calls = []
+
+    def my_force(force, state, t, *, setup, cache=None, **params):
+        calls.append(float(t))
+        return I.navierstokes_(force, state, t, setup=setup, **params)
+
+    dt = T(2e-3)
+    tol = 1e-13 if T is np.float64 else 2e-6
+    for mname in ("RK44", "RK33C2", "Wray3", "FE11", "LMWray3"):
+        m = I.LMWray3(T) if mname == "LMWray3" else getattr(I.RKMethods, mname)(T)
+        res = {}
+        for tag, f in (("fused", I.navierstokes_), ("staged", my_force)):
+            sp = I.create_stepper(m, setup=sg, psolver=ps, state={"u": I.to_device(sg, u0)}, t=0.0)
+            I.apply_bc_u_(sp["state"]["u"], 0.0, sg)
+            for _ in range(2):
+                sp = I.timestep_(m, f, sp, dt, params=dict(viscosity=1e-2))
+            res[tag] = I.to_host(sp["state"]["u"])
+            assert abs(sp["t"] - 2 * float(dt)) < 1e-12
+        assert rel_l2(res["staged"], res["fused"]) <= tol, mname
+    assert len(calls) == 2 * (4 + 3 + 3 + 1 + 3)
+    # the oracle, once, through the staged path (RK44, one step)
+    m = I.RKMethods.RK44(T)
+    sp = I.create_stepper(m, setup=sg, psolver=ps, state={"u": I.to_device(sg, u0)}, t=0.0)
+    I.apply_bc_u_(sp["state"]["u"], 0.0, sg)
+    sp = I.timestep_(m, my_force, sp, dt, params=dict(viscosity=1e-2))
+    import oracle.timestep as ots
+    from oracle import bc as obc2
+
+    uo = obc2.apply_bc_u(u0.copy(order="F"), 0.0, so)
+    pso = opr.psolver_spectral(so) if bcs[1] == "P" else opr.psolver_tridiagonal(so)
+    m_o, st_o = ots.RK44(T), {"u": uo}
+    sp_o = ots.timestep_(m_o, ots.make_navierstokes(so, 1e-2), ots.create_stepper(m_o, so, pso, st_o, 0.0), dt,
+                         ots.get_cache(m_o, st_o, so))
+    want = sp_o["state"]["u"]
+    assert rel_l2(I.to_host(sp["state"]["u"]), want) <= (1e-12 if T is np.float64 else 1e-5)
+    # no torch kernels inside a staged step: only the library's launches (and no allocation: same cache arrays)
+    cache = sg._plans["stage_cache"][("u",)]
+    ptrs = [k["u"].data_ptr() for k in cache["k"]]
+    try:
+        from torch.profiler import ProfilerActivity, profile
+
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            sp = I.timestep_(m, my_force, sp, dt, params=dict(viscosity=1e-2))
+            torch.cuda.synchronize()
+        names = [e.key for e in prof.key_averages() if getattr(e, "device_type", None) is not None]
+        kernels = [n for n in names if "insb" in n]
+        foreign = [n for n in names if ("at::" in n or "elementwise" in n or "vectorized" in n)]
+        if kernels:  # (CUPTI available)
+            assert not foreign, foreign
+    except (ImportError, RuntimeError):
+        pass
+    assert [k["u"].data_ptr() for k in sg._plans["stage_cache"][("u",)]["k"]] == ptrs

@@ -60,7 +60,51 @@ __global__ void stream_copy(const float4 *__restrict__ src, float4 *__restrict__
     for (; i < n4; i += step) dst[i] = src[i];
 }
 
-
+// bulk (TMA) variant: a CTA stages CH-byte chunks in shared memory with cp.async.bulk (local load, mbarrier)
+// and stores them with cp.async.bulk.global.shared::cta in runs of RUN bytes (dst may be a peer); two buffers.
+__device__ __forceinline__ unsigned s32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+template <int CH>
+__global__ void __launch_bounds__(32) bulk_copy(const char *__restrict__ src, char *__restrict__ dst, long long nchunk, int run) {
+    extern __shared__ __align__(128) unsigned char sm[];
+    __shared__ unsigned long long bar[2];
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < 2; b++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(bar + b)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (threadIdx.x != 0) return;
+    long long c = blockIdx.x;
+    int it = 0;
+    auto load = [&](long long cc, int b) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar + b)), "r"(CH) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(sm + b * CH)),
+                     "l"(src + cc * CH), "r"(CH), "r"(s32(bar + b))
+                     : "memory");
+    };
+    if (c < nchunk) load(c, 0);
+    for (; c < nchunk; c += gridDim.x, it++) {
+        const int b = it & 1;
+        const long long nx = c + gridDim.x;
+        if (nx < nchunk) {
+            // buffer b^1 was stored from in iteration it - 1: wait until that store has read it
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            load(nx, b ^ 1);
+        }
+        unsigned ok = 0;
+        const unsigned par = (it >> 1) & 1;
+        while (!ok)
+            asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(ok)
+                         : "r"(s32(bar + b)), "r"(par)
+                         : "memory");
+        for (int o = 0; o < CH; o += run)
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + c * CH + o), "r"(s32(sm + b * CH + o)),
+                         "r"(run)
+                         : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
 
 #include <functional>
 static float time_ms(cudaStream_t st, int reps, const std::function<void()> &f) {
@@ -150,6 +194,22 @@ int main() {
         ms = time_ms(st, reps, [&] { CK(cudaMemcpyAsync(b0, a0, bytes, cudaMemcpyDeviceToDevice, st)); });
         printf("cudaMemcpyAsync local -> local (512 MB): %8.1f GB/s (read + write %8.1f)\n", bytes / ms * 1e-6,
                2 * bytes / ms * 1e-6);
+    }
+    // --- bulk (TMA) copies: 16 KB chunks staged in shared memory, stored in runs of 256 B .. 16 KB
+    {
+        constexpr int CH = 16384;
+        CK(cudaFuncSetAttribute(bulk_copy<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CH));
+        for (int ctas : {148, 296, 592, 888})
+            for (int run : {256, 1024, 4096, 16384}) {
+                float ms = time_ms(st, reps, [&] {
+                    bulk_copy<CH><<<ctas, 32, 2 * CH, st>>>((const char *)a0, (char *)a1, (long long)(bytes / CH), run);
+                });
+                float ms2 = time_ms(st, reps, [&] {
+                    bulk_copy<CH><<<ctas, 32, 2 * CH, st>>>((const char *)a0, (char *)b0, (long long)(bytes / CH), run);
+                });
+                printf("bulk copy %4d CTAs, runs of %5d B: store to peer %8.1f GB/s, local %8.1f GB/s\n", ctas, run,
+                       bytes / ms * 1e-6, bytes / ms2 * 1e-6);
+            }
     }
     // --- bidirectional: both GPUs store to each other at the same time (segment 64 / 256 and stream)
     {
