@@ -90,6 +90,11 @@ struct Ops<float> {
     static __device__ __forceinline__ C scale(C a, float s) { return c(__fmul2_rn(f(a), make_float2(s, s))); }
 };
 
+// factor / den of the eigenvalue division: Float32 takes the fast reciprocal (two instructions, <= 2 ulp, no
+// slow-path call per element); Float64 keeps the correctly rounded quotient
+__device__ __forceinline__ float fast_div(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ double fast_div(double a, double b) { return a / b; }
+
 // radix-R butterfly on v[b + B*r], r = 0..R-1, natural-order output
 template <typename T, int R, int B, bool INV>
 __device__ __forceinline__ void butterfly(Cx<T> (&v)[8], int b) {
@@ -162,10 +167,15 @@ __device__ __forceinline__ void fft_stages(Cx<T> (&v)[8], int t, const LineSmem<
                 v[b + 2 * B] = O::mul(v[b + 2 * B], w2);
                 v[b + 3 * B] = O::mul(v[b + 3 * B], w3);
             } else {
-                Cx<T> w1 = tw[k * TSTEP], w2 = tw[2 * k * TSTEP], w4 = tw[4 * k * TSTEP];
-                if (INV) w1 = cconj(w1), w2 = cconj(w2), w4 = cconj(w4);
-                Cx<T> w3 = O::mul(w1, w2), w5 = O::mul(w1, w4), w6 = O::mul(w2, w4);
-                Cx<T> w7 = O::mul(w3, w4);
+                // all seven powers straight from the table (r k TSTEP < N): four more L1 hits instead of four complex
+                // products, and every twiddle is the correctly rounded table entry
+                const Cx<T> *twk = tw + k * TSTEP;
+                Cx<T> w1 = twk[0], w2 = twk[k * TSTEP], w3 = twk[2 * k * TSTEP], w4 = twk[3 * k * TSTEP];
+                Cx<T> w5 = twk[4 * k * TSTEP], w6 = twk[5 * k * TSTEP], w7 = twk[6 * k * TSTEP];
+                if (INV) {
+                    w1 = cconj(w1), w2 = cconj(w2), w3 = cconj(w3), w4 = cconj(w4);
+                    w5 = cconj(w5), w6 = cconj(w6), w7 = cconj(w7);
+                }
                 v[1] = O::mul(v[1], w1);
                 v[2] = O::mul(v[2], w2);
                 v[3] = O::mul(v[3], w3);
@@ -278,32 +288,23 @@ __global__ void __launch_bounds__(StridedShape<T, N>::NT, (sizeof(T) == 4 && Str
 #pragma unroll
         for (int m = 0; m < 8; m++) v[m] = ip[m * step];
     }
-    T f[8];
-    if (MODE >= 2) {
-        // phat = -phat / ((ax + ay) + az), phat[1] = 0 (pressure.jl:360-372); `factor` carries
-        // the sign and the 1/prod(Np) of the inverse transform.  Evaluated while the loads
-        // above are in flight.
-#pragma unroll
-        for (int m = 0; m < 8; m++) {
-            int k = t + P * m;
-            T den;
-            bool zero;
-            if (g.D == 3) {
-                int k1 = tdim == 1 ? k : other + g.eig_off, k2 = tdim == 1 ? other + g.eig_off : k;
-                den = (e0[kx] + e1[k1]) + e2[k2];
-                zero = (kx | k1 | k2) == 0;
-            } else {
-                den = e0[kx] + e1[k];
-                zero = (kx | k) == 0;
-            }
-            f[m] = zero ? T(0) : factor / den;
-        }
-    }
     int exch = 0;
     if (MODE == 0 || MODE >= 2) fft_stages<T, N, false, 0, L>(v, t, sm, tw, exch);
     if (MODE >= 2) {
+        // phat = -phat / ((ax + ay) + az), phat[1] = 0 (pressure.jl:360-372); `factor` carries
+        // the sign and the 1/prod(Np) of the inverse transform.
+        const T e01 = g.D == 3 ? e0[kx] + (tdim == 1 ? T(0) : e1[other + g.eig_off]) : e0[kx];
+        const T eo2 = g.D == 3 && tdim == 1 ? e2[other + g.eig_off] : T(0);
+        const T *el = (g.D == 3 && tdim == 2) ? e2 : e1;
+        const bool zero_rest = g.D == 3 ? (kx | (other + g.eig_off)) == 0 : kx == 0;
 #pragma unroll
-        for (int m = 0; m < 8; m++) v[m] = Ops<T>::scale(v[m], f[m]);
+        for (int m = 0; m < 8; m++) {
+            const int k = t + P * m;
+            // (ax + ay) + az in the reference's order: the line runs along y (tdim == 1) or z
+            const T den = (g.D == 3 && tdim == 1) ? (e01 + el[k]) + eo2 : e01 + el[k];
+            const T f = (zero_rest && k == 0) ? T(0) : fast_div(factor, den);
+            v[m] = Ops<T>::scale(v[m], f);
+        }
     }
     if (MODE >= 1) fft_stages<T, N, true, 0, L>(v, t, sm, tw, exch);
     if (BLK) {
