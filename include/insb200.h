@@ -133,6 +133,10 @@ int insb200_comm_unique_id(void *id128);
  * ranks synchronise through flags in peer memory. */
 int insb200_plan_ipc_export(insb200_plan_t *plan, void *blob192);
 int insb200_plan_ipc_import(insb200_plan_t *plan, const void *blobs);
+/* Collective tear-down of decomposed plans: every rank first unmaps its peers' buffers (insb200_plan_ipc_close),
+ * all ranks synchronise (a barrier of the caller's launcher), and only then the plans are destroyed -- memory that
+ * another process still has mapped must not be freed (CUDA IPC).  After the call the plan keeps working over NCCL. */
+int insb200_plan_ipc_close(insb200_plan_t *plan);
 /* Extents (including ghosts) of the arrays this rank passes in: N of the setup, with the slab
  * extent in z when world > 1. */
 int insb200_plan_local_n(const insb200_plan_t *plan, int N_local[3]);
@@ -245,6 +249,17 @@ int insb200_kinetic_energy(insb200_plan_t *plan, void *ke, const void *u, int in
  * decomposed plan).  Synchronises the stream and returns the host scalar. */
 int insb200_total_kinetic_energy(insb200_plan_t *plan, const void *u, int interpolate_first,
                                  double *out, void *stream);
+
+/* random_field(setup, t; profile, totalenergy, rng) (src/initializers.jl:109-183) on the device, with the FFT
+ * passes of the plan's psolver_spectral: white noise per component -> projection onto the divergence-free space of
+ * the staggered grid (:133-151) -> shell-wise rescaling to the target spectrum (:153-172, shells of
+ * src/spectral.jl:39-67) -> view(u, Ip, a), then apply_bc_u!.  shell_energy[kappa] (host, kdiag + 1 entries,
+ * kdiag = isqrt(sum (Np/2)^2)) = totalenergy * profile(kappa) / sum(profile): the caller evaluates the profile
+ * function, which cannot cross the ABI.  fill_noise == 0: the interior of u holds the caller's N(0, 1) samples
+ * (the reference draws them with its own rng); != 0: they are generated here (Philox4x32-10 keyed with `seed`,
+ * Box-Muller), so that fields too large for the host never exist there. */
+int insb200_random_field(insb200_plan_t *plan, void *u, const double *shell_energy, int nshell, int fill_noise,
+                         unsigned long long seed, double t, void *stream);
 
 /* energyspectrum(u, setup) (src/spectral.jl:75-117) on a plan holding psolver_spectral (periodic,
  * power-of-two extents, single GPU): the solver's FFT passes transform every component, the modes

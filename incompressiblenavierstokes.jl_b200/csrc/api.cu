@@ -848,8 +848,11 @@ int insb200_plan_create(const insb200_setup_t *setup, insb200_plan_t **out) {
         }
     }
     if (s.world > 1) {
-        if (s.D != 3 || s.bc_u[2][0] != INSB200_BC_PERIODIC) {
-            set_error("world > 1: the slab decomposition needs a 3-D grid that is periodic in z");
+        // z periodic, or closed by walls / symmetry planes (the physical boundary planes then live on the first
+        // and the last rank, bc.cu); a pressure boundary shifts the DOF ranges and is not decomposed
+        if (s.D != 3 || s.bc_u[2][0] == INSB200_BC_PRESSURE || s.bc_u[2][1] == INSB200_BC_PRESSURE ||
+            (s.bc_u[2][0] == INSB200_BC_PERIODIC) != (s.bc_u[2][1] == INSB200_BC_PERIODIC)) {
+            set_error("world > 1: the slab decomposition needs a 3-D grid that is periodic, wall-bounded or symmetric in z");
             return 1;
         }
         if ((s.N[2] - 2) % s.world) {
@@ -901,7 +904,11 @@ int insb200_plan_create(const insb200_setup_t *setup, insb200_plan_t **out) {
     std::memcpy(pl->Iu_loc, pl->Iu, sizeof(pl->Iu));
     if (pl->comm) {
         pl->ncell = (long long)s.N[0] * s.N[1] * (pl->nzl + 2);
-        for (int c = 0; c < 3; c++) pl->Iu_loc[c][2][0] = 1, pl->Iu_loc[c][2][1] = pl->nzl + 1;
+        const int zoff = s.rank * pl->nzl;  // local plane = global plane - zoff
+        for (int c = 0; c < 3; c++) {
+            pl->Iu_loc[c][2][0] = std::max(1, pl->Iu[c][2][0] - zoff);
+            pl->Iu_loc[c][2][1] = std::min(pl->nzl + 1, pl->Iu[c][2][1] - zoff);
+        }
     }
     int r = pl->f64 ? build_grid<double>(pl, pl->gd) : build_grid<float>(pl, pl->gf);
     if (r) {
@@ -951,7 +958,7 @@ int insb200_plan_destroy(insb200_plan_t *pl) {
     if (pl->ps) poisson_destroy(pl->ps);
     for (void *p : {pl->V[0], pl->V[1], pl->ACC, pl->P, pl->TV[0], pl->TV[1], pl->TACC, pl->dev_tables,
                     (void *)pl->scratch, (void *)pl->ke_partial, pl->LES_G, pl->LES_visc, pl->HU, pl->HT, pl->HU2, pl->HT2,
-                    pl->FV[0], pl->FV[1], pl->FACC, pl->FP, pl->FD})
+                    pl->FV[0], pl->FV[1], pl->FACC, pl->FP, pl->FD, pl->FUB})
         if (p) cudaFree(p);
     if (pl->fctx.maps) fused_maps_destroy(pl->fctx.maps);
     if (pl->s_in) cudaStreamDestroy(pl->s_in);
@@ -1001,6 +1008,13 @@ int insb200_plan_ipc_import(insb200_plan_t *pl, const void *blobs) {
         return 1;
     }
     return poisson_ipc_import(pl->ps, blobs);
+    API_END
+}
+
+int insb200_plan_ipc_close(insb200_plan_t *pl) {
+    API_BEGIN
+    if (pl && pl->ps) poisson_ipc_close(pl->ps);
+    return 0;
     API_END
 }
 
@@ -1492,6 +1506,20 @@ int insb200_total_kinetic_energy(insb200_plan_t *pl, const void *u, int interpol
     INSB_CUDA(cudaMemcpyAsync(out, pl->scratch, sizeof(double), cudaMemcpyDeviceToHost, L.stream));
     INSB_CUDA(cudaStreamSynchronize(L.stream));
     return 0;
+    API_END
+}
+
+int insb200_random_field(insb200_plan_t *pl, void *u, const double *shell_energy, int nshell, int fill_noise,
+                         unsigned long long seed, double t, void *stream) {
+    API_BEGIN
+    if (!pl->ps) {
+        set_error("random_field needs a plan with psolver_spectral");
+        return 1;
+    }
+    Launch L = L_of(pl, stream);
+    INSB_TRY(poisson_random_field(pl->ps, u, pl->ncell, shell_energy, nshell, fill_noise, seed, pl->s.xlims, L));
+    (void)t;
+    return DISPATCH(launch_bc_u<float>(pl->gf, pl->bc, (float *)u, 0, L), launch_bc_u<double>(pl->gd, pl->bc, (double *)u, 0, L));
     API_END
 }
 

@@ -82,16 +82,33 @@ static int offset_p(int bc, bool isright) {
 template <typename T>
 static int halo_dim(const Grid<T> &g, const BcDesc &b, T *f, int ncomp, Launch L) {
     if (L.counter) *L.counter += comm_halo_launches(b.comm);
-    return comm_halo_z(b.comm, f, sizeof(T), g.s[2], g.N[2], ncomp, g.cs, L.stream);
+    const bool ring = b.bc_u[2][0] == INSB200_BC_PERIODIC;  // walls / symmetry planes in z: open ends
+    return comm_halo_z(b.comm, f, sizeof(T), g.s[2], g.N[2], ncomp, g.cs, L.stream, ring);
+}
+
+// Slab decomposition along a NON-periodic z (walls / symmetry planes, BASELINE config 4): the interfaces between
+// slabs are exchanged like periodic ghosts; the physical boundary planes exist on the first rank (lower side) and
+// on the last rank (upper side) only, where the plane operations of the reference run on the local slab (the
+// exchange is open-ended: nothing travels between the last and the first rank).
+static bool z_decomposed_walls(const BcDesc &b, const int (*types)[2]) {
+    return b.comm && (types[2][0] != INSB200_BC_PERIODIC || types[2][1] != INSB200_BC_PERIODIC);
+}
+static void keep_end_rank_sides(const BcDesc &b, BcOps &ops) {
+    const int rank = comm_rank(b.comm), world = comm_world(b.comm);
+    for (int c = 0; c < MAXBCF; c++) {
+        if (rank != 0) ops.op[0][c].mode = OP_NONE;
+        if (rank != world - 1) ops.op[1][c].mode = OP_NONE;
+    }
 }
 
 template <typename T>
 int launch_bc_u(const Grid<T> &g, const BcDesc &b, T *u, int dudt, Launch L, int dims) {
     for (int beta = 0; beta < g.D; beta++) {
         if (!(dims >> beta & 1)) continue;
-        if (beta == 2 && b.comm) {
+        const bool slab_dim = beta == 2 && b.comm;
+        if (slab_dim) {
             INSB_TRY(halo_dim<T>(g, b, u, g.D, L));
-            continue;
+            if (!z_decomposed_walls(b, b.bc_u)) continue;
         }
         BcOps ops{};
         ops.ncomp = g.D;
@@ -140,6 +157,7 @@ int launch_bc_u(const Grid<T> &g, const BcDesc &b, T *u, int dudt, Launch L, int
                 }
             }
         }
+        if (slab_dim) keep_end_rank_sides(b, ops);
         INSB_TRY(run_dim<T>(g, beta, ops, u, L));
     }
     return 0;
@@ -151,10 +169,11 @@ static int scalar_bc(const Grid<T> &g, const BcDesc &b, const int (*types)[2], b
                      Launch L, int dims = 7, int nf = 1) {
     for (int beta = 0; beta < g.D; beta++) {
         if (!(dims >> beta & 1)) continue;
-        if (beta == 2 && b.comm) {  // decomposed direction is periodic for every field
-            for (int f0 = 0; f0 < nf; f0 += 3)  // the peer-store halo window holds three planes per side
+        const bool slab_dim = beta == 2 && b.comm;
+        if (slab_dim) {
+            for (int f0 = 0; f0 < nf; f0 += 3)  // (three planes per side and exchange)
                 INSB_TRY(halo_dim<T>(g, b, p + (long long)f0 * g.cs, nf - f0 < 3 ? nf - f0 : 3, L));
-            continue;
+            if (!z_decomposed_walls(b, b.bc_u) && !z_decomposed_walls(b, types)) continue;
         }
         BcOps ops{};
         ops.ncomp = nf;
@@ -198,6 +217,7 @@ static int scalar_bc(const Grid<T> &g, const BcDesc &b, const int (*types)[2], b
         }
         for (int side = 0; side < 2; side++)
             for (int f = 1; f < nf; f++) ops.op[side][f] = ops.op[side][0];
+        if (slab_dim) keep_end_rank_sides(b, ops);
         INSB_TRY(run_dim<T>(g, beta, ops, p, L));
     }
     return 0;
@@ -213,7 +233,8 @@ int launch_bc_p_fields(const Grid<T> &g, const BcDesc &b, T *fields, int nf, Lau
 template <typename T>
 int launch_zero_out_wall(const Grid<T> &g, const BcDesc &b, T *fields, int nf, Launch L) {
     for (int beta = 0; beta < g.D; beta++) {
-        if (beta == 2 && b.comm) continue;  // the decomposed direction is periodic
+        const bool slab_dim = beta == 2 && b.comm;
+        if (slab_dim && !z_decomposed_walls(b, b.bc_u)) continue;  // a periodic decomposed direction has no wall
         BcOps ops{};
         ops.ncomp = nf;
         for (int side = 0; side < 2; side++)
@@ -223,6 +244,7 @@ int launch_zero_out_wall(const Grid<T> &g, const BcDesc &b, T *fields, int nf, L
                     ops.op[side][f].val = 0.0;
                     ops.op[side][f].dst = side ? g.N[beta] - 1 : 0;
                 }
+        if (slab_dim) keep_end_rank_sides(b, ops);
         INSB_TRY(run_dim<T>(g, beta, ops, fields, L));
     }
     return 0;

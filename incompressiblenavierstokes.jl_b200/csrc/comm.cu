@@ -311,17 +311,22 @@ int comm_exchange_launches(const Comm *c, size_t chunk_bytes, int ncomp) {
 
 // Ghost planes of a field whose component is `nplanes` contiguous planes of `plane` elements with `ng` ghost
 // planes on either side: the top ng interior planes go up, the first ng interior planes go down.
+// ring == false: the decomposed direction is not periodic -- nothing travels between the last and the first rank
+// (their outer ghost planes belong to the physical boundary conditions and stay untouched).
 int comm_halo_planes(Comm *c, void *field, size_t esz, long long plane, int nplanes, int ng, int ncomp, long long cs,
-                     cudaStream_t st) {
+                     cudaStream_t st, bool ring) {
     char *f = (char *)field;
     const size_t pb = (size_t)plane * esz, csb = (size_t)cs * esz;
-    return comm_exchange(c, f + (size_t)(nplanes - 2 * ng) * pb, f + (size_t)ng * pb, f, f + (size_t)(nplanes - ng) * pb,
-                         (size_t)ng * pb, ncomp, csb, csb, st);
+    const bool first = c->rank == 0, last = c->rank == c->world - 1;
+    const bool up = ring || !last, down = ring || !first;
+    return comm_exchange(c, up ? f + (size_t)(nplanes - 2 * ng) * pb : nullptr, down ? f + (size_t)ng * pb : nullptr,
+                         down ? f : nullptr, up ? f + (size_t)(nplanes - ng) * pb : nullptr, (size_t)ng * pb, ncomp, csb,
+                         csb, st);
 }
 
 int comm_halo_z(Comm *c, void *field, size_t esz, long long plane, int nplanes, int ncomp, long long cs,
-                cudaStream_t st) {
-    return comm_halo_planes(c, field, esz, plane, nplanes, 1, ncomp, cs, st);
+                cudaStream_t st, bool ring) {
+    return comm_halo_planes(c, field, esz, plane, nplanes, 1, ncomp, cs, st, ring);
 }
 
 // All-to-all of `world` equal blocks of `block_bytes`: block r of `send` goes to rank r and

@@ -355,7 +355,9 @@ __device__ __forceinline__ void exchange_rev(const Cx<T> (&v)[8], Cx<T> (&vr)[8]
     exch++;
 }
 
-template <typename T, int N, int MODE>
+// BLK: the generalised (blocked / grouped / peer-store) addressing of the slab-decomposed solve, exactly the one of
+// fft_strided_kernel (fft_fast.h); element k of the line is read at in_at(k) and written at out_at(k).
+template <typename T, int N, int MODE, bool BLK>
 __global__ void __launch_bounds__(StridedShape<T, N>::NT, (sizeof(T) == 4 && StridedShape<T, N>::NT <= 512) ? 2 : 1)
     fft_strided_dct_kernel(Cx<T> *__restrict__ W, FastGeom g, int tdim, const Cx<T> *__restrict__ tw,
                            const T *__restrict__ e0, const T *__restrict__ e1, const T *__restrict__ e2, T factor) {
@@ -368,6 +370,25 @@ __global__ void __launch_bounds__(StridedShape<T, N>::NT, (sizeof(T) == 4 && Str
     const int odim = tdim == 1 ? 2 : 1;
     const long long sd = g.ws[tdim];
     Cx<T> *base = W + kx + (g.D == 3 ? other * g.ws[odim] : 0);
+    const long long in_sd = g.in_sd >= 0 ? g.in_sd : g.ws[tdim], out_sd = g.out_sd >= 0 ? g.out_sd : g.ws[tdim];
+    const long long in_os = g.in_os >= 0 ? g.in_os : g.ws[odim], out_os = g.out_os >= 0 ? g.out_os : g.ws[odim];
+    const long long xin = (BLK && g.in_grp) ? grp_x<T>(kx) : kx, xout = (BLK && g.out_grp) ? grp_x<T>(kx) : kx;
+    const long long oin = (BLK && g.in_grp == 2) ? grp_row<T>(other, g.m0p) : other * in_os;
+    const long long oout = (BLK && g.out_grp == 2) ? grp_row<T>(other, g.m0p) : other * out_os;
+    const Cx<T> *ibase = (g.in ? (const Cx<T> *)g.in : W) + xin + (g.D == 3 ? oin : 0);
+    Cx<T> *obase = (g.out ? (Cx<T> *)g.out : W) + xout + (g.D == 3 ? oout : 0);
+    auto in_at = [&](int k) -> const Cx<T> * {
+        if (!BLK) return base + (long long)k * sd;
+        const int kl = k & ((1 << g.in_sh) - 1);
+        return ibase + (long long)(k >> g.in_sh) * g.in_blk + (g.in_grp == 1 ? grp_row<T>(kl, g.m0p) : (long long)kl * in_sd);
+    };
+    auto out_at = [&](int k) -> Cx<T> * {
+        if (!BLK) return base + (long long)k * sd;
+        const int kl = k & ((1 << g.out_sh) - 1);
+        const long long rel = g.out_grp == 1 ? grp_row<T>(kl, g.m0p) : (long long)kl * out_sd;
+        if (g.use_outp) return reinterpret_cast<Cx<T> *>(g.outp[k >> g.out_sh]) + xout + oout + rel;
+        return obase + (long long)(k >> g.out_sh) * g.out_blk + rel;
+    };
     const Cx<T> *dw = (const Cx<T> *)g.dw, *dwi = (const Cx<T> *)g.dwi;
     LineSmem<T> sm;
     sm.buf[0] = reinterpret_cast<Cx<T> *>(smem_raw) + l;
@@ -377,10 +398,10 @@ __global__ void __launch_bounds__(StridedShape<T, N>::NT, (sizeof(T) == 4 && Str
     auto perm = [](int p) { return p < N / 2 ? 2 * p : 2 * (N - 1 - p) + 1; };
     if (MODE == 1) {
 #pragma unroll
-        for (int m = 0; m < 8; m++) v[m] = base[(long long)(t + P * m) * sd];
+        for (int m = 0; m < 8; m++) v[m] = *in_at(t + P * m);
     } else {
 #pragma unroll
-        for (int m = 0; m < 8; m++) v[m] = base[(long long)perm(t + P * m) * sd];
+        for (int m = 0; m < 8; m++) v[m] = *in_at(perm(t + P * m));
     }
     T f[8];
     if (MODE == 2) {
@@ -390,7 +411,7 @@ __global__ void __launch_bounds__(StridedShape<T, N>::NT, (sizeof(T) == 4 && Str
             T den;
             bool zero;
             if (g.D == 3) {
-                int k1 = tdim == 1 ? k : other, k2 = tdim == 1 ? other : k;
+                int k1 = tdim == 1 ? k : other + g.eig_off, k2 = tdim == 1 ? other + g.eig_off : k;
                 den = (e0[kx] + e1[k1]) + e2[k2];
                 zero = (kx | k1 | k2) == 0;
             } else {
@@ -436,10 +457,10 @@ __global__ void __launch_bounds__(StridedShape<T, N>::NT, (sizeof(T) == 4 && Str
         fft_stages<T, N, true, 0, L>(v, t, sm, tw, exch);
         const T invn = T(1) / T(N);
 #pragma unroll
-        for (int m = 0; m < 8; m++) base[(long long)perm(t + P * m) * sd] = Ops<T>::scale(v[m], invn);
+        for (int m = 0; m < 8; m++) *out_at(perm(t + P * m)) = Ops<T>::scale(v[m], invn);
     } else {
 #pragma unroll
-        for (int m = 0; m < 8; m++) base[(long long)(t + P * m) * sd] = v[m];
+        for (int m = 0; m < 8; m++) *out_at(t + P * m) = v[m];
     }
 }
 
@@ -793,9 +814,11 @@ static int fast_pass_n(int kind, T *R, Cx<T> *W, const FastGeom &g, int tdim, co
             set_error("fast DCT pass: bad geometry");
             return 1;
         }
-        dim3 grid(g.m0p / SS::L, g.D == 3 ? g.n[tdim == 1 ? 2 : 1] : 1);
-        auto kern = kind == 5 ? fft_strided_dct_kernel<T, N, 0> : kind == 6 ? fft_strided_dct_kernel<T, N, 1>
-                                                                           : fft_strided_dct_kernel<T, N, 2>;
+        const bool blk = g.in_sh < 30 || g.out_sh < 30 || g.use_outp || g.in_grp || g.out_grp || g.in || g.out;
+        dim3 grid(g.m0p / SS::L, g.D == 3 ? (g.nother >= 0 ? g.nother : g.n[tdim == 1 ? 2 : 1]) : 1);
+        auto kern = kind == 5   ? (blk ? fft_strided_dct_kernel<T, N, 0, true> : fft_strided_dct_kernel<T, N, 0, false>)
+                    : kind == 6 ? (blk ? fft_strided_dct_kernel<T, N, 1, true> : fft_strided_dct_kernel<T, N, 1, false>)
+                                : (blk ? fft_strided_dct_kernel<T, N, 2, true> : fft_strided_dct_kernel<T, N, 2, false>);
         INSB_TRY(allow_smem(kern, SS::smem));
         kern<<<grid, SS::NT, SS::smem, L.stream>>>(W, g, tdim, tw, e0, e1, e2, factor);
     } else {

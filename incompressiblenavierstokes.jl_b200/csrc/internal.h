@@ -62,7 +62,7 @@ void comm_destroy(Comm *c);
 int comm_rank(const Comm *c);   // 0 for nullptr
 int comm_world(const Comm *c);  // 1 for nullptr
 int comm_halo_z(Comm *c, void *field, size_t esz, long long plane, int nplanes, int ncomp, long long cs,
-                cudaStream_t st);
+                cudaStream_t st, bool ring = true);
 // Generic neighbour exchange along the decomposed direction: chunk `send_up` (+ c * src_cs_bytes for component
 // c) goes to the rank above, which receives it in `recv_below` (+ c * dst_cs_bytes); `send_down` / `recv_above`
 // likewise downwards.  Null pointers skip a direction (all ranks alike).
@@ -71,7 +71,7 @@ int comm_exchange(Comm *c, const void *send_up, const void *send_down, void *rec
 int comm_exchange_launches(const Comm *c, size_t chunk_bytes, int ncomp);
 // `ng` ghost planes on either side of `nplanes` contiguous planes per component
 int comm_halo_planes(Comm *c, void *field, size_t esz, long long plane, int nplanes, int ng, int ncomp, long long cs,
-                     cudaStream_t st);
+                     cudaStream_t st, bool ring = true);
 // Halo exchange by direct peer stores: `windows[r]` is rank r's window (peer-mapped, windows[rank]
 // local) of comm_halo_window_bytes(slot_bytes) bytes, zero-initialised; slot_bytes >= bytes of
 // the ghost planes of one exchange (all components).  Until enabled comm_halo_z uses NCCL.
@@ -211,6 +211,10 @@ long long poisson_bytes(const Poisson *p);
 int poisson_iterations(const Poisson *p);
 // energyspectrum (src/spectral.jl:75-117): ehat = kmax + 1 device doubles
 int poisson_energy_spectrum(Poisson *ps, const void *u, long long cs, int kmax, double *ehat, Launch L);  // psolver_cg: iterations of the last solve
+// random_field (src/initializers.jl:109-183): the interior of u holds white noise (fill == 0) or is filled with
+// Philox N(0, 1) from `seed` first; e0_host[kappa] = target energy of shell kappa (kdiag + 1 entries)
+int poisson_random_field(Poisson *ps, void *u, long long cs, const double *e0_host, int nshell, int fill,
+                         unsigned long long seed, const double xlims[3][2], Launch L);
 // ---- cg.cu ----
 struct CgSolver;
 int cg_create(const insb200_setup_t &s, const int Ip[3][2], double reltol, double abstol, long long maxiter,
@@ -245,5 +249,6 @@ int poisson_solve(Poisson *ps, void *p_ghosted, Launch L, const DivSource *div =
 constexpr int POISSON_IPC_BYTES = 192;
 int poisson_ipc_export(Poisson *ps, void *blob);
 int poisson_ipc_import(Poisson *ps, const void *blobs);
+void poisson_ipc_close(Poisson *ps);
 
 }  // namespace insb

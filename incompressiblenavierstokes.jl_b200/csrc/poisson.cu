@@ -776,9 +776,15 @@ int poisson_create(const insb200_setup_t &s, const int Ip[3][2], int kind, Comm 
         // modes (all y, all z), z FFT + Thomas along y + inverse z FFT there, transpose back
         const bool tri = kind == INSB200_PSOLVER_TRIDIAGONAL && D == 3 && ps->wdir == 1 &&
                          fast_fft_supported(ps->n[0]) && fast_fft_supported(ps->n[2]) && ps->n[1] % 2 == 0;
-        if (!spec && !tri)
-            return fail("world > 1: only psolver_spectral on 3-D power-of-two grids (32..2048 per dim) and "
-                        "psolver_tridiagonal with walls in y (power-of-two x and z extents) are decomposed");
+        // psolver_transform (x periodic, DCT along the wall-bounded directions): the same pass structure and
+        // transposes as psolver_spectral with DCT kernels in y and / or z
+        bool dct = kind == INSB200_PSOLVER_TRANSFORM && D == 3 && ps->per[0];
+        for (int a = 0; a < D; a++) dct = dct && fast_fft_supported(ps->n[a]);
+        if (!spec && !tri && !dct)
+            return fail("world > 1: only psolver_spectral / psolver_transform (x periodic) on 3-D power-of-two grids "
+                        "(32..2048 per dim) and psolver_tridiagonal with walls in y (power-of-two x and z extents) "
+                        "are decomposed");
+        spec = spec || dct;  // (same divisibility requirements)
         if (ps->n[2] % world || (ps->nzl & (ps->nzl - 1)))
             return fail("world > 1: n3 must be divisible by the number of ranks (power-of-two planes per rank)");
         if (spec && (ps->n[1] % world || (ps->kyl & (ps->kyl - 1))))
@@ -866,8 +872,8 @@ int poisson_create(const insb200_setup_t &s, const int Ip[3][2], int kind, Comm 
         ps->bytes += (long long)wb;
     }
     // psolver_transform fast path: x periodic, every extent a supported power of two
-    ps->fast_dct = kind == INSB200_PSOLVER_TRANSFORM && ps->per[0] && world == 1 && D >= 2 &&
-                   getenv("INSB200_GENERIC_FFT") == nullptr && ps->n[1] % 2 == 0;
+    ps->fast_dct = kind == INSB200_PSOLVER_TRANSFORM && ps->per[0] && D >= 2 &&
+                   (world > 1 || getenv("INSB200_GENERIC_FFT") == nullptr) && ps->n[1] % 2 == 0;
     for (int a = 0; a < D; a++) ps->fast_dct = ps->fast_dct && fast_fft_supported(ps->n[a]);
     ps->tile = ps->f64 ? 4 : 8;
     if (const char *e = getenv("INSB200_FFT_TILE")) ps->tile = atoi(e) > 0 ? atoi(e) : ps->tile;
@@ -879,19 +885,30 @@ int poisson_create(const insb200_setup_t &s, const int Ip[3][2], int kind, Comm 
     return 0;
 }
 
-void poisson_destroy(Poisson *p) {
+// First half of a collective tear-down: unmap the peers' buffers (the exporting process must not free memory
+// another process still has open, CUDA IPC); from here on the transposes / halo exchange use NCCL again.
+void poisson_ipc_close(Poisson *p) {
     if (!p) return;
-    if (p->cg) cg_destroy(p->cg);
     if (p->comm && p->flags) comm_disable_p2p_halo(p->comm, p->flags);
     if (p->p2p) {
+        cudaDeviceSynchronize();
         const int rank = comm_rank(p->comm), world = comm_world(p->comm);
         for (int s = 0; s < world; s++) {
             if (s == rank) continue;
             if (p->peerS[s]) cudaIpcCloseMemHandle(p->peerS[s]);
             if (p->peerRv[s]) cudaIpcCloseMemHandle(p->peerRv[s]);
             if (p->peerFlags[s]) cudaIpcCloseMemHandle(p->peerFlags[s]);
+            p->peerS[s] = p->peerRv[s] = nullptr;
+            p->peerFlags[s] = nullptr;
         }
+        p->p2p = false;
     }
+}
+
+void poisson_destroy(Poisson *p) {
+    if (!p) return;
+    if (p->cg) cg_destroy(p->cg);
+    poisson_ipc_close(p);
     for (void *q : p->owned) cudaFree(q);
     if (p->W) cudaFree(p->W);
     delete p;
@@ -976,6 +993,241 @@ int poisson_energy_spectrum(Poisson *ps, const void *u, long long cs, int kmax, 
                    : spectrum_t<float>(ps, (const float *)u, cs, kmax, ehat, L);
 }
 
+// ----------------------------------------------------------------------------------------
+// random_field (src/initializers.jl:109-183) on the device with the solver's own FFT passes:
+//   white noise per component (the caller's, or Philox4x32-10 + Box-Muller here) -> forward transforms ->
+//   projection onto the divergence-free space of the STAGGERED grid with the symbol of the backward difference,
+//   m_a = (1 - exp(-i theta_a)) / h_a (:133-151) -> shell energies (spectral.jl:39-67, conjugate modes counted
+//   twice) -> shell-wise rescaling to the target profile (:160-172) -> inverse transforms into view(u, Ip, a).
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(unsigned c[4], unsigned k0, unsigned k1) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const unsigned n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+        c[0] = n0, c[1] = lo1, c[2] = n2, c[3] = lo0;
+        k0 += 0x9E3779B9u, k1 += 0xBB67AE85u;
+    }
+}
+
+// N(0, 1) into the interior of `ncomp` ghosted scalar fields: four values per counter, interior cell q of
+// component c comes from counter (q / 4, c) -- independent of the launch shape
+template <typename T>
+__global__ void __launch_bounds__(256) rf_noise_kernel(T *u, long long cs, int ncomp, int n0, int n1, int n2, long long s1,
+                                                       long long s2, unsigned long long seed) {
+    const long long total4 = ((long long)n0 * n1 * n2 + 3) / 4;
+    const long long q4 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int c = blockIdx.y;
+    if (q4 >= total4 || c >= ncomp) return;
+    unsigned ctr[4] = {(unsigned)q4, (unsigned)(q4 >> 32), (unsigned)c, 0x1234567u};
+    philox4x32_10(ctr, (unsigned)seed, (unsigned)(seed >> 32));
+    double z[4];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const double u1 = ((double)ctr[2 * h] + 0.5) * 2.3283064365386963e-10;  // (0, 1)
+        const double u2 = ((double)ctr[2 * h + 1] + 0.5) * 2.3283064365386963e-10;
+        const double r = sqrt(-2.0 * log(u1));
+        double sn, cs2;
+        sincospi(2.0 * u2, &sn, &cs2);
+        z[2 * h] = r * cs2, z[2 * h + 1] = r * sn;
+    }
+    const long long total = (long long)n0 * n1 * n2;
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        const long long q = 4 * q4 + e;
+        if (q >= total) break;
+        const int i = (int)(q % n0), j = (int)((q / n0) % n1), k = (int)(q / ((long long)n0 * n1));
+        u[c * cs + i + j * s1 + k * s2] = (T)z[e];
+    }
+}
+
+struct RfGeom {
+    int D, m0, m0p, n0, n1, n2;
+    double h[3];
+    int kmax;
+    double escale;  // 1 / (2 Ntot^2)
+};
+
+template <typename T>
+__device__ __forceinline__ Cx<T> rf_symbol(int k, int n, double h) {
+    double sn, cs;
+    sincospi(2.0 * (double)k / (double)n, &sn, &cs);
+    return Cx<T>{(T)((1.0 - cs) / h), (T)(sn / h)};  // (1 - exp(-i theta)) / h
+}
+
+__device__ __forceinline__ int rf_shell(long long k2) {
+    int kap = (int)sqrt((double)k2);
+    while ((long long)kap * kap > k2) kap--;
+    while ((long long)(kap + 1) * (kap + 1) <= k2) kap++;
+    return kap;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) rf_project_kernel(Cx<T> *U0, Cx<T> *U1, Cx<T> *U2, RfGeom g, double *eshell) {
+    extern __shared__ double bins[];
+    for (int i = threadIdx.x; i <= g.kmax; i += blockDim.x) bins[i] = 0.0;
+    __syncthreads();
+    const long long total = (long long)g.m0 * g.n1 * g.n2;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+        const int kx = (int)(q % g.m0);
+        const int iy = (int)((q / g.m0) % g.n1), iz = (int)(q / ((long long)g.m0 * g.n1));
+        const int ky = iy < (g.n1 + 1) / 2 ? iy : iy - g.n1;
+        const int kz = g.D == 3 ? (iz < (g.n2 + 1) / 2 ? iz : iz - g.n2) : 0;
+        const long long at = kx + (long long)iy * g.m0p + (long long)iz * g.m0p * g.n1;
+        Cx<T> u[3] = {U0[at], U1[at], g.D == 3 ? U2[at] : Cx<T>{T(0), T(0)}};
+        Cx<T> m[3] = {rf_symbol<T>(kx, g.n0, g.h[0]), rf_symbol<T>(ky, g.n1, g.h[1]),
+                      g.D == 3 ? rf_symbol<T>(kz, g.n2, g.h[2]) : Cx<T>{T(0), T(0)}};
+        Cx<T> mdotu = cmul(m[0], u[0]);
+        mdotu = cadd(mdotu, cmul(m[1], u[1]));
+        if (g.D == 3) mdotu = cadd(mdotu, cmul(m[2], u[2]));
+        T m2 = (m[0].x * m[0].x + m[0].y * m[0].y) + (m[1].x * m[1].x + m[1].y * m[1].y);
+        if (g.D == 3) m2 = m2 + (m[2].x * m[2].x + m[2].y * m[2].y);
+        double e = 0.0;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            if (a == 2 && g.D == 2) break;
+            if (m2 > T(0)) {
+                const Cx<T> t = cmul(cconj(m[a]), mdotu);
+                u[a] = Cx<T>{u[a].x - t.x / m2, u[a].y - t.y / m2};
+            }
+            e += (double)u[a].x * (double)u[a].x + (double)u[a].y * (double)u[a].y;
+        }
+        U0[at] = u[0], U1[at] = u[1];
+        if (g.D == 3) U2[at] = u[2];
+        const int kap = rf_shell((long long)kx * kx + (long long)ky * ky + (long long)kz * kz);
+        if (kap <= g.kmax) atomicAdd(&bins[kap], ((kx > 0 && kx < g.n0 / 2) ? 2.0 : 1.0) * g.escale * e);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i <= g.kmax; i += blockDim.x)
+        if (bins[i] != 0.0) atomicAdd(eshell + i, bins[i]);
+}
+
+// factor[kappa] = sqrt(e0 / eshell) (0 for an empty shell), evaluated in the field type like :165-167, times the
+// 1 / prod(Np) of the inverse transform
+template <typename T>
+__global__ void rf_factor_kernel(const double *e0, const double *eshell, int kmax, double invn, T *factor) {
+    for (int i = threadIdx.x; i <= kmax; i += blockDim.x) {
+        const T es = (T)eshell[i], et = (T)e0[i];
+        const T f = es > T(0) ? (T)sqrt((double)(et / es)) : T(0);
+        factor[i] = (T)((double)f * invn);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) rf_scale_kernel(Cx<T> *U0, Cx<T> *U1, Cx<T> *U2, RfGeom g, const T *__restrict__ factor) {
+    const long long total = (long long)g.m0p * g.n1 * g.n2;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+        const int kx = (int)(q % g.m0p);
+        const int iy = (int)((q / g.m0p) % g.n1), iz = (int)(q / ((long long)g.m0p * g.n1));
+        const int ky = iy < (g.n1 + 1) / 2 ? iy : iy - g.n1;
+        const int kz = g.D == 3 ? (iz < (g.n2 + 1) / 2 ? iz : iz - g.n2) : 0;
+        const int kap = rf_shell((long long)kx * kx + (long long)ky * ky + (long long)kz * kz);
+        const T f = (kx < g.m0 && kap <= g.kmax) ? factor[kap] : T(0);
+        U0[q] = Cx<T>{U0[q].x * f, U0[q].y * f}, U1[q] = Cx<T>{U1[q].x * f, U1[q].y * f};
+        if (g.D == 3) U2[q] = Cx<T>{U2[q].x * f, U2[q].y * f};
+    }
+}
+
+template <typename T>
+static int random_field_t(Poisson *ps, T *u, long long cs, const double *e0_host, int nshell, int fill, unsigned long long seed,
+                          const double xlims[3][2], Launch L) {
+    const int D = ps->D;
+    long long rs[3] = {1, ps->Ng[0], (long long)ps->Ng[0] * ps->Ng[1]};
+    FastGeom g;
+    g.D = D;
+    for (int d = 0; d < 3; d++) {
+        g.n[d] = ps->n[d];
+        g.ws[d] = ps->wstride[d];
+        g.rs[d] = rs[d];
+    }
+    g.m0p = (int)ps->wstride[1];
+    RfGeom rg{};
+    rg.D = D, rg.m0 = ps->m[0], rg.m0p = g.m0p, rg.n0 = ps->n[0], rg.n1 = ps->n[1], rg.n2 = D == 3 ? ps->n[2] : 1;
+    double np = 1.0, k2max = 0.0;
+    for (int a = 0; a < D; a++) {
+        np *= (double)ps->n[a];
+        rg.h[a] = (xlims[a][1] - xlims[a][0]) / ps->n[a];
+        k2max += (double)(ps->n[a] / 2) * (ps->n[a] / 2);
+    }
+    rg.kmax = (int)std::floor(std::sqrt(k2max));  // kdiag: the last shell holds the largest wavenumber of the grid
+    while ((double)(rg.kmax + 1) * (rg.kmax + 1) <= k2max) rg.kmax++;
+    while ((double)rg.kmax * rg.kmax > k2max) rg.kmax--;
+    if (nshell != rg.kmax + 1) {
+        set_error("random_field: the profile table must hold kdiag + 1 = " + std::to_string(rg.kmax + 1) + " shells");
+        return 1;
+    }
+    rg.escale = 1.0 / (2.0 * np * np);
+    const size_t wb = (size_t)g.m0p * ps->n[1] * rg.n2 * sizeof(Cx<T>);
+    void *tmp[2] = {nullptr, nullptr};
+    double *dsh = nullptr;
+    T *dfac = nullptr;
+    auto cleanup = [&]() {
+        cudaStreamSynchronize(L.stream);
+        for (void *p : tmp) cudaFree(p);
+        cudaFree(dsh);
+        cudaFree(dfac);
+    };
+    if (cudaMalloc(&tmp[0], wb) != cudaSuccess || (D == 3 && cudaMalloc(&tmp[1], wb) != cudaSuccess) ||
+        cudaMalloc((void **)&dsh, 2 * (size_t)nshell * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void **)&dfac, (size_t)nshell * sizeof(T)) != cudaSuccess) {
+        cleanup();
+        set_error("random_field: cudaMalloc of the spectral work arrays failed");
+        return 1;
+    }
+    Cx<T> *U[3] = {(Cx<T> *)ps->W, (Cx<T> *)tmp[0], D == 3 ? (Cx<T> *)tmp[1] : (Cx<T> *)tmp[0]};
+    T *R0 = u;
+    for (int a = 0; a < D; a++) R0 += ps->ioff[a] * rs[a];
+    const T *e0 = (const T *)ps->eig[0];
+    int rc = 0;
+    auto run = [&]() -> int {
+        if (fill) {
+            const long long total4 = ((long long)rg.n0 * rg.n1 * rg.n2 + 3) / 4;
+            dim3 gr((unsigned)((total4 + 255) / 256), D);
+            rf_noise_kernel<T><<<gr, 256, 0, L.stream>>>(R0, cs, D, rg.n0, rg.n1, rg.n2, rs[1], rs[2], seed);
+            if (L.counter) ++*L.counter;
+        }
+        for (int c = 0; c < D; c++) {
+            T *R = R0 + c * cs;
+            INSB_TRY(fast_pass<T>(3, ps->n[0], R, U[c], g, 0, ps->tw[0], e0, e0, e0, T(1), 0, L));
+            INSB_TRY(fast_pass<T>(0, ps->n[1], R, U[c], g, 1, ps->tw[1], e0, e0, e0, T(1), 0, L));
+            if (D == 3) INSB_TRY(fast_pass<T>(0, ps->n[2], R, U[c], g, 2, ps->tw[2], e0, e0, e0, T(1), 0, L));
+        }
+        INSB_CUDA(cudaMemsetAsync(dsh, 0, (size_t)nshell * sizeof(double), L.stream));
+        INSB_CUDA(cudaMemcpyAsync(dsh + nshell, e0_host, (size_t)nshell * sizeof(double), cudaMemcpyHostToDevice, L.stream));
+        const size_t sm = (size_t)nshell * sizeof(double);
+        rf_project_kernel<T><<<148 * 4, 256, sm, L.stream>>>(U[0], U[1], U[2], rg, dsh);
+        rf_factor_kernel<T><<<1, 256, 0, L.stream>>>(dsh + nshell, dsh, rg.kmax, 1.0 / np, dfac);
+        rf_scale_kernel<T><<<148 * 8, 256, 0, L.stream>>>(U[0], U[1], U[2], rg, dfac);
+        if (L.counter) *L.counter += 3;
+        INSB_CUDA(cudaGetLastError());
+        for (int c = 0; c < D; c++) {
+            T *R = R0 + c * cs;
+            if (D == 3) INSB_TRY(fast_pass<T>(1, ps->n[2], R, U[c], g, 2, ps->tw[2], e0, e0, e0, T(1), 0, L));
+            INSB_TRY(fast_pass<T>(1, ps->n[1], R, U[c], g, 1, ps->tw[1], e0, e0, e0, T(1), 0, L));
+            INSB_TRY(fast_pass<T>(4, ps->n[0], R, U[c], g, 0, ps->tw[0], e0, e0, e0, T(1), 0, L));
+        }
+        return 0;
+    };
+    rc = run();
+    cleanup();
+    return rc;
+}
+
+int poisson_random_field(Poisson *ps, void *u, long long cs, const double *e0_host, int nshell, int fill,
+                         unsigned long long seed, const double xlims[3][2], Launch L) {
+    if (!ps || !ps->fast || ps->comm) {
+        set_error("random_field needs a single-GPU psolver_spectral plan on a power-of-two periodic grid");
+        return 1;
+    }
+    if (nshell < 1 || nshell > 4096) {
+        set_error("random_field: shell count out of range");
+        return 1;
+    }
+    return ps->f64 ? random_field_t<double>(ps, (double *)u, cs, e0_host, nshell, fill, seed, xlims, L)
+                   : random_field_t<float>(ps, (float *)u, cs, e0_host, nshell, fill, seed, xlims, L);
+}
+
 int poisson_ipc_export(Poisson *ps, void *blob) {
     if (!ps || !ps->comm) {
         set_error("ipc export: the plan is not slab-decomposed");
@@ -1056,7 +1308,7 @@ static int solve_t(Poisson *ps, T *p, Launch L, const DivSource *div, const Pois
         gx.div_cs = div->cs;
         gx.div_wrap = div->wrap;
     };
-    if (ps->fast) {
+    if (ps->fast || (ps->fast_dct && ps->comm)) {
         FastGeom g;
         g.D = D;
         for (int d = 0; d < 3; d++) {
@@ -1076,6 +1328,12 @@ static int solve_t(Poisson *ps, T *p, Launch L, const DivSource *div, const Pois
             const long long blk = m0p * kyl * nzl;  // complex elements per peer block
             int sh = 0;
             while ((1 << sh) < kyl) sh++;
+            // psolver_transform: DCT kernels (kinds 5-7) along the wall-bounded directions
+            auto kind_of = [&](int base_kind, int dim) { return base_kind + (ps->per[dim] ? 0 : 5); };
+            auto dct_tables = [&](FastGeom &gg, int dim) {
+                gg.dw = ps->dw[dim];
+                gg.dwi = ps->dwi[dim];
+            };
             FastGeom gx = g;  // x passes see only the local planes
             gx.n[2] = nzl;
             {
@@ -1102,7 +1360,8 @@ static int solve_t(Poisson *ps, T *p, Launch L, const DivSource *div, const Pois
             }
             {
                 ProfScope sc(L, 6);
-                INSB_TRY(fast_pass<T>(0, ps->n[1], R, ps->W, gy, 1, ps->tw[1], e0, e1, e2, factor, tl, L));
+                dct_tables(gy, 1);
+                INSB_TRY(fast_pass<T>(kind_of(0, 1), ps->n[1], R, ps->W, gy, 1, ps->tw[1], e0, e1, e2, factor, tl, L));
             }
             {
                 ProfScope sc(L, 7);
@@ -1134,7 +1393,8 @@ static int solve_t(Poisson *ps, T *p, Launch L, const DivSource *div, const Pois
             }
             {
                 ProfScope sc(L, 8);
-                INSB_TRY(fast_pass<T>(2, ps->n[2], R, ps->W, gz, 2, ps->tw[2], e0, e1, e2, factor, tl, L));
+                dct_tables(gz, 2);
+                INSB_TRY(fast_pass<T>(kind_of(2, 2), ps->n[2], R, ps->W, gz, 2, ps->tw[2], e0, e1, e2, factor, tl, L));
             }
             {
                 ProfScope sc(L, 9);
@@ -1163,7 +1423,8 @@ static int solve_t(Poisson *ps, T *p, Launch L, const DivSource *div, const Pois
             }
             {
                 ProfScope sc(L, 10);
-                INSB_TRY(fast_pass<T>(1, ps->n[1], R, ps->W, gi, 1, ps->tw[1], e0, e1, e2, factor, tl, L));
+                dct_tables(gi, 1);
+                INSB_TRY(fast_pass<T>(kind_of(1, 1), ps->n[1], R, ps->W, gi, 1, ps->tw[1], e0, e1, e2, factor, tl, L));
             }
             {
                 ProfScope sc(L, 11);

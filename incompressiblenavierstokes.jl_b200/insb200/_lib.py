@@ -68,6 +68,7 @@ _PROTOTYPES = {
     "insb200_plan_local_n": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "insb200_plan_ipc_export": (C.c_int, [_P, _P]),
     "insb200_plan_ipc_import": (C.c_int, [_P, _P]),
+    "insb200_plan_ipc_close": (C.c_int, [_P]),
     "insb200_plan_psolver": (C.c_int, [_P]),
     "insb200_plan_workspace_bytes": (C.c_longlong, [_P]),
     "insb200_apply_bc_u": (C.c_int, [_P, _P, C.c_double, C.c_int, _P]),
@@ -114,6 +115,7 @@ _PROTOTYPES = {
     "insb200_kinetic_energy": (C.c_int, [_P, _P, _P, C.c_int, _P]),
     "insb200_total_kinetic_energy": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_double), _P]),
     "insb200_energy_spectrum": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_double), _P]),
+    "insb200_random_field": (C.c_int, [_P, _P, C.POINTER(C.c_double), C.c_int, C.c_int, C.c_ulonglong, C.c_double, _P]),
     "insb200_solve_unsteady": (
         C.c_int,
         [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_int, _P, _P, C.c_double, C.c_double,

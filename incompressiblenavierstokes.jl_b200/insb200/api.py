@@ -17,6 +17,7 @@ streams; all arithmetic happens in the CUDA library.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 import os
 import time
 from fractions import Fraction
@@ -157,6 +158,7 @@ class Plan:
         self.p2p = False
         if setup.world > 1 and self.psolver != _lib.PSOLVER_NONE and not os.environ.get("INSB200_NO_P2P"):
             self._enable_p2p()
+        setup._plans.setdefault("_registry", weakref.WeakSet()).add(self)  # (release_plans)
 
     def _enable_p2p(self):
         """Direct peer-store FFT transposes: gather everybody's CUDA IPC handles through the
@@ -197,6 +199,30 @@ class Plan:
         names = ("rhs_combine", "divergence", "poisson", "project", "bc", "fft_x_r2c", "fft_y_fwd", "transpose_fwd",
                  "fft_z_mid", "transpose_bwd", "fft_y_inv", "fft_x_c2r")
         return {n: (ms[i], cnt[i]) for i, n in enumerate(names)}
+
+
+def release_plans(setup: Setup):
+    """Collective tear-down of every plan of a decomposed setup (call on all ranks at the same point): unmap the
+    peers' buffers, barrier, destroy, barrier -- an exporting process must not free memory a peer still has mapped,
+    and the next setup's IPC handles must not meet stale mappings.  A no-op chain for world == 1."""
+    plans = list(setup._plans.get("_registry", ()))
+    if setup.world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.synchronize()
+        for p in plans:
+            if p.h:
+                check(lib().insb200_plan_ipc_close(p.h))
+        dist.barrier()
+    for p in plans:
+        if p.h:
+            lib().insb200_plan_destroy(p.h)
+            p.h = None
+    setup._plans.clear()
+    if setup.world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
 
 
 def _base_plan(setup: Setup) -> Plan:
@@ -1100,6 +1126,42 @@ def velocityfield(setup, ufunc, t=0.0, *, psolver=None, doproject=True):
         ud = project(ud, setup, psolver=psolver)
         apply_bc_u_(ud, t, setup)
     return ud
+
+
+def orlandi_profile(k, kpeak=10):
+    """orlandi_profile (src/initializers.jl:93): E(k) ~ k^4 exp(-2 (k / kpeak)^2)."""
+    return k**4 * np.exp(-2 * (k / kpeak) ** 2)
+
+
+def random_field(setup, t=0.0, *, profile=orlandi_profile, totalenergy=1.0, rng=None, psolver=None, **kwargs):
+    """random_field (src/initializers.jl:109-183), synthesised on the device with the FFT passes of the
+    setup's psolver_spectral (insb200_random_field): divergence free on the staggered grid to round-off, shell
+    energies equal to ``totalenergy * profile(kappa) / sum(profile)``.  ``rng``: a NumPy Generator draws the white
+    noise on the host like the reference's ``randn!(rng, v)`` per component (reproducible against the oracle);
+    ``None`` or an integer seed generates it on the device (Philox4x32-10), so that fields too large for the host
+    never exist there.  The profile function is evaluated here (it cannot cross the ABI)."""
+    if any(not setup.is_periodic(d) for d in range(setup.D)):
+        raise ValueError("Random field requires periodic boundary conditions.")
+    T, D, Np = setup.T, setup.D, setup.Np
+    psolver = psolver if psolver is not None else psolver_spectral(setup)
+    kdiag = int(np.floor(np.sqrt(sum((n // 2) ** 2 for n in Np))))
+    while (kdiag + 1) ** 2 <= sum((n // 2) ** 2 for n in Np):
+        kdiag += 1
+    prof = [T(profile(T(k), **kwargs)) for k in range(kdiag + 1)]
+    totalprofile = sum(prof)
+    e0 = (C.c_double * (kdiag + 1))(*[float(T(totalenergy) * pk / totalprofile) for pk in prof])
+    u = vectorfield(setup)
+    if isinstance(rng, np.random.Generator):
+        host = np.zeros(setup.N + (D,), dtype=T, order="F")
+        for a in range(D):
+            host[tuple(slice(lo, hi) for lo, hi in setup.Ip) + (a,)] = rng.standard_normal(Np).astype(T)
+        u = to_device(setup, host)
+        fill, seed = 0, 0
+    else:
+        fill, seed = 1, int(rng) if rng is not None else int(np.random.SeedSequence().entropy % (1 << 63))
+    check(lib().insb200_random_field(psolver.plan.h, _ptr(u), e0, kdiag + 1, fill, C.c_ulonglong(seed), float(t),
+                                     _stream()))
+    return u
 
 
 def temperaturefield(setup, tempfunc, t=0.0):

@@ -177,8 +177,9 @@ class Setup:
         # z-slab decomposition
         self.rank, self.world, self.nccl_id = int(rank), int(world), nccl_id
         if self.world > 1:
-            if D != 3 or not self.is_periodic(2):
-                raise ValueError("world > 1 needs a 3-D grid that is periodic in z")
+            zt = [type(b).__name__ for b in boundary_conditions["u"][2]] if D == 3 else []
+            if D != 3 or "PressureBC" in zt or (zt[0] == "PeriodicBC") != (zt[1] == "PeriodicBC"):
+                raise ValueError("world > 1 needs a 3-D grid that is periodic, wall-bounded or symmetric in z")
             if (N[2] - 2) % self.world:
                 raise ValueError("the number of z volumes must be divisible by world")
             if nccl_id is None or len(nccl_id) != 128:

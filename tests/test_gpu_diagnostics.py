@@ -159,3 +159,44 @@ def opr_project(u, so):
     u = opr.project(u, so, opr.psolver_spectral(so))
     obc.apply_bc_u(u, 0.0, so)
     return u
+
+
+@pytest.mark.parametrize("T", [np.float64, np.float32])
+@pytest.mark.parametrize("n", [(32, 32, 32), (64, 32, 128), (64, 32)])
+def test_random_field_on_device(n, T):
+    """random_field (src/initializers.jl:109-183, test/spectral.jl:29-56) synthesised on the device with the
+    solver's FFT passes: with the oracle's white noise injected the field equals the oracle's; with the device
+    generator (Philox) it is divergence free on the staggered grid, its spectrum equals the target in every shell
+    (the oracle's energyspectrum is the independent check), the same seed reproduces it (to round-off) and another one does not."""
+    import insb200 as I
+    from oracle import initializers as oini, operators as oops
+
+    D = len(n)
+    L = (1.0, 2.0, 0.5)[:D]
+    so, sg = make_setups(tuple(uniform(m, l) for m, l in zip(n, L)), ("P",) * D, T=T)
+    ps = I.psolver_spectral(sg)
+    total, kpeak = 0.3, 5
+    want = oini.random_field(so, 0.0, totalenergy=total, kpeak=kpeak, rng=np.random.default_rng(123))
+    got = I.to_host(I.random_field(sg, 0.0, totalenergy=total, kpeak=kpeak, rng=np.random.default_rng(123), psolver=ps))
+    assert rel_l2(got, want) < (1e-12 if T is np.float64 else 2e-5)
+    kdiag = int(np.floor(np.sqrt(sum((m // 2) ** 2 for m in so.Np))))
+    target = oini.orlandi_profile(np.arange(kdiag + 1, dtype=np.float64), kpeak=kpeak)
+    target = total * target / target.sum()
+    fields = []
+    for seed in (7, 7, 8):
+        ud = I.random_field(sg, 0.0, totalenergy=total, kpeak=kpeak, rng=seed, psolver=ps)
+        u = I.to_host(ud).astype(np.float64)
+        fields.append(u)
+        so64 = make_setups(tuple(uniform(m, l) for m, l in zip(n, L)), ("P",) * D, T=np.float64)[0]
+        div = oops.divergence_(O.scalarfield(so64), u, so64)
+        umax = np.abs(u).max()
+        assert np.max(np.abs(div[so64.Ip])) < (1e-10 if T is np.float64 else 2e-4) * umax * max(n)
+        kap, e = opp.energyspectrum(u, so64, kmax=kdiag)
+        assert abs(e.sum() - total) < (1e-12 if T is np.float64 else 1e-6)
+        assert np.linalg.norm(e - target) <= (1e-10 if T is np.float64 else 1e-5) * np.linalg.norm(target)
+        # ghost cells are the periodic images (apply_bc_u!)
+        assert np.array_equal(u[0], u[-2]) and np.array_equal(u[-1], u[1])
+    # same seed: the same noise bit for bit; the shell sums are accumulated with atomics, so the rescaling factors
+    # (and the field) agree to round-off rather than bitwise
+    assert rel_l2(fields[0], fields[1]) < (1e-13 if T is np.float64 else 1e-6)
+    assert rel_l2(fields[0], fields[2]) > 0.5

@@ -64,11 +64,22 @@ def _worker(rank, world, port, q):
         # bad decompositions are refused
         with pytest.raises(ValueError):
             I.Setup((x[0], x[1], np.linspace(0, 1, 8)), bcs, rank=rank, world=world, nccl_id=nid)
-        with pytest.raises(ValueError):
-            I.Setup(x, {"u": ((I.PeriodicBC(), I.PeriodicBC()),) * 2 + ((I.DirichletBC(), I.DirichletBC()),)},
+        with pytest.raises(ValueError):  # a pressure boundary in the decomposed direction shifts the DOF ranges
+            I.Setup(x, {"u": ((I.PeriodicBC(), I.PeriodicBC()),) * 2 + ((I.DirichletBC(), I.PressureBC()),)},
                     rank=rank, world=world, nccl_id=nid)
+        with pytest.raises(ValueError):
+            I.Setup(x, {"u": ((I.PeriodicBC(), I.PeriodicBC()),) * 2 + ((I.PeriodicBC(), I.DirichletBC()),)},
+                    rank=rank, world=world, nccl_id=nid)
+        # walls in the decomposed direction (BASELINE config 4): the wall-normal velocity DOFs exclude the last
+        # interior plane, which only the last rank owns; the other DOF ranges tile the interior as before
+        sw = I.Setup(x, {"u": ((I.PeriodicBC(), I.PeriodicBC()),) * 2 + ((I.DirichletBC(), I.DirichletBC()),),
+                         "temp": ((I.PeriodicBC(), I.PeriodicBC()),) * 2 + ((I.DirichletBC(1.0), I.DirichletBC(0.0)),)},
+                     rank=rank, world=world, nccl_id=nid)
+        lo, hi = sw.local_range(sw.Iu[2][2], 2)
+        assert (lo, hi) == (1, sw.nzl + 1 - (1 if rank == world - 1 else 0))
+        assert sw.local_range(sw.Iu[0][2], 2) == (1, sw.nzl + 1) and sw.local_range(sw.Ip[2], 2) == (1, sw.nzl + 1)
         q.put((rank, "ok"))
-    except Exception as e:  # noqa: BLE001
+    except BaseException as e:  # noqa: BLE001  (pytest's Failed derives from BaseException)
         q.put((rank, repr(e)))
     finally:
         dist.destroy_process_group()
