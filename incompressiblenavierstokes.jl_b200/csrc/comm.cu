@@ -360,6 +360,11 @@ int comm_sum_double(Comm *c, double *value, cudaStream_t st) {
     return 0;
 }
 
+int comm_sum_doubles(Comm *c, double *values, int n, cudaStream_t st) {
+    INSB_NCCL(g_nccl.AllReduce(values, values, (size_t)n, ncclDouble, ncclSum, c->comm, st));
+    return 0;
+}
+
 // ---- peer flags ---------------------------------------------------------------------------
 struct PeerPtrs {
     unsigned *p[8];

@@ -82,6 +82,7 @@ int comm_halo_launches(const Comm *c);  // kernels of this library per halo exch
 int comm_all_to_all(Comm *c, const void *send, void *recv, size_t block_bytes, cudaStream_t st);
 int comm_reduce_scratch(Comm *c, double *scratch, bool is_min, cudaStream_t st);
 int comm_sum_double(Comm *c, double *value, cudaStream_t st);  // in-place all-reduce(sum) of one device double
+int comm_sum_doubles(Comm *c, double *values, int n, cudaStream_t st);
 // cross-process flags in peer-mapped memory: every rank stores `epoch` into slot `rank` of the
 // flag row `row` of all ranks (after everything enqueued before on `st`), resp. waits until all
 // slots of its own row hold a value >= epoch.

@@ -1013,14 +1013,16 @@ __device__ __forceinline__ void philox4x32_10(unsigned c[4], unsigned k0, unsign
 
 // N(0, 1) into the interior of `ncomp` ghosted scalar fields: four values per counter, interior cell q of
 // component c comes from counter (q / 4, c) -- independent of the launch shape
+// (q4off: counter of the first cell of this rank's slab -- the field does not depend on the decomposition)
 template <typename T>
 __global__ void __launch_bounds__(256) rf_noise_kernel(T *u, long long cs, int ncomp, int n0, int n1, int n2, long long s1,
-                                                       long long s2, unsigned long long seed) {
+                                                       long long s2, unsigned long long seed, long long q4off) {
     const long long total4 = ((long long)n0 * n1 * n2 + 3) / 4;
     const long long q4 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const int c = blockIdx.y;
     if (q4 >= total4 || c >= ncomp) return;
-    unsigned ctr[4] = {(unsigned)q4, (unsigned)(q4 >> 32), (unsigned)c, 0x1234567u};
+    const long long g4 = q4 + q4off;
+    unsigned ctr[4] = {(unsigned)g4, (unsigned)(g4 >> 32), (unsigned)c, 0x1234567u};
     philox4x32_10(ctr, (unsigned)seed, (unsigned)(seed >> 32));
     double z[4];
 #pragma unroll
@@ -1047,6 +1049,9 @@ struct RfGeom {
     double h[3];
     int kmax;
     double escale;  // 1 / (2 Ntot^2)
+    // spectral array of this rank: [n2][n1l][m0p], row iy stands for ky index iy + ky0 (one GPU: n1l = n1, ky0 = 0;
+    // decomposed: the ky-slab of this rank after the transpose)
+    int n1l, ky0;
 };
 
 template <typename T>
@@ -1068,13 +1073,14 @@ __global__ void __launch_bounds__(256) rf_project_kernel(Cx<T> *U0, Cx<T> *U1, C
     extern __shared__ double bins[];
     for (int i = threadIdx.x; i <= g.kmax; i += blockDim.x) bins[i] = 0.0;
     __syncthreads();
-    const long long total = (long long)g.m0 * g.n1 * g.n2;
+    const long long total = (long long)g.m0 * g.n1l * g.n2;
     for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
         const int kx = (int)(q % g.m0);
-        const int iy = (int)((q / g.m0) % g.n1), iz = (int)(q / ((long long)g.m0 * g.n1));
+        const int iyl = (int)((q / g.m0) % g.n1l), iz = (int)(q / ((long long)g.m0 * g.n1l));
+        const int iy = iyl + g.ky0;
         const int ky = iy < (g.n1 + 1) / 2 ? iy : iy - g.n1;
         const int kz = g.D == 3 ? (iz < (g.n2 + 1) / 2 ? iz : iz - g.n2) : 0;
-        const long long at = kx + (long long)iy * g.m0p + (long long)iz * g.m0p * g.n1;
+        const long long at = kx + (long long)iyl * g.m0p + (long long)iz * g.m0p * g.n1l;
         Cx<T> u[3] = {U0[at], U1[at], g.D == 3 ? U2[at] : Cx<T>{T(0), T(0)}};
         Cx<T> m[3] = {rf_symbol<T>(kx, g.n0, g.h[0]), rf_symbol<T>(ky, g.n1, g.h[1]),
                       g.D == 3 ? rf_symbol<T>(kz, g.n2, g.h[2]) : Cx<T>{T(0), T(0)}};
@@ -1116,10 +1122,10 @@ __global__ void rf_factor_kernel(const double *e0, const double *eshell, int kma
 
 template <typename T>
 __global__ void __launch_bounds__(256) rf_scale_kernel(Cx<T> *U0, Cx<T> *U1, Cx<T> *U2, RfGeom g, const T *__restrict__ factor) {
-    const long long total = (long long)g.m0p * g.n1 * g.n2;
+    const long long total = (long long)g.m0p * g.n1l * g.n2;
     for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
         const int kx = (int)(q % g.m0p);
-        const int iy = (int)((q / g.m0p) % g.n1), iz = (int)(q / ((long long)g.m0p * g.n1));
+        const int iy = (int)((q / g.m0p) % g.n1l) + g.ky0, iz = (int)(q / ((long long)g.m0p * g.n1l));
         const int ky = iy < (g.n1 + 1) / 2 ? iy : iy - g.n1;
         const int kz = g.D == 3 ? (iz < (g.n2 + 1) / 2 ? iz : iz - g.n2) : 0;
         const int kap = rf_shell((long long)kx * kx + (long long)ky * ky + (long long)kz * kz);
@@ -1158,7 +1164,12 @@ static int random_field_t(Poisson *ps, T *u, long long cs, const double *e0_host
         return 1;
     }
     rg.escale = 1.0 / (2.0 * np * np);
-    const size_t wb = (size_t)g.m0p * ps->n[1] * rg.n2 * sizeof(Cx<T>);
+    rg.n1l = ps->n[1], rg.ky0 = 0;
+    const int world = comm_world(ps->comm), rank = comm_rank(ps->comm);
+    const int nzl = ps->nzl, kyl = ps->kyl;
+    if (ps->comm) rg.n1l = kyl, rg.ky0 = rank * kyl;
+    // (decomposed: [n3][kyl][m0p] holds as many elements as the slab's [nzl][n1][m0p])
+    const size_t wb = (size_t)g.m0p * ps->n[1] * (ps->comm ? nzl : rg.n2) * sizeof(Cx<T>);
     void *tmp[2] = {nullptr, nullptr};
     double *dsh = nullptr;
     T *dfac = nullptr;
@@ -1175,20 +1186,89 @@ static int random_field_t(Poisson *ps, T *u, long long cs, const double *e0_host
         set_error("random_field: cudaMalloc of the spectral work arrays failed");
         return 1;
     }
-    Cx<T> *U[3] = {(Cx<T> *)ps->W, (Cx<T> *)tmp[0], D == 3 ? (Cx<T> *)tmp[1] : (Cx<T> *)tmp[0]};
+    void *tmp3 = nullptr;  // decomposed: W is the slab-side workspace of every transform, so three more arrays
+    if (ps->comm && cudaMalloc(&tmp3, wb) != cudaSuccess) {
+        cleanup();
+        set_error("random_field: cudaMalloc of the spectral work arrays failed");
+        return 1;
+    }
+    Cx<T> *U[3] = {ps->comm ? (Cx<T> *)tmp3 : (Cx<T> *)ps->W, (Cx<T> *)tmp[0], D == 3 ? (Cx<T> *)tmp[1] : (Cx<T> *)tmp[0]};
     T *R0 = u;
     for (int a = 0; a < D; a++) R0 += ps->ioff[a] * rs[a];
     const T *e0 = (const T *)ps->eig[0];
     int rc = 0;
+    // ---- decomposed transforms (plain block layouts; the same transposes as the solve, poisson_solve) ----
+    const long long m0p = g.m0p, blk = m0p * kyl * nzl;
+    int sh = 0, shz = 0;
+    while ((1 << sh) < kyl) sh++;
+    while ((1 << shz) < nzl) shz++;
+    FastGeom gx = g;
+    gx.n[2] = nzl;
+    // all ranks have passed this point of the stream (flag row `row`): buffers written by peers may be reused
+    auto sync_ranks = [&](int row) -> int {
+        if (ps->p2p) {
+            INSB_TRY(comm_signal_peers(ps->peerFlags, row, rank, world, ps->epoch, L.stream));
+            return comm_wait_flags(ps->flags, row, world, ps->epoch, ps->flags + 16, L.stream);
+        }
+        return 0;  // NCCL all-to-all calls are collective and stream ordered
+    };
+    auto forward_slab = [&](T *R, Cx<T> *dst) -> int {  // slab of one component -> dst = [n3][kyl][m0p]
+        INSB_TRY(fast_pass<T>(3, ps->n[0], R, ps->W, gx, 0, ps->tw[0], e0, e0, e0, T(1), 0, L));
+        FastGeom gy = g;
+        gy.nother = nzl, gy.in = ps->W, gy.out = ps->S;
+        gy.out_sd = m0p, gy.out_os = m0p * kyl, gy.out_sh = sh, gy.out_blk = blk;
+        ps->epoch++;
+        if (ps->p2p) {
+            gy.use_outp = 1;
+            for (int s2 = 0; s2 < world; s2++) gy.outp[s2] = (Cx<T> *)ps->peerRv[s2] + (long long)rank * blk;
+        }
+        INSB_TRY(fast_pass<T>(0, ps->n[1], R, ps->W, gy, 1, ps->tw[1], e0, e0, e0, T(1), 0, L));
+        if (ps->p2p)
+            INSB_TRY(sync_ranks(0));
+        else
+            INSB_TRY(comm_all_to_all(ps->comm, ps->S, ps->Rv, (size_t)blk * sizeof(Cx<T>), L.stream));
+        FastGeom gz = g;
+        gz.nother = kyl, gz.in = ps->Rv, gz.out = dst;
+        gz.in_sd = gz.out_sd = m0p * kyl, gz.in_os = gz.out_os = m0p;
+        INSB_TRY(fast_pass<T>(0, ps->n[2], R, ps->W, gz, 2, ps->tw[2], e0, e0, e0, T(1), 0, L));
+        return sync_ranks(1);  // everybody has read its Rv: the next component may store into it
+    };
+    auto inverse_slab = [&](Cx<T> *src, T *R) -> int {  // src = [n3][kyl][m0p] -> slab of one component
+        FastGeom gz = g;
+        gz.nother = kyl, gz.in = src, gz.out = ps->Rv;
+        gz.in_sd = gz.out_sd = m0p * kyl, gz.in_os = gz.out_os = m0p;
+        ps->epoch++;
+        if (ps->p2p) {  // z index k -> owner k / nzl, whose S holds [source rank][z local][ky local][kx]
+            gz.use_outp = 1, gz.out_sh = shz, gz.out_sd = m0p * kyl, gz.out_os = m0p;
+            for (int s2 = 0; s2 < world; s2++) gz.outp[s2] = (Cx<T> *)ps->peerS[s2] + (long long)rank * blk;
+        }
+        INSB_TRY(fast_pass<T>(1, ps->n[2], R, ps->W, gz, 2, ps->tw[2], e0, e0, e0, T(1), 0, L));
+        if (ps->p2p)
+            INSB_TRY(sync_ranks(1));
+        else
+            INSB_TRY(comm_all_to_all(ps->comm, ps->Rv, ps->S, (size_t)blk * sizeof(Cx<T>), L.stream));
+        FastGeom gi = g;
+        gi.nother = nzl, gi.in = ps->S, gi.out = ps->W;
+        gi.in_sd = m0p, gi.in_os = m0p * kyl, gi.in_sh = sh, gi.in_blk = blk;
+        INSB_TRY(fast_pass<T>(1, ps->n[1], R, ps->W, gi, 1, ps->tw[1], e0, e0, e0, T(1), 0, L));
+        INSB_TRY(fast_pass<T>(4, ps->n[0], R, ps->W, gx, 0, ps->tw[0], e0, e0, e0, T(1), 0, L));
+        return sync_ranks(0);  // everybody has read its S
+    };
     auto run = [&]() -> int {
         if (fill) {
-            const long long total4 = ((long long)rg.n0 * rg.n1 * rg.n2 + 3) / 4;
+            const int n2l = ps->comm ? nzl : rg.n2;
+            const long long total4 = ((long long)rg.n0 * rg.n1 * n2l + 3) / 4;
             dim3 gr((unsigned)((total4 + 255) / 256), D);
-            rf_noise_kernel<T><<<gr, 256, 0, L.stream>>>(R0, cs, D, rg.n0, rg.n1, rg.n2, rs[1], rs[2], seed);
+            rf_noise_kernel<T><<<gr, 256, 0, L.stream>>>(R0, cs, D, rg.n0, rg.n1, n2l, rs[1], rs[2], seed,
+                                                         (long long)rank * nzl * rg.n0 * rg.n1 / 4);
             if (L.counter) ++*L.counter;
         }
         for (int c = 0; c < D; c++) {
             T *R = R0 + c * cs;
+            if (ps->comm) {
+                INSB_TRY(forward_slab(R, U[c]));
+                continue;
+            }
             INSB_TRY(fast_pass<T>(3, ps->n[0], R, U[c], g, 0, ps->tw[0], e0, e0, e0, T(1), 0, L));
             INSB_TRY(fast_pass<T>(0, ps->n[1], R, U[c], g, 1, ps->tw[1], e0, e0, e0, T(1), 0, L));
             if (D == 3) INSB_TRY(fast_pass<T>(0, ps->n[2], R, U[c], g, 2, ps->tw[2], e0, e0, e0, T(1), 0, L));
@@ -1197,12 +1277,17 @@ static int random_field_t(Poisson *ps, T *u, long long cs, const double *e0_host
         INSB_CUDA(cudaMemcpyAsync(dsh + nshell, e0_host, (size_t)nshell * sizeof(double), cudaMemcpyHostToDevice, L.stream));
         const size_t sm = (size_t)nshell * sizeof(double);
         rf_project_kernel<T><<<148 * 4, 256, sm, L.stream>>>(U[0], U[1], U[2], rg, dsh);
+        if (ps->comm) INSB_TRY(comm_sum_doubles(ps->comm, dsh, nshell, L.stream));
         rf_factor_kernel<T><<<1, 256, 0, L.stream>>>(dsh + nshell, dsh, rg.kmax, 1.0 / np, dfac);
         rf_scale_kernel<T><<<148 * 8, 256, 0, L.stream>>>(U[0], U[1], U[2], rg, dfac);
         if (L.counter) *L.counter += 3;
         INSB_CUDA(cudaGetLastError());
         for (int c = 0; c < D; c++) {
             T *R = R0 + c * cs;
+            if (ps->comm) {
+                INSB_TRY(inverse_slab(U[c], R));
+                continue;
+            }
             if (D == 3) INSB_TRY(fast_pass<T>(1, ps->n[2], R, U[c], g, 2, ps->tw[2], e0, e0, e0, T(1), 0, L));
             INSB_TRY(fast_pass<T>(1, ps->n[1], R, U[c], g, 1, ps->tw[1], e0, e0, e0, T(1), 0, L));
             INSB_TRY(fast_pass<T>(4, ps->n[0], R, U[c], g, 0, ps->tw[0], e0, e0, e0, T(1), 0, L));
@@ -1211,13 +1296,14 @@ static int random_field_t(Poisson *ps, T *u, long long cs, const double *e0_host
     };
     rc = run();
     cleanup();
+    cudaFree(tmp3);
     return rc;
 }
 
 int poisson_random_field(Poisson *ps, void *u, long long cs, const double *e0_host, int nshell, int fill,
                          unsigned long long seed, const double xlims[3][2], Launch L) {
-    if (!ps || !ps->fast || ps->comm) {
-        set_error("random_field needs a single-GPU psolver_spectral plan on a power-of-two periodic grid");
+    if (!ps || !ps->fast || (ps->comm && ps->D != 3)) {
+        set_error("random_field needs a psolver_spectral plan on a power-of-two periodic grid");
         return 1;
     }
     if (nshell < 1 || nshell > 4096) {

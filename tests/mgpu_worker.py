@@ -153,7 +153,17 @@ def run_case(args, case, rank, world, quiet=False):
     res["tke"] = float(I.total_kinetic_energy(st["state"]["u"], sd, plan=psd.plan))
     res["vort"] = I.gather_global(sd, I.vorticity(st["state"]["u"], sd))
 
+    # random_field synthesised on the slabs (distributed transforms, all-reduced shell sums): injected host noise
+    # and the device generator, which is keyed by the GLOBAL cell index
+    if case == "periodic":
+        for tag, r in (("host_noise", np.random.default_rng(11)), ("device_noise", 1234)):
+            res["rf_" + tag] = I.gather_global(sd, I.random_field(sd, 0.0, totalenergy=0.5, kpeak=4, rng=r, psolver=psd))
+
     if rank == 0:
+        if case == "periodic":
+            for tag, r in (("host_noise", np.random.default_rng(11)), ("device_noise", 1234)):
+                f1 = I.to_host(I.random_field(s1, 0.0, totalenergy=0.5, kpeak=4, rng=r, psolver=ps1))
+                report("random_field_" + tag, rel(res["rf_" + tag], f1), 1e-13 if T is np.float64 else 2e-6)
         u1 = I.to_device(s1, ug)
         I.apply_bc_u_(u1, 0.0, s1)
         p1 = I.scalarfield(s1)
