@@ -200,8 +200,12 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
         "steps_requested": args.steps, "warmup": warm, "ms_per_step": 1e3 * tot / done, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": f"TaylorGreenVortex3D {args.n}^3 periodic {args.dtype} RK44 psolver_spectral",
-                   "sample": f"{n}^3 grid" + ("" if n == args.n else " (bounded CPU sample of the same workload)")},
+        "config": {"workload": (f"TaylorGreenVortex3D {args.n}^3 periodic {args.dtype} RK44 psolver_spectral" if args.gpus == 1 else
+                                "DecayingTurbulence3D periodic %s RK44 psolver_spectral, weak-scaling series with %d^3 cells per GPU"
+                                % (args.dtype, args.n)),
+                   "sample": f"{n}^3 grid" + ("" if n == args.n else " (bounded CPU sample of the same workload)")
+                   + ("" if args.gpus == 1 else "; one GPU's share of the box, stepped from the Taylor-Green field "
+                      "(the cost per cell of the operator sequence does not depend on the field)")},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -235,10 +239,20 @@ def run_gpu(args):
     nid = I.share_unique_id() if world > 1 else None
     sg = I.Setup(x, {"u": ((I.PeriodicBC(), I.PeriodicBC()),) * 3}, rank=rank, world=world, nccl_id=nid)
     ps = I.psolver_spectral(sg)
-    u = I.velocityfield(sg, tgv3d_u, psolver=ps)
+    # N = 1: BASELINE config[1], the Taylor-Green vortex; N > 1: config[2], DecayingTurbulence3D -- the random_field
+    # initial condition of examples/DecayingTurbulence3D.jl:31 (Orlandi spectrum, total energy 1), synthesised on the
+    # slabs by the library (insb200_random_field, noise keyed by the global cell index)
+    decaying = args.workload == "decaying" or (args.workload == "auto" and world > 1)
+    if decaying:
+        u = I.random_field(sg, 0.0, rng=20261018, psolver=ps)
+        umax0 = I.maxabs(u, sg, plan=ps.plan)
+    else:
+        u = I.velocityfield(sg, tgv3d_u, psolver=ps)
+        umax0 = 0.5
     method = I.RKMethods.RK44(T)
     params = dict(viscosity=NU)
-    dt = T(fixed_dt(max(dims)))  # eltype(u): the stage combine then stays in the field type
+    # eltype(u): the stage combine then stays in the field type
+    dt = T(fixed_dt(max(dims)) if not decaying else 0.5 * min((1.0 / max(dims)) ** 2 / NU / 6, 1.0 / max(dims) / umax0))
     stepper = I.create_stepper(method, setup=sg, psolver=ps, state={"u": u}, t=0.0)
     ke0 = float(I.total_kinetic_energy(u, sg, plan=ps.plan))
 
@@ -285,7 +299,7 @@ def run_gpu(args):
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms = float(tms.item())
     umax = I.maxabs(stepper["state"]["u"], sg, plan=ps.plan)
-    assert np.isfinite(umax) and 0 < umax < 10, f"solution blew up: max|u| = {umax}"
+    assert np.isfinite(umax) and 0 < umax < 4 * umax0 + 1, f"solution blew up: max|u| = {umax}"
     # ---- self-check of the state the timed steps produced (a wrong halo / transpose that stays finite
     # would still break these): post-projection divergence at round-off level, and the kinetic energy
     # of the Taylor-Green vortex against its viscous decay KE(0) exp(-2 nu |k|^2 t), |k|^2 = 12 pi^2
@@ -300,13 +314,20 @@ def run_gpu(args):
         max_div = float(td.item())
     ke = float(I.total_kinetic_energy(stepper["state"]["u"], sg, plan=ps.plan))
     t_end = float(stepper["t"])
-    ke_expected = ke0 * float(np.exp(-2.0 * NU * 12.0 * np.pi**2 * t_end))
     eps = float(np.finfo(T).eps)
     selfcheck = {"t": t_end, "max_abs_u": umax, "max_div_after_projection": max_div,
-                 "max_div_bound": 50 * eps * umax * max(dims), "kinetic_energy": ke, "kinetic_energy_t0": ke0,
-                 "kinetic_energy_expected": ke_expected, "kinetic_energy_rel_dev": abs(ke / ke_expected - 1.0)}
+                 "max_div_bound": 50 * eps * umax * max(dims), "kinetic_energy": ke, "kinetic_energy_t0": ke0}
     assert max_div < selfcheck["max_div_bound"], f"projected field is not divergence free: {selfcheck}"
-    assert selfcheck["kinetic_energy_rel_dev"] < 1e-3, f"kinetic energy off the Taylor-Green decay: {selfcheck}"
+    if decaying:
+        # no closed form: the energy-conserving scheme can only lose energy through viscosity; the synthesised
+        # field starts at the prescribed total energy 1 (random_field) and decays slowly over these few steps
+        selfcheck["kinetic_energy_target_t0"] = 1.0
+        assert abs(ke0 - 1.0) < 1e-3, f"random_field missed its total energy: {selfcheck}"
+        assert 0.9 * ke0 < ke < ke0, f"kinetic energy did not decay monotonically: {selfcheck}"
+    else:
+        ke_expected = ke0 * float(np.exp(-2.0 * NU * 12.0 * np.pi**2 * t_end))
+        selfcheck.update(kinetic_energy_expected=ke_expected, kinetic_energy_rel_dev=abs(ke / ke_expected - 1.0))
+        assert selfcheck["kinetic_energy_rel_dev"] < 1e-3, f"kinetic energy off the Taylor-Green decay: {selfcheck}"
 
     cells = int(np.prod(dims))  # one z-slab of the global grid per GPU
     value = cells * args.steps / (ms * 1e-3)
@@ -471,10 +492,11 @@ def run_gpu(args):
             assert ok, f"{world}-GPU result differs from the 1-GPU result: {rows}"
 
     if rank == 0:
-        wl = f"TaylorGreenVortex3D {dims[0]}x{dims[1]}x{dims[2]} periodic {args.dtype} RK44 psolver_spectral"
+        name = "DecayingTurbulence3D" if decaying else "TaylorGreenVortex3D"
+        wl = f"{name} {dims[0]}x{dims[1]}x{dims[2]} periodic {args.dtype} RK44 psolver_spectral"
         if world > 1:
-            wl += (f" (weak-scaling series of BASELINE config[1]: {n}^3 cells per GPU; the cost per cell equals "
-                   "config[2] DecayingTurbulence3D, whose random_field initial condition this run does not use)")
+            wl += (f" (weak-scaling series: {n}^3 cells per GPU, BASELINE config[2] at 8 GPUs"
+                   + (", random_field initial condition synthesised on the slabs)" if decaying else ")"))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -507,6 +529,8 @@ def main():
     ap.add_argument("--ref-budget", type=float, default=150.0, help="seconds of CPU stepping of --impl reference")
     ap.add_argument("--no-check", action="store_true", help="skip the full-size parity leg against the oracle")
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "tgv", "decaying"],
+                    help="auto: Taylor-Green vortex on one GPU (config[1]), decaying turbulence on several (config[2])")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -48,7 +48,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", nargs="+", default=["cfg1", "cfg4", "cfg5"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink every extent (tests)")
-    ap.add_argument("--world", type=int, default=1, help="cfg5 only: z-slab decomposition (run under torchrun)")
+    ap.add_argument("--world", type=int, default=1, help="cfg4 / cfg5: z-slab decomposition (run under torchrun)")
     a = ap.parse_args()
     import insb200 as I
 
@@ -95,14 +95,15 @@ def main():
             x = (np.linspace(0, np.pi, n[0] + 1).astype(T), np.linspace(0, 1, n[1] + 1).astype(T),
                  np.linspace(0, 1, n[2] + 1).astype(T))
             sg = I.Setup(x, {"u": ((P(), P()), (D(), D()), (D(), D())),
-                             "temp": ((P(), P()), (S(), S()), (D(1.0), D(0.0)))})
+                             "temp": ((P(), P()), (S(), S()), (D(1.0), D(0.0)))}, rank=rank, world=a.world, nccl_id=nid)
             ps = I.psolver_transform(sg)
             u = I.vectorfield(sg)
             temp = I.temperaturefield(sg, lambda x, y, z: 0.5 + np.sin(20 * x) * np.sin(np.pi * 20 * y) / 100 + 0 * z)
             params = dict(viscosity=2.5e-4, conductivity=2.5e-4, gravity=1.0, gdir=2, dodissipation=True)
             for mname, m in (("RK44", I.RKMethods.RK44(T)), ("LMWray3", I.LMWray3(T))):
-                run(f"cfg4 RayleighBenard3D {mname}", sg, ps, {"u": u.clone(), "temp": temp.clone()}, m, I.boussinesq_,
-                    params, T(1e-3), 5)
+                run(f"cfg4 RayleighBenard3D {mname} {np.dtype(T).name} ({a.world} GPU)", sg, ps,
+                    {"u": u.clone(), "temp": temp.clone()}, m, I.boussinesq_, params, T(1e-3), 5)
+            I.release_plans(sg)
             del sg, ps, u, temp
             torch.cuda.empty_cache()
     if "cfg5" in a.cases:  # examples/ChannelFlow.jl:33-167
