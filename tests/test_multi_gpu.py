@@ -21,7 +21,9 @@ def _ngpu():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("grid,dtype,case", [((64, 32, 64), "f64", "periodic"), ((128, 64, 128), "f32", "periodic"),
-                                             ((64, 24, 64), "f64", "channel"), ((128, 32, 64), "f32", "channel")])
+                                             ((64, 24, 64), "f64", "channel"), ((128, 32, 64), "f32", "channel"),
+                                             ((64, 32, 64), "f64", "rb"), ((128, 64, 128), "f32", "rb"),
+                                             ((64, 32, 64), "f64", "all")])
 def test_slab_equals_single_gpu(grid, dtype, case):
     n = _ngpu()
     if n < 2:
