@@ -413,7 +413,7 @@ int fused_stage_and_solve(insb200_plan *pl, const FusedStage<T> &st_in, bool ct_
     if (pl->comm) {
         Scope sc(pl, L.stream, 4);
         INSB_TRY(fused_halo<T>(pl, st.v_out, 3, L));
-        if (st.acc_out) INSB_TRY(fused_halo<T>(pl, st.acc_out, 3, L));
+        if (st.acc_out && st.acc_halo) INSB_TRY(fused_halo<T>(pl, st.acc_out, 3, L));
     }
     const FusedLayout &FL = pl->fctx.L;
     PoissonIO io{};
@@ -533,6 +533,7 @@ int step_rk_t(insb200_plan *pl, const double *A, const double *c, int s, int coe
             }
             if (!last) {
                 st.acc_out = (T *)pl->FACC;
+                st.acc_halo = i == s - 2;  // the last stage reads the accumulator as its vbase
                 st.ca = coef(s - 1, i);
                 if (i > 0) {
                     st.vbase_ref = U;
@@ -639,6 +640,7 @@ int step_wray_t(insb200_plan *pl, T *U, T *TU, double t, double dt, const insb20
             if (i == 0) {  // statestart += b[0] dt k; v = u + a[0] dt k
                 st.u_ref = U;
                 st.acc_out = (T *)pl->FACC;
+                st.acc_halo = true;  // stages 2 and 3 read it as their vbase
                 st.ca = (double)(T)((double)b3[0] * dt);
             } else {
                 st.v_in = (const T *)pl->FV[(i - 1) & 1];

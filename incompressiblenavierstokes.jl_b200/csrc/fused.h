@@ -57,6 +57,7 @@ struct FusedStage {
     const T *v_in = nullptr, *p_in = nullptr;
     const T *vbase_ref = nullptr, *vbase_int = nullptr, *acc_in = nullptr;
     T *v_out = nullptr, *acc_out = nullptr, *d_out = nullptr;
+    bool acc_halo = false;  // slab mode: a later stage reads acc_out as vbase_int (on its z halo too): exchange its ghost planes
     double cv = 0, ca = 0, nu = 0;
     double bodyforce[3] = {0, 0, 0};
 };

@@ -498,6 +498,32 @@ function INS.solve_unsteady_b200(; setup, tlims, start, force!::BuiltinForce = n
     (; state..., t = typeof(tstart)(tout[])), outputs
 end
 
+# random_field(setup, t; profile, totalenergy, rng)   (src/initializers.jl:109-183) on the device: the white noise is
+# the caller's (`rng`: `randn!` into view(u, Ip, α), the reference's stream) or generated by the library from `seed`;
+# the profile closure is evaluated here on the shells 0:kdiag.
+function INS.random_field_b200(setup, psolver::B200PSolver, t = zero(eltype(setup.x[1]));
+        profile = INS.orlandi_profile, totalenergy = one(eltype(setup.x[1])), rng = nothing, seed = rand(UInt64), kwargs...)
+    (; Np, Ip) = setup
+    T = eltype(setup.x[1])
+    D = length(Np)
+    kdiag = isqrt(sum(α -> (Np[α] ÷ 2)^2, 1:D))
+    prof = [T(profile(T(κ); kwargs...)) for κ = 0:kdiag]
+    e0 = Float64[Float64(T(totalenergy) * p / sum(prof)) for p in prof]
+    u = INS.vectorfield(setup)
+    fill = isnothing(rng)
+    if !fill
+        v = similar(setup.x[1], Np)
+        for α = 1:D
+            INS.Random.randn!(rng, v)
+            copyto!(view(u, Ip, α), v)
+        end
+    end
+    check(ccall((:insb200_random_field, libinsb200), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cdouble}, Cint, Cint, Culonglong, Cdouble, Ptr{Cvoid}),
+        psolver.plan, devptr(u), e0, length(e0), Cint(fill), UInt64(seed), Float64(t), stream()))
+    u
+end
+
 # right_hand_side!(dudt, u, params_ref, t)   (src/sciml.jl:35-48)
 function INS.right_hand_side!(dudt::CuArray, u::CuArray, params_ref::Base.RefValue{<:Tuple{Any,<:B200PSolver,Any}}, t)
     setup, psolver, viscosity = params_ref[]
