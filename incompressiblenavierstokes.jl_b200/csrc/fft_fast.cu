@@ -144,7 +144,8 @@ struct LineSmem {
     Cx<T> *buf[2];
 };
 
-template <typename T, int N, bool INV, int S, int ES, int SH = 3>
+// TW7: all seven radix-8 twiddles from the table (strided passes) instead of three loads + four products
+template <typename T, int N, bool INV, int S, int ES, int SH = 3, bool TW7 = (ES > 1)>
 __device__ __forceinline__ void fft_stages(Cx<T> (&v)[8], int t, const LineSmem<T> &sm,
                                            const Cx<T> *__restrict__ tw, int &exch) {
     typedef Ops<T> O;
@@ -172,7 +173,7 @@ __device__ __forceinline__ void fft_stages(Cx<T> (&v)[8], int t, const LineSmem<
                 v[b + 3 * B] = O::mul(v[b + 3 * B], w3);
             } else {
                 Cx<T> w1, w2, w3, w4, w5, w6, w7;
-                if constexpr (ES > 1) {
+                if constexpr (TW7) {
                     // strided passes (the lanes of a warp run over lines: k takes four values per warp, the loads
                     // are broadcasts): all seven powers straight from the table (r k TSTEP < N) -- four more L1
                     // hits instead of four complex products, every twiddle the correctly rounded table entry
@@ -230,7 +231,7 @@ __device__ __forceinline__ void fft_stages(Cx<T> (&v)[8], int t, const LineSmem<
             for (int m = 0; m < 8; m++) v[m] = buf[spx<SH>(t + P * m) * ES];
         }
         exch++;
-        fft_stages<T, N, INV, S + 1, ES, SH>(v, t, sm, tw, exch);
+        fft_stages<T, N, INV, S + 1, ES, SH, TW7>(v, t, sm, tw, exch);
     }
 }
 
@@ -303,7 +304,9 @@ __global__ void __launch_bounds__(StridedShape<T, N>::NT, (sizeof(T) == 4 && Str
         for (int m = 0; m < 8; m++) v[m] = ip[m * step];
     }
     int exch = 0;
-    if (MODE == 0 || MODE >= 2) fft_stages<T, N, false, 0, L>(v, t, sm, tw, exch);
+    // (the generalised middle pass spills at its 64-register cap with seven live twiddles: it keeps the products)
+    constexpr bool TW7 = !(MODE == 2 && (BLK || N > 512));
+    if (MODE == 0 || MODE >= 2) fft_stages<T, N, false, 0, L, 3, TW7>(v, t, sm, tw, exch);
     if (MODE >= 2) {
         // phat = -phat / ((ax + ay) + az), phat[1] = 0 (pressure.jl:360-372); `factor` carries
         // the sign and the 1/prod(Np) of the inverse transform.
@@ -320,7 +323,7 @@ __global__ void __launch_bounds__(StridedShape<T, N>::NT, (sizeof(T) == 4 && Str
             v[m] = Ops<T>::scale(v[m], f);
         }
     }
-    if (MODE >= 1) fft_stages<T, N, true, 0, L>(v, t, sm, tw, exch);
+    if (MODE >= 1) fft_stages<T, N, true, 0, L, 3, TW7>(v, t, sm, tw, exch);
     if (BLK) {
         const int out_mask = (1 << g.out_sh) - 1;
         if (g.use_outp) {  // tile-by-tile stores straight into the peers' buffers (NVLink P2P)
@@ -439,7 +442,8 @@ __global__ void __launch_bounds__(StridedShape<T, N>::NT, (sizeof(T) == 4 && Str
         sm.buf[0] = X + l;
         sm.buf[1] = B + l;
         int exch = 0;
-        if (MODE == 0 || MODE >= 2) fft_stages<T, N, false, 0, L>(v, t, sm, tw, exch);
+        constexpr bool TW7 = !(MODE == 2 && N > 512);  // (64-register cap of the 1024-thread blocks)
+        if (MODE == 0 || MODE >= 2) fft_stages<T, N, false, 0, L, 3, TW7>(v, t, sm, tw, exch);
         if (MODE >= 2) {
             const T e01 = e0[kx] + (tdim == 1 ? T(0) : e1[other + g.eig_off]);
             const T eo2 = tdim == 1 ? e2[other + g.eig_off] : T(0);
@@ -453,7 +457,7 @@ __global__ void __launch_bounds__(StridedShape<T, N>::NT, (sizeof(T) == 4 && Str
                 v[m] = Ops<T>::scale(v[m], f);
             }
         }
-        if (MODE >= 1) fft_stages<T, N, true, 0, L>(v, t, sm, tw, exch);
+        if (MODE >= 1) fft_stages<T, N, true, 0, L, 3, TW7>(v, t, sm, tw, exch);
         Cx<T> *O = (exch & 1) ? B : X;  // the buffer the last exchange did not use
 #pragma unroll
         for (int m = 0; m < 8; m++) O[(t + P * m) * L + l] = v[m];
@@ -563,7 +567,7 @@ __global__ void __launch_bounds__(StridedShape<T, N>::NT, (sizeof(T) == 4 && Str
     }
     int exch = 0;
     if (MODE != 1) {  // DCT-II: FFT, then X_k = 2 Re(w_k F_k) for the real and the imaginary sequence
-        fft_stages<T, N, false, 0, L>(v, t, sm, tw, exch);
+        fft_stages<T, N, false, 0, L, 3, MODE != 2>(v, t, sm, tw, exch);
         exchange_rev<T, N, L>(v, vr, t, sm, exch);
 #pragma unroll
         for (int m = 0; m < 8; m++) {
@@ -594,7 +598,7 @@ __global__ void __launch_bounds__(StridedShape<T, N>::NT, (sizeof(T) == 4 && Str
                 v[m] = Cx<T>{ha.x - hb.y, ha.y + hb.x};
             }
         }
-        fft_stages<T, N, true, 0, L>(v, t, sm, tw, exch);
+        fft_stages<T, N, true, 0, L, 3, MODE != 2>(v, t, sm, tw, exch);
         const T invn = T(1) / T(N);
 #pragma unroll
         for (int m = 0; m < 8; m++) *out_at(perm(t + P * m)) = Ops<T>::scale(v[m], invn);

@@ -36,6 +36,12 @@ __device__ __forceinline__ double2 psub(double2 a, double2 b) { return make_doub
 __device__ __forceinline__ double2 pbc(double v) { return make_double2(v, v); }
 __device__ __forceinline__ double2 pmk(double a, double b) { return make_double2(a, b); }
 
+// separately rounded pair operations (never contracted into an FMA with a neighbouring operation)
+__device__ __forceinline__ float2 psub_rn(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }  // exact a - b
+__device__ __forceinline__ float2 pmul_rn(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ double2 psub_rn(double2 a, double2 b) { return make_double2(__dsub_rn(a.x, b.x), __dsub_rn(a.y, b.y)); }
+__device__ __forceinline__ double2 pmul_rn(double2 a, double2 b) { return make_double2(__dmul_rn(a.x, b.x), __dmul_rn(a.y, b.y)); }
+
 // diagonal face flux: lo, hi = u_i on the two sides of the face, mnrd = -nu/Δ_i at the face
 template <typename P>
 __device__ __forceinline__ P flux_diag(P lo, P hi, P mnrd, P quarter) {

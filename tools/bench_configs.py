@@ -94,6 +94,7 @@ def main():
             n = (sz(512), sz(512), sz(256))
             x = (np.linspace(0, np.pi, n[0] + 1).astype(T), np.linspace(0, 1, n[1] + 1).astype(T),
                  np.linspace(0, 1, n[2] + 1).astype(T))
+            nid = I.share_unique_id() if a.world > 1 else None  # (an NCCL id serves one communicator)
             sg = I.Setup(x, {"u": ((P(), P()), (D(), D()), (D(), D())),
                              "temp": ((P(), P()), (S(), S()), (D(1.0), D(0.0)))}, rank=rank, world=a.world, nccl_id=nid)
             ps = I.psolver_transform(sg)
@@ -109,6 +110,7 @@ def main():
     if "cfg5" in a.cases:  # examples/ChannelFlow.jl:33-167
         n = (sz(1024), sz(512), sz(512))
         x = (np.linspace(0, 4 * np.pi, n[0] + 1), I.tanh_grid(0.0, 2.0, n[1], 1.4), np.linspace(0, 4 * np.pi / 3, n[2] + 1))
+        nid = I.share_unique_id() if a.world > 1 else None
         sg = I.Setup(x, {"u": ((P(), P()), (D(), D()), (P(), P()))}, rank=rank, world=a.world, nccl_id=nid)
         ps = I.default_psolver(sg)
         assert ps.kind == "tridiagonal"
