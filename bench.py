@@ -402,7 +402,11 @@ def run_gpu(args):
         cc = (C.c_double * s)(*[float(v) for v in method.c])
         pr = _params(sg, viscosity=NU)
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        ptrs = (C.c_void_p * ke)(*[uh_.data_ptr() for uh_ in uhs])
+        # the ke pinned states form a ring: member m works on state m % ke, so a call with 3 ke members steps every
+        # state three times, each time through host memory (the D2H of member m precedes the H2D of member m + ke on
+        # the library's copy streams); the longer run amortises the fill and drain of the pipeline
+        nmem = 3 * ke
+        ptrs = (C.c_void_p * nmem)(*[uhs[m % ke].data_ptr() for m in range(nmem)])
 
         def host_steps(nm):
             # one call = nm independent pinned host states, each: H2D, one fused RK44 step, D2H;
@@ -422,8 +426,8 @@ def run_gpu(args):
                 el = float(tel.item())
             return el
 
-        host_steps(2)
-        el = timed(lambda: host_steps(ke))
+        host_steps(3)
+        el = timed(lambda: host_steps(nmem))
 
         # the same state stepped sequentially: every step waits for its own H2D and D2H (no overlap)
         def seq_steps():
@@ -434,13 +438,14 @@ def run_gpu(args):
         seq_steps()
         el_seq = timed(seq_steps)
         nbytes = uh.numel() * uh.element_size() * world
-        e2e = {"value": cells * ke / el, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
-               "steps": ke, "ms_per_step": 1e3 * el / ke,
+        e2e = {"value": cells * nmem / el, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+               "steps": nmem, "ms_per_step": 1e3 * el / nmem,
                "sequential": {"value": cells * ke / el_seq, "unit": UNIT, "ms_per_step": 1e3 * el_seq / ke,
                               "note": "insb200_step_rk_host on ONE state: H2D, fused RK44 step, D2H, synchronise, repeat"},
                "note": "insb200_step_rk_host_ensemble on every rank: each step = one pinned host state (slab of u) "
-                       "-> device, one fused RK44 step, device -> host; the copies of step i+1 / i-1 overlap the "
-                       "kernels of step i (3 streams); bytes summed over ranks, time = max over ranks"}
+                       "-> device, one fused RK44 step, device -> host; the copies of the neighbouring steps overlap "
+                       "the kernels of step i (3 streams, 3 device slots, a ring of %d pinned states stepped round-robin); "
+                       "bytes summed over ranks, time = max over ranks" % ke}
         assert all(np.isfinite(float(uh_.abs().max())) for uh_ in uhs)
         del uhs
 

@@ -45,7 +45,8 @@ struct insb200_plan : public insb::Profiler {
     void *TV[2] = {nullptr, nullptr}, *TACC = nullptr;
     std::vector<void *> K, TK;
     void *HU = nullptr, *HT = nullptr;  // device state of the host-buffer entry point
-    void *HU2 = nullptr, *HT2 = nullptr;  // second slot of the pipelined ensemble entry point
+    void *HU2 = nullptr, *HT2 = nullptr;  // second and
+    void *HU3 = nullptr, *HT3 = nullptr;  // third slot of the pipelined ensemble entry point
     cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of the ensemble entry point
     cudaStream_t s_graph = nullptr;                // capture / replay stream of insb200_solve_unsteady
     double *scratch = nullptr;  // reductions
@@ -959,7 +960,7 @@ int insb200_plan_destroy(insb200_plan_t *pl) {
     cudaDeviceSynchronize();
     if (pl->ps) poisson_destroy(pl->ps);
     for (void *p : {pl->V[0], pl->V[1], pl->ACC, pl->P, pl->TV[0], pl->TV[1], pl->TACC, pl->dev_tables,
-                    (void *)pl->scratch, (void *)pl->ke_partial, pl->LES_G, pl->LES_visc, pl->HU, pl->HT, pl->HU2, pl->HT2,
+                    (void *)pl->scratch, (void *)pl->ke_partial, pl->LES_G, pl->LES_visc, pl->HU, pl->HT, pl->HU2, pl->HT2, pl->HU3, pl->HT3,
                     pl->FV[0], pl->FV[1], pl->FACC, pl->FP, pl->FD, pl->FUB})
         if (p) cudaFree(p);
     if (pl->fctx.maps) fused_maps_destroy(pl->fctx.maps);
@@ -1215,12 +1216,18 @@ int insb200_step_rk_host_ensemble(insb200_plan_t *pl, const double *A, const dou
     }
     if (!pl->HU) INSB_TRY(dev_alloc(pl, &pl->HU, vb));
     if (!pl->HU2) INSB_TRY(dev_alloc(pl, &pl->HU2, vb));
+    if (nmembers > 2 && !pl->HU3) INSB_TRY(dev_alloc(pl, &pl->HU3, vb));
     if (bouss && !pl->HT) INSB_TRY(dev_alloc(pl, &pl->HT, sb));
     if (bouss && !pl->HT2) INSB_TRY(dev_alloc(pl, &pl->HT2, sb));
+    if (bouss && nmembers > 2 && !pl->HT3) INSB_TRY(dev_alloc(pl, &pl->HT3, sb));
+    // a slot is busy for H2D + steps + D2H; with the copies near the PCIe rate (2 x 29 ms for 1.6 GB each way) and a
+    // 14 ms step, two slots cap the pipeline at 37 ms per member, three let it run at the rate of one copy direction
+    const int nslot = nmembers > 2 ? 3 : 2;
+    void *slotU[3] = {pl->HU, pl->HU2, pl->HU3}, *slotT[3] = {pl->HT, pl->HT2, pl->HT3};
     if (!pl->s_in) INSB_CUDA(cudaStreamCreateWithFlags(&pl->s_in, cudaStreamNonBlocking));
     if (!pl->s_out) INSB_CUDA(cudaStreamCreateWithFlags(&pl->s_out, cudaStreamNonBlocking));
-    // three-deep pipeline over the members: H2D of member m+1 (s_in) and D2H of member m-1 (s_out)
-    // run while member m is being stepped on the caller's stream; two device slots
+    // pipeline over the members: H2D of the next members (s_in) and D2H of the previous ones (s_out) run while
+    // member m is being stepped on the caller's stream; three device slots (two for a pair of members)
     std::vector<cudaEvent_t> ev(3 * (size_t)nmembers);
     for (auto &e : ev) INSB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     int rc = 0;
@@ -1232,10 +1239,10 @@ int insb200_step_rk_host_ensemble(insb200_plan_t *pl, const double *A, const dou
         INSB_CUDA(cudaEventDestroy(start));
     }
     for (int m = 0; m < nmembers && rc == 0; m++) {
-        void *dU = (m & 1) ? pl->HU2 : pl->HU;
-        void *dT = bouss ? ((m & 1) ? pl->HT2 : pl->HT) : nullptr;
+        void *dU = slotU[m % nslot];
+        void *dT = bouss ? slotT[m % nslot] : nullptr;
         cudaEvent_t in_done = ev[3 * m], comp_done = ev[3 * m + 1], out_done = ev[3 * m + 2];
-        if (m >= 2) INSB_CUDA(cudaStreamWaitEvent(pl->s_in, ev[3 * (m - 2) + 2], 0));  // slot free again
+        if (m >= nslot) INSB_CUDA(cudaStreamWaitEvent(pl->s_in, ev[3 * (m - nslot) + 2], 0));  // slot free again
         INSB_CUDA(cudaMemcpyAsync(dU, u_hosts[m], vb, cudaMemcpyHostToDevice, pl->s_in));
         if (bouss) INSB_CUDA(cudaMemcpyAsync(dT, temp_hosts[m], sb, cudaMemcpyHostToDevice, pl->s_in));
         INSB_CUDA(cudaEventRecord(in_done, pl->s_in));
