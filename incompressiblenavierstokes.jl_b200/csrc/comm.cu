@@ -82,6 +82,18 @@ int load_nccl() {
 
 }  // namespace
 
+// How long a rank waits for a peer's flag before it gives up with a sticky launch error (__trap): 20 s, or
+// INSB200_PEER_TIMEOUT_MS (tests/mgpu_worker.py --case timeout uses a short one).
+static unsigned long long peer_timeout_ns() {
+    static unsigned long long ns = 0;
+    if (!ns) {
+        const char *e = getenv("INSB200_PEER_TIMEOUT_MS");
+        const long long ms = e ? atoll(e) : 20000;
+        ns = (unsigned long long)(ms > 0 ? ms : 20000) * 1000000ULL;
+    }
+    return ns;
+}
+
 struct Comm {
     int rank = 0, world = 1;
     ncclComm_t comm = nullptr;
@@ -213,7 +225,8 @@ template <typename V>
 __global__ void __launch_bounds__(256) halo_pull_kernel(char *dst_below, char *dst_above, size_t chunk_bytes,
                                                         size_t cs_bytes, const char *below_slot, const char *above_slot,
                                                         const unsigned *below_flag, const unsigned *above_flag,
-                                                        unsigned epoch, unsigned *timeout_flag) {
+                                                        unsigned epoch, unsigned *timeout_flag,
+                                                        unsigned long long timeout_ns) {
     const int comp = blockIdx.y, dir = blockIdx.z;  // dir 0: data from below -> lower ghost, 1: from above -> upper ghost
     if (threadIdx.x == 0) {
         const volatile unsigned *f = dir == 0 ? below_flag : above_flag;
@@ -222,7 +235,7 @@ __global__ void __launch_bounds__(256) halo_pull_kernel(char *dst_below, char *d
         while ((int)(*f - epoch) < 0) {
             unsigned long long t1;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 20000000000ULL) {  // 20 s: a peer died; fail loudly instead of hanging or
+            if (t1 - t0 > timeout_ns) {  // (20 s by default) a peer died; fail loudly instead of hanging or
                 *timeout_flag = 1;           // continuing with stale ghost planes
                 __threadfence_system();
                 __trap();
@@ -260,7 +273,7 @@ static int exchange_p2p_t(Comm *c, const char *send_up, const char *send_down, c
                                             flag(down, 1), e, mine + HALO_COUNTER);
     INSB_CUDA(cudaGetLastError());
     halo_pull_kernel<V><<<gr, 256, 0, st>>>(recv_below, recv_above, chunk, dst_cs, slot(c->rank, 0), slot(c->rank, 1),
-                                            flag(c->rank, 0), flag(c->rank, 1), e, mine + HALO_TIMEOUT);
+                                            flag(c->rank, 0), flag(c->rank, 1), e, mine + HALO_TIMEOUT, peer_timeout_ns());
     INSB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -380,7 +393,8 @@ __global__ void signal_peers_kernel(PeerPtrs flags, int row, int rank, int world
     __threadfence_system();
 }
 
-__global__ void wait_flags_kernel(unsigned *flags, int row, int world, unsigned epoch, unsigned *timeout_flag) {
+__global__ void wait_flags_kernel(unsigned *flags, int row, int world, unsigned epoch, unsigned *timeout_flag,
+                                  unsigned long long timeout_ns) {
     int s = threadIdx.x;
     if (s < world) {
         volatile unsigned *f = flags + row * 8 + s;
@@ -389,7 +403,7 @@ __global__ void wait_flags_kernel(unsigned *flags, int row, int world, unsigned 
         while ((int)(*f - epoch) < 0) {
             unsigned long long t1;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 20000000000ULL) {  // 20 s: a peer died; fail loudly (sticky launch error)
+            if (t1 - t0 > timeout_ns) {  // (20 s by default) a peer died; fail loudly (sticky launch error)
                 *timeout_flag = 1;           // instead of hanging or transforming stale data
                 __threadfence_system();
                 __trap();
@@ -408,7 +422,7 @@ int comm_signal_peers(unsigned *const *peer_flags, int row, int rank, int world,
 }
 
 int comm_wait_flags(unsigned *my_flags, int row, int world, unsigned epoch, unsigned *timeout_flag, cudaStream_t st) {
-    wait_flags_kernel<<<1, 32, 0, st>>>(my_flags, row, world, epoch, timeout_flag);
+    wait_flags_kernel<<<1, 32, 0, st>>>(my_flags, row, world, epoch, timeout_flag, peer_timeout_ns());
     INSB_CUDA(cudaGetLastError());
     return 0;
 }

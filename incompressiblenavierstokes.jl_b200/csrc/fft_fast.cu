@@ -304,8 +304,10 @@ __global__ void __launch_bounds__(StridedShape<T, N>::NT, (sizeof(T) == 4 && Str
         for (int m = 0; m < 8; m++) v[m] = ip[m * step];
     }
     int exch = 0;
-    // (the generalised middle pass spills at its 64-register cap with seven live twiddles: it keeps the products)
-    constexpr bool TW7 = !(MODE == 2 && (BLK || N > 512));
+    // (the middle pass of the 1024-thread blocks spills at its 64-register cap with seven live twiddles: it keeps the
+    // products.  The rule depends on (N, MODE) only -- the plain, the generalised and the TMA variant of a pass must
+    // round alike, or P GPUs would not reproduce one GPU bit for bit.)
+    constexpr bool TW7 = !(MODE == 2 && N > 512);
     if (MODE == 0 || MODE >= 2) fft_stages<T, N, false, 0, L, 3, TW7>(v, t, sm, tw, exch);
     if (MODE >= 2) {
         // phat = -phat / ((ax + ay) + az), phat[1] = 0 (pressure.jl:360-372); `factor` carries

@@ -320,3 +320,53 @@ def test_user_defined_force_composed_stage_by_stage(T, bcs):
     except (ImportError, RuntimeError):
         pass
     assert [k["u"].data_ptr() for k in sg._plans["stage_cache"][("u",)]["k"]] == ptrs
+
+
+@pytest.mark.parametrize("T", [np.float64, np.float32])
+@pytest.mark.parametrize("coef64", [False, True])
+def test_stage_combine_and_axpy_round_like_the_reference_broadcast(T, coef64):
+    """insb200_stage_combine / insb200_axpy: u = u_start + sum_j c_j k_j evaluated like `@. u += dt * A[i, j] * k`
+    (step_explicit_runge_kutta.jl:28-32) -- every product and every sum rounded separately in
+    promote(field type, coefficient type), stored in the field type; bit-exact against NumPy."""
+    import ctypes as C
+
+    import torch
+
+    from insb200 import _lib
+    from insb200._lib import check, lib
+    from insb200.api import _base_plan, _ptr, _stream
+
+    I = ins()
+    so, sg = make_setups((uniform(12), uniform(10), uniform(8)), ("P", "P", "P"), T=T)
+    rng = np.random.default_rng(5)
+    h = _base_plan(sg).h
+    shape = (3,) + tuple(reversed(sg.N))
+    base = rng.standard_normal(shape).astype(T)
+    ks = [rng.standard_normal(shape).astype(T) for _ in range(4)]
+    CT = np.float64 if (coef64 or T is np.float64) else np.float32
+    cdt = _lib.F64 if coef64 else (_lib.F64 if T is np.float64 else _lib.F32)
+    coefs = [float(CT(v)) for v in (0.5e-3, -0.25e-3, 1.7e-3, 0.1e-3)]
+    want = base.astype(CT)
+    for c, k in zip(coefs, ks):
+        want = (want.astype(T).astype(CT) + CT(c) * k.astype(CT))  # rounded to the field type after every axpy
+    want = want.astype(T)
+    dev = [torch.from_numpy(k).cuda() for k in ks]
+    b = torch.from_numpy(base).cuda()
+    out = torch.empty_like(b)
+    kp = (C.c_void_p * 4)(*[_ptr(d) for d in dev])
+    cf = (C.c_double * 4)(*coefs)
+    check(lib().insb200_stage_combine(h, _ptr(out), _ptr(b), 4, kp, cf, cdt, 3, _stream()))
+    assert np.array_equal(out.cpu().numpy(), want)
+    # in place (dst aliases base) and axpy
+    check(lib().insb200_stage_combine(h, _ptr(b), _ptr(b), 4, kp, cf, cdt, 3, _stream()))
+    assert np.array_equal(b.cpu().numpy(), want)
+    y = torch.from_numpy(base).cuda()
+    check(lib().insb200_axpy(h, _ptr(y), coefs[0], _ptr(dev[0]), cdt, 3, _stream()))
+    assert np.array_equal(y.cpu().numpy(), (base.astype(CT) + CT(coefs[0]) * ks[0].astype(CT)).astype(T))
+    # scalar fields (ncomp = 1) and the copy (nk = 0)
+    s_out = torch.empty(tuple(reversed(sg.N)), dtype=b.dtype, device="cuda")
+    check(lib().insb200_stage_combine(h, _ptr(s_out), _ptr(b), 0, None, None, cdt, 1, _stream()))
+    assert np.array_equal(s_out.cpu().numpy(), want[0])
+    # more than 8 stage arrays are refused
+    many = (C.c_void_p * 9)(*[_ptr(dev[0])] * 9)
+    assert lib().insb200_stage_combine(h, _ptr(out), _ptr(b), 9, many, (C.c_double * 9)(*[0.0] * 9), cdt, 3, _stream()) != 0
