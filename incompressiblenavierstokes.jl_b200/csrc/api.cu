@@ -56,6 +56,13 @@ struct insb200_plan : public insb::Profiler {
     // the running accumulator, the pressure and the scaled divergence -- and their tensor maps
     void *FV[2] = {nullptr, nullptr}, *FACC = nullptr, *FP = nullptr, *FD = nullptr;
     void *FUB = nullptr;  // slab mode: plane "-1" of the caller's velocity (from the rank below), [3][N1][N0]
+    // chained steps (insb200_solve_unsteady): between two steps of the native loop the state stays in its lazy form
+    // (unprojected velocity FV[chain_slot] + pressure FP) -- no explicit projection into the caller's array, and the
+    // first stage of the next step reads it by TMA; FU0 keeps the step's projected input for the stage combine.
+    // The caller's array is materialised before anything else looks at it (call-backs, CFL, the end of the loop).
+    void *FU0 = nullptr;
+    bool chain_in = false, chain_out = false, chain_valid = false;
+    int chain_slot = 1;
     FusedCtx fctx{};
     bool fused_ready = false;
     long long bytes = 0;
@@ -415,6 +422,7 @@ int fused_stage_and_solve(insb200_plan *pl, const FusedStage<T> &st_in, bool ct_
         Scope sc(pl, L.stream, 4);
         INSB_TRY(fused_halo<T>(pl, st.v_out, 3, L));
         if (st.acc_out && st.acc_halo) INSB_TRY(fused_halo<T>(pl, st.acc_out, 3, L));
+        if (st.u0_out) INSB_TRY(fused_halo<T>(pl, st.u0_out, 3, L));
     }
     const FusedLayout &FL = pl->fctx.L;
     PoissonIO io{};
@@ -519,25 +527,35 @@ int step_rk_t(insb200_plan *pl, const double *A, const double *c, int s, int coe
         // fused periodic path: per stage ONE stencil launch (lazy projection of the previous stage on load,
         // stage combine, divergence of its own output) + the Poisson solve; explicit projection only at the end
         INSB_TRY(ensure_fused(pl));
+        // chained steps: the input is the lazy state the previous step left (cin), the output stays lazy (cout)
+        const bool cin = pl->chain_in && pl->chain_valid, cout = pl->chain_out;
+        // (allocated by the step that starts a chain: the next one may already run under stream capture)
+        if ((cin || cout) && !pl->FU0) INSB_TRY(dev_alloc(pl, &pl->FU0, 3 * (size_t)pl->fctx.L.cs * pl->esz));
+        const int cs = cin ? pl->chain_slot : 1;  // stage i writes FV[(cs + 1 + i) & 1]: never the buffer it reads
+        auto slot = [&](int i) { return (cs + 1 + i) & 1; };
         for (int i = 0; i < s; i++) {
             const bool last = i == s - 1;
             FusedStage<T> st;
             fused_params(st, pr);
             st.cv = coef(i, i);
-            st.v_out = (T *)pl->FV[i & 1];
+            st.v_out = (T *)pl->FV[slot(i)];
             st.d_out = (T *)pl->FD;
-            if (i == 0) {
+            if (i == 0 && !cin) {
                 st.u_ref = U;
             } else {
-                st.v_in = (const T *)pl->FV[(i - 1) & 1];
+                st.v_in = (const T *)pl->FV[i == 0 ? cs : slot(i - 1)];
                 st.p_in = (const T *)pl->FP;
+                if (i == 0) st.u0_out = (T *)pl->FU0;
             }
             if (!last) {
                 st.acc_out = (T *)pl->FACC;
                 st.acc_halo = i == s - 2;  // the last stage reads the accumulator as its vbase
                 st.ca = coef(s - 1, i);
                 if (i > 0) {
-                    st.vbase_ref = U;
+                    if (cin)
+                        st.vbase_int = (const T *)pl->FU0;
+                    else
+                        st.vbase_ref = U;
                     st.acc_in = (const T *)pl->FACC;
                 }
             } else {
@@ -547,7 +565,10 @@ int step_rk_t(insb200_plan *pl, const double *A, const double *c, int s, int coe
             if (const char *e = getenv("INSB200_FUSED_STOP_AFTER"))  // debugging aid (tools/debug_fused.py)
                 if (atoi(e) == i + 1) return 0;
         }
-        return fused_finish<T>(pl, (const T *)pl->FV[(s - 1) & 1], U, stream);
+        pl->chain_slot = slot(s - 1);
+        pl->chain_valid = cout;
+        if (cout) return 0;
+        return fused_finish<T>(pl, (const T *)pl->FV[slot(s - 1)], U, stream);
     }
     if (!fast) INSB_TRY(ensure_k(pl, s - 1, bouss));
     size_t vb = (size_t)pl->ncell * pl->D * pl->esz, sb = (size_t)pl->ncell * pl->esz;
@@ -632,25 +653,36 @@ int step_wray_t(insb200_plan *pl, T *U, T *TU, double t, double dt, const insb20
     const T c3[3] = {(T)(8.0 / 15.0), (T)(2.0 / 3.0), (T)1};
     if (fused_applicable(pl, pr)) {
         INSB_TRY(ensure_fused(pl));
+        const bool cin = pl->chain_in && pl->chain_valid, cout = pl->chain_out;  // chained steps, see step_rk_t
+        const int cs = cin ? pl->chain_slot : 1;
+        auto slot = [&](int i) { return (cs + 1 + i) & 1; };
         for (int i = 0; i < 3; i++) {
             FusedStage<T> st;
             fused_params(st, pr);
             st.cv = (double)(T)((double)a3[i] * dt);
-            st.v_out = (T *)pl->FV[i & 1];
+            st.v_out = (T *)pl->FV[slot(i)];
             st.d_out = (T *)pl->FD;
             if (i == 0) {  // statestart += b[0] dt k; v = u + a[0] dt k
-                st.u_ref = U;
+                if (cin) {
+                    st.v_in = (const T *)pl->FV[cs];
+                    st.p_in = (const T *)pl->FP;
+                } else {
+                    st.u_ref = U;
+                }
                 st.acc_out = (T *)pl->FACC;
                 st.acc_halo = true;  // stages 2 and 3 read it as their vbase
                 st.ca = (double)(T)((double)b3[0] * dt);
             } else {
-                st.v_in = (const T *)pl->FV[(i - 1) & 1];
+                st.v_in = (const T *)pl->FV[slot(i - 1)];
                 st.p_in = (const T *)pl->FP;
                 st.vbase_int = (const T *)pl->FACC;
             }
             INSB_TRY(fused_stage_and_solve<T>(pl, st, pl->f64, stream));
         }
-        return fused_finish<T>(pl, (const T *)pl->FV[0], U, stream);
+        pl->chain_slot = slot(2);
+        pl->chain_valid = cout;
+        if (cout) return 0;
+        return fused_finish<T>(pl, (const T *)pl->FV[slot(2)], U, stream);
     }
     const T *src = U;
     const T *tsrc = TU;
@@ -961,7 +993,7 @@ int insb200_plan_destroy(insb200_plan_t *pl) {
     if (pl->ps) poisson_destroy(pl->ps);
     for (void *p : {pl->V[0], pl->V[1], pl->ACC, pl->P, pl->TV[0], pl->TV[1], pl->TACC, pl->dev_tables,
                     (void *)pl->scratch, (void *)pl->ke_partial, pl->LES_G, pl->LES_visc, pl->HU, pl->HT, pl->HU2, pl->HT2, pl->HU3, pl->HT3,
-                    pl->FV[0], pl->FV[1], pl->FACC, pl->FP, pl->FD, pl->FUB})
+                    pl->FV[0], pl->FV[1], pl->FACC, pl->FP, pl->FD, pl->FUB, pl->FU0})
         if (p) cudaFree(p);
     if (pl->fctx.maps) fused_maps_destroy(pl->fctx.maps);
     if (pl->s_in) cudaStreamDestroy(pl->s_in);
@@ -1282,10 +1314,29 @@ int insb200_solve_unsteady(insb200_plan_t *pl, int method, const double *A, cons
     const bool tf32 = time_dtype == INSB200_F32;
     // t, Δt arithmetic in the caller's time type (the reference keeps typeof(tstart), typeof(Δt))
     auto R = [&](double v) { return tf32 ? (double)(float)v : v; };
+    // the limits live in the time type too: a Float32 clock can never reach a Float64 tend that is not representable
+    // (t < tend would hold forever with steps that round to nothing)
+    tstart = R(tstart);
+    tend = R(tend);
     auto step = [&](void *st, double t, double h) -> int {
         if (method == 1) return insb200_step_lmwray3(pl, u, temp, t, h, pr, st);
         return insb200_step_rk(pl, A, c, s, coef_dtype, u, temp, t, h, pr, st);
     };
+    // chained steps on the fused periodic path: between two steps the state stays lazy (no explicit projection into
+    // u); u is materialised before a call-back, before a CFL evaluation and at the end of the loop
+    const bool can_chain = getenv("INSB200_NO_CHAINED_STEPS") == nullptr && fused_applicable(pl, pr);
+    auto materialise = [&](void *st) -> int {
+        if (!pl->chain_valid) return 0;
+        pl->chain_valid = false;
+        const int sl = pl->chain_slot;
+        return pl->f64 ? fused_finish<double>(pl, (const double *)pl->FV[sl], (double *)u, st)
+                       : fused_finish<float>(pl, (const float *)pl->FV[sl], (float *)u, st);
+    };
+    struct ChainReset {  // whatever happens, the plan leaves the loop without chaining
+        insb200_plan *p;
+        ~ChainReset() { p->chain_in = p->chain_out = p->chain_valid = false; }
+    } chain_reset{pl};
+    auto cb_due = [&](long long nn) { return cb && callback_every > 0 && nn % callback_every == 0; };
     double t = tstart;
     long long n = 0;
     int rc = 0;
@@ -1309,11 +1360,15 @@ int insb200_solve_unsteady(insb200_plan_t *pl, int method, const double *A, cons
                 }
             }
             const double hs = std::fmin(h, R(tend - t));
+            const bool lastone = !(R(t + hs) < tend);
+            pl->chain_in = can_chain;
+            pl->chain_out = can_chain && !lastone && !cb_due(n + 1) && (n + 1) % n_adapt_dt != 0;
             INSB_TRY(step(stream, t, hs));
             t = R(t + hs);
             n++;
             notify();
         }
+        INSB_TRY(materialise(stream));
     } else {  // fixed: Δt rounded so that (tend - tstart) / Δt is an integer (:123-132)
         const long long nstep = std::llround(R(tend - tstart) / dt);
         if (nstep < 1) {
@@ -1326,11 +1381,14 @@ int insb200_solve_unsteady(insb200_plan_t *pl, int method, const double *A, cons
         const bool graph = use_graph && !pl->comm && !pl->prof && nstep > 2 && pl->psolver != INSB200_PSOLVER_CG;
         if (!graph) {
             for (long long it = 0; it < nstep && !stop; it++) {
+                pl->chain_in = can_chain;
+                pl->chain_out = can_chain && it < nstep - 1 && !cb_due(n + 1);
                 INSB_TRY(step(stream, t, h));
                 t = R(t + h);
                 n++;
                 notify();
             }
+            INSB_TRY(materialise(stream));
         } else {
             // one eager step (allocations, function attributes), then the step is captured once and
             // replayed: the launch-bound small grids (config 1: 256^2) stop paying per-kernel launches.
@@ -1343,11 +1401,17 @@ int insb200_solve_unsteady(insb200_plan_t *pl, int method, const double *A, cons
                 INSB_CUDA(cudaStreamWaitEvent(to, ev, 0));
                 return 0;
             };
+            // chained replay: every step must use the buffers in the same roles (an even number of stages) and nothing
+            // may look at u in between (no call-backs); the last step runs eagerly and materialises u
+            const bool gchain = can_chain && method == 0 && s % 2 == 0 && !(cb && callback_every > 0) && nstep > 3;
+            pl->chain_in = false;
+            pl->chain_out = gchain;
             INSB_TRY(step(stream, t, h));
             t = R(t + h);
             n++;
             notify();
             INSB_TRY(handoff(user_st, pl->s_graph));
+            pl->chain_in = gchain;
             const long long l0 = pl->launches;
             cudaGraph_t g = nullptr;
             cudaGraphExec_t ge = nullptr;
@@ -1369,7 +1433,16 @@ int insb200_solve_unsteady(insb200_plan_t *pl, int method, const double *A, cons
                 set_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
                 return 1;
             }
+            pl->chain_valid = gchain;  // (the capture did not execute: the eager first step left the lazy state)
             for (long long it = 1; it < nstep && !stop; it++) {
+                if (gchain && it == nstep - 1) {  // the last step: eager, into u
+                    pl->chain_out = false;
+                    rc = step((void *)pl->s_graph, t, h);
+                    if (rc) break;
+                    t = R(t + h);
+                    n++;
+                    break;
+                }
                 ce = cudaGraphLaunch(ge, pl->s_graph);
                 if (ce != cudaSuccess) break;
                 pl->launches += per_step;
@@ -1387,6 +1460,7 @@ int insb200_solve_unsteady(insb200_plan_t *pl, int method, const double *A, cons
             cudaEventDestroy(ev);
             INSB_CUDA(ce);
             if (rc || hrc) return 1;
+            INSB_TRY(materialise(stream));
         }
     }
     if (t_out) *t_out = t;

@@ -57,6 +57,9 @@ struct FusedStage {
     const T *v_in = nullptr, *p_in = nullptr;
     const T *vbase_ref = nullptr, *vbase_int = nullptr, *acc_in = nullptr;
     T *v_out = nullptr, *acc_out = nullptr, *d_out = nullptr;
+    // chained steps (insb200_solve_unsteady): the first stage of a step that starts from the lazy state of the previous
+    // step also stores the projected velocity u0 = v_in - G p_in (internal layout): the vbase of the later stages
+    T *u0_out = nullptr;
     bool acc_halo = false;  // slab mode: a later stage reads acc_out as vbase_int (on its z halo too): exchange its ghost planes
     double cv = 0, ca = 0, nu = 0;
     double bodyforce[3] = {0, 0, 0};

@@ -121,7 +121,7 @@ struct FusedDev {
     int N0, N1;            // reference extents (ghosted) of u_ref / vb_ref
     long long rs2, rcs;    // plane and component stride of the reference layout
     // internal outputs (pointers to component 0, element (0, 0, 0) of the padded array)
-    T *v_out, *acc_out, *d_out;
+    T *v_out, *acc_out, *d_out, *u0_out;
     long long s1, s2, cs;  // internal strides
     int n0, n1, nz;        // interior extents (local planes)
     int zwrap, zoff, n2g;
@@ -529,6 +529,12 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1)
                     store_img(v_b + zo, vn0);
                     store_img(v_b + zo + a.cs, vn1);
                     store_img(v_b + zo + 2 * a.cs, vn2);
+                    if (IN == 1 && VB == 0 && a.u0_out) {  // chained step: keep the projected input of the step
+                        T *u0_b = a.u0_out + q_int + zo;
+                        store_img(u0_b, u0c);
+                        store_img(u0_b + a.cs, u1c);
+                        store_img(u0_b + 2 * a.cs, u2c);
+                    }
                     if (ACC) {
                         // (the accumulator is the vbase of the last stage, which reads it on its halo too)
                         if (VB == 0) {
@@ -761,6 +767,7 @@ int launch_variant(const Grid<T> &g, const FusedCtx &c, const FusedStage<T> &s, 
     a.v_out = s.v_out;
     a.acc_out = s.acc_out;
     a.d_out = s.d_out;
+    a.u0_out = s.u0_out;
     a.s1 = c.L.s1, a.s2 = c.L.s2, a.cs = c.L.cs;
     a.n0 = c.L.n[0], a.n1 = c.L.n[1], a.nz = c.L.n[2];
     a.zwrap = c.zwrap, a.zoff = c.zoff, a.n2g = c.n2g;
@@ -809,6 +816,8 @@ int launch_stage_fused_ct(const Grid<T> &g, const FusedCtx &c, const FusedStage<
     if (in == 0 && vb == 0 && acc) return launch_variant<T, CT, 0, 0, true>(g, c, s, g, L);
     if (in == 0 && vb == 0 && !acc) return launch_variant<T, CT, 0, 0, false>(g, c, s, g, L);
     if (in == 1 && vb == 1 && acc) return launch_variant<T, CT, 1, 1, true>(g, c, s, g, L);
+    if (in == 1 && vb == 0 && acc) return launch_variant<T, CT, 1, 0, true>(g, c, s, g, L);  // chained first stage
+    if (in == 1 && vb == 2 && acc) return launch_variant<T, CT, 1, 2, true>(g, c, s, g, L);  // chained middle stages
     if (in == 1 && vb == 2 && !acc) return launch_variant<T, CT, 1, 2, false>(g, c, s, g, L);
     set_error("fused stage: unsupported operand combination");
     return 1;

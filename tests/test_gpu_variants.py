@@ -370,3 +370,39 @@ def test_stage_combine_and_axpy_round_like_the_reference_broadcast(T, coef64):
     # more than 8 stage arrays are refused
     many = (C.c_void_p * 9)(*[_ptr(dev[0])] * 9)
     assert lib().insb200_stage_combine(h, _ptr(out), _ptr(b), 9, many, (C.c_double * 9)(*[0.0] * 9), cdt, 3, _stream()) != 0
+
+
+@pytest.mark.parametrize("T", [np.float64, np.float32])
+@pytest.mark.parametrize("mname", ["RK44", "LMWray3"])
+def test_chained_steps_of_the_native_loop_are_bit_identical(mname, T):
+    """Inside insb200_solve_unsteady the fused periodic path keeps the state lazy between steps (unprojected velocity +
+    pressure: no explicit projection into u, the next step's first stage projects on load) and materialises u only for
+    call-backs, CFL evaluations and at the end.  The result must equal stepping from Python -- one library call per
+    step, u materialised every time -- bit for bit: fixed dt with and without CUDA-graph replay, with processors that
+    look at the state every third step, and adaptive dt with a CFL evaluation every third step."""
+    I = ins()
+    so, sg = make_setups((uniform(70), uniform(24), uniform(20)), ("P", "P", "P"), T=T)
+    ps = I.psolver_spectral(sg)
+    u0 = I.to_device(sg, smooth_vec(so, 33))
+    I.project_(u0, sg, psolver=ps, p=I.scalarfield(sg))
+    I.apply_bc_u_(u0, 0.0, sg)
+    m = I.LMWray3(T) if mname == "LMWray3" else I.RKMethods.RK44(T)
+    base = dict(setup=sg, start={"u": u0}, method=m, psolver=ps, params=dict(viscosity=1e-2))
+    for name, kw, procs in (("fixed", dict(tlims=(0.0, 0.014), dt=0.002), False),
+                            ("fixed+processors", dict(tlims=(0.0, 0.014), dt=0.002), True),
+                            ("adaptive", dict(tlims=(0.0, 0.02), cfl=0.4, n_adapt_dt=3), False)):
+        res = {}
+        for tag, opts in (("python", dict(native=False)), ("native", dict(native=True, graph=False)),
+                          ("graph", dict(native=True, graph=True)), ("unchained", dict(native=True, graph=False))):
+            log = []
+            pr = {"log": I.timelogger(sg, nupdate=3, out=log), "save": I.fieldsaver(sg, nupdate=3)} if procs else {}
+            with env(INSB200_NO_CHAINED_STEPS=1 if tag == "unchained" else None):
+                out, outputs = I.solve_unsteady(processors=pr, **base, **kw, **opts)
+            res[tag] = (I.to_host(out["u"]), float(out["t"]), [(e["n"], e["umax"]) for e in log],
+                        [(s["n"], s["u"]) for s in outputs.get("save", [])])
+        for tag in ("native", "graph", "unchained"):
+            assert np.array_equal(res[tag][0], res["python"][0]), (name, tag)
+            assert res[tag][1] == res["python"][1] and res[tag][2] == res["python"][2], (name, tag)
+            for (na, ua), (nb, ub) in zip(res[tag][3], res["python"][3]):
+                assert na == nb and np.array_equal(ua, ub), (name, tag)
+        assert np.all(np.isfinite(res["python"][0]))
