@@ -134,7 +134,8 @@ def run_case(args, case, rank, world, quiet=False):
     ok = True
     out = []
 
-    exact = {"project", "psolve", "RK44", "LMWray3", "RK44_temp", "LMWray3_temp", "LES_WALE_RK44", "vorticity"}
+    exact = {"project", "psolve", "RK44", "LMWray3", "RK44_temp", "LMWray3_temp", "LES_WALE_RK44", "vorticity",
+             "RK44_native_loop", "LMWray3_native_loop"}
 
     def report(name, err, lim):
         nonlocal ok
@@ -194,6 +195,13 @@ def run_case(args, case, rank, world, quiet=False):
     res["tke"] = float(I.total_kinetic_energy(st["state"]["u"], sd, plan=psd.plan))
     res["vort"] = I.gather_global(sd, I.vorticity(st["state"]["u"], sd))
 
+    # the time loop inside the library (chained steps on the fused periodic path: the state stays lazy between steps)
+    if case == "periodic":
+        for name, method in (("RK44", I.RKMethods.RK44(T)), ("LMWray3", I.LMWray3(T))):
+            fin, _ = I.solve_unsteady(setup=sd, tlims=(0.0, 3 * float(dt)), start={"u": ud}, method=method, psolver=psd,
+                                      dt=dt, params=params, native=True)
+            res[name + "_native_loop"] = I.gather_global(sd, fin["u"])
+
     # random_field synthesised on the slabs (distributed transforms, all-reduced shell sums): injected host noise
     # and the device generator, which is keyed by the GLOBAL cell index
     if case == "periodic":
@@ -202,6 +210,20 @@ def run_case(args, case, rank, world, quiet=False):
 
     if rank == 0:
         if case == "periodic":
+            u1s = I.to_device(s1, ug)
+            I.apply_bc_u_(u1s, 0.0, s1)
+            I.project_(u1s, s1, psolver=ps1, p=I.scalarfield(s1))
+            I.apply_bc_u_(u1s, 0.0, s1)
+            for name, method in (("RK44", I.RKMethods.RK44(T)), ("LMWray3", I.LMWray3(T))):
+                # one GPU, the same loop with chaining switched off: u is materialised after every step (that the
+                # chained loop equals call-by-call stepping bit for bit is tests/test_gpu_variants.py's business)
+                os.environ["INSB200_NO_CHAINED_STEPS"] = "1"
+                try:
+                    ref, _ = I.solve_unsteady(setup=s1, tlims=(0.0, 3 * float(dt)), start={"u": u1s}, method=method,
+                                              psolver=ps1, dt=dt, params=params, native=True, graph=False)
+                finally:
+                    del os.environ["INSB200_NO_CHAINED_STEPS"]
+                report(name + "_native_loop", rel(res[name + "_native_loop"], I.to_host(ref["u"])), tol)
             for tag, r in (("host_noise", np.random.default_rng(11)), ("device_noise", 1234)):
                 f1 = I.to_host(I.random_field(s1, 0.0, totalenergy=0.5, kpeak=4, rng=r, psolver=ps1))
                 report("random_field_" + tag, rel(res["rf_" + tag], f1), 1e-13 if T is np.float64 else 2e-6)
