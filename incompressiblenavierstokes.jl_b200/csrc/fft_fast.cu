@@ -19,6 +19,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "cx.cuh"
@@ -947,12 +948,14 @@ struct FftMapEntry {
     long long key[6];
     CUtensorMap map;
 };
-static std::vector<FftMapEntry> g_fft_maps;
+static std::vector<FftMapEntry> g_fft_maps;  // (a tensor map depends on the address and the geometry only)
+static std::mutex g_fft_maps_mu;
 
 // W viewed as [n2][n1][m0p complex] of 4-byte words; box = rowb bytes (L lines) x BOXR rows along `tdim`
 static int fft_tensor_map(const void *W, long long m0p, int n1, int n2, long long ws1, long long ws2, int esz_cx, int tdim,
                           int boxr, int rowb, CUtensorMap *out) {
     const long long key[6] = {m0p, n1, n2, ws1 * 1000003 + ws2, esz_cx * 16 + tdim, boxr * 1024 + rowb};
+    std::lock_guard<std::mutex> lock(g_fft_maps_mu);
     for (auto &e : g_fft_maps)
         if (e.ptr == W && !std::memcmp(e.key, key, sizeof(key))) {
             *out = e.map;
@@ -1000,11 +1003,8 @@ static int fast_pass_n(int kind, T *R, Cx<T> *W, const FastGeom &g, int tdim, co
         // 1024: 0.364 -> 0.329 ms; lines of 128 lose, 0.36 -> 0.48 ms: the per-tile hand-shake outweighs an 8 KB tile).
         // INSB200_FFT_TMA=0 disables it, =1 restricts it to the middle pass.
         {
-            static int mode = -1;
-            if (mode < 0) {
-                const char *e = getenv("INSB200_FFT_TMA");
-                mode = e ? atoi(e) : 2;
-            }
+            const char *tma_env = getenv("INSB200_FFT_TMA");  // (read per call, like the other switches)
+            const int mode = tma_env ? atoi(tma_env) : 2;
             typedef TmaStridedShape<T, N> TS;
             const bool plain = !blk && !g.in && !g.out && g.in_sd < 0 && g.out_sd < 0 && g.in_os < 0 && g.out_os < 0 && g.nother < 0;
             if (sizeof(T) == 4 && N >= 256 && g.D == 3 && plain && mode > 0 && (kind == 2 || mode >= 2) &&
