@@ -145,6 +145,21 @@ struct LineSmem {
     Cx<T> *buf[2];
 };
 
+// Barrier of the threads that share a line's exchange buffer.  Strided passes (ES > 1): the lines of a block are
+// interleaved over all its threads -- the whole block.  x passes (ES == 1): line lp is the P consecutive threads
+// [lp P, (lp + 1) P) with their own buffer, so the lines of a block need not wait for one another: a named barrier
+// per line (bar.sync id, P), or the warp barrier when a line lives inside one warp.
+template <int ES, int P>
+__device__ __forceinline__ void line_barrier() {
+    if constexpr (ES > 1) {
+        __syncthreads();
+    } else if constexpr (P <= 32) {
+        __syncwarp();
+    } else {
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)(threadIdx.x / P)), "n"(P) : "memory");
+    }
+}
+
 // TW7: all seven radix-8 twiddles from the table (strided passes) instead of three loads + four products
 template <typename T, int N, bool INV, int S, int ES, int SH = 3, bool TW7 = (ES > 1)>
 __device__ __forceinline__ void fft_stages(Cx<T> (&v)[8], int t, const LineSmem<T> &sm,
@@ -222,7 +237,7 @@ __device__ __forceinline__ void fft_stages(Cx<T> (&v)[8], int t, const LineSmem<
                 for (int r = 0; r < R; r++) buf[spx<SH>(j0 + r * NS) * ES] = v[b + B * r];
             }
         }
-        __syncthreads();
+        line_barrier<ES, P>();
         if constexpr (P % (1 << SH) == 0) {
             const Cx<T> *rd = buf + spx<SH>(t) * ES;
 #pragma unroll
@@ -697,7 +712,7 @@ __global__ void __launch_bounds__(XShape<T, N>::NT)
     Cx<T> *buf = sm.buf[exch & 1];
 #pragma unroll
     for (int m = 0; m < 8; m++) buf[spx<SH>(t + P * m)] = v[m];
-    __syncthreads();
+    line_barrier<1, P>();
     Cx<T> *wa = W + (long long)(2 * jp) * g.ws[1] + (long long)kz * g.ws[2];
     Cx<T> *wb = wa + g.ws[1];
     if (valid) {
@@ -842,7 +857,7 @@ __global__ void __launch_bounds__(XDivShape<T, N>::NT)
     Cx<T> *buf = sm.buf[exch & 1];
 #pragma unroll
     for (int m = 0; m < 8; m++) buf[spx<SH>(t + P * m)] = v[m];
-    __syncthreads();
+    line_barrier<1, P>();
     Cx<T> *wa = W + (long long)(2 * jp) * g.ws[1] + (long long)kz * g.ws[2];
     Cx<T> *wb = wa + g.ws[1];
 #pragma unroll
