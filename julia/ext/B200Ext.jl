@@ -134,12 +134,16 @@ mutable struct B200PSolver{S} <: Function
 end
 
 # The stock drivers call `propose_timestep(force!, state, setup, params)` without the psolver
-# (src/solver.jl:111): the plan is found through the setup it was made for.  Weak keys: a setup that is
-# garbage collected drops its entry, and the psolver is only referenced weakly through its own finalizer.
-const PLAN_OF_SETUP = WeakKeyDict{Any,WeakRef}()
+# (src/solver.jl:111): the plan is found through the setup it was made for.  A setup is an immutable NamedTuple
+# (it cannot key a WeakKeyDict), so the registry is keyed by the identity of its first grid-spacing array and holds
+# the psolver weakly -- a collected psolver leaves a dead reference that the next registration overwrites.
+const PLAN_OF_SETUP = Dict{UInt,WeakRef}()
+setupkey(setup) = objectid(setup.Δ[1])
 function psolver_of(setup)
-    w = get(PLAN_OF_SETUP, setup, nothing)
-    isnothing(w) ? nothing : w.value
+    w = get(PLAN_OF_SETUP, setupkey(setup), nothing)
+    isnothing(w) && return nothing
+    ps = w.value
+    (ps isa B200PSolver && ps.setup === setup) ? ps : nothing
 end
 
 const KINDS = (; spectral = Cint(0), transform = Cint(1), tridiagonal = Cint(2), default = Cint(3), cg = Cint(4))
@@ -203,7 +207,7 @@ function INS.psolver_b200(setup; kind = :default, dir = nothing, rank = 0, world
     # inspected); `bc_time_dependent = false` keeps the fused one-call steppers and the CUDA-graph replay
     td = isnothing(bc_time_dependent) ? hasfuncbc(setup) : bc_time_dependent
     ps = B200PSolver(out[], setup, (:spectral, :transform, :tridiagonal, :default, :cg)[resolved+1]; bc_time_dependent = td)
-    PLAN_OF_SETUP[setup] = WeakRef(ps)
+    PLAN_OF_SETUP[setupkey(setup)] = WeakRef(ps)
     hasfuncbc(setup) && refresh_bc!(ps, 0)      # the planes must exist before the first ghost fill
     ps
 end
