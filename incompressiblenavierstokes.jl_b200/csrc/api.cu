@@ -469,7 +469,8 @@ int stage_with_closures(insb200_plan *pl, const Grid<T> &g, const StageArgs<T> &
     INSB_TRY(launch_stage<T>(g, a, ct_double, L));
     if (a.eddy_model != 0) {
         size_t sb = (size_t)pl->ncell * pl->esz;
-        if (!pl->LES_G) INSB_TRY(dev_alloc(pl, &pl->LES_G, 9 * sb));
+        if (!pl->LES_G && les_needs_tensor(g.D, g.N, pl->bc, a.u, a.k_out, a.v, a.acc_out))
+            INSB_TRY(dev_alloc(pl, &pl->LES_G, 9 * sb));
         if (!pl->LES_visc) INSB_TRY(dev_alloc(pl, &pl->LES_visc, sb));
         INSB_TRY(launch_les_closure<T>(g, pl->bc, a.eddy_model, a.eddy_C, a.u, (T *)pl->LES_G, (T *)pl->LES_visc, a.k_out,
                                        a.v, a.cv, a.acc_out, a.ca, ct_double, L));
@@ -1519,7 +1520,8 @@ int insb200_cfl(insb200_plan_t *pl, const void *u, const insb200_params_t *pr, d
 int insb200_eddy_viscosity_closure(insb200_plan_t *pl, int model, double C, void *f, const void *u, void *stream) {
     API_BEGIN
     size_t sb = (size_t)pl->ncell * pl->esz;
-    if (!pl->LES_G) INSB_TRY(dev_alloc(pl, &pl->LES_G, 9 * sb));
+    const int *Ng = pl->f64 ? pl->gd.N : pl->gf.N;
+    if (!pl->LES_G && les_needs_tensor(pl->D, Ng, pl->bc, u, f, nullptr, nullptr)) INSB_TRY(dev_alloc(pl, &pl->LES_G, 9 * sb));
     if (!pl->LES_visc) INSB_TRY(dev_alloc(pl, &pl->LES_visc, sb));
     Launch L = L_of(pl, stream);
     return DISPATCH(launch_les_closure<float>(pl->gf, pl->bc, model, C, (const float *)u, (float *)pl->LES_G,

@@ -199,7 +199,11 @@ int launch_zero_out_wall(const Grid<T> &g, const BcDesc &b, T *fields, int nf, L
 // ---- les.cu ----
 // eddy_viscosity_closure! (src/eddyviscosity.jl:356-378).  model: 1 Smagorinsky, 2 WALE, 3 Vreman,
 // 4 QR.  G: 9 scalar fields, visc: 1 (scratch).  With fl = -(div sigma): k_out += fl, v += cv fl,
-// acc += ca fl (null pointers are skipped).
+// acc += ca fl (null pointers are skipped).  Default: the two fused kernels (nu_t from u, then stress
+// divergence from u and nu_t; G unused and may be null); the four-pass path with the stored tensor is taken
+// when les_needs_tensor says so (PressureBC sides, decomposed grids, u aliasing an output, INSB200_LES_UNFUSED).
+bool les_needs_tensor(int D, const int N[3], const BcDesc &b, const void *u, const void *k_out, const void *v,
+                      const void *acc);
 template <typename T>
 int launch_les_closure(const Grid<T> &g, const BcDesc &b, int model, double C, const T *u, T *G, T *visc, T *k_out, T *v,
                        double cv, T *acc, double ca, bool ct_double, Launch L);

@@ -1,7 +1,11 @@
 // les.cu -- eddy-viscosity closures: eddy_viscosity_closure! with the
 // Smagorinsky / WALE / Vreman / QR models, 3-D (src/eddyviscosity.jl:57-74, 235-378).
 //
-// Same sequence as the reference -- gradient tensor, wall zeroing + ghost fills, viscosity at the
+// Default: two fused kernels (below, cell functions in les_math.cuh) that store nothing but nu_t -- the
+// staggered gradients and the stresses a cell needs are recomputed from the velocity, ghost entries by the
+// rule zero_out_wall! + apply_bc_p! amount to.  20 scalar fields of traffic per closure instead of 62.
+// Four-pass path (PressureBC sides, decomposed grids, INSB200_LES_UNFUSED): same sequence as the reference
+// -- gradient tensor, wall zeroing + ghost fills, viscosity at the
 // cell centres, ghost fills, symmetrise + scale with the interpolated viscosity, ghost fills,
 // divergence of the stress -- with symmetrize! folded into the scaling pass (the ghost entries it
 // would touch are overwritten by the fills that follow) and the divergence pass applying the
@@ -9,6 +13,7 @@
 // The nine tensor components are one allocation, component (a, b) = du_a/dx_b at index a + 3 b
 // (the reference's tensorfield order xx, yx, zx, xy, yy, zy, xz, yz, zz).
 #include "stencil_math.cuh"
+#include "les_math.cuh"
 
 namespace insb {
 
@@ -37,14 +42,7 @@ __global__ void __launch_bounds__(256) les_gradient_kernel(Grid<T> g, const T *_
     }
 }
 
-template <typename T>
-__device__ __forceinline__ T eps_of();
-template <>
-__device__ __forceinline__ float eps_of<float>() { return 1.1920929e-07f; }
-template <>
-__device__ __forceinline__ double eps_of<double>() { return 2.220446049250313e-16; }
-
-// MODEL: 1 Smagorinsky, 2 WALE, 3 Vreman, 4 QR
+// MODEL: 1 Smagorinsky, 2 WALE, 3 Vreman, 4 QR (bodies in les_math.cuh)
 template <typename T, int MODEL>
 __global__ void __launch_bounds__(256) les_viscosity_kernel(Grid<T> g, const T *__restrict__ G, T *__restrict__ visc, T C) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y * blockDim.y + threadIdx.y + 1, k = blockIdx.z + 1;
@@ -66,68 +64,7 @@ __global__ void __launch_bounds__(256) les_viscosity_kernel(Grid<T> g, const T *
             }
         }
     const T dx = __ldg(g.dl[0] + i), dy = __ldg(g.dl[1] + j), dz = __ldg(g.dl[2] + k);
-    T out;
-    if (MODEL == 3) {  // Vreman (:307-340)
-        const T d1 = dx * dx, d2 = dy * dy, d3 = dz * dz;
-        const T a11 = M[0][0], a21 = M[0][1], a31 = M[0][2];
-        const T a12 = M[1][0], a22 = M[1][1], a32 = M[1][2];
-        const T a13 = M[2][0], a23 = M[2][1], a33 = M[2][2];
-        const T b11 = d1 * a11 * a11 + d2 * a21 * a21 + d3 * a31 * a31;
-        const T b12 = d1 * a11 * a12 + d2 * a21 * a22 + d3 * a31 * a32;
-        const T b13 = d1 * a11 * a13 + d2 * a21 * a23 + d3 * a31 * a33;
-        const T b22 = d1 * a12 * a12 + d2 * a22 * a22 + d3 * a32 * a32;
-        const T b23 = d1 * a12 * a13 + d2 * a22 * a23 + d3 * a32 * a33;
-        const T b33 = d1 * a13 * a13 + d2 * a23 * a23 + d3 * a33 * a33;
-        const T abeta = a11 * a11 + a12 * a12 + a13 * a13 + a21 * a21 + a22 * a22 + a23 * a23 + a31 * a31 + a32 * a32 + a33 * a33;
-        const T bbeta = b11 * b22 - b12 * b12 + b11 * b33 - b13 * b13 + b22 * b33 - b23 * b23;
-        const T value = C * C * sqrt(bbeta / abeta);
-        const T tol = sizeof(T) == 8 ? T(1e-12) : T(1e-6);
-        out = abeta > tol ? value : T(0);
-    } else {
-        const T d = cbrt(dx * dy * dz);  // gridsize_vol (operators.jl:914-915)
-        T S[3][3];
-#pragma unroll
-        for (int a = 0; a < 3; a++)
-#pragma unroll
-            for (int b = 0; b < 3; b++) S[a][b] = (M[a][b] + M[b][a]) * T(0.5);
-        T ss = T(0);
-#pragma unroll
-        for (int b = 0; b < 3; b++)
-#pragma unroll
-            for (int a = 0; a < 3; a++) ss += S[a][b] * S[a][b];
-        const T cd2 = (C * d) * (C * d);
-        if (MODEL == 1) {  // Smagorinsky (:265-278)
-            out = cd2 * sqrt(T(2) * ss);
-        } else if (MODEL == 2) {  // WALE (:280-292)
-            T G2[3][3];
-#pragma unroll
-            for (int a = 0; a < 3; a++)
-#pragma unroll
-                for (int b = 0; b < 3; b++) G2[a][b] = M[a][0] * M[0][b] + M[a][1] * M[1][b] + M[a][2] * M[2][b];
-            const T tr3 = (G2[0][0] + G2[1][1] + G2[2][2]) / T(3);
-            T sdsd = T(0);
-#pragma unroll
-            for (int b = 0; b < 3; b++)
-#pragma unroll
-                for (int a = 0; a < 3; a++) {
-                    const T sd = (G2[a][b] + G2[b][a]) * T(0.5) - (a == b ? tr3 : T(0));
-                    sdsd += sd * sd;
-                }
-            out = cd2 * pow(sdsd, T(1.5)) / (pow(ss, T(2.5)) + pow(sdsd, T(1.25)) + eps_of<T>());
-        } else {  // QR (:294-305)
-            T SS[3][3];
-#pragma unroll
-            for (int a = 0; a < 3; a++)
-#pragma unroll
-                for (int b = 0; b < 3; b++) SS[a][b] = S[a][0] * S[0][b] + S[a][1] * S[1][b] + S[a][2] * S[2][b];
-            const T QS = (SS[0][0] + SS[1][1] + SS[2][2]) * T(0.5);
-            T tr = T(0);
-#pragma unroll
-            for (int a = 0; a < 3; a++) tr += SS[a][0] * S[0][a] + SS[a][1] * S[1][a] + SS[a][2] * S[2][a];
-            out = cd2 * fabs(tr / T(3)) / (QS + eps_of<T>());
-        }
-    }
-    visc[idx] = out;
+    visc[idx] = eddy_visc_value<T, MODEL>(M, dx, dy, dz, C);
 }
 
 // symmetrize! + apply_eddy_viscosity_kernel! (:81-86, :144-181): sigma = -2 nu_t S in the slots
@@ -186,6 +123,74 @@ __global__ void __launch_bounds__(256) les_divergence_kernel(Grid<T> g, const T 
     }
 }
 
+// ---- fused closure: two kernels, neither the gradient tensor nor the stress is ever stored --------------
+// (1) nu_t at the cell centres straight from the velocity; (2) after the ghost fills of nu_t, the
+// divergence of the stress with the stress recomputed at the six / nine points each cell needs, applied to
+// the stage outputs.  Traffic per closure: 4 + (4 + 2 per output field) scalar fields instead of 62.
+template <typename T, int MODEL>
+__global__ void __launch_bounds__(256) les_visc_fused_kernel(Grid<T> g, LesEdge e, const T *__restrict__ u,
+                                                            T *__restrict__ visc, T C) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y * blockDim.y + threadIdx.y + 1, k = blockIdx.z + 1;
+    if (i >= g.N[0] - 1 || j >= g.N[1] - 1) return;
+    const int I[3] = {i, j, k};
+    T M[3][3];
+    if (i == 1 || j == 1 || k == 1)
+        les_collocated_gradient<T, true>(g, e, u, I, M);
+    else
+        les_collocated_gradient<T, false>(g, e, u, I, M);
+    const T dx = __ldg(g.dl[0] + i), dy = __ldg(g.dl[1] + j), dz = __ldg(g.dl[2] + k);
+    visc[i + j * g.s[1] + k * g.s[2]] = eddy_visc_value<T, MODEL>(M, dx, dy, dz, C);
+}
+
+template <typename T, typename CT>
+__global__ void __launch_bounds__(256) les_apply_fused_kernel(Grid<T> g, LesEdge e, const T *__restrict__ u,
+                                                             const T *__restrict__ visc, T *__restrict__ k_out,
+                                                             T *__restrict__ v, double cv, T *__restrict__ acc, double ca) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y * blockDim.y + threadIdx.y + 1, k = blockIdx.z + 1;
+    if (i >= g.N[0] - 1 || j >= g.N[1] - 1) return;
+    const int I[3] = {i, j, k};
+    T f[3];
+    if (i == 1 || j == 1 || k == 1 || i == g.N[0] - 2 || j == g.N[1] - 2 || k == g.N[2] - 2)
+        les_stress_divergence<T, true>(g, e, u, visc, I, f);
+    else
+        les_stress_divergence<T, false>(g, e, u, visc, I, f);
+    const long long idx = i + j * g.s[1] + k * g.s[2];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const T fl = -f[c];
+        const long long q = idx + c * g.cs;
+        if (k_out) k_out[q] += fl;
+        if (v) v[q] = axpy_rn<T, CT>(v[q], cv, fl);
+        if (acc) acc[q] = axpy_rn<T, CT>(acc[q], ca, fl);
+    }
+}
+
+// Ghost-plane sources of a cell field after zero_out_wall! + apply_bc_p! (les_math.cuh); false when a side
+// needs the four-pass path.
+static bool les_edge(const int N[3], const BcDesc &b, LesEdge &e) {
+    if (b.comm) return false;  // a ghost plane of the gradient would need two velocity planes of the neighbour
+    for (int d = 0; d < 3; d++)
+        for (int side = 0; side < 2; side++) {
+            int src;
+            switch (b.bc_u[d][side]) {
+                case INSB200_BC_PERIODIC: src = side ? 1 : N[d] - 2; break;
+                case INSB200_BC_SYMMETRIC: src = side ? N[d] - 2 : 1; break;
+                case INSB200_BC_DIRICHLET: src = -1; break;
+                default: return false;  // PressureBC: two ghost layers
+            }
+            (side ? e.hi : e.lo)[d] = src;
+        }
+    return true;
+}
+
+bool les_needs_tensor(int D, const int N[3], const BcDesc &b, const void *u, const void *k_out, const void *v,
+                      const void *acc) {
+    LesEdge e;
+    if (D != 3 || getenv("INSB200_LES_UNFUSED") != nullptr) return true;  // (read per call: the tests toggle it)
+    if (u == k_out || u == v || u == acc) return true;  // the fused apply kernel reads u around the cells it updates
+    return !les_edge(N, b, e);
+}
+
 template <typename T>
 int launch_les_closure(const Grid<T> &g, const BcDesc &b, int model, double C, const T *u, T *G, T *visc, T *k_out, T *v,
                        double cv, T *acc, double ca, bool ct_double, Launch L) {
@@ -199,6 +204,30 @@ int launch_les_closure(const Grid<T> &g, const BcDesc &b, int model, double C, c
     }
     dim3 blk(64, 4, 1);
     dim3 gr((g.N[0] - 2 + blk.x - 1) / blk.x, (g.N[1] - 2 + blk.y - 1) / blk.y, g.N[2] - 2);
+    if (!les_needs_tensor(g.D, g.N, b, u, k_out, v, acc)) {
+        LesEdge e;
+        les_edge(g.N, b, e);
+        switch (model) {
+            case 1: les_visc_fused_kernel<T, 1><<<gr, blk, 0, L.stream>>>(g, e, u, visc, (T)C); break;
+            case 2: les_visc_fused_kernel<T, 2><<<gr, blk, 0, L.stream>>>(g, e, u, visc, (T)C); break;
+            case 3: les_visc_fused_kernel<T, 3><<<gr, blk, 0, L.stream>>>(g, e, u, visc, (T)C); break;
+            default: les_visc_fused_kernel<T, 4><<<gr, blk, 0, L.stream>>>(g, e, u, visc, (T)C); break;
+        }
+        if (L.counter) ++*L.counter;
+        INSB_TRY(launch_zero_out_wall<T>(g, b, visc, 1, L));
+        INSB_TRY(launch_bc_p_fields<T>(g, b, visc, 1, L));
+        if (sizeof(T) == 8 || ct_double)
+            les_apply_fused_kernel<T, double><<<gr, blk, 0, L.stream>>>(g, e, u, visc, k_out, v, cv, acc, ca);
+        else
+            les_apply_fused_kernel<T, T><<<gr, blk, 0, L.stream>>>(g, e, u, visc, k_out, v, cv, acc, ca);
+        if (L.counter) ++*L.counter;
+        INSB_CUDA(cudaGetLastError());
+        return 0;
+    }
+    if (!G) {
+        set_error("eddy_viscosity_closure!: the four-pass path needs the tensor scratch (les_needs_tensor)");
+        return 1;
+    }
     // fill!(visc, 0); fill!(g, 0) (:358-361): every interior entry is written below and every ghost
     // plane by zero_out_wall! / apply_bc_p!, except the second ghost layer of a PressureBC side
     bool pressure_bc = false;

@@ -1,0 +1,236 @@
+// les_math.cuh -- point functions of the eddy-viscosity closure (src/eddyviscosity.jl), shared by the
+// four-pass kernels and the two fused kernels of les.cu.  Everything here is __host__ __device__ so
+// that tests/host_les.cu can run the very same cell functions on the CPU against the oracle.
+//
+// The fused kernels never store the gradient tensor or the stress: a value of such a cell field at a
+// neighbour J of cell I is recomputed from the velocity.  When J lies on a ghost plane the reference
+// would read what zero_out_wall! (:344-353) followed by apply_bc_p! (boundary_conditions.jl:200-208)
+// left there.  Both act plane by plane over the full extent of the other dimensions, dimensions in
+// order, so the ghost entry equals -- dimension by dimension, independently --
+//   periodic  : the entry of the opposite interior plane      (N-2 for plane 0, 1 for plane N-1)
+//   symmetric : the entry of the adjacent interior plane      (1 for plane 0, N-2 for plane N-1)
+//   Dirichlet : zero (zeroed by zero_out_wall!, apply_bc_p! is a no-op there, and a later copy along
+//               another dimension copies a zero)
+// LesEdge carries that per-dimension source plane (-1 = zero).  PressureBC sides (two ghost layers) and
+// decomposed directions are left to the four-pass path.
+#pragma once
+#include "internal.h"
+
+namespace insb {
+
+#if defined(__CUDA_ARCH__)
+#define LES_LD(p) __ldg(p)
+#else
+#define LES_LD(p) (*(p))
+#endif
+#define LES_HD __host__ __device__ __forceinline__
+
+struct LesEdge {
+    int lo[3];  // source plane of ghost plane 0 per dimension, -1: the plane is zero
+    int hi[3];  // source plane of ghost plane N-1
+};
+
+template <typename T>
+LES_HD T les_eps();
+template <>
+LES_HD float les_eps<float>() { return 1.1920929e-07f; }
+template <>
+LES_HD double les_eps<double>() { return 2.220446049250313e-16; }
+
+// eddy_viscosity_kernel! bodies (:265-340) on the collocated gradient M[a][b] = du_a/dx_b.
+// MODEL: 1 Smagorinsky, 2 WALE, 3 Vreman, 4 QR
+template <typename T, int MODEL>
+LES_HD T eddy_visc_value(const T (&M)[3][3], T dx, T dy, T dz, T C) {
+    T out;
+    if (MODEL == 3) {  // Vreman (:307-340)
+        const T d1 = dx * dx, d2 = dy * dy, d3 = dz * dz;
+        const T a11 = M[0][0], a21 = M[0][1], a31 = M[0][2];
+        const T a12 = M[1][0], a22 = M[1][1], a32 = M[1][2];
+        const T a13 = M[2][0], a23 = M[2][1], a33 = M[2][2];
+        const T b11 = d1 * a11 * a11 + d2 * a21 * a21 + d3 * a31 * a31;
+        const T b12 = d1 * a11 * a12 + d2 * a21 * a22 + d3 * a31 * a32;
+        const T b13 = d1 * a11 * a13 + d2 * a21 * a23 + d3 * a31 * a33;
+        const T b22 = d1 * a12 * a12 + d2 * a22 * a22 + d3 * a32 * a32;
+        const T b23 = d1 * a12 * a13 + d2 * a22 * a23 + d3 * a32 * a33;
+        const T b33 = d1 * a13 * a13 + d2 * a23 * a23 + d3 * a33 * a33;
+        const T abeta = a11 * a11 + a12 * a12 + a13 * a13 + a21 * a21 + a22 * a22 + a23 * a23 + a31 * a31 + a32 * a32 + a33 * a33;
+        const T bbeta = b11 * b22 - b12 * b12 + b11 * b33 - b13 * b13 + b22 * b33 - b23 * b23;
+        const T value = C * C * sqrt(bbeta / abeta);
+        const T tol = sizeof(T) == 8 ? T(1e-12) : T(1e-6);
+        out = abeta > tol ? value : T(0);
+    } else {
+        const T d = cbrt(dx * dy * dz);  // gridsize_vol (operators.jl:914-915)
+        T S[3][3];
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int b = 0; b < 3; b++) S[a][b] = (M[a][b] + M[b][a]) * T(0.5);
+        T ss = T(0);
+#pragma unroll
+        for (int b = 0; b < 3; b++)
+#pragma unroll
+            for (int a = 0; a < 3; a++) ss += S[a][b] * S[a][b];
+        const T cd2 = (C * d) * (C * d);
+        if (MODEL == 1) {  // Smagorinsky (:265-278)
+            out = cd2 * sqrt(T(2) * ss);
+        } else if (MODEL == 2) {  // WALE (:280-292)
+            T G2[3][3];
+#pragma unroll
+            for (int a = 0; a < 3; a++)
+#pragma unroll
+                for (int b = 0; b < 3; b++) G2[a][b] = M[a][0] * M[0][b] + M[a][1] * M[1][b] + M[a][2] * M[2][b];
+            const T tr3 = (G2[0][0] + G2[1][1] + G2[2][2]) / T(3);
+            T sdsd = T(0);
+#pragma unroll
+            for (int b = 0; b < 3; b++)
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    const T sd = (G2[a][b] + G2[b][a]) * T(0.5) - (a == b ? tr3 : T(0));
+                    sdsd += sd * sd;
+                }
+            out = cd2 * pow(sdsd, T(1.5)) / (pow(ss, T(2.5)) + pow(sdsd, T(1.25)) + les_eps<T>());
+        } else {  // QR (:294-305)
+            T SS[3][3];
+#pragma unroll
+            for (int a = 0; a < 3; a++)
+#pragma unroll
+                for (int b = 0; b < 3; b++) SS[a][b] = S[a][0] * S[0][b] + S[a][1] * S[1][b] + S[a][2] * S[2][b];
+            const T QS = (SS[0][0] + SS[1][1] + SS[2][2]) * T(0.5);
+            T tr = T(0);
+#pragma unroll
+            for (int a = 0; a < 3; a++) tr += SS[a][0] * S[0][a] + SS[a][1] * S[1][a] + SS[a][2] * S[2][a];
+            out = cd2 * fabs(tr / T(3)) / (QS + les_eps<T>());
+        }
+    }
+    return out;
+}
+
+// Where the neighbours I - e_d / I + e_d of cell I are taken from (EDGE: cell I touches a ghost plane).
+template <bool EDGE>
+struct LesNb {
+    int m[3], p[3];    // coordinate of the source of I - e_d / I + e_d
+    bool zm[3], zp[3];  // that neighbour reads as zero
+    template <typename T>
+    LES_HD void init(const Grid<T> &g, const LesEdge &e, const int I[3]) {
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            m[d] = I[d] - 1, p[d] = I[d] + 1;
+            zm[d] = zp[d] = false;
+            if (EDGE) {
+                if (I[d] == 1) {
+                    zm[d] = e.lo[d] < 0;
+                    m[d] = zm[d] ? 1 : e.lo[d];
+                }
+                if (I[d] == g.N[d] - 2) {
+                    zp[d] = e.hi[d] < 0;
+                    p[d] = zp[d] ? I[d] : e.hi[d];
+                }
+            }
+        }
+    }
+};
+
+// collocate_tensor (:235-250) straight from the velocity: M[a][b] at the centre of cell I, the staggered
+// gradients gradient_tensor_kernel! (:57-74) would have stored recomputed at I, I - e_lo, I - e_hi,
+// I - e_lo - e_hi (the reference's summation order)
+template <typename T, bool EDGE>
+LES_HD void les_collocated_gradient(const Grid<T> &g, const LesEdge &e, const T *__restrict__ u, const int I[3], T (&M)[3][3]) {
+    const long long s[3] = {1, g.s[1], g.s[2]};
+    LesNb<EDGE> nb;
+    nb.init(g, e, I);
+    const long long q0 = I[0] + I[1] * s[1] + I[2] * s[2];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const T *ua = u + a * g.cs;
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+            if (a == b) {
+                M[a][a] = (LES_LD(ua + q0) - LES_LD(ua + q0 - s[a])) * LES_LD(g.rdl[a] + I[a]);
+            } else {
+                const int lo = a < b ? a : b, hi = a < b ? b : a;
+                T sum = T(0);
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    int J[3] = {I[0], I[1], I[2]};
+                    bool z = false;
+                    if (c & 1) J[lo] = nb.m[lo], z = z || nb.zm[lo];
+                    if (c & 2) J[hi] = nb.m[hi], z = z || nb.zm[hi];
+                    const long long q = J[0] + J[1] * s[1] + J[2] * s[2];
+                    T v = (LES_LD(ua + q + s[b]) - LES_LD(ua + q)) * LES_LD(g.rdu[b] + J[b]);
+                    if (EDGE && z) v = T(0);
+                    sum = c == 0 ? v : sum + v;
+                }
+                M[a][b] = sum * T(0.25);
+            }
+        }
+    }
+}
+
+// sigma_aa = -2 nu_t du_a/dx_a at the interior cell J (apply_eddy_viscosity_kernel!, :144-181)
+template <typename T>
+LES_HD T les_sigma_diag(const Grid<T> &g, const T *__restrict__ u, const T *__restrict__ visc, int a, const int J[3]) {
+    const long long s[3] = {1, g.s[1], g.s[2]};
+    const long long q = J[0] + J[1] * s[1] + J[2] * s[2];
+    const T *ua = u + a * g.cs + q;
+    const T G = (LES_LD(ua) - LES_LD(ua - s[a])) * LES_LD(g.rdl[a] + J[a]);
+    return T(-2) * LES_LD(visc + q) * G;
+}
+
+// sigma_ab = -2 nu_ab (du_a/dx_b + du_b/dx_a)/2 at the edge point of the interior cell J, a < b; nu_ab is
+// the viscosity interpolated from the four surrounding centres (symmetrize! :81-86 + :144-181)
+template <typename T>
+LES_HD T les_sigma_off(const Grid<T> &g, const T *__restrict__ u, const T *__restrict__ visc, int a, int b, const int J[3]) {
+    const long long s[3] = {1, g.s[1], g.s[2]};
+    const long long q = J[0] + J[1] * s[1] + J[2] * s[2];
+    const T *ua = u + a * g.cs + q, *ub = u + b * g.cs + q;
+    const T Gab = (LES_LD(ua + s[b]) - LES_LD(ua)) * LES_LD(g.rdu[b] + J[b]);
+    const T Gba = (LES_LD(ub + s[a]) - LES_LD(ub)) * LES_LD(g.rdu[a] + J[a]);
+    const T wa_a = LES_LD(g.wa[a] + J[a]), wb_a = LES_LD(g.wb[a] + J[a]);
+    const T wa_b = LES_LD(g.wa[b] + J[b]), wb_b = LES_LD(g.wb[b] + J[b]);
+    const T *v = visc + q;
+    const T nu = wa_a * wa_b * LES_LD(v) + wb_a * wa_b * LES_LD(v + s[a]) + wa_a * wb_b * LES_LD(v + s[b]) +
+                 wb_a * wb_b * LES_LD(v + s[a] + s[b]);
+    return T(-2) * nu * ((Gab + Gba) * T(0.5));
+}
+
+// divoftensor_kernel! (:200-219) with the stress recomputed on the fly: f[a] = sum_b d(sigma_ab)/dx_b at cell I
+template <typename T, bool EDGE>
+LES_HD void les_stress_divergence(const Grid<T> &g, const LesEdge &e, const T *__restrict__ u, const T *__restrict__ visc,
+                                  const int I[3], T (&f)[3]) {
+    LesNb<EDGE> nb;
+    nb.init(g, e, I);
+    // diagonal stresses at I and I + e_a
+    T dterm[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        int J[3] = {I[0], I[1], I[2]};
+        const T s0 = les_sigma_diag<T>(g, u, visc, a, J);
+        J[a] = nb.p[a];
+        T s1 = les_sigma_diag<T>(g, u, visc, a, J);
+        if (EDGE && nb.zp[a]) s1 = T(0);
+        dterm[a] = (s1 - s0) * LES_LD(g.rdu[a] + I[a]);
+    }
+    // off-diagonal stresses at I, I - e_a, I - e_b:  oterm[a][b] = d(sigma_ab)/dx_b
+    T oterm[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = a + 1; b < 3; b++) {
+            int J[3] = {I[0], I[1], I[2]};
+            const T s0 = les_sigma_off<T>(g, u, visc, a, b, J);
+            J[b] = nb.m[b];
+            T sb = les_sigma_off<T>(g, u, visc, a, b, J);
+            if (EDGE && nb.zm[b]) sb = T(0);
+            J[b] = I[b];
+            J[a] = nb.m[a];
+            T sa = les_sigma_off<T>(g, u, visc, a, b, J);
+            if (EDGE && nb.zm[a]) sa = T(0);
+            oterm[a][b] = (s0 - sb) * LES_LD(g.rdl[b] + I[b]);
+            oterm[b][a] = (s0 - sa) * LES_LD(g.rdl[a] + I[a]);
+        }
+    f[0] = dterm[0] + oterm[0][1] + oterm[0][2];
+    f[1] = oterm[1][0] + dterm[1] + oterm[1][2];
+    f[2] = oterm[2][0] + oterm[2][1] + dterm[2];
+}
+
+}  // namespace insb

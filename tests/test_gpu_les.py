@@ -16,6 +16,10 @@ CASES = [
     ("channel", (uniform(16, 4.0), O.tanh_grid(0, 2, 12, 1.4), uniform(8, 2.0)), ("P", "D", "P"), "tridiagonal"),
     ("walls", (O.tanh_grid(0, 1, 12, 1.2), O.tanh_grid(0, 1, 10, 1.1), O.cosine_grid(0, 1, 14)), ("D", "D", "D"), None),
     ("mixed", (uniform(10), O.cosine_grid(0, 1, 8), uniform(12)), ("S", "D", "P"), None),
+    # two x blocks and three y blocks of the 64 x 4 launch tiles, a different BC on either side
+    ("wide", (uniform(70, 3.0), O.tanh_grid(0, 1, 9, 1.2), O.cosine_grid(0, 1, 6)), ("P", ("S", "D"), ("D", "S")), None),
+    # PressureBC side: two ghost layers, stays on the four-pass path (les_needs_tensor)
+    ("outflow", (O.tanh_grid(0, 1, 12, 1.2), uniform(8), uniform(10)), (("D", "O"), "D", "P"), None),
 ]
 MODELS = [("smagorinsky", "Smagorinsky", 0.17), ("wale", "WALE", 0.569), ("vreman", "Vreman", 0.28), ("qr", "QR", 0.092)]
 
@@ -38,6 +42,32 @@ def test_closure_term_matches_oracle(name, x, bcs, kind, mo, mg, C, T):
     scale = max(np.linalg.norm(term_o.ravel()), 1e-300)
     err = np.linalg.norm((term_g - term_o).ravel()) / scale
     assert err < (1e-11 if T is np.float64 else 3e-4), (name, mo, err)
+
+
+@pytest.mark.parametrize("T", [np.float64, np.float32])
+@pytest.mark.parametrize("mo,mg,C", MODELS)
+@pytest.mark.parametrize("name,x,bcs,kind", CASES[:5])
+def test_fused_closure_equals_four_pass_closure(name, x, bcs, kind, mo, mg, C, T, monkeypatch):
+    """Default path (two fused kernels, nothing but nu_t stored) against the four-pass path with the stored
+    gradient / stress tensors (INSB200_LES_UNFUSED): same arithmetic up to the reciprocal metric tables."""
+    import insb200 as I
+
+    so, sg = make_setups(x, bcs, T=T)
+    u = I.to_device(sg, smooth_vec(so, 201))
+    f0 = smooth_vec(so, 202)
+    out = []
+    for unfused in (False, True):
+        if unfused:
+            monkeypatch.setenv("INSB200_LES_UNFUSED", "1")
+        else:
+            monkeypatch.delenv("INSB200_LES_UNFUSED", raising=False)
+        fd = I.to_device(sg, f0)
+        I.eddy_viscosity_closure_(getattr(I, mg)(C), fd, u, None, sg)
+        out.append(I.to_host(fd) - f0)
+    scale = max(np.linalg.norm(out[1].ravel()), 1e-300)
+    err = np.linalg.norm((out[0] - out[1]).ravel()) / scale
+    assert err < (1e-12 if T is np.float64 else 1e-5), (name, mo, err)
+    assert scale > 1e-6
 
 
 @pytest.mark.parametrize("T", [np.float64, np.float32])
