@@ -127,34 +127,35 @@ __global__ void __launch_bounds__(256) les_divergence_kernel(Grid<T> g, const T 
 // (1) nu_t at the cell centres straight from the velocity; (2) after the ghost fills of nu_t, the
 // divergence of the stress with the stress recomputed at the six / nine points each cell needs, applied to
 // the stage outputs.  Traffic per closure: 4 + (4 + 2 per output field) scalar fields instead of 62.
+// Default: tile kernels -- a block marches a TX x TY column along z with the planes z-1, z, z+1 of
+// (u_x, u_y, u_z[, nu_t]) and a one-cell halo in a 4-slot shared-memory ring (the next plane prefetched
+// into registers during the arithmetic), so the ~55 / ~105 neighbour reads per cell are shared-memory
+// reads.  INSB200_LES_TILE=0: one thread per cell, neighbours through L1 / L2.
+struct LesBox {  // half-open index box the one-thread-per-cell kernels cover
+    int lo[3], hi[3];
+};
+
 template <typename T, int MODEL>
-__global__ void __launch_bounds__(256) les_visc_fused_kernel(Grid<T> g, LesEdge e, const T *__restrict__ u,
+__global__ void __launch_bounds__(256) les_visc_fused_kernel(Grid<T> g, LesEdge e, LesBox bx, const T *__restrict__ u,
                                                             T *__restrict__ visc, T C) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y * blockDim.y + threadIdx.y + 1, k = blockIdx.z + 1;
-    if (i >= g.N[0] - 1 || j >= g.N[1] - 1) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + bx.lo[0], j = blockIdx.y * blockDim.y + threadIdx.y + bx.lo[1];
+    const int k = blockIdx.z + bx.lo[2];
+    if (i >= bx.hi[0] || j >= bx.hi[1]) return;
     const int I[3] = {i, j, k};
+    const long long idx = i + j * g.s[1] + k * g.s[2];
+    const LesGLoad<T> U{u + idx, g.s[1], g.s[2], g.cs};
     T M[3][3];
     if (i == 1 || j == 1 || k == 1)
-        les_collocated_gradient<T, true>(g, e, u, I, M);
+        les_collocated_gradient<T, true>(g, e, U, I, M);
     else
-        les_collocated_gradient<T, false>(g, e, u, I, M);
+        les_collocated_gradient<T, false>(g, e, U, I, M);
     const T dx = __ldg(g.dl[0] + i), dy = __ldg(g.dl[1] + j), dz = __ldg(g.dl[2] + k);
-    visc[i + j * g.s[1] + k * g.s[2]] = eddy_visc_value<T, MODEL>(M, dx, dy, dz, C);
+    visc[idx] = eddy_visc_value<T, MODEL>(M, dx, dy, dz, C);
 }
 
 template <typename T, typename CT>
-__global__ void __launch_bounds__(256) les_apply_fused_kernel(Grid<T> g, LesEdge e, const T *__restrict__ u,
-                                                             const T *__restrict__ visc, T *__restrict__ k_out,
-                                                             T *__restrict__ v, double cv, T *__restrict__ acc, double ca) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y * blockDim.y + threadIdx.y + 1, k = blockIdx.z + 1;
-    if (i >= g.N[0] - 1 || j >= g.N[1] - 1) return;
-    const int I[3] = {i, j, k};
-    T f[3];
-    if (i == 1 || j == 1 || k == 1 || i == g.N[0] - 2 || j == g.N[1] - 2 || k == g.N[2] - 2)
-        les_stress_divergence<T, true>(g, e, u, visc, I, f);
-    else
-        les_stress_divergence<T, false>(g, e, u, visc, I, f);
-    const long long idx = i + j * g.s[1] + k * g.s[2];
+__device__ __forceinline__ void les_apply_cell(const Grid<T> &g, long long idx, const T (&f)[3], T *__restrict__ k_out,
+                                               T *__restrict__ v, double cv, T *__restrict__ acc, double ca) {
 #pragma unroll
     for (int c = 0; c < 3; c++) {
         const T fl = -f[c];
@@ -165,20 +166,204 @@ __global__ void __launch_bounds__(256) les_apply_fused_kernel(Grid<T> g, LesEdge
     }
 }
 
-// Ghost-plane sources of a cell field after zero_out_wall! + apply_bc_p! (les_math.cuh); false when a side
-// needs the four-pass path.
-static bool les_edge(const int N[3], const BcDesc &b, LesEdge &e) {
+template <typename T, typename CT>
+__global__ void __launch_bounds__(256) les_apply_fused_kernel(Grid<T> g, LesEdge e, LesBox bx, const T *__restrict__ u,
+                                                             const T *__restrict__ visc, T *__restrict__ k_out,
+                                                             T *__restrict__ v, double cv, T *__restrict__ acc, double ca) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + bx.lo[0], j = blockIdx.y * blockDim.y + threadIdx.y + bx.lo[1];
+    const int k = blockIdx.z + bx.lo[2];
+    if (i >= bx.hi[0] || j >= bx.hi[1]) return;
+    const int I[3] = {i, j, k};
+    const long long idx = i + j * g.s[1] + k * g.s[2];
+    const LesGLoad<T> U{u + idx, g.s[1], g.s[2], g.cs}, V{visc + idx, g.s[1], g.s[2], 0};
+    T f[3];
+    if (i == 1 || j == 1 || k == 1 || i == g.N[0] - 2 || j == g.N[1] - 2 || k == g.N[2] - 2)
+        les_stress_divergence<T, true>(g, e, U, V, I, f);
+    else
+        les_stress_divergence<T, false>(g, e, U, V, I, f);
+    les_apply_cell<T, CT>(g, idx, f, k_out, v, cv, acc, ca);
+}
+
+// shared planes of the tile kernels: pl[dz + 1] points at field 0 of this thread's cell in plane z + dz
+template <typename T, int PX, int PLANE>
+struct LesTileLoad {
+    const T *pl[3];
+    int f0;  // first field (the viscosity is field 3 of the apply kernel's ring)
+    __device__ __forceinline__ T operator()(int c, int dx, int dy, int dz) const {
+        return pl[dz + 1][(f0 + c) * PLANE + dy * PX + dx];
+    }
+};
+
+// MODEL > 0: viscosity kernel (fields u_x, u_y, u_z; writes nu_t); MODEL == 0: apply kernel (fields u_x, u_y,
+// u_z, nu_t; updates k_out / v / acc).  The cells next to a ghost plane are left to the one-thread-per-cell
+// kernels (launch_les_shell): the ghost rules cost 46 registers here, i.e. one of two resident blocks.
+template <typename T, typename CT, int MODEL, int TX, int TY, int ZC>
+__global__ void __launch_bounds__(TX *TY) les_tile_kernel(Grid<T> g, LesEdge e, const T *__restrict__ u,
+                                                         const T *__restrict__ visc_in, T *__restrict__ visc_out, T C,
+                                                         T *__restrict__ k_out, T *__restrict__ v, double cv,
+                                                         T *__restrict__ acc, double ca) {
+    constexpr int NF = MODEL == 0 ? 4 : 3;
+    constexpr int PX = TX + 2, PY = TY + 2, PLANE = PX * PY, NT = TX * TY, NE = NF * PLANE;
+    constexpr int NL = (NE + NT - 1) / NT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *s = reinterpret_cast<T *>(smem_raw);  // [4 slots][NF fields][PY][PX]
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
+    const int x0 = 1 + blockIdx.x * TX, y0 = 1 + blockIdx.y * TY;
+    const int zbeg = 1 + blockIdx.z * ZC;
+    const int zend = min(zbeg + ZC, g.N[2] - 1);
+    if (zbeg >= zend) return;
+    const T *lp[NL];
+    bool lv[NL];
+#pragma unroll
+    for (int i = 0; i < NL; i++) {
+        const int el = min(tid + i * NT, NE - 1);
+        const int c = el / PLANE, r = el - c * PLANE;
+        const int py = r / PX, px = r - py * PX;
+        const int gx = min(x0 - 1 + px, g.N[0] - 1), gy = min(y0 - 1 + py, g.N[1] - 1);
+        lv[i] = tid + i * NT < NE;
+        const T *base = c < 3 ? u + c * g.cs : visc_in;
+        lp[i] = base + gx + (long long)gy * g.s[1] + (long long)(zbeg - 1) * g.s[2];
+    }
+    T reg[NL];
+    const long long zs = g.s[2];
+    auto load_plane = [&]() {
+#pragma unroll
+        for (int i = 0; i < NL; i++) {
+            if (lv[i]) reg[i] = __ldg(lp[i]);
+            lp[i] += zs;
+        }
+    };
+    auto store_plane = [&](int z) {
+        T *dst = s + (z & 3) * NE + tid;
+#pragma unroll
+        for (int i = 0; i < NL; i++)
+            if (lv[i]) dst[i * NT] = reg[i];
+    };
+    for (int p = -1; p <= 1; p++) {
+        load_plane();
+        store_plane(zbeg + p);
+    }
+    const int I0 = x0 + tx, I1 = y0 + ty;
+    const bool active = I0 < g.N[0] - 1 && I1 < g.N[1] - 1;
+    const int Ic0 = min(I0, g.N[0] - 2), Ic1 = min(I1, g.N[1] - 2);
+    const bool edge_xy = Ic0 == 1 || Ic1 == 1 || Ic0 == g.N[0] - 2 || Ic1 == g.N[1] - 2;
+    __syncthreads();
+    const int lidx = (ty + 1) * PX + tx + 1;
+    long long idx = Ic0 + (long long)Ic1 * g.s[1] + (long long)zbeg * g.s[2];
+    for (int z = zbeg; z < zend; z++, idx += zs) {
+        const bool more = z + 1 < zend;
+        if (more) load_plane();
+        if (active) {
+            const int I[3] = {Ic0, Ic1, z};
+            LesTileLoad<T, PX, PLANE> U, V;
+#pragma unroll
+            for (int k = 0; k < 3; k++) U.pl[k] = V.pl[k] = s + ((z - 1 + k) & 3) * NE + lidx;
+            U.f0 = 0, V.f0 = 3;
+            const bool edge = edge_xy || z == 1 || z == g.N[2] - 2;
+            if (edge) {
+            } else if (MODEL > 0) {
+                T M[3][3];
+                les_collocated_gradient<T, false>(g, e, U, I, M);
+                const T dx = __ldg(g.dl[0] + Ic0), dy = __ldg(g.dl[1] + Ic1), dz = __ldg(g.dl[2] + z);
+                visc_out[idx] = eddy_visc_value<T, (MODEL > 0 ? MODEL : 1)>(M, dx, dy, dz, C);
+            } else {
+                T f[3];
+                les_stress_divergence<T, false>(g, e, U, V, I, f);
+                les_apply_cell<T, CT>(g, idx, f, k_out, v, cv, acc, ca);
+            }
+        }
+        if (more) store_plane(z + 2);
+        __syncthreads();
+    }
+}
+
+template <typename T, typename CT, int MODEL>
+static int launch_les_tile(const Grid<T> &g, const LesEdge &e, const T *u, const T *visc_in, T *visc_out, T C, T *k_out, T *v,
+                           double cv, T *acc, double ca, Launch L) {
+    constexpr int TX = 32, TY = 8, ZC = 64, NF = MODEL == 0 ? 4 : 3;
+    constexpr size_t smem = (size_t)4 * NF * (TX + 2) * (TY + 2) * sizeof(T);
+    dim3 b(TX, TY, 1);
+    dim3 gr((g.N[0] - 2 + TX - 1) / TX, (g.N[1] - 2 + TY - 1) / TY, (g.N[2] - 2 + ZC - 1) / ZC);
+    les_tile_kernel<T, CT, MODEL, TX, TY, ZC><<<gr, b, smem, L.stream>>>(g, e, u, visc_in, visc_out, C, k_out, v, cv, acc, ca);
+    if (L.counter) ++*L.counter;
+    INSB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// The cells with a ghost-plane neighbour as at most six disjoint boxes (z faces, y faces without the z faces, x
+// faces without both); fn(box) launches a one-thread-per-cell kernel on each.
+template <typename T, typename F>
+static int les_for_shell_boxes(const Grid<T> &g, F fn) {
+    int face[3][2], nface[3], in_lo[3], in_hi[3];
+    for (int d = 0; d < 3; d++) {
+        face[d][0] = 1, face[d][1] = g.N[d] - 2;
+        nface[d] = g.N[d] - 2 > 1 ? 2 : 1;
+        in_lo[d] = 2, in_hi[d] = g.N[d] - 2;  // interior of the interior (may be empty)
+    }
+    for (int d = 2; d >= 0; d--)
+        for (int f = 0; f < nface[d]; f++) {
+            LesBox bx;
+            bool empty = false;
+            for (int c = 0; c < 3; c++) {
+                if (c == d)
+                    bx.lo[c] = face[d][f], bx.hi[c] = face[d][f] + 1;
+                else if (c > d)
+                    bx.lo[c] = in_lo[c], bx.hi[c] = in_hi[c];
+                else
+                    bx.lo[c] = 1, bx.hi[c] = g.N[c] - 1;
+                empty = empty || bx.hi[c] <= bx.lo[c];
+            }
+            if (!empty) INSB_TRY(fn(bx));
+        }
+    return 0;
+}
+
+static void les_box_launch(const LesBox &bx, dim3 &gr, dim3 &blk) {
+    const int ex = bx.hi[0] - bx.lo[0], ey = bx.hi[1] - bx.lo[1];
+    blk = ex >= 64 ? dim3(64, 4, 1) : ex >= 8 ? dim3(8, 32, 1) : dim3(1, 256, 1);
+    gr = dim3((ex + blk.x - 1) / blk.x, (ey + blk.y - 1) / blk.y, bx.hi[2] - bx.lo[2]);
+}
+
+template <typename T>
+static int launch_les_visc_box(const Grid<T> &g, const LesEdge &e, const LesBox &bx, int model, const T *u, T *visc, T C,
+                               Launch L) {
+    dim3 gr, blk;
+    les_box_launch(bx, gr, blk);
+    switch (model) {
+        case 1: les_visc_fused_kernel<T, 1><<<gr, blk, 0, L.stream>>>(g, e, bx, u, visc, C); break;
+        case 2: les_visc_fused_kernel<T, 2><<<gr, blk, 0, L.stream>>>(g, e, bx, u, visc, C); break;
+        case 3: les_visc_fused_kernel<T, 3><<<gr, blk, 0, L.stream>>>(g, e, bx, u, visc, C); break;
+        default: les_visc_fused_kernel<T, 4><<<gr, blk, 0, L.stream>>>(g, e, bx, u, visc, C); break;
+    }
+    if (L.counter) ++*L.counter;
+    INSB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+static int launch_les_apply_box(const Grid<T> &g, const LesEdge &e, const LesBox &bx, const T *u, const T *visc, T *k_out,
+                                T *v, double cv, T *acc, double ca, bool wide, Launch L) {
+    dim3 gr, blk;
+    les_box_launch(bx, gr, blk);
+    if (wide)
+        les_apply_fused_kernel<T, double><<<gr, blk, 0, L.stream>>>(g, e, bx, u, visc, k_out, v, cv, acc, ca);
+    else
+        les_apply_fused_kernel<T, T><<<gr, blk, 0, L.stream>>>(g, e, bx, u, visc, k_out, v, cv, acc, ca);
+    if (L.counter) ++*L.counter;
+    INSB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// BC kinds of the ghost planes of a cell field after zero_out_wall! + apply_bc_p! (les_math.cuh); false when a
+// side needs the four-pass path.
+static bool les_edge(const BcDesc &b, LesEdge &e) {
     if (b.comm) return false;  // a ghost plane of the gradient would need two velocity planes of the neighbour
     for (int d = 0; d < 3; d++)
         for (int side = 0; side < 2; side++) {
-            int src;
-            switch (b.bc_u[d][side]) {
-                case INSB200_BC_PERIODIC: src = side ? 1 : N[d] - 2; break;
-                case INSB200_BC_SYMMETRIC: src = side ? N[d] - 2 : 1; break;
-                case INSB200_BC_DIRICHLET: src = -1; break;
-                default: return false;  // PressureBC: two ghost layers
-            }
-            (side ? e.hi : e.lo)[d] = src;
+            const int bc = b.bc_u[d][side];
+            if (bc != INSB200_BC_PERIODIC && bc != INSB200_BC_SYMMETRIC && bc != INSB200_BC_DIRICHLET)
+                return false;  // PressureBC: two ghost layers
+            (side ? e.hi : e.lo)[d] = bc;
         }
     return true;
 }
@@ -188,7 +373,8 @@ bool les_needs_tensor(int D, const int N[3], const BcDesc &b, const void *u, con
     LesEdge e;
     if (D != 3 || getenv("INSB200_LES_UNFUSED") != nullptr) return true;  // (read per call: the tests toggle it)
     if (u == k_out || u == v || u == acc) return true;  // the fused apply kernel reads u around the cells it updates
-    return !les_edge(N, b, e);
+    (void)N;
+    return !les_edge(b, e);
 }
 
 template <typename T>
@@ -206,22 +392,35 @@ int launch_les_closure(const Grid<T> &g, const BcDesc &b, int model, double C, c
     dim3 gr((g.N[0] - 2 + blk.x - 1) / blk.x, (g.N[1] - 2 + blk.y - 1) / blk.y, g.N[2] - 2);
     if (!les_needs_tensor(g.D, g.N, b, u, k_out, v, acc)) {
         LesEdge e;
-        les_edge(g.N, b, e);
-        switch (model) {
-            case 1: les_visc_fused_kernel<T, 1><<<gr, blk, 0, L.stream>>>(g, e, u, visc, (T)C); break;
-            case 2: les_visc_fused_kernel<T, 2><<<gr, blk, 0, L.stream>>>(g, e, u, visc, (T)C); break;
-            case 3: les_visc_fused_kernel<T, 3><<<gr, blk, 0, L.stream>>>(g, e, u, visc, (T)C); break;
-            default: les_visc_fused_kernel<T, 4><<<gr, blk, 0, L.stream>>>(g, e, u, visc, (T)C); break;
+        les_edge(b, e);
+        const char *te = getenv("INSB200_LES_TILE");  // (read per call: the tests toggle it)
+        const bool tile = !te || atoi(te) != 0;
+        const bool wide = sizeof(T) == 8 || ct_double;
+        LesBox all;
+        for (int d = 0; d < 3; d++) all.lo[d] = 1, all.hi[d] = g.N[d] - 1;
+        if (tile) {
+            switch (model) {
+                case 1: INSB_TRY((launch_les_tile<T, T, 1>(g, e, u, nullptr, visc, (T)C, nullptr, nullptr, 0, nullptr, 0, L))); break;
+                case 2: INSB_TRY((launch_les_tile<T, T, 2>(g, e, u, nullptr, visc, (T)C, nullptr, nullptr, 0, nullptr, 0, L))); break;
+                case 3: INSB_TRY((launch_les_tile<T, T, 3>(g, e, u, nullptr, visc, (T)C, nullptr, nullptr, 0, nullptr, 0, L))); break;
+                default: INSB_TRY((launch_les_tile<T, T, 4>(g, e, u, nullptr, visc, (T)C, nullptr, nullptr, 0, nullptr, 0, L))); break;
+            }
+            INSB_TRY(les_for_shell_boxes<T>(g, [&](const LesBox &bx) { return launch_les_visc_box<T>(g, e, bx, model, u, visc, (T)C, L); }));
+        } else {
+            INSB_TRY(launch_les_visc_box<T>(g, e, all, model, u, visc, (T)C, L));
         }
-        if (L.counter) ++*L.counter;
         INSB_TRY(launch_zero_out_wall<T>(g, b, visc, 1, L));
         INSB_TRY(launch_bc_p_fields<T>(g, b, visc, 1, L));
-        if (sizeof(T) == 8 || ct_double)
-            les_apply_fused_kernel<T, double><<<gr, blk, 0, L.stream>>>(g, e, u, visc, k_out, v, cv, acc, ca);
-        else
-            les_apply_fused_kernel<T, T><<<gr, blk, 0, L.stream>>>(g, e, u, visc, k_out, v, cv, acc, ca);
-        if (L.counter) ++*L.counter;
-        INSB_CUDA(cudaGetLastError());
+        if (tile) {
+            if (wide)
+                INSB_TRY((launch_les_tile<T, double, 0>(g, e, u, visc, nullptr, (T)0, k_out, v, cv, acc, ca, L)));
+            else
+                INSB_TRY((launch_les_tile<T, T, 0>(g, e, u, visc, nullptr, (T)0, k_out, v, cv, acc, ca, L)));
+            INSB_TRY(les_for_shell_boxes<T>(
+                g, [&](const LesBox &bx) { return launch_les_apply_box<T>(g, e, bx, u, visc, k_out, v, cv, acc, ca, wide, L); }));
+        } else {
+            INSB_TRY(launch_les_apply_box<T>(g, e, all, u, visc, k_out, v, cv, acc, ca, wide, L));
+        }
         return 0;
     }
     if (!G) {

@@ -11,7 +11,7 @@
 //   symmetric : the entry of the adjacent interior plane      (1 for plane 0, N-2 for plane N-1)
 //   Dirichlet : zero (zeroed by zero_out_wall!, apply_bc_p! is a no-op there, and a later copy along
 //               another dimension copies a zero)
-// LesEdge carries that per-dimension source plane (-1 = zero).  PressureBC sides (two ghost layers) and
+// LesEdge carries the BC kind per dimension and side.  PressureBC sides (two ghost layers) and
 // decomposed directions are left to the four-pass path.
 #pragma once
 #include "internal.h"
@@ -26,8 +26,7 @@ namespace insb {
 #define LES_HD __host__ __device__ __forceinline__
 
 struct LesEdge {
-    int lo[3];  // source plane of ghost plane 0 per dimension, -1: the plane is zero
-    int hi[3];  // source plane of ghost plane N-1
+    int lo[3], hi[3];  // INSB200_BC_PERIODIC / _SYMMETRIC / _DIRICHLET per dimension and side
 };
 
 template <typename T>
@@ -88,7 +87,9 @@ LES_HD T eddy_visc_value(const T (&M)[3][3], T dx, T dy, T dz, T C) {
                     const T sd = (G2[a][b] + G2[b][a]) * T(0.5) - (a == b ? tr3 : T(0));
                     sdsd += sd * sd;
                 }
-            out = cd2 * pow(sdsd, T(1.5)) / (pow(ss, T(2.5)) + pow(sdsd, T(1.25)) + les_eps<T>());
+            // x^(3/2), x^(5/2), x^(5/4) by square roots (three pow calls cost more than the rest of the kernel)
+            const T rs = sqrt(sdsd), rq = sqrt(ss);
+            out = cd2 * (sdsd * rs) / (ss * ss * rq + sdsd * sqrt(rs) + les_eps<T>());
         } else {  // QR (:294-305)
             T SS[3][3];
 #pragma unroll
@@ -105,25 +106,47 @@ LES_HD T eddy_visc_value(const T (&M)[3][3], T dx, T dy, T dz, T C) {
     return out;
 }
 
-// Where the neighbours I - e_d / I + e_d of cell I are taken from (EDGE: cell I touches a ghost plane).
+// Field access relative to the current cell: U(c, dx, dy, dz) = component c at I + (dx, dy, dz), offsets in
+// [-1, 1].  LesGLoad reads global memory (p = component 0 at the cell); the tile kernels read shared planes.
+template <typename T>
+struct LesGLoad {
+    const T *p;
+    long long s1, s2, cs;
+    LES_HD T operator()(int c, int dx, int dy, int dz) const { return LES_LD(p + c * cs + dx + dy * s1 + dz * s2); }
+};
+
+// Where the values of a cell field at the neighbours I - e_d / I + e_d come from (EDGE: cell I touches a
+// ghost plane).  Periodic: the velocity / viscosity ghost planes hold the periodic images, so the stencil is
+// evaluated at the ghost position itself, only the metric tables are taken at the image (N-2 resp. 1: the
+// ghost entries of the tables are not periodic images).  Symmetric: the cell itself.  Dirichlet: zero.
 template <bool EDGE>
 struct LesNb {
-    int m[3], p[3];    // coordinate of the source of I - e_d / I + e_d
+    int om[3], op[3];   // field offset of the source of I - e_d / I + e_d
+    int tm[3], tp[3];   // metric-table index of that source
     bool zm[3], zp[3];  // that neighbour reads as zero
     template <typename T>
     LES_HD void init(const Grid<T> &g, const LesEdge &e, const int I[3]) {
 #pragma unroll
         for (int d = 0; d < 3; d++) {
-            m[d] = I[d] - 1, p[d] = I[d] + 1;
+            om[d] = -1, op[d] = 1;
+            tm[d] = I[d] - 1, tp[d] = I[d] + 1;
             zm[d] = zp[d] = false;
             if (EDGE) {
                 if (I[d] == 1) {
-                    zm[d] = e.lo[d] < 0;
-                    m[d] = zm[d] ? 1 : e.lo[d];
+                    if (e.lo[d] == INSB200_BC_PERIODIC) {
+                        tm[d] = g.N[d] - 2;
+                    } else {
+                        om[d] = 0, tm[d] = 1;
+                        zm[d] = e.lo[d] != INSB200_BC_SYMMETRIC;
+                    }
                 }
                 if (I[d] == g.N[d] - 2) {
-                    zp[d] = e.hi[d] < 0;
-                    p[d] = zp[d] ? I[d] : e.hi[d];
+                    if (e.hi[d] == INSB200_BC_PERIODIC) {
+                        tp[d] = 1;
+                    } else {
+                        op[d] = 0, tp[d] = I[d];
+                        zp[d] = e.hi[d] != INSB200_BC_SYMMETRIC;
+                    }
                 }
             }
         }
@@ -133,30 +156,35 @@ struct LesNb {
 // collocate_tensor (:235-250) straight from the velocity: M[a][b] at the centre of cell I, the staggered
 // gradients gradient_tensor_kernel! (:57-74) would have stored recomputed at I, I - e_lo, I - e_hi,
 // I - e_lo - e_hi (the reference's summation order)
-template <typename T, bool EDGE>
-LES_HD void les_collocated_gradient(const Grid<T> &g, const LesEdge &e, const T *__restrict__ u, const int I[3], T (&M)[3][3]) {
-    const long long s[3] = {1, g.s[1], g.s[2]};
+template <typename T, bool EDGE, typename LU>
+LES_HD void les_collocated_gradient(const Grid<T> &g, const LesEdge &e, const LU &U, const int I[3], T (&M)[3][3]) {
     LesNb<EDGE> nb;
     nb.init(g, e, I);
-    const long long q0 = I[0] + I[1] * s[1] + I[2] * s[2];
 #pragma unroll
     for (int a = 0; a < 3; a++) {
-        const T *ua = u + a * g.cs;
 #pragma unroll
         for (int b = 0; b < 3; b++) {
             if (a == b) {
-                M[a][a] = (LES_LD(ua + q0) - LES_LD(ua + q0 - s[a])) * LES_LD(g.rdl[a] + I[a]);
+                M[a][a] = (U(a, 0, 0, 0) - U(a, a == 0 ? -1 : 0, a == 1 ? -1 : 0, a == 2 ? -1 : 0)) * LES_LD(g.rdl[a] + I[a]);
             } else {
                 const int lo = a < b ? a : b, hi = a < b ? b : a;
                 T sum = T(0);
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
-                    int J[3] = {I[0], I[1], I[2]};
+                    int o[3] = {0, 0, 0};
+                    int tb = I[b];
                     bool z = false;
-                    if (c & 1) J[lo] = nb.m[lo], z = z || nb.zm[lo];
-                    if (c & 2) J[hi] = nb.m[hi], z = z || nb.zm[hi];
-                    const long long q = J[0] + J[1] * s[1] + J[2] * s[2];
-                    T v = (LES_LD(ua + q + s[b]) - LES_LD(ua + q)) * LES_LD(g.rdu[b] + J[b]);
+                    if (c & 1) {
+                        o[lo] = nb.om[lo], z = z || nb.zm[lo];
+                        if (lo == b) tb = nb.tm[lo];
+                    }
+                    if (c & 2) {
+                        o[hi] = nb.om[hi], z = z || nb.zm[hi];
+                        if (hi == b) tb = nb.tm[hi];
+                    }
+                    int o2[3] = {o[0], o[1], o[2]};
+                    o2[b] += 1;
+                    T v = (U(a, o2[0], o2[1], o2[2]) - U(a, o[0], o[1], o[2])) * LES_LD(g.rdu[b] + tb);
                     if (EDGE && z) v = T(0);
                     sum = c == 0 ? v : sum + v;
                 }
@@ -166,47 +194,45 @@ LES_HD void les_collocated_gradient(const Grid<T> &g, const LesEdge &e, const T 
     }
 }
 
-// sigma_aa = -2 nu_t du_a/dx_a at the interior cell J (apply_eddy_viscosity_kernel!, :144-181)
-template <typename T>
-LES_HD T les_sigma_diag(const Grid<T> &g, const T *__restrict__ u, const T *__restrict__ visc, int a, const int J[3]) {
-    const long long s[3] = {1, g.s[1], g.s[2]};
-    const long long q = J[0] + J[1] * s[1] + J[2] * s[2];
-    const T *ua = u + a * g.cs + q;
-    const T G = (LES_LD(ua) - LES_LD(ua - s[a])) * LES_LD(g.rdl[a] + J[a]);
-    return T(-2) * LES_LD(visc + q) * G;
+// sigma_aa = -2 nu_t du_a/dx_a at the cell I + o (apply_eddy_viscosity_kernel!, :144-181); ta = index of the
+// metric tables of dimension a there
+template <typename T, typename LU, typename LV>
+LES_HD T les_sigma_diag(const Grid<T> &g, const LU &U, const LV &V, int a, const int o[3], int ta) {
+    int o1[3] = {o[0], o[1], o[2]};
+    o1[a] -= 1;
+    const T G = (U(a, o[0], o[1], o[2]) - U(a, o1[0], o1[1], o1[2])) * LES_LD(g.rdl[a] + ta);
+    return T(-2) * V(0, o[0], o[1], o[2]) * G;
 }
 
-// sigma_ab = -2 nu_ab (du_a/dx_b + du_b/dx_a)/2 at the edge point of the interior cell J, a < b; nu_ab is
-// the viscosity interpolated from the four surrounding centres (symmetrize! :81-86 + :144-181)
-template <typename T>
-LES_HD T les_sigma_off(const Grid<T> &g, const T *__restrict__ u, const T *__restrict__ visc, int a, int b, const int J[3]) {
-    const long long s[3] = {1, g.s[1], g.s[2]};
-    const long long q = J[0] + J[1] * s[1] + J[2] * s[2];
-    const T *ua = u + a * g.cs + q, *ub = u + b * g.cs + q;
-    const T Gab = (LES_LD(ua + s[b]) - LES_LD(ua)) * LES_LD(g.rdu[b] + J[b]);
-    const T Gba = (LES_LD(ub + s[a]) - LES_LD(ub)) * LES_LD(g.rdu[a] + J[a]);
-    const T wa_a = LES_LD(g.wa[a] + J[a]), wb_a = LES_LD(g.wb[a] + J[a]);
-    const T wa_b = LES_LD(g.wa[b] + J[b]), wb_b = LES_LD(g.wb[b] + J[b]);
-    const T *v = visc + q;
-    const T nu = wa_a * wa_b * LES_LD(v) + wb_a * wa_b * LES_LD(v + s[a]) + wa_a * wb_b * LES_LD(v + s[b]) +
-                 wb_a * wb_b * LES_LD(v + s[a] + s[b]);
+// sigma_ab = -2 nu_ab (du_a/dx_b + du_b/dx_a)/2 at the edge point of the cell I + o, a < b; nu_ab is the
+// viscosity interpolated from the four surrounding centres (symmetrize! :81-86 + :144-181); ta, tb = indices
+// of the metric tables of dimensions a and b there
+template <typename T, typename LU, typename LV>
+LES_HD T les_sigma_off(const Grid<T> &g, const LU &U, const LV &V, int a, int b, const int o[3], int ta, int tb) {
+    int oa[3] = {o[0], o[1], o[2]}, ob[3] = {o[0], o[1], o[2]}, oab[3] = {o[0], o[1], o[2]};
+    oa[a] += 1, ob[b] += 1, oab[a] += 1, oab[b] += 1;
+    const T Gab = (U(a, ob[0], ob[1], ob[2]) - U(a, o[0], o[1], o[2])) * LES_LD(g.rdu[b] + tb);
+    const T Gba = (U(b, oa[0], oa[1], oa[2]) - U(b, o[0], o[1], o[2])) * LES_LD(g.rdu[a] + ta);
+    const T wa_a = LES_LD(g.wa[a] + ta), wb_a = LES_LD(g.wb[a] + ta);
+    const T wa_b = LES_LD(g.wa[b] + tb), wb_b = LES_LD(g.wb[b] + tb);
+    const T nu = wa_a * wa_b * V(0, o[0], o[1], o[2]) + wb_a * wa_b * V(0, oa[0], oa[1], oa[2]) +
+                 wa_a * wb_b * V(0, ob[0], ob[1], ob[2]) + wb_a * wb_b * V(0, oab[0], oab[1], oab[2]);
     return T(-2) * nu * ((Gab + Gba) * T(0.5));
 }
 
 // divoftensor_kernel! (:200-219) with the stress recomputed on the fly: f[a] = sum_b d(sigma_ab)/dx_b at cell I
-template <typename T, bool EDGE>
-LES_HD void les_stress_divergence(const Grid<T> &g, const LesEdge &e, const T *__restrict__ u, const T *__restrict__ visc,
-                                  const int I[3], T (&f)[3]) {
+template <typename T, bool EDGE, typename LU, typename LV>
+LES_HD void les_stress_divergence(const Grid<T> &g, const LesEdge &e, const LU &U, const LV &V, const int I[3], T (&f)[3]) {
     LesNb<EDGE> nb;
     nb.init(g, e, I);
     // diagonal stresses at I and I + e_a
     T dterm[3];
 #pragma unroll
     for (int a = 0; a < 3; a++) {
-        int J[3] = {I[0], I[1], I[2]};
-        const T s0 = les_sigma_diag<T>(g, u, visc, a, J);
-        J[a] = nb.p[a];
-        T s1 = les_sigma_diag<T>(g, u, visc, a, J);
+        int o[3] = {0, 0, 0};
+        const T s0 = les_sigma_diag<T>(g, U, V, a, o, I[a]);
+        o[a] = nb.op[a];
+        T s1 = les_sigma_diag<T>(g, U, V, a, o, nb.tp[a]);
         if (EDGE && nb.zp[a]) s1 = T(0);
         dterm[a] = (s1 - s0) * LES_LD(g.rdu[a] + I[a]);
     }
@@ -216,14 +242,14 @@ LES_HD void les_stress_divergence(const Grid<T> &g, const LesEdge &e, const T *_
     for (int a = 0; a < 3; a++)
 #pragma unroll
         for (int b = a + 1; b < 3; b++) {
-            int J[3] = {I[0], I[1], I[2]};
-            const T s0 = les_sigma_off<T>(g, u, visc, a, b, J);
-            J[b] = nb.m[b];
-            T sb = les_sigma_off<T>(g, u, visc, a, b, J);
+            int o[3] = {0, 0, 0};
+            const T s0 = les_sigma_off<T>(g, U, V, a, b, o, I[a], I[b]);
+            o[b] = nb.om[b];
+            T sb = les_sigma_off<T>(g, U, V, a, b, o, I[a], nb.tm[b]);
             if (EDGE && nb.zm[b]) sb = T(0);
-            J[b] = I[b];
-            J[a] = nb.m[a];
-            T sa = les_sigma_off<T>(g, u, visc, a, b, J);
+            o[b] = 0;
+            o[a] = nb.om[a];
+            T sa = les_sigma_off<T>(g, U, V, a, b, o, nb.tm[a], I[b]);
             if (EDGE && nb.zm[a]) sa = T(0);
             oterm[a][b] = (s0 - sb) * LES_LD(g.rdl[b] + I[b]);
             oterm[b][a] = (s0 - sa) * LES_LD(g.rdl[a] + I[a]);

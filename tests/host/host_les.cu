@@ -23,7 +23,7 @@ static Grid<T> make_grid(const int N[3], const void *const tab[3][5]) {
 }
 
 template <typename T>
-static void run(int phase, const int N[3], const void *const tab[3][5], const int lo[3], const int hi[3], int model, double C,
+static void run(int phase, bool edge_all, const int N[3], const void *const tab[3][5], const int lo[3], const int hi[3], int model, double C,
                 const T *u, T *visc, T *f) {
     Grid<T> g = make_grid<T>(N, tab);
     LesEdge e;
@@ -33,12 +33,16 @@ static void run(int phase, const int N[3], const void *const tab[3][5], const in
             for (int i = 1; i < N[0] - 1; i++) {
                 const int I[3] = {i, j, k};
                 const long long idx = i + j * g.s[1] + k * g.s[2];
+                const LesGLoad<T> U{u + idx, g.s[1], g.s[2], g.cs}, V{visc + idx, g.s[1], g.s[2], 0};
+                // like the kernels: the ghost rules only where a cell touches a ghost plane (edge_all: everywhere,
+                // which must give the same result)
+                const bool edge = edge_all || i == 1 || j == 1 || k == 1 || i == N[0] - 2 || j == N[1] - 2 || k == N[2] - 2;
                 if (phase == 1) {
                     T M[3][3];
-                    if (i == 1 || j == 1 || k == 1)
-                        les_collocated_gradient<T, true>(g, e, u, I, M);
+                    if (edge)
+                        les_collocated_gradient<T, true>(g, e, U, I, M);
                     else
-                        les_collocated_gradient<T, false>(g, e, u, I, M);
+                        les_collocated_gradient<T, false>(g, e, U, I, M);
                     const T dx = g.dl[0][i], dy = g.dl[1][j], dz = g.dl[2][k];
                     T out;
                     switch (model) {
@@ -50,23 +54,23 @@ static void run(int phase, const int N[3], const void *const tab[3][5], const in
                     visc[idx] = out;
                 } else {
                     T fl[3];
-                    if (i == 1 || j == 1 || k == 1 || i == N[0] - 2 || j == N[1] - 2 || k == N[2] - 2)
-                        les_stress_divergence<T, true>(g, e, u, visc, I, fl);
+                    if (edge)
+                        les_stress_divergence<T, true>(g, e, U, V, I, fl);
                     else
-                        les_stress_divergence<T, false>(g, e, u, visc, I, fl);
+                        les_stress_divergence<T, false>(g, e, U, V, I, fl);
                     for (int c = 0; c < 3; c++) f[idx + c * g.cs] += -fl[c];
                 }
             }
 }
 
-extern "C" int host_les(int f64, int phase, const int *N, const void *const *tab15, const int *lo, const int *hi, int model,
+extern "C" int host_les(int f64, int phase, int edge_all, const int *N, const void *const *tab15, const int *lo, const int *hi, int model,
                         double C, const void *u, void *visc, void *f) {
     const void *tab[3][5];
     for (int a = 0; a < 3; a++)
         for (int t = 0; t < 5; t++) tab[a][t] = tab15[a * 5 + t];
     if (f64)
-        run<double>(phase, N, tab, lo, hi, model, C, (const double *)u, (double *)visc, (double *)f);
+        run<double>(phase, edge_all != 0, N, tab, lo, hi, model, C, (const double *)u, (double *)visc, (double *)f);
     else
-        run<float>(phase, N, tab, lo, hi, model, C, (const float *)u, (float *)visc, (float *)f);
+        run<float>(phase, edge_all != 0, N, tab, lo, hi, model, C, (const float *)u, (float *)visc, (float *)f);
     return 0;
 }

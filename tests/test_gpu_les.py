@@ -18,6 +18,8 @@ CASES = [
     ("mixed", (uniform(10), O.cosine_grid(0, 1, 8), uniform(12)), ("S", "D", "P"), None),
     # two x blocks and three y blocks of the 64 x 4 launch tiles, a different BC on either side
     ("wide", (uniform(70, 3.0), O.tanh_grid(0, 1, 9, 1.2), O.cosine_grid(0, 1, 6)), ("P", ("S", "D"), ("D", "S")), None),
+    # two z chunks of the tile kernels (64 planes per block), partial tiles in x and y
+    ("tall", (uniform(37, 2.0), O.tanh_grid(0, 1, 11, 1.2), uniform(70, 3.0)), ("S", "D", "P"), None),
     # PressureBC side: two ghost layers, stays on the four-pass path (les_needs_tensor)
     ("outflow", (O.tanh_grid(0, 1, 12, 1.2), uniform(8), uniform(10)), (("D", "O"), "D", "P"), None),
 ]
@@ -46,27 +48,31 @@ def test_closure_term_matches_oracle(name, x, bcs, kind, mo, mg, C, T):
 
 @pytest.mark.parametrize("T", [np.float64, np.float32])
 @pytest.mark.parametrize("mo,mg,C", MODELS)
-@pytest.mark.parametrize("name,x,bcs,kind", CASES[:5])
+@pytest.mark.parametrize("name,x,bcs,kind", CASES[:6])
 def test_fused_closure_equals_four_pass_closure(name, x, bcs, kind, mo, mg, C, T, monkeypatch):
-    """Default path (two fused kernels, nothing but nu_t stored) against the four-pass path with the stored
-    gradient / stress tensors (INSB200_LES_UNFUSED): same arithmetic up to the reciprocal metric tables."""
+    """Default path (two fused kernels, nothing but nu_t stored: shared-memory tile kernels + the boundary shell;
+    INSB200_LES_TILE=0: one thread per cell) against the four-pass path with the stored gradient / stress tensors
+    (INSB200_LES_UNFUSED): same arithmetic up to the reciprocal metric tables."""
     import insb200 as I
 
     so, sg = make_setups(x, bcs, T=T)
     u = I.to_device(sg, smooth_vec(so, 201))
     f0 = smooth_vec(so, 202)
     out = []
-    for unfused in (False, True):
-        if unfused:
-            monkeypatch.setenv("INSB200_LES_UNFUSED", "1")
-        else:
-            monkeypatch.delenv("INSB200_LES_UNFUSED", raising=False)
+    for env in ({}, {"INSB200_LES_TILE": "0"}, {"INSB200_LES_UNFUSED": "1"}):
+        monkeypatch.delenv("INSB200_LES_UNFUSED", raising=False)
+        monkeypatch.delenv("INSB200_LES_TILE", raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
         fd = I.to_device(sg, f0)
         I.eddy_viscosity_closure_(getattr(I, mg)(C), fd, u, None, sg)
         out.append(I.to_host(fd) - f0)
-    scale = max(np.linalg.norm(out[1].ravel()), 1e-300)
-    err = np.linalg.norm((out[0] - out[1]).ravel()) / scale
-    assert err < (1e-12 if T is np.float64 else 1e-5), (name, mo, err)
+    scale = max(np.linalg.norm(out[2].ravel()), 1e-300)
+    for o in out[:2]:
+        err = np.linalg.norm((o - out[2]).ravel()) / scale
+        assert err < (1e-12 if T is np.float64 else 1e-5), (name, mo, err)
+    # the same cell functions, whatever feeds them (up to the compiler's contraction choices per instantiation)
+    assert np.linalg.norm((out[0] - out[1]).ravel()) / scale < (1e-14 if T is np.float64 else 1e-6)
     assert scale > 1e-6
 
 

@@ -41,6 +41,8 @@ CASES = [
     ("mixed", (uniform(7), O.cosine_grid(0, 1, 8), uniform(6)), ("S", "D", "P")),
     ("sides", (O.tanh_grid(0, 1, 6, 1.3), uniform(5), O.cosine_grid(0, 1, 7)), (("S", "D"), ("D", "S"), "S")),
     ("thin", (uniform(1), uniform(2), uniform(5)), ("P", "S", "D")),
+    # periodic directions on stretched grids: the ghost entries of the metric tables are not periodic images
+    ("stretched", (O.tanh_grid(0, 1, 6, 1.3), O.cosine_grid(0, 2, 7), O.tanh_grid(0, 1, 5, 1.1)), ("P", "P", "P")),
 ]
 MODELS = [("smagorinsky", 1, 0.17), ("wale", 2, 0.569), ("vreman", 3, 0.28), ("qr", 4, 0.092)]
 
@@ -59,22 +61,14 @@ def tables(so):
 
 
 def edges(so):
-    lo, hi = [], []
-    for d in range(3):
-        n = so.N[d]
-        for side, dst in ((0, lo), (1, hi)):
-            bc = so.bc_u[d][side]
-            if isinstance(bc, PeriodicBC):
-                dst.append(1 if side else n - 2)
-            elif isinstance(bc, SymmetricBC):
-                dst.append(n - 2 if side else 1)
-            else:
-                assert isinstance(bc, DirichletBC)
-                dst.append(-1)
+    """BC codes of include/insb200.h per dimension and side."""
+    code = {PeriodicBC: 0, DirichletBC: 1, SymmetricBC: 2}
+    lo = [code[type(so.bc_u[d][0])] for d in range(3)]
+    hi = [code[type(so.bc_u[d][1])] for d in range(3)]
     return lo, hi
 
 
-def host_closure(lib, so, model, C, u, f):
+def host_closure(lib, so, model, C, u, f, edge_all=False):
     T = so.T
     tabs = tables(so)
     flat = [t for row in tabs for t in row]
@@ -83,7 +77,7 @@ def host_closure(lib, so, model, C, u, f):
     lo, hi = edges(so)
     lo_c, hi_c = (ctypes.c_int * 3)(*lo), (ctypes.c_int * 3)(*hi)
     visc = np.zeros(so.N, dtype=T, order="F")
-    args = lambda phase: (int(T is np.float64), phase, N, ptrs, lo_c, hi_c, model, ctypes.c_double(C),
+    args = lambda phase: (int(T is np.float64), phase, int(edge_all), N, ptrs, lo_c, hi_c, model, ctypes.c_double(C),
                           ctypes.c_void_p(u.ctypes.data), ctypes.c_void_p(visc.ctypes.data), ctypes.c_void_p(f.ctypes.data))
     assert lib.host_les(*args(1)) == 0
     oev.zero_out_wall_(visc, so)
@@ -104,6 +98,10 @@ def test_fused_cell_functions_match_oracle(lib, name, x, bcs, mo, mid, C, T):
     want = oev.eddy_viscosity_closure_(mo, C, f0.copy(order="F"), u, so, cache)
     got = f0.copy(order="F")
     visc = host_closure(lib, so, mid, C, np.asfortranarray(u), got)
+    # the ghost rules applied to every cell (they reduce to the plain stencil away from the ghost planes)
+    got2 = f0.copy(order="F")
+    visc2 = host_closure(lib, so, mid, C, np.asfortranarray(u), got2, edge_all=True)
+    assert np.array_equal(visc, visc2) and np.array_equal(got, got2)
     tol = 1e-12 if T is np.float64 else 1e-5
     vs = max(np.abs(cache["visc"]).max(), 1e-300)
     assert np.abs(visc - cache["visc"]).max() / vs < tol, (name, mo)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Times eddy_viscosity_closure! alone on the ChannelFlow grid (cfg 5, optionally scaled), fused (default) against
-the four-pass path (INSB200_LES_UNFUSED=1), per model and dtype; prints one JSON line per case with ms per closure
+"""Times eddy_viscosity_closure! alone on the ChannelFlow grid (cfg 5, optionally scaled), fused (default: tile
+kernels; INSB200_LES_TILE=0: one thread per cell) against the four-pass path (INSB200_LES_UNFUSED=1), per model and dtype; prints one JSON line per case with ms per closure
 and the effective bandwidth over the fused path's 10 scalar fields (u 3 R, nu_t 1 W + 1 R, u 3 R again, f 3 RMW = 6).
 
     python tools/bench_les.py [--scale 0.5] [--models WALE Smagorinsky] [--reps 5]
@@ -39,11 +39,14 @@ def main():
         cells = float(np.prod(sg.Np))
         for model in a.models:
             ref = None
-            for unfused in (True, False):
+            for mode in ("four-pass", "fused, one thread per cell", "fused"):
+                unfused = mode == "four-pass"
+                for k in ("INSB200_LES_UNFUSED", "INSB200_LES_TILE"):
+                    os.environ.pop(k, None)
                 if unfused:
                     os.environ["INSB200_LES_UNFUSED"] = "1"
-                else:
-                    os.environ.pop("INSB200_LES_UNFUSED", None)
+                elif mode != "fused":
+                    os.environ["INSB200_LES_TILE"] = "0"
                 f.zero_()
                 I.eddy_viscosity_closure_(getattr(I, model)(0.3), f, u, None, sg)
                 out = f.clone()
@@ -60,8 +63,7 @@ def main():
                     diff = None
                 else:
                     diff = float((out - ref).norm() / ref.norm())
-                    del ref
-                print(json.dumps({"case": f"closure {model} {np.dtype(T).name} {'four-pass' if unfused else 'fused'}",
+                print(json.dumps({"case": f"closure {model} {np.dtype(T).name} {mode}",
                                   "N": list(sg.N), "ms_per_closure": round(ms, 3),
                                   "GBps_over_10_fields": round(10 * cells * np.dtype(T).itemsize / ms / 1e6, 1),
                                   "rel_diff_vs_four_pass": diff}), flush=True)
