@@ -166,6 +166,37 @@ __device__ __forceinline__ void les_apply_cell(const Grid<T> &g, long long idx, 
     }
 }
 
+// The same in two halves for the tile kernel: the old values are requested before the stress arithmetic, so that
+// their DRAM latency runs under it (the warps of a block march in lock-step behind one barrier per plane).
+template <typename T>
+struct LesOld {
+    T k[3], v[3], a[3];
+};
+template <typename T>
+__device__ __forceinline__ void les_apply_load(const Grid<T> &g, long long idx, const T *__restrict__ k_out,
+                                               const T *__restrict__ v, const T *__restrict__ acc, LesOld<T> &o) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const long long q = idx + c * g.cs;
+        if (k_out) o.k[c] = k_out[q];
+        if (v) o.v[c] = v[q];
+        if (acc) o.a[c] = acc[q];
+    }
+}
+template <typename T, typename CT>
+__device__ __forceinline__ void les_apply_store(const Grid<T> &g, long long idx, const T (&f)[3], const LesOld<T> &o,
+                                                T *__restrict__ k_out, T *__restrict__ v, double cv, T *__restrict__ acc,
+                                                double ca) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const T fl = -f[c];
+        const long long q = idx + c * g.cs;
+        if (k_out) k_out[q] = o.k[c] + fl;
+        if (v) v[q] = axpy_rn<T, CT>(o.v[c], cv, fl);
+        if (acc) acc[q] = axpy_rn<T, CT>(o.a[c], ca, fl);
+    }
+}
+
 template <typename T, typename CT>
 __global__ void __launch_bounds__(256) les_apply_fused_kernel(Grid<T> g, LesEdge e, LesBox bx, const T *__restrict__ u,
                                                              const T *__restrict__ visc, T *__restrict__ k_out,
@@ -197,8 +228,10 @@ struct LesTileLoad {
 // MODEL > 0: viscosity kernel (fields u_x, u_y, u_z; writes nu_t); MODEL == 0: apply kernel (fields u_x, u_y,
 // u_z, nu_t; updates k_out / v / acc).  The cells next to a ghost plane are left to the one-thread-per-cell
 // kernels (launch_les_shell): the ghost rules cost 46 registers here, i.e. one of two resident blocks.
-template <typename T, typename CT, int MODEL, int TX, int TY, int ZC>
-__global__ void __launch_bounds__(TX *TY) les_tile_kernel(Grid<T> g, LesEdge e, const T *__restrict__ u,
+// PREF (apply kernel): request the old output values before the stress arithmetic (les_apply_load); costs
+// registers (Float64: capped at 128 by the launch bounds, a few spills) -- INSB200_LES_PREFETCH=0 switches it off.
+template <typename T, typename CT, int MODEL, int TX, int TY, int ZC, bool PREF>
+__global__ void __launch_bounds__(TX *TY, (MODEL == 0 && sizeof(T) == 8) ? 2 : (MODEL == 0 ? 3 : 1)) les_tile_kernel(Grid<T> g, LesEdge e, const T *__restrict__ u,
                                                          const T *__restrict__ visc_in, T *__restrict__ visc_out, T C,
                                                          T *__restrict__ k_out, T *__restrict__ v, double cv,
                                                          T *__restrict__ acc, double ca) {
@@ -267,9 +300,14 @@ __global__ void __launch_bounds__(TX *TY) les_tile_kernel(Grid<T> g, LesEdge e, 
                 const T dx = __ldg(g.dl[0] + Ic0), dy = __ldg(g.dl[1] + Ic1), dz = __ldg(g.dl[2] + z);
                 visc_out[idx] = eddy_visc_value<T, (MODEL > 0 ? MODEL : 1)>(M, dx, dy, dz, C);
             } else {
+                LesOld<T> old;
+                if (PREF) les_apply_load<T>(g, idx, k_out, v, acc, old);
                 T f[3];
                 les_stress_divergence<T, false>(g, e, U, V, I, f);
-                les_apply_cell<T, CT>(g, idx, f, k_out, v, cv, acc, ca);
+                if (PREF)
+                    les_apply_store<T, CT>(g, idx, f, old, k_out, v, cv, acc, ca);
+                else
+                    les_apply_cell<T, CT>(g, idx, f, k_out, v, cv, acc, ca);
             }
         }
         if (more) store_plane(z + 2);
@@ -284,7 +322,11 @@ static int launch_les_tile(const Grid<T> &g, const LesEdge &e, const T *u, const
     constexpr size_t smem = (size_t)4 * NF * (TX + 2) * (TY + 2) * sizeof(T);
     dim3 b(TX, TY, 1);
     dim3 gr((g.N[0] - 2 + TX - 1) / TX, (g.N[1] - 2 + TY - 1) / TY, (g.N[2] - 2 + ZC - 1) / ZC);
-    les_tile_kernel<T, CT, MODEL, TX, TY, ZC><<<gr, b, smem, L.stream>>>(g, e, u, visc_in, visc_out, C, k_out, v, cv, acc, ca);
+    const char *pe = getenv("INSB200_LES_PREFETCH");
+    if (MODEL == 0 && (!pe || atoi(pe) != 0))
+        les_tile_kernel<T, CT, MODEL, TX, TY, ZC, true><<<gr, b, smem, L.stream>>>(g, e, u, visc_in, visc_out, C, k_out, v, cv, acc, ca);
+    else
+        les_tile_kernel<T, CT, MODEL, TX, TY, ZC, false><<<gr, b, smem, L.stream>>>(g, e, u, visc_in, visc_out, C, k_out, v, cv, acc, ca);
     if (L.counter) ++*L.counter;
     INSB_CUDA(cudaGetLastError());
     return 0;

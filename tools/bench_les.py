@@ -39,14 +39,16 @@ def main():
         cells = float(np.prod(sg.Np))
         for model in a.models:
             ref = None
-            for mode in ("four-pass", "fused, one thread per cell", "fused"):
+            for mode in ("four-pass", "fused, one thread per cell", "fused, no output prefetch", "fused"):
                 unfused = mode == "four-pass"
-                for k in ("INSB200_LES_UNFUSED", "INSB200_LES_TILE"):
+                for k in ("INSB200_LES_UNFUSED", "INSB200_LES_TILE", "INSB200_LES_PREFETCH"):
                     os.environ.pop(k, None)
                 if unfused:
                     os.environ["INSB200_LES_UNFUSED"] = "1"
-                elif mode != "fused":
+                elif mode == "fused, one thread per cell":
                     os.environ["INSB200_LES_TILE"] = "0"
+                elif mode == "fused, no output prefetch":
+                    os.environ["INSB200_LES_PREFETCH"] = "0"
                 f.zero_()
                 I.eddy_viscosity_closure_(getattr(I, model)(0.3), f, u, None, sg)
                 out = f.clone()
