@@ -231,7 +231,7 @@ struct LesTileLoad {
 // PREF (apply kernel): request the old output values before the stress arithmetic (les_apply_load); costs
 // registers (Float64: capped at 128 by the launch bounds, a few spills) -- INSB200_LES_PREFETCH=0 switches it off.
 template <typename T, typename CT, int MODEL, int TX, int TY, int ZC, bool PREF>
-__global__ void __launch_bounds__(TX *TY, (MODEL == 0 && sizeof(T) == 8) ? 2 : (MODEL == 0 ? 3 : 1)) les_tile_kernel(Grid<T> g, LesEdge e, const T *__restrict__ u,
+__global__ void __launch_bounds__(TX *TY, (MODEL == 0 && sizeof(T) == 8) ? 2 : (MODEL == 0 ? 3 : 4)) les_tile_kernel(Grid<T> g, LesEdge e, const T *__restrict__ u,
                                                          const T *__restrict__ visc_in, T *__restrict__ visc_out, T C,
                                                          T *__restrict__ k_out, T *__restrict__ v, double cv,
                                                          T *__restrict__ acc, double ca) {

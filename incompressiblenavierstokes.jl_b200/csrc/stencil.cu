@@ -541,8 +541,8 @@ __global__ void __launch_bounds__(256) bouss_extra_kernel(Grid<T> g, StageArgs<T
 // marches a TX x TY column along z with the planes z-1, z, z+1 of (u_x, u_y, u_z, temp) and a
 // one-cell halo in a 4-slot ring (next plane prefetched into registers during the arithmetic), so
 // every value comes from HBM/L2 once per block column.
-template <typename T, typename CT, int TX, int TY, int ZC>
-__global__ void __launch_bounds__(TX *TY) bouss_tile_kernel(Grid<T> g, StageArgs<T> a) {
+template <typename T, typename CT, int TX, int TY, int ZC, bool PREF>
+__global__ void __launch_bounds__(TX *TY, sizeof(T) == 4 ? 4 : 2) bouss_tile_kernel(Grid<T> g, StageArgs<T> a) {
     constexpr int PX = TX + 2, PY = TY + 2, PLANE = PX * PY, NT = TX * TY, NE = 4 * PLANE;
     constexpr int NL = (NE + NT - 1) / NT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -600,22 +600,31 @@ __global__ void __launch_bounds__(TX *TY) bouss_tile_kernel(Grid<T> g, StageArgs
                 U.pl[k] = s + ((z - 1 + k) & 3) * NE + lidx;
                 Tm.pl[k] = U.pl[k] + 3 * PLANE;
             }
+            // PREF: the old values of the combine are requested before the arithmetic (the warps of a block march
+            // in lock-step behind one barrier per plane, so a load issued after it is exposed DRAM latency)
+            const bool grav_ok = a.gdir >= 0 && a.gdir < 3;
+            const long long qg = idx + (long long)(grav_ok ? a.gdir : 0) * g.cs;
+            T o_tb = T(0), o_ta = T(0), o_v = T(0), o_acc = T(0);
+            if (PREF) {
+                if (a.tv) o_tb = a.tvbase[idx];
+                if (a.tacc_out) o_ta = a.tacc_in[idx];
+                if (grav_ok && a.v) o_v = a.v[qg];
+                if (grav_ok && a.acc_out) o_acc = a.acc_out[qg];
+            }
             const T kt = temperature_rhs<T, 3>(U, Tm, g, I, (T)a.kappa, (T)a.nu, a.dodiss != 0);
             if (a.tk_out) a.tk_out[idx] = kt;
             if (a.tv) {
-                T x = a.tvbase[idx];
+                T x = PREF ? o_tb : a.tvbase[idx];
                 for (int j = 0; j < a.nprev; j++) x = axpy_rn<T, CT>(x, a.cprev[j], a.tkprev[j][idx]);
                 a.tv[idx] = axpy_rn<T, CT>(x, a.cv, kt);
             }
-            if (a.tacc_out) a.tacc_out[idx] = axpy_rn<T, CT>(a.tacc_in[idx], a.ca, kt);
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                if (c != a.gdir) continue;
-                const T gk = (T)a.grav * avg_face<3>(Tm, g, I, c, 0);
-                const long long q = idx + c * g.cs;
-                if (a.k_out) a.k_out[q] += gk;
-                if (a.v) a.v[q] = axpy_rn<T, CT>(a.v[q], a.cv, gk);
-                if (a.acc_out) a.acc_out[q] = axpy_rn<T, CT>(a.acc_out[q], a.ca, gk);
+            if (a.tacc_out) a.tacc_out[idx] = axpy_rn<T, CT>(PREF ? o_ta : a.tacc_in[idx], a.ca, kt);
+            if (grav_ok) {
+                const int c = a.gdir;
+                const T gk = (T)a.grav * (c == 0 ? avg_face<3>(Tm, g, I, 0, 0) : c == 1 ? avg_face<3>(Tm, g, I, 1, 0) : avg_face<3>(Tm, g, I, 2, 0));
+                if (a.k_out) a.k_out[qg] += gk;
+                if (a.v) a.v[qg] = axpy_rn<T, CT>(PREF ? o_v : a.v[qg], a.cv, gk);
+                if (a.acc_out) a.acc_out[qg] = axpy_rn<T, CT>(PREF ? o_acc : a.acc_out[qg], a.ca, gk);
             }
         }
         if (more) store_plane(z + 2);
@@ -638,7 +647,11 @@ static int launch_stage_bouss_split(const Grid<T> &g, const StageArgs<T> &a, Lau
         constexpr size_t smem = (size_t)4 * 4 * (TX + 2) * (TY + 2) * sizeof(T);
         dim3 b(TX, TY, 1);
         dim3 gr((g.N[0] - 2 + TX - 1) / TX, (g.N[1] - 2 + TY - 1) / TY, (g.N[2] - 2 + ZC - 1) / ZC);
-        bouss_tile_kernel<T, CT, TX, TY, ZC><<<gr, b, smem, L.stream>>>(g, a);
+        const char *pe = getenv("INSB200_BOUSS_PREFETCH");
+        if (!pe || atoi(pe) != 0)
+            bouss_tile_kernel<T, CT, TX, TY, ZC, true><<<gr, b, smem, L.stream>>>(g, a);
+        else
+            bouss_tile_kernel<T, CT, TX, TY, ZC, false><<<gr, b, smem, L.stream>>>(g, a);
         if (L.counter) ++*L.counter;
         INSB_CUDA(cudaGetLastError());
         return 0;
