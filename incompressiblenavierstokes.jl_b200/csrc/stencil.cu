@@ -639,10 +639,11 @@ static int launch_stage_bouss_split(const Grid<T> &g, const StageArgs<T> &a, Lau
     m.temp = nullptr;
     m.tv = m.tacc_out = m.tk_out = nullptr;
     INSB_TRY((launch_stage_pair<T, CT>(g, m, L)));
-    // measured at 512x512x256 (cfg 4): Float32 2.07 -> 1.60 ms per launch with the tile kernel, Float64
-    // 3.05 -> 3.30 ms (table loads, not field loads, dominate there): tiles for Float32 only
+    // measured at 512x512x256 (cfg 4), rhs + combine per RK44 step: Float32 direct 11.1 -> tile 8.96 -> tile with the
+    // operand prefetch 7.17 ms; Float64 direct 15.17, tile 17.64, tile with the prefetch 14.57 ms.  INSB200_BOUSS_TILE=0:
+    // the one-thread-per-cell pass
     const char *te = getenv("INSB200_BOUSS_TILE");
-    if (te ? atoi(te) != 0 : sizeof(T) == 4) {
+    if (!te || atoi(te) != 0) {
         constexpr int TX = 32, TY = 8, ZC = 64;
         constexpr size_t smem = (size_t)4 * 4 * (TX + 2) * (TY + 2) * sizeof(T);
         dim3 b(TX, TY, 1);

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """A/B of the Boussinesq temperature pass on cfg 4 (RayleighBenard3D 512x512x256, RK44), one process: the switches are
-read per launch.  Float32: tile kernel with / without the operand prefetch; Float64: direct kernel (default), tile
-kernel with / without the prefetch.
+read per launch.  tile kernel with / without the operand prefetch (INSB200_BOUSS_PREFETCH=0), Float64 also the one-thread-per-cell
+pass (INSB200_BOUSS_TILE=0).
 
     python tools/bench_bouss.py [--scale 1.0]
 """
@@ -28,8 +28,8 @@ def main():
     sz = lambda n: max(8, int(round(n * a.scale / 2)) * 2)
     variants = {
         np.float32: [("tile + prefetch (default)", {}), ("tile, no prefetch", {"INSB200_BOUSS_PREFETCH": "0"})],
-        np.float64: [("direct (default)", {}), ("tile + prefetch", {"INSB200_BOUSS_TILE": "1"}),
-                     ("tile, no prefetch", {"INSB200_BOUSS_TILE": "1", "INSB200_BOUSS_PREFETCH": "0"})],
+        np.float64: [("tile + prefetch (default)", {}), ("tile, no prefetch", {"INSB200_BOUSS_PREFETCH": "0"}),
+                     ("direct", {"INSB200_BOUSS_TILE": "0"})],
     }
     for T in (np.float32, np.float64):
         n = (sz(512), sz(512), sz(256))
