@@ -144,11 +144,12 @@ __global__ void __launch_bounds__(256) les_visc_fused_kernel(Grid<T> g, LesEdge 
     const int I[3] = {i, j, k};
     const long long idx = i + j * g.s[1] + k * g.s[2];
     const LesGLoad<T> U{u + idx, g.s[1], g.s[2], g.cs};
+    const LesGridTab<T> mt{g};
     T M[3][3];
     if (i == 1 || j == 1 || k == 1)
-        les_collocated_gradient<T, true>(g, e, U, I, M);
+        les_collocated_gradient<T, true>(g, mt, e, U, I, M);
     else
-        les_collocated_gradient<T, false>(g, e, U, I, M);
+        les_collocated_gradient<T, false>(g, mt, e, U, I, M);
     const T dx = __ldg(g.dl[0] + i), dy = __ldg(g.dl[1] + j), dz = __ldg(g.dl[2] + k);
     visc[idx] = eddy_visc_value<T, MODEL>(M, dx, dy, dz, C);
 }
@@ -207,11 +208,12 @@ __global__ void __launch_bounds__(256) les_apply_fused_kernel(Grid<T> g, LesEdge
     const int I[3] = {i, j, k};
     const long long idx = i + j * g.s[1] + k * g.s[2];
     const LesGLoad<T> U{u + idx, g.s[1], g.s[2], g.cs}, V{visc + idx, g.s[1], g.s[2], 0};
+    const LesGridTab<T> mt{g};
     T f[3];
     if (i == 1 || j == 1 || k == 1 || i == g.N[0] - 2 || j == g.N[1] - 2 || k == g.N[2] - 2)
-        les_stress_divergence<T, true>(g, e, U, V, I, f);
+        les_stress_divergence<T, true>(g, mt, e, U, V, I, f);
     else
-        les_stress_divergence<T, false>(g, e, U, V, I, f);
+        les_stress_divergence<T, false>(g, mt, e, U, V, I, f);
     les_apply_cell<T, CT>(g, idx, f, k_out, v, cv, acc, ca);
 }
 
@@ -238,13 +240,26 @@ __global__ void __launch_bounds__(TX *TY, (MODEL == 0 && sizeof(T) == 8) ? 2 : (
     constexpr int NF = MODEL == 0 ? 4 : 3;
     constexpr int PX = TX + 2, PY = TY + 2, PLANE = PX * PY, NT = TX * TY, NE = NF * PLANE;
     constexpr int NL = (NE + NT - 1) / NT;
+    constexpr int LX = TX + 2, LY = TY + 2, LZ = ZC + 2, LEN = LX + LY + LZ;  // metric-table slices: x, y, z back to back
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *s = reinterpret_cast<T *>(smem_raw);  // [4 slots][NF fields][PY][PX]
+    T *mtab = s + 4 * NE;                    // [rdl, rdu, wa, wb][LEN]
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
     const int x0 = 1 + blockIdx.x * TX, y0 = 1 + blockIdx.y * TY;
     const int zbeg = 1 + blockIdx.z * ZC;
     const int zend = min(zbeg + ZC, g.N[2] - 1);
     if (zbeg >= zend) return;
+    // entry r of a slice <-> index base - 1 + r of the dimension (clamped; clamped entries are never used)
+    for (int el = tid; el < 4 * LEN; el += NT) {
+        const int tb = el / LEN, r = el - tb * LEN;
+        const int d = r < LX ? 0 : r < LX + LY ? 1 : 2;
+        const int rl = d == 0 ? r : d == 1 ? r - LX : r - LX - LY;
+        const int gi = min((d == 0 ? x0 : d == 1 ? y0 : zbeg) - 1 + rl, g.N[d] - 1);
+        const T *tp = tb == 0 ? g.rdl[d] : tb == 1 ? g.rdu[d] : tb == 2 ? g.wa[d] : g.wb[d];
+        mtab[el] = __ldg(tp + gi);
+    }
+    LesSmemTab<T, LEN> mt;  // addressed by the absolute index: entry of index 0 = slice start - (base - 1)
+    mt.p[0] = mtab - (x0 - 1), mt.p[1] = mtab + LX - (y0 - 1), mt.p[2] = mtab + LX + LY - (zbeg - 1);
     const T *lp[NL];
     bool lv[NL];
 #pragma unroll
@@ -296,14 +311,14 @@ __global__ void __launch_bounds__(TX *TY, (MODEL == 0 && sizeof(T) == 8) ? 2 : (
             if (edge) {
             } else if (MODEL > 0) {
                 T M[3][3];
-                les_collocated_gradient<T, false>(g, e, U, I, M);
+                les_collocated_gradient<T, false>(g, mt, e, U, I, M);
                 const T dx = __ldg(g.dl[0] + Ic0), dy = __ldg(g.dl[1] + Ic1), dz = __ldg(g.dl[2] + z);
                 visc_out[idx] = eddy_visc_value<T, (MODEL > 0 ? MODEL : 1)>(M, dx, dy, dz, C);
             } else {
                 LesOld<T> old;
                 if (PREF) les_apply_load<T>(g, idx, k_out, v, acc, old);
                 T f[3];
-                les_stress_divergence<T, false>(g, e, U, V, I, f);
+                les_stress_divergence<T, false>(g, mt, e, U, V, I, f);
                 if (PREF)
                     les_apply_store<T, CT>(g, idx, f, old, k_out, v, cv, acc, ca);
                 else
@@ -319,14 +334,14 @@ template <typename T, typename CT, int MODEL>
 static int launch_les_tile(const Grid<T> &g, const LesEdge &e, const T *u, const T *visc_in, T *visc_out, T C, T *k_out, T *v,
                            double cv, T *acc, double ca, Launch L) {
     constexpr int TX = 32, TY = 8, ZC = 64, NF = MODEL == 0 ? 4 : 3;
-    constexpr size_t smem = (size_t)4 * NF * (TX + 2) * (TY + 2) * sizeof(T);
+    constexpr size_t smem = (size_t)4 * NF * (TX + 2) * (TY + 2) * sizeof(T) + (size_t)4 * (TX + 2 + TY + 2 + ZC + 2) * sizeof(T);
     dim3 b(TX, TY, 1);
     dim3 gr((g.N[0] - 2 + TX - 1) / TX, (g.N[1] - 2 + TY - 1) / TY, (g.N[2] - 2 + ZC - 1) / ZC);
     const char *pe = getenv("INSB200_LES_PREFETCH");
-    if (MODEL == 0 && (!pe || atoi(pe) != 0))
-        les_tile_kernel<T, CT, MODEL, TX, TY, ZC, true><<<gr, b, smem, L.stream>>>(g, e, u, visc_in, visc_out, C, k_out, v, cv, acc, ca);
-    else
-        les_tile_kernel<T, CT, MODEL, TX, TY, ZC, false><<<gr, b, smem, L.stream>>>(g, e, u, visc_in, visc_out, C, k_out, v, cv, acc, ca);
+    auto kern = les_tile_kernel<T, CT, MODEL, TX, TY, ZC, false>;
+    if (MODEL == 0 && (!pe || atoi(pe) != 0)) kern = les_tile_kernel<T, CT, MODEL, TX, TY, ZC, MODEL == 0>;
+    if (smem > 48 * 1024) INSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<gr, b, smem, L.stream>>>(g, e, u, visc_in, visc_out, C, k_out, v, cv, acc, ca);
     if (L.counter) ++*L.counter;
     INSB_CUDA(cudaGetLastError());
     return 0;

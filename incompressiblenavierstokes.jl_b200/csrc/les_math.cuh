@@ -115,6 +115,25 @@ struct LesGLoad {
     LES_HD T operator()(int c, int dx, int dy, int dz) const { return LES_LD(p + c * cs + dx + dy * s1 + dz * s2); }
 };
 
+// Metric tables by absolute index t of dimension a: straight from the Grid (read-only cache), or from the slices a
+// tile kernel staged in shared memory (p[a] points at the entry of index 0 of table 0; tables LEN entries apart).
+template <typename T>
+struct LesGridTab {
+    const Grid<T> &g;
+    LES_HD T rdl(int a, int t) const { return LES_LD(g.rdl[a] + t); }
+    LES_HD T rdu(int a, int t) const { return LES_LD(g.rdu[a] + t); }
+    LES_HD T wa(int a, int t) const { return LES_LD(g.wa[a] + t); }
+    LES_HD T wb(int a, int t) const { return LES_LD(g.wb[a] + t); }
+};
+template <typename T, int LEN>
+struct LesSmemTab {
+    const T *p[3];
+    LES_HD T rdl(int a, int t) const { return p[a][0 * LEN + t]; }
+    LES_HD T rdu(int a, int t) const { return p[a][1 * LEN + t]; }
+    LES_HD T wa(int a, int t) const { return p[a][2 * LEN + t]; }
+    LES_HD T wb(int a, int t) const { return p[a][3 * LEN + t]; }
+};
+
 // Where the values of a cell field at the neighbours I - e_d / I + e_d come from (EDGE: cell I touches a
 // ghost plane).  Periodic: the velocity / viscosity ghost planes hold the periodic images, so the stencil is
 // evaluated at the ghost position itself, only the metric tables are taken at the image (N-2 resp. 1: the
@@ -156,8 +175,8 @@ struct LesNb {
 // collocate_tensor (:235-250) straight from the velocity: M[a][b] at the centre of cell I, the staggered
 // gradients gradient_tensor_kernel! (:57-74) would have stored recomputed at I, I - e_lo, I - e_hi,
 // I - e_lo - e_hi (the reference's summation order)
-template <typename T, bool EDGE, typename LU>
-LES_HD void les_collocated_gradient(const Grid<T> &g, const LesEdge &e, const LU &U, const int I[3], T (&M)[3][3]) {
+template <typename T, bool EDGE, typename LU, typename MET>
+LES_HD void les_collocated_gradient(const Grid<T> &g, const MET &mt, const LesEdge &e, const LU &U, const int I[3], T (&M)[3][3]) {
     LesNb<EDGE> nb;
     nb.init(g, e, I);
 #pragma unroll
@@ -165,7 +184,7 @@ LES_HD void les_collocated_gradient(const Grid<T> &g, const LesEdge &e, const LU
 #pragma unroll
         for (int b = 0; b < 3; b++) {
             if (a == b) {
-                M[a][a] = (U(a, 0, 0, 0) - U(a, a == 0 ? -1 : 0, a == 1 ? -1 : 0, a == 2 ? -1 : 0)) * LES_LD(g.rdl[a] + I[a]);
+                M[a][a] = (U(a, 0, 0, 0) - U(a, a == 0 ? -1 : 0, a == 1 ? -1 : 0, a == 2 ? -1 : 0)) * mt.rdl(a, I[a]);
             } else {
                 const int lo = a < b ? a : b, hi = a < b ? b : a;
                 T sum = T(0);
@@ -184,7 +203,7 @@ LES_HD void les_collocated_gradient(const Grid<T> &g, const LesEdge &e, const LU
                     }
                     int o2[3] = {o[0], o[1], o[2]};
                     o2[b] += 1;
-                    T v = (U(a, o2[0], o2[1], o2[2]) - U(a, o[0], o[1], o[2])) * LES_LD(g.rdu[b] + tb);
+                    T v = (U(a, o2[0], o2[1], o2[2]) - U(a, o[0], o[1], o[2])) * mt.rdu(b, tb);
                     if (EDGE && z) v = T(0);
                     sum = c == 0 ? v : sum + v;
                 }
@@ -196,33 +215,34 @@ LES_HD void les_collocated_gradient(const Grid<T> &g, const LesEdge &e, const LU
 
 // sigma_aa = -2 nu_t du_a/dx_a at the cell I + o (apply_eddy_viscosity_kernel!, :144-181); ta = index of the
 // metric tables of dimension a there
-template <typename T, typename LU, typename LV>
-LES_HD T les_sigma_diag(const Grid<T> &g, const LU &U, const LV &V, int a, const int o[3], int ta) {
+template <typename T, typename LU, typename LV, typename MET>
+LES_HD T les_sigma_diag(const MET &mt, const LU &U, const LV &V, int a, const int o[3], int ta) {
     int o1[3] = {o[0], o[1], o[2]};
     o1[a] -= 1;
-    const T G = (U(a, o[0], o[1], o[2]) - U(a, o1[0], o1[1], o1[2])) * LES_LD(g.rdl[a] + ta);
+    const T G = (U(a, o[0], o[1], o[2]) - U(a, o1[0], o1[1], o1[2])) * mt.rdl(a, ta);
     return T(-2) * V(0, o[0], o[1], o[2]) * G;
 }
 
 // sigma_ab = -2 nu_ab (du_a/dx_b + du_b/dx_a)/2 at the edge point of the cell I + o, a < b; nu_ab is the
 // viscosity interpolated from the four surrounding centres (symmetrize! :81-86 + :144-181); ta, tb = indices
 // of the metric tables of dimensions a and b there
-template <typename T, typename LU, typename LV>
-LES_HD T les_sigma_off(const Grid<T> &g, const LU &U, const LV &V, int a, int b, const int o[3], int ta, int tb) {
+template <typename T, typename LU, typename LV, typename MET>
+LES_HD T les_sigma_off(const MET &mt, const LU &U, const LV &V, int a, int b, const int o[3], int ta, int tb) {
     int oa[3] = {o[0], o[1], o[2]}, ob[3] = {o[0], o[1], o[2]}, oab[3] = {o[0], o[1], o[2]};
     oa[a] += 1, ob[b] += 1, oab[a] += 1, oab[b] += 1;
-    const T Gab = (U(a, ob[0], ob[1], ob[2]) - U(a, o[0], o[1], o[2])) * LES_LD(g.rdu[b] + tb);
-    const T Gba = (U(b, oa[0], oa[1], oa[2]) - U(b, o[0], o[1], o[2])) * LES_LD(g.rdu[a] + ta);
-    const T wa_a = LES_LD(g.wa[a] + ta), wb_a = LES_LD(g.wb[a] + ta);
-    const T wa_b = LES_LD(g.wa[b] + tb), wb_b = LES_LD(g.wb[b] + tb);
+    const T Gab = (U(a, ob[0], ob[1], ob[2]) - U(a, o[0], o[1], o[2])) * mt.rdu(b, tb);
+    const T Gba = (U(b, oa[0], oa[1], oa[2]) - U(b, o[0], o[1], o[2])) * mt.rdu(a, ta);
+    const T wa_a = mt.wa(a, ta), wb_a = mt.wb(a, ta);
+    const T wa_b = mt.wa(b, tb), wb_b = mt.wb(b, tb);
     const T nu = wa_a * wa_b * V(0, o[0], o[1], o[2]) + wb_a * wa_b * V(0, oa[0], oa[1], oa[2]) +
                  wa_a * wb_b * V(0, ob[0], ob[1], ob[2]) + wb_a * wb_b * V(0, oab[0], oab[1], oab[2]);
     return T(-2) * nu * ((Gab + Gba) * T(0.5));
 }
 
 // divoftensor_kernel! (:200-219) with the stress recomputed on the fly: f[a] = sum_b d(sigma_ab)/dx_b at cell I
-template <typename T, bool EDGE, typename LU, typename LV>
-LES_HD void les_stress_divergence(const Grid<T> &g, const LesEdge &e, const LU &U, const LV &V, const int I[3], T (&f)[3]) {
+template <typename T, bool EDGE, typename LU, typename LV, typename MET>
+LES_HD void les_stress_divergence(const Grid<T> &g, const MET &mt, const LesEdge &e, const LU &U, const LV &V, const int I[3],
+                                  T (&f)[3]) {
     LesNb<EDGE> nb;
     nb.init(g, e, I);
     // diagonal stresses at I and I + e_a
@@ -230,11 +250,11 @@ LES_HD void les_stress_divergence(const Grid<T> &g, const LesEdge &e, const LU &
 #pragma unroll
     for (int a = 0; a < 3; a++) {
         int o[3] = {0, 0, 0};
-        const T s0 = les_sigma_diag<T>(g, U, V, a, o, I[a]);
+        const T s0 = les_sigma_diag<T>(mt, U, V, a, o, I[a]);
         o[a] = nb.op[a];
-        T s1 = les_sigma_diag<T>(g, U, V, a, o, nb.tp[a]);
+        T s1 = les_sigma_diag<T>(mt, U, V, a, o, nb.tp[a]);
         if (EDGE && nb.zp[a]) s1 = T(0);
-        dterm[a] = (s1 - s0) * LES_LD(g.rdu[a] + I[a]);
+        dterm[a] = (s1 - s0) * mt.rdu(a, I[a]);
     }
     // off-diagonal stresses at I, I - e_a, I - e_b:  oterm[a][b] = d(sigma_ab)/dx_b
     T oterm[3][3];
@@ -243,16 +263,16 @@ LES_HD void les_stress_divergence(const Grid<T> &g, const LesEdge &e, const LU &
 #pragma unroll
         for (int b = a + 1; b < 3; b++) {
             int o[3] = {0, 0, 0};
-            const T s0 = les_sigma_off<T>(g, U, V, a, b, o, I[a], I[b]);
+            const T s0 = les_sigma_off<T>(mt, U, V, a, b, o, I[a], I[b]);
             o[b] = nb.om[b];
-            T sb = les_sigma_off<T>(g, U, V, a, b, o, I[a], nb.tm[b]);
+            T sb = les_sigma_off<T>(mt, U, V, a, b, o, I[a], nb.tm[b]);
             if (EDGE && nb.zm[b]) sb = T(0);
             o[b] = 0;
             o[a] = nb.om[a];
-            T sa = les_sigma_off<T>(g, U, V, a, b, o, nb.tm[a], I[b]);
+            T sa = les_sigma_off<T>(mt, U, V, a, b, o, nb.tm[a], I[b]);
             if (EDGE && nb.zm[a]) sa = T(0);
-            oterm[a][b] = (s0 - sb) * LES_LD(g.rdl[b] + I[b]);
-            oterm[b][a] = (s0 - sa) * LES_LD(g.rdl[a] + I[a]);
+            oterm[a][b] = (s0 - sb) * mt.rdl(b, I[b]);
+            oterm[b][a] = (s0 - sa) * mt.rdl(a, I[a]);
         }
     f[0] = dterm[0] + oterm[0][1] + oterm[0][2];
     f[1] = oterm[1][0] + dterm[1] + oterm[1][2];

@@ -541,17 +541,31 @@ __global__ void __launch_bounds__(256) bouss_extra_kernel(Grid<T> g, StageArgs<T
 // marches a TX x TY column along z with the planes z-1, z, z+1 of (u_x, u_y, u_z, temp) and a
 // one-cell halo in a 4-slot ring (next plane prefetched into registers during the arithmetic), so
 // every value comes from HBM/L2 once per block column.
-template <typename T, typename CT, int TX, int TY, int ZC, bool PREF>
+// TAB: the slices of the six metric tables the block needs sit in shared memory too (one LDS with an immediate
+// offset per entry instead of a parameter load + 64-bit address + LDG: the pass is issue-bound).
+template <typename T, typename CT, int TX, int TY, int ZC, bool PREF, bool TAB>
 __global__ void __launch_bounds__(TX *TY, sizeof(T) == 4 ? 4 : 2) bouss_tile_kernel(Grid<T> g, StageArgs<T> a) {
     constexpr int PX = TX + 2, PY = TY + 2, PLANE = PX * PY, NT = TX * TY, NE = 4 * PLANE;
     constexpr int NL = (NE + NT - 1) / NT;
+    constexpr int LX = TX + 2, LY = TY + 2, LZ = ZC + 2, LEN = LX + LY + LZ;  // table slices: x, y, z back to back
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *s = reinterpret_cast<T *>(smem_raw);  // [4 slots][u_x, u_y, u_z, temp][PY][PX]
+    T *mt = s + 4 * NE;                      // [rdu, rdl, rdlg, rdug, wa, wb][LEN]
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
     const int x0 = 1 + blockIdx.x * TX, y0 = 1 + blockIdx.y * TY;
     const int zbeg = 1 + blockIdx.z * ZC;
     const int zend = min(zbeg + ZC, g.N[2] - 1);
     if (zbeg >= zend) return;
+    if (TAB) {  // entry r of a slice <-> index base - 1 + r of the dimension (clamped; clamped entries are never used)
+        for (int e = tid; e < 6 * LEN; e += NT) {
+            const int tb = e / LEN, r = e - tb * LEN;
+            const int d = r < LX ? 0 : r < LX + LY ? 1 : 2;
+            const int rl = d == 0 ? r : d == 1 ? r - LX : r - LX - LY;
+            const int gi = min((d == 0 ? x0 : d == 1 ? y0 : zbeg) - 1 + rl, g.N[d] - 1);
+            const T *tp = tb == 0 ? g.rdu[d] : tb == 1 ? g.rdl[d] : tb == 2 ? g.rdlg[d] : tb == 3 ? g.rdug[d] : tb == 4 ? g.wa[d] : g.wb[d];
+            mt[e] = __ldg(tp + gi);
+        }
+    }
     const T *lp[NL];
     bool lv[NL];
 #pragma unroll
@@ -611,7 +625,11 @@ __global__ void __launch_bounds__(TX *TY, sizeof(T) == 4 ? 4 : 2) bouss_tile_ker
                 if (grav_ok && a.v) o_v = a.v[qg];
                 if (grav_ok && a.acc_out) o_acc = a.acc_out[qg];
             }
-            const T kt = temperature_rhs<T, 3>(U, Tm, g, I, (T)a.kappa, (T)a.nu, a.dodiss != 0);
+            // entries of this thread's cell in the table slices (x: tx + 1, y: ty + 1, z: z - zbeg + 1)
+            SmemTab<T, LEN> MT;
+            MT.p[0] = mt + tx + 1, MT.p[1] = mt + LX + ty + 1, MT.p[2] = mt + LX + LY + (z - zbeg) + 1;
+            const T kt = TAB ? temperature_rhs_m<T, 3>(U, Tm, MT, (T)a.kappa, (T)a.nu, a.dodiss != 0)
+                             : temperature_rhs<T, 3>(U, Tm, g, I, (T)a.kappa, (T)a.nu, a.dodiss != 0);
             if (a.tk_out) a.tk_out[idx] = kt;
             if (a.tv) {
                 T x = PREF ? o_tb : a.tvbase[idx];
@@ -621,7 +639,12 @@ __global__ void __launch_bounds__(TX *TY, sizeof(T) == 4 ? 4 : 2) bouss_tile_ker
             if (a.tacc_out) a.tacc_out[idx] = axpy_rn<T, CT>(PREF ? o_ta : a.tacc_in[idx], a.ca, kt);
             if (grav_ok) {
                 const int c = a.gdir;
-                const T gk = (T)a.grav * (c == 0 ? avg_face<3>(Tm, g, I, 0, 0) : c == 1 ? avg_face<3>(Tm, g, I, 1, 0) : avg_face<3>(Tm, g, I, 2, 0));
+                T av;
+                if (TAB)
+                    av = c == 0 ? avg_face_m<3, T>(Tm, MT, 0, 0) : c == 1 ? avg_face_m<3, T>(Tm, MT, 1, 0) : avg_face_m<3, T>(Tm, MT, 2, 0);
+                else
+                    av = c == 0 ? avg_face<3>(Tm, g, I, 0, 0) : c == 1 ? avg_face<3>(Tm, g, I, 1, 0) : avg_face<3>(Tm, g, I, 2, 0);
+                const T gk = (T)a.grav * av;
                 if (a.k_out) a.k_out[qg] += gk;
                 if (a.v) a.v[qg] = axpy_rn<T, CT>(PREF ? o_v : a.v[qg], a.cv, gk);
                 if (a.acc_out) a.acc_out[qg] = axpy_rn<T, CT>(PREF ? o_acc : a.acc_out[qg], a.ca, gk);
@@ -645,14 +668,21 @@ static int launch_stage_bouss_split(const Grid<T> &g, const StageArgs<T> &a, Lau
     const char *te = getenv("INSB200_BOUSS_TILE");
     if (!te || atoi(te) != 0) {
         constexpr int TX = 32, TY = 8, ZC = 64;
-        constexpr size_t smem = (size_t)4 * 4 * (TX + 2) * (TY + 2) * sizeof(T);
+        constexpr size_t smem_f = (size_t)4 * 4 * (TX + 2) * (TY + 2) * sizeof(T);
+        constexpr size_t smem_t = smem_f + (size_t)6 * (TX + 2 + TY + 2 + ZC + 2) * sizeof(T);
         dim3 b(TX, TY, 1);
         dim3 gr((g.N[0] - 2 + TX - 1) / TX, (g.N[1] - 2 + TY - 1) / TY, (g.N[2] - 2 + ZC - 1) / ZC);
-        const char *pe = getenv("INSB200_BOUSS_PREFETCH");
-        if (!pe || atoi(pe) != 0)
-            bouss_tile_kernel<T, CT, TX, TY, ZC, true><<<gr, b, smem, L.stream>>>(g, a);
-        else
-            bouss_tile_kernel<T, CT, TX, TY, ZC, false><<<gr, b, smem, L.stream>>>(g, a);
+        const char *pe = getenv("INSB200_BOUSS_PREFETCH"), *se = getenv("INSB200_BOUSS_SMEMTAB");
+        const bool pref = !pe || atoi(pe) != 0, tab = !se || atoi(se) != 0;
+        if (tab && pref) {
+            auto kern = bouss_tile_kernel<T, CT, TX, TY, ZC, true, true>;
+            if (smem_t > 48 * 1024) INSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+            kern<<<gr, b, smem_t, L.stream>>>(g, a);
+        } else if (pref) {
+            bouss_tile_kernel<T, CT, TX, TY, ZC, true, false><<<gr, b, smem_f, L.stream>>>(g, a);
+        } else {
+            bouss_tile_kernel<T, CT, TX, TY, ZC, false, false><<<gr, b, smem_f, L.stream>>>(g, a);
+        }
         if (L.counter) ++*L.counter;
         INSB_CUDA(cudaGetLastError());
         return 0;

@@ -108,44 +108,74 @@ __device__ __forceinline__ void momentum_rhs(const LD &U, const Grid<T> &g, cons
     momentum_rhs_m<T, D, FULL>(U, M, nu, cfac, k);
 }
 
+// Metric tables of the temperature / collocated-gradient functions at offset o (-1, 0) from I[i]:
+// straight from global memory (read-only cache), or from the slices a tile kernel staged in shared memory.
+template <typename T>
+struct GridTab {
+    const Grid<T> &g;
+    const int *I;
+    __device__ __forceinline__ T rdu(int i, int o) const { return __ldg(g.rdu[i] + I[i] + o); }
+    __device__ __forceinline__ T rdl(int i, int o) const { return __ldg(g.rdl[i] + I[i] + o); }
+    __device__ __forceinline__ T rdlg(int i, int o) const { return __ldg(g.rdlg[i] + I[i] + o); }
+    __device__ __forceinline__ T rdug(int i, int o) const { return __ldg(g.rdug[i] + I[i] + o); }
+    __device__ __forceinline__ T wa(int i, int o) const { return __ldg(g.wa[i] + I[i] + o); }
+    __device__ __forceinline__ T wb(int i, int o) const { return __ldg(g.wb[i] + I[i] + o); }
+};
+template <typename T, int LEN>
+struct SmemTab {  // p[i] points at the entry of I[i] in table 0 (rdu); tables LEN entries apart: rdu, rdl, rdlg, rdug, wa, wb
+    const T *p[3];
+    __device__ __forceinline__ T rdu(int i, int o) const { return p[i][0 * LEN + o]; }
+    __device__ __forceinline__ T rdl(int i, int o) const { return p[i][1 * LEN + o]; }
+    __device__ __forceinline__ T rdlg(int i, int o) const { return p[i][2 * LEN + o]; }
+    __device__ __forceinline__ T rdug(int i, int o) const { return p[i][3 * LEN + o]; }
+    __device__ __forceinline__ T wa(int i, int o) const { return p[i][4 * LEN + o]; }
+    __device__ __forceinline__ T wb(int i, int o) const { return p[i][5 * LEN + o]; }
+};
+
 // avg(temp, Δ, I + s*e_i, i)
-template <int D, typename T, typename LT>
-__device__ __forceinline__ T avg_face(const LT &Tm, const Grid<T> &g, const int I[3], int i, int s) {
+template <int D, typename T, typename LT, typename MET>
+__device__ __forceinline__ T avg_face_m(const LT &Tm, const MET &M, int i, int s) {
     T t0 = at2<D>(Tm, 0, i, s, i, 0);
     T t1 = at2<D>(Tm, 0, i, s + 1, i, 0);
-    return __ldg(g.wa[i] + I[i] + s) * t0 + __ldg(g.wb[i] + I[i] + s) * t1;
+    return M.wa(i, s) * t0 + M.wb(i, s) * t1;
+}
+template <int D, typename T, typename LT>
+__device__ __forceinline__ T avg_face(const LT &Tm, const Grid<T> &g, const int I[3], int i, int s) {
+    return avg_face_m<D, T>(Tm, GridTab<T>{g, I}, i, s);
 }
 
 // guarded δ(u, i, j, I + off) for the collocated gradient
-template <typename T, int D, typename LD>
-__device__ __forceinline__ T delta_g(const LD &U, const Grid<T> &g, const int I[3], int i, int j,
-                                     int oi, int oj) {
+template <typename T, int D, typename LD, typename MET>
+__device__ __forceinline__ T delta_g_m(const LD &U, const MET &M, int i, int j, int oi, int oj) {
     // offset = oi*e_i + oj*e_j (oi, oj in {0,-1}); i == j: oi is the only offset
     if (i == j) {
         T a = at2<D>(U, i, i, oi - 1, i, 0);
         T b = at2<D>(U, i, i, oi, i, 0);
-        return (b - a) * __ldg(g.rdlg[i] + I[i] + oi);
+        return (b - a) * M.rdlg(i, oi);
     }
     T a = at2<D>(U, i, i, oi, j, oj);
     T b = at2<D>(U, i, i, oi, j, oj + 1);
-    return (b - a) * __ldg(g.rdug[j] + I[j] + oj);
+    return (b - a) * M.rdug(j, oj);
+}
+template <typename T, int D, typename LD>
+__device__ __forceinline__ T delta_g(const LD &U, const Grid<T> &g, const int I[3], int i, int j, int oi, int oj) {
+    return delta_g_m<T, D>(U, GridTab<T>{g, I}, i, j, oi, oj);
 }
 
 // Temperature right-hand side (convection_diffusion_temp! + optional dissipation!).
-template <typename T, int D, typename LD, typename LT>
-__device__ __forceinline__ T temperature_rhs(const LD &U, const LT &Tm, const Grid<T> &g,
-                                             const int I[3], T kappa, T nu, bool dodiss) {
+template <typename T, int D, typename LD, typename LT, typename MET>
+__device__ __forceinline__ T temperature_rhs_m(const LD &U, const LT &Tm, const MET &M, T kappa, T nu, bool dodiss) {
     T acc = T(0);
     T tc = Tm(0, 0, 0, 0);
 #pragma unroll
     for (int i = 0; i < D; i++) {
         T tm = at2<D>(Tm, 0, i, -1, i, 0);
         T tp = at2<D>(Tm, 0, i, +1, i, 0);
-        T dT1 = (tc - tm) * __ldg(g.rdu[i] + I[i] - 1);
-        T dT2 = (tp - tc) * __ldg(g.rdu[i] + I[i]);
-        T uT1 = at2<D>(U, i, i, -1, i, 0) * avg_face<D>(Tm, g, I, i, -1);
-        T uT2 = U(i, 0, 0, 0) * avg_face<D>(Tm, g, I, i, 0);
-        T t = (-(uT2 - uT1) + kappa * (dT2 - dT1)) * __ldg(g.rdl[i] + I[i]);
+        T dT1 = (tc - tm) * M.rdu(i, -1);
+        T dT2 = (tp - tc) * M.rdu(i, 0);
+        T uT1 = at2<D>(U, i, i, -1, i, 0) * avg_face_m<D, T>(Tm, M, i, -1);
+        T uT2 = U(i, 0, 0, 0) * avg_face_m<D, T>(Tm, M, i, 0);
+        T t = (-(uT2 - uT1) + kappa * (dT2 - dT1)) * M.rdl(i, 0);
         acc = (i == 0) ? t : acc + t;
     }
     if (dodiss) {
@@ -156,11 +186,10 @@ __device__ __forceinline__ T temperature_rhs(const LD &U, const LT &Tm, const Gr
             for (int i = 0; i < D; i++) {
                 T gij;
                 if (i == j) {
-                    gij = delta_g<T, D>(U, g, I, i, j, 0, 0);
+                    gij = delta_g_m<T, D>(U, M, i, j, 0, 0);
                 } else {
-                    gij = (delta_g<T, D>(U, g, I, i, j, 0, 0) + delta_g<T, D>(U, g, I, i, j, -1, 0) +
-                           delta_g<T, D>(U, g, I, i, j, 0, -1) +
-                           delta_g<T, D>(U, g, I, i, j, -1, -1)) *
+                    gij = (delta_g_m<T, D>(U, M, i, j, 0, 0) + delta_g_m<T, D>(U, M, i, j, -1, 0) +
+                           delta_g_m<T, D>(U, M, i, j, 0, -1) + delta_g_m<T, D>(U, M, i, j, -1, -1)) *
                           T(0.25);
                 }
                 ss += gij * gij;
@@ -169,6 +198,11 @@ __device__ __forceinline__ T temperature_rhs(const LD &U, const LT &Tm, const Gr
         acc += nu * ss;
     }
     return acc;
+}
+template <typename T, int D, typename LD, typename LT>
+__device__ __forceinline__ T temperature_rhs(const LD &U, const LT &Tm, const Grid<T> &g, const int I[3], T kappa, T nu,
+                                             bool dodiss) {
+    return temperature_rhs_m<T, D>(U, Tm, GridTab<T>{g, I}, kappa, nu, dodiss);
 }
 
 // Divergence (divergence!, src/operators.jl:242-247) optionally scaled with the cell volume

@@ -37,12 +37,13 @@ static void run(int phase, bool edge_all, const int N[3], const void *const tab[
                 // like the kernels: the ghost rules only where a cell touches a ghost plane (edge_all: everywhere,
                 // which must give the same result)
                 const bool edge = edge_all || i == 1 || j == 1 || k == 1 || i == N[0] - 2 || j == N[1] - 2 || k == N[2] - 2;
+                const LesGridTab<T> mt{g};
                 if (phase == 1) {
                     T M[3][3];
                     if (edge)
-                        les_collocated_gradient<T, true>(g, e, U, I, M);
+                        les_collocated_gradient<T, true>(g, mt, e, U, I, M);
                     else
-                        les_collocated_gradient<T, false>(g, e, U, I, M);
+                        les_collocated_gradient<T, false>(g, mt, e, U, I, M);
                     const T dx = g.dl[0][i], dy = g.dl[1][j], dz = g.dl[2][k];
                     T out;
                     switch (model) {
@@ -55,9 +56,9 @@ static void run(int phase, bool edge_all, const int N[3], const void *const tab[
                 } else {
                     T fl[3];
                     if (edge)
-                        les_stress_divergence<T, true>(g, e, U, V, I, fl);
+                        les_stress_divergence<T, true>(g, mt, e, U, V, I, fl);
                     else
-                        les_stress_divergence<T, false>(g, e, U, V, I, fl);
+                        les_stress_divergence<T, false>(g, mt, e, U, V, I, fl);
                     for (int c = 0; c < 3; c++) f[idx + c * g.cs] += -fl[c];
                 }
             }

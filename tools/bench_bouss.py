@@ -27,8 +27,10 @@ def main():
     P, D, S = I.PeriodicBC, I.DirichletBC, I.SymmetricBC
     sz = lambda n: max(8, int(round(n * a.scale / 2)) * 2)
     variants = {
-        np.float32: [("tile + prefetch (default)", {}), ("tile, no prefetch", {"INSB200_BOUSS_PREFETCH": "0"})],
-        np.float64: [("tile + prefetch (default)", {}), ("tile, no prefetch", {"INSB200_BOUSS_PREFETCH": "0"}),
+        np.float32: [("tile + prefetch + shared metric tables (default)", {}),
+                     ("tile + prefetch", {"INSB200_BOUSS_SMEMTAB": "0"}), ("tile, no prefetch", {"INSB200_BOUSS_PREFETCH": "0"})],
+        np.float64: [("tile + prefetch + shared metric tables (default)", {}),
+                     ("tile + prefetch", {"INSB200_BOUSS_SMEMTAB": "0"}), ("tile, no prefetch", {"INSB200_BOUSS_PREFETCH": "0"}),
                      ("direct", {"INSB200_BOUSS_TILE": "0"})],
     }
     for T in (np.float32, np.float64):
@@ -41,7 +43,7 @@ def main():
         temp = I.temperaturefield(sg, lambda x, y, z: 0.5 + np.sin(20 * x) * np.sin(np.pi * 20 * y) / 100 + 0 * z)
         params = dict(viscosity=2.5e-4, conductivity=2.5e-4, gravity=1.0, gdir=2, dodissipation=True)
         for tag, env in variants[T]:
-            for k in ("INSB200_BOUSS_TILE", "INSB200_BOUSS_PREFETCH"):
+            for k in ("INSB200_BOUSS_TILE", "INSB200_BOUSS_PREFETCH", "INSB200_BOUSS_SMEMTAB"):
                 os.environ.pop(k, None)
             os.environ.update(env)
             run(f"cfg4 RK44 {np.dtype(T).name} {tag}", sg, ps, {"u": u.clone(), "temp": temp.clone()}, I.RKMethods.RK44(T),
