@@ -226,7 +226,9 @@ int insb200_step_rk_host_ensemble(insb200_plan_t *plan, const double *A, const d
                                   const insb200_params_t *params, void *stream);
 
 /* eddy_viscosity_closure!(model, f, u, cache, setup) (src/eddyviscosity.jl:356-378): f -= div of the
- * modelled stress; the cache (visc, G) is plan-owned scratch. */
+ * modelled stress; u with its ghost cells filled, f and u distinct arrays.  The cache is plan-owned scratch:
+ * one scalar field (visc) on the default path, which recomputes the gradient tensor and the stress from u
+ * instead of storing them; the nine tensor components G only with PressureBC sides or on slabs. */
 int insb200_eddy_viscosity_closure(insb200_plan_t *plan, int model, double C, void *f, const void *u,
                                    void *stream);
 
