@@ -269,6 +269,13 @@ int insb200_random_field(insb200_plan_t *plan, void *u, const double *shell_ener
  * receives kmax + 1 host doubles whose sum is the mean kinetic energy density.  Synchronises. */
 int insb200_energy_spectrum(insb200_plan_t *plan, const void *u, int kmax, double *ehat, void *stream);
 
+/* The spectral sums turbulence_statistics(u, setup, viscosity) is made of (src/spectral.jl:144-257; same plans and
+ * preconditions as above): moments[j] = sum over all wavenumbers (spectralsum :89-90, conjugate modes counted) of
+ * |2 pi k / L|^(2 j) |u_hat(k)|^2 / 2, j = 0, 1, 2, with spectral_energy_field! (:75-87) and
+ * squared_wavenumbers_dimensional (:121-135) evaluated on the fly behind the solver's FFT passes.  The caller forms
+ * e = m0, diss = 2 nu m1, enstrophy_diss = 2 nu m2 and the derived scales.  3 host doubles; synchronises. */
+int insb200_spectral_moments(insb200_plan_t *plan, const void *u, double *moments, void *stream);
+
 /* solve_unsteady (src/solver.jl:77-149): the time loop itself, so that a run of many small steps
  * does not return to the host language per step.
  *   method 0: explicit Runge-Kutta with the tableau (A, c, s, coef_dtype) of insb200_step_rk;

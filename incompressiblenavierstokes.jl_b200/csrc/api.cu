@@ -1635,6 +1635,31 @@ int insb200_energy_spectrum(insb200_plan_t *pl, const void *u, int kmax, double 
     API_END
 }
 
+int insb200_spectral_moments(insb200_plan_t *pl, const void *u, double *moments, void *stream) {
+    API_BEGIN
+    if (!pl->ps) {
+        set_error("turbulence_statistics needs a plan with psolver_spectral");
+        return 1;
+    }
+    double lengths[3] = {0.0, 0.0, 0.0};
+    for (int a = 0; a < pl->D; a++) lengths[a] = pl->s.xlims[a][1] - pl->s.xlims[a][0];
+    double *dev = nullptr;
+    INSB_CUDA(cudaMalloc((void **)&dev, 3 * sizeof(double)));
+    Launch L = L_of(pl, stream);
+    int rc = poisson_spectral_moments(pl->ps, u, pl->ncell, lengths, dev, L);
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(moments, dev, 3 * sizeof(double), cudaMemcpyDeviceToHost, L.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(L.stream);
+        if (e != cudaSuccess) {
+            set_error(std::string("turbulence_statistics: ") + cudaGetErrorString(e));
+            rc = 1;
+        }
+    }
+    cudaFree(dev);
+    return rc;
+    API_END
+}
+
 int insb200_maxabs(insb200_plan_t *pl, const void *u, double *out, void *stream) {
     API_BEGIN
     Launch L = L_of(pl, stream);

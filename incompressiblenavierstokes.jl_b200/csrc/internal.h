@@ -215,7 +215,10 @@ void poisson_destroy(Poisson *p);
 long long poisson_bytes(const Poisson *p);
 int poisson_iterations(const Poisson *p);
 // energyspectrum (src/spectral.jl:75-117): ehat = kmax + 1 device doubles
-int poisson_energy_spectrum(Poisson *ps, const void *u, long long cs, int kmax, double *ehat, Launch L);  // psolver_cg: iterations of the last solve
+int poisson_energy_spectrum(Poisson *ps, const void *u, long long cs, int kmax, double *ehat, Launch L);
+// spectral sums of turbulence_statistics (src/spectral.jl:166-257): mom = 3 device doubles, sum of |k|^(2j) e(k), j = 0..2,
+// with the dimensional wavenumbers 2 pi k / lengths[a]
+int poisson_spectral_moments(Poisson *ps, const void *u, long long cs, const double lengths[3], double *mom, Launch L);  // psolver_cg: iterations of the last solve
 // random_field (src/initializers.jl:109-183): the interior of u holds white noise (fill == 0) or is filled with
 // Philox N(0, 1) from `seed` first; e0_host[kappa] = target energy of shell kappa (kdiag + 1 entries)
 int poisson_random_field(Poisson *ps, void *u, long long cs, const double *e0_host, int nshell, int fill,

@@ -949,9 +949,45 @@ __global__ void __launch_bounds__(256) spectrum_bin_kernel(const Cx<T> *__restri
         if (bins[i] != 0.0) atomicAdd(ehat + i, bins[i]);
 }
 
-// u: ghosted velocity field (D components, stride cs); ehat: kmax + 1 device doubles (zeroed here)
+// Spectral sums of turbulence_statistics (src/spectral.jl:89-90, :121-135, :166-257): mom[j] += sum over all
+// wavenumbers (conjugate modes counted) of |2 pi k / L|^(2 j) |u_hat|^2 / (2 N^2), j = 0, 1, 2; c[a] = (2 pi / L_a)^2.
 template <typename T>
-static int spectrum_t(Poisson *ps, const T *u, long long cs, int kmax, double *ehat, Launch L) {
+__global__ void __launch_bounds__(256) spectrum_moment_kernel(const Cx<T> *__restrict__ W, int m0, int m0p, int n0, int n1, int n2,
+                                                              double scale, double c0, double c1, double c2, double *mom) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    const long long total = (long long)m0 * n1 * n2;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+        const int kx = (int)(q % m0);
+        const int iy = (int)((q / m0) % n1), iz = (int)(q / ((long long)m0 * n1));
+        const int ky = iy < (n1 + 1) / 2 ? iy : iy - n1;  // fftfreq_int (spectral.jl:7)
+        const int kz = n2 > 1 ? (iz < (n2 + 1) / 2 ? iz : iz - n2) : 0;
+        const double k2 = c0 * (double)kx * (double)kx + c1 * (double)ky * (double)ky + c2 * (double)kz * (double)kz;
+        const Cx<T> v = W[kx + (long long)iy * m0p + (long long)iz * m0p * n1];
+        const double w = (kx > 0 && kx < n0 / 2) ? 2.0 : 1.0;
+        const double e = w * scale * ((double)v.x * (double)v.x + (double)v.y * (double)v.y);
+        s0 += e, s1 += k2 * e, s2 += k2 * k2 * e;
+    }
+    __shared__ double part[8][3];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_down_sync(0xffffffffu, s0, o);
+        s1 += __shfl_down_sync(0xffffffffu, s1, o);
+        s2 += __shfl_down_sync(0xffffffffu, s2, o);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) part[warp][0] = s0, part[warp][1] = s1, part[warp][2] = s2;
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double t = 0.0;
+        for (int wv = 0; wv < 8; wv++) t += part[wv][threadIdx.x];
+        atomicAdd(mom + threadIdx.x, t);
+    }
+}
+
+// u: ghosted velocity field (D components, stride cs); ehat: kmax + 1 device doubles (zeroed here), or -- with
+// moment_c -- the three spectral moments of spectrum_moment_kernel
+template <typename T>
+static int spectrum_t(Poisson *ps, const T *u, long long cs, int kmax, double *ehat, Launch L, const double *moment_c = nullptr) {
     const int D = ps->D;
     long long rs[3] = {1, ps->Ng[0], (long long)ps->Ng[0] * ps->Ng[1]};
     FastGeom g;
@@ -963,7 +999,7 @@ static int spectrum_t(Poisson *ps, const T *u, long long cs, int kmax, double *e
     }
     g.m0p = (int)ps->wstride[1];
     const T *e0 = (const T *)ps->eig[0];
-    INSB_CUDA(cudaMemsetAsync(ehat, 0, (size_t)(kmax + 1) * sizeof(double), L.stream));
+    INSB_CUDA(cudaMemsetAsync(ehat, 0, (size_t)(moment_c ? 3 : kmax + 1) * sizeof(double), L.stream));
     double np = 1.0;
     for (int a = 0; a < D; a++) np *= (double)ps->n[a];
     for (int c = 0; c < D; c++) {
@@ -972,8 +1008,13 @@ static int spectrum_t(Poisson *ps, const T *u, long long cs, int kmax, double *e
         INSB_TRY(fast_pass<T>(3, ps->n[0], R, ps->W, g, 0, ps->tw[0], e0, e0, e0, T(1), 0, L));
         INSB_TRY(fast_pass<T>(0, ps->n[1], R, ps->W, g, 1, ps->tw[1], e0, e0, e0, T(1), 0, L));
         if (D == 3) INSB_TRY(fast_pass<T>(0, ps->n[2], R, ps->W, g, 2, ps->tw[2], e0, e0, e0, T(1), 0, L));
-        spectrum_bin_kernel<T><<<148 * 4, 256, (size_t)(kmax + 1) * sizeof(double), L.stream>>>(
-            (const Cx<T> *)ps->W, ps->m[0], g.m0p, ps->n[0], ps->n[1], D == 3 ? ps->n[2] : 1, kmax, 1.0 / (2.0 * np * np), ehat);
+        if (moment_c)
+            spectrum_moment_kernel<T><<<148 * 4, 256, 0, L.stream>>>((const Cx<T> *)ps->W, ps->m[0], g.m0p, ps->n[0], ps->n[1],
+                                                                      D == 3 ? ps->n[2] : 1, 1.0 / (2.0 * np * np), moment_c[0],
+                                                                      moment_c[1], D == 3 ? moment_c[2] : 0.0, ehat);
+        else
+            spectrum_bin_kernel<T><<<148 * 4, 256, (size_t)(kmax + 1) * sizeof(double), L.stream>>>(
+                (const Cx<T> *)ps->W, ps->m[0], g.m0p, ps->n[0], ps->n[1], D == 3 ? ps->n[2] : 1, kmax, 1.0 / (2.0 * np * np), ehat);
         if (L.counter) ++*L.counter;
     }
     INSB_CUDA(cudaGetLastError());
@@ -991,6 +1032,19 @@ int poisson_energy_spectrum(Poisson *ps, const void *u, long long cs, int kmax, 
     }
     return ps->f64 ? spectrum_t<double>(ps, (const double *)u, cs, kmax, ehat, L)
                    : spectrum_t<float>(ps, (const float *)u, cs, kmax, ehat, L);
+}
+
+int poisson_spectral_moments(Poisson *ps, const void *u, long long cs, const double lengths[3], double *mom, Launch L) {
+    if (!ps || !ps->fast || ps->comm) {
+        set_error("turbulence_statistics needs a single-GPU psolver_spectral plan on a power-of-two periodic grid");
+        return 1;
+    }
+    double c[3];
+    for (int a = 0; a < 3; a++) {
+        const double k = lengths[a] > 0.0 ? 2.0 * 3.14159265358979323846 / lengths[a] : 0.0;
+        c[a] = k * k;
+    }
+    return ps->f64 ? spectrum_t<double>(ps, (const double *)u, cs, 0, mom, L, c) : spectrum_t<float>(ps, (const float *)u, cs, 0, mom, L, c);
 }
 
 // ----------------------------------------------------------------------------------------

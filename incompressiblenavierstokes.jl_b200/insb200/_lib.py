@@ -115,6 +115,7 @@ _PROTOTYPES = {
     "insb200_kinetic_energy": (C.c_int, [_P, _P, _P, C.c_int, _P]),
     "insb200_total_kinetic_energy": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_double), _P]),
     "insb200_energy_spectrum": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_double), _P]),
+    "insb200_spectral_moments": (C.c_int, [_P, _P, C.POINTER(C.c_double), _P]),
     "insb200_random_field": (C.c_int, [_P, _P, C.POINTER(C.c_double), C.c_int, C.c_int, C.c_ulonglong, C.c_double, _P]),
     "insb200_solve_unsteady": (
         C.c_int,

@@ -758,6 +758,37 @@ def energyspectrum(u, setup, psolver, kmax=None):
     return dict(kappa=np.arange(kmax + 1), ehat=np.array(out[:], dtype=setup.T))
 
 
+def turbulence_statistics(u, setup, viscosity, psolver):
+    """turbulence_statistics (src/spectral.jl:144-257): Kolmogorov scaling in 3-D, Kraichnan-Batchelor-Leith scaling
+    in 2-D, from the spectral sums insb200_spectral_moments evaluates behind the psolver_spectral plan's FFT passes
+    (uniform periodic grids only, like the reference's assert_uniform_periodic)."""
+    if getattr(psolver, "kind", None) != "spectral":
+        raise AssertionError("Turbulence statistics requires a uniform periodic grid (psolver_spectral plan)")
+    m = (C.c_double * 3)()
+    check(lib().insb200_spectral_moments(psolver.plan.h, _ptr(_chk(setup, u, True)), m, _stream()))
+    T = setup.T
+    nu, e = T(viscosity), T(m[0])
+    diss = T(2) * nu * T(m[1])
+    kmax = T(np.pi) * min(setup.Np[a] / (setup.xlims[a][1] - setup.xlims[a][0]) for a in range(setup.D))
+    if setup.D == 3:
+        uavg = np.sqrt(2 * e / 3)
+        l_kol = (nu**3 / diss) ** T(1 / 4)
+        l_tay = np.sqrt(15 * nu / diss) * uavg
+        l_int = uavg**3 / diss
+        return dict(e=e, uavg=uavg, diss=diss, l_int=l_int, l_tay=l_tay, l_kol=l_kol, t_int=l_int / uavg,
+                    t_tay=l_tay / uavg, t_kol=np.sqrt(nu / diss), Re_int=l_int * uavg / nu, Re_tay=l_tay * uavg / nu,
+                    kmax_eta=kmax * l_kol)
+    uavg = np.sqrt(e)
+    enstrophy = diss / (2 * nu)
+    omega_rms = np.sqrt(2 * enstrophy)
+    enstrophy_diss = T(2) * nu * T(m[2])
+    l_kra = (nu**3 / enstrophy_diss) ** T(1 / 6)
+    l_omega = uavg / omega_rms
+    return dict(e=e, uavg=uavg, diss=diss, enstrophy=enstrophy, palinstrophy=enstrophy_diss / (2 * nu),
+                enstrophy_diss=enstrophy_diss, omega_rms=omega_rms, l_kra=l_kra, l_omega=l_omega, t_eddy=1 / omega_rms,
+                t_ens=enstrophy_diss ** (-T(1 / 3)), Re=uavg * l_omega / nu, kmax_etaK=kmax * l_kra)
+
+
 # ------------------------------------------------------------------------------------
 # processors (src/processors.jl): the call-back boundary of solve_unsteady
 # ------------------------------------------------------------------------------------

@@ -528,6 +528,58 @@ function INS.random_field_b200(setup, psolver::B200PSolver, t = zero(eltype(setu
     u
 end
 
+# energyspectrum(u, setup; stuff)   (src/spectral.jl:75-117): the shells 0:kmax of spectral_stuff, evaluated behind the
+# psolver_spectral plan's FFT passes; returns (; κ, ehat) like the reference.
+function INS.energyspectrum(u::CuArray, setup, psolver::B200PSolver; stuff = nothing)
+    T = eltype(setup.x[1])
+    kmax = isnothing(stuff) ? minimum(setup.Np) ÷ 2 : Int(last(stuff.κ))
+    ehat = Vector{Float64}(undef, kmax + 1)
+    check(ccall((:insb200_energy_spectrum, libinsb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Cdouble}, Ptr{Cvoid}),
+        psolver.plan, devptr(u), Cint(kmax), ehat, stream()))
+    (; κ = 0:kmax, ehat = T.(ehat))
+end
+
+# turbulence_statistics(u, setup, viscosity)   (src/spectral.jl:144-257): the three spectral sums come from the library
+# (spectral_energy_field!, squared_wavenumbers_dimensional and spectralsum fused behind the FFT passes), the derived
+# scales are formed here exactly like the reference's two methods.
+function INS.turbulence_statistics(u::CuArray, setup, viscosity, psolver::B200PSolver)
+    (; Np, xlims) = setup
+    T = eltype(setup.x[1])
+    D = length(Np)
+    m = Vector{Float64}(undef, 3)
+    check(ccall((:insb200_spectral_moments, libinsb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cvoid}),
+        psolver.plan, devptr(u), m, stream()))
+    viscosity = T(viscosity)
+    e = T(m[1])
+    diss = 2 * viscosity * T(m[2])
+    kmax = T(π) * minimum(α -> Np[α] / (xlims[α][2] - xlims[α][1]), 1:D)
+    if D == 3
+        uavg = sqrt(2 * e / 3)
+        l_kol = (viscosity^3 / diss)^T(1 / 4)
+        l_tay = sqrt(15 * viscosity / diss) * uavg
+        l_int = uavg^3 / diss
+        t_int = l_int / uavg
+        t_tay = l_tay / uavg
+        t_kol = sqrt(viscosity / diss)
+        Re_int = l_int * uavg / viscosity
+        Re_tay = l_tay * uavg / viscosity
+        kmax_eta = kmax * l_kol
+        return (; e, uavg, diss, l_int, l_tay, l_kol, t_int, t_tay, t_kol, Re_int, Re_tay, kmax_eta)
+    end
+    uavg = sqrt(e)
+    enstrophy = diss / (2 * viscosity)
+    omega_rms = sqrt(2 * enstrophy)
+    enstrophy_diss = 2 * viscosity * T(m[3])
+    palinstrophy = enstrophy_diss / (2 * viscosity)
+    l_kra = (viscosity^3 / enstrophy_diss)^T(1 / 6)
+    l_omega = uavg / omega_rms
+    t_eddy = 1 / omega_rms
+    t_ens = enstrophy_diss^(-T(1 / 3))
+    Re = uavg * l_omega / viscosity
+    kmax_etaK = kmax * l_kra
+    (; e, uavg, diss, enstrophy, palinstrophy, enstrophy_diss, omega_rms, l_kra, l_omega, t_eddy, t_ens, Re, kmax_etaK)
+end
+
 # right_hand_side!(dudt, u, params_ref, t)   (src/sciml.jl:35-48)
 function INS.right_hand_side!(dudt::CuArray, u::CuArray, params_ref::Base.RefValue{<:Tuple{Any,<:B200PSolver,Any}}, t)
     setup, psolver, viscosity = params_ref[]

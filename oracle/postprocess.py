@@ -188,3 +188,70 @@ def energyspectrum(u, setup, kmax=None):
     w = efield * weight
     ehat = np.array([w[shell == kap].sum() for kap in range(kmax + 1)])
     return np.arange(kmax + 1), ehat
+
+
+def spectral_energy_field(u, setup):
+    """spectral_energy_field! (src/spectral.jl:75-87): sum over the components of |rfft(u_a)|^2 / (2 prod(Np)^2)
+    on the RFFT-sized array (real transform along dim 1 of the reference)."""
+    import scipy.fft as sfft
+
+    D, Np, T = setup.D, setup.Np, setup.T
+    axes = tuple(range(D - 1, -1, -1))
+    efield = 0
+    for a in range(D):
+        uhat = sfft.rfftn(np.ascontiguousarray(u[setup.Ip + (a,)]), axes=axes)
+        efield = efield + (uhat.real**2 + uhat.imag**2).astype(T)
+    return efield / (2 * T(np.prod(Np)) ** 2)
+
+
+def spectralsum(f):
+    """spectralsum (src/spectral.jl:89-90): sum over an RFFT-sized array, the missing conjugate modes counted."""
+    return f.sum() + f[1:-1].sum()
+
+
+def squared_wavenumbers_dimensional(setup):
+    """squared_wavenumbers_dimensional (src/spectral.jl:121-135): |2 pi k / L|^2 on the RFFT-sized array."""
+    D, Np, T = setup.D, setup.Np, setup.T
+    k2 = 0
+    for a in range(D):
+        L = T(setup.xlims[a][1] - setup.xlims[a][0])
+        kint = np.arange(Np[0] // 2 + 1) if a == 0 else np.fft.fftfreq(Np[a], 1.0 / Np[a])
+        shape = [1] * D
+        shape[a] = -1
+        k2 = k2 + ((T(2 * np.pi) * kint.astype(T) / L) ** 2).reshape(shape)
+    return k2
+
+
+def turbulence_statistics(u, setup, viscosity):
+    """turbulence_statistics (src/spectral.jl:144-257): Kolmogorov scaling in 3-D, Kraichnan-Batchelor-Leith
+    scaling in 2-D; uniform periodic grids only (assert_uniform_periodic, :10-23)."""
+    from .grid import PeriodicBC
+
+    T, D, Np = setup.T, setup.D, setup.Np
+    for a in range(D):
+        assert all(isinstance(b, PeriodicBC) for b in setup.bc_u[a]), "Turbulence statistics requires periodic boundary conditions"
+        d = np.asarray(setup.Delta[a])
+        assert np.all(np.abs(d - d[0]) <= np.sqrt(np.finfo(T).eps) * abs(d[0])), "Turbulence statistics requires a uniform grid"
+    nu = T(viscosity)
+    ef = spectral_energy_field(u, setup)
+    k2 = squared_wavenumbers_dimensional(setup)
+    e = spectralsum(ef)
+    diss = 2 * nu * spectralsum(k2 * ef)
+    kmax = T(np.pi) * min(Np[a] / (setup.xlims[a][1] - setup.xlims[a][0]) for a in range(D))
+    if D == 3:
+        uavg = np.sqrt(2 * e / 3)
+        l_kol = (nu**3 / diss) ** T(1 / 4)
+        l_tay = np.sqrt(15 * nu / diss) * uavg
+        l_int = uavg**3 / diss
+        return dict(e=e, uavg=uavg, diss=diss, l_int=l_int, l_tay=l_tay, l_kol=l_kol, t_int=l_int / uavg,
+                    t_tay=l_tay / uavg, t_kol=np.sqrt(nu / diss), Re_int=l_int * uavg / nu, Re_tay=l_tay * uavg / nu,
+                    kmax_eta=kmax * l_kol)
+    uavg = np.sqrt(e)
+    enstrophy = diss / (2 * nu)
+    omega_rms = np.sqrt(2 * enstrophy)
+    enstrophy_diss = 2 * nu * spectralsum(k2**2 * ef)
+    l_kra = (nu**3 / enstrophy_diss) ** T(1 / 6)
+    l_omega = uavg / omega_rms
+    return dict(e=e, uavg=uavg, diss=diss, enstrophy=enstrophy, palinstrophy=enstrophy_diss / (2 * nu),
+                enstrophy_diss=enstrophy_diss, omega_rms=omega_rms, l_kra=l_kra, l_omega=l_omega, t_eddy=1 / omega_rms,
+                t_ens=enstrophy_diss ** (-T(1 / 3)), Re=uavg * l_omega / nu, kmax_etaK=kmax * l_kra)

@@ -107,6 +107,36 @@ def test_energy_spectrum_matches_oracle(n, T):
     assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("T", [np.float64, np.float32])
+@pytest.mark.parametrize("n,L", [((64, 32, 128), (2 * np.pi, 1.0, 3.0)), ((128, 64), (1.0, 2.0))])
+def test_turbulence_statistics_match_oracle(n, L, T):
+    """turbulence_statistics (src/spectral.jl:144-257) through insb200_spectral_moments against the oracle's
+    restatement, anisotropic box lengths so that every dimension's 2 pi / L enters."""
+    import insb200 as I
+
+    D = len(n)
+    so, sg = make_setups(tuple(uniform(m, l) for m, l in zip(n, L)), ("P",) * D, T=T)
+    ps = I.psolver_spectral(sg)
+    u = smooth_vec(so, 131) + 0.05 * random_vec(so, 132)
+    nu = 2e-3
+    want = opp.turbulence_statistics(u.astype(T), so, nu)
+    got = I.turbulence_statistics(I.to_device(sg, u), sg, nu, ps)
+    assert set(got) == set(want)
+    for k, v in want.items():
+        assert abs(float(got[k]) - float(v)) <= (1e-11 if T is np.float64 else 2e-4) * abs(float(v)), (k, got[k], v)
+    assert all(np.asarray(v).dtype == np.dtype(T) for v in got.values())
+    # repeatable up to the order of the atomic adds, and the Poisson workspace is shared without harm
+    again = I.turbulence_statistics(I.to_device(sg, u), sg, nu, ps)
+    assert abs(float(again["diss"]) - float(got["diss"])) <= 1e-12 * float(got["diss"]) * (1 if T is np.float64 else 1e6)
+    f = smooth_vec(so, 133)[..., 0].copy(order="F")
+    a = I.to_host(ps(I.to_device(sg, f)))
+    I.turbulence_statistics(I.to_device(sg, u), sg, nu, ps)
+    assert np.array_equal(a, I.to_host(ps(I.to_device(sg, f))))
+    with pytest.raises(AssertionError):
+        so2, sg2 = make_setups(tuple(uniform(16) for _ in range(D)), ("D",) * D, T=T)
+        I.turbulence_statistics(I.vectorfield(sg2), sg2, nu, I.default_psolver(sg2))
+
+
 def test_field_observers_and_vtk_output(tmp_path):
     """observefield / observespectrum / vtk_writer (src/processors.jl:85-277) over the device diagnostics."""
     import xml.etree.ElementTree as ET

@@ -1,5 +1,6 @@
 """Oracle diagnostics (oracle/postprocess.py) against analytic fields and identities."""
 import numpy as np
+import pytest
 
 import oracle as O
 from oracle import bc as obc, initializers as oini, postprocess as opp
@@ -112,3 +113,44 @@ def test_random_field_spectrum_matches_target_profile():
         target = total * target / target.sum()
         assert abs(e.sum() - total) < 1e-12
         assert np.linalg.norm(e - target) <= 1e-8 * np.linalg.norm(target)
+
+
+def test_turbulence_statistics_relations_and_taylor_green_closed_form():
+    """test/spectral.jl:70-110 (relations between the statistics of a random field, 2-D and 3-D, assertion on
+    non-periodic setups) plus a closed form: the 2-D Taylor-Green vortex on [0, 2 pi]^2 has all its energy at
+    |k|^2 = 2, so e = 1/4, diss = 2 nu |k|^2 e = nu, enstrophy = 1/2, palinstrophy = |k|^4 e = 1."""
+    nu = 1e-3
+    for D in (2, 3):
+        x = tuple(np.linspace(0.0, 1.0, 33) for _ in range(D))
+        so = O.Setup(x, {"u": ((O.PeriodicBC(), O.PeriodicBC()),) * D})
+        u = oini.random_field(so, 0.0, totalenergy=0.1, rng=np.random.default_rng(42))
+        st = opp.turbulence_statistics(u, so, nu)
+        assert all(v > 0 for v in st.values())
+        assert abs(st["e"] - 0.1) < 1e-12
+        if D == 2:
+            assert "enstrophy" in st and "l_kra" in st and "l_kol" not in st
+            assert np.isclose(st["uavg"], np.sqrt(st["e"]))
+            assert np.isclose(st["diss"], 2 * nu * st["enstrophy"])
+            assert np.isclose(st["enstrophy_diss"], 2 * nu * st["palinstrophy"])
+        else:
+            assert "l_kol" in st and "enstrophy" not in st
+            assert np.isclose(st["uavg"], np.sqrt(2 * st["e"] / 3))
+            assert np.isclose(st["Re_tay"], st["l_tay"] * st["uavg"] / nu)
+            # mean dissipation by Parseval against the spectral derivative of each component
+            assert np.isclose(st["kmax_eta"], np.pi * 32 * (nu**3 / st["diss"]) ** 0.25)
+    n = 32
+    x = tuple(np.linspace(0.0, 2 * np.pi, n + 1) for _ in range(2))
+    so = O.Setup(x, {"u": ((O.PeriodicBC(), O.PeriodicBC()),) * 2})
+    u = O.vectorfield(so)
+    X0, Y0 = np.asarray(so.xu[0][0]).reshape(-1, 1), np.asarray(so.xu[0][1]).reshape(1, -1)
+    X1, Y1 = np.asarray(so.xu[1][0]).reshape(-1, 1), np.asarray(so.xu[1][1]).reshape(1, -1)
+    u[..., 0] = -np.sin(X0) * np.cos(Y0)
+    u[..., 1] = np.cos(X1) * np.sin(Y1)
+    st = opp.turbulence_statistics(u, so, nu)
+    assert abs(st["e"] - 0.25) < 1e-13 and abs(st["diss"] - nu) < 1e-15
+    assert abs(st["enstrophy"] - 0.5) < 1e-12 and abs(st["palinstrophy"] - 1.0) < 1e-12
+    assert abs(st["omega_rms"] - 1.0) < 1e-12 and abs(st["Re"] - 0.25 / nu) < 1e-9
+    xw = tuple(np.linspace(0.0, 1.0, 17) for _ in range(2))
+    sw = O.Setup(xw, {"u": ((O.DirichletBC(), O.DirichletBC()),) * 2})
+    with pytest.raises(AssertionError):
+        opp.turbulence_statistics(O.vectorfield(sw), sw, nu)
