@@ -171,3 +171,90 @@ def test_grids():
     for g in (O.cosine_grid(0.0, 2.0, 10), O.tanh_grid(0.0, 2.0, 10, 1.4), O.stretched_grid(0.0, 2.0, 10, 1.1)):
         assert np.isclose(g[0], 0) and np.isclose(g[-1], 2)
         assert np.all(np.diff(g) > 0)
+
+
+def _linear_u(setup, A, c):
+    """u_a = c_a + sum_b A[a, b] x_b at the velocity points of component a."""
+    D = setup.D
+    u = O.vectorfield(setup)
+    for a in range(D):
+        acc = c[a]
+        for b in range(D):
+            shape = [1] * D
+            shape[b] = -1
+            acc = acc + A[a, b] * np.asarray(setup.xu[a][b], dtype=np.float64).reshape(shape)
+        u[..., a] = acc
+    return u
+
+
+def _scalar_at_p(setup, fun):
+    D = setup.D
+    xs = []
+    for b in range(D):
+        shape = [1] * D
+        shape[b] = -1
+        xs.append(np.asarray(setup.xp[b], dtype=np.float64).reshape(shape))
+    out = O.scalarfield(setup)
+    out[...] = fun(*xs)
+    return out
+
+
+@pytest.mark.parametrize("D", [2, 3])
+def test_boussinesq_terms_closed_forms_on_stretched_grids(D):
+    """Known answers for the three Boussinesq kernels on the reference's stretched test grids (the reference only
+    checks that they run, test/operators.jl:169-205): for a linear velocity field the collocated gradient is exact, so
+    dissipation! gives nu |grad u|_F^2; for a linear temperature avg() is exact at the faces, so applygravity! gives
+    g T(x_face) and convection_diffusion_temp! gives -div(u T) exactly when u is constant along its own direction
+    (zero diffusion of a linear field)."""
+    setup = _setup(D)
+    rng = np.random.default_rng(11)
+    inner = (slice(2, -2),) * D  # the collocation reaches one cell to the left
+    # dissipation!
+    A = rng.standard_normal((D, D))
+    u = _linear_u(setup, A, rng.standard_normal(D))
+    diss = ops.dissipation_(O.scalarfield(setup), u, setup, 0.37)
+    np.testing.assert_allclose(diss[inner], 0.37 * np.sum(A * A), rtol=1e-11)
+    # applygravity!
+    g = rng.standard_normal(D)
+    temp = _scalar_at_p(setup, lambda *x: 0.3 + sum(gi * xi for gi, xi in zip(g, x)))
+    for gdir in range(D):
+        f = ops.applygravity_(O.vectorfield(setup), temp, setup, gdir, 1.7)
+        xs = []
+        for b in range(D):
+            shape = [1] * D
+            shape[b] = -1
+            xs.append(np.asarray(setup.xu[gdir][b], dtype=np.float64).reshape(shape))
+        want = 1.7 * (0.3 + sum(gi * xi for gi, xi in zip(g, xs)))
+        sl = (slice(1, -1),) * D
+        np.testing.assert_allclose(f[sl + (gdir,)], np.broadcast_to(want, f[..., gdir].shape)[sl], rtol=1e-12)
+        for a in range(D):
+            if a != gdir:
+                assert np.all(f[..., a] == 0)
+    # convection_diffusion_temp!: u_a = c_a + sum_{b != a} A[a, b] x_b (divergence free, constant along a)
+    A0 = A - np.diag(np.diag(A))
+    c0 = rng.standard_normal(D)
+    u = _linear_u(setup, A0, c0)
+    ct = ops.convection_diffusion_temp_(O.scalarfield(setup), u, temp, setup, 0.21)
+    xs = []
+    for b in range(D):
+        shape = [1] * D
+        shape[b] = -1
+        xs.append(np.asarray(setup.xp[b], dtype=np.float64).reshape(shape))
+    want = 0
+    for a in range(D):  # -d/dx_a (u_a T) = -u_a g_a with u_a at the cell centre (it does not depend on x_a)
+        ua = c0[a] + sum(A0[a, b] * xs[b] for b in range(D))
+        want = want - ua * g[a]
+    sl = (slice(1, -1),) * D
+    np.testing.assert_allclose(ct[sl], np.broadcast_to(want, ct.shape)[sl], rtol=1e-10, atol=1e-12)
+
+
+def test_temperature_diffusion_of_a_parabola_is_exact_on_a_uniform_grid():
+    """kappa * laplace(T) for T = sum q_a x_a^2 is 2 kappa sum(q) exactly (central differences of a quadratic), u = 0."""
+    x = tuple(np.linspace(0.0, L, n + 1) for n, L in ((8, 1.0), (10, 2.0), (6, 0.5)))
+    b = (O.PeriodicBC(), O.PeriodicBC())
+    setup = O.Setup(x, dict(u=(b,) * 3, temp=(b,) * 3))
+    q = np.array([0.7, -1.3, 2.1])
+    temp = _scalar_at_p(setup, lambda X, Y, Z: q[0] * X**2 + q[1] * Y**2 + q[2] * Z**2)
+    ct = ops.convection_diffusion_temp_(O.scalarfield(setup), O.vectorfield(setup), temp, setup, 0.4)
+    inner = (slice(2, -2),) * 3  # away from the periodic seam, where the parabola is not periodic
+    np.testing.assert_allclose(ct[inner], 0.4 * 2 * q.sum(), rtol=1e-11)
