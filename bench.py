@@ -34,7 +34,7 @@ for p in (ROOT, PKG):
 import numpy as np  # noqa: E402
 
 # ncu --set full, bytes per launch (average over the 4 launches of an RK44 step where they differ)
-NCU_TRAFFIC_SOURCE = ("profiles/r2v_ncu_full_summary.md + profiles/r2w (dram__bytes_read.sum + dram__bytes_write.sum per launch; "
+NCU_TRAFFIC_SOURCE = ("profiles/r3g_ncu_full_summary.md + profiles/r2v_ncu_full_summary.md (dram__bytes_read.sum + dram__bytes_write.sum per launch; "
                       "rhs_combine = mean of the four fused stage launches of a step: 5.95 (first) + 2 x 9.79 (middle) + 6.36 (last) GB)")
 # fused periodic step (round 2); the stage-by-stage path of round 1 moved 6.58 / 2.15 / 3.73 / 5.27 GB
 NCU_TRAFFIC = {"rhs_combine": 7.97e9, "divergence": 2.15e9, "project": 3.73e9, "poisson": 5.29e9}
