@@ -542,6 +542,81 @@ class RKMethods:
         return runge_kutta_method(A, [Fraction(1, 4), 0, Fraction(3, 4)], [0, Fraction(2, 3), Fraction(2, 3)], 0, T)
 
 
+# The other literal explicit tableaus of src/time_steppers/RKMethods.jl (the families built by linear solves -- SSP104,
+# rSSPs2, rSSPs3 -- go through runge_kutta_method directly): name -> (A rows "a b; c d", b, c or None = row sums, r).
+_TABLEAUS = {
+    "DOPRI6": ("0 0 0 0 0 0; 1/5 0 0 0 0 0; 3/40 9/40 0 0 0 0; 44/45 -56/15 32/9 0 0 0; 19372/6561 -25360/2187 64448/6561 -212/729 0 0; 9017/3168 -355/33 46732/5247 49/176 -5103/18656 0",
+              "35/384 0 500/1113 125/192 -2187/6784 11/84", None, "0"),
+    "HEM3": ("0 0 0; 1/3 0 0; -1 2 0",
+            "0 3/4 1/4", None, "0"),
+    "HEM3BS": ("0 0 0; 1/2 0 0; -1 2 0",
+              "1/6 2/3 1/6", None, "0"),
+    "Heun33": ("0 0 0; 1/3 0 0; 0 2/3 0",
+              "1/4 0 3/4", None, "0"),
+    "MTE22": ("0 0; 2/3 0",
+             "1/4 3/4", None, "1/2"),
+    "Mid22": ("0 0; 1/2 0",
+             "0 1", None, "1/2"),
+    "NSSP21": ("0 0; 3/4 0",
+              "0 1", None, "0"),
+    "NSSP32": ("0 0 0; 1/3 0 0; 0 1 0",
+              "1/2 0 1/2", None, "0"),
+    "NSSP33": ("0 0 0; -4/9 0 0; 7/6 -1/2 0",
+              "1/4 0 3/4", None, "0"),
+    "NSSP53": ("0 0 0 0 0; 1/7 0 0 0 0; 0 3/16 0 0 0; 0 0 1/3 0 0; 0 0 0 2/3 0",
+              "1/4 0 0 0 3/4", None, "0"),
+    "RK33P2": ("0 0 0; 1/3 0 0; -1 2 0",
+              "0 3/4 1/4", None, "0"),
+    "RK44C2": ("0 0 0 0; 1/4 0 0 0; 0 1/2 0 0; 1 -2 2 0",
+              "1/6 0 2/3 1/6", None, "0"),
+    "RK44C23": ("0 0 0 0; 1/2 0 0 0; 1/4 1/4 0 0; 0 -1 2 0",
+               "1/6 0 2/3 1/6", None, "0"),
+    "RK44P2": ("0 0 0 0; 1 0 0 0; 3/8 1/8 0 0; -1/8 -3/8 3/2 0",
+              "1/6 -1/18 2/3 2/9", None, "0"),
+    "RK56": ("0 0 0 0 0 0; 1/4 0 0 0 0 0; 1/8 1/8 0 0 0 0; 0 0 1/2 0 0 0; 3/16 -3/8 3/8 9/16 0 0; -3/7 8/7 6/7 -12/7 8/7 0",
+            "7/90 0 16/45 2/15 16/45 7/90", None, "0"),
+    "SSP22": ("0 0; 1 0",
+             "1/2 1/2", None, "1"),
+    "SSP33": ("0 0 0; 1 0 0; 1/4 1/4 0",
+             "1/6 1/6 2/3", None, "1"),
+    "SSP42": ("0 0 0 0; 1/3 0 0 0; 1/3 1/3 0 0; 1/3 1/3 1/3 0",
+             "1/4 1/4 1/4 1/4", None, "3"),
+    "SSP43": ("0 0 0 0; 1/2 0 0 0; 1/2 1/2 0 0; 1/6 1/6 1/6 0",
+             "1/6 1/6 1/6 1/2", None, "2"),
+}
+
+
+def _rat(txt):
+    return [Fraction(v) for v in txt.split()]
+
+
+def _tableau_method(name):
+    def make(T=np.float64):
+        A, b, c, r = _TABLEAUS[name]
+        A = [_rat(row) for row in A.split(";")]
+        return runge_kutta_method(A, _rat(b), [sum(row) for row in A] if c is None else _rat(c), Fraction(r), T)
+
+    make.__name__ = name
+    make.__doc__ = f"RKMethods.{name} (src/time_steppers/RKMethods.jl)"
+    return staticmethod(make)
+
+
+for _name in _TABLEAUS:
+    setattr(RKMethods, _name, _tableau_method(_name))
+
+
+def _hem5(T=np.float64):
+    """RKMethods.HEM5 (Brasey and Hairer, 5 stages, 4th order): irrational entries, evaluated in Float64 first."""
+    q = np.sqrt(6.0)
+    A = [[0, 0, 0, 0, 0], [3 / 10, 0, 0, 0, 0], [(1 + q) / 30, (11 - 4 * q) / 30, 0, 0, 0],
+         [(-79 - 31 * q) / 150, (-1 - 4 * q) / 30, (24 + 11 * q) / 25, 0, 0],
+         [(14 + 5 * q) / 6, (-8 + 7 * q) / 6, (-9 - 7 * q) / 4, (9 - q) / 4, 0]]
+    return runge_kutta_method(A, [0, 0, (16 - q) / 36, (16 + q) / 36, 1 / 9], [sum(r) for r in A], 0, T)
+
+
+RKMethods.HEM5 = staticmethod(_hem5)
+
+
 class LMWray3:
     def __init__(self, T=np.float64):
         self.T = np.dtype(T).type
