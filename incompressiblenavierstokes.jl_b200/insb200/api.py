@@ -365,6 +365,19 @@ def apply_bc_temp_(temp, t, setup, plan=None):
     return temp
 
 
+def apply_bc_u(u, t, setup, dudt=False):
+    """apply_bc_u (src/boundary_conditions.jl:148-160): the allocating variant, the argument is left alone."""
+    return apply_bc_u_(u.clone(), t, setup, dudt)
+
+
+def apply_bc_p(p, t, setup):
+    return apply_bc_p_(p.clone(), t, setup)
+
+
+def apply_bc_temp(temp, t, setup):
+    return apply_bc_temp_(temp.clone(), t, setup)
+
+
 def divergence_(div, u, setup):
     check(lib().insb200_divergence(_base_plan(setup).h, _ptr(_chk(setup, div, False)), _ptr(_chk(setup, u, True)), _stream()))
     return div
@@ -377,6 +390,11 @@ def divergence(u, setup):
 def scalewithvolume_(p, setup):
     check(lib().insb200_scalewithvolume(_base_plan(setup).h, _ptr(_chk(setup, p, False)), _stream()))
     return p
+
+
+def scalewithvolume(p, setup):
+    """scalewithvolume (src/operators.jl:203-216): allocating variant."""
+    return scalewithvolume_(p.clone(), setup)
 
 
 def pressuregradient_(G, p, setup):
@@ -429,6 +447,29 @@ def boussinesq_(force, state, t, *, setup, cache=None, viscosity, conductivity, 
     return force
 
 
+def navierstokes(state, t, *, setup, viscosity):
+    """navierstokes (src/solver.jl:9-13), the allocating right-hand side: c = convection(u), d = diffusion(u), c + d
+    -- summed after the two operators, so it differs from navierstokes! by rounding like in the reference
+    (test/operators.jl:152-167); diffusion! adds into the convection result (0 + c is exact)."""
+    f = convection(state["u"], setup)
+    return {"u": diffusion_(f, state["u"], setup, viscosity)}
+
+
+def boussinesq(state, t, *, setup, viscosity, conductivity, gdir, gravity, dodissipation):
+    """boussinesq (src/solver.jl:38-48), allocating; evaluated by the fused right-hand side (insb200_rhs), i.e. with
+    the rounding of boussinesq! rather than of the operator-by-operator sum."""
+    force = {"u": torch.zeros_like(state["u"]), "temp": torch.zeros_like(state["temp"])}
+    return boussinesq_(force, state, t, setup=setup, viscosity=viscosity, conductivity=conductivity, gdir=gdir,
+                       gravity=gravity, dodissipation=dodissipation)
+
+
+def get_cache(obj, *args, **kwargs):
+    """get_cache (src/solver.jl:55-61, time_steppers/time_stepper_caches.jl:11-24): the built-in forces have none, and
+    the stage arrays of the time steppers are owned by the plan (allocated on first use), so there is nothing for the
+    caller to hold; accepted for signature parity."""
+    return None
+
+
 # ------------------------------------------------------------------------------------
 # pressure solvers (src/pressure.jl)
 # ------------------------------------------------------------------------------------
@@ -478,6 +519,11 @@ def default_psolver(setup):
 
 def poisson_(psolver, f):
     return psolver(f)
+
+
+def poisson(psolver, f):
+    """poisson (src/pressure.jl:16): poisson!(psolver, copy(f))."""
+    return psolver(f.clone())
 
 
 def project_(u, setup, *, psolver, p):
@@ -742,6 +788,14 @@ def timestep_(method, force, stepper, dt, *, params=None, ode_cache=None, force_
     return create_stepper(method, setup=setup, psolver=psolver, state=state, t=t + dt, n=stepper["n"] + 1)
 
 
+def timestep(method, force, stepper, dt, *, params=None):
+    """timestep (src/time_steppers/step.jl:17, step_explicit_runge_kutta.jl:59-101): the non-mutating variant -- the
+    state of `stepper` is left alone, the new stepper holds fresh arrays."""
+    fresh = dict(stepper)
+    fresh["state"] = {k: v.clone() for k, v in stepper["state"].items()}
+    return timestep_(method, force, fresh, dt, params=params)
+
+
 def propose_timestep(force, state, setup, params, plan=None):
     pr = _force_params(force, setup, params)
     out = C.c_double()
@@ -822,6 +876,33 @@ def total_kinetic_energy(u, setup, interpolate_first=False, plan=None):
     check(lib().insb200_total_kinetic_energy((plan or _base_plan(setup)).h, _ptr(_chk(setup, u, True)),
                                              int(interpolate_first), C.byref(out), _stream()))
     return setup.T(out.value)
+
+
+def spectral_stuff(setup, kmax=None):
+    """spectral_stuff (src/spectral.jl:39-67) on the host: kappa = 0..kmax, per shell the (0-based, first index
+    fastest) linear indices into the RFFT-sized array of the modes with kappa <= |k| < kappa + 1 (`inds`), the same
+    with the modes whose conjugate is not stored repeated (`energyinds`), and Nhat.  The library bins the shells inside
+    its own kernel (insb200_energy_spectrum); this is for callers that index spectra themselves."""
+    Np, D = setup.Np, setup.D
+    kmax = min(Np) // 2 if kmax is None else int(kmax)
+    Nhat = (Np[0] // 2 + 1,) + tuple(Np[1:])
+    k2 = (np.arange(Nhat[0]) ** 2).reshape((-1,) + (1,) * (D - 1))
+    for a in range(1, D):
+        ka = np.fft.fftfreq(Np[a], 1.0 / Np[a]).astype(np.int64)
+        shape = [1] * D
+        shape[a] = -1
+        k2 = k2 + (ka**2).reshape(shape)
+    k2 = k2.reshape(-1, order="F")
+    isort = np.argsort(k2, kind="stable")
+    k2s = k2[isort]
+    inds, energyinds = [], []
+    for kap in range(kmax + 1):
+        shell = isort[np.searchsorted(k2s, kap**2, "left"):np.searchsorted(k2s, (kap + 1) ** 2, "left")]
+        kx = shell % Nhat[0]
+        conj = shell[(kx > 0) & (kx < Nhat[0] - 1)]
+        inds.append(shell)
+        energyinds.append(np.concatenate([shell, conj]))
+    return dict(kappa=np.arange(kmax + 1), inds=inds, energyinds=energyinds, Nhat=Nhat)
 
 
 def energyspectrum(u, setup, psolver, kmax=None):
