@@ -258,3 +258,42 @@ def test_temperature_diffusion_of_a_parabola_is_exact_on_a_uniform_grid():
     ct = ops.convection_diffusion_temp_(O.scalarfield(setup), O.vectorfield(setup), temp, setup, 0.4)
     inner = (slice(2, -2),) * 3  # away from the periodic seam, where the parabola is not periodic
     np.testing.assert_allclose(ct[inner], 0.4 * 2 * q.sum(), rtol=1e-11)
+
+
+def test_momentum_operators_closed_forms_on_a_uniform_grid():
+    """convection! of a divergence-free linear field u = c + A x is -(u . grad) u = -A (c + A x) exactly (the face
+    interpolations are exact for linear fields, the flux differences are central differences of quadratics);
+    diffusion! of a quadratic field is nu * 2 sum(q) exactly; convectiondiffusion! is their sum up to rounding."""
+    rng = np.random.default_rng(5)
+    x = tuple(np.linspace(0.0, L, n + 1) for n, L in ((10, 1.0), (8, 2.0), (12, 1.5)))
+    b = (O.PeriodicBC(), O.PeriodicBC())
+    setup = O.Setup(x, dict(u=(b,) * 3))
+    A = rng.standard_normal((3, 3))
+    A -= np.trace(A) / 3 * np.eye(3)
+    c = rng.standard_normal(3)
+    u = _linear_u(setup, A, c)
+    conv = ops.convection_(O.vectorfield(setup), u, setup)
+    inner = (slice(2, -2),) * 3  # away from the periodic seam (a linear field is not periodic)
+    AA = A @ A
+    for i in range(3):
+        xs = []
+        for d in range(3):
+            shape = [1, 1, 1]
+            shape[d] = -1
+            xs.append(np.asarray(setup.xu[i][d], dtype=np.float64).reshape(shape))
+        want = -(A[i] @ c) - sum(AA[i, d] * xs[d] for d in range(3))
+        np.testing.assert_allclose(conv[inner + (i,)], np.broadcast_to(want, conv[..., i].shape)[inner], rtol=1e-10, atol=1e-11)
+    q = rng.standard_normal((3, 3))
+    uq = O.vectorfield(setup)
+    for i in range(3):
+        acc = 0
+        for d in range(3):
+            shape = [1, 1, 1]
+            shape[d] = -1
+            acc = acc + q[i, d] * np.asarray(setup.xu[i][d], dtype=np.float64).reshape(shape) ** 2
+        uq[..., i] = acc
+    diff = ops.diffusion_(O.vectorfield(setup), uq, setup, 0.3)
+    for i in range(3):
+        np.testing.assert_allclose(diff[inner + (i,)], 0.3 * 2 * q[i].sum(), rtol=1e-10)
+    both = ops.convectiondiffusion_(O.vectorfield(setup), u, setup, 0.3)  # diffusion of a linear field is zero
+    np.testing.assert_allclose(both[inner], conv[inner], rtol=1e-10, atol=1e-11)
