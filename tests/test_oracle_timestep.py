@@ -113,3 +113,39 @@ def test_cfl():
     h = 1 / 16
     assert dt <= h**2 / 1e-3 / 6 + 1e-15
     assert np.isclose(dt, min(h / np.max(np.abs(u[setup.inside])), h**2 / 1e-3 / 6))
+
+
+@pytest.mark.parametrize("name,order", [("FE11", 1), ("Heun33", 3), ("Wray3", 3), ("RK33C2", 3), ("RK44", 4), ("LMWray3", 3)])
+def test_observed_temporal_order_of_the_steppers(name, order):
+    """The projected Runge-Kutta steppers reach their classical order on a smooth periodic flow (time-independent
+    boundary data; Sanderse & Koren 2012): error against a fine-step solution, halving the step three times.  A random
+    solenoidal field is used -- for a single Taylor-Green mode the convective term is a gradient and only the linear
+    decay would be integrated."""
+    import json
+    import os
+    from fractions import Fraction
+
+    setup = periodic_setup(12, 2, L=2 * np.pi)
+    psolver = pressure.default_psolver(setup)
+    u0 = ini.random_field(setup, rng=np.random.default_rng(1), kpeak=2, totalenergy=0.5)
+    force = ts.make_navierstokes(setup, 0.05)
+    if name == "LMWray3":
+        method = ts.LMWray3()
+    elif hasattr(ts, name):
+        method = getattr(ts, name)()
+    else:  # from the reference's tableaus (tests/golden/rk_tableaus.json)
+        gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rk_tableaus.json")))[name]
+        fr = lambda v: float(Fraction(v))
+        method = ts.runge_kutta_method([[fr(v) for v in r] for r in gold["A"]], [fr(v) for v in gold["b"]],
+                                       [fr(v) for v in gold["c"]], fr(gold["r"]))
+
+    def run(nstep):
+        out = ts.solve_unsteady(setup, (0.0, 0.8), dict(u=u0.copy(order="F")), force, method=method, psolver=psolver,
+                                dt=0.8 / nstep)
+        return out["u"]
+
+    ref = run(256 if order > 1 else 4096)
+    errs = [rel_l2(run(n), ref) for n in (4, 8, 16)]
+    rates = [np.log2(errs[i] / errs[i + 1]) for i in range(2)]
+    assert errs[-1] < errs[0] and min(rates) > order - 0.2, (name, errs, rates)
+    assert max(rates) < order + 0.3, (name, errs, rates)
